@@ -1,0 +1,194 @@
+/* ramnet_b200.h — C ABI of libramnet_sm100a.so (B200 / sm_100a only).
+ *
+ * The drop-in boundary for the RAM-Net per-timestep hot path.
+ * The reference (uzh-rpg/rpg_ramnet) has no native code: every device op it
+ * issues is a stock ATen/cuDNN call made from Python.  Each entry point below
+ * therefore names the reference Python call site(s) whose device work it
+ * replaces.  The Python host side (rpg_ramnet_b200/) binds these with ctypes;
+ * INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch types, no C++ in the signatures;
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns all memory (inputs, outputs, workspaces); the library
+ *     never allocates on the hot path and never synchronises the host;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *     all work is enqueued on it, so every call is CUDA-graph capturable;
+ *   - return value: 0 on success, negative RAMNET_E* otherwise; the message
+ *     is available from ramnet_last_error() (thread-local, valid until the
+ *     next failing call on that thread);
+ *   - activations are fp32 NHWC ("pixel-major": [N, H, W, C], C contiguous);
+ *     network inputs are fp32 NCHW exactly as the reference feeds them.
+ */
+#ifndef RAMNET_B200_H
+#define RAMNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RAMNET_ABI_VERSION 1
+
+enum {
+    RAMNET_OK = 0,
+    RAMNET_EINVAL = -1,       /* bad argument / unsupported shape */
+    RAMNET_ECUDA = -2,        /* CUDA runtime / driver error */
+    RAMNET_EUNSUPPORTED = -3, /* valid request the library does not implement */
+    RAMNET_EDEVICE = -4       /* not an sm_100 device */
+};
+
+/* Arithmetic of the dense contraction (ramnet_conv_desc.mma_kind). */
+enum {
+    RAMNET_MMA_FP32 = 0, /* CUDA-core FFMA, fp32 exact: strict-parity mode */
+    RAMNET_MMA_TF32 = 1  /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM */
+};
+
+/* Fused epilogues of the implicit-GEMM convolution. `acc` is the fp32
+ * accumulator of GEMM column n (output channel) at output pixel m. */
+enum {
+    /* y0 = acc + b                                   (pred logits, generic) */
+    RAMNET_EPI_BIAS = 0,
+    /* y0 = relu(acc + b)        ConvLayer.forward, submodules.py:26-35       */
+    RAMNET_EPI_BIAS_RELU = 1,
+    /* y0 = relu(acc + b + aux0) ResidualBlock.forward tail, submodules.py:213-215 */
+    RAMNET_EPI_BIAS_RES_RELU = 2,
+    /* ConvGRU gates, submodules.py:446-448.  Cout = 2C, columns [0,C) are the
+     * reset gate, [C,2C) the update gate.  aux0 = h (prev state, C channels).
+     * y0 = u = sigmoid(acc_u + b_u)            [.., C]
+     * y1 = h * sigmoid(acc_r + b_r)            [.., C]                        */
+    RAMNET_EPI_GRU_RU = 3,
+    /* ConvGRU candidate + blend, submodules.py:449-452.  aux0 = h, aux1 = u.
+     * y0 = h*(1-u) + tanh(acc + b)*u                                          */
+    RAMNET_EPI_GRU_OUT = 4,
+    /* ConvLSTM, submodules.py:341-356.  Cout = 4C with columns interleaved at
+     * pack time: column 4c+g, g = 0 in, 1 remember, 2 out, 3 cell (the
+     * reference's chunk order, :344).  aux0 = c (prev cell).
+     * y1 = c' = s(f)c + s(i)tanh(g);  y0 = h' = s(o)tanh(c')                 */
+    RAMNET_EPI_LSTM = 5
+};
+
+enum {
+    RAMNET_FLAG_ROUND_TF32 = 1 /* round every stored output to TF32 (rna) so a
+                                  following kind::tf32 MMA truncates nothing */
+};
+
+/* One implicit-GEMM convolution:  y[m, n] = epi( sum_{tap,c} x[pix(m,tap), c] * w[tap, n, c] ).
+ * The K dimension is the virtual concatenation [x0 | x1] along channels
+ * (torch.cat(...,1) at submodules.py:340,445,449 without the copy).
+ * Zero padding of ksize/2, cross-correlation (nn.Conv2d semantics). */
+typedef struct ramnet_conv_desc {
+    int32_t N, H, W;   /* input batch / height / width */
+    int32_t C0, C1;    /* channels of x0, x1 (C1 = 0 when x1 is NULL) */
+    int32_t Cout;      /* GEMM N (2C for GRU_RU, 4C for LSTM) */
+    int32_t ksize;     /* 1, 3 or 5 */
+    int32_t stride;    /* 1 or 2; Ho = (H-1)/stride+1 */
+    int32_t epilogue;  /* RAMNET_EPI_* */
+    int32_t mma_kind;  /* RAMNET_MMA_* */
+    int32_t flags;     /* RAMNET_FLAG_* */
+    int32_t reserved;
+} ramnet_conv_desc;
+
+typedef struct ramnet_handle ramnet_handle;
+
+/* ---- library / handle ------------------------------------------------- */
+int ramnet_version(void);
+const char *ramnet_last_error(void);
+/* Binds to CUDA device `device` (must be sm_100); caches SM count, the
+ * cuTensorMapEncodeTiled entry point and per-kernel attributes. */
+int ramnet_create(int device, ramnet_handle **out);
+int ramnet_destroy(ramnet_handle *h);
+int ramnet_sm_count(const ramnet_handle *h);
+/* Kernels launched through this handle since creation (bench.py's gpu_launches). */
+int64_t ramnet_launch_count(const ramnet_handle *h);
+
+/* ---- a-1  events_to_voxel_grid ---------------------------------------- *
+ * Replaces utils/event_tensor_utils.py:71-117 (numpy) and :120-187 (torch
+ * index_add_ twin); live twin data_loader/dataset_asynchronous.py:253-298.
+ * events: [n,4] float64 rows [t, x, y, p] (not modified, unlike the
+ * reference).  grid: [bins, height, width] float32, zeroed by the callee.
+ * Index arithmetic is int64 and bit-exact with the reference; votes whose
+ * pixel falls outside the grid are dropped and counted in *oob_count
+ * (device int32, may be NULL; the reference raises IndexError / wraps). */
+int ramnet_voxel_grid(ramnet_handle *h, const double *events, int64_t n, int bins, int width,
+                      int height, float *grid, int32_t *oob_count, void *stream);
+/* Debug/parity twin: writes the un-accumulated vote stream instead of
+ * scattering it (idx = -1 for a dropped vote). Arrays of length n. */
+int ramnet_voxel_votes(ramnet_handle *h, const double *events, int64_t n, int bins, int width,
+                       int height, int64_t *idx_left, float *val_left, int64_t *idx_right,
+                       float *val_right, void *stream);
+
+/* ---- a-2  head convolution -------------------------------------------- *
+ * Replaces ConvLayer.forward for head_events / head_rgb / unet.head
+ * (statenet.py:139-145, unet.py:93-94): 5x5 s1 p2 conv + bias + ReLU on the
+ * raw NCHW network input with Cin <= 8; writes NHWC [N,H,W,Cout].  fp32 FFMA
+ * (HBM-bound: 12-54 FLOP/B).  w: [Cout, Cin, 5, 5] exactly as nn.Conv2d holds it. */
+int ramnet_head_conv(ramnet_handle *h, const float *x_nchw, const float *w_oihw, const float *bias,
+                     float *y_nhwc, int N, int Cin, int H, int W, int Cout, int flags, void *stream);
+
+/* ---- a-3..a-7  implicit-GEMM convolution with fused epilogue ----------- *
+ * Replaces nn.Conv2d + torch.cat + the pointwise gate kernels at
+ * submodules.py:27-33 (ConvLayer), :340-356 (ConvLSTM), :445-452 (ConvGRU),
+ * :202-215 (ResidualBlock), :89-95 (UpsampleConvLayer after upsample).
+ * w_packed: see ramnet_pack_weights.  bias: [Cout] (NULL = 0).
+ * workspace: ramnet_conv_workspace_bytes(desc) bytes (may be 0/NULL). */
+size_t ramnet_conv_workspace_bytes(const ramnet_conv_desc *d);
+int ramnet_conv_fwd(ramnet_handle *h, const ramnet_conv_desc *d, const float *x0, const float *x1,
+                    const float *w_packed, const float *bias, const float *aux0, const float *aux1,
+                    float *y0, float *y1, void *workspace, size_t workspace_bytes, void *stream);
+/* [Cout, Cin, k, k] fp32 (nn.Conv2d layout) -> the layout `mma_kind` consumes:
+ *   FP32: [k*k][Cin][Cout]           TF32: [k*k][Cout][Cin], values rounded to TF32 (rna).
+ * `lstm_interleave` != 0 permutes output channels to 4c+g (RAMNET_EPI_LSTM). */
+int ramnet_pack_weights(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin,
+                        int ksize, int mma_kind, int lstm_interleave, void *stream);
+
+/* ---- a-7  decoder prologue --------------------------------------------- *
+ * Replaces skip_sum (statenet.py:15-16,306-308) + f.interpolate(scale 2,
+ * bilinear, align_corners=False) (submodules.py:88).  NHWC in [N,H,W,C]
+ * (+ optional skip of the same shape) -> NHWC out [N,2H,2W,C]. */
+int ramnet_upsample2x_add(ramnet_handle *h, const float *x, const float *skip, float *y, int N,
+                          int H, int W, int C, int flags, void *stream);
+
+/* ---- a-8  prediction head ---------------------------------------------- *
+ * Replaces pred (1x1 conv, no activation, statenet.py:116-117) + torch.sigmoid
+ * (:313); `skip` (may be NULL) is unet.py:129's x + head.  x: NHWC [M, C];
+ * w: [C]; logits / depth: [M] (= [N,1,H,W]); either output may be NULL. */
+int ramnet_pred_sigmoid(ramnet_handle *h, const float *x, const float *skip, const float *w,
+                        const float *bias, float *logits, float *depth, int64_t M, int C, void *stream);
+
+/* ---- layout helpers ----------------------------------------------------- */
+int ramnet_nchw_to_nhwc(ramnet_handle *h, const float *x, float *y, int N, int C, int H, int W,
+                        int flags, void *stream);
+int ramnet_nhwc_to_nchw(ramnet_handle *h, const float *x, float *y, int N, int C, int H, int W,
+                        void *stream);
+int ramnet_round_tf32(ramnet_handle *h, const float *x, float *y, int64_t n, void *stream);
+
+/* ---- a-12  scale_invariant_loss ---------------------------------------- *
+ * Replaces model/loss.py:6-9 (boolean-mask gathers + host sync).
+ * stats[0..2] = sum(d), sum(d^2), count over non-NaN d = pred - target, in
+ * float64 (zeroed by the callee).  ramnet_si_loss_grad then writes
+ * grad[i] = scale * (2w/n)(d_i - lambda*mean(d)), 0 where d is NaN, reading n
+ * and mean from `stats` on the device (no host sync).  For data-parallel
+ * exact-loss mode all-reduce `stats` between the two calls. */
+int ramnet_si_loss_stats(ramnet_handle *h, const float *pred, const float *target, int64_t n,
+                         double *stats, void *stream);
+int ramnet_si_loss_value(ramnet_handle *h, const double *stats, float weight, float n_lambda,
+                         float *loss_out, void *stream);
+int ramnet_si_loss_grad(ramnet_handle *h, const float *pred, const float *target, int64_t n,
+                        const double *stats, float weight, float n_lambda, float scale, float *grad,
+                        void *stream);
+
+/* ---- a-14  Adam --------------------------------------------------------- *
+ * Replaces torch.optim.Adam.step (built at base/base_trainer.py:36-37,
+ * stepped at trainer/lstm_trainer.py:453) with one multi-tensor launch over a
+ * flat fp32 buffer.  step is 1-based; L2 weight decay as torch.optim.Adam. */
+int ramnet_adam_step(ramnet_handle *h, float *p, const float *g, float *m, float *v, int64_t n,
+                     float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                     void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAMNET_B200_H */

@@ -1,0 +1,102 @@
+"""ctypes binding of libramnet_sm100a.so (include/ramnet_b200.h).
+
+The CUDA library is the product; this module only loads it and converts error codes into
+exceptions.  There is deliberately no fallback: if the shared library is missing or the device is
+not sm_100 every op raises.
+"""
+import ctypes
+import os
+import threading
+from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p, POINTER
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libramnet_sm100a.so')
+
+MMA_FP32, MMA_TF32 = 0, 1
+EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RES_RELU, EPI_GRU_RU, EPI_GRU_OUT, EPI_LSTM = range(6)
+FLAG_ROUND_TF32 = 1
+
+
+class ConvDesc(ctypes.Structure):
+    """struct ramnet_conv_desc."""
+    _fields_ = [(n, c_int32) for n in ('N', 'H', 'W', 'C0', 'C1', 'Cout', 'ksize', 'stride', 'epilogue',
+                                       'mma_kind', 'flags', 'reserved')]
+
+
+# name -> (restype, argtypes); every symbol include/ramnet_b200.h declares
+SIGNATURES = {
+    'ramnet_version': (c_int, []),
+    'ramnet_last_error': (c_char_p, []),
+    'ramnet_create': (c_int, [c_int, POINTER(c_void_p)]),
+    'ramnet_destroy': (c_int, [c_void_p]),
+    'ramnet_sm_count': (c_int, [c_void_p]),
+    'ramnet_launch_count': (c_int64, [c_void_p]),
+    'ramnet_voxel_grid': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'ramnet_voxel_votes': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p]),
+    'ramnet_head_conv': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                 c_int, c_void_p]),
+    'ramnet_conv_workspace_bytes': (c_size_t, [POINTER(ConvDesc)]),
+    'ramnet_conv_fwd': (c_int, [c_void_p, POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ramnet_pack_weights': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'ramnet_upsample2x_add': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                      c_void_p]),
+    'ramnet_pred_sigmoid': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                    c_int, c_void_p]),
+    'ramnet_nchw_to_nhwc': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'ramnet_nhwc_to_nchw': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'ramnet_round_tf32': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    'ramnet_si_loss_stats': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    'ramnet_si_loss_value': (c_int, [c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p]),
+    'ramnet_si_loss_grad': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float, c_float,
+                                    c_void_p, c_void_p]),
+    'ramnet_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,
+                                 c_float, c_float, c_float, c_int, c_void_p]),
+}
+
+_lib = None
+_lock = threading.Lock()
+_handles = {}
+
+
+class RamnetError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen the library and declare every prototype (no CUDA call is made)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RamnetError(
+                    f'{LIB_PATH} is missing: build it with `python -m rpg_ramnet_b200.build` '
+                    '(nvcc, sm_100a). There is no CPU or PyTorch fallback for the hot path.')
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype, fn.argtypes = res, args
+            _lib = lib
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise RamnetError(f'libramnet error {rc}: {load().ramnet_last_error().decode()}')
+
+
+def handle(device_index: int) -> c_void_p:
+    """One ramnet_handle per CUDA device per process."""
+    lib = load()
+    with _lock:
+        h = _handles.get(device_index)
+        if h is None:
+            h = c_void_p()
+            check(lib.ramnet_create(int(device_index), ctypes.byref(h)))
+            _handles[device_index] = h
+    return h
+
+
+def launch_count(device_index: int) -> int:
+    return int(load().ramnet_launch_count(handle(device_index)))

@@ -1,0 +1,138 @@
+// Shared device/host helpers for libramnet_sm100a.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/ramnet_b200.h"
+
+struct ramnet_handle {
+    int device;
+    int sm_count;
+    int64_t launches;
+    void *encode_tiled;  // PFN_cuTensorMapEncodeTiled, resolved at create
+};
+
+// ---- error plumbing (api.cu) ------------------------------------------------
+int ramnet_set_error(int code, const char *fmt, ...);
+#define RAMNET_CHECK_ARG(cond, ...)                                      \
+    do {                                                                  \
+        if (!(cond)) return ramnet_set_error(RAMNET_EINVAL, __VA_ARGS__); \
+    } while (0)
+#define RAMNET_CUDA(expr)                                                                    \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return ramnet_set_error(RAMNET_ECUDA, "%s failed: %s (%s:%d)", #expr,            \
+                                    cudaGetErrorString(e__), __FILE__, __LINE__);            \
+    } while (0)
+#define RAMNET_LAUNCH_CHECK(h)                                                               \
+    do {                                                                                     \
+        cudaError_t e__ = cudaGetLastError();                                                \
+        if (e__ != cudaSuccess)                                                              \
+            return ramnet_set_error(RAMNET_ECUDA, "kernel launch failed: %s (%s:%d)",        \
+                                    cudaGetErrorString(e__), __FILE__, __LINE__);            \
+        (h)->launches++;                                                                     \
+    } while (0)
+
+// ---- device math --------------------------------------------------------------
+// Accurate (not --use_fast_math) transcendental forms: parity with torch.sigmoid / tanh
+// to ~1 ulp matters more here than the handful of SFU cycles.
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// ---- fused epilogue -------------------------------------------------------------
+struct EpiParams {
+    const float *bias;  // [Cout] or nullptr
+    const float *aux0;  // residual / h / c_prev
+    const float *aux1;  // u
+    float *y0;
+    float *y1;
+    int Cout;   // GEMM N
+    int flags;  // RAMNET_FLAG_*
+};
+
+// Stores NV consecutive GEMM columns [n0, n0+NV) of output pixel m.  NV is a multiple of 4,
+// n0 a multiple of NV, so every access below is a 16-byte vector access.
+template <int EPI, int NV>
+__device__ __forceinline__ void epilogue_store(const EpiParams &p, int64_t m, int n0, float (&v)[NV]) {
+    static_assert(NV % 4 == 0, "NV must be a multiple of 4");
+    if (p.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < NV; j += 4) {
+            float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
+    }
+    const bool rnd = (p.flags & RAMNET_FLAG_ROUND_TF32) != 0;
+    auto st4 = [&](float *dst, float a, float b, float c, float d) {
+        if (rnd) { a = round_tf32(a); b = round_tf32(b); c = round_tf32(c); d = round_tf32(d); }
+        *reinterpret_cast<float4 *>(dst) = make_float4(a, b, c, d);
+    };
+    if constexpr (EPI == RAMNET_EPI_BIAS) {
+#pragma unroll
+        for (int j = 0; j < NV; j += 4) st4(p.y0 + m * p.Cout + n0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else if constexpr (EPI == RAMNET_EPI_BIAS_RELU) {
+#pragma unroll
+        for (int j = 0; j < NV; j += 4)
+            st4(p.y0 + m * p.Cout + n0 + j, fmaxf(v[j], 0.f), fmaxf(v[j + 1], 0.f), fmaxf(v[j + 2], 0.f),
+                fmaxf(v[j + 3], 0.f));
+    } else if constexpr (EPI == RAMNET_EPI_BIAS_RES_RELU) {
+#pragma unroll
+        for (int j = 0; j < NV; j += 4) {
+            float4 r = *reinterpret_cast<const float4 *>(p.aux0 + m * p.Cout + n0 + j);
+            st4(p.y0 + m * p.Cout + n0 + j, fmaxf(v[j] + r.x, 0.f), fmaxf(v[j + 1] + r.y, 0.f),
+                fmaxf(v[j + 2] + r.z, 0.f), fmaxf(v[j + 3] + r.w, 0.f));
+        }
+    } else if constexpr (EPI == RAMNET_EPI_GRU_RU) {
+        const int C = p.Cout >> 1;
+        if (n0 < C) {  // reset gate -> y1 = h * r
+#pragma unroll
+            for (int j = 0; j < NV; j += 4) {
+                float4 h = *reinterpret_cast<const float4 *>(p.aux0 + m * C + n0 + j);
+                st4(p.y1 + m * C + n0 + j, h.x * sigmoidf_(v[j]), h.y * sigmoidf_(v[j + 1]),
+                    h.z * sigmoidf_(v[j + 2]), h.w * sigmoidf_(v[j + 3]));
+            }
+        } else {  // update gate -> y0 = u   (kept full fp32: it is a pointwise operand only)
+#pragma unroll
+            for (int j = 0; j < NV; j += 4)
+                *reinterpret_cast<float4 *>(p.y0 + m * C + (n0 - C) + j) =
+                    make_float4(sigmoidf_(v[j]), sigmoidf_(v[j + 1]), sigmoidf_(v[j + 2]), sigmoidf_(v[j + 3]));
+        }
+    } else if constexpr (EPI == RAMNET_EPI_GRU_OUT) {
+#pragma unroll
+        for (int j = 0; j < NV; j += 4) {
+            float4 h = *reinterpret_cast<const float4 *>(p.aux0 + m * p.Cout + n0 + j);
+            float4 u = *reinterpret_cast<const float4 *>(p.aux1 + m * p.Cout + n0 + j);
+            st4(p.y0 + m * p.Cout + n0 + j, h.x * (1.f - u.x) + tanhf(v[j]) * u.x,
+                h.y * (1.f - u.y) + tanhf(v[j + 1]) * u.y, h.z * (1.f - u.z) + tanhf(v[j + 2]) * u.z,
+                h.w * (1.f - u.w) + tanhf(v[j + 3]) * u.w);
+        }
+    } else if constexpr (EPI == RAMNET_EPI_LSTM) {
+        const int C = p.Cout >> 2;
+        float hn[NV / 4], cn[NV / 4];
+#pragma unroll
+        for (int q = 0; q < NV / 4; ++q) {
+            const float cp = p.aux0[m * C + (n0 >> 2) + q];
+            const float gi = sigmoidf_(v[4 * q]), gf = sigmoidf_(v[4 * q + 1]);
+            const float go = sigmoidf_(v[4 * q + 2]), gc = tanhf(v[4 * q + 3]);
+            cn[q] = gf * cp + gi * gc;
+            hn[q] = go * tanhf(cn[q]);
+            if (rnd) hn[q] = round_tf32(hn[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < NV / 4; ++q) {
+            p.y0[m * C + (n0 >> 2) + q] = hn[q];
+            p.y1[m * C + (n0 >> 2) + q] = cn[q];
+        }
+    }
+}
+
+static inline int conv_out_dim(int in, int stride) { return (in - 1) / stride + 1; }
+static inline int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }

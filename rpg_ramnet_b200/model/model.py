@@ -1,0 +1,122 @@
+"""ERGB2Depth / ERGB2DepthRecurrent — the drop-in boundary (mirrors RAM_Net/model/model.py:12-219).
+
+Same constructor (`config` dict with the reference's keys), same
+`forward(item, prev_super_states, prev_states_lstm) -> (predictions, super_states, states_lstm)`
+contract, same schedule (K event passes then one image pass, a decoder pass after each,
+model.py:161-217), so `trainer/lstm_trainer.py:270-272` and `test.py:230-232` can call it
+unchanged.  One extra, optional config key: `mma_kind` ('tf32' default | 'fp32').
+"""
+import torch
+
+from ..base import BaseModel
+from .. import ops
+from .._lib import RamnetError
+from .statenet import StateNetPhasedRecurrent
+from .unet import UNet
+
+
+class BaseERGB2Depth(BaseModel):
+    """Config parsing of model.py:12-77, key for key (defaults included)."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        assert 'num_bins_rgb' in config
+        assert 'num_bins_events' in config
+        self.num_bins_rgb = int(config['num_bins_rgb'])
+        self.num_bins_events = int(config['num_bins_events'])
+        self.skip_type = str(config.get('skip_type', 'sum'))
+        self.state_combination = str(config.get('state_combination', 'sum'))
+        self.num_encoders = int(config.get('num_encoders', 4))
+        self.base_num_channels = int(config.get('base_num_channels', 32))
+        self.num_residual_blocks = int(config.get('num_residual_blocks', 2))
+        self.recurrent_block_type = str(config.get('recurrent_block_type', 'convlstm'))
+        self.norm = str(config['norm']) if 'norm' in config else None
+        self.use_upsample_conv = bool(config.get('use_upsample_conv', True))
+        self.every_x_rgb_frame = config.get('every_x_rgb_frame', 1)
+        self.baseline = config.get('baseline', False)
+        self.loss_composition = config.get('loss_composition', False)
+        self.kernel_size = int(config.get('kernel_size', 5))
+        self.mma_kind = config.get('mma_kind', None)
+        self.gpu = torch.device('cuda:' + str(config['gpu']))
+
+    def _grad_guard(self):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise RamnetError('autograd through the CUDA graph is not wired yet: call under torch.no_grad() '
+                              '(inference) — the training path is SURVEY.md §8 rows a-13/a-14')
+
+
+class ERGB2Depth(BaseERGB2Depth):
+    """model.py:79-111: non-recurrent UNet on item['image']."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.unet = UNet(num_input_channels=self.num_bins_rgb, num_output_channels=1, skip_type=self.skip_type,
+                         activation='sigmoid', num_encoders=self.num_encoders,
+                         base_num_channels=self.base_num_channels, num_residual_blocks=self.num_residual_blocks,
+                         norm=self.norm, use_upsample_conv=self.use_upsample_conv, mma_kind=self.mma_kind)
+
+    def forward(self, item, prev_super_states, prev_states_lstm):
+        self._grad_guard()
+        x = item['image'].to(self.gpu, non_blocking=True)
+        return {'image': self.unet(x)}, {'image': None}, prev_states_lstm
+
+
+class ERGB2DepthRecurrent(BaseERGB2Depth):
+    """model.py:114-219."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.statenetphasedrecurrent = StateNetPhasedRecurrent(
+            num_input_channels_rgb=self.num_bins_rgb, num_input_channels_events=self.num_bins_events,
+            num_output_channels=1, skip_type=self.skip_type, state_combination=self.state_combination,
+            activation='sigmoid', num_encoders=self.num_encoders, base_num_channels=self.base_num_channels,
+            num_residual_blocks=self.num_residual_blocks, norm=self.norm, use_upsample_conv=self.use_upsample_conv,
+            recurrent_block_type=self.recurrent_block_type, baseline=self.baseline, mma_kind=self.mma_kind)
+        self.max_num_channels = self.base_num_channels * pow(2, self.num_encoders)
+
+    def _zero_states(self, B, H, W):
+        """model.py:146-159, allocated on the device directly (the reference builds them on the host
+        and copies)."""
+        pair = (not bool(self.baseline)) and self.state_combination == 'convlstm'
+        states = []
+        for i in range(self.num_encoders):
+            h, w = int(H / pow(2, i + 1)), int(W / pow(2, i + 1))
+            c = int(self.base_num_channels * pow(2, i + 1))
+            if pair:
+                states.append([ops.zeros_nhwc(B, c, h, w, self.gpu), ops.zeros_nhwc(B, c, h, w, self.gpu)])
+            else:
+                states.append(ops.zeros_nhwc(B, c, h, w, self.gpu))
+        return states
+
+    def forward(self, item, prev_super_states, prev_states_lstm):
+        self._grad_guard()
+        net = self.statenetphasedrecurrent
+        predictions, super_states, states_lstm = {}, {}, {}
+        if prev_super_states is None:
+            B, _, H, W = item['image'].shape
+            prev_super_states = self._zero_states(B, H, W)
+        bl, K = self.baseline, self.every_x_rgb_frame
+        events_through_image_encoder = bl == 'ergb0' or (bl == 'e' and self.loss_composition == 'image')
+        last = None
+        if (not bool(bl)) or events_through_image_encoder:
+            if events_through_image_encoder:      # model.py:165-168
+                n_event_passes, last = K - 1, prev_states_lstm['image']
+            else:                                  # model.py:170-172
+                n_event_passes, last = K, prev_states_lstm['events{}'.format(K - 1)]
+            for k in range(n_event_passes):
+                key = 'events{}'.format(k)
+                x = item[key].to(self.gpu, non_blocking=True)
+                if bl == 'ergb0' or bl == 'e':
+                    s, l = net.forward_images(x, prev_super_states, last, None)
+                else:
+                    s, l = net.forward_events(x, prev_super_states, last, None)
+                predictions[key] = net.forward_decoder(s)
+                super_states[key], states_lstm[key] = s, l
+                prev_super_states, last = s, l
+        x = item['image'].to(self.gpu, non_blocking=True)
+        if (not bool(bl)) or bl == 'rgb' or (bl == 'e' and self.loss_composition != 'image'):
+            last = prev_states_lstm['image']       # model.py:203-208
+        s, l = net.forward_images(x, prev_super_states, last, None)
+        predictions['image'] = net.forward_decoder(s)
+        super_states['image'], states_lstm['image'] = s, l
+        return predictions, super_states, states_lstm

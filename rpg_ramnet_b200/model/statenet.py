@@ -1,0 +1,240 @@
+"""StateNetPhasedRecurrent — the RAM-Net graph (mirrors RAM_Net/model/statenet.py:120-315).
+
+Same constructor signature, child-module names/order (=> identical seeded init and state_dict keys)
+and the same three entry points `forward_events`, `forward_images`, `forward_decoder` with the
+same argument and return structure.  The arithmetic is the fused CUDA graph of
+rpg_ramnet_b200/engine.py; activations and states are fp32 NHWC-strided [N,C,H,W] tensors.
+"""
+import torch
+import torch.nn as nn
+
+from .. import engine as E
+from .. import ops
+from .._lib import RamnetError
+from .submodules import (ConvLayer, Recurrent2ConvLayer, RecurrentConvLayer, ResidualBlock, TransposedConvLayer,
+                         UpsampleConvLayer)
+
+
+class BaseStateNet(nn.Module):
+    """statenet.py:39-117 (argument validation + the shared tail builders)."""
+
+    def __init__(self, num_input_channels_rgb, num_input_channels_events, num_output_channels=1, skip_type='sum',
+                 state_combination='sum', activation='sigmoid', num_encoders=4, base_num_channels=32,
+                 num_residual_blocks=2, norm=None, use_upsample_conv=True, recurrent_block_type='convlstm',
+                 baseline=False):
+        super().__init__()
+        if skip_type not in ('sum', 'concat', 'no_skip', None):
+            raise KeyError('Could not identify skip_type, please add "skip_type": "sum", "concat" or "no_skip" '
+                           'to config["model"]')
+        if state_combination not in ('sum', 'conv', 'convlstm', 'convgru'):
+            raise KeyError('Could not identify state_combination, please add "state_combination": "sum", "conv", '
+                           '"convlstm" or "convgru" to config["model"]')
+        assert num_input_channels_rgb > 0 or num_input_channels_events > 0
+        assert num_output_channels > 0
+        self.num_input_channels_rgb = num_input_channels_rgb
+        self.num_input_channels_events = num_input_channels_events
+        self.num_output_channels = num_output_channels
+        self.skip_type = skip_type
+        self.state_combination = state_combination
+        self.recurrent_block_type = recurrent_block_type
+        self.activation_name = activation
+        self.norm = norm
+        self.baseline = baseline
+        self.use_upsample_conv = use_upsample_conv
+        print('Using UpsampleConvLayer (slow, but no checkerboard artefacts)' if use_upsample_conv else
+              'Using TransposedConvLayer (fast, with checkerboard artefacts)')
+        self.UpsampleLayer = UpsampleConvLayer if use_upsample_conv else TransposedConvLayer
+        self.num_encoders = num_encoders
+        self.base_num_channels = base_num_channels
+        self.num_residual_blocks = num_residual_blocks
+        self.max_num_channels = base_num_channels * pow(2, num_encoders)
+        self.encoder_input_sizes = [base_num_channels * pow(2, i) for i in range(num_encoders)]
+        self.encoder_output_sizes = [base_num_channels * pow(2, i + 1) for i in range(num_encoders)]
+
+    def build_resblocks(self):
+        self.resblocks = nn.ModuleList(
+            ResidualBlock(self.max_num_channels, self.max_num_channels, norm=self.norm)
+            for _ in range(self.num_residual_blocks))
+
+    def build_decoders(self):
+        self.decoders = nn.ModuleList()
+        for c in reversed(self.encoder_output_sizes):
+            self.decoders.append(self.UpsampleLayer(c if self.skip_type == 'sum' else 2 * c, c // 2,
+                                                    kernel_size=5, padding=2, norm=self.norm))
+
+    def build_prediction_layer(self):
+        self.pred = ConvLayer(self.base_num_channels if self.skip_type == 'sum' else 2 * self.base_num_channels,
+                              self.num_output_channels, 1, activation=None, norm=self.norm)
+
+
+class StateNetPhasedRecurrent(BaseStateNet):
+    def __init__(self, num_input_channels_rgb, num_input_channels_events, num_output_channels=1, skip_type='sum',
+                 state_combination='sum', activation='sigmoid', num_encoders=4, base_num_channels=32,
+                 num_residual_blocks=2, norm=None, use_upsample_conv=True, recurrent_block_type='convlstm',
+                 baseline=False, mma_kind=None):
+        super().__init__(num_input_channels_rgb, num_input_channels_events, num_output_channels, skip_type,
+                         state_combination, activation, num_encoders, base_num_channels, num_residual_blocks, norm,
+                         use_upsample_conv, recurrent_block_type, baseline)
+        has_events = not bool(baseline)
+        stateful = state_combination in ('convlstm', 'conv', 'convgru')
+        # registration order == reference (statenet.py:139-155): head_rgb, encoders_rgb, head_events,
+        # encoders_events, state_combination_events, state_combination_images
+        self.head_rgb = ConvLayer(num_input_channels_rgb, base_num_channels, kernel_size=5, stride=1, padding=2)
+        self.encoders_rgb = nn.ModuleList()
+        if has_events:
+            self.head_events = ConvLayer(num_input_channels_events, base_num_channels, kernel_size=5, stride=1,
+                                         padding=2)
+            self.encoders_events = nn.ModuleList()
+        if stateful:
+            if has_events:
+                self.state_combination_events = nn.ModuleList()
+            self.state_combination_images = nn.ModuleList()
+        else:
+            self.state_combination_events, self.state_combination_images = [], []
+
+        def encoder(cin, cout):
+            if recurrent_block_type == 'convlstm':
+                return Recurrent2ConvLayer(cin, cout, kernel_size=5, stride=2, padding=2, norm=norm,
+                                           recurrent_block_type=recurrent_block_type)
+            if recurrent_block_type == 'conv':
+                return ConvLayer(cin, cout, kernel_size=5, stride=2, padding=2, norm=norm)
+            return None
+
+        def combiner(cout):
+            if state_combination in ('convlstm', 'convgru'):
+                return RecurrentConvLayer(cout, cout, kernel_size=5, stride=1, padding=2, norm=norm,
+                                          recurrent_block_type=state_combination)
+            if state_combination == 'conv':
+                return ConvLayer(cout * 2, cout, kernel_size=5, stride=1, padding=2, norm=norm)
+            return None
+
+        # per level: encoder_rgb, encoder_events, comb_events, comb_images (statenet.py:157-198)
+        for cin, cout in zip(self.encoder_input_sizes, self.encoder_output_sizes):
+            e = encoder(cin, cout)
+            if e is not None:
+                self.encoders_rgb.append(e)
+            if has_events:
+                e = encoder(cin, cout)
+                if e is not None:
+                    self.encoders_events.append(e)
+            if has_events:
+                self.state_combination_events.append(combiner(cout))
+            self.state_combination_images.append(combiner(cout))
+
+        self.build_resblocks()
+        self.build_decoders()
+        self.build_prediction_layer()
+        self._mma_kind_name = mma_kind
+        self._wcache = E.WeightCache()
+
+    # ---- configuration the CUDA graph supports ------------------------------------------------
+    def _kind(self):
+        return E.resolve_mma_kind(self._mma_kind_name)
+
+    def _check_supported(self):
+        if self.state_combination in ('sum', 'conv'):
+            # statenet.py:231 / :272 tuple-unpack the single tensor state_sum/state_conv return:
+            # ill-formed upstream (works only by accident for batch size 2)
+            raise RamnetError(f"state_combination={self.state_combination!r} is ill-formed in the reference "
+                              "(statenet.py:231 unpacks one tensor into two); use 'convgru' or 'convlstm'")
+        if self.recurrent_block_type not in ('conv', 'convlstm'):
+            raise RamnetError(f'recurrent_block_type={self.recurrent_block_type!r} is not supported')
+        if self.skip_type != 'sum':
+            # skip_type='concat' crashes in the reference StateNet too (decoder 0 gets no skip, :302-303)
+            raise RamnetError("only skip_type='sum' is well-formed for StateNetPhasedRecurrent")
+        if self.activation_name != 'sigmoid':
+            raise RamnetError('only the sigmoid output activation is implemented')
+        if self.num_output_channels != 1:
+            raise RamnetError('only num_output_channels=1 is implemented')
+
+    # ---- encoders -----------------------------------------------------------------------------
+    def _encode(self, which, x, prev_super_state, prev_states_lstm):
+        self._check_supported()
+        kind = self._kind()
+        tf32 = kind == ops.MMA_TF32
+        cache, n = self._wcache, self.num_encoders
+        head = self.head_events if which == 'events' else self.head_rgb
+        encoders = self.encoders_events if which == 'events' else self.encoders_rgb
+        combs = self.state_combination_events if which == 'events' else self.state_combination_images
+        baseline_path = bool(self.baseline) and which == 'images'
+        if x.dim() != 4 or x.shape[2] % (1 << n) or x.shape[3] % (1 << n):
+            raise RamnetError(f'input {tuple(x.shape)}: H and W must be divisible by 2**num_encoders = {1 << n} '
+                              '(the reference fails on such shapes too, SURVEY Appendix A)')
+        hp = E.pack_head(cache, which + '/head', head.conv2d)
+        x = ops.head_conv(x.float(), hp.w, hp.b, round_tf32=tf32)
+        if prev_states_lstm is None:
+            prev_states_lstm = {'encoders': [None] * n, 'state_comb': [None] * n}
+        super_states, states_lstm = [], {'encoders': [], 'state_comb': []}
+        for i in range(n):
+            enc = encoders[i]
+            if self.recurrent_block_type == 'conv':
+                p = E.pack_conv(cache, f'{which}/enc{i}', enc.conv2d, kind, getattr(enc, 'norm_layer', None),
+                                enc.norm, self.training)
+                x = E.run_conv(x, p, ops.EPI_BIAS_RELU, kind, round_out=True)
+                enc_state = None
+            else:
+                p = E.pack_conv(cache, f'{which}/enc{i}', enc.conv.conv2d, kind,
+                                getattr(enc.conv, 'norm_layer', None), enc.conv.norm, self.training)
+                x = E.run_conv(x, p, ops.EPI_BIAS_RELU, kind, round_out=True)
+                lp = E.pack_lstm(cache, f'{which}/enc{i}/lstm', enc.recurrent_block, kind)
+                enc_state = E.run_lstm(x, prev_states_lstm['encoders'][i], lp, kind)
+                x = enc_state[0]
+            blk = combs[i].recurrent_block
+            if self.state_combination == 'convlstm' and not baseline_path:
+                lp = E.pack_lstm(cache, f'{which}/comb{i}', blk, kind)
+                st = E.run_lstm(x, prev_super_state[i], lp, kind)          # state = previous super state [h, c]
+                super_state = comb_state = st
+            elif self.state_combination == 'convgru':
+                ru, out = E.pack_gru(cache, f'{which}/comb{i}', blk, kind)
+                hprev = None if prev_super_state[i] is None else ops.as_nhwc(prev_super_state[i])
+                hnew = E.run_gru(x, hprev, ru, out, kind)
+                super_state = comb_state = hnew
+                if baseline_path:
+                    x = hnew
+            else:  # baseline + convlstm: private LSTM state, recurrent output feeds the next encoder
+                lp = E.pack_lstm(cache, f'{which}/comb{i}', blk, kind)
+                st = E.run_lstm(x, prev_states_lstm['state_comb'][i], lp, kind)
+                x, super_state, comb_state = st[0], st[0], st
+            super_states.append(super_state)
+            states_lstm['encoders'].append(enc_state)
+            states_lstm['state_comb'].append(comb_state)
+        return super_states, states_lstm
+
+    def forward_events(self, x, prev_super_state, prev_states_lstm, times=None):
+        """statenet.py:204-239."""
+        if bool(self.baseline):
+            raise RamnetError('baseline models have no event encoder (statenet.py:143-147)')
+        return self._encode('events', x, prev_super_state, prev_states_lstm)
+
+    def forward_images(self, x, prev_super_state, prev_states_lstm, times=None):
+        """statenet.py:241-288."""
+        return self._encode('images', x, prev_super_state, prev_states_lstm)
+
+    # ---- decoder ------------------------------------------------------------------------------
+    def forward_decoder(self, super_states, return_logits=False):
+        """statenet.py:290-315: resblocks(S[-1]) -> dec0(x) -> dec_i(x + S[n-i-1]) -> pred -> sigmoid."""
+        self._check_supported()
+        kind = self._kind()
+        cache, n = self._wcache, self.num_encoders
+        tup = (not bool(self.baseline)) and self.state_combination == 'convlstm'
+        pick = (lambda s: s[0]) if tup else (lambda s: s)
+        x = ops.as_nhwc(pick(super_states[-1]))
+        for i, rb in enumerate(self.resblocks):
+            if rb.norm == 'IN':
+                raise RamnetError("norm='IN' inside ResidualBlock uses per-instance statistics; not implemented")
+            p1 = E.pack_conv(cache, f'res{i}/1', rb.conv1, kind, getattr(rb, 'bn1', None), rb.norm, self.training)
+            p2 = E.pack_conv(cache, f'res{i}/2', rb.conv2, kind, getattr(rb, 'bn2', None), rb.norm, self.training)
+            y = E.run_conv(x, p1, ops.EPI_BIAS_RELU, kind, round_out=True)
+            x = E.run_conv(y, p2, ops.EPI_BIAS_RES_RELU, kind, aux0=x, round_out=True)
+        if not self.use_upsample_conv:
+            raise RamnetError('use_upsample_conv=False (TransposedConvLayer) is not implemented yet')
+        for i, dec in enumerate(self.decoders):
+            skip = None if i == 0 else ops.as_nhwc(pick(super_states[n - i - 1]))
+            up = ops.upsample2x_add(x, skip, round_tf32=(kind == ops.MMA_TF32))
+            p = E.pack_conv(cache, f'dec{i}', dec.conv2d, kind, getattr(dec, 'norm_layer', None), dec.norm,
+                            self.training)
+            x = E.run_conv(up, p, ops.EPI_BIAS_RELU, kind)
+        pr = self.pred
+        w, b = pr.conv2d.weight.detach().float(), None if pr.conv2d.bias is None else pr.conv2d.bias.detach().float()
+        w, b = E._fold_norm(w, b, getattr(pr, 'norm_layer', None), pr.norm, self.training)
+        return ops.pred_sigmoid(x, None, w, b, want_logits=return_logits)

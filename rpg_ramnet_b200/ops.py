@@ -1,0 +1,214 @@
+"""Tensor-level wrappers over the C ABI (pointers + sizes in, nothing allocated by the library).
+
+Activations are fp32 "pixel-major" tensors: logical shape [N, C, H, W] with channels_last
+strides, i.e. the memory is NHWC as include/ramnet_b200.h specifies.  PyTorch is used for device
+memory and streams only.
+"""
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (ConvDesc, EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RES_RELU, EPI_GRU_OUT, EPI_GRU_RU, EPI_LSTM,  # noqa
+                   FLAG_ROUND_TF32, MMA_FP32, MMA_TF32, check)
+
+
+def _stream(t: torch.Tensor):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _h(t: torch.Tensor):
+    if not t.is_cuda:
+        raise _lib.RamnetError('rpg_ramnet_b200 ops need CUDA tensors (sm_100a); there is no CPU path')
+    return _lib.handle(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def empty_nhwc(N, C, H, W, device) -> torch.Tensor:
+    """fp32 activation: logical [N,C,H,W], NHWC memory."""
+    return torch.empty((N, H, W, C), dtype=torch.float32, device=device).permute(0, 3, 1, 2)
+
+
+def zeros_nhwc(N, C, H, W, device) -> torch.Tensor:
+    return torch.zeros((N, H, W, C), dtype=torch.float32, device=device).permute(0, 3, 1, 2)
+
+
+def as_nhwc(t: torch.Tensor) -> torch.Tensor:
+    """Accept a foreign [N,C,H,W] tensor (e.g. a state handed back by the caller) and make sure its
+    memory is NHWC fp32.  No copy when it already is."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    N, C, H, W = t.shape
+    if t.stride() == (H * W * C, 1, W * C, C):
+        return t
+    out = empty_nhwc(N, C, H, W, t.device)
+    if t.is_contiguous():
+        lib = _lib.load()
+        check(lib.ramnet_nchw_to_nhwc(_h(t), _p(t), _p(out), N, C, H, W, 0, _stream(t)))
+    else:
+        out.copy_(t)
+    return out
+
+
+def to_nchw_contiguous(t: torch.Tensor) -> torch.Tensor:
+    N, C, H, W = t.shape
+    out = torch.empty((N, C, H, W), dtype=torch.float32, device=t.device)
+    check(_lib.load().ramnet_nhwc_to_nchw(_h(t), _p(t), _p(out), N, C, H, W, _stream(t)))
+    return out
+
+
+def _check_nhwc(t: torch.Tensor, name: str):
+    N, C, H, W = t.shape
+    if t.dtype != torch.float32 or t.stride() != (H * W * C, 1, W * C, C):
+        raise _lib.RamnetError(f'{name}: expected fp32 NHWC-strided [N,C,H,W] tensor, got {t.dtype} '
+                               f'shape {tuple(t.shape)} strides {t.stride()}')
+
+
+def voxel_grid(events: torch.Tensor, num_bins: int, width: int, height: int,
+               oob_count: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """events: [n,4] float64 CUDA rows [t,x,y,p] -> [num_bins, height, width] fp32."""
+    if events.dtype != torch.float64 or events.dim() != 2 or events.shape[1] != 4 or not events.is_contiguous():
+        raise _lib.RamnetError('voxel_grid: events must be a contiguous [n,4] float64 tensor')
+    grid = torch.empty((num_bins, height, width), dtype=torch.float32, device=events.device)
+    check(_lib.load().ramnet_voxel_grid(_h(events), _p(events), events.shape[0], num_bins, width, height, _p(grid),
+                                        _p(oob_count), _stream(events)))
+    return grid
+
+
+def voxel_votes(events: torch.Tensor, num_bins: int, width: int, height: int):
+    n = events.shape[0]
+    dev = events.device
+    il = torch.empty(n, dtype=torch.int64, device=dev)
+    ir = torch.empty(n, dtype=torch.int64, device=dev)
+    vl = torch.empty(n, dtype=torch.float32, device=dev)
+    vr = torch.empty(n, dtype=torch.float32, device=dev)
+    check(_lib.load().ramnet_voxel_votes(_h(events), _p(events), n, num_bins, width, height, _p(il), _p(vl), _p(ir),
+                                         _p(vr), _stream(events)))
+    return il, vl, ir, vr
+
+
+def head_conv(x_nchw: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], round_tf32: bool) -> torch.Tensor:
+    x = x_nchw.contiguous()
+    N, Cin, H, W = x.shape
+    Cout = w.shape[0]
+    y = empty_nhwc(N, Cout, H, W, x.device)
+    check(_lib.load().ramnet_head_conv(_h(x), _p(x), _p(w), _p(b), _p(y), N, Cin, H, W, Cout,
+                                       FLAG_ROUND_TF32 if round_tf32 else 0, _stream(x)))
+    return y
+
+
+def pack_weights(w_oihw: torch.Tensor, mma_kind: int, lstm_interleave: bool = False) -> torch.Tensor:
+    w = w_oihw.detach().contiguous().float()
+    Cout, Cin, k, _ = w.shape
+    out = torch.empty(w.numel(), dtype=torch.float32, device=w.device)
+    check(_lib.load().ramnet_pack_weights(_h(w), _p(w), _p(out), Cout, Cin, k, mma_kind, int(lstm_interleave),
+                                          _stream(w)))
+    return out
+
+
+_workspaces = {}
+
+
+def _workspace(device, nbytes: int):
+    if nbytes == 0:
+        return None
+    ws = _workspaces.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _workspaces[device] = ws
+    return ws
+
+
+def conv_fwd(x0: torch.Tensor, x1: Optional[torch.Tensor], w_packed: torch.Tensor, bias: Optional[torch.Tensor],
+             Cout: int, ksize: int, stride: int, epilogue: int, mma_kind: int, aux0=None, aux1=None,
+             round_tf32: bool = False):
+    """Implicit-GEMM convolution with fused epilogue.  Returns y0 or (y0, y1)."""
+    _check_nhwc(x0, 'conv_fwd x0')
+    N, C0, H, W = x0.shape
+    C1 = 0
+    if x1 is not None:
+        _check_nhwc(x1, 'conv_fwd x1')
+        C1 = x1.shape[1]
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    dev = x0.device
+    y1 = None
+    if epilogue == EPI_GRU_RU:
+        C = Cout // 2
+        y0, y1 = empty_nhwc(N, C, Ho, Wo, dev), empty_nhwc(N, C, Ho, Wo, dev)
+    elif epilogue == EPI_LSTM:
+        C = Cout // 4
+        y0, y1 = empty_nhwc(N, C, Ho, Wo, dev), empty_nhwc(N, C, Ho, Wo, dev)
+    else:
+        y0 = empty_nhwc(N, Cout, Ho, Wo, dev)
+    for a, nm in ((aux0, 'aux0'), (aux1, 'aux1')):
+        if a is not None:
+            _check_nhwc(a, 'conv_fwd ' + nm)
+    d = ConvDesc(N, H, W, C0, C1, Cout, ksize, stride, epilogue, mma_kind, FLAG_ROUND_TF32 if round_tf32 else 0, 0)
+    lib = _lib.load()
+    nws = lib.ramnet_conv_workspace_bytes(ctypes.byref(d))
+    ws = _workspace(dev, nws)
+    check(lib.ramnet_conv_fwd(_h(x0), ctypes.byref(d), _p(x0), _p(x1), _p(w_packed), _p(bias), _p(aux0), _p(aux1),
+                              _p(y0), _p(y1), _p(ws), nws, _stream(x0)))
+    return (y0, y1) if y1 is not None else y0
+
+
+def upsample2x_add(x: torch.Tensor, skip: Optional[torch.Tensor], round_tf32: bool) -> torch.Tensor:
+    _check_nhwc(x, 'upsample2x_add x')
+    if skip is not None:
+        _check_nhwc(skip, 'upsample2x_add skip')
+        if skip.shape != x.shape:
+            raise _lib.RamnetError(f'upsample2x_add: skip shape {tuple(skip.shape)} != x shape {tuple(x.shape)}')
+    N, C, H, W = x.shape
+    y = empty_nhwc(N, C, 2 * H, 2 * W, x.device)
+    check(_lib.load().ramnet_upsample2x_add(_h(x), _p(x), _p(skip), _p(y), N, H, W, C,
+                                            FLAG_ROUND_TF32 if round_tf32 else 0, _stream(x)))
+    return y
+
+
+def pred_sigmoid(x: torch.Tensor, skip: Optional[torch.Tensor], w: torch.Tensor, b: Optional[torch.Tensor],
+                 want_logits: bool = False):
+    """1x1 conv to one channel + sigmoid. Returns depth [N,1,H,W] (and logits)."""
+    _check_nhwc(x, 'pred_sigmoid x')
+    if skip is not None:
+        _check_nhwc(skip, 'pred_sigmoid skip')
+    N, C, H, W = x.shape
+    depth = torch.empty((N, 1, H, W), dtype=torch.float32, device=x.device)
+    logits = torch.empty_like(depth) if want_logits else None
+    wv = w.detach().reshape(-1).contiguous().float()
+    check(_lib.load().ramnet_pred_sigmoid(_h(x), _p(x), _p(skip), _p(wv), _p(b), _p(logits), _p(depth), N * H * W, C,
+                                          _stream(x)))
+    return (depth, logits) if want_logits else depth
+
+
+def si_loss_stats(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    pred, target = pred.contiguous(), target.contiguous()
+    stats = torch.empty(3, dtype=torch.float64, device=pred.device)
+    check(_lib.load().ramnet_si_loss_stats(_h(pred), _p(pred), _p(target), pred.numel(), _p(stats), _stream(pred)))
+    return stats
+
+
+def si_loss_value(stats: torch.Tensor, weight: float, n_lambda: float) -> torch.Tensor:
+    out = torch.empty((), dtype=torch.float32, device=stats.device)
+    check(_lib.load().ramnet_si_loss_value(_h(stats), _p(stats), weight, n_lambda, _p(out), _stream(stats)))
+    return out
+
+
+def si_loss_grad(pred, target, stats, weight: float, n_lambda: float, scale: float = 1.0) -> torch.Tensor:
+    pred, target = pred.contiguous(), target.contiguous()
+    grad = torch.empty_like(pred)
+    check(_lib.load().ramnet_si_loss_grad(_h(pred), _p(pred), _p(target), pred.numel(), _p(stats), weight, n_lambda,
+                                          scale, _p(grad), _stream(pred)))
+    return grad
+
+
+def adam_step(p, g, m, v, step: int, lr=3e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0):
+    """In-place fused Adam on flat fp32 buffers."""
+    for t in (p, g, m, v):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise _lib.RamnetError('adam_step: flat contiguous fp32 buffers required')
+    check(_lib.load().ramnet_adam_step(_h(p), _p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps,
+                                       weight_decay, step, _stream(p)))
