@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""RAM-Net hot-path benchmark (BASELINE.json metric: depth-maps/sec at 512x256, 5-bin voxel, seq=8).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mma-kind tf32|fp32]
+
+Workload at N=1 = BASELINE.json configs[1]: EventScape-shape 512x256 (H=256, W=512), 5-bin event
+voxel grid + 1-channel frame, batch 4, sequence length 8 with one event pass and one image pass
+per timestep (K=1), recurrent state carried across the 8 timesteps, forward only.  One "step" is
+one such sequence = 16 passes x 4 samples = 64 depth maps per GPU.  N>1: one process per GPU
+(torchrun), the batch dimension shards across ranks (4 samples per GPU, weak scaling), no
+data-path collective (inference replicas).
+
+JSON keys follow the driver contract; see DESIGN.md "Measurement".
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W, B, L, K_EVENTS, BINS = 256, 512, 4, 8, 1, 5
+MODEL_CFG = dict(num_bins_rgb=1, num_bins_events=BINS, skip_type='sum', recurrent_block_type='conv',
+                 state_combination='convgru', num_encoders=3, base_num_channels=32, num_residual_blocks=2,
+                 use_upsample_conv=True, norm='none', every_x_rgb_frame=K_EVENTS)
+MAPS_PER_STEP = B * L * (K_EVENTS + 1)
+METRIC = 'depth-maps/sec at 512x256, 5-bin voxel, seq=8 (forward)'
+UNIT = 'depth-maps/s'
+
+
+def conv_flops_per_map(h=H, w=W):
+    """Algorithmic conv FLOPs of the reference graph for one pass, B=1:
+    2*Ho*Wo*Cout*Cin*k*k over every nn.Conv2d, mean of the events and image pass."""
+    def conv(ho, wo, cin, cout, k):
+        return 2.0 * ho * wo * cout * cin * k * k
+    per = {}
+    for name, cin0 in (('events', BINS), ('image', 1)):
+        f = conv(h, w, cin0, 32, 5)
+        c, hh, ww = 32, h, w
+        for _ in range(3):
+            hh, ww = hh // 2, ww // 2
+            f += conv(hh, ww, c, 2 * c, 5)            # encoder
+            f += 3 * conv(hh, ww, 4 * c, 2 * c, 3)    # ConvGRU: 3 gate convs over [x|h]
+            c *= 2
+        f += 4 * conv(hh, ww, 256, 256, 3)            # 2 residual blocks
+        for _ in range(3):
+            hh, ww = hh * 2, ww * 2
+            f += conv(hh, ww, c, c // 2, 5)           # decoders (on the upsampled tensor)
+            c //= 2
+        f += conv(h, w, 32, 1, 1)
+        per[name] = f
+    return 0.5 * (per['events'] + per['image'])
+
+
+def read_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, 'measured (MEASURED_PEAKS.json)'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, \
+        'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.12)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def build_model(torch, device_index, mma_kind):
+    import rpg_ramnet_b200 as R
+    cfg = dict(MODEL_CFG, gpu=device_index, mma_kind=mma_kind)
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = R.ERGB2DepthRecurrent(cfg)
+    return m.eval().to(f'cuda:{device_index}')
+
+
+def run_sequence(model, items):
+    """One step: L timesteps with state carry, exactly the call pattern of lstm_trainer.py:256-272."""
+    prev_super, prev_lstm = None, {'events0': None, 'image': None}
+    outs = []
+    for item in items:
+        preds, supers, lstm = model(item, prev_super, prev_lstm)
+        outs.append(preds)
+        prev_super, prev_lstm = supers['image'], lstm
+    return outs
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation of the path = the oracle port (torch CPU
+# conv2d / interpolate exactly as the reference's nn.Modules call them), all host threads.
+# ------------------------------------------------------------------------------------------------
+def cpu_port_rate(torch, n_timesteps, threads, warm=True):
+    from oracle import ramnet_oracle as O
+    torch.set_num_threads(threads)
+    cfg = dict(MODEL_CFG, gpu=0)
+    import rpg_ramnet_b200 as R
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = R.ERGB2DepthRecurrent(cfg)            # parameter container only; never run
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    items = O.synth_sequence(B, H, W, n_timesteps + (1 if warm else 0), K_EVENTS, seed=2, with_targets=False)
+    prev_super, prev_lstm = None, {'events0': None, 'image': None}
+    t0 = None
+    with torch.no_grad():
+        for i, item in enumerate(items):
+            if i == (1 if warm else 0):
+                t0 = time.perf_counter()
+            _, supers, lstm = O.ergb2depth_recurrent(sd, cfg, item, prev_super, prev_lstm)
+            prev_super, prev_lstm = supers['image'], lstm
+    dt = time.perf_counter() - t0
+    maps = n_timesteps * B * (K_EVENTS + 1)
+    return maps / dt, dt
+
+
+def main_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    import torch
+    threads = os.cpu_count() or 1
+    per_step_timesteps = 1          # bounded sample: one timestep (1 event pass + 1 image pass, B=4) per step
+    from oracle import ramnet_oracle as O
+    torch.set_num_threads(threads)
+    cfg = dict(MODEL_CFG, gpu=0)
+    import rpg_ramnet_b200 as R
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = R.ERGB2DepthRecurrent(cfg)
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    items = O.synth_sequence(B, H, W, 2, K_EVENTS, seed=2, with_targets=False)
+    prev_super, prev_lstm = None, {'events0': None, 'image': None}
+    times = []
+    with torch.no_grad():
+        for s in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            _, supers, lstm = O.ergb2depth_recurrent(sd, cfg, items[s % 2], prev_super, prev_lstm)
+            prev_super, prev_lstm = supers['image'], lstm
+            if s >= args.warmup:
+                times.append(time.perf_counter() - t0)
+    total = sum(times)
+    maps = per_step_timesteps * B * (K_EVENTS + 1) * args.steps
+    val = maps / total
+    sample = (f'{args.steps} steps x 1 timestep (1 event pass + 1 image pass, batch {B}, {W}x{H}) of the '
+              f'seq={L} workload, state carried; torch CPU fp32, {threads} threads')
+    line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'RAM-Net shipped block forward, {W}x{H}, batch {B}, seq {L}, K=1 '
+                                   '(CPU arm: bounded sample, see cpu_baseline.sample)'},
+            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+
+    import rpg_ramnet_b200 as R
+    from rpg_ramnet_b200 import ops
+    from rpg_ramnet_b200.utils.synthetic import synth_sequence
+
+    model = build_model(torch, local, args.mma_kind)
+    host_items = synth_sequence(B, H, W, L, K_EVENTS, seed=2 + rank, with_targets=False)
+    host_items = [{k: v.pin_memory() for k, v in it.items()} for it in host_items]
+    dev_items = [{k: v.to(dev) for k, v in it.items()} for it in host_items]
+    h2d = sum(v.numel() * 4 for it in host_items for v in it.values())
+    d2h = MAPS_PER_STEP * H * W * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_resident():
+        with torch.no_grad():
+            run_sequence(model, dev_items)
+
+    host_out = [torch.empty((B, 1, H, W), dtype=torch.float32).pin_memory() for _ in range(L * (K_EVENTS + 1))]
+
+    def step_e2e():
+        with torch.no_grad():
+            outs = run_sequence(model, host_items)        # H2D copies happen inside model.forward (model.py:177,200)
+            i = 0
+            for preds in outs:
+                for p in preds.values():
+                    host_out[i].copy_(p, non_blocking=True)
+                    i += 1
+        torch.cuda.current_stream().synchronize()          # the caller reads the depth maps
+
+    for _ in range(args.warmup):
+        step_resident()
+    launches0 = R.launch_count(local)
+    with ClockSampler(local) as clk:
+        ms = timed(step_resident, args.steps)
+    launches = R.launch_count(local) - launches0
+    value = world * MAPS_PER_STEP * args.steps / (ms * 1e-3)
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    value_e2e = world * MAPS_PER_STEP * args.steps / (ms_e2e * 1e-3)
+
+    # roofline of the dominant kernel family (the implicit-GEMM convolution): every conv launch of one
+    # instrumented step bracketed by CUDA events on the launching stream.
+    peaks, peak_src = read_peaks()
+    ops.PROFILE = []
+    step_resident()
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    conv_ms = sum(a.elapsed_time(b) for (_, _, a, b) in prof if _ == 'conv')
+    conv_flops = sum(f for (k, f, _, _) in prof if k == 'conv')
+    n_conv = sum(1 for p in prof if p[0] == 'conv')
+    achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    peak_tf = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops')))
+    other = {}
+    for k, f, a, b in prof:
+        if k != 'conv':
+            other[k] = other.get(k, 0.0) + a.elapsed_time(b)
+    roofline = {'bound': 'tensor', 'kernel': 'conv_implicit_gemm (ramnet_conv_fwd, all instances)',
+                'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
+                'traffic': None, 'peak_source': peak_src + ', bf16 sustained; kind::tf32 nominal peak is half of bf16',
+                'launches_per_step': n_conv, 'ms_per_step_in_kernel': conv_ms,
+                'algorithmic_gflop_per_step': conv_flops / 1e9,
+                'other_kernels_ms_per_step': other, 'mma_kind': args.mma_kind}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, dt = cpu_port_rate(torch, n_timesteps=2, threads=threads)
+        cpu_baseline = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                        'sample': f'2 timesteps (4 passes, batch {B}, {W}x{H}) after 1 warm-up timestep of the same '
+                                  f'workload; oracle port = torch CPU fp32 conv2d/interpolate, {dt:.1f} s'}
+
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'tf32' if args.mma_kind == 'tf32' else 'f32', 'data': 'synthetic',
+                'config': {'workload': f'BASELINE configs[1]: RAM-Net shipped block (ConvGRU state, 3 encoders, base 32) '
+                                       f'forward, {W}x{H}, 5-bin voxel + 1 frame, batch {B}/GPU, seq {L}, K=1 '
+                                       f'-> {MAPS_PER_STEP} depth maps per step per GPU',
+                           'parallelism': f'dp{world} (batch sharded, no collective)',
+                           'l2': 'per-step working set (>4 GB of activations) exceeds the 126 MB L2; no explicit flush',
+                           'random_init_weights': 'torch.manual_seed(0), reference construction order'},
+                'clocks': clk.summary(),
+                'e2e': {'value': value_e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                        'ms_per_step': ms_e2e / args.steps,
+                        'api': 'ERGB2DepthRecurrent.forward(item, prev_super_states, prev_states_lstm) with pinned '
+                               'host tensors; depth maps copied back to pinned host memory'},
+                'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
+                'algorithmic_gflop_per_map': conv_flops_per_map() / 1e9}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--mma-kind', default=os.environ.get('RAMNET_MMA_KIND', 'tf32'), choices=['tf32', 'fp32'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'reference':
+        return main_reference(args)
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}',
+               '--master-addr', '127.0.0.1', '--master-port', os.environ.get('MASTER_PORT', '29511'),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return main_ours(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -33,9 +33,10 @@ def voxel_grid(events: np.ndarray, num_bins: int, width: int, height: int) -> np
     Follows event_tensor_utils.py:71-117 step for step but does NOT mutate its
     input (the reference overwrites columns 0 and 3, :95,:100).  Index
     arithmetic is int64 (truncation toward zero, :102), timestamps/weights are
-    float64 and are cast to float32 only when accumulated; ``np.add.at`` adds
-    sequentially in float32 in event order (left votes first, then right
-    votes, :107-113).
+    float64; ``np.add.at(float32_grid, idx, float64_vals)`` resolves to the
+    float64 add loop, i.e. each step is grid = f32(f64(grid) + val), sequential
+    in event order, left votes first, then right votes (:107-113) — probed:
+    pre-casting val to float32 differs by 1 ulp on pixels with >= 2 votes.
     """
     assert events.ndim == 2 and events.shape[1] == 4
     assert num_bins > 0 and width > 0 and height > 0
@@ -64,14 +65,15 @@ def voxel_grid(events: np.ndarray, num_bins: int, width: int, height: int) -> np
 
 
 def voxel_grid_votes(events: np.ndarray, num_bins: int, width: int, height: int):
-    """The integer index stream and float32 vote values of `voxel_grid`,
+    """The integer index stream and float64 vote values of `voxel_grid`,
     returned un-accumulated: (idx_left, val_left, idx_right, val_right) with
-    index -1 where the vote is dropped.  Used for the bit-exact index check."""
+    index -1 where the vote is dropped.  Used for the bit-exact index check
+    (cast the values to float32 to compare with the CUDA vote stream)."""
     ev = np.asarray(events, dtype=np.float64)
     n = ev.shape[0]
     if n == 0:
         z = np.zeros(0, np.int64)
-        return z, np.zeros(0, np.float32), z, np.zeros(0, np.float32)
+        return z, np.zeros(0, np.float64), z, np.zeros(0, np.float64)
     t0 = ev[0, 0]
     dT = ev[-1, 0] - t0
     if dT == 0:
@@ -86,7 +88,7 @@ def voxel_grid_votes(events: np.ndarray, num_bins: int, width: int, height: int)
     base = xs + ys * width
     il = np.where(tis < num_bins, base + tis * width * height, -1)
     ir = np.where(tis + 1 < num_bins, base + (tis + 1) * width * height, -1)
-    return il, (pol * (1.0 - dts)).astype(np.float32), ir, (pol * dts).astype(np.float32)
+    return il, pol * (1.0 - dts), ir, pol * dts
 
 
 # --------------------------------------------------------------------------
@@ -423,45 +425,10 @@ def adam_step(p: np.ndarray, g: np.ndarray, m: np.ndarray, v: np.ndarray, step: 
 
 
 # --------------------------------------------------------------------------
-# synthetic inputs — shared by tests, smoke and bench
+# synthetic inputs: the generators live in the product package
+# (bench.py's GPU arm must not import oracle/); re-exported for the tests.
 # --------------------------------------------------------------------------
-def synth_sequence(B: int, H: int, W: int, L: int, K: int, seed: int, bins_events: int = 5,
-                   bins_rgb: int = 1, with_targets: bool = True) -> List[dict]:
-    """L items of {'events{k}': sparse signed voxel grids, 'image': grey in [0,1],
-    'depth_*': targets in [0,1] with a 10x10 NaN patch}."""
-    g = torch.Generator().manual_seed(seed)
-    seq = []
-    for _ in range(L):
-        item = {}
-        for k in range(K):
-            item[f'events{k}'] = torch.randn(B, bins_events, H, W, generator=g) * \
-                (torch.rand(B, bins_events, H, W, generator=g) < 0.1).float()
-        item['image'] = torch.rand(B, bins_rgb, H, W, generator=g)
-        if with_targets:
-            for key in [f'events{k}' for k in range(K)] + ['image']:
-                t = torch.rand(B, 1, H, W, generator=g)
-                t[:, :, 3:13, 5:15] = float('nan')
-                item['depth_' + key] = t
-        seq.append(item)
-    return seq
-
-
-def synth_events(n: int, width: int, height: int, seed: int, hot: bool = False) -> np.ndarray:
-    """[n,4] float64 rows [t, x, y, p]; t sorted in [0, 0.05); 'hot' puts 90% of
-    events on 1% of the pixels to expose atomic contention."""
-    rng = np.random.default_rng(seed)
-    t = np.sort(rng.uniform(0.0, 0.05, n))
-    if hot:
-        npix = max(1, (width * height) // 100)
-        hot_pix = rng.integers(0, width * height, npix)
-        pix = np.where(rng.uniform(size=n) < 0.9, hot_pix[rng.integers(0, npix, n)],
-                       rng.integers(0, width * height, n))
-        x, y = pix % width, pix // width
-    else:
-        x = rng.integers(0, width, n)
-        y = rng.integers(0, height, n)
-    p = rng.integers(0, 2, n)
-    return np.stack([t, x.astype(np.float64), y.astype(np.float64), p.astype(np.float64)], 1)
+from rpg_ramnet_b200.utils.synthetic import synth_events, synth_sequence  # noqa: E402,F401
 
 
 def scale_weights(model, s: float):

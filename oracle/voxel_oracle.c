@@ -10,9 +10,11 @@
  *     (the reference overwrites columns 0 and 3 in place, :95,:100);
  *   - t^ = (B-1)(t - t0)/dT with dT = t[N-1]-t[0], dT==0 -> 1.0 (:88-95), float64;
  *   - ti = (int64) t^  (truncation toward zero, numpy astype(int), :102);
- *   - p==0 -> -1 (:100); left = p(1-dt), right = p*dt in float64, cast to
- *     float32 when accumulated; np.add.at accumulates sequentially in float32,
- *     all left votes first (:107-109), then all right votes (:111-113);
+ *   - p==0 -> -1 (:100); left = p(1-dt), right = p*dt in float64;
+ *     np.add.at(float32 grid, idx, float64 vals) runs the float64 add loop, so
+ *     each step is grid = (float)((double)grid + val), sequentially, all left
+ *     votes first (:107-109), then all right votes (:111-113) (probed: casting
+ *     val to float first is 1 ulp off on pixels that receive >= 2 votes);
  *   - a vote is dropped iff ti >= B (resp. ti+1 >= B); no lower bound check.
  */
 #include <stdint.h>
@@ -36,9 +38,9 @@ int voxel_oracle(const double *ev, int64_t n, int bins, int width, int height, f
             const int64_t ti = (int64_t)ts;
             const double dt = ts - (double)ti;
             if (pass == 0) {
-                if (ti < bins) grid[x + y * width + ti * plane] += (float)(p * (1.0 - dt));
+                if (ti < bins) { float *c = &grid[x + y * width + ti * plane]; *c = (float)((double)*c + p * (1.0 - dt)); }
             } else {
-                if (ti + 1 < bins) grid[x + y * width + (ti + 1) * plane] += (float)(p * dt);
+                if (ti + 1 < bins) { float *c = &grid[x + y * width + (ti + 1) * plane]; *c = (float)((double)*c + p * dt); }
             }
         }
     }

@@ -96,8 +96,9 @@ def head_conv(x_nchw: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], 
     N, Cin, H, W = x.shape
     Cout = w.shape[0]
     y = empty_nhwc(N, Cout, H, W, x.device)
-    check(_lib.load().ramnet_head_conv(_h(x), _p(x), _p(w), _p(b), _p(y), N, Cin, H, W, Cout,
-                                       FLAG_ROUND_TF32 if round_tf32 else 0, _stream(x)))
+    with _Prof('head_conv', 2.0 * N * H * W * Cout * Cin * 25, x.device):
+        check(_lib.load().ramnet_head_conv(_h(x), _p(x), _p(w), _p(b), _p(y), N, Cin, H, W, Cout,
+                                           FLAG_ROUND_TF32 if round_tf32 else 0, _stream(x)))
     return y
 
 
@@ -108,6 +109,25 @@ def pack_weights(w_oihw: torch.Tensor, mma_kind: int, lstm_interleave: bool = Fa
     check(_lib.load().ramnet_pack_weights(_h(w), _p(w), _p(out), Cout, Cin, k, mma_kind, int(lstm_interleave),
                                           _stream(w)))
     return out
+
+
+# bench.py hook: when a list, every wrapped launch appends (kind, algorithmic_flops, start_event, end_event)
+PROFILE = None
+
+
+class _Prof:
+    def __init__(self, kind, flops, dev):
+        self.kind, self.flops, self.dev = kind, flops, dev
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.a, self.b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.a.record(torch.cuda.current_stream(self.dev))
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.b.record(torch.cuda.current_stream(self.dev))
+            PROFILE.append((self.kind, self.flops, self.a, self.b))
 
 
 _workspaces = {}
@@ -151,8 +171,9 @@ def conv_fwd(x0: torch.Tensor, x1: Optional[torch.Tensor], w_packed: torch.Tenso
     lib = _lib.load()
     nws = lib.ramnet_conv_workspace_bytes(ctypes.byref(d))
     ws = _workspace(dev, nws)
-    check(lib.ramnet_conv_fwd(_h(x0), ctypes.byref(d), _p(x0), _p(x1), _p(w_packed), _p(bias), _p(aux0), _p(aux1),
-                              _p(y0), _p(y1), _p(ws), nws, _stream(x0)))
+    with _Prof('conv', 2.0 * N * Ho * Wo * Cout * (C0 + C1) * ksize * ksize, dev):
+        check(lib.ramnet_conv_fwd(_h(x0), ctypes.byref(d), _p(x0), _p(x1), _p(w_packed), _p(bias), _p(aux0),
+                                  _p(aux1), _p(y0), _p(y1), _p(ws), nws, _stream(x0)))
     return (y0, y1) if y1 is not None else y0
 
 
@@ -164,8 +185,9 @@ def upsample2x_add(x: torch.Tensor, skip: Optional[torch.Tensor], round_tf32: bo
             raise _lib.RamnetError(f'upsample2x_add: skip shape {tuple(skip.shape)} != x shape {tuple(x.shape)}')
     N, C, H, W = x.shape
     y = empty_nhwc(N, C, 2 * H, 2 * W, x.device)
-    check(_lib.load().ramnet_upsample2x_add(_h(x), _p(x), _p(skip), _p(y), N, H, W, C,
-                                            FLAG_ROUND_TF32 if round_tf32 else 0, _stream(x)))
+    with _Prof('upsample2x_add', 0.0, x.device):
+        check(_lib.load().ramnet_upsample2x_add(_h(x), _p(x), _p(skip), _p(y), N, H, W, C,
+                                                FLAG_ROUND_TF32 if round_tf32 else 0, _stream(x)))
     return y
 
 
@@ -179,8 +201,9 @@ def pred_sigmoid(x: torch.Tensor, skip: Optional[torch.Tensor], w: torch.Tensor,
     depth = torch.empty((N, 1, H, W), dtype=torch.float32, device=x.device)
     logits = torch.empty_like(depth) if want_logits else None
     wv = w.detach().reshape(-1).contiguous().float()
-    check(_lib.load().ramnet_pred_sigmoid(_h(x), _p(x), _p(skip), _p(wv), _p(b), _p(logits), _p(depth), N * H * W, C,
-                                          _stream(x)))
+    with _Prof('pred_sigmoid', 2.0 * N * H * W * C, x.device):
+        check(_lib.load().ramnet_pred_sigmoid(_h(x), _p(x), _p(skip), _p(wv), _p(b), _p(logits), _p(depth),
+                                              N * H * W, C, _stream(x)))
     return (depth, logits) if want_logits else depth
 
 

@@ -1,0 +1,123 @@
+"""GPU: whole-model parity — our CUDA graph vs (a) the reference's own outputs (tests/golden) and
+(b) the CPU oracle on the same seeded inputs, through the reference-shaped module API."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ramnet_oracle as O
+from helpers import (MODEL_CASES, build_product_model, case_inputs, flat_supers, load_case, max_rel_err,
+                     run_oracle_sequence, run_product_sequence)
+
+pytestmark = pytest.mark.gpu
+
+SUPPORTED = [c for c in MODEL_CASES if c != 'transposed']
+# north_star tolerance: fp32 depth maps within 1e-3 relative of the reference forward.
+REL_TOL = {'fp32': 1e-4, 'tf32': 1e-3}
+
+
+@pytest.mark.parametrize('kind', ['fp32', 'tf32'])
+@pytest.mark.parametrize('name', SUPPORTED)
+def test_model_matches_reference_golden(name, kind):
+    g, meta = load_case(name)
+    model, _ = build_product_model(meta, mma_kind=kind)
+    model.to('cuda:0')
+    outs = run_product_sequence(model, meta, case_inputs(meta))
+    n = 0
+    for l, (preds, supers) in enumerate(outs):
+        assert [k for k in preds] == [k.split('/')[-1] for k in g.files if k.startswith(f'pred/{l}/')]
+        for key, p in preds.items():
+            ref = g[f'pred/{l}/{key}']
+            assert p.shape == ref.shape and p.dtype == torch.float32
+            err = max_rel_err(p.cpu().numpy(), ref)
+            assert err <= REL_TOL[kind], f'{name} {kind} pred/{l}/{key}: max rel err {err:.3e}'
+            n += 1
+        if supers.get('image') is not None:
+            for key, s in supers.items():
+                for j, t in enumerate(flat_supers(s)):
+                    ref = g[f'super/{l}/{key}/{j}']
+                    got = t[:, ::8, ::4, ::4].cpu().numpy()
+                    scale = max(1e-3, float(np.abs(ref).max()))
+                    assert np.abs(got - ref).max() <= (5e-5 if kind == 'fp32' else 3e-3) * scale, \
+                        f'{name} {kind} super/{l}/{key}/{j}'
+    assert n == len([k for k in g.files if k.startswith('pred/')])
+
+
+@pytest.mark.parametrize('kind', ['fp32', 'tf32'])
+def test_forward_events_images_decoder_api(kind):
+    """Inner API of StateNetPhasedRecurrent called in an irregular order (BASELINE config 4's schedule):
+    3 event passes, 1 image pass, 1 event pass, on a non-square MVSEC-like crop."""
+    g, meta = load_case('cfg1_shipped')
+    meta = dict(meta, H=64, W=88, B=1, wscale=1.5)
+    model, cfg = build_product_model(meta, mma_kind=kind)
+    model.to('cuda:0')
+    net = model.statenetphasedrecurrent
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    ocfg = O.NetCfg(cfg)
+    gen = torch.Generator().manual_seed(77)
+    ev = [torch.randn(1, 5, 64, 88, generator=gen) * (torch.rand(1, 5, 64, 88, generator=gen) < 0.1) for _ in range(4)]
+    im = torch.rand(1, 1, 64, 88, generator=gen)
+    s_ref = O.zero_super_states(ocfg, 1, 64, 88)
+    s = model._zero_states(1, 64, 88)
+    order = [('e', ev[0]), ('e', ev[1]), ('e', ev[2]), ('i', im), ('e', ev[3])]
+    with torch.no_grad():
+        for which, x in order:
+            if which == 'e':
+                s, _ = net.forward_events(x.to('cuda:0'), s, None, None)
+                s_ref, _ = O.forward_events(sd, ocfg, x, s_ref, None)
+            else:
+                s, _ = net.forward_images(x.to('cuda:0'), s, None, None)
+                s_ref, _ = O.forward_images(sd, ocfg, x, s_ref, None)
+            d = net.forward_decoder(s)
+            d_ref = O.forward_decoder(sd, ocfg, s_ref)
+            assert max_rel_err(d.cpu().numpy(), d_ref.numpy()) <= REL_TOL[kind]
+
+
+def test_states_round_trip_through_plain_nchw_tensors():
+    """A caller may hand back states as ordinary contiguous NCHW tensors (e.g. after a checkpoint)."""
+    g, meta = load_case('rect_b2')
+    model, _ = build_product_model(meta, mma_kind='fp32')
+    model.to('cuda:0')
+    seq = case_inputs(meta)
+    with torch.no_grad():
+        p1, s1, l1 = model(seq[0], None, {'events0': None, 'image': None})
+        p2, _, _ = model(seq[1], s1['image'], l1)
+        s_plain = [t.contiguous().clone() for t in s1['image']]
+        p2b, _, _ = model(seq[1], s_plain, l1)
+    assert torch.equal(p2['image'], p2b['image'])
+
+
+def test_weight_cache_tracks_parameter_updates():
+    g, meta = load_case('cfg1_shipped')
+    meta = dict(meta, H=32, W=32)
+    model, _ = build_product_model(meta, mma_kind='fp32')
+    model.to('cuda:0')
+    item = O.synth_sequence(1, 32, 32, 1, 1, seed=3)[0]
+    states = {'events0': None, 'image': None}
+    with torch.no_grad():
+        a = model(item, None, states)[0]['image'].clone()
+        b = model(item, None, states)[0]['image'].clone()
+        assert torch.equal(a, b)
+        model.statenetphasedrecurrent.pred.conv2d.bias.add_(0.5)
+        model.statenetphasedrecurrent.decoders[2].conv2d.weight.mul_(1.1)
+        c = model(item, None, states)[0]['image']
+    assert not torch.equal(a, c)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    ref = O.ergb2depth_recurrent(sd, dict(meta['config']), item, None, states)[0]['image']
+    assert max_rel_err(c.cpu().numpy(), ref.numpy()) <= 1e-4
+
+
+def test_unsupported_and_bad_shapes_raise():
+    import rpg_ramnet_b200 as R
+    g, meta = load_case('cfg1_shipped')
+    model, _ = build_product_model(meta, mma_kind='fp32')
+    model.to('cuda:0')
+    bad = O.synth_sequence(1, 36, 52, 1, 1, seed=1)[0]      # 36 % 8 != 0: reference fails too (Appendix A)
+    with torch.no_grad(), pytest.raises(R.RamnetError):
+        model(bad, None, {'events0': None, 'image': None})
+    with pytest.raises(R.RamnetError):                      # grad mode is not silently degraded
+        model(O.synth_sequence(1, 32, 32, 1, 1, seed=1)[0], None, {'events0': None, 'image': None})
+
+
+def test_smoke_entry():
+    import __graft_entry__ as ge
+    ge.smoke()
