@@ -290,7 +290,7 @@ def main_ours(args):
     step_resident()
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
-    conv_ms = sum(a.elapsed_time(b) for (_, _, a, b) in prof if _ == 'conv')
+    conv_ms = sum(a.elapsed_time(b) for (k, f, a, b) in prof if k == 'conv')
     conv_flops = sum(f for (k, f, _, _) in prof if k == 'conv')
     n_conv = sum(1 for p in prof if p[0] == 'conv')
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0

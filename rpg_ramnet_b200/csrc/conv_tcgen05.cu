@@ -1,7 +1,378 @@
-// placeholder: replaced by the tcgen05/TMA implicit-GEMM kernel
+// Implicit-GEMM convolution on the 5th-gen tensor cores (RAMNET_MMA_TF32): TMA -> smem ->
+// tcgen05.mma kind::tf32 -> TMEM -> fused epilogue.  sm_100a only.
+//
+// GEMM view:  D[m, n] = sum_{tap, c} A[pix(m, tap), c] * W[tap, n, c]
+//   m = output pixel of a TH x TW patch of one image (TH*TW = 128 = UMMA M),
+//   n = output channel (GEMM column; BN per CTA, UMMA N),
+//   k = (filter tap, input channel), walked as taps x 32-channel chunks (32 fp32 = one 128-byte
+//       swizzle row, 4 UMMA K-steps of 8).
+//
+// Data movement: activations are NHWC fp32, so the 32 channels of one pixel are one contiguous
+// 128-byte row.  For a stride-1 conv the A tile of tap (r, s) is the TMA box
+// {32 ch, TW px, TH rows, 1 image} at (c, x0+s-pad, y0+r-pad, n) of the 4-D tensor (C, W, H, N):
+// the hardware zero-fills out-of-bounds pixels, which IS the convolution's zero padding, so the
+// im2col matrix never exists anywhere.  Stride-2 convs view the same memory as the 5-D tensor
+// (2C, W/2, 2, H/2, N) (column parity folded into the channel axis, row parity its own axis) so
+// that "every other pixel" is again a dense box.  The virtual concat [x0 | x1] of the recurrent
+// cells is two tensor maps walked back to back.  Weights are packed [tap][Cout][Cin] (K-major)
+// and fetched as {32 ch, BN rows} boxes.  Both operands land in 128B-swizzled K-major smem tiles
+// that tcgen05.mma consumes through shared-memory descriptors; accumulators live in TMEM.
+//
+// Roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane),
+// warps 2-5 = epilogue (TMEM lane quarter = warp_id % 4).  mbarrier rings: full[s] (TMA ->
+// MMA), empty[s] (tcgen05.commit -> TMA), accum (last commit -> epilogue).
+#include <cuda.h>
+
 #include "common.cuh"
+
+namespace {
+
+constexpr int kTileM = 128;        // UMMA M
+constexpr int kChunk = 32;         // channels per K-chunk (128 bytes of fp32)
+constexpr int kABytes = kTileM * kChunk * 4;  // 16 KB
+constexpr int kThreads = 192;
+constexpr uint32_t kSpinLimit = 1u << 28;     // bring-up guard: trap instead of hanging the GPU
+
+struct TcGeom {
+    int N, Ho, Wo, Cout;
+    int C0, C1;          // channels of the two sources
+    int ks, stride, pad;
+    int TW, TH;          // output patch (TW*TH = 128)
+    int tiles_x, tiles_y;
+    int BN;              // GEMM columns per CTA
+    int stages;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0, spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!done && ++spins > kSpinLimit) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+        "[%2];" ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address            bits [0,14)
+    d |= (uint64_t)1 << 16;                     // leading byte offset (unused for swizzled K-major) = 16 B
+    d |= (uint64_t)(1024 >> 4) << 32;           // stride byte offset: next 8-row atom
+    d |= (uint64_t)1 << 46;                     // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                     // layout: SWIZZLE_128B
+    return d;
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = n.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+        "[%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---------------------------------------------------------------- kernel
+template <int EPI>
+__global__ void __launch_bounds__(kThreads) conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x0,
+                                                                const __grid_constant__ CUtensorMap map_x1,
+                                                                const __grid_constant__ CUtensorMap map_w, TcGeom g,
+                                                                EpiParams ep) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment for the 128B swizzle atoms
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int b_bytes = g.BN * kChunk * 4;
+    const int stage_bytes = kABytes + b_bytes;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)g.stages * stage_bytes);
+    uint64_t *empty_bar = full_bar + g.stages;
+    uint64_t *accum_bar = empty_bar + g.stages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // tile coordinates
+    int t = blockIdx.x;
+    const int tx = t % g.tiles_x;
+    t /= g.tiles_x;
+    const int ty = t % g.tiles_y;
+    const int img = t / g.tiles_y;
+    const int x0 = tx * g.TW, y0 = ty * g.TH;
+    const int n0 = blockIdx.y * g.BN;
+
+    const int chunks0 = g.C0 / kChunk, chunks = (g.C0 + g.C1) / kChunk;
+    const int ksteps = g.ks * g.ks * chunks;
+    // TMEM columns: power of two >= 32
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < g.BN) tmem_cols <<= 1;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_x0);
+        prefetch_tmap(&map_x1);
+        prefetch_tmap(&map_w);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < g.stages; ++s) {
+            mbar_init(full_bar + s, 1);
+            mbar_init(empty_bar + s, 1);
+        }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tap = 0; tap < g.ks * g.ks; ++tap) {
+                const int r = tap / g.ks, s = tap % g.ks;
+                for (int ch = 0; ch < chunks; ++ch) {
+                    mbar_wait(empty_bar + stage, phase ^ 1);
+                    uint8_t *sa = smem + (size_t)stage * stage_bytes;
+                    uint8_t *sb = sa + kABytes;
+                    mbar_expect_tx(full_bar + stage, (uint32_t)stage_bytes);
+                    const bool second = ch >= chunks0;
+                    const CUtensorMap *mx = second ? &map_x1 : &map_x0;
+                    const int c = (second ? ch - chunks0 : ch) * kChunk;
+                    if (g.stride == 1) {
+                        tma_load_4d(sa, mx, full_bar + stage, c, x0 + s - g.pad, y0 + r - g.pad, img);
+                    } else {
+                        // input row 2*oy + (r - pad) = 2*(oy + dy) + py, likewise for columns
+                        const int ry = r - g.pad, rx = s - g.pad;
+                        const int dy = ry >> 1, py = ry & 1, dx = rx >> 1, px = rx & 1;  // arithmetic shift = floor
+                        const int Csrc = second ? g.C1 : g.C0;
+                        tma_load_5d(sa, mx, full_bar + stage, px * Csrc + c, x0 + dx, py, y0 + dy, img);
+                    }
+                    tma_load_3d(sb, &map_w, full_bar + stage, ch * kChunk, n0, tap);
+                    if (++stage == g.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(g.BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int k = 0; k < ksteps; ++k) {
+                mbar_wait(full_bar + stage, phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + kABytes);
+#pragma unroll
+                for (int kk = 0; kk < kChunk / 8; ++kk)  // 8 tf32 = 32 bytes per UMMA K-step: +2 in the >>4 address field
+                    umma_tf32(tmem_base, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0);
+                umma_commit(empty_bar + stage);  // frees the smem slot once these MMAs have read it
+                if (++stage == g.stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(accum_bar);  // accumulator complete
+        }
+    } else {
+        // ===================== epilogue: TMEM -> registers -> fused math -> global =====================
+        const int quarter = warp & 3;             // TMEM lanes [32q, 32q+32) are visible to warps with id%4 == q
+        const int row = quarter * 32 + lane;      // GEMM row inside the tile
+        const int oy = y0 + row / g.TW, ox = x0 + row % g.TW;
+        const bool valid = oy < g.Ho && ox < g.Wo;
+        const int64_t m = ((int64_t)img * g.Ho + oy) * g.Wo + ox;
+        mbar_wait(accum_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        for (int c = 0; c < g.BN; c += 16) {
+            float v[16];
+            tmem_ld16(lane_addr + (uint32_t)c, v);   // warp-collective: every lane participates
+            if (valid) epilogue_store<EPI, 16>(ep, m, n0 + c, v);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode(ramnet_handle *h, CUtensorMap *map, const void *base, int rank, const cuuint64_t *dims,
+           const cuuint64_t *strides_bytes, const cuuint32_t *box) {
+    cuuint32_t elem[5] = {1, 1, 1, 1, 1};
+    CUresult r = ((EncodeTiledFn)h->encode_tiled)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                                                  const_cast<void *>(base), dims, strides_bytes, box, elem,
+                                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return ramnet_set_error(RAMNET_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return RAMNET_OK;
+}
+
+// activation map: stride 1 -> (C, W, H, N); stride 2 -> (2C, W/2, 2, H/2, N)
+int encode_activation(ramnet_handle *h, CUtensorMap *map, const float *x, int N, int H, int W, int C, int stride,
+                      int TW, int TH) {
+    if (stride == 1) {
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+        cuuint64_t str[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+        cuuint32_t box[4] = {kChunk, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+        return encode(h, map, x, 4, dims, str, box);
+    }
+    cuuint64_t dims[5] = {(cuuint64_t)2 * C, (cuuint64_t)W / 2, 2, (cuuint64_t)H / 2, (cuuint64_t)N};
+    cuuint64_t str[4] = {(cuuint64_t)2 * C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)2 * W * C * 4,
+                         (cuuint64_t)H * W * C * 4};
+    cuuint32_t box[5] = {kChunk, (cuuint32_t)TW, 1, (cuuint32_t)TH, 1};
+    return encode(h, map, x, 5, dims, str, box);
+}
+
+void pick_tile(int Ho, int Wo, int *TW, int *TH) {
+    int64_t best = -1;
+    for (int tw = 128; tw >= 8; tw >>= 1) {
+        const int th = kTileM / tw;
+        const int64_t covered = (int64_t)((Wo + tw - 1) / tw) * tw * ((Ho + th - 1) / th) * th;
+        if (best < 0 || covered < best) { best = covered; *TW = tw; *TH = th; }
+    }
+}
+
+template <int EPI>
+int launch(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap &m1, const CUtensorMap &mw, const TcGeom &g,
+           const EpiParams &ep, cudaStream_t s) {
+    const size_t smem = (size_t)g.stages * (kABytes + (size_t)g.BN * kChunk * 4) + (2 * g.stages + 1) * 8 + 16 + 1024;
+    static size_t configured = 0;   // per template instance
+    if (smem > configured) {
+        RAMNET_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid((unsigned)(g.tiles_x * g.tiles_y * g.N), (unsigned)(g.Cout / g.BN));
+    conv_tcgen05_kernel<EPI><<<grid, kThreads, smem, s>>>(m0, m1, mw, g, ep);
+    RAMNET_LAUNCH_CHECK(h);
+    return RAMNET_OK;
+}
+}  // namespace
+
 size_t conv_tf32_workspace_bytes(const ramnet_conv_desc *) { return 0; }
-int conv_fwd_tf32(ramnet_handle *, const ramnet_conv_desc *, const float *, const float *, const float *,
-                  const EpiParams &, void *, size_t, cudaStream_t) {
-    return ramnet_set_error(RAMNET_EUNSUPPORTED, "conv_fwd: RAMNET_MMA_TF32 path not built");
+
+int conv_fwd_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *x0, const float *x1, const float *wp,
+                  const EpiParams &ep, void *, size_t, cudaStream_t s) {
+    RAMNET_CHECK_ARG(d->C0 % kChunk == 0 && d->C1 % kChunk == 0,
+                     "conv_fwd(tf32): C0=%d, C1=%d must be multiples of 32 (one 128-byte swizzle row)", d->C0, d->C1);
+    RAMNET_CHECK_ARG(d->Cout % 16 == 0, "conv_fwd(tf32): Cout=%d must be a multiple of 16", d->Cout);
+    RAMNET_CHECK_ARG(d->stride == 1 || (d->H % 2 == 0 && d->W % 2 == 0), "conv_fwd(tf32): stride 2 needs even H, W");
+    RAMNET_CHECK_ARG((((uintptr_t)x0 | (uintptr_t)x1 | (uintptr_t)wp) & 15) == 0, "conv_fwd(tf32): 16-byte alignment");
+    TcGeom g;
+    g.N = d->N; g.Cout = d->Cout; g.C0 = d->C0; g.C1 = d->C1;
+    g.ks = d->ksize; g.stride = d->stride; g.pad = d->ksize / 2;
+    g.Ho = conv_out_dim(d->H, d->stride); g.Wo = conv_out_dim(d->W, d->stride);
+    pick_tile(g.Ho, g.Wo, &g.TW, &g.TH);
+    g.tiles_x = (g.Wo + g.TW - 1) / g.TW; g.tiles_y = (g.Ho + g.TH - 1) / g.TH;
+    // GEMM columns per CTA: the largest UMMA N dividing Cout that still yields >= one CTA per SM
+    const int64_t mtiles = (int64_t)g.tiles_x * g.tiles_y * g.N;
+    RAMNET_CHECK_ARG(mtiles <= 0x7fffffff, "conv_fwd(tf32): too many tiles");
+    g.BN = 0;
+    for (int bn = 256; bn >= 16; bn >>= 1) {
+        if (d->Cout % bn) continue;
+        if (g.BN == 0) g.BN = bn;
+        if (mtiles * (d->Cout / bn) >= h->sm_count) { g.BN = bn; break; }
+        g.BN = bn;
+        if (bn <= 64) break;   // do not shrink below 64 columns just to fill SMs
+    }
+    RAMNET_CHECK_ARG(g.BN >= 16, "conv_fwd(tf32): no UMMA N divides Cout=%d", d->Cout);
+    if (d->epilogue == RAMNET_EPI_GRU_RU || d->epilogue == RAMNET_EPI_LSTM)
+        RAMNET_CHECK_ARG(g.BN % 16 == 0, "conv_fwd(tf32): gate epilogues need 16-column groups");
+    const int stage_bytes = kABytes + g.BN * kChunk * 4;
+    g.stages = g.BN > 128 ? 4 : (100 * 1024) / stage_bytes;   // <=128 columns: two CTAs per SM
+    if (g.stages > 8) g.stages = 8;
+    if (g.stages < 2) g.stages = 2;
+
+    CUtensorMap m0, m1, mw;
+    int rc = encode_activation(h, &m0, x0, d->N, d->H, d->W, d->C0, d->stride, g.TW, g.TH);
+    if (rc) return rc;
+    if (x1) {
+        rc = encode_activation(h, &m1, x1, d->N, d->H, d->W, d->C1, d->stride, g.TW, g.TH);
+        if (rc) return rc;
+    } else {
+        m1 = m0;
+    }
+    const int Ct = d->C0 + d->C1, taps = d->ksize * d->ksize;
+    cuuint64_t wd[3] = {(cuuint64_t)Ct, (cuuint64_t)d->Cout, (cuuint64_t)taps};
+    cuuint64_t ws[2] = {(cuuint64_t)Ct * 4, (cuuint64_t)Ct * d->Cout * 4};
+    cuuint32_t wb[3] = {kChunk, (cuuint32_t)g.BN, 1};
+    rc = encode(h, &mw, wp, 3, wd, ws, wb);
+    if (rc) return rc;
+
+    switch (d->epilogue) {
+        case RAMNET_EPI_BIAS: return launch<RAMNET_EPI_BIAS>(h, m0, m1, mw, g, ep, s);
+        case RAMNET_EPI_BIAS_RELU: return launch<RAMNET_EPI_BIAS_RELU>(h, m0, m1, mw, g, ep, s);
+        case RAMNET_EPI_BIAS_RES_RELU: return launch<RAMNET_EPI_BIAS_RES_RELU>(h, m0, m1, mw, g, ep, s);
+        case RAMNET_EPI_GRU_RU: return launch<RAMNET_EPI_GRU_RU>(h, m0, m1, mw, g, ep, s);
+        case RAMNET_EPI_GRU_OUT: return launch<RAMNET_EPI_GRU_OUT>(h, m0, m1, mw, g, ep, s);
+        case RAMNET_EPI_LSTM: return launch<RAMNET_EPI_LSTM>(h, m0, m1, mw, g, ep, s);
+    }
+    return ramnet_set_error(RAMNET_EINVAL, "conv_fwd(tf32): unreachable");
 }

@@ -37,13 +37,20 @@ def zeros_nhwc(N, C, H, W, device) -> torch.Tensor:
     return torch.zeros((N, H, W, C), dtype=torch.float32, device=device).permute(0, 3, 1, 2)
 
 
+def _is_nhwc(t: torch.Tensor) -> bool:
+    """NHWC memory under a logical [N,C,H,W] shape; strides of size-1 dims are irrelevant."""
+    N, C, H, W = t.shape
+    want = (H * W * C, 1, W * C, C)
+    return all(sz == 1 or st == w for sz, st, w in zip(t.shape, t.stride(), want))
+
+
 def as_nhwc(t: torch.Tensor) -> torch.Tensor:
     """Accept a foreign [N,C,H,W] tensor (e.g. a state handed back by the caller) and make sure its
     memory is NHWC fp32.  No copy when it already is."""
     if t.dtype != torch.float32:
         t = t.float()
     N, C, H, W = t.shape
-    if t.stride() == (H * W * C, 1, W * C, C):
+    if _is_nhwc(t):
         return t
     out = empty_nhwc(N, C, H, W, t.device)
     if t.is_contiguous():
@@ -62,8 +69,7 @@ def to_nchw_contiguous(t: torch.Tensor) -> torch.Tensor:
 
 
 def _check_nhwc(t: torch.Tensor, name: str):
-    N, C, H, W = t.shape
-    if t.dtype != torch.float32 or t.stride() != (H * W * C, 1, W * C, C):
+    if t.dim() != 4 or t.dtype != torch.float32 or not _is_nhwc(t):
         raise _lib.RamnetError(f'{name}: expected fp32 NHWC-strided [N,C,H,W] tensor, got {t.dtype} '
                                f'shape {tuple(t.shape)} strides {t.stride()}')
 
