@@ -183,9 +183,10 @@ int ramnet_si_loss_grad(ramnet_handle *h, const float *pred, const float *target
 /* ---- a-14  Adam --------------------------------------------------------- *
  * Replaces torch.optim.Adam.step (built at base/base_trainer.py:36-37,
  * stepped at trainer/lstm_trainer.py:453) with one multi-tensor launch over a
- * flat fp32 buffer.  step is 1-based; L2 weight decay as torch.optim.Adam. */
+ * flat fp32 buffer.  step is 1-based; L2 weight decay as torch.optim.Adam.  Hyper-parameters
+ * are doubles: torch derives 1-beta, the bias corrections and the step size in double. */
 int ramnet_adam_step(ramnet_handle *h, float *p, const float *g, float *m, float *v, int64_t n,
-                     float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                     double lr, double beta1, double beta2, double eps, double weight_decay, int step,
                      void *stream);
 
 #ifdef __cplusplus
