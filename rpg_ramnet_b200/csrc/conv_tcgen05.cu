@@ -22,6 +22,7 @@
 // warps 2-5 = epilogue (TMEM lane quarter = warp_id % 4).  mbarrier rings: full[s] (TMA ->
 // MMA), empty[s] (tcgen05.commit -> TMA), accum (last commit -> epilogue).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -259,6 +260,187 @@ __global__ void __launch_bounds__(kThreads) conv_tcgen05_kernel(const __grid_con
     }
 }
 
+
+// ================================================================================================
+// v2 "halo" kernel for stride-1 convolutions: tap reuse out of shared memory.
+//
+// The per-tap kernel above re-reads every input pixel ks*ks times from L2 and is pinned at the
+// ~12 TB/s L2->SM ceiling (profiles/r01_layers_v1_per_tap.txt).  Here one TMA box brings the
+// patch PLUS its halo, (8*PTX + ks-1) x (16*PTY + ks-1) pixels x 32 channels, into smem once per
+// 32-channel chunk, and all ks*ks taps are issued from it: the A operand of tap (r, s) for the
+// M-tile at (tx, ty) is the SAME buffer addressed through a descriptor whose start is shifted by
+// ((16*ty + r) * HX + 8*tx + s) pixel rows (128 B each) and whose 8-row-group stride (SBO) is one
+// halo row (HX * 128 B): an M-tile is 8 pixels wide (one swizzle atom) by 16 tall.
+// Up to 4 M-tiles share the halo and every weight tile (accumulators = ntiles * BN TMEM columns),
+// so weights are re-read 2-4x less often as well.
+//
+// Roles (256 threads): warp 0 = halo (A) producer, warp 1 = MMA issuer, warp 2 = weight (B)
+// producer, warp 3 = TMEM allocator, warps 4-7 = epilogue.
+// ================================================================================================
+struct HaloGeom {
+    int N, H, W, Cout;
+    int C0, C1;
+    int ks, pad;
+    int PTX, PTY;        // M-tiles per patch along x / y (tile = 8 x 16 pixels)
+    int HX, HY;          // halo buffer pitch (pixels) and rows
+    int patches_x, patches_y;
+    int BN;
+    int a_stages, b_stages;
+    int base_offset_mode;  // 1: descriptor base_offset = (start >> 7) & 7
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc_halo(uint32_t saddr, uint32_t sbo_bytes, int base_offset_mode) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    if (base_offset_mode) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(256) conv_tcgen05_halo_kernel(const __grid_constant__ CUtensorMap map_x0,
+                                                                const __grid_constant__ CUtensorMap map_x1,
+                                                                const __grid_constant__ CUtensorMap map_w, HaloGeom g,
+                                                                EpiParams ep) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int a_bytes = g.HX * g.HY * kChunk * 4;
+    const int a_stride = (a_bytes + 1023) & ~1023;
+    const int b_bytes = g.BN * kChunk * 4;
+    uint8_t *smem_b = smem + (size_t)g.a_stages * a_stride;
+    uint64_t *a_full = reinterpret_cast<uint64_t *>(smem_b + (size_t)g.b_stages * b_bytes);
+    uint64_t *a_empty = a_full + g.a_stages;
+    uint64_t *b_full = a_empty + g.a_stages;
+    uint64_t *b_empty = b_full + g.b_stages;
+    uint64_t *accum_bar = b_empty + g.b_stages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int t = blockIdx.x;
+    const int pxi = t % g.patches_x;
+    t /= g.patches_x;
+    const int pyi = t % g.patches_y;
+    const int img = t / g.patches_y;
+    const int x0 = pxi * g.PTX * 8, y0 = pyi * g.PTY * 16;
+    const int n0 = blockIdx.y * g.BN;
+    const int ntiles = g.PTX * g.PTY;
+    const int chunks0 = g.C0 / kChunk, chunks = (g.C0 + g.C1) / kChunk;
+    const int taps = g.ks * g.ks;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < ntiles * g.BN) tmem_cols <<= 1;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_x0);
+        prefetch_tmap(&map_x1);
+        prefetch_tmap(&map_w);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < g.a_stages; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
+        for (int s = 0; s < g.b_stages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 3) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------- halo producer: one box per 32-channel chunk ----------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int ch = 0; ch < chunks; ++ch) {
+                mbar_wait(a_empty + stage, phase ^ 1);
+                mbar_expect_tx(a_full + stage, (uint32_t)a_bytes);
+                const bool second = ch >= chunks0;
+                tma_load_4d(smem + (size_t)stage * a_stride, second ? &map_x1 : &map_x0, a_full + stage,
+                            (second ? ch - chunks0 : ch) * kChunk, x0 - g.pad, y0 - g.pad, img);
+                if (++stage == g.a_stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 2) {
+        // ---------------- weight producer: one [BN x 32] tile per (chunk, tap) ----------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int ch = 0; ch < chunks; ++ch) {
+                for (int tap = 0; tap < taps; ++tap) {
+                    mbar_wait(b_empty + stage, phase ^ 1);
+                    mbar_expect_tx(b_full + stage, (uint32_t)b_bytes);
+                    tma_load_3d(smem_b + (size_t)stage * b_bytes, &map_w, b_full + stage, ch * kChunk, n0, tap);
+                    if (++stage == g.b_stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(g.BN);
+            const uint32_t sbo = (uint32_t)g.HX * 128u;
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            for (int ch = 0; ch < chunks; ++ch) {
+                mbar_wait(a_full + sa, pa);
+                const uint32_t a_base = smem_u32(smem + (size_t)sa * a_stride);
+                for (int tap = 0; tap < taps; ++tap) {
+                    const int r = tap / g.ks, s = tap - r * g.ks;
+                    mbar_wait(b_full + sb, pb);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + (size_t)sb * b_bytes));
+                    for (int tl = 0; tl < ntiles; ++tl) {
+                        const int tx = tl % g.PTX, ty = tl / g.PTX;
+                        const uint32_t a_addr = a_base + (uint32_t)(((ty * 16 + r) * g.HX + tx * 8 + s) * 128);
+                        const uint64_t adesc = make_smem_desc_halo(a_addr, sbo, g.base_offset_mode);
+#pragma unroll
+                        for (int kk = 0; kk < kChunk / 8; ++kk)
+                            umma_tf32(tmem_base + (uint32_t)(tl * g.BN), adesc + 2 * kk, bdesc + 2 * kk, idesc,
+                                      (ch | tap | kk) != 0);
+                    }
+                    umma_commit(b_empty + sb);
+                    if (++sb == g.b_stages) { sb = 0; pb ^= 1; }
+                }
+                umma_commit(a_empty + sa);
+                if (++sa == g.a_stages) { sa = 0; pa ^= 1; }
+            }
+            umma_commit(accum_bar);
+        }
+    } else if (warp >= 4) {
+        // ---------------- epilogue ----------------
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;      // M row: 8 pixels along x per group, 16 groups along y
+        mbar_wait(accum_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int tl = 0; tl < ntiles; ++tl) {
+            const int tx = tl % g.PTX, ty = tl / g.PTX;
+            const int ox = x0 + tx * 8 + (row & 7), oy = y0 + ty * 16 + (row >> 3);
+            const bool valid = oy < g.H && ox < g.W;
+            const int64_t m = ((int64_t)img * g.H + oy) * g.W + ox;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tl * g.BN);
+            for (int c = 0; c < g.BN; c += 16) {
+                float v[16];
+                tmem_ld16(taddr + (uint32_t)c, v);
+                if (valid) epilogue_store<EPI, 16>(ep, m, n0 + c, v);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 3) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -314,6 +496,84 @@ int launch(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap &m1, const
     RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;
 }
+
+template <int EPI>
+int launch_halo(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap &m1, const CUtensorMap &mw,
+                const HaloGeom &g, const EpiParams &ep, cudaStream_t s) {
+    const size_t a_stride = ((size_t)g.HX * g.HY * kChunk * 4 + 1023) & ~(size_t)1023;
+    const size_t smem = g.a_stages * a_stride + (size_t)g.b_stages * g.BN * kChunk * 4 +
+                        (2 * g.a_stages + 2 * g.b_stages + 1) * 8 + 16 + 1024;
+    static size_t configured = 0;
+    if (smem > configured) {
+        RAMNET_CUDA(cudaFuncSetAttribute(conv_tcgen05_halo_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+        configured = smem;
+    }
+    dim3 grid((unsigned)(g.patches_x * g.patches_y * g.N), (unsigned)(g.Cout / g.BN));
+    conv_tcgen05_halo_kernel<EPI><<<grid, 256, smem, s>>>(m0, m1, mw, g, ep);
+    RAMNET_LAUNCH_CHECK(h);
+    return RAMNET_OK;
+}
+
+int halo_mode_env() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("RAMNET_HALO_MODE");
+        mode = e ? atoi(e) : 0;
+    }
+    return mode;
+}
+
+// Chooses patch shape, BN and pipeline depths for the halo kernel; returns false when the layer
+// should stay on the per-tap kernel (stride 2, 1x1, or no configuration fits shared memory).
+bool plan_halo(const ramnet_handle *h, const ramnet_conv_desc *d, HaloGeom *g) {
+    const int mode = halo_mode_env();
+    if (mode & 4) return false;                      // RAMNET_HALO_MODE bit 2: force the per-tap kernel
+    if (d->stride != 1 || d->ksize == 1) return false;
+    g->N = d->N; g->H = d->H; g->W = d->W; g->Cout = d->Cout; g->C0 = d->C0; g->C1 = d->C1;
+    g->ks = d->ksize; g->pad = d->ksize / 2;
+    g->base_offset_mode = mode & 1;
+    const bool pad8 = (mode & 2) != 0;
+    const size_t budget = 200 * 1024;
+    double best_score = -1;
+    bool found = false;
+    static const int shapes[][2] = {{2, 1}, {1, 1}, {4, 1}, {2, 2}, {1, 2}};
+    for (const auto &sh : shapes) {
+        for (int bn = 256; bn >= 16; bn >>= 1) {
+            if (d->Cout % bn) continue;
+            const int ntiles = sh[0] * sh[1];
+            if (ntiles * bn > 512) continue;
+            int hx = sh[0] * 8 + d->ksize - 1;
+            if (pad8) hx = (hx + 7) & ~7;
+            const int hy = sh[1] * 16 + d->ksize - 1;
+            if (hx > 256 || hy > 256) continue;
+            const size_t a_stride = ((size_t)hx * hy * kChunk * 4 + 1023) & ~(size_t)1023;
+            const size_t b_bytes = (size_t)bn * kChunk * 4;
+            const int a_st = 2;
+            int b_st = (int)((budget - a_st * a_stride) / b_bytes);
+            if (budget < a_st * a_stride || b_st < 2) continue;
+            if (b_st > 8) b_st = 8;
+            const int px = (d->W + sh[0] * 8 - 1) / (sh[0] * 8), py = (d->H + sh[1] * 16 - 1) / (sh[1] * 16);
+            const int64_t ctas = (int64_t)px * py * d->N * (d->Cout / bn);
+            // bytes moved from L2 per useful output pixel and chunk (halo + weights), waste for ragged edges,
+            // and SM fill: score = useful flops per byte x wave efficiency
+            const double pix = (double)d->W * d->H * d->N;
+            const double cov = (double)px * py * d->N * ntiles * 128.0;
+            const double bytes = (double)hx * hy * 128.0 * (d->Cout / bn) / (ntiles * 128.0) +
+                                 (double)d->ksize * d->ksize * bn * 128.0 * (d->Cout / bn) / (ntiles * 128.0);
+            const double waves = (double)ctas / h->sm_count;
+            const double fill = waves / (double)((int64_t)(waves + 0.999999));
+            const double score = (pix / cov) * fill / bytes;
+            if (score > best_score) {
+                best_score = score;
+                g->PTX = sh[0]; g->PTY = sh[1]; g->HX = hx; g->HY = hy; g->BN = bn;
+                g->a_stages = a_st; g->b_stages = b_st; g->patches_x = px; g->patches_y = py;
+                found = true;
+            }
+        }
+    }
+    return found;
+}
 }  // namespace
 
 size_t conv_tf32_workspace_bytes(const ramnet_conv_desc *) { return 0; }
@@ -325,6 +585,38 @@ int conv_fwd_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *x0, 
     RAMNET_CHECK_ARG(d->Cout % 16 == 0, "conv_fwd(tf32): Cout=%d must be a multiple of 16", d->Cout);
     RAMNET_CHECK_ARG(d->stride == 1 || (d->H % 2 == 0 && d->W % 2 == 0), "conv_fwd(tf32): stride 2 needs even H, W");
     RAMNET_CHECK_ARG((((uintptr_t)x0 | (uintptr_t)x1 | (uintptr_t)wp) & 15) == 0, "conv_fwd(tf32): 16-byte alignment");
+    HaloGeom hg;
+    if (plan_halo(h, d, &hg)) {
+        CUtensorMap m0, m1, mw;
+        cuuint32_t box[4] = {kChunk, (cuuint32_t)hg.HX, (cuuint32_t)hg.HY, 1};
+        auto enc_act = [&](CUtensorMap *m, const float *x, int C) {
+            cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+            cuuint64_t str[3] = {(cuuint64_t)C * 4, (cuuint64_t)d->W * C * 4, (cuuint64_t)d->H * d->W * C * 4};
+            return encode(h, m, x, 4, dims, str, box);
+        };
+        int rc = enc_act(&m0, x0, d->C0);
+        if (rc) return rc;
+        if (x1) {
+            rc = enc_act(&m1, x1, d->C1);
+            if (rc) return rc;
+        } else {
+            m1 = m0;
+        }
+        const int Ct = d->C0 + d->C1, taps = d->ksize * d->ksize;
+        cuuint64_t wd[3] = {(cuuint64_t)Ct, (cuuint64_t)d->Cout, (cuuint64_t)taps};
+        cuuint64_t ws[2] = {(cuuint64_t)Ct * 4, (cuuint64_t)Ct * d->Cout * 4};
+        cuuint32_t wb[3] = {kChunk, (cuuint32_t)hg.BN, 1};
+        rc = encode(h, &mw, wp, 3, wd, ws, wb);
+        if (rc) return rc;
+        switch (d->epilogue) {
+            case RAMNET_EPI_BIAS: return launch_halo<RAMNET_EPI_BIAS>(h, m0, m1, mw, hg, ep, s);
+            case RAMNET_EPI_BIAS_RELU: return launch_halo<RAMNET_EPI_BIAS_RELU>(h, m0, m1, mw, hg, ep, s);
+            case RAMNET_EPI_BIAS_RES_RELU: return launch_halo<RAMNET_EPI_BIAS_RES_RELU>(h, m0, m1, mw, hg, ep, s);
+            case RAMNET_EPI_GRU_RU: return launch_halo<RAMNET_EPI_GRU_RU>(h, m0, m1, mw, hg, ep, s);
+            case RAMNET_EPI_GRU_OUT: return launch_halo<RAMNET_EPI_GRU_OUT>(h, m0, m1, mw, hg, ep, s);
+            case RAMNET_EPI_LSTM: return launch_halo<RAMNET_EPI_LSTM>(h, m0, m1, mw, hg, ep, s);
+        }
+    }
     TcGeom g;
     g.N = d->N; g.Cout = d->Cout; g.C0 = d->C0; g.C1 = d->C1;
     g.ks = d->ksize; g.stride = d->stride; g.pad = d->ksize / 2;
