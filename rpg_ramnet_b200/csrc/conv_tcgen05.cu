@@ -47,6 +47,18 @@ struct TcGeom {
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a fully-converged warp (deterministic leader): control flow stays warp-uniform so the
+// compiler keeps descriptors in uniform registers and emits a single predicated UTCHMMA / UTMALDG.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -189,52 +201,56 @@ __global__ void __launch_bounds__(kThreads) conv_tcgen05_kernel(const __grid_con
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tap = 0; tap < g.ks * g.ks; ++tap) {
-                const int r = tap / g.ks, s = tap % g.ks;
+        // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int r = 0; r < g.ks; ++r) {
+            for (int s = 0; s < g.ks; ++s) {
+                const int tap = r * g.ks + s;
                 for (int ch = 0; ch < chunks; ++ch) {
                     mbar_wait(empty_bar + stage, phase ^ 1);
-                    uint8_t *sa = smem + (size_t)stage * stage_bytes;
-                    uint8_t *sb = sa + kABytes;
-                    mbar_expect_tx(full_bar + stage, (uint32_t)stage_bytes);
-                    const bool second = ch >= chunks0;
-                    const CUtensorMap *mx = second ? &map_x1 : &map_x0;
-                    const int c = (second ? ch - chunks0 : ch) * kChunk;
-                    if (g.stride == 1) {
-                        tma_load_4d(sa, mx, full_bar + stage, c, x0 + s - g.pad, y0 + r - g.pad, img);
-                    } else {
-                        // input row 2*oy + (r - pad) = 2*(oy + dy) + py, likewise for columns
-                        const int ry = r - g.pad, rx = s - g.pad;
-                        const int dy = ry >> 1, py = ry & 1, dx = rx >> 1, px = rx & 1;  // arithmetic shift = floor
-                        const int Csrc = second ? g.C1 : g.C0;
-                        tma_load_5d(sa, mx, full_bar + stage, px * Csrc + c, x0 + dx, py, y0 + dy, img);
+                    if (elect_one()) {
+                        uint8_t *sa = smem + (size_t)stage * stage_bytes;
+                        uint8_t *sb = sa + kABytes;
+                        mbar_expect_tx(full_bar + stage, (uint32_t)stage_bytes);
+                        const bool second = ch >= chunks0;
+                        const CUtensorMap *mx = second ? &map_x1 : &map_x0;
+                        const int c = (second ? ch - chunks0 : ch) * kChunk;
+                        if (g.stride == 1) {
+                            tma_load_4d(sa, mx, full_bar + stage, c, x0 + s - g.pad, y0 + r - g.pad, img);
+                        } else {
+                            // input row 2*oy + (r - pad) = 2*(oy + dy) + py, likewise for columns
+                            const int ry = r - g.pad, rx = s - g.pad;
+                            const int dy = ry >> 1, py = ry & 1, dx = rx >> 1, px = rx & 1;  // arithmetic shift = floor
+                            const int Csrc = second ? g.C1 : g.C0;
+                            tma_load_5d(sa, mx, full_bar + stage, px * Csrc + c, x0 + dx, py, y0 + dy, img);
+                        }
+                        tma_load_3d(sb, &map_w, full_bar + stage, ch * kChunk, n0, tap);
                     }
-                    tma_load_3d(sb, &map_w, full_bar + stage, ch * kChunk, n0, tap);
+                    __syncwarp();
                     if (++stage == g.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(g.BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int k = 0; k < ksteps; ++k) {
-                mbar_wait(full_bar + stage, phase);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + kABytes);
+        // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+        const uint32_t idesc = make_idesc_tf32(g.BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int k = 0; k < ksteps; ++k) {
+            mbar_wait(full_bar + stage, phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + kABytes);
+            if (elect_one()) {
 #pragma unroll
                 for (int kk = 0; kk < kChunk / 8; ++kk)  // 8 tf32 = 32 bytes per UMMA K-step: +2 in the >>4 address field
                     umma_tf32(tmem_base, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0);
                 umma_commit(empty_bar + stage);  // frees the smem slot once these MMAs have read it
-                if (++stage == g.stages) { stage = 0; phase ^= 1; }
+                if (k == ksteps - 1) umma_commit(accum_bar);  // accumulator complete
             }
-            umma_commit(accum_bar);  // accumulator complete
+            __syncwarp();
+            if (++stage == g.stages) { stage = 0; phase ^= 1; }
         }
     } else {
         // ===================== epilogue: TMEM -> registers -> fused math -> global =====================
@@ -286,19 +302,7 @@ struct HaloGeom {
     int patches_x, patches_y;
     int BN;
     int a_stages, b_stages;
-    int base_offset_mode;  // 1: descriptor base_offset = (start >> 7) & 7
 };
-
-__device__ __forceinline__ uint64_t make_smem_desc_halo(uint32_t saddr, uint32_t sbo_bytes, int base_offset_mode) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(sbo_bytes >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    if (base_offset_mode) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
 
 template <int EPI>
 __global__ void __launch_bounds__(256) conv_tcgen05_halo_kernel(const __grid_constant__ CUtensorMap map_x0,
@@ -356,63 +360,82 @@ __global__ void __launch_bounds__(256) conv_tcgen05_halo_kernel(const __grid_con
 
     if (warp == 0) {
         // ---------------- halo producer: one box per 32-channel chunk ----------------
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int ch = 0; ch < chunks; ++ch) {
-                mbar_wait(a_empty + stage, phase ^ 1);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int ch = 0; ch < chunks; ++ch) {
+            mbar_wait(a_empty + stage, phase ^ 1);
+            if (elect_one()) {
                 mbar_expect_tx(a_full + stage, (uint32_t)a_bytes);
                 const bool second = ch >= chunks0;
                 tma_load_4d(smem + (size_t)stage * a_stride, second ? &map_x1 : &map_x0, a_full + stage,
                             (second ? ch - chunks0 : ch) * kChunk, x0 - g.pad, y0 - g.pad, img);
-                if (++stage == g.a_stages) { stage = 0; phase ^= 1; }
             }
+            __syncwarp();
+            if (++stage == g.a_stages) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 2) {
         // ---------------- weight producer: one [BN x 32] tile per (chunk, tap) ----------------
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int ch = 0; ch < chunks; ++ch) {
-                for (int tap = 0; tap < taps; ++tap) {
-                    mbar_wait(b_empty + stage, phase ^ 1);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int ch = 0; ch < chunks; ++ch) {
+            for (int tap = 0; tap < taps; ++tap) {
+                mbar_wait(b_empty + stage, phase ^ 1);
+                if (elect_one()) {
                     mbar_expect_tx(b_full + stage, (uint32_t)b_bytes);
                     tma_load_3d(smem_b + (size_t)stage * b_bytes, &map_w, b_full + stage, ch * kChunk, n0, tap);
-                    if (++stage == g.b_stages) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == g.b_stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ---------------- MMA issuer ----------------
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(g.BN);
-            const uint32_t sbo = (uint32_t)g.HX * 128u;
-            int sa = 0, sb = 0;
-            uint32_t pa = 0, pb = 0;
-            for (int ch = 0; ch < chunks; ++ch) {
-                mbar_wait(a_full + sa, pa);
-                const uint32_t a_base = smem_u32(smem + (size_t)sa * a_stride);
-                for (int tap = 0; tap < taps; ++tap) {
-                    const int r = tap / g.ks, s = tap - r * g.ks;
+        // ---------------- MMA issuer: warp-uniform loops, no divisions, one elected lane issues ----------------
+        const uint32_t idesc = make_idesc_tf32(g.BN);
+        // descriptor bits above the 14-bit start-address field: LBO=16 B, SBO = one halo row, version 1, SWIZZLE_128B
+        const uint64_t a_hi = ((uint64_t)1 << 16) | ((uint64_t)((uint32_t)g.HX * 128u >> 4) << 32) | ((uint64_t)1 << 46) |
+                              ((uint64_t)2 << 61);
+        uint32_t tile_off16[4];   // (tile origin inside the halo buffer) / 16 bytes
+#pragma unroll
+        for (int tl = 0; tl < 4; ++tl) {
+            const int tx = tl % g.PTX, ty = tl / g.PTX;
+            tile_off16[tl] = (uint32_t)((ty * 16 * g.HX + tx * 8) * 8);
+        }
+        int sa = 0, sb = 0;
+        uint32_t pa = 0, pb = 0;
+        for (int ch = 0; ch < chunks; ++ch) {
+            mbar_wait(a_full + sa, pa);
+            const uint32_t a16 = (smem_u32(smem + (size_t)sa * a_stride) & 0x3FFFFu) >> 4;
+            uint32_t row16 = 0;   // (r * HX) * 8
+            for (int r = 0; r < g.ks; ++r, row16 += (uint32_t)g.HX * 8u) {
+                for (int sx = 0; sx < g.ks; ++sx) {
                     mbar_wait(b_full + sb, pb);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + (size_t)sb * b_bytes));
-                    for (int tl = 0; tl < ntiles; ++tl) {
-                        const int tx = tl % g.PTX, ty = tl / g.PTX;
-                        const uint32_t a_addr = a_base + (uint32_t)(((ty * 16 + r) * g.HX + tx * 8 + s) * 128);
-                        const uint64_t adesc = make_smem_desc_halo(a_addr, sbo, g.base_offset_mode);
+                    const uint32_t tap16 = a16 + row16 + (uint32_t)sx * 8u;
+                    const uint32_t first = (uint32_t)(ch | r | sx);
+                    if (elect_one()) {
 #pragma unroll
-                        for (int kk = 0; kk < kChunk / 8; ++kk)
-                            umma_tf32(tmem_base + (uint32_t)(tl * g.BN), adesc + 2 * kk, bdesc + 2 * kk, idesc,
-                                      (ch | tap | kk) != 0);
+                        for (int tl = 0; tl < 4; ++tl) {
+                            if (tl < ntiles) {
+                                const uint64_t adesc = a_hi | (uint64_t)(tap16 + tile_off16[tl]);
+#pragma unroll
+                                for (int kk = 0; kk < kChunk / 8; ++kk)
+                                    umma_tf32(tmem_base + (uint32_t)(tl * g.BN), adesc + 2 * kk, bdesc + 2 * kk, idesc,
+                                              (first | (uint32_t)kk) != 0);
+                            }
+                        }
+                        umma_commit(b_empty + sb);
                     }
-                    umma_commit(b_empty + sb);
+                    __syncwarp();
                     if (++sb == g.b_stages) { sb = 0; pb ^= 1; }
                 }
-                umma_commit(a_empty + sa);
-                if (++sa == g.a_stages) { sa = 0; pa ^= 1; }
             }
-            umma_commit(accum_bar);
+            if (elect_one()) {
+                umma_commit(a_empty + sa);
+                if (ch == chunks - 1) umma_commit(accum_bar);
+            }
+            __syncwarp();
+            if (++sa == g.a_stages) { sa = 0; pa ^= 1; }
         }
     } else if (warp >= 4) {
         // ---------------- epilogue ----------------
@@ -532,11 +555,21 @@ bool plan_halo(const ramnet_handle *h, const ramnet_conv_desc *d, HaloGeom *g) {
     if (d->stride != 1 || d->ksize == 1) return false;
     g->N = d->N; g->H = d->H; g->W = d->W; g->Cout = d->Cout; g->C0 = d->C0; g->C1 = d->C1;
     g->ks = d->ksize; g->pad = d->ksize / 2;
-    g->base_offset_mode = mode & 1;
-    const bool pad8 = (mode & 2) != 0;
     const size_t budget = 200 * 1024;
     double best_score = -1;
     bool found = false;
+    if (const char *f = getenv("RAMNET_HALO_FORCE")) {   // tuning aid: "PTX,PTY,BN,a_stages,b_stages"
+        int ptx, pty, bn, ast, bst;
+        if (sscanf(f, "%d,%d,%d,%d,%d", &ptx, &pty, &bn, &ast, &bst) == 5 && d->Cout % bn == 0 && ptx * pty * bn <= 512 &&
+            ptx * pty <= 4) {
+            g->PTX = ptx; g->PTY = pty; g->BN = bn; g->a_stages = ast; g->b_stages = bst;
+            g->HX = ptx * 8 + d->ksize - 1; g->HY = pty * 16 + d->ksize - 1;
+            g->patches_x = (d->W + ptx * 8 - 1) / (ptx * 8); g->patches_y = (d->H + pty * 16 - 1) / (pty * 16);
+            const size_t need = ast * (((size_t)g->HX * g->HY * kChunk * 4 + 1023) & ~(size_t)1023) +
+                                (size_t)bst * bn * kChunk * 4 + 4096;
+            if (need <= 227 * 1024) return true;
+        }
+    }
     static const int shapes[][2] = {{2, 1}, {1, 1}, {4, 1}, {2, 2}, {1, 2}};
     for (const auto &sh : shapes) {
         for (int bn = 256; bn >= 16; bn >>= 1) {
@@ -544,7 +577,6 @@ bool plan_halo(const ramnet_handle *h, const ramnet_conv_desc *d, HaloGeom *g) {
             const int ntiles = sh[0] * sh[1];
             if (ntiles * bn > 512) continue;
             int hx = sh[0] * 8 + d->ksize - 1;
-            if (pad8) hx = (hx + 7) & ~7;
             const int hy = sh[1] * 16 + d->ksize - 1;
             if (hx > 256 || hy > 256) continue;
             const size_t a_stride = ((size_t)hx * hy * kChunk * 4 + 1023) & ~(size_t)1023;
@@ -587,6 +619,10 @@ int conv_fwd_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *x0, 
     RAMNET_CHECK_ARG((((uintptr_t)x0 | (uintptr_t)x1 | (uintptr_t)wp) & 15) == 0, "conv_fwd(tf32): 16-byte alignment");
     HaloGeom hg;
     if (plan_halo(h, d, &hg)) {
+        if (getenv("RAMNET_DEBUG"))
+            fprintf(stderr, "[ramnet] halo plan %dx%d C=%d+%d->%d k%d: tiles %dx%d HX=%d HY=%d BN=%d a_st=%d b_st=%d grid=%dx%d\n",
+                    d->H, d->W, d->C0, d->C1, d->Cout, d->ksize, hg.PTX, hg.PTY, hg.HX, hg.HY, hg.BN, hg.a_stages,
+                    hg.b_stages, hg.patches_x * hg.patches_y * hg.N, hg.Cout / hg.BN);
         CUtensorMap m0, m1, mw;
         cuuint32_t box[4] = {kChunk, (cuuint32_t)hg.HX, (cuuint32_t)hg.HY, 1};
         auto enc_act = [&](CUtensorMap *m, const float *x, int C) {
