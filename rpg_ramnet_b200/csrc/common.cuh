@@ -58,17 +58,58 @@ struct EpiParams {
     int flags;  // RAMNET_FLAG_*
 };
 
-// Stores NV consecutive GEMM columns [n0, n0+NV) of output pixel m.  NV is a multiple of 4,
-// n0 a multiple of NV, so every access below is a 16-byte vector access.
+// The epilogue of NV consecutive GEMM columns [n0, n0+NV) of output pixel m, in two phases so that
+// callers can software-pipeline it: `epilogue_prefetch` issues every global load the epilogue needs
+// (bias, residual / h / u / c) into registers, `epilogue_finish` does the math and the stores.
+// NV is a multiple of 4 and n0 a multiple of NV, so every access is a 16-byte vector access.
+template <int NV>
+struct EpiAux {
+    float4 bias[NV / 4];
+    float4 a[NV / 4];   // aux0: residual / h / c_prev (LSTM uses the first NV/4 scalars)
+    float4 b[NV / 4];   // aux1: u
+};
+
 template <int EPI, int NV>
-__device__ __forceinline__ void epilogue_store(const EpiParams &p, int64_t m, int n0, float (&v)[NV]) {
+__device__ __forceinline__ void epilogue_prefetch(const EpiParams &p, int64_t m, int n0, EpiAux<NV> &x) {
     static_assert(NV % 4 == 0, "NV must be a multiple of 4");
-    if (p.bias != nullptr) {
 #pragma unroll
-        for (int j = 0; j < NV; j += 4) {
-            float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + n0 + j));
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    for (int j = 0; j < NV / 4; ++j)
+        x.bias[j] = p.bias ? __ldg(reinterpret_cast<const float4 *>(p.bias + n0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (EPI == RAMNET_EPI_BIAS_RES_RELU) {
+#pragma unroll
+        for (int j = 0; j < NV / 4; ++j) x.a[j] = *(reinterpret_cast<const float4 *>(p.aux0 + m * p.Cout + n0) + j);
+    } else if constexpr (EPI == RAMNET_EPI_GRU_RU) {
+        const int C = p.Cout >> 1;
+        if (n0 < C) {
+#pragma unroll
+            for (int j = 0; j < NV / 4; ++j) x.a[j] = *(reinterpret_cast<const float4 *>(p.aux0 + m * C + n0) + j);
         }
+    } else if constexpr (EPI == RAMNET_EPI_GRU_OUT) {
+#pragma unroll
+        for (int j = 0; j < NV / 4; ++j) {
+            x.a[j] = *(reinterpret_cast<const float4 *>(p.aux0 + m * p.Cout + n0) + j);
+            x.b[j] = *(reinterpret_cast<const float4 *>(p.aux1 + m * p.Cout + n0) + j);
+        }
+    } else if constexpr (EPI == RAMNET_EPI_LSTM) {
+        const int C = p.Cout >> 2;
+        const float *cp = p.aux0 + m * C + (n0 >> 2);
+        if constexpr (NV % 16 == 0) {
+#pragma unroll
+            for (int j = 0; j < NV / 16; ++j) x.a[j] = *(reinterpret_cast<const float4 *>(cp) + j);
+        } else {
+            float *dst = reinterpret_cast<float *>(&x.a[0]);
+#pragma unroll
+            for (int q = 0; q < NV / 4; ++q) dst[q] = cp[q];
+        }
+    }
+}
+
+template <int EPI, int NV>
+__device__ __forceinline__ void epilogue_finish(const EpiParams &p, int64_t m, int n0, float (&v)[NV],
+                                                const EpiAux<NV> &x) {
+#pragma unroll
+    for (int j = 0; j < NV / 4; ++j) {
+        v[4 * j] += x.bias[j].x; v[4 * j + 1] += x.bias[j].y; v[4 * j + 2] += x.bias[j].z; v[4 * j + 3] += x.bias[j].w;
     }
     const bool rnd = (p.flags & RAMNET_FLAG_ROUND_TF32) != 0;
     auto st4 = [&](float *dst, float a, float b, float c, float d) {
@@ -86,7 +127,7 @@ __device__ __forceinline__ void epilogue_store(const EpiParams &p, int64_t m, in
     } else if constexpr (EPI == RAMNET_EPI_BIAS_RES_RELU) {
 #pragma unroll
         for (int j = 0; j < NV; j += 4) {
-            float4 r = *reinterpret_cast<const float4 *>(p.aux0 + m * p.Cout + n0 + j);
+            const float4 r = x.a[j / 4];
             st4(p.y0 + m * p.Cout + n0 + j, fmaxf(v[j] + r.x, 0.f), fmaxf(v[j + 1] + r.y, 0.f),
                 fmaxf(v[j + 2] + r.z, 0.f), fmaxf(v[j + 3] + r.w, 0.f));
         }
@@ -95,7 +136,7 @@ __device__ __forceinline__ void epilogue_store(const EpiParams &p, int64_t m, in
         if (n0 < C) {  // reset gate -> y1 = h * r
 #pragma unroll
             for (int j = 0; j < NV; j += 4) {
-                float4 h = *reinterpret_cast<const float4 *>(p.aux0 + m * C + n0 + j);
+                const float4 h = x.a[j / 4];
                 st4(p.y1 + m * C + n0 + j, h.x * sigmoidf_(v[j]), h.y * sigmoidf_(v[j + 1]),
                     h.z * sigmoidf_(v[j + 2]), h.w * sigmoidf_(v[j + 3]));
             }
@@ -108,30 +149,44 @@ __device__ __forceinline__ void epilogue_store(const EpiParams &p, int64_t m, in
     } else if constexpr (EPI == RAMNET_EPI_GRU_OUT) {
 #pragma unroll
         for (int j = 0; j < NV; j += 4) {
-            float4 h = *reinterpret_cast<const float4 *>(p.aux0 + m * p.Cout + n0 + j);
-            float4 u = *reinterpret_cast<const float4 *>(p.aux1 + m * p.Cout + n0 + j);
+            const float4 h = x.a[j / 4], u = x.b[j / 4];
             st4(p.y0 + m * p.Cout + n0 + j, h.x * (1.f - u.x) + tanhf(v[j]) * u.x,
                 h.y * (1.f - u.y) + tanhf(v[j + 1]) * u.y, h.z * (1.f - u.z) + tanhf(v[j + 2]) * u.z,
                 h.w * (1.f - u.w) + tanhf(v[j + 3]) * u.w);
         }
     } else if constexpr (EPI == RAMNET_EPI_LSTM) {
         const int C = p.Cout >> 2;
+        const float *cprev = reinterpret_cast<const float *>(&x.a[0]);
         float hn[NV / 4], cn[NV / 4];
 #pragma unroll
         for (int q = 0; q < NV / 4; ++q) {
-            const float cp = p.aux0[m * C + (n0 >> 2) + q];
             const float gi = sigmoidf_(v[4 * q]), gf = sigmoidf_(v[4 * q + 1]);
             const float go = sigmoidf_(v[4 * q + 2]), gc = tanhf(v[4 * q + 3]);
-            cn[q] = gf * cp + gi * gc;
+            cn[q] = gf * cprev[q] + gi * gc;
             hn[q] = go * tanhf(cn[q]);
             if (rnd) hn[q] = round_tf32(hn[q]);
         }
+        if constexpr (NV % 16 == 0) {
 #pragma unroll
-        for (int q = 0; q < NV / 4; ++q) {
-            p.y0[m * C + (n0 >> 2) + q] = hn[q];
-            p.y1[m * C + (n0 >> 2) + q] = cn[q];
+            for (int q = 0; q < NV / 4; q += 4) {
+                *reinterpret_cast<float4 *>(p.y0 + m * C + (n0 >> 2) + q) = make_float4(hn[q], hn[q + 1], hn[q + 2], hn[q + 3]);
+                *reinterpret_cast<float4 *>(p.y1 + m * C + (n0 >> 2) + q) = make_float4(cn[q], cn[q + 1], cn[q + 2], cn[q + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < NV / 4; ++q) {
+                p.y0[m * C + (n0 >> 2) + q] = hn[q];
+                p.y1[m * C + (n0 >> 2) + q] = cn[q];
+            }
         }
     }
+}
+
+template <int EPI, int NV>
+__device__ __forceinline__ void epilogue_store(const EpiParams &p, int64_t m, int n0, float (&v)[NV]) {
+    EpiAux<NV> x;
+    epilogue_prefetch<EPI, NV>(p, m, n0, x);
+    epilogue_finish<EPI, NV>(p, m, n0, v, x);
 }
 
 static inline int conv_out_dim(int in, int stride) { return (in - 1) / stride + 1; }

@@ -278,37 +278,81 @@ __global__ void __launch_bounds__(kThreads) conv_tcgen05_kernel(const __grid_con
 
 
 // ================================================================================================
-// v2 "halo" kernel for stride-1 convolutions: tap reuse out of shared memory.
+// Persistent "halo" kernel for stride-1 convolutions: tap reuse out of shared memory.
 //
 // The per-tap kernel above re-reads every input pixel ks*ks times from L2 and is pinned at the
-// ~12 TB/s L2->SM ceiling (profiles/r01_layers_v1_per_tap.txt).  Here one TMA box brings the
-// patch PLUS its halo, (8*PTX + ks-1) x (16*PTY + ks-1) pixels x 32 channels, into smem once per
-// 32-channel chunk, and all ks*ks taps are issued from it: the A operand of tap (r, s) for the
-// M-tile at (tx, ty) is the SAME buffer addressed through a descriptor whose start is shifted by
-// ((16*ty + r) * HX + 8*tx + s) pixel rows (128 B each) and whose 8-row-group stride (SBO) is one
-// halo row (HX * 128 B): an M-tile is 8 pixels wide (one swizzle atom) by 16 tall.
-// Up to 4 M-tiles share the halo and every weight tile (accumulators = ntiles * BN TMEM columns),
-// so weights are re-read 2-4x less often as well.
+// ~15 TB/s L2->SM ceiling (profiles/r01_layers_v1_per_tap.txt, ncu: l1tex__m_xbar2l1tex_read_bytes).
+// Here one TMA box brings the patch PLUS its halo, (8*PTX + ks-1) x (16*PTY + ks-1) pixels x 32
+// channels, into smem once per 32-channel chunk, and all ks*ks taps are issued from it: the A operand
+// of tap (r, s) for the M-tile at (tx, ty) is the SAME buffer addressed through a descriptor whose
+// start is shifted by ((16*ty + r) * HX + 8*tx + s) pixel rows (128 B each) and whose 8-row-group
+// stride (SBO) is one halo row (HX * 128 B): an M-tile is 8 pixels wide (one swizzle atom) by 16 tall.
+// This works because the 128B swizzle of both TMA and tcgen05.mma is a function of the ABSOLUTE
+// shared-memory address bits (measured: any 128-byte-aligned start and any SBO multiple of 128 B read
+// back what TMA wrote; the descriptor's base_offset field must stay 0), and it costs nothing
+// (tools/microbench/umma_rate.cu: 40/48/64/128 cycles per 128xNx8 MMA for N = 32/64/128/256 either way).
+// Up to 4 M-tiles share the halo and every weight tile, so weights are re-read 2-4x less often too.
 //
-// Roles (256 threads): warp 0 = halo (A) producer, warp 1 = MMA issuer, warp 2 = weight (B)
-// producer, warp 3 = TMEM allocator, warps 4-7 = epilogue.
+// Persistent: one CTA per SM walks work items (patch, Cout slice) round-robin.  Accumulators are
+// double-buffered in TMEM (2 x ntiles x BN columns) so the fused epilogue of item i runs under the
+// MMAs of item i+1.  Roles (384 threads): warp 0 = halo (A) producer, warp 1 = MMA issuer,
+// warp 2 = weight (B) producer, warp 3 = TMEM allocator, warps 4-11 = epilogue (TMEM lane quarter =
+// warp % 4, two warps per quarter split the 16-column chunks).  The epilogue is software-pipelined:
+// the tcgen05.ld and the global aux loads (bias, h, u, c, residual) of chunk k+1 are in flight while
+// chunk k is computed and stored.
 // ================================================================================================
 struct HaloGeom {
     int N, H, W, Cout;
     int C0, C1;
     int ks, pad;
-    int PTX, PTY;        // M-tiles per patch along x / y (tile = 8 x 16 pixels)
-    int HX, HY;          // halo buffer pitch (pixels) and rows
+    int PTX, PTY, ptx_log2;  // M-tiles per patch along x / y (tile = 8 x 16 pixels); PTX is a power of two
+    int HX, HY;              // halo buffer pitch (pixels) and rows
     int patches_x, patches_y;
-    int BN;
+    int BN, n_slices;        // GEMM columns per item, Cout / BN
     int a_stages, b_stages;
+    int nbuf;                // TMEM accumulator buffers
+    int items;               // patches * n_slices
+    unsigned long long *prof; // RAMNET_PROF=1: per-role wait-cycle counters (debug), else nullptr
 };
 
+constexpr int kHaloThreads = 384;
+constexpr int kEpiWarps = 8;
+
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+        "[%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+// The "+r" operands make every later use of the loaded registers depend on the wait.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait_t(uint64_t *bar, uint32_t parity, bool prof, unsigned long long &acc) {
+    if (prof) {
+        const long long t0 = clock64();
+        mbar_wait(bar, parity);
+        acc += (unsigned long long)(clock64() - t0);
+    } else {
+        mbar_wait(bar, parity);
+    }
+}
+
 template <int EPI>
-__global__ void __launch_bounds__(256) conv_tcgen05_halo_kernel(const __grid_constant__ CUtensorMap map_x0,
-                                                                const __grid_constant__ CUtensorMap map_x1,
-                                                                const __grid_constant__ CUtensorMap map_w, HaloGeom g,
-                                                                EpiParams ep) {
+__global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(const __grid_constant__ CUtensorMap map_x0,
+                                                                            const __grid_constant__ CUtensorMap map_x1,
+                                                                            const __grid_constant__ CUtensorMap map_w,
+                                                                            HaloGeom g, EpiParams ep) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int a_bytes = g.HX * g.HY * kChunk * 4;
@@ -319,22 +363,18 @@ __global__ void __launch_bounds__(256) conv_tcgen05_halo_kernel(const __grid_con
     uint64_t *a_empty = a_full + g.a_stages;
     uint64_t *b_full = a_empty + g.a_stages;
     uint64_t *b_empty = b_full + g.b_stages;
-    uint64_t *accum_bar = b_empty + g.b_stages;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
+    uint64_t *acc_full = b_empty + g.b_stages;   // [2]
+    uint64_t *acc_empty = acc_full + 2;          // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int t = blockIdx.x;
-    const int pxi = t % g.patches_x;
-    t /= g.patches_x;
-    const int pyi = t % g.patches_y;
-    const int img = t / g.patches_y;
-    const int x0 = pxi * g.PTX * 8, y0 = pyi * g.PTY * 16;
-    const int n0 = blockIdx.y * g.BN;
     const int ntiles = g.PTX * g.PTY;
     const int chunks0 = g.C0 / kChunk, chunks = (g.C0 + g.C1) / kChunk;
     const int taps = g.ks * g.ks;
+    const int patches = g.patches_x * g.patches_y * g.N;
+    const int acc_cols = ntiles * g.BN;          // TMEM columns of one accumulator buffer
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < ntiles * g.BN) tmem_cols <<= 1;
+    while ((int)tmem_cols < g.nbuf * acc_cols) tmem_cols <<= 1;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_x0);
@@ -344,7 +384,7 @@ __global__ void __launch_bounds__(256) conv_tcgen05_halo_kernel(const __grid_con
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < g.a_stages; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
         for (int s = 0; s < g.b_stages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
-        mbar_init(accum_bar, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 3) {
@@ -358,36 +398,62 @@ __global__ void __launch_bounds__(256) conv_tcgen05_halo_kernel(const __grid_con
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
+    const bool prof = g.prof != nullptr;
+    unsigned long long w0 = 0, w1 = 0, w2 = 0;
+    const long long t_start = clock64();
+
+    // item -> (Cout slice, image, patch origin); consecutive items share the weight slice (L2 reuse)
+    auto decode = [&](int item, int &n0, int &img, int &x0, int &y0) {
+        const int slice = item / patches;
+        int t = item - slice * patches;
+        const int pxi = t % g.patches_x;
+        t /= g.patches_x;
+        const int pyi = t % g.patches_y;
+        img = t / g.patches_y;
+        x0 = pxi * g.PTX * 8;
+        y0 = pyi * g.PTY * 16;
+        n0 = slice * g.BN;
+    };
+
     if (warp == 0) {
-        // ---------------- halo producer: one box per 32-channel chunk ----------------
+        // ---------------- halo producer: one box per (item, 32-channel chunk) ----------------
         int stage = 0;
         uint32_t phase = 0;
-        for (int ch = 0; ch < chunks; ++ch) {
-            mbar_wait(a_empty + stage, phase ^ 1);
-            if (elect_one()) {
-                mbar_expect_tx(a_full + stage, (uint32_t)a_bytes);
-                const bool second = ch >= chunks0;
-                tma_load_4d(smem + (size_t)stage * a_stride, second ? &map_x1 : &map_x0, a_full + stage,
-                            (second ? ch - chunks0 : ch) * kChunk, x0 - g.pad, y0 - g.pad, img);
-            }
-            __syncwarp();
-            if (++stage == g.a_stages) { stage = 0; phase ^= 1; }
-        }
-    } else if (warp == 2) {
-        // ---------------- weight producer: one [BN x 32] tile per (chunk, tap) ----------------
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int ch = 0; ch < chunks; ++ch) {
-            for (int tap = 0; tap < taps; ++tap) {
-                mbar_wait(b_empty + stage, phase ^ 1);
+        for (int item = blockIdx.x; item < g.items; item += gridDim.x) {
+            int n0, img, x0, y0;
+            decode(item, n0, img, x0, y0);
+            for (int ch = 0; ch < chunks; ++ch) {
+                mbar_wait_t(a_empty + stage, phase ^ 1, prof, w0);
                 if (elect_one()) {
-                    mbar_expect_tx(b_full + stage, (uint32_t)b_bytes);
-                    tma_load_3d(smem_b + (size_t)stage * b_bytes, &map_w, b_full + stage, ch * kChunk, n0, tap);
+                    mbar_expect_tx(a_full + stage, (uint32_t)a_bytes);
+                    const bool second = ch >= chunks0;
+                    tma_load_4d(smem + (size_t)stage * a_stride, second ? &map_x1 : &map_x0, a_full + stage,
+                                (second ? ch - chunks0 : ch) * kChunk, x0 - g.pad, y0 - g.pad, img);
                 }
                 __syncwarp();
-                if (++stage == g.b_stages) { stage = 0; phase ^= 1; }
+                if (++stage == g.a_stages) { stage = 0; phase ^= 1; }
             }
         }
+        if (prof && lane == 0) atomicAdd(g.prof + 4, w0);
+    } else if (warp == 2) {
+        // ---------------- weight producer: one [BN x 32] tile per (item, chunk, tap) ----------------
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int item = blockIdx.x; item < g.items; item += gridDim.x) {
+            const int n0 = (item / patches) * g.BN;
+            for (int ch = 0; ch < chunks; ++ch) {
+                for (int tap = 0; tap < taps; ++tap) {
+                    mbar_wait_t(b_empty + stage, phase ^ 1, prof, w0);
+                    if (elect_one()) {
+                        mbar_expect_tx(b_full + stage, (uint32_t)b_bytes);
+                        tma_load_3d(smem_b + (size_t)stage * b_bytes, &map_w, b_full + stage, ch * kChunk, n0, tap);
+                    }
+                    __syncwarp();
+                    if (++stage == g.b_stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        if (prof && lane == 0) atomicAdd(g.prof + 5, w0);
     } else if (warp == 1) {
         // ---------------- MMA issuer: warp-uniform loops, no divisions, one elected lane issues ----------------
         const uint32_t idesc = make_idesc_tf32(g.BN);
@@ -397,66 +463,136 @@ __global__ void __launch_bounds__(256) conv_tcgen05_halo_kernel(const __grid_con
         uint32_t tile_off16[4];   // (tile origin inside the halo buffer) / 16 bytes
 #pragma unroll
         for (int tl = 0; tl < 4; ++tl) {
-            const int tx = tl % g.PTX, ty = tl / g.PTX;
+            const int tx = tl & (g.PTX - 1), ty = tl >> g.ptx_log2;
             tile_off16[tl] = (uint32_t)((ty * 16 * g.HX + tx * 8) * 8);
         }
         int sa = 0, sb = 0;
         uint32_t pa = 0, pb = 0;
-        for (int ch = 0; ch < chunks; ++ch) {
-            mbar_wait(a_full + sa, pa);
-            const uint32_t a16 = (smem_u32(smem + (size_t)sa * a_stride) & 0x3FFFFu) >> 4;
-            uint32_t row16 = 0;   // (r * HX) * 8
-            for (int r = 0; r < g.ks; ++r, row16 += (uint32_t)g.HX * 8u) {
-                for (int sx = 0; sx < g.ks; ++sx) {
-                    mbar_wait(b_full + sb, pb);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + (size_t)sb * b_bytes));
-                    const uint32_t tap16 = a16 + row16 + (uint32_t)sx * 8u;
-                    const uint32_t first = (uint32_t)(ch | r | sx);
-                    if (elect_one()) {
+        int li = 0;   // local item counter
+        for (int item = blockIdx.x; item < g.items; item += gridDim.x, ++li) {
+            const int buf = (g.nbuf == 2) ? (li & 1) : 0;
+            const uint32_t use = (uint32_t)((g.nbuf == 2) ? (li >> 1) : li);
+            mbar_wait_t(acc_empty + buf, (use & 1) ^ 1, prof, w2);          // epilogue has drained this buffer
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t acc_base = tmem_base + (uint32_t)(buf * acc_cols);
+            for (int ch = 0; ch < chunks; ++ch) {
+                mbar_wait_t(a_full + sa, pa, prof, w0);
+                const uint32_t a16 = (smem_u32(smem + (size_t)sa * a_stride) & 0x3FFFFu) >> 4;
+                uint32_t row16 = 0;   // (r * HX) * 8
+                for (int r = 0; r < g.ks; ++r, row16 += (uint32_t)g.HX * 8u) {
+                    for (int sx = 0; sx < g.ks; ++sx) {
+                        mbar_wait_t(b_full + sb, pb, prof, w1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + (size_t)sb * b_bytes));
+                        const uint32_t tap16 = a16 + row16 + (uint32_t)sx * 8u;
+                        const uint32_t first = (uint32_t)(ch | r | sx);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int tl = 0; tl < 4; ++tl) {
-                            if (tl < ntiles) {
-                                const uint64_t adesc = a_hi | (uint64_t)(tap16 + tile_off16[tl]);
+                            for (int tl = 0; tl < 4; ++tl) {
+                                if (tl < ntiles) {
+                                    const uint64_t adesc = a_hi | (uint64_t)(tap16 + tile_off16[tl]);
 #pragma unroll
-                                for (int kk = 0; kk < kChunk / 8; ++kk)
-                                    umma_tf32(tmem_base + (uint32_t)(tl * g.BN), adesc + 2 * kk, bdesc + 2 * kk, idesc,
-                                              (first | (uint32_t)kk) != 0);
+                                    for (int kk = 0; kk < kChunk / 8; ++kk)
+                                        umma_tf32(acc_base + (uint32_t)(tl * g.BN), adesc + 2 * kk, bdesc + 2 * kk,
+                                                  idesc, (first | (uint32_t)kk) != 0);
+                                }
                             }
+                            umma_commit(b_empty + sb);
                         }
-                        umma_commit(b_empty + sb);
+                        __syncwarp();
+                        if (++sb == g.b_stages) { sb = 0; pb ^= 1; }
                     }
-                    __syncwarp();
-                    if (++sb == g.b_stages) { sb = 0; pb ^= 1; }
                 }
+                if (elect_one()) {
+                    umma_commit(a_empty + sa);
+                    if (ch == chunks - 1) umma_commit(acc_full + buf);
+                }
+                __syncwarp();
+                if (++sa == g.a_stages) { sa = 0; pa ^= 1; }
             }
-            if (elect_one()) {
-                umma_commit(a_empty + sa);
-                if (ch == chunks - 1) umma_commit(accum_bar);
-            }
-            __syncwarp();
-            if (++sa == g.a_stages) { sa = 0; pa ^= 1; }
+        }
+        if (prof && lane == 0) {
+            atomicAdd(g.prof + 0, (unsigned long long)(clock64() - t_start));
+            atomicAdd(g.prof + 1, w0);
+            atomicAdd(g.prof + 2, w1);
+            atomicAdd(g.prof + 3, w2);
         }
     } else if (warp >= 4) {
-        // ---------------- epilogue ----------------
-        const int quarter = warp & 3;
+        // ---------------- epilogue: software-pipelined TMEM -> registers -> fused math -> global ----------------
+        const int quarter = warp & 3, half = (warp - 4) >> 2;
         const int row = quarter * 32 + lane;      // M row: 8 pixels along x per group, 16 groups along y
-        mbar_wait(accum_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int tl = 0; tl < ntiles; ++tl) {
-            const int tx = tl % g.PTX, ty = tl / g.PTX;
-            const int ox = x0 + tx * 8 + (row & 7), oy = y0 + ty * 16 + (row >> 3);
-            const bool valid = oy < g.H && ox < g.W;
-            const int64_t m = ((int64_t)img * g.H + oy) * g.W + ox;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tl * g.BN);
-            for (int c = 0; c < g.BN; c += 16) {
-                float v[16];
-                tmem_ld16(taddr + (uint32_t)c, v);
-                if (valid) epilogue_store<EPI, 16>(ep, m, n0 + c, v);
+        const int nch = (g.BN / 16 - half + 1) / 2;   // this warp's 16-column chunks: c = 16*half + 32*j
+        const int units = ntiles * nch;
+        int li = 0;
+        for (int item = blockIdx.x; item < g.items; item += gridDim.x, ++li) {
+            int n0, img, x0, y0;
+            decode(item, n0, img, x0, y0);
+            const int buf = (g.nbuf == 2) ? (li & 1) : 0;
+            const uint32_t use = (uint32_t)((g.nbuf == 2) ? (li >> 1) : li);
+            mbar_wait_t(acc_full + buf, use & 1, prof, w0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * acc_cols);
+
+            // unit u -> (tile tl, chunk j); walked incrementally
+            struct Unit { int tl, j; int64_t m; bool valid; int col; };
+            auto make_unit = [&](int tl, int j) {
+                Unit u;
+                u.tl = tl; u.j = j;
+                const int ox = x0 + (tl & (g.PTX - 1)) * 8 + (row & 7), oy = y0 + (tl >> g.ptx_log2) * 16 + (row >> 3);
+                u.valid = oy < g.H && ox < g.W;
+                u.m = ((int64_t)img * g.H + oy) * g.W + ox;
+                u.col = half * 16 + 32 * j;
+                return u;
+            };
+            auto next_unit = [&](const Unit &u) { return (u.j + 1 < nch) ? make_unit(u.tl, u.j + 1) : make_unit(u.tl + 1, 0); };
+
+            uint32_t ra[16], rb[16];
+            EpiAux<16> xa, xb;
+            if (units > 0) {
+                Unit ua = make_unit(0, 0), ub = ua;
+                tmem_ld16_issue(lane_base + (uint32_t)(ua.tl * g.BN + ua.col), ra);
+                if (ua.valid) epilogue_prefetch<EPI, 16>(ep, ua.m, n0 + ua.col, xa);
+                for (int u = 0; u < units; u += 2) {
+                    tmem_ld_wait(ra);
+                    if (u + 1 < units) {
+                        ub = next_unit(ua);
+                        tmem_ld16_issue(lane_base + (uint32_t)(ub.tl * g.BN + ub.col), rb);
+                        if (ub.valid) epilogue_prefetch<EPI, 16>(ep, ub.m, n0 + ub.col, xb);
+                    }
+                    if (ua.valid) {
+                        float v[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]);
+                        epilogue_finish<EPI, 16>(ep, ua.m, n0 + ua.col, v, xa);
+                    }
+                    if (u + 1 < units) {
+                        tmem_ld_wait(rb);
+                        if (u + 2 < units) {
+                            ua = next_unit(ub);
+                            tmem_ld16_issue(lane_base + (uint32_t)(ua.tl * g.BN + ua.col), ra);
+                            if (ua.valid) epilogue_prefetch<EPI, 16>(ep, ua.m, n0 + ua.col, xa);
+                        }
+                        if (ub.valid) {
+                            float v[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rb[i]);
+                            epilogue_finish<EPI, 16>(ep, ub.m, n0 + ub.col, v, xb);
+                        }
+                    }
+                }
             }
+            // all tcgen05.ld of this warp have completed (waited above): hand the buffer back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (elect_one()) mbar_arrive(acc_empty + buf);
+            __syncwarp();
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (prof && lane == 0) {
+            atomicAdd(g.prof + 6, w0);
+            atomicAdd(g.prof + 7, (unsigned long long)(clock64() - t_start));
+        }
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 3) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -525,15 +661,34 @@ int launch_halo(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap &m1, 
                 const HaloGeom &g, const EpiParams &ep, cudaStream_t s) {
     const size_t a_stride = ((size_t)g.HX * g.HY * kChunk * 4 + 1023) & ~(size_t)1023;
     const size_t smem = g.a_stages * a_stride + (size_t)g.b_stages * g.BN * kChunk * 4 +
-                        (2 * g.a_stages + 2 * g.b_stages + 1) * 8 + 16 + 1024;
+                        (2 * g.a_stages + 2 * g.b_stages + 4) * 8 + 16 + 1024;
     static size_t configured = 0;
     if (smem > configured) {
         RAMNET_CUDA(cudaFuncSetAttribute(conv_tcgen05_halo_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
         configured = smem;
     }
-    dim3 grid((unsigned)(g.patches_x * g.patches_y * g.N), (unsigned)(g.Cout / g.BN));
-    conv_tcgen05_halo_kernel<EPI><<<grid, 256, smem, s>>>(m0, m1, mw, g, ep);
+    const int grid = g.items < h->sm_count ? g.items : h->sm_count;   // persistent: one CTA per SM
+    static const bool do_prof = getenv("RAMNET_PROF") != nullptr;      // debug only: synchronises and prints
+    if (do_prof) {
+        static unsigned long long *buf = nullptr;
+        if (!buf) cudaMalloc(&buf, 64);
+        cudaMemsetAsync(buf, 0, 64, s);
+        HaloGeom gp = g;
+        gp.prof = buf;
+        conv_tcgen05_halo_kernel<EPI><<<grid, kHaloThreads, smem, s>>>(m0, m1, mw, gp, ep);
+        unsigned long long hbuf[8];
+        cudaMemcpyAsync(hbuf, buf, 64, cudaMemcpyDeviceToHost, s);
+        cudaStreamSynchronize(s);
+        const double n = grid;
+        fprintf(stderr, "[ramnet-prof] grid=%d items=%d per-CTA kcycles: mma_total=%.1f wait_a_full=%.1f wait_b_full=%.1f "
+                        "wait_acc_empty=%.1f | prodA_wait_empty=%.1f prodB_wait_empty=%.1f | epi(avg of 8 warps) "
+                        "wait_acc_full=%.1f total=%.1f\n",
+                grid, g.items, hbuf[0] / n / 1e3, hbuf[1] / n / 1e3, hbuf[2] / n / 1e3, hbuf[3] / n / 1e3, hbuf[4] / n / 1e3,
+                hbuf[5] / n / 1e3, hbuf[6] / n / 8e3, hbuf[7] / n / 8e3);
+    } else {
+        conv_tcgen05_halo_kernel<EPI><<<grid, kHaloThreads, smem, s>>>(m0, m1, mw, g, ep);
+    }
     RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;
 }
@@ -547,64 +702,77 @@ int halo_mode_env() {
     return mode;
 }
 
+bool fill_halo(const ramnet_conv_desc *d, HaloGeom *g, int ptx, int pty, int bn, int a_st, int b_st) {
+    if (d->Cout % bn || ptx * pty > 4 || ptx * pty * bn > 512 || (ptx & (ptx - 1))) return false;
+    g->N = d->N; g->H = d->H; g->W = d->W; g->Cout = d->Cout; g->C0 = d->C0; g->C1 = d->C1;
+    g->ks = d->ksize; g->pad = d->ksize / 2; g->prof = nullptr;
+    g->PTX = ptx; g->PTY = pty; g->ptx_log2 = ptx == 4 ? 2 : (ptx == 2 ? 1 : 0);
+    g->HX = ptx * 8 + d->ksize - 1; g->HY = pty * 16 + d->ksize - 1;
+    if (g->HX > 256 || g->HY > 256) return false;
+    g->BN = bn; g->n_slices = d->Cout / bn;
+    g->patches_x = (d->W + ptx * 8 - 1) / (ptx * 8); g->patches_y = (d->H + pty * 16 - 1) / (pty * 16);
+    const int64_t items = (int64_t)g->patches_x * g->patches_y * d->N * g->n_slices;
+    if (items > 0x7fffffff) return false;
+    g->items = (int)items;
+    g->nbuf = (2 * ptx * pty * bn <= 512) ? 2 : 1;
+    const size_t a_stride = ((size_t)g->HX * g->HY * kChunk * 4 + 1023) & ~(size_t)1023;
+    const size_t b_bytes = (size_t)bn * kChunk * 4;
+    const size_t budget = 222 * 1024;
+    if (a_st <= 0) {   // automatic pipeline depths
+        a_st = 2;
+        if (budget < a_st * a_stride + 3 * b_bytes) a_st = 1;
+        if (budget < a_st * a_stride + 3 * b_bytes) return false;
+        b_st = (int)((budget - a_st * a_stride) / b_bytes);
+        if (b_st > 10) b_st = 10;
+    }
+    if (a_st * a_stride + b_st * b_bytes > budget || b_st < 2) return false;
+    g->a_stages = a_st; g->b_stages = b_st;
+    return true;
+}
+
+// Cycle model of one launch (per SM), from measurements on B200:
+//  - shared memory moves 128 B/clk/SM and is shared between the UMMA operand reads and the TMA fills:
+//    a 128xBNx8 tf32 MMA reads (128+BN)*32 B (tools/microbench/umma_rate.cu: max(BN/2,(128+BN)/4) clk),
+//    each tap additionally writes one BN x 128 B weight tile and 1/taps of the halo box
+//    (RAMNET_PROF counters: 678 clk per tap measured vs 676 predicted for BN=128, 2 tiles);
+//  - L2 -> SM delivers ~15 TB/s chip-wide (~50 B/clk/SM);
+//  - the epilogue is hidden under the next item when TMEM is double-buffered;
+//  - persistent scheduling => ceil(items / SMs) rounds.
+double halo_cost(const ramnet_handle *h, const ramnet_conv_desc *d, const HaloGeom &g) {
+    const int ntiles = g.PTX * g.PTY, chunks = (d->C0 + d->C1) / kChunk, taps = d->ksize * d->ksize;
+    const double halo_bytes = (double)g.HX * g.HY * 128.0;
+    const double smem_tap = (ntiles * 4.0 * (128 + g.BN) * 32.0 + g.BN * 128.0 + halo_bytes / taps) / 128.0;
+    const double math_tap = ntiles * 4.0 * g.BN / 2.0;
+    const double tap = (smem_tap > math_tap ? smem_tap : math_tap) + 20.0;
+    const double mma = (double)chunks * taps * tap;
+    const double l2 = (double)chunks * (halo_bytes + (double)taps * g.BN * 128.0) / 50.0;
+    const double main = mma > l2 ? mma : l2;
+    const double epi = (double)ntiles * (g.BN / 32.0 + 0.5) * 900.0 + 500.0;
+    const double per_item = g.nbuf == 2 ? (main > epi ? main : epi) + 300.0 : main + epi;
+    const int64_t rounds = (g.items + h->sm_count - 1) / h->sm_count;
+    return (double)rounds * per_item + (g.nbuf == 2 ? epi : 0.0) + 4000.0;
+}
+
 // Chooses patch shape, BN and pipeline depths for the halo kernel; returns false when the layer
 // should stay on the per-tap kernel (stride 2, 1x1, or no configuration fits shared memory).
 bool plan_halo(const ramnet_handle *h, const ramnet_conv_desc *d, HaloGeom *g) {
-    const int mode = halo_mode_env();
-    if (mode & 4) return false;                      // RAMNET_HALO_MODE bit 2: force the per-tap kernel
+    if (halo_mode_env() & 4) return false;           // RAMNET_HALO_MODE=4: force the per-tap kernel (A/B tests)
     if (d->stride != 1 || d->ksize == 1) return false;
-    g->N = d->N; g->H = d->H; g->W = d->W; g->Cout = d->Cout; g->C0 = d->C0; g->C1 = d->C1;
-    g->ks = d->ksize; g->pad = d->ksize / 2;
-    const size_t budget = 200 * 1024;
-    double best_score = -1;
-    bool found = false;
     if (const char *f = getenv("RAMNET_HALO_FORCE")) {   // tuning aid: "PTX,PTY,BN,a_stages,b_stages"
         int ptx, pty, bn, ast, bst;
-        if (sscanf(f, "%d,%d,%d,%d,%d", &ptx, &pty, &bn, &ast, &bst) == 5 && d->Cout % bn == 0 && ptx * pty * bn <= 512 &&
-            ptx * pty <= 4) {
-            g->PTX = ptx; g->PTY = pty; g->BN = bn; g->a_stages = ast; g->b_stages = bst;
-            g->HX = ptx * 8 + d->ksize - 1; g->HY = pty * 16 + d->ksize - 1;
-            g->patches_x = (d->W + ptx * 8 - 1) / (ptx * 8); g->patches_y = (d->H + pty * 16 - 1) / (pty * 16);
-            const size_t need = ast * (((size_t)g->HX * g->HY * kChunk * 4 + 1023) & ~(size_t)1023) +
-                                (size_t)bst * bn * kChunk * 4 + 4096;
-            if (need <= 227 * 1024) return true;
-        }
+        if (sscanf(f, "%d,%d,%d,%d,%d", &ptx, &pty, &bn, &ast, &bst) == 5 && fill_halo(d, g, ptx, pty, bn, ast, bst))
+            return true;
     }
     static const int shapes[][2] = {{2, 1}, {1, 1}, {4, 1}, {2, 2}, {1, 2}};
-    for (const auto &sh : shapes) {
+    double best = -1;
+    HaloGeom cand;
+    for (const auto &sh : shapes)
         for (int bn = 256; bn >= 16; bn >>= 1) {
-            if (d->Cout % bn) continue;
-            const int ntiles = sh[0] * sh[1];
-            if (ntiles * bn > 512) continue;
-            int hx = sh[0] * 8 + d->ksize - 1;
-            const int hy = sh[1] * 16 + d->ksize - 1;
-            if (hx > 256 || hy > 256) continue;
-            const size_t a_stride = ((size_t)hx * hy * kChunk * 4 + 1023) & ~(size_t)1023;
-            const size_t b_bytes = (size_t)bn * kChunk * 4;
-            const int a_st = 2;
-            int b_st = (int)((budget - a_st * a_stride) / b_bytes);
-            if (budget < a_st * a_stride || b_st < 2) continue;
-            if (b_st > 8) b_st = 8;
-            const int px = (d->W + sh[0] * 8 - 1) / (sh[0] * 8), py = (d->H + sh[1] * 16 - 1) / (sh[1] * 16);
-            const int64_t ctas = (int64_t)px * py * d->N * (d->Cout / bn);
-            // bytes moved from L2 per useful output pixel and chunk (halo + weights), waste for ragged edges,
-            // and SM fill: score = useful flops per byte x wave efficiency
-            const double pix = (double)d->W * d->H * d->N;
-            const double cov = (double)px * py * d->N * ntiles * 128.0;
-            const double bytes = (double)hx * hy * 128.0 * (d->Cout / bn) / (ntiles * 128.0) +
-                                 (double)d->ksize * d->ksize * bn * 128.0 * (d->Cout / bn) / (ntiles * 128.0);
-            const double waves = (double)ctas / h->sm_count;
-            const double fill = waves / (double)((int64_t)(waves + 0.999999));
-            const double score = (pix / cov) * fill / bytes;
-            if (score > best_score) {
-                best_score = score;
-                g->PTX = sh[0]; g->PTY = sh[1]; g->HX = hx; g->HY = hy; g->BN = bn;
-                g->a_stages = a_st; g->b_stages = b_st; g->patches_x = px; g->patches_y = py;
-                found = true;
-            }
+            if (!fill_halo(d, &cand, sh[0], sh[1], bn, 0, 0)) continue;
+            const double c = halo_cost(h, d, cand);
+            if (best < 0 || c < best) { best = c; *g = cand; }
         }
-    }
-    return found;
+    return best >= 0;
 }
 }  // namespace
 
@@ -620,9 +788,9 @@ int conv_fwd_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *x0, 
     HaloGeom hg;
     if (plan_halo(h, d, &hg)) {
         if (getenv("RAMNET_DEBUG"))
-            fprintf(stderr, "[ramnet] halo plan %dx%d C=%d+%d->%d k%d: tiles %dx%d HX=%d HY=%d BN=%d a_st=%d b_st=%d grid=%dx%d\n",
+            fprintf(stderr, "[ramnet] halo plan %dx%d C=%d+%d->%d k%d: tiles %dx%d HX=%d HY=%d BN=%d a_st=%d b_st=%d nbuf=%d items=%d\n",
                     d->H, d->W, d->C0, d->C1, d->Cout, d->ksize, hg.PTX, hg.PTY, hg.HX, hg.HY, hg.BN, hg.a_stages,
-                    hg.b_stages, hg.patches_x * hg.patches_y * hg.N, hg.Cout / hg.BN);
+                    hg.b_stages, hg.nbuf, hg.items);
         CUtensorMap m0, m1, mw;
         cuuint32_t box[4] = {kChunk, (cuuint32_t)hg.HX, (cuuint32_t)hg.HY, 1};
         auto enc_act = [&](CUtensorMap *m, const float *x, int C) {
