@@ -122,9 +122,9 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
-def build_model(torch, device_index, mma_kind):
+def build_model(torch, device_index, mma_kind, cuda_graphs=True):
     import rpg_ramnet_b200 as R
-    cfg = dict(MODEL_CFG, gpu=device_index, mma_kind=mma_kind)
+    cfg = dict(MODEL_CFG, gpu=device_index, mma_kind=mma_kind, cuda_graphs=cuda_graphs)
     torch.manual_seed(0)
     with contextlib.redirect_stdout(io.StringIO()):
         m = R.ERGB2DepthRecurrent(cfg)
@@ -229,7 +229,7 @@ def main_ours(args):
     from rpg_ramnet_b200 import ops
     from rpg_ramnet_b200.utils.synthetic import synth_sequence
 
-    model = build_model(torch, local, args.mma_kind)
+    model = build_model(torch, local, args.mma_kind, cuda_graphs=not args.no_graphs)
     host_items = synth_sequence(B, H, W, L, K_EVENTS, seed=2 + rank, with_targets=False)
     host_items = [{k: v.pin_memory() for k, v in it.items()} for it in host_items]
     dev_items = [{k: v.to(dev) for k, v in it.items()} for it in host_items]
@@ -276,6 +276,13 @@ def main_ours(args):
     with ClockSampler(local) as clk:
         ms = timed(step_resident, args.steps)
     launches = R.launch_count(local) - launches0
+    if not args.no_graphs:
+        # graph replays do not pass through the C ABI counter: count the kernels of one eager step instead
+        model.cuda_graphs = False
+        l0 = R.launch_count(local)
+        step_resident()
+        launches = (R.launch_count(local) - l0) * args.steps
+        model.cuda_graphs = True
     value = world * MAPS_PER_STEP * args.steps / (ms * 1e-3)
 
     for _ in range(max(1, args.warmup // 2)):
@@ -286,10 +293,13 @@ def main_ours(args):
     # roofline of the dominant kernel family (the implicit-GEMM convolution): every conv launch of one
     # instrumented step bracketed by CUDA events on the launching stream.
     peaks, peak_src = read_peaks()
+    graphs_on, model.cuda_graphs = model.cuda_graphs, False      # per-kernel events need eager launches
+    step_resident()
     ops.PROFILE = []
     step_resident()
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
+    model.cuda_graphs = graphs_on
     conv_ms = sum(a.elapsed_time(b) for (k, f, a, b) in prof if k == 'conv')
     conv_flops = sum(f for (k, f, _, _) in prof if k == 'conv')
     n_conv = sum(1 for p in prof if p[0] == 'conv')
@@ -323,7 +333,8 @@ def main_ours(args):
                                        f'-> {MAPS_PER_STEP} depth maps per step per GPU',
                            'parallelism': f'dp{world} (batch sharded, no collective)',
                            'l2': 'per-step working set (>4 GB of activations) exceeds the 126 MB L2; no explicit flush',
-                           'random_init_weights': 'torch.manual_seed(0), reference construction order'},
+                           'random_init_weights': 'torch.manual_seed(0), reference construction order',
+                           'cuda_graphs': not args.no_graphs},
                 'clocks': clk.summary(),
                 'e2e': {'value': value_e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                         'ms_per_step': ms_e2e / args.steps,
@@ -345,6 +356,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--mma-kind', default=os.environ.get('RAMNET_MMA_KIND', 'tf32'), choices=['tf32', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graphs', action='store_true', help='issue every kernel from Python instead of CUDA-graph replay')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':

@@ -144,24 +144,24 @@ def pack_lstm(cache: WeightCache, key, lstm, kind: int) -> Packed:
 # ------------------------------------------------------------------------------------------
 # fused blocks
 # ------------------------------------------------------------------------------------------
-def run_conv(x, p: Packed, epilogue, kind, x1=None, aux0=None, aux1=None, round_out=False):
+def run_conv(x, p: Packed, epilogue, kind, x1=None, aux0=None, aux1=None, round_out=False, out0=None, out1=None):
     return ops.conv_fwd(x, x1, p.w, p.b, p.Cout, p.ksize, p.stride, epilogue, kind, aux0=aux0, aux1=aux1,
-                        round_tf32=round_out and kind == ops.MMA_TF32)
+                        round_tf32=round_out and kind == ops.MMA_TF32, out0=out0, out1=out1)
 
 
-def run_gru(x, h, ru: Packed, out: Packed, kind):
-    """submodules.py:436-454 as two fused convolutions; returns h'."""
+def run_gru(x, h, ru: Packed, out: Packed, kind, out_h=None):
+    """submodules.py:436-454 as two fused convolutions; returns h' (written into `out_h` when given)."""
     if h is None:
         h = ops.zeros_nhwc(x.shape[0], x.shape[1], x.shape[2], x.shape[3], x.device)
     if h.shape != x.shape:
         raise RamnetError(f'ConvGRU: state shape {tuple(h.shape)} does not match input {tuple(x.shape)} '
                           '(H and W must be divisible by 2**num_encoders)')
     u, rh = run_conv(x, ru, ops.EPI_GRU_RU, kind, x1=h, aux0=h, round_out=True)
-    return run_conv(x, out, ops.EPI_GRU_OUT, kind, x1=rh, aux0=h, aux1=u, round_out=True)
+    return run_conv(x, out, ops.EPI_GRU_OUT, kind, x1=rh, aux0=h, aux1=u, round_out=True, out0=out_h)
 
 
-def run_lstm(x, state, p: Packed, kind):
-    """submodules.py:318-358 as one fused convolution; returns (h', c')."""
+def run_lstm(x, state, p: Packed, kind, out_state=None):
+    """submodules.py:318-358 as one fused convolution; returns (h', c') (written into `out_state` when given)."""
     if state is None:
         h = ops.zeros_nhwc(x.shape[0], p.Cout // 4, x.shape[2], x.shape[3], x.device)
         c = ops.zeros_nhwc(x.shape[0], p.Cout // 4, x.shape[2], x.shape[3], x.device)
@@ -169,4 +169,110 @@ def run_lstm(x, state, p: Packed, kind):
         h, c = ops.as_nhwc(state[0]), ops.as_nhwc(state[1])
     if h.shape[2:] != x.shape[2:]:
         raise RamnetError(f'ConvLSTM: state shape {tuple(h.shape)} does not match input {tuple(x.shape)}')
-    return run_conv(x, p, ops.EPI_LSTM, kind, x1=h, aux0=c, round_out=True)
+    o0, o1 = (None, None) if out_state is None else out_state
+    return run_conv(x, p, ops.EPI_LSTM, kind, x1=h, aux0=c, round_out=True, out0=o0, out1=o1)
+
+
+# ------------------------------------------------------------------------------------------
+# CUDA-graph runner (inference): one captured graph per (pass type, state direction)
+# ------------------------------------------------------------------------------------------
+class GraphRunner:
+    """Replays a whole RAM-Net pass (head -> encoders -> state update -> decoder -> depth) as ONE CUDA
+    graph launch instead of ~30 Python-issued kernel launches (the reference issues ~70 per pass,
+    SURVEY.md §3.3).  Recurrent state ping-pongs between two persistent buffer sets so no state copy is
+    ever made: the graph for direction s reads set s and writes set 1-s.
+
+    Aliasing contract: the state tensors returned by a pass ARE these persistent buffers; they stay
+    valid until the second-next pass overwrites them (callers that carry only the latest state —
+    trainer/lstm_trainer.py:380, test.py:380 — are unaffected).  Depth maps are returned as fresh
+    tensors."""
+
+    def __init__(self, net, B, H, W, device):
+        self.net, self.B, self.H, self.W, self.device = net, B, H, W, device
+        self.pair = (not bool(net.baseline)) and net.state_combination == 'convlstm'
+        self.sets = [self._alloc_states(), self._alloc_states()]
+        self.x_in, self.graphs = {}, {}
+        self.param_sig = None
+        self.pool = None
+
+    def _alloc_states(self):
+        out = []
+        n = self.net
+        for i in range(n.num_encoders):
+            c, h, w = n.base_num_channels << (i + 1), self.H >> (i + 1), self.W >> (i + 1)
+            if self.pair:
+                out.append([ops.zeros_nhwc(self.B, c, h, w, self.device), ops.zeros_nhwc(self.B, c, h, w, self.device)])
+            else:
+                out.append(ops.zeros_nhwc(self.B, c, h, w, self.device))
+        return out
+
+    @staticmethod
+    def _flat(states):
+        flat = []
+        for s in states:
+            flat.extend(s if isinstance(s, (list, tuple)) else [s])
+        return flat
+
+    def _which_set(self, prev):
+        if prev is None:
+            return None
+        flat = self._flat(prev)
+        for k in (0, 1):
+            mine = self._flat(self.sets[k])
+            if len(mine) == len(flat) and all(a is b or (a.data_ptr() == b.data_ptr() and a.shape == b.shape)
+                                             for a, b in zip(flat, mine)):
+                return k
+        return None
+
+    def _sig(self):
+        return tuple((p.data_ptr(), p._version) for p in self.net.parameters()) + \
+            tuple((b.data_ptr(), b._version) for b in self.net.buffers()) + (self.net.training, self.net._kind())
+
+    def run(self, which, x, prev_super):
+        sig = self._sig()
+        if sig != self.param_sig:           # weights changed (optimizer step / load_state_dict): re-capture
+            self.graphs.clear()
+            self.param_sig = sig
+        src = self._which_set(prev_super)
+        if src is None:                     # foreign or initial state: bring it into set 0
+            src = 0
+            mine = self._flat(self.sets[0])
+            if prev_super is None:
+                for t in mine:
+                    t.zero_()
+            else:
+                for t, f in zip(mine, self._flat(prev_super)):
+                    t.copy_(f)
+        dst = 1 - src
+        xin = self.x_in.get(which)
+        if xin is None or xin.shape != x.shape:
+            xin = torch.empty(tuple(x.shape), dtype=torch.float32, device=self.device)
+            self.x_in[which] = xin
+            self.graphs = {k: v for k, v in self.graphs.items() if k[0] != which}
+        xin.copy_(x, non_blocking=True)
+        key = (which, src)
+        entry = self.graphs.get(key)
+        if entry is None:
+            entry = self._capture(which, xin, src, dst)
+            self.graphs[key] = entry
+        graph, pred = entry
+        graph.replay()
+        return self.sets[dst], pred.clone()
+
+    def _capture(self, which, xin, src, dst):
+        net = self.net
+        keep = [t.clone() for t in self._flat(self.sets[dst])]     # warm-up must not disturb live state
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):                                      # populates weight cache + kernel attributes
+                net._pass(which, xin, self.sets[src], None, out_states=self.sets[dst])
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, pool=self.pool):
+            _, _, pred = net._pass(which, xin, self.sets[src], None, out_states=self.sets[dst])
+        if self.pool is None:
+            self.pool = graph.pool()
+        for t, k in zip(self._flat(self.sets[dst]), keep):
+            t.copy_(k)
+        return graph, pred

@@ -37,6 +37,8 @@ class BaseERGB2Depth(BaseModel):
         self.loss_composition = config.get('loss_composition', False)
         self.kernel_size = int(config.get('kernel_size', 5))
         self.mma_kind = config.get('mma_kind', None)
+        # optional: replay each pass as one CUDA graph (inference; see engine.GraphRunner for the aliasing contract)
+        self.cuda_graphs = bool(config.get('cuda_graphs', False))
         self.gpu = torch.device('cuda:' + str(config['gpu']))
 
     def _grad_guard(self):
@@ -73,6 +75,22 @@ class ERGB2DepthRecurrent(BaseERGB2Depth):
             num_residual_blocks=self.num_residual_blocks, norm=self.norm, use_upsample_conv=self.use_upsample_conv,
             recurrent_block_type=self.recurrent_block_type, baseline=self.baseline, mma_kind=self.mma_kind)
         self.max_num_channels = self.base_num_channels * pow(2, self.num_encoders)
+        self._runners = {}
+
+    def _run_pass(self, which, x, prev_super_states, last):
+        """forward_events / forward_images + forward_decoder, eagerly or as one CUDA-graph replay."""
+        net = self.statenetphasedrecurrent
+        if self.cuda_graphs and net.graph_capable() and not self.training:
+            B, _, H, W = x.shape
+            key = (B, H, W)
+            runner = self._runners.get(key)
+            if runner is None:
+                from ..engine import GraphRunner
+                runner = self._runners[key] = GraphRunner(net, B, H, W, self.gpu)
+            s, pred = runner.run(which, x, prev_super_states)
+            return s, {'encoders': [None] * net.num_encoders, 'state_comb': list(s)}, pred
+        x = x.to(self.gpu, non_blocking=True)
+        return net._pass(which, x, prev_super_states, last)
 
     def _zero_states(self, B, H, W):
         """model.py:146-159, allocated on the device directly (the reference builds them on the host
@@ -92,7 +110,7 @@ class ERGB2DepthRecurrent(BaseERGB2Depth):
         self._grad_guard()
         net = self.statenetphasedrecurrent
         predictions, super_states, states_lstm = {}, {}, {}
-        if prev_super_states is None:
+        if prev_super_states is None and not (self.cuda_graphs and net.graph_capable() and not self.training):
             B, _, H, W = item['image'].shape
             prev_super_states = self._zero_states(B, H, W)
         bl, K = self.baseline, self.every_x_rgb_frame
@@ -105,18 +123,12 @@ class ERGB2DepthRecurrent(BaseERGB2Depth):
                 n_event_passes, last = K, prev_states_lstm['events{}'.format(K - 1)]
             for k in range(n_event_passes):
                 key = 'events{}'.format(k)
-                x = item[key].to(self.gpu, non_blocking=True)
-                if bl == 'ergb0' or bl == 'e':
-                    s, l = net.forward_images(x, prev_super_states, last, None)
-                else:
-                    s, l = net.forward_events(x, prev_super_states, last, None)
-                predictions[key] = net.forward_decoder(s)
+                which = 'images' if (bl == 'ergb0' or bl == 'e') else 'events'   # baselines have no event encoder
+                s, l, predictions[key] = self._run_pass(which, item[key], prev_super_states, last)
                 super_states[key], states_lstm[key] = s, l
                 prev_super_states, last = s, l
-        x = item['image'].to(self.gpu, non_blocking=True)
         if (not bool(bl)) or bl == 'rgb' or (bl == 'e' and self.loss_composition != 'image'):
             last = prev_states_lstm['image']       # model.py:203-208
-        s, l = net.forward_images(x, prev_super_states, last, None)
-        predictions['image'] = net.forward_decoder(s)
+        s, l, predictions['image'] = self._run_pass('images', item['image'], prev_super_states, last)
         super_states['image'], states_lstm['image'] = s, l
         return predictions, super_states, states_lstm

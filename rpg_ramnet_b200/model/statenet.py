@@ -148,7 +148,18 @@ class StateNetPhasedRecurrent(BaseStateNet):
             raise RamnetError('only num_output_channels=1 is implemented')
 
     # ---- encoders -----------------------------------------------------------------------------
-    def _encode(self, which, x, prev_super_state, prev_states_lstm):
+    def _pass(self, which, x, prev_super_state, prev_states_lstm, out_states=None, return_logits=False):
+        """One full pass: encoder of one modality + state update + decoder.  `out_states` (optional) are
+        preallocated state buffers the new super states are written into (CUDA-graph runner)."""
+        s, l = self._encode(which, x, prev_super_state, prev_states_lstm, out_states)
+        return s, l, self.forward_decoder(s, return_logits)
+
+    def graph_capable(self):
+        """CUDA-graph replay covers the configurations whose only recurrent state is the super state."""
+        return self.recurrent_block_type == 'conv' and not bool(self.baseline) and \
+            self.state_combination in ('convgru', 'convlstm')
+
+    def _encode(self, which, x, prev_super_state, prev_states_lstm, out_states=None):
         self._check_supported()
         kind = self._kind()
         tf32 = kind == ops.MMA_TF32
@@ -182,12 +193,13 @@ class StateNetPhasedRecurrent(BaseStateNet):
             blk = combs[i].recurrent_block
             if self.state_combination == 'convlstm' and not baseline_path:
                 lp = E.pack_lstm(cache, f'{which}/comb{i}', blk, kind)
-                st = E.run_lstm(x, prev_super_state[i], lp, kind)          # state = previous super state [h, c]
+                st = E.run_lstm(x, prev_super_state[i], lp, kind,          # state = previous super state [h, c]
+                                out_state=None if out_states is None else out_states[i])
                 super_state = comb_state = st
             elif self.state_combination == 'convgru':
                 ru, out = E.pack_gru(cache, f'{which}/comb{i}', blk, kind)
                 hprev = None if prev_super_state[i] is None else ops.as_nhwc(prev_super_state[i])
-                hnew = E.run_gru(x, hprev, ru, out, kind)
+                hnew = E.run_gru(x, hprev, ru, out, kind, out_h=None if out_states is None else out_states[i])
                 super_state = comb_state = hnew
                 if baseline_path:
                     x = hnew

@@ -151,8 +151,9 @@ def _workspace(device, nbytes: int):
 
 def conv_fwd(x0: torch.Tensor, x1: Optional[torch.Tensor], w_packed: torch.Tensor, bias: Optional[torch.Tensor],
              Cout: int, ksize: int, stride: int, epilogue: int, mma_kind: int, aux0=None, aux1=None,
-             round_tf32: bool = False):
-    """Implicit-GEMM convolution with fused epilogue.  Returns y0 or (y0, y1)."""
+             round_tf32: bool = False, out0=None, out1=None):
+    """Implicit-GEMM convolution with fused epilogue.  Returns y0 or (y0, y1).
+    `out0` / `out1`: optional preallocated NHWC outputs (persistent state buffers of the CUDA-graph runner)."""
     _check_nhwc(x0, 'conv_fwd x0')
     N, C0, H, W = x0.shape
     C1 = 0
@@ -162,14 +163,20 @@ def conv_fwd(x0: torch.Tensor, x1: Optional[torch.Tensor], w_packed: torch.Tenso
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
     dev = x0.device
     y1 = None
+    def _out(given, C):
+        if given is None:
+            return empty_nhwc(N, C, Ho, Wo, dev)
+        _check_nhwc(given, 'conv_fwd out')
+        if tuple(given.shape) != (N, C, Ho, Wo):
+            raise _lib.RamnetError(f'conv_fwd: out shape {tuple(given.shape)} != {(N, C, Ho, Wo)}')
+        return given
+
     if epilogue == EPI_GRU_RU:
-        C = Cout // 2
-        y0, y1 = empty_nhwc(N, C, Ho, Wo, dev), empty_nhwc(N, C, Ho, Wo, dev)
+        y0, y1 = _out(out0, Cout // 2), _out(out1, Cout // 2)
     elif epilogue == EPI_LSTM:
-        C = Cout // 4
-        y0, y1 = empty_nhwc(N, C, Ho, Wo, dev), empty_nhwc(N, C, Ho, Wo, dev)
+        y0, y1 = _out(out0, Cout // 4), _out(out1, Cout // 4)
     else:
-        y0 = empty_nhwc(N, Cout, Ho, Wo, dev)
+        y0 = _out(out0, Cout)
     for a, nm in ((aux0, 'aux0'), (aux1, 'aux1')):
         if a is not None:
             _check_nhwc(a, 'conv_fwd ' + nm)

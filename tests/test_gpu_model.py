@@ -106,6 +106,31 @@ def test_weight_cache_tracks_parameter_updates():
     assert max_rel_err(c.cpu().numpy(), ref.numpy()) <= 1e-4
 
 
+@pytest.mark.parametrize('name', ['rect_b2', 'lstm_state', 'k5_shipped'])
+def test_cuda_graph_replay_is_bit_identical_to_eager(name):
+    """config['cuda_graphs']=True replays each pass as one CUDA graph (ping-pong state buffers); same kernels,
+    same order => bit-identical depth maps and states, across a state reset and a weight update."""
+    g, meta = load_case(name)
+    eager, _ = build_product_model(meta, mma_kind='tf32')
+    eager.to('cuda:0')
+    meta_g = dict(meta, config=dict(meta['config'], cuda_graphs=True))
+    graphed, _ = build_product_model(meta_g, mma_kind='tf32')
+    graphed.to('cuda:0')
+    assert graphed.cuda_graphs and graphed.statenetphasedrecurrent.graph_capable()
+    seq = case_inputs(meta)
+    for rep in range(2):                      # second repetition: state reset (None) with graphs already captured
+        a = run_product_sequence(eager, meta, seq)
+        b = run_product_sequence(graphed, meta, seq)
+        for (pa, sa), (pb, sb) in zip(a, b):
+            for k in pa:
+                assert torch.equal(pa[k], pb[k]), (name, rep, k)
+            for x, y in zip(flat_supers(sa['image']), flat_supers(sb['image'])):
+                assert torch.equal(x, y)
+        with torch.no_grad():                 # weight update => graphs are re-captured with re-packed weights
+            for m in (eager, graphed):
+                m.statenetphasedrecurrent.resblocks[0].conv1.weight.mul_(1.01)
+
+
 def test_unsupported_and_bad_shapes_raise():
     import rpg_ramnet_b200 as R
     g, meta = load_case('cfg1_shipped')
