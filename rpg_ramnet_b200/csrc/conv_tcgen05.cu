@@ -338,6 +338,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+
 __device__ __forceinline__ void mbar_wait_t(uint64_t *bar, uint32_t parity, bool prof, unsigned long long &acc) {
     if (prof) {
         const long long t0 = clock64();
@@ -469,6 +481,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
         int sa = 0, sb = 0;
         uint32_t pa = 0, pb = 0;
         int li = 0;   // local item counter
+        int ready = 0;   // weight stages known to be full, starting at sb
         for (int item = blockIdx.x; item < g.items; item += gridDim.x, ++li) {
             const int buf = (g.nbuf == 2) ? (li & 1) : 0;
             const uint32_t use = (uint32_t)((g.nbuf == 2) ? (li >> 1) : li);
@@ -481,7 +494,22 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
                 uint32_t row16 = 0;   // (r * HX) * 8
                 for (int r = 0; r < g.ks; ++r, row16 += (uint32_t)g.HX * 8u) {
                     for (int sx = 0; sx < g.ks; ++sx) {
-                        mbar_wait_t(b_full + sb, pb, prof, w1);
+                        // One barrier round trip (~100+ cycles even when complete) tells us about EVERY weight stage:
+                        // lane i polls the stage i slots ahead; the ballot gives the run of ready stages.
+                        if (ready == 0) {
+                            const long long tw = prof ? clock64() : 0;
+                            int j = sb + lane;
+                            uint32_t pj = pb;
+                            if (j >= g.b_stages) { j -= g.b_stages; pj ^= 1; }
+                            uint32_t mask;
+                            do {
+                                const bool ok = lane < g.b_stages && mbar_test(b_full + j, pj);
+                                mask = __ballot_sync(0xffffffffu, ok);
+                            } while (!(mask & 1u));
+                            ready = __ffs(~mask) - 1;          // consecutive ready stages starting at sb
+                            if (prof) w1 += (unsigned long long)(clock64() - tw);
+                        }
+                        --ready;
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + (size_t)sb * b_bytes));
                         const uint32_t tap16 = a16 + row16 + (uint32_t)sx * 8u;
