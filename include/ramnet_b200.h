@@ -67,7 +67,12 @@ enum {
      * pack time: column 4c+g, g = 0 in, 1 remember, 2 out, 3 cell (the
      * reference's chunk order, :344).  aux0 = c (prev cell).
      * y1 = c' = s(f)c + s(i)tanh(g);  y0 = h' = s(o)tanh(c')                 */
-    RAMNET_EPI_LSTM = 5
+    RAMNET_EPI_LSTM = 5,
+    /* Last decoder + prediction head fused (statenet.py:116-117,313 on top of submodules.py:89-95):
+     * t = relu(acc + b) is never written; y0[m] = sigmoid(sum_n t[n]*aux0[n] + aux1[0]) (depth,
+     * [N,1,H,W]); y1[m] (may be NULL) = the logit.  aux0 = pred weight [Cout], aux1 = pred bias [1].
+     * TF32 path only, Cout a multiple of 32 and <= 256 (one Cout slice per tile). */
+    RAMNET_EPI_BIAS_RELU_PRED = 6
 };
 
 enum {

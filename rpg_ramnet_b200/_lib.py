@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libramnet_sm100a.so')
 
 MMA_FP32, MMA_TF32 = 0, 1
-EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RES_RELU, EPI_GRU_RU, EPI_GRU_OUT, EPI_LSTM = range(6)
+EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RES_RELU, EPI_GRU_RU, EPI_GRU_OUT, EPI_LSTM, EPI_BIAS_RELU_PRED = range(7)
 FLAG_ROUND_TF32 = 1
 
 

@@ -52,47 +52,77 @@ extern "C" int64_t ramnet_launch_count(const ramnet_handle *h) { return h ? h->l
 
 // ---------------------------------------------------------------------------------
 // decoder prologue: (x + skip) -> bilinear x2, align_corners=False, NHWC
-//   out[2m]   = .25 in[m-1] + .75 in[m];  out[2m+1] = .75 in[m] + .25 in[m+1], clamped
-// One thread per (output pixel, 4 channels): 4 float4 loads (x2 with skip), 1 store.
-// HBM-bound: reads C*4 B per input pixel (L1/L2 serve the 4x reuse), writes 4x that.
+//   out[2m]   = .25 in[m-1] + .75 in[m];  out[2m+1] = .75 in[m] + .25 in[m+1], indices clamped
+// HBM-bound: reads C*4 B per input pixel (+ skip), writes 4x that.  One thread owns 4 channels
+// of one input row and slides a 3x3 window along x: 3 (6 with skip) 16-byte loads and 4 16-byte
+// stores per input pixel instead of 4-8 loads per OUTPUT pixel; consecutive threads are
+// consecutive channel quads, so every warp access is a contiguous run of the NHWC pixel.
+// Association matches ATen's upsample_bilinear2d: w_y0*(w_x0*a + w_x1*b) + w_y1*(w_x0*c + w_x1*d).
 // ---------------------------------------------------------------------------------
+__device__ __forceinline__ float4 f4_lerp(float wa, const float4 &a, float wb, const float4 &b) {
+    return make_float4(wa * a.x + wb * b.x, wa * a.y + wb * b.y, wa * a.z + wb * b.z, wa * a.w + wb * b.w);
+}
+
+constexpr int kUpStrip = 8;   // input pixels per thread along x
+
 __global__ void __launch_bounds__(256) upsample2x_add_kernel(const float4 *__restrict__ x,
                                                              const float4 *__restrict__ skip,
                                                              float4 *__restrict__ y, int N, int H, int W,
                                                              int C4, int round) {
-    const int64_t total = (int64_t)N * 2 * H * 2 * W * C4;
+    const int strips = (W + kUpStrip - 1) / kUpStrip;
+    const int64_t total = (int64_t)N * H * strips * C4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % C4);
         int64_t p = i / C4;
-        const int ox = (int)(p % (2 * W));
-        p /= 2 * W;
-        const int oy = (int)(p % (2 * H));
-        const int n = (int)(p / (2 * H));
-        // source coordinate (o + .5)/2 - .5 : floor index and weight of the upper tap
-        const int x0 = (ox >> 1) + ((ox & 1) ? 0 : -1), y0 = (oy >> 1) + ((oy & 1) ? 0 : -1);
-        const float wx1 = (ox & 1) ? 0.25f : 0.75f, wy1 = (oy & 1) ? 0.25f : 0.75f;
-        const int xa = max(x0, 0), xb = min(x0 + 1, W - 1), ya = max(y0, 0), yb = min(y0 + 1, H - 1);
-        const int64_t base = (int64_t)n * H * W;
-        auto ld = [&](int yy, int xx) {
-            const int64_t o = (base + (int64_t)yy * W + xx) * C4 + c;
+        const int xs = (int)(p % strips);
+        p /= strips;
+        const int yi = (int)(p % H);
+        const int n = (int)(p / H);
+        const int64_t img = (int64_t)n * H * W;
+        const int rows[3] = {max(yi - 1, 0), yi, min(yi + 1, H - 1)};
+        auto ld = [&](int r, int xx) {
+            const int64_t o = (img + (int64_t)rows[r] * W + xx) * C4 + c;
             float4 a = __ldg(x + o);
             if (skip != nullptr) {
-                float4 s = __ldg(skip + o);
+                const float4 s = __ldg(skip + o);
                 a.x += s.x; a.y += s.y; a.z += s.z; a.w += s.w;
             }
             return a;
         };
-        const float4 v00 = ld(ya, xa), v01 = ld(ya, xb), v10 = ld(yb, xa), v11 = ld(yb, xb);
-        const float wx0 = 1.f - wx1, wy0 = 1.f - wy1;
-        // same association as ATen's upsample_bilinear2d: w_y0*(w_x0*a + w_x1*b) + w_y1*(w_x0*c + w_x1*d)
-        float4 r;
-        r.x = wy0 * (wx0 * v00.x + wx1 * v01.x) + wy1 * (wx0 * v10.x + wx1 * v11.x);
-        r.y = wy0 * (wx0 * v00.y + wx1 * v01.y) + wy1 * (wx0 * v10.y + wx1 * v11.y);
-        r.z = wy0 * (wx0 * v00.z + wx1 * v01.z) + wy1 * (wx0 * v10.z + wx1 * v11.z);
-        r.w = wy0 * (wx0 * v00.w + wx1 * v01.w) + wy1 * (wx0 * v10.w + wx1 * v11.w);
-        if (round) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
-        y[i] = r;
+        const int xbeg = xs * kUpStrip, xend = min(xbeg + kUpStrip, W);
+        float4 prev[3], cur[3], nxt[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            prev[r] = ld(r, max(xbeg - 1, 0));
+            cur[r] = ld(r, xbeg);
+        }
+        float4 *out0 = y + (((int64_t)n * 2 * H + 2 * yi) * 2 * W) * C4 + c;   // output row 2*yi
+        float4 *out1 = out0 + (int64_t)2 * W * C4;                              // output row 2*yi + 1
+        for (int xi = xbeg; xi < xend; ++xi) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) nxt[r] = ld(r, min(xi + 1, W - 1));
+            float4 he[3], ho[3];   // horizontal blends: even / odd output column of each of the 3 input rows
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                he[r] = f4_lerp(0.25f, prev[r], 0.75f, cur[r]);
+                ho[r] = f4_lerp(0.75f, cur[r], 0.25f, nxt[r]);
+            }
+            float4 o00 = f4_lerp(0.25f, he[0], 0.75f, he[1]), o01 = f4_lerp(0.25f, ho[0], 0.75f, ho[1]);
+            float4 o10 = f4_lerp(0.75f, he[1], 0.25f, he[2]), o11 = f4_lerp(0.75f, ho[1], 0.25f, ho[2]);
+            if (round) {
+                o00 = make_float4(round_tf32(o00.x), round_tf32(o00.y), round_tf32(o00.z), round_tf32(o00.w));
+                o01 = make_float4(round_tf32(o01.x), round_tf32(o01.y), round_tf32(o01.z), round_tf32(o01.w));
+                o10 = make_float4(round_tf32(o10.x), round_tf32(o10.y), round_tf32(o10.z), round_tf32(o10.w));
+                o11 = make_float4(round_tf32(o11.x), round_tf32(o11.y), round_tf32(o11.z), round_tf32(o11.w));
+            }
+            out0[(int64_t)(2 * xi) * C4] = o00;
+            out0[(int64_t)(2 * xi + 1) * C4] = o01;
+            out1[(int64_t)(2 * xi) * C4] = o10;
+            out1[(int64_t)(2 * xi + 1) * C4] = o11;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { prev[r] = cur[r]; cur[r] = nxt[r]; }
+        }
     }
 }
 
@@ -100,7 +130,7 @@ extern "C" int ramnet_upsample2x_add(ramnet_handle *h, const float *x, const flo
                                      int W, int C, int flags, void *stream) {
     RAMNET_CHECK_ARG(h && x && y, "ramnet_upsample2x_add: NULL argument");
     RAMNET_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "ramnet_upsample2x_add: bad shape N=%d H=%d W=%d C=%d (C%%4)", N, H, W, C);
-    const int64_t total = (int64_t)N * 4 * H * W * (C / 4);
+    const int64_t total = (int64_t)N * H * ((W + kUpStrip - 1) / kUpStrip) * (C / 4);
     const int blocks = (int)imin64((total + 255) / 256, (int64_t)h->sm_count * 16);
     upsample2x_add_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
         (const float4 *)x, (const float4 *)skip, (float4 *)y, N, H, W, C / 4, (flags & RAMNET_FLAG_ROUND_TF32) != 0);

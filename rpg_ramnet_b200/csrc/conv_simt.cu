@@ -135,7 +135,7 @@ static int validate_desc(const ramnet_conv_desc *d) {
     RAMNET_CHECK_ARG(d->C0 > 0 && d->C0 % 16 == 0 && d->C1 >= 0 && d->C1 % 16 == 0,
                      "conv: channel counts C0=%d C1=%d must be multiples of 16", d->C0, d->C1);
     RAMNET_CHECK_ARG(d->Cout > 0 && d->Cout % 4 == 0, "conv: Cout=%d must be a positive multiple of 4", d->Cout);
-    RAMNET_CHECK_ARG(d->epilogue >= RAMNET_EPI_BIAS && d->epilogue <= RAMNET_EPI_LSTM, "conv: bad epilogue %d", d->epilogue);
+    RAMNET_CHECK_ARG(d->epilogue >= RAMNET_EPI_BIAS && d->epilogue <= RAMNET_EPI_BIAS_RELU_PRED, "conv: bad epilogue %d", d->epilogue);
     RAMNET_CHECK_ARG(d->mma_kind == RAMNET_MMA_FP32 || d->mma_kind == RAMNET_MMA_TF32, "conv: bad mma_kind %d", d->mma_kind);
     if (d->epilogue == RAMNET_EPI_GRU_RU) RAMNET_CHECK_ARG(d->Cout % 8 == 0, "conv: GRU_RU needs Cout = 2C with C%%4 == 0");
     if (d->epilogue == RAMNET_EPI_LSTM) RAMNET_CHECK_ARG(d->Cout % 16 == 0, "conv: LSTM needs Cout = 4C with C%%4 == 0");
@@ -160,6 +160,12 @@ extern "C" int ramnet_conv_fwd(ramnet_handle *h, const ramnet_conv_desc *d, cons
         case RAMNET_EPI_GRU_RU: RAMNET_CHECK_ARG(aux0 && y1, "conv_fwd: GRU_RU needs aux0 (h) and y1"); break;
         case RAMNET_EPI_GRU_OUT: RAMNET_CHECK_ARG(aux0 && aux1, "conv_fwd: GRU_OUT needs aux0 (h) and aux1 (u)"); break;
         case RAMNET_EPI_LSTM: RAMNET_CHECK_ARG(aux0 && y1, "conv_fwd: LSTM needs aux0 (c) and y1"); break;
+        case RAMNET_EPI_BIAS_RELU_PRED:
+            RAMNET_CHECK_ARG(aux0 && aux1, "conv_fwd: PRED needs aux0 (pred weight) and aux1 (pred bias)");
+            if (d->mma_kind != RAMNET_MMA_TF32 || d->stride != 1 || d->ksize == 1 || d->Cout % 32 || d->Cout > 256)
+                return ramnet_set_error(RAMNET_EUNSUPPORTED, "conv_fwd: the fused prediction epilogue needs mma_kind=TF32, "
+                                        "stride 1, ksize 3/5 and Cout %% 32 == 0, Cout <= 256");
+            break;
         default: break;
     }
     EpiParams ep{bias, aux0, aux1, y0, y1, d->Cout, d->flags};

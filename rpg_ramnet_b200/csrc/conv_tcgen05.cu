@@ -574,6 +574,37 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
             };
             auto next_unit = [&](const Unit &u) { return (u.j + 1 < nch) ? make_unit(u.tl, u.j + 1) : make_unit(u.tl + 1, 0); };
 
+            if constexpr (EPI == RAMNET_EPI_BIAS_RELU_PRED) {
+                // fused 1x1 prediction head: every row's BN = Cout activations are reduced in registers by the
+                // first warp of each lane quarter; the 32-channel decoder output never leaves the SM
+                if (half == 0) {
+                    for (int tl = 0; tl < ntiles; ++tl) {
+                        const int ox = x0 + (tl & (g.PTX - 1)) * 8 + (row & 7), oy = y0 + (tl >> g.ptx_log2) * 16 + (row >> 3);
+                        float dot = 0.f;
+                        for (int c = 0; c < g.BN; c += 16) {
+                            uint32_t r[16];
+                            tmem_ld16_issue(lane_base + (uint32_t)(tl * g.BN + c), r);
+                            tmem_ld_wait(r);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float4 bb = ep.bias ? __ldg(reinterpret_cast<const float4 *>(ep.bias + c) + q)
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                                const float4 ww = __ldg(reinterpret_cast<const float4 *>(ep.aux0 + c) + q);
+                                dot = fmaf(fmaxf(__uint_as_float(r[4 * q]) + bb.x, 0.f), ww.x, dot);
+                                dot = fmaf(fmaxf(__uint_as_float(r[4 * q + 1]) + bb.y, 0.f), ww.y, dot);
+                                dot = fmaf(fmaxf(__uint_as_float(r[4 * q + 2]) + bb.z, 0.f), ww.z, dot);
+                                dot = fmaf(fmaxf(__uint_as_float(r[4 * q + 3]) + bb.w, 0.f), ww.w, dot);
+                            }
+                        }
+                        if (oy < g.H && ox < g.W) {
+                            const int64_t m = ((int64_t)img * g.H + oy) * g.W + ox;
+                            const float logit = dot + __ldg(ep.aux1);
+                            if (ep.y1) ep.y1[m] = logit;
+                            ep.y0[m] = sigmoidf_(logit);
+                        }
+                    }
+                }
+            } else {
             uint32_t ra[16], rb[16];
             EpiAux<16> xa, xb;
             if (units > 0) {
@@ -608,6 +639,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
                         }
                     }
                 }
+            }
             }
             // all tcgen05.ld of this warp have completed (waited above): hand the buffer back to the MMA warp
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -796,6 +828,7 @@ bool plan_halo(const ramnet_handle *h, const ramnet_conv_desc *d, HaloGeom *g) {
     HaloGeom cand;
     for (const auto &sh : shapes)
         for (int bn = 256; bn >= 16; bn >>= 1) {
+            if (d->epilogue == RAMNET_EPI_BIAS_RELU_PRED && bn != d->Cout) continue;   // one slice: whole-row reduction
             if (!fill_halo(d, &cand, sh[0], sh[1], bn, 0, 0)) continue;
             const double c = halo_cost(h, d, cand);
             if (best < 0 || c < best) { best = c; *g = cand; }
@@ -814,7 +847,10 @@ int conv_fwd_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *x0, 
     RAMNET_CHECK_ARG(d->stride == 1 || (d->H % 2 == 0 && d->W % 2 == 0), "conv_fwd(tf32): stride 2 needs even H, W");
     RAMNET_CHECK_ARG((((uintptr_t)x0 | (uintptr_t)x1 | (uintptr_t)wp) & 15) == 0, "conv_fwd(tf32): 16-byte alignment");
     HaloGeom hg;
-    if (plan_halo(h, d, &hg)) {
+    const bool halo_ok = plan_halo(h, d, &hg);
+    if (!halo_ok && d->epilogue == RAMNET_EPI_BIAS_RELU_PRED)
+        return ramnet_set_error(RAMNET_EUNSUPPORTED, "conv_fwd: no halo-kernel configuration for the fused prediction epilogue");
+    if (halo_ok) {
         if (getenv("RAMNET_DEBUG"))
             fprintf(stderr, "[ramnet] halo plan %dx%d C=%d+%d->%d k%d: tiles %dx%d HX=%d HY=%d BN=%d a_st=%d b_st=%d nbuf=%d items=%d\n",
                     d->H, d->W, d->C0, d->C1, d->Cout, d->ksize, hg.PTX, hg.PTY, hg.HX, hg.HY, hg.BN, hg.a_stages,
@@ -847,6 +883,7 @@ int conv_fwd_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *x0, 
             case RAMNET_EPI_GRU_RU: return launch_halo<RAMNET_EPI_GRU_RU>(h, m0, m1, mw, hg, ep, s);
             case RAMNET_EPI_GRU_OUT: return launch_halo<RAMNET_EPI_GRU_OUT>(h, m0, m1, mw, hg, ep, s);
             case RAMNET_EPI_LSTM: return launch_halo<RAMNET_EPI_LSTM>(h, m0, m1, mw, hg, ep, s);
+            case RAMNET_EPI_BIAS_RELU_PRED: return launch_halo<RAMNET_EPI_BIAS_RELU_PRED>(h, m0, m1, mw, hg, ep, s);
         }
     }
     TcGeom g;

@@ -240,13 +240,22 @@ class StateNetPhasedRecurrent(BaseStateNet):
             x = E.run_conv(y, p2, ops.EPI_BIAS_RES_RELU, kind, aux0=x, round_out=True)
         if not self.use_upsample_conv:
             raise RamnetError('use_upsample_conv=False (TransposedConvLayer) is not implemented yet')
+        pr = self.pred
+        pw, pb = pr.conv2d.weight.detach().float(), None if pr.conv2d.bias is None else pr.conv2d.bias.detach().float()
+        pw, pb = E._fold_norm(pw, pb, getattr(pr, 'norm_layer', None), pr.norm, self.training)
         for i, dec in enumerate(self.decoders):
             skip = None if i == 0 else ops.as_nhwc(pick(super_states[n - i - 1]))
             up = ops.upsample2x_add(x, skip, round_tf32=(kind == ops.MMA_TF32))
             p = E.pack_conv(cache, f'dec{i}', dec.conv2d, kind, getattr(dec, 'norm_layer', None), dec.norm,
                             self.training)
+            last = i == len(self.decoders) - 1
+            if last and kind == ops.MMA_TF32 and p.Cout % 32 == 0 and p.Cout <= 256:
+                # last decoder + pred + sigmoid in one kernel: the 32-channel full-resolution tensor is never written
+                N, _, Hh, Ww = up.shape
+                pbias = pb if pb is not None else torch.zeros(1, dtype=torch.float32, device=up.device)
+                logits = torch.empty((N, 1, Hh, Ww), dtype=torch.float32, device=up.device) if return_logits else None
+                depth = ops.conv_fwd(up, None, p.w, p.b, p.Cout, p.ksize, p.stride, ops.EPI_BIAS_RELU_PRED, kind,
+                                     aux0=pw.reshape(-1).contiguous(), aux1=pbias.reshape(-1).contiguous(), out1=logits)
+                return (depth, logits) if return_logits else depth
             x = E.run_conv(up, p, ops.EPI_BIAS_RELU, kind)
-        pr = self.pred
-        w, b = pr.conv2d.weight.detach().float(), None if pr.conv2d.bias is None else pr.conv2d.bias.detach().float()
-        w, b = E._fold_norm(w, b, getattr(pr, 'norm_layer', None), pr.norm, self.training)
-        return ops.pred_sigmoid(x, None, w, b, want_logits=return_logits)
+        return ops.pred_sigmoid(x, None, pw, pb, want_logits=return_logits)

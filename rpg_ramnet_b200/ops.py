@@ -10,7 +10,8 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (ConvDesc, EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RES_RELU, EPI_GRU_OUT, EPI_GRU_RU, EPI_LSTM,  # noqa
+from ._lib import (ConvDesc, EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RELU_PRED, EPI_BIAS_RES_RELU, EPI_GRU_OUT, EPI_GRU_RU,  # noqa
+                   EPI_LSTM,
                    FLAG_ROUND_TF32, MMA_FP32, MMA_TF32, check)
 
 
@@ -175,11 +176,15 @@ def conv_fwd(x0: torch.Tensor, x1: Optional[torch.Tensor], w_packed: torch.Tenso
         y0, y1 = _out(out0, Cout // 2), _out(out1, Cout // 2)
     elif epilogue == EPI_LSTM:
         y0, y1 = _out(out0, Cout // 4), _out(out1, Cout // 4)
+    elif epilogue == EPI_BIAS_RELU_PRED:      # depth [N,1,H,W] (+ logits when out1 is given)
+        y0 = torch.empty((N, 1, Ho, Wo), dtype=torch.float32, device=dev) if out0 is None else out0
+        y1 = out1
     else:
         y0 = _out(out0, Cout)
-    for a, nm in ((aux0, 'aux0'), (aux1, 'aux1')):
-        if a is not None:
-            _check_nhwc(a, 'conv_fwd ' + nm)
+    if epilogue != EPI_BIAS_RELU_PRED:
+        for a, nm in ((aux0, 'aux0'), (aux1, 'aux1')):
+            if a is not None:
+                _check_nhwc(a, 'conv_fwd ' + nm)
     d = ConvDesc(N, H, W, C0, C1, Cout, ksize, stride, epilogue, mma_kind, FLAG_ROUND_TF32 if round_tf32 else 0, 0)
     lib = _lib.load()
     nws = lib.ramnet_conv_workspace_bytes(ctypes.byref(d))
@@ -187,7 +192,7 @@ def conv_fwd(x0: torch.Tensor, x1: Optional[torch.Tensor], w_packed: torch.Tenso
     with _Prof('conv', 2.0 * N * Ho * Wo * Cout * (C0 + C1) * ksize * ksize, dev):
         check(lib.ramnet_conv_fwd(_h(x0), ctypes.byref(d), _p(x0), _p(x1), _p(w_packed), _p(bias), _p(aux0),
                                   _p(aux1), _p(y0), _p(y1), _p(ws), nws, _stream(x0)))
-    return (y0, y1) if y1 is not None else y0
+    return (y0, y1) if (y1 is not None and epilogue != EPI_BIAS_RELU_PRED) else y0
 
 
 def upsample2x_add(x: torch.Tensor, skip: Optional[torch.Tensor], round_tf32: bool) -> torch.Tensor:
