@@ -302,9 +302,13 @@ __global__ void __launch_bounds__(kThreads) conv_tcgen05_kernel(const __grid_con
 // chunk k is computed and stored.
 // ================================================================================================
 struct HaloGeom {
-    int N, H, W, Cout;
+    int N, H, W, Cout;       // input height / width
+    int Ho, Wo;              // output height / width
     int C0, C1;
-    int ks, pad;
+    int ks, pad, stride;
+    int nplanes;             // 1 (stride 1) or 4 (stride 2: input parity planes (py, px))
+    int plane_stride;        // bytes between parity planes inside one halo stage (multiple of 1024)
+    int lo;                  // first halo row/column relative to the patch origin (floor(-pad/stride))
     int PTX, PTY, ptx_log2;  // M-tiles per patch along x / y (tile = 8 x 16 pixels); PTX is a power of two
     int HX, HY;              // halo buffer pitch (pixels) and rows
     int patches_x, patches_y;
@@ -367,8 +371,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
                                                                             HaloGeom g, EpiParams ep) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int a_bytes = g.HX * g.HY * kChunk * 4;
-    const int a_stride = (a_bytes + 1023) & ~1023;
+    const int plane_bytes = g.HX * g.HY * kChunk * 4;
+    const int a_bytes = g.nplanes * plane_bytes;             // TMA transaction bytes per halo stage
+    const int a_stride = g.nplanes * g.plane_stride;
     const int b_bytes = g.BN * kChunk * 4;
     uint8_t *smem_b = smem + (size_t)g.a_stages * a_stride;
     uint64_t *a_full = reinterpret_cast<uint64_t *>(smem_b + (size_t)g.b_stages * b_bytes);
@@ -378,6 +383,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
     uint64_t *acc_full = b_empty + g.b_stages;   // [2]
     uint64_t *acc_empty = acc_full + 2;          // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    uint32_t *tap_tab = tmem_slot + 2;           // [ks*ks] halo offset of each filter tap, in 16-byte units
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = g.PTX * g.PTY;
@@ -400,6 +406,20 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 3) {
+        // tap (r, s) -> where its A tile starts inside a halo stage.  Stride 1: one plane, shift (r, s).
+        // Stride 2: input row 2*oy + (r - pad) = 2*(oy + dy) + py -> parity plane (py, px), shift (dy, dx).
+        if (lane < g.ks * g.ks) {
+            const int r = lane / g.ks, sx = lane % g.ks;
+            int off;
+            if (g.stride == 1) {
+                off = (r * g.HX + sx) * 8;
+            } else {
+                const int ry = r - g.pad, rx = sx - g.pad;
+                const int dy = ry >> 1, py = ry & 1, dx = rx >> 1, px = rx & 1;     // arithmetic shift = floor
+                off = (py * 2 + px) * (g.plane_stride >> 4) + ((dy - g.lo) * g.HX + (dx - g.lo)) * 8;
+            }
+            tap_tab[lane] = (uint32_t)off;
+        }
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"(tmem_cols)
                      : "memory");
@@ -439,8 +459,18 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
                 if (elect_one()) {
                     mbar_expect_tx(a_full + stage, (uint32_t)a_bytes);
                     const bool second = ch >= chunks0;
-                    tma_load_4d(smem + (size_t)stage * a_stride, second ? &map_x1 : &map_x0, a_full + stage,
-                                (second ? ch - chunks0 : ch) * kChunk, x0 - g.pad, y0 - g.pad, img);
+                    const CUtensorMap *mx = second ? &map_x1 : &map_x0;
+                    const int c = (second ? ch - chunks0 : ch) * kChunk;
+                    uint8_t *dst = smem + (size_t)stage * a_stride;
+                    if (g.stride == 1) {
+                        tma_load_4d(dst, mx, a_full + stage, c, x0 + g.lo, y0 + g.lo, img);
+                    } else {
+                        const int Csrc = second ? g.C1 : g.C0;
+#pragma unroll
+                        for (int pl = 0; pl < 4; ++pl)   // (py, px) parity planes of the 5-D view (2C, W/2, 2, H/2, N)
+                            tma_load_5d(dst + (size_t)pl * g.plane_stride, mx, a_full + stage, (pl & 1) * Csrc + c,
+                                        x0 + g.lo, pl >> 1, y0 + g.lo, img);
+                    }
                 }
                 __syncwarp();
                 if (++stage == g.a_stages) { stage = 0; phase ^= 1; }
@@ -491,9 +521,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
             for (int ch = 0; ch < chunks; ++ch) {
                 mbar_wait_t(a_full + sa, pa, prof, w0);
                 const uint32_t a16 = (smem_u32(smem + (size_t)sa * a_stride) & 0x3FFFFu) >> 4;
-                uint32_t row16 = 0;   // (r * HX) * 8
-                for (int r = 0; r < g.ks; ++r, row16 += (uint32_t)g.HX * 8u) {
-                    for (int sx = 0; sx < g.ks; ++sx) {
+                for (int r = 0, tap = 0; r < g.ks; ++r) {
+                    for (int sx = 0; sx < g.ks; ++sx, ++tap) {
                         // One barrier round trip (~100+ cycles even when complete) tells us about EVERY weight stage:
                         // lane i polls the stage i slots ahead; the ballot gives the run of ready stages.
                         if (ready == 0) {
@@ -512,7 +541,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
                         --ready;
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + (size_t)sb * b_bytes));
-                        const uint32_t tap16 = a16 + row16 + (uint32_t)sx * 8u;
+                        const uint32_t tap16 = a16 + tap_tab[tap];
                         const uint32_t first = (uint32_t)(ch | r | sx);
                         if (elect_one()) {
 #pragma unroll
@@ -567,8 +596,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
                 Unit u;
                 u.tl = tl; u.j = j;
                 const int ox = x0 + (tl & (g.PTX - 1)) * 8 + (row & 7), oy = y0 + (tl >> g.ptx_log2) * 16 + (row >> 3);
-                u.valid = oy < g.H && ox < g.W;
-                u.m = ((int64_t)img * g.H + oy) * g.W + ox;
+                u.valid = oy < g.Ho && ox < g.Wo;
+                u.m = ((int64_t)img * g.Ho + oy) * g.Wo + ox;
                 u.col = half * 16 + 32 * j;
                 return u;
             };
@@ -596,8 +625,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
                                 dot = fmaf(fmaxf(__uint_as_float(r[4 * q + 3]) + bb.w, 0.f), ww.w, dot);
                             }
                         }
-                        if (oy < g.H && ox < g.W) {
-                            const int64_t m = ((int64_t)img * g.H + oy) * g.W + ox;
+                        if (oy < g.Ho && ox < g.Wo) {
+                            const int64_t m = ((int64_t)img * g.Ho + oy) * g.Wo + ox;
                             const float logit = dot + __ldg(ep.aux1);
                             if (ep.y1) ep.y1[m] = logit;
                             ep.y0[m] = sigmoidf_(logit);
@@ -719,9 +748,9 @@ int launch(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap &m1, const
 template <int EPI>
 int launch_halo(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap &m1, const CUtensorMap &mw,
                 const HaloGeom &g, const EpiParams &ep, cudaStream_t s) {
-    const size_t a_stride = ((size_t)g.HX * g.HY * kChunk * 4 + 1023) & ~(size_t)1023;
+    const size_t a_stride = (size_t)g.nplanes * g.plane_stride;
     const size_t smem = g.a_stages * a_stride + (size_t)g.b_stages * g.BN * kChunk * 4 +
-                        (2 * g.a_stages + 2 * g.b_stages + 4) * 8 + 16 + 1024;
+                        (2 * g.a_stages + 2 * g.b_stages + 4) * 8 + 16 + 32 * 4 + 1024;
     static size_t configured = 0;
     if (smem > configured) {
         RAMNET_CUDA(cudaFuncSetAttribute(conv_tcgen05_halo_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -765,17 +794,24 @@ int halo_mode_env() {
 bool fill_halo(const ramnet_conv_desc *d, HaloGeom *g, int ptx, int pty, int bn, int a_st, int b_st) {
     if (d->Cout % bn || ptx * pty > 4 || ptx * pty * bn > 512 || (ptx & (ptx - 1))) return false;
     g->N = d->N; g->H = d->H; g->W = d->W; g->Cout = d->Cout; g->C0 = d->C0; g->C1 = d->C1;
-    g->ks = d->ksize; g->pad = d->ksize / 2; g->prof = nullptr;
+    g->Ho = conv_out_dim(d->H, d->stride); g->Wo = conv_out_dim(d->W, d->stride);
+    g->ks = d->ksize; g->pad = d->ksize / 2; g->stride = d->stride; g->prof = nullptr;
+    g->nplanes = d->stride == 1 ? 1 : 4;
+    // halo extent along one axis, in plane pixels: shifts floor((r - pad)/stride) for r = 0..ks-1
+    auto fdiv = [](int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); };
+    g->lo = fdiv(-g->pad, d->stride);
+    const int hi = fdiv(d->ksize - 1 - g->pad, d->stride);
     g->PTX = ptx; g->PTY = pty; g->ptx_log2 = ptx == 4 ? 2 : (ptx == 2 ? 1 : 0);
-    g->HX = ptx * 8 + d->ksize - 1; g->HY = pty * 16 + d->ksize - 1;
+    g->HX = ptx * 8 + (hi - g->lo); g->HY = pty * 16 + (hi - g->lo);
     if (g->HX > 256 || g->HY > 256) return false;
     g->BN = bn; g->n_slices = d->Cout / bn;
-    g->patches_x = (d->W + ptx * 8 - 1) / (ptx * 8); g->patches_y = (d->H + pty * 16 - 1) / (pty * 16);
+    g->patches_x = (g->Wo + ptx * 8 - 1) / (ptx * 8); g->patches_y = (g->Ho + pty * 16 - 1) / (pty * 16);
     const int64_t items = (int64_t)g->patches_x * g->patches_y * d->N * g->n_slices;
     if (items > 0x7fffffff) return false;
     g->items = (int)items;
     g->nbuf = (2 * ptx * pty * bn <= 512) ? 2 : 1;
-    const size_t a_stride = ((size_t)g->HX * g->HY * kChunk * 4 + 1023) & ~(size_t)1023;
+    g->plane_stride = (int)(((size_t)g->HX * g->HY * kChunk * 4 + 1023) & ~(size_t)1023);
+    const size_t a_stride = (size_t)g->nplanes * g->plane_stride;
     const size_t b_bytes = (size_t)bn * kChunk * 4;
     const size_t budget = 222 * 1024;
     if (a_st <= 0) {   // automatic pipeline depths
@@ -800,7 +836,7 @@ bool fill_halo(const ramnet_conv_desc *d, HaloGeom *g, int ptx, int pty, int bn,
 //  - persistent scheduling => ceil(items / SMs) rounds.
 double halo_cost(const ramnet_handle *h, const ramnet_conv_desc *d, const HaloGeom &g) {
     const int ntiles = g.PTX * g.PTY, chunks = (d->C0 + d->C1) / kChunk, taps = d->ksize * d->ksize;
-    const double halo_bytes = (double)g.HX * g.HY * 128.0;
+    const double halo_bytes = (double)g.nplanes * g.HX * g.HY * 128.0;
     const double smem_tap = (ntiles * 4.0 * (128 + g.BN) * 32.0 + g.BN * 128.0 + halo_bytes / taps) / 128.0;
     const double math_tap = ntiles * 4.0 * g.BN / 2.0;
     const double tap = (smem_tap > math_tap ? smem_tap : math_tap) + 20.0;
@@ -817,7 +853,8 @@ double halo_cost(const ramnet_handle *h, const ramnet_conv_desc *d, const HaloGe
 // should stay on the per-tap kernel (stride 2, 1x1, or no configuration fits shared memory).
 bool plan_halo(const ramnet_handle *h, const ramnet_conv_desc *d, HaloGeom *g) {
     if (halo_mode_env() & 4) return false;           // RAMNET_HALO_MODE=4: force the per-tap kernel (A/B tests)
-    if (d->stride != 1 || d->ksize == 1) return false;
+    if (d->ksize == 1) return false;
+    if (d->stride == 2 && ((d->H | d->W) & 1)) return false;
     if (const char *f = getenv("RAMNET_HALO_FORCE")) {   // tuning aid: "PTX,PTY,BN,a_stages,b_stages"
         int ptx, pty, bn, ast, bst;
         if (sscanf(f, "%d,%d,%d,%d,%d", &ptx, &pty, &bn, &ast, &bst) == 5 && fill_halo(d, g, ptx, pty, bn, ast, bst))
@@ -852,15 +889,23 @@ int conv_fwd_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *x0, 
         return ramnet_set_error(RAMNET_EUNSUPPORTED, "conv_fwd: no halo-kernel configuration for the fused prediction epilogue");
     if (halo_ok) {
         if (getenv("RAMNET_DEBUG"))
-            fprintf(stderr, "[ramnet] halo plan %dx%d C=%d+%d->%d k%d: tiles %dx%d HX=%d HY=%d BN=%d a_st=%d b_st=%d nbuf=%d items=%d\n",
-                    d->H, d->W, d->C0, d->C1, d->Cout, d->ksize, hg.PTX, hg.PTY, hg.HX, hg.HY, hg.BN, hg.a_stages,
+            fprintf(stderr, "[ramnet] halo plan s%d %dx%d C=%d+%d->%d k%d: tiles %dx%d HX=%d HY=%d BN=%d a_st=%d b_st=%d nbuf=%d items=%d\n",
+                    d->stride, d->H, d->W, d->C0, d->C1, d->Cout, d->ksize, hg.PTX, hg.PTY, hg.HX, hg.HY, hg.BN, hg.a_stages,
                     hg.b_stages, hg.nbuf, hg.items);
         CUtensorMap m0, m1, mw;
-        cuuint32_t box[4] = {kChunk, (cuuint32_t)hg.HX, (cuuint32_t)hg.HY, 1};
         auto enc_act = [&](CUtensorMap *m, const float *x, int C) {
-            cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
-            cuuint64_t str[3] = {(cuuint64_t)C * 4, (cuuint64_t)d->W * C * 4, (cuuint64_t)d->H * d->W * C * 4};
-            return encode(h, m, x, 4, dims, str, box);
+            if (d->stride == 1) {
+                cuuint32_t box[4] = {kChunk, (cuuint32_t)hg.HX, (cuuint32_t)hg.HY, 1};
+                cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+                cuuint64_t str[3] = {(cuuint64_t)C * 4, (cuuint64_t)d->W * C * 4, (cuuint64_t)d->H * d->W * C * 4};
+                return encode(h, m, x, 4, dims, str, box);
+            }
+            // stride 2: 5-D parity view (2C, W/2, 2, H/2, N); one box = one parity plane of the halo
+            cuuint32_t box[5] = {kChunk, (cuuint32_t)hg.HX, 1, (cuuint32_t)hg.HY, 1};
+            cuuint64_t dims[5] = {(cuuint64_t)2 * C, (cuuint64_t)d->W / 2, 2, (cuuint64_t)d->H / 2, (cuuint64_t)d->N};
+            cuuint64_t str[4] = {(cuuint64_t)2 * C * 4, (cuuint64_t)d->W * C * 4, (cuuint64_t)2 * d->W * C * 4,
+                                 (cuuint64_t)d->H * d->W * C * 4};
+            return encode(h, m, x, 5, dims, str, box);
         };
         int rc = enc_act(&m0, x0, d->C0);
         if (rc) return rc;
