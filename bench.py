@@ -309,9 +309,14 @@ def main_ours(args):
     for k, f, a, b in prof:
         if k != 'conv':
             other[k] = other.get(k, 0.0) + a.elapsed_time(b)
+    traffic, traffic_src = None, None
+    import glob
+    for f in sorted(glob.glob(os.path.join(ROOT, 'profiles', '*conv_traffic.json'))):
+        t = json.load(open(f))
+        traffic, traffic_src = t.get('bytes_per_launch'), t.get('source')
     roofline = {'bound': 'tensor', 'kernel': 'conv_implicit_gemm (ramnet_conv_fwd, all instances)',
                 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
-                'traffic': None, 'peak_source': peak_src + ', bf16 sustained; kind::tf32 nominal peak is half of bf16',
+                'traffic': traffic, 'traffic_unit': 'DRAM bytes per conv launch (read+write), ncu', 'traffic_source': traffic_src, 'peak_source': peak_src + ', bf16 sustained; kind::tf32 nominal peak is half of bf16',
                 'launches_per_step': n_conv, 'ms_per_step_in_kernel': conv_ms,
                 'algorithmic_gflop_per_step': conv_flops / 1e9,
                 'other_kernels_ms_per_step': other, 'mma_kind': args.mma_kind}
