@@ -142,7 +142,9 @@ int ramnet_head_conv(ramnet_handle *h, const float *x_nchw, const float *w_oihw,
 size_t ramnet_conv_workspace_bytes(const ramnet_conv_desc *d);
 int ramnet_conv_fwd(ramnet_handle *h, const ramnet_conv_desc *d, const float *x0, const float *x1,
                     const float *w_packed, const float *bias, const float *aux0, const float *aux1,
-                    float *y0, float *y1, void *workspace, size_t workspace_bytes, void *stream);
+                    float *y0, float *y1, float *y2, void *workspace, size_t workspace_bytes, void *stream);
+/* y2 (may be NULL) is the training stash: RAMNET_EPI_GRU_RU writes r = sigmoid(reset), RAMNET_EPI_GRU_OUT
+ * writes o = tanh(candidate) — the values autograd would have kept for backward. */
 /* [Cout, Cin, k, k] fp32 (nn.Conv2d layout) -> the layout `mma_kind` consumes:
  *   FP32: [k*k][Cin][Cout]           TF32: [k*k][Cout][Cin], values rounded to TF32 (rna).
  * `lstm_interleave` != 0 permutes output channels to 4c+g (RAMNET_EPI_LSTM). */
@@ -169,6 +171,35 @@ int ramnet_nchw_to_nhwc(ramnet_handle *h, const float *x, float *y, int N, int C
 int ramnet_nhwc_to_nchw(ramnet_handle *h, const float *x, float *y, int N, int C, int H, int W,
                         void *stream);
 int ramnet_round_tf32(ramnet_handle *h, const float *x, float *y, int64_t n, void *stream);
+
+/* ---- a-13  backward building blocks -------------------------------------- *
+ * Replace what loss.backward() (trainer/lstm_trainer.py:450) dispatches to cuDNN/ATen:
+ * data gradient = ramnet_conv_fwd on dZ with ramnet_pack_weights_dgrad weights (stride 2: after
+ * ramnet_zero_insert2x); weight/bias gradient = ramnet_conv_wgrad, ACCUMULATED (+=) into buffers in
+ * nn.Conv2d layout [Cout, C0+C1, k, k] / [Cout]; the rest are pointwise adjoints of the fused epilogues.
+ * dz: gradient w.r.t. the GEMM output (pre-activation), NHWC [N, Ho, Wo, Cout]. */
+int ramnet_conv_wgrad(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz, const float *x0,
+                      const float *x1, float *dw_oihw, float *db, void *stream);
+int ramnet_head_conv_wgrad(ramnet_handle *h, const float *x_nchw, const float *dz_nhwc, float *dw_oihw,
+                           float *db, int N, int Cin, int H, int W, int Cout, void *stream);
+int ramnet_pack_weights_dgrad(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin,
+                              int ksize, int mma_kind, int ci_begin, int ci_count, void *stream);
+int ramnet_zero_insert2x(ramnet_handle *h, const float *x, float *y, int N, int H, int W, int C, int Hout,
+                         int Wout, void *stream);
+/* dz = dy * (y > 0) */
+int ramnet_relu_bwd(ramnet_handle *h, const float *dy, const float *y, float *dz, int64_t n, void *stream);
+/* ConvGRU adjoints (submodules.py:446-452).  gru_out_bwd: dzo = dh'*u*(1-o^2); columns [C,2C) of dzru =
+ * dh'*(o-h)*u*(1-u); dh = dh'*(1-u).  gru_ru_bwd: columns [0,C) of dzru = drh*h*r*(1-r); dh += drh*r. */
+int ramnet_gru_out_bwd(ramnet_handle *h, const float *dhn, const float *hprev, const float *u, const float *o,
+                       float *dzo, float *dzru, float *dh, int64_t M, int C, void *stream);
+int ramnet_gru_ru_bwd(ramnet_handle *h, const float *drh, const float *hprev, const float *r, float *dzru,
+                      float *dh, int64_t M, int C, void *stream);
+/* pred + sigmoid adjoint: dx[m,c] = g*w[c], dw[c] += sum g*x[m,c], db += sum g, g = ddepth*s(1-s) */
+int ramnet_pred_bwd(ramnet_handle *h, const float *ddepth, const float *depth, const float *x, const float *w,
+                    float *dx, float *dw, float *db, int64_t M, int C, void *stream);
+/* adjoint of ramnet_upsample2x_add: dx (= dskip) [N,H,W,C] from dy [N,2H,2W,C] */
+int ramnet_upsample2x_bwd(ramnet_handle *h, const float *dy, float *dx, int N, int H, int W, int C,
+                          void *stream);
 
 /* ---- a-12  scale_invariant_loss ---------------------------------------- *
  * Replaces model/loss.py:6-9 (boolean-mask gathers + host sync).

@@ -54,6 +54,7 @@ struct EpiParams {
     const float *aux1;  // u
     float *y0;
     float *y1;
+    float *y2;  // training stash: GRU_RU -> r, GRU_OUT -> o (candidate), else unused; may be nullptr
     int Cout;   // GEMM N
     int flags;  // RAMNET_FLAG_*
 };
@@ -137,8 +138,9 @@ __device__ __forceinline__ void epilogue_finish(const EpiParams &p, int64_t m, i
 #pragma unroll
             for (int j = 0; j < NV; j += 4) {
                 const float4 h = x.a[j / 4];
-                st4(p.y1 + m * C + n0 + j, h.x * sigmoidf_(v[j]), h.y * sigmoidf_(v[j + 1]),
-                    h.z * sigmoidf_(v[j + 2]), h.w * sigmoidf_(v[j + 3]));
+                const float r0 = sigmoidf_(v[j]), r1 = sigmoidf_(v[j + 1]), r2 = sigmoidf_(v[j + 2]), r3 = sigmoidf_(v[j + 3]);
+                if (p.y2) *reinterpret_cast<float4 *>(p.y2 + m * C + n0 + j) = make_float4(r0, r1, r2, r3);
+                st4(p.y1 + m * C + n0 + j, h.x * r0, h.y * r1, h.z * r2, h.w * r3);
             }
         } else {  // update gate -> y0 = u   (kept full fp32: it is a pointwise operand only)
 #pragma unroll
@@ -150,9 +152,10 @@ __device__ __forceinline__ void epilogue_finish(const EpiParams &p, int64_t m, i
 #pragma unroll
         for (int j = 0; j < NV; j += 4) {
             const float4 h = x.a[j / 4], u = x.b[j / 4];
-            st4(p.y0 + m * p.Cout + n0 + j, h.x * (1.f - u.x) + tanhf(v[j]) * u.x,
-                h.y * (1.f - u.y) + tanhf(v[j + 1]) * u.y, h.z * (1.f - u.z) + tanhf(v[j + 2]) * u.z,
-                h.w * (1.f - u.w) + tanhf(v[j + 3]) * u.w);
+            const float o0 = tanhf(v[j]), o1 = tanhf(v[j + 1]), o2 = tanhf(v[j + 2]), o3 = tanhf(v[j + 3]);
+            if (p.y2) *reinterpret_cast<float4 *>(p.y2 + m * p.Cout + n0 + j) = make_float4(o0, o1, o2, o3);
+            st4(p.y0 + m * p.Cout + n0 + j, h.x * (1.f - u.x) + o0 * u.x, h.y * (1.f - u.y) + o1 * u.y,
+                h.z * (1.f - u.z) + o2 * u.z, h.w * (1.f - u.w) + o3 * u.w);
         }
     } else if constexpr (EPI == RAMNET_EPI_LSTM) {
         const int C = p.Cout >> 2;

@@ -1,0 +1,433 @@
+// Backward pass building blocks: what autograd's cuDNN/ATen backward kernels do
+// for the reference (loss.backward() at trainer/lstm_trainer.py:450), as explicit kernels.
+//
+//  * data gradient of a convolution = the forward implicit-GEMM kernel (tcgen05 halo kernel) run on
+//    dZ with tap-flipped, channel-transposed weights (ramnet_pack_weights_dgrad); a stride-2 conv's
+//    data gradient first zero-inserts dZ to the input resolution (ramnet_zero_insert2x);
+//  * weight gradient dW[co][ci][r][s] = sum_pixels dZ[p][co] * X[p*stride + (r,s) - pad][ci] is a GEMM
+//    whose K dimension is the pixel axis: first version = fp32 FFMA, 64x64 tiles, split-K over pixel
+//    ranges with fp32 atomics, accumulating straight into the nn.Conv2d-layout .grad buffer (so
+//    BPTT's sum over timesteps costs nothing extra);
+//  * the pointwise adjoints of the fused epilogues (ReLU mask, GRU / LSTM gates, sigmoid head,
+//    bilinear x2 + skip).
+// All tensors NHWC fp32 as in the forward pass.
+#include "common.cuh"
+
+namespace {
+constexpr int WB = 64, WK = 16;   // wgrad tile: 64 cout x 64 cin, 16 pixels per K step
+
+struct WgradGeom {
+    int N, H, W, C0, C1, Cout, ks, stride, pad, Ho, Wo;
+    int64_t M;            // output pixels
+    int pix_per_block;    // split-K range
+};
+
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradGeom g, const float *__restrict__ dz,
+                                                         const float *__restrict__ x0, const float *__restrict__ x1,
+                                                         float *__restrict__ dw) {
+    __shared__ __align__(16) float As[WK * WB];   // [k = pixel][co]
+    __shared__ __align__(16) float Bs[WK * WB];   // [k = pixel][ci]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int Ct = g.C0 + g.C1;
+    const int ci_tiles = (Ct + WB - 1) / WB;
+    const int tap = blockIdx.y / ci_tiles, ci0 = (blockIdx.y % ci_tiles) * WB;
+    const int co0 = blockIdx.z * WB;
+    const int r = tap / g.ks, s = tap % g.ks;
+    const int64_t p_begin = (int64_t)blockIdx.x * g.pix_per_block;
+    const int64_t p_end = p_begin + g.pix_per_block < g.M ? p_begin + g.pix_per_block : g.M;
+    // loader mapping: 16 pixels x 16 channel quads
+    const int lp = tid >> 4, lq = tid & 15;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int64_t p0 = p_begin; p0 < p_end; p0 += WK) {
+        const int64_t p = p0 + lp;
+        float4 a = make_float4(0, 0, 0, 0), b = make_float4(0, 0, 0, 0);
+        if (p < p_end) {
+            const int co = co0 + lq * 4;
+            if (co < g.Cout) a = *reinterpret_cast<const float4 *>(dz + p * g.Cout + co);
+            const int ox = (int)(p % g.Wo), oy = (int)((p / g.Wo) % g.Ho), n = (int)(p / ((int64_t)g.Wo * g.Ho));
+            const int iy = oy * g.stride + r - g.pad, ix = ox * g.stride + s - g.pad;
+            const int ci = ci0 + lq * 4;
+            if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W && ci < Ct) {
+                const int64_t ip = ((int64_t)n * g.H + iy) * g.W + ix;
+                b = (ci < g.C0) ? *reinterpret_cast<const float4 *>(x0 + ip * g.C0 + ci)
+                                : *reinterpret_cast<const float4 *>(x1 + ip * g.C1 + (ci - g.C0));
+            }
+        }
+        __syncthreads();
+        *reinterpret_cast<float4 *>(&As[lp * WB + lq * 4]) = a;
+        *reinterpret_cast<float4 *>(&Bs[lp * WB + lq * 4]) = b;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < WK; ++k) {
+            const float4 av = *reinterpret_cast<const float4 *>(&As[k * WB + ty * 4]);
+            const float4 bv = *reinterpret_cast<const float4 *>(&Bs[k * WB + tx * 4]);
+            const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+        }
+    }
+    // dW is [Cout][Ct][ks][ks] (nn.Conv2d layout), accumulated
+    const int taps = g.ks * g.ks;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int co = co0 + ty * 4 + i;
+        if (co >= g.Cout) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ci = ci0 + tx * 4 + j;
+            if (ci < Ct) atomicAdd(dw + ((int64_t)co * Ct + ci) * taps + tap, acc[i][j]);
+        }
+    }
+}
+
+// db[c] += sum over rows of dz[M][C]
+__global__ void __launch_bounds__(256) colsum_kernel(const float *__restrict__ dz, int64_t M, int C,
+                                                     float *__restrict__ db, int rows_per_block) {
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc = 0.f;
+        for (int64_t r = r0; r < r1; ++r) acc += dz[r * C + c];
+        atomicAdd(db + c, acc);
+    }
+}
+
+// y[n, 2h, 2w, c] = x[n, h, w, c], zeros elsewhere (the input of a stride-2 conv's data gradient)
+__global__ void __launch_bounds__(256) zero_insert_kernel(const float4 *__restrict__ x, float4 *__restrict__ y, int N,
+                                                          int H, int W, int C4, int Hout, int Wout) {
+    const int64_t total = (int64_t)N * Hout * Wout * C4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4);
+        int64_t p = i / C4;
+        const int ox = (int)(p % Wout);
+        p /= Wout;
+        const int oy = (int)(p % Hout);
+        const int n = (int)(p / Hout);
+        float4 v = make_float4(0, 0, 0, 0);
+        if (!(ox & 1) && !(oy & 1) && (oy >> 1) < H && (ox >> 1) < W)
+            v = x[(((int64_t)n * H + (oy >> 1)) * W + (ox >> 1)) * C4 + c];
+        y[i] = v;
+    }
+}
+
+// [Cout, Cin, k, k] -> data-gradient weights for the FORWARD kernels: a conv with Cin' = Cout, Cout' = Cin,
+// taps flipped.  FP32: [tap'][Cout][Cin]   TF32: [tap'][Cin][Cout] (K-major B operand), rna-rounded.
+// ci_begin/ci_count select the slice of input channels (one launch per source of a virtual concat).
+__global__ void pack_dgrad_kernel(const float *__restrict__ w, float *__restrict__ out, int Cout, int Cin, int taps,
+                                  int kind, int ci_begin, int ci_count) {
+    const int64_t total = (int64_t)Cout * ci_count * taps;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int tap = (int)(i % taps);
+        const int cil = (int)((i / taps) % ci_count);
+        const int co = (int)(i / ((int64_t)taps * ci_count));
+        const float v = w[((int64_t)co * Cin + ci_begin + cil) * taps + tap];
+        const int ftap = taps - 1 - tap;   // flip both axes
+        if (kind == RAMNET_MMA_FP32)
+            out[((int64_t)ftap * Cout + co) * ci_count + cil] = v;          // [tap][K = Cout][N = ci]
+        else
+            out[((int64_t)ftap * ci_count + cil) * Cout + co] = round_tf32(v);  // [tap][N = ci][K = Cout]
+    }
+}
+
+// ---------------------------------------------------------------- pointwise adjoints (float4 over NHWC)
+__device__ __forceinline__ float4 ld4(const float *p, int64_t i) { return reinterpret_cast<const float4 *>(p)[i]; }
+__device__ __forceinline__ void st4(float *p, int64_t i, float4 v) { reinterpret_cast<float4 *>(p)[i] = v; }
+#define F4_MAP2(a, b, expr)                                                                         \
+    make_float4(([&](float A, float B) { return expr; })(a.x, b.x), ([&](float A, float B) { return expr; })(a.y, b.y), \
+                ([&](float A, float B) { return expr; })(a.z, b.z), ([&](float A, float B) { return expr; })(a.w, b.w))
+
+// dz = dy * (y > 0)
+__global__ void relu_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ y, float *__restrict__ dz,
+                                int64_t n4) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 g = ld4(dy, i), v = ld4(y, i);
+        st4(dz, i, F4_MAP2(g, v, B > 0.f ? A : 0.f));
+    }
+}
+
+// ConvGRU candidate+blend adjoint.  in: dh' (dhn), h, u, o.  out: dzo = dh'*u*(1-o^2), dzu = dh'*(o-h)*u*(1-u)
+// written into the update half of dzru [M, 2C] (columns [C, 2C)), dh = dh'*(1-u).
+__global__ void gru_out_bwd_kernel(const float *__restrict__ dhn, const float *__restrict__ h, const float *__restrict__ u,
+                                   const float *__restrict__ o, float *__restrict__ dzo, float *__restrict__ dzru,
+                                   float *__restrict__ dh, int64_t M, int C) {
+    const int C4 = C >> 2;
+    const int64_t n4 = M * C4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / C4;
+        const int c = (int)(i % C4);
+        const float4 g = ld4(dhn, i), hv = ld4(h, i), uv = ld4(u, i), ov = ld4(o, i);
+        float4 a, b, d;
+        a.x = g.x * uv.x * (1.f - ov.x * ov.x); a.y = g.y * uv.y * (1.f - ov.y * ov.y);
+        a.z = g.z * uv.z * (1.f - ov.z * ov.z); a.w = g.w * uv.w * (1.f - ov.w * ov.w);
+        b.x = g.x * (ov.x - hv.x) * uv.x * (1.f - uv.x); b.y = g.y * (ov.y - hv.y) * uv.y * (1.f - uv.y);
+        b.z = g.z * (ov.z - hv.z) * uv.z * (1.f - uv.z); b.w = g.w * (ov.w - hv.w) * uv.w * (1.f - uv.w);
+        d.x = g.x * (1.f - uv.x); d.y = g.y * (1.f - uv.y); d.z = g.z * (1.f - uv.z); d.w = g.w * (1.f - uv.w);
+        st4(dzo, i, a);
+        st4(dzru, m * (2 * C4) + C4 + c, b);
+        st4(dh, i, d);
+    }
+}
+
+// ConvGRU reset adjoint.  in: drh (grad of h*r), h, r.  out: dzr = drh*h*r*(1-r) into columns [0, C) of dzru,
+// dh += drh*r.
+__global__ void gru_ru_bwd_kernel(const float *__restrict__ drh, const float *__restrict__ h, const float *__restrict__ r,
+                                  float *__restrict__ dzru, float *__restrict__ dh, int64_t M, int C) {
+    const int C4 = C >> 2;
+    const int64_t n4 = M * C4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / C4;
+        const int c = (int)(i % C4);
+        const float4 g = ld4(drh, i), hv = ld4(h, i), rv = ld4(r, i);
+        float4 a, d = ld4(dh, i);
+        a.x = g.x * hv.x * rv.x * (1.f - rv.x); a.y = g.y * hv.y * rv.y * (1.f - rv.y);
+        a.z = g.z * hv.z * rv.z * (1.f - rv.z); a.w = g.w * hv.w * rv.w * (1.f - rv.w);
+        d.x += g.x * rv.x; d.y += g.y * rv.y; d.z += g.z * rv.z; d.w += g.w * rv.w;
+        st4(dzru, m * (2 * C4) + c, a);
+        st4(dh, i, d);
+    }
+}
+
+// prediction head adjoint: dlogit = ddepth * s(1-s); dx[m, c] = dlogit[m] * w[c]; dw[c] += sum_m dlogit*x[m,c]; db += sum dlogit
+__global__ void __launch_bounds__(256) pred_bwd_kernel(const float *__restrict__ ddepth, const float *__restrict__ depth,
+                                                       const float *__restrict__ x, const float *__restrict__ w,
+                                                       float *__restrict__ dx, float *__restrict__ dw,
+                                                       float *__restrict__ db, int64_t M, int C) {
+    extern __shared__ float sacc[];   // [C + 1]
+    for (int c = threadIdx.x; c <= C; c += blockDim.x) sacc[c] = 0.f;
+    __syncthreads();
+    const int lane8 = threadIdx.x & 7;
+    float wreg[8], dwreg[8];   // C <= 64: lane handles channels lane8*4.. (+32)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { wreg[j] = 0.f; dwreg[j] = 0.f; }
+    for (int c = lane8 * 4, j = 0; c < C; c += 32, j += 4)
+        for (int e = 0; e < 4; ++e) wreg[j + e] = w[c + e];
+    float dbacc = 0.f;
+    const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> 3;
+    for (int64_t m = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3; m < M; m += stride) {
+        const float s = depth[m];
+        const float dl = ddepth[m] * s * (1.f - s);
+        if (lane8 == 0) dbacc += dl;
+        for (int c = lane8 * 4, j = 0; c < C; c += 32, j += 4) {
+            const float4 xv = *reinterpret_cast<const float4 *>(x + m * C + c);
+            *reinterpret_cast<float4 *>(dx + m * C + c) = make_float4(dl * wreg[j], dl * wreg[j + 1], dl * wreg[j + 2], dl * wreg[j + 3]);
+            dwreg[j] += dl * xv.x; dwreg[j + 1] += dl * xv.y; dwreg[j + 2] += dl * xv.z; dwreg[j + 3] += dl * xv.w;
+        }
+    }
+    for (int c = lane8 * 4, j = 0; c < C; c += 32, j += 4)
+        for (int e = 0; e < 4; ++e) atomicAdd(&sacc[c + e], dwreg[j + e]);
+    if (lane8 == 0) atomicAdd(&sacc[C], dbacc);
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(dw + c, sacc[c]);
+    if (threadIdx.x == 0 && db) atomicAdd(db, sacc[C]);
+}
+
+// adjoint of (x + skip) -> bilinear x2: dx[m] gathers from the <= 3x3 output pixels it feeds; dskip = dx.
+__global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const float4 *__restrict__ dy, float4 *__restrict__ dx, int N,
+                                                             int H, int W, int C4) {
+    const int64_t total = (int64_t)N * H * W * C4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4);
+        int64_t p = i / C4;
+        const int xi = (int)(p % W);
+        p /= W;
+        const int yi = (int)(p % H);
+        const int n = (int)(p / H);
+        // output index o reads input floor-index f(o) = (o>>1) - (o even) with weight (o even ? .25 : .75) and f+1 with the
+        // complement, both clamped to [0, n-1].  Enumerate the outputs 2m-2 .. 2m+2 that can touch input m.
+        float wy[6];
+        int oyv[6], ny = 0;
+        for (int o = 2 * yi - 2; o <= 2 * yi + 3; ++o) {
+            if (o < 0 || o >= 2 * H) continue;
+            const int f = (o >> 1) - ((o & 1) ? 0 : 1);
+            const float w1 = (o & 1) ? 0.25f : 0.75f;       // weight of tap f+1
+            float wgt = 0.f;
+            if (max(f, 0) == yi) wgt += 1.f - w1;
+            if (min(f + 1, H - 1) == yi) wgt += w1;
+            if (wgt != 0.f) { wy[ny] = wgt; oyv[ny] = o; ++ny; }
+        }
+        float4 acc = make_float4(0, 0, 0, 0);
+        for (int o = 2 * xi - 2; o <= 2 * xi + 3; ++o) {
+            if (o < 0 || o >= 2 * W) continue;
+            const int f = (o >> 1) - ((o & 1) ? 0 : 1);
+            const float w1 = (o & 1) ? 0.25f : 0.75f;
+            float wx = 0.f;
+            if (max(f, 0) == xi) wx += 1.f - w1;
+            if (min(f + 1, W - 1) == xi) wx += w1;
+            if (wx == 0.f) continue;
+            for (int k = 0; k < ny; ++k) {
+                const float4 g = dy[(((int64_t)n * 2 * H + oyv[k]) * 2 * W + o) * C4 + c];
+                const float ww = wx * wy[k];
+                acc.x += ww * g.x; acc.y += ww * g.y; acc.z += ww * g.z; acc.w += ww * g.w;
+            }
+        }
+        dx[i] = acc;
+    }
+}
+
+
+// Head conv weight gradient: dW[co][ci][r][s] = sum_{n,y,x} dz[n,y,x,co] * x[n,ci,y+r-2,x+s-2]   (NCHW input,
+// Cin <= 8, 5x5, NHWC dz with Cout <= 32).  CTA = one 8x32 pixel tile: input halo and dz tile in shared
+// memory, thread = one (ci, r, s) x 16 output channels, 256-pixel reduction in registers, then atomics.
+constexpr int HW_TW = 32, HW_TH = 8;
+__global__ void __launch_bounds__(256) head_wgrad_kernel(const float *__restrict__ x, const float *__restrict__ dz,
+                                                         float *__restrict__ dw, int N, int Cin, int H, int W,
+                                                         int Cout) {
+    __shared__ float in_s[8 * (HW_TH + 4) * (HW_TW + 4)];
+    __shared__ __align__(16) float dz_s[HW_TH * HW_TW * 32];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * HW_TW, y0 = blockIdx.y * HW_TH, n = blockIdx.z;
+    constexpr int IW = HW_TW + 4, IH = HW_TH + 4;
+    for (int i = tid; i < Cin * IH * IW; i += 256) {
+        const int c = i / (IH * IW), r = (i / IW) % IH, sx = i % IW;
+        const int gy = y0 + r - 2, gx = x0 + sx - 2;
+        in_s[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(x + (((int64_t)n * Cin + c) * H + gy) * W + gx) : 0.f;
+    }
+    for (int i = tid; i < HW_TH * HW_TW * 8; i += 256) {   // float4 granules: pixel p, quad q
+        const int p = i >> 3, q = i & 7;
+        const int gy = y0 + p / HW_TW, gx = x0 + p % HW_TW;
+        float4 v = make_float4(0, 0, 0, 0);
+        if (gy < H && gx < W && q * 4 < Cout) v = *reinterpret_cast<const float4 *>(dz + (((int64_t)n * H + gy) * W + gx) * Cout + q * 4);
+        *reinterpret_cast<float4 *>(&dz_s[p * 32 + q * 4]) = v;
+    }
+    __syncthreads();
+    const int combo = tid >> 1, half = tid & 1;
+    if (combo >= Cin * 25) return;
+    const int ci = combo / 25, r = (combo % 25) / 5, sx = combo % 5;
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int p = 0; p < HW_TH * HW_TW; ++p) {
+        const float v = in_s[(ci * IH + p / HW_TW + r) * IW + p % HW_TW + sx];
+        const float4 *d4 = reinterpret_cast<const float4 *>(&dz_s[p * 32 + half * 16]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 g = d4[q];
+            acc[4 * q] = fmaf(v, g.x, acc[4 * q]);
+            acc[4 * q + 1] = fmaf(v, g.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(v, g.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(v, g.w, acc[4 * q + 3]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int co = half * 16 + j;
+        if (co < Cout) atomicAdd(dw + (((int64_t)co * Cin + ci) * 5 + r) * 5 + sx, acc[j]);
+    }
+}
+
+int grid_for(ramnet_handle *h, int64_t n) { return (int)imin64((n + 255) / 256, (int64_t)h->sm_count * 16); }
+}  // namespace
+
+extern "C" int ramnet_conv_wgrad(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz, const float *x0,
+                                 const float *x1, float *dw_oihw, float *db, void *stream) {
+    RAMNET_CHECK_ARG(h && d && dz && x0 && dw_oihw, "conv_wgrad: NULL argument");
+    RAMNET_CHECK_ARG(d->C0 % 4 == 0 && d->C1 % 4 == 0 && d->Cout % 4 == 0, "conv_wgrad: channel counts must be multiples of 4");
+    RAMNET_CHECK_ARG((d->C1 == 0) == (x1 == nullptr), "conv_wgrad: x1 and C1 disagree");
+    WgradGeom g;
+    g.N = d->N; g.H = d->H; g.W = d->W; g.C0 = d->C0; g.C1 = d->C1; g.Cout = d->Cout; g.ks = d->ksize;
+    g.stride = d->stride; g.pad = d->ksize / 2;
+    g.Ho = conv_out_dim(d->H, d->stride); g.Wo = conv_out_dim(d->W, d->stride);
+    g.M = (int64_t)g.N * g.Ho * g.Wo;
+    const int Ct = d->C0 + d->C1, taps = d->ksize * d->ksize;
+    const int tiles = taps * ((Ct + WB - 1) / WB) * ((d->Cout + WB - 1) / WB);
+    // split K so that the launch has ~8 CTAs per SM
+    int64_t splits = ((int64_t)h->sm_count * 8 + tiles - 1) / tiles;
+    int64_t ppb = (g.M + splits - 1) / splits;
+    ppb = ((ppb + WK - 1) / WK) * WK;
+    if (ppb < 256) ppb = 256;
+    g.pix_per_block = (int)ppb;
+    dim3 grid((unsigned)((g.M + ppb - 1) / ppb), (unsigned)(taps * ((Ct + WB - 1) / WB)), (unsigned)((d->Cout + WB - 1) / WB));
+    conv_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, dz, x0, x1, dw_oihw);
+    RAMNET_LAUNCH_CHECK(h);
+    if (db) {
+        const int rpb = 2048;
+        colsum_kernel<<<(unsigned)((g.M + rpb - 1) / rpb), 256, 0, (cudaStream_t)stream>>>(dz, g.M, d->Cout, db, rpb);
+        RAMNET_LAUNCH_CHECK(h);
+    }
+    return RAMNET_OK;
+}
+
+extern "C" int ramnet_zero_insert2x(ramnet_handle *h, const float *x, float *y, int N, int H, int W, int C, int Hout,
+                                    int Wout, void *stream) {
+    RAMNET_CHECK_ARG(h && x && y && C % 4 == 0 && Hout >= 2 * H - 1 && Wout >= 2 * W - 1, "zero_insert2x: bad argument");
+    const int64_t total = (int64_t)N * Hout * Wout * (C / 4);
+    zero_insert_kernel<<<grid_for(h, total), 256, 0, (cudaStream_t)stream>>>((const float4 *)x, (float4 *)y, N, H, W, C / 4,
+                                                                            Hout, Wout);
+    RAMNET_LAUNCH_CHECK(h);
+    return RAMNET_OK;
+}
+
+extern "C" int ramnet_pack_weights_dgrad(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin,
+                                         int ksize, int mma_kind, int ci_begin, int ci_count, void *stream) {
+    RAMNET_CHECK_ARG(h && w_oihw && w_packed && ci_begin >= 0 && ci_count > 0 && ci_begin + ci_count <= Cin,
+                     "pack_weights_dgrad: bad argument");
+    const int64_t total = (int64_t)Cout * ci_count * ksize * ksize;
+    pack_dgrad_kernel<<<grid_for(h, total), 256, 0, (cudaStream_t)stream>>>(w_oihw, w_packed, Cout, Cin, ksize * ksize,
+                                                                           mma_kind, ci_begin, ci_count);
+    RAMNET_LAUNCH_CHECK(h);
+    return RAMNET_OK;
+}
+
+extern "C" int ramnet_relu_bwd(ramnet_handle *h, const float *dy, const float *y, float *dz, int64_t n, void *stream) {
+    RAMNET_CHECK_ARG(h && dy && y && dz && n > 0 && n % 4 == 0, "relu_bwd: bad argument");
+    relu_bwd_kernel<<<grid_for(h, n / 4), 256, 0, (cudaStream_t)stream>>>(dy, y, dz, n / 4);
+    RAMNET_LAUNCH_CHECK(h);
+    return RAMNET_OK;
+}
+
+extern "C" int ramnet_gru_out_bwd(ramnet_handle *h, const float *dhn, const float *hprev, const float *u, const float *o,
+                                  float *dzo, float *dzru, float *dh, int64_t M, int C, void *stream) {
+    RAMNET_CHECK_ARG(h && dhn && hprev && u && o && dzo && dzru && dh && M > 0 && C % 4 == 0, "gru_out_bwd: bad argument");
+    gru_out_bwd_kernel<<<grid_for(h, M * (C / 4)), 256, 0, (cudaStream_t)stream>>>(dhn, hprev, u, o, dzo, dzru, dh, M, C);
+    RAMNET_LAUNCH_CHECK(h);
+    return RAMNET_OK;
+}
+
+extern "C" int ramnet_gru_ru_bwd(ramnet_handle *h, const float *drh, const float *hprev, const float *r, float *dzru,
+                                 float *dh, int64_t M, int C, void *stream) {
+    RAMNET_CHECK_ARG(h && drh && hprev && r && dzru && dh && M > 0 && C % 4 == 0, "gru_ru_bwd: bad argument");
+    gru_ru_bwd_kernel<<<grid_for(h, M * (C / 4)), 256, 0, (cudaStream_t)stream>>>(drh, hprev, r, dzru, dh, M, C);
+    RAMNET_LAUNCH_CHECK(h);
+    return RAMNET_OK;
+}
+
+extern "C" int ramnet_pred_bwd(ramnet_handle *h, const float *ddepth, const float *depth, const float *x, const float *w,
+                               float *dx, float *dw, float *db, int64_t M, int C, void *stream) {
+    RAMNET_CHECK_ARG(h && ddepth && depth && x && w && dx && dw && M > 0 && C % 4 == 0 && C <= 64, "pred_bwd: bad argument (C <= 64)");
+    const int blocks = (int)imin64((M * 8 + 255) / 256, (int64_t)h->sm_count * 8);
+    pred_bwd_kernel<<<blocks, 256, (C + 1) * sizeof(float), (cudaStream_t)stream>>>(ddepth, depth, x, w, dx, dw, db, M, C);
+    RAMNET_LAUNCH_CHECK(h);
+    return RAMNET_OK;
+}
+
+extern "C" int ramnet_upsample2x_bwd(ramnet_handle *h, const float *dy, float *dx, int N, int H, int W, int C,
+                                     void *stream) {
+    RAMNET_CHECK_ARG(h && dy && dx && N > 0 && H > 0 && W > 0 && C % 4 == 0, "upsample2x_bwd: bad argument");
+    const int64_t total = (int64_t)N * H * W * (C / 4);
+    upsample2x_bwd_kernel<<<grid_for(h, total), 256, 0, (cudaStream_t)stream>>>((const float4 *)dy, (float4 *)dx, N, H, W, C / 4);
+    RAMNET_LAUNCH_CHECK(h);
+    return RAMNET_OK;
+}
+
+extern "C" int ramnet_head_conv_wgrad(ramnet_handle *h, const float *x_nchw, const float *dz_nhwc, float *dw_oihw,
+                                      float *db, int N, int Cin, int H, int W, int Cout, void *stream) {
+    RAMNET_CHECK_ARG(h && x_nchw && dz_nhwc && dw_oihw, "head_conv_wgrad: NULL argument");
+    RAMNET_CHECK_ARG(Cin >= 1 && Cin <= 8 && Cout % 4 == 0 && Cout <= 32, "head_conv_wgrad: Cin in [1,8], Cout <= 32 (multiple of 4)");
+    dim3 grid((W + HW_TW - 1) / HW_TW, (H + HW_TH - 1) / HW_TH, N);
+    head_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, dz_nhwc, dw_oihw, N, Cin, H, W, Cout);
+    RAMNET_LAUNCH_CHECK(h);
+    if (db) {
+        const int64_t M = (int64_t)N * H * W;
+        const int rpb = 2048;
+        colsum_kernel<<<(unsigned)((M + rpb - 1) / rpb), 256, 0, (cudaStream_t)stream>>>(dz_nhwc, M, Cout, db, rpb);
+        RAMNET_LAUNCH_CHECK(h);
+    }
+    return RAMNET_OK;
+}

@@ -149,7 +149,8 @@ extern "C" size_t ramnet_conv_workspace_bytes(const ramnet_conv_desc *d) {
 
 extern "C" int ramnet_conv_fwd(ramnet_handle *h, const ramnet_conv_desc *d, const float *x0, const float *x1,
                                const float *w_packed, const float *bias, const float *aux0, const float *aux1,
-                               float *y0, float *y1, void *workspace, size_t workspace_bytes, void *stream) {
+                               float *y0, float *y1, float *y2, void *workspace, size_t workspace_bytes,
+                               void *stream) {
     RAMNET_CHECK_ARG(h != nullptr, "conv_fwd: handle is NULL");
     int rc = validate_desc(d);
     if (rc) return rc;
@@ -168,7 +169,7 @@ extern "C" int ramnet_conv_fwd(ramnet_handle *h, const ramnet_conv_desc *d, cons
             break;
         default: break;
     }
-    EpiParams ep{bias, aux0, aux1, y0, y1, d->Cout, d->flags};
+    EpiParams ep{bias, aux0, aux1, y0, y1, y2, d->Cout, d->flags};
     cudaStream_t s = (cudaStream_t)stream;
     if (d->mma_kind == RAMNET_MMA_TF32) return conv_fwd_tf32(h, d, x0, x1, w_packed, ep, workspace, workspace_bytes, s);
 

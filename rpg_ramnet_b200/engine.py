@@ -38,8 +38,17 @@ class Packed:
     __slots__ = ('w', 'b', 'Cout', 'ksize', 'stride', 'token')
 
 
+# bumped by anything that rewrites parameters behind autograd's back (the fused Adam kernel)
+_WEIGHT_EPOCH = 0
+
+
+def bump_weight_epoch():
+    global _WEIGHT_EPOCH
+    _WEIGHT_EPOCH += 1
+
+
 def _token(tensors, extra):
-    return tuple((t.data_ptr(), t._version, t.device) for t in tensors if t is not None) + tuple(extra)
+    return tuple((t.data_ptr(), t._version, t.device) for t in tensors if t is not None) + tuple(extra) + (_WEIGHT_EPOCH,)
 
 
 def _fold_norm(w, b, norm_mod, norm_kind, training):
@@ -174,6 +183,82 @@ def run_lstm(x, state, p: Packed, kind, out_state=None):
 
 
 # ------------------------------------------------------------------------------------------
+# layer-level entry points: inference launches the kernels directly, training (grad mode) routes
+# through the autograd.Function wrappers whose backward is our own kernels (autograd.py)
+# ------------------------------------------------------------------------------------------
+def needs_grad(*ts) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts)
+
+
+def _no_fold_in_training(norm_mod, norm_kind):
+    if norm_kind in ('BN', 'IN') and norm_mod is not None:
+        raise RamnetError('gradients through folded BatchNorm/InstanceNorm are not implemented '
+                          "(all shipped configs use norm='none')")
+
+
+def head_layer(cache, key, conv, x, tf32):
+    if needs_grad(conv.weight, conv.bias):
+        from .autograd import HeadConvFn
+        return HeadConvFn.apply(x.float().contiguous(), conv.weight, conv.bias, tf32)
+    hp = pack_head(cache, key, conv)
+    return ops.head_conv(x.float(), hp.w, hp.b, round_tf32=tf32)
+
+
+def conv_layer(cache, key, conv, kind, x, epilogue, x1=None, res=None, norm_mod=None, norm_kind=None, training=False,
+               round_out=False):
+    p = pack_conv(cache, key, conv, kind, norm_mod, norm_kind, training)
+    if needs_grad(x, x1, res, conv.weight, conv.bias):
+        _no_fold_in_training(norm_mod, norm_kind)
+        from .autograd import ConvFn
+        return ConvFn.apply(x, x1, res, conv.weight, conv.bias, p.w, epilogue, kind, p.stride,
+                            round_out and kind == ops.MMA_TF32)
+    return run_conv(x, p, epilogue, kind, x1=x1, aux0=res, round_out=round_out)
+
+
+def gru_layer(cache, key, gru, kind, x, h, out_h=None):
+    ru, out = pack_gru(cache, key, gru, kind)
+    params = (gru.reset_gate.weight, gru.reset_gate.bias, gru.update_gate.weight, gru.update_gate.bias,
+              gru.out_gate.weight, gru.out_gate.bias)
+    if needs_grad(x, h, *params):
+        from .autograd import GruFn
+        if h is None:
+            h = ops.zeros_nhwc(x.shape[0], x.shape[1], x.shape[2], x.shape[3], x.device)
+        if h.shape != x.shape:
+            raise RamnetError(f'ConvGRU: state shape {tuple(h.shape)} does not match input {tuple(x.shape)}')
+        return GruFn.apply(x, h, *params, ru, out, kind)
+    return run_gru(x, h, ru, out, kind, out_h=out_h)
+
+
+def lstm_layer(cache, key, lstm, kind, x, state, out_state=None):
+    p = pack_lstm(cache, key, lstm, kind)
+    st = None if state is None else (state[0], state[1])
+    if needs_grad(x, lstm.Gates.weight, lstm.Gates.bias, *(st or ())):
+        raise RamnetError('the ConvLSTM backward pass is not implemented yet: train the shipped ConvGRU configuration '
+                          'or run ConvLSTM models under torch.no_grad()')
+    return run_lstm(x, state, p, kind, out_state=out_state)
+
+
+def upsample_add(x, skip, tf32):
+    if needs_grad(x, skip):
+        from .autograd import UpsampleAddFn
+        return UpsampleAddFn.apply(x, skip, tf32)
+    return ops.upsample2x_add(x, skip, round_tf32=tf32)
+
+
+def pred_layer(x, pred_conv, norm_mod, norm_kind, training, return_logits=False):
+    w = pred_conv.weight
+    b = pred_conv.bias
+    if needs_grad(x, w, b):
+        _no_fold_in_training(norm_mod, norm_kind)
+        if return_logits:
+            raise RamnetError('return_logits is an inference-only debugging aid')
+        from .autograd import PredFn
+        return PredFn.apply(x, w, b)
+    wf, bf = _fold_norm(w.detach().float(), None if b is None else b.detach().float(), norm_mod, norm_kind, training)
+    return ops.pred_sigmoid(x, None, wf, bf, want_logits=return_logits)
+
+
+# ------------------------------------------------------------------------------------------
 # CUDA-graph runner (inference): one captured graph per (pass type, state direction)
 # ------------------------------------------------------------------------------------------
 class GraphRunner:
@@ -226,7 +311,8 @@ class GraphRunner:
 
     def _sig(self):
         return tuple((p.data_ptr(), p._version) for p in self.net.parameters()) + \
-            tuple((b.data_ptr(), b._version) for b in self.net.buffers()) + (self.net.training, self.net._kind())
+            tuple((b.data_ptr(), b._version) for b in self.net.buffers()) + \
+            (self.net.training, self.net._kind(), _WEIGHT_EPOCH)
 
     def run(self, which, x, prev_super):
         sig = self._sig()

@@ -41,11 +41,6 @@ class BaseERGB2Depth(BaseModel):
         self.cuda_graphs = bool(config.get('cuda_graphs', False))
         self.gpu = torch.device('cuda:' + str(config['gpu']))
 
-    def _grad_guard(self):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise RamnetError('autograd through the CUDA graph is not wired yet: call under torch.no_grad() '
-                              '(inference) — the training path is SURVEY.md §8 rows a-13/a-14')
-
 
 class ERGB2Depth(BaseERGB2Depth):
     """model.py:79-111: non-recurrent UNet on item['image']."""
@@ -58,7 +53,6 @@ class ERGB2Depth(BaseERGB2Depth):
                          norm=self.norm, use_upsample_conv=self.use_upsample_conv, mma_kind=self.mma_kind)
 
     def forward(self, item, prev_super_states, prev_states_lstm):
-        self._grad_guard()
         x = item['image'].to(self.gpu, non_blocking=True)
         return {'image': self.unet(x)}, {'image': None}, prev_states_lstm
 
@@ -107,7 +101,6 @@ class ERGB2DepthRecurrent(BaseERGB2Depth):
         return states
 
     def forward(self, item, prev_super_states, prev_states_lstm):
-        self._grad_guard()
         net = self.statenetphasedrecurrent
         predictions, super_states, states_lstm = {}, {}, {}
         if prev_super_states is None and not (self.cuda_graphs and net.graph_capable() and not self.training):

@@ -171,41 +171,38 @@ class StateNetPhasedRecurrent(BaseStateNet):
         if x.dim() != 4 or x.shape[2] % (1 << n) or x.shape[3] % (1 << n):
             raise RamnetError(f'input {tuple(x.shape)}: H and W must be divisible by 2**num_encoders = {1 << n} '
                               '(the reference fails on such shapes too, SURVEY Appendix A)')
-        hp = E.pack_head(cache, which + '/head', head.conv2d)
-        x = ops.head_conv(x.float(), hp.w, hp.b, round_tf32=tf32)
+        x = E.head_layer(cache, which + '/head', head.conv2d, x, tf32)
         if prev_states_lstm is None:
             prev_states_lstm = {'encoders': [None] * n, 'state_comb': [None] * n}
         super_states, states_lstm = [], {'encoders': [], 'state_comb': []}
         for i in range(n):
             enc = encoders[i]
             if self.recurrent_block_type == 'conv':
-                p = E.pack_conv(cache, f'{which}/enc{i}', enc.conv2d, kind, getattr(enc, 'norm_layer', None),
-                                enc.norm, self.training)
-                x = E.run_conv(x, p, ops.EPI_BIAS_RELU, kind, round_out=True)
+                x = E.conv_layer(cache, f'{which}/enc{i}', enc.conv2d, kind, x, ops.EPI_BIAS_RELU,
+                                 norm_mod=getattr(enc, 'norm_layer', None), norm_kind=enc.norm, training=self.training,
+                                 round_out=True)
                 enc_state = None
             else:
-                p = E.pack_conv(cache, f'{which}/enc{i}', enc.conv.conv2d, kind,
-                                getattr(enc.conv, 'norm_layer', None), enc.conv.norm, self.training)
-                x = E.run_conv(x, p, ops.EPI_BIAS_RELU, kind, round_out=True)
-                lp = E.pack_lstm(cache, f'{which}/enc{i}/lstm', enc.recurrent_block, kind)
-                enc_state = E.run_lstm(x, prev_states_lstm['encoders'][i], lp, kind)
+                x = E.conv_layer(cache, f'{which}/enc{i}', enc.conv.conv2d, kind, x, ops.EPI_BIAS_RELU,
+                                 norm_mod=getattr(enc.conv, 'norm_layer', None), norm_kind=enc.conv.norm,
+                                 training=self.training, round_out=True)
+                enc_state = E.lstm_layer(cache, f'{which}/enc{i}/lstm', enc.recurrent_block, kind, x,
+                                         prev_states_lstm['encoders'][i])
                 x = enc_state[0]
             blk = combs[i].recurrent_block
             if self.state_combination == 'convlstm' and not baseline_path:
-                lp = E.pack_lstm(cache, f'{which}/comb{i}', blk, kind)
-                st = E.run_lstm(x, prev_super_state[i], lp, kind,          # state = previous super state [h, c]
-                                out_state=None if out_states is None else out_states[i])
+                st = E.lstm_layer(cache, f'{which}/comb{i}', blk, kind, x, prev_super_state[i],   # state = prev super state
+                                  out_state=None if out_states is None else out_states[i])
                 super_state = comb_state = st
             elif self.state_combination == 'convgru':
-                ru, out = E.pack_gru(cache, f'{which}/comb{i}', blk, kind)
                 hprev = None if prev_super_state[i] is None else ops.as_nhwc(prev_super_state[i])
-                hnew = E.run_gru(x, hprev, ru, out, kind, out_h=None if out_states is None else out_states[i])
+                hnew = E.gru_layer(cache, f'{which}/comb{i}', blk, kind, x, hprev,
+                                   out_h=None if out_states is None else out_states[i])
                 super_state = comb_state = hnew
                 if baseline_path:
                     x = hnew
             else:  # baseline + convlstm: private LSTM state, recurrent output feeds the next encoder
-                lp = E.pack_lstm(cache, f'{which}/comb{i}', blk, kind)
-                st = E.run_lstm(x, prev_states_lstm['state_comb'][i], lp, kind)
+                st = E.lstm_layer(cache, f'{which}/comb{i}', blk, kind, x, prev_states_lstm['state_comb'][i])
                 x, super_state, comb_state = st[0], st[0], st
             super_states.append(super_state)
             states_lstm['encoders'].append(enc_state)
@@ -234,28 +231,32 @@ class StateNetPhasedRecurrent(BaseStateNet):
         for i, rb in enumerate(self.resblocks):
             if rb.norm == 'IN':
                 raise RamnetError("norm='IN' inside ResidualBlock uses per-instance statistics; not implemented")
-            p1 = E.pack_conv(cache, f'res{i}/1', rb.conv1, kind, getattr(rb, 'bn1', None), rb.norm, self.training)
-            p2 = E.pack_conv(cache, f'res{i}/2', rb.conv2, kind, getattr(rb, 'bn2', None), rb.norm, self.training)
-            y = E.run_conv(x, p1, ops.EPI_BIAS_RELU, kind, round_out=True)
-            x = E.run_conv(y, p2, ops.EPI_BIAS_RES_RELU, kind, aux0=x, round_out=True)
+            y = E.conv_layer(cache, f'res{i}/1', rb.conv1, kind, x, ops.EPI_BIAS_RELU, norm_mod=getattr(rb, 'bn1', None),
+                             norm_kind=rb.norm, training=self.training, round_out=True)
+            x = E.conv_layer(cache, f'res{i}/2', rb.conv2, kind, y, ops.EPI_BIAS_RES_RELU, res=x,
+                             norm_mod=getattr(rb, 'bn2', None), norm_kind=rb.norm, training=self.training, round_out=True)
         if not self.use_upsample_conv:
             raise RamnetError('use_upsample_conv=False (TransposedConvLayer) is not implemented yet')
         pr = self.pred
-        pw, pb = pr.conv2d.weight.detach().float(), None if pr.conv2d.bias is None else pr.conv2d.bias.detach().float()
-        pw, pb = E._fold_norm(pw, pb, getattr(pr, 'norm_layer', None), pr.norm, self.training)
+        tf32 = kind == ops.MMA_TF32
         for i, dec in enumerate(self.decoders):
             skip = None if i == 0 else ops.as_nhwc(pick(super_states[n - i - 1]))
-            up = ops.upsample2x_add(x, skip, round_tf32=(kind == ops.MMA_TF32))
-            p = E.pack_conv(cache, f'dec{i}', dec.conv2d, kind, getattr(dec, 'norm_layer', None), dec.norm,
-                            self.training)
+            up = E.upsample_add(x, skip, tf32)
             last = i == len(self.decoders) - 1
-            if last and kind == ops.MMA_TF32 and p.Cout % 32 == 0 and p.Cout <= 256:
+            fuse = last and tf32 and dec.conv2d.out_channels % 32 == 0 and dec.conv2d.out_channels <= 256 and \
+                not E.needs_grad(up, dec.conv2d.weight, dec.conv2d.bias, pr.conv2d.weight, pr.conv2d.bias)
+            if fuse:
                 # last decoder + pred + sigmoid in one kernel: the 32-channel full-resolution tensor is never written
+                p = E.pack_conv(cache, f'dec{i}', dec.conv2d, kind, getattr(dec, 'norm_layer', None), dec.norm,
+                                self.training)
+                pw, pb = pr.conv2d.weight.detach().float(), None if pr.conv2d.bias is None else pr.conv2d.bias.detach().float()
+                pw, pb = E._fold_norm(pw, pb, getattr(pr, 'norm_layer', None), pr.norm, self.training)
                 N, _, Hh, Ww = up.shape
                 pbias = pb if pb is not None else torch.zeros(1, dtype=torch.float32, device=up.device)
                 logits = torch.empty((N, 1, Hh, Ww), dtype=torch.float32, device=up.device) if return_logits else None
                 depth = ops.conv_fwd(up, None, p.w, p.b, p.Cout, p.ksize, p.stride, ops.EPI_BIAS_RELU_PRED, kind,
                                      aux0=pw.reshape(-1).contiguous(), aux1=pbias.reshape(-1).contiguous(), out1=logits)
                 return (depth, logits) if return_logits else depth
-            x = E.run_conv(up, p, ops.EPI_BIAS_RELU, kind)
-        return ops.pred_sigmoid(x, None, pw, pb, want_logits=return_logits)
+            x = E.conv_layer(cache, f'dec{i}', dec.conv2d, kind, up, ops.EPI_BIAS_RELU,
+                             norm_mod=getattr(dec, 'norm_layer', None), norm_kind=dec.norm, training=self.training)
+        return E.pred_layer(x, pr.conv2d, getattr(pr, 'norm_layer', None), pr.norm, self.training, return_logits)

@@ -74,26 +74,28 @@ class UNet(BaseUNet):
         cache, n = self._wcache, self.num_encoders
         if x.dim() != 4 or x.shape[2] % (1 << n) or x.shape[3] % (1 << n):
             raise RamnetError(f'input {tuple(x.shape)}: H and W must be divisible by {1 << n}')
+        if E.needs_grad(*self.parameters()):
+            raise RamnetError('training the non-recurrent UNet baseline (pred on x + head) is not wired yet; '
+                              'call under torch.no_grad()')
         hp = E.pack_head(cache, 'head', self.head.conv2d)
         x = ops.head_conv(x.float(), hp.w, hp.b, round_tf32=tf32)
         head, blocks = x, []
         for i, enc in enumerate(self.encoders):
-            p = E.pack_conv(cache, f'enc{i}', enc.conv2d, kind, getattr(enc, 'norm_layer', None), enc.norm,
-                            self.training)
-            x = E.run_conv(x, p, ops.EPI_BIAS_RELU, kind, round_out=True)
+            x = E.conv_layer(cache, f'enc{i}', enc.conv2d, kind, x, ops.EPI_BIAS_RELU,
+                             norm_mod=getattr(enc, 'norm_layer', None), norm_kind=enc.norm, training=self.training,
+                             round_out=True)
             blocks.append(x)
         for i, rb in enumerate(self.resblocks):
             if rb.norm == 'IN':
                 raise RamnetError("norm='IN' inside ResidualBlock is not implemented")
-            p1 = E.pack_conv(cache, f'res{i}/1', rb.conv1, kind, getattr(rb, 'bn1', None), rb.norm, self.training)
-            p2 = E.pack_conv(cache, f'res{i}/2', rb.conv2, kind, getattr(rb, 'bn2', None), rb.norm, self.training)
-            y = E.run_conv(x, p1, ops.EPI_BIAS_RELU, kind, round_out=True)
-            x = E.run_conv(y, p2, ops.EPI_BIAS_RES_RELU, kind, aux0=x, round_out=True)
+            y = E.conv_layer(cache, f'res{i}/1', rb.conv1, kind, x, ops.EPI_BIAS_RELU, norm_mod=getattr(rb, 'bn1', None),
+                             norm_kind=rb.norm, training=self.training, round_out=True)
+            x = E.conv_layer(cache, f'res{i}/2', rb.conv2, kind, y, ops.EPI_BIAS_RES_RELU, res=x,
+                             norm_mod=getattr(rb, 'bn2', None), norm_kind=rb.norm, training=self.training, round_out=True)
         for i, dec in enumerate(self.decoders):
             up = ops.upsample2x_add(x, blocks[n - i - 1], round_tf32=tf32)
-            p = E.pack_conv(cache, f'dec{i}', dec.conv2d, kind, getattr(dec, 'norm_layer', None), dec.norm,
-                            self.training)
-            x = E.run_conv(up, p, ops.EPI_BIAS_RELU, kind)
+            x = E.conv_layer(cache, f'dec{i}', dec.conv2d, kind, up, ops.EPI_BIAS_RELU,
+                             norm_mod=getattr(dec, 'norm_layer', None), norm_kind=dec.norm, training=self.training)
         pr = self.pred
         w, b = pr.conv2d.weight.detach().float(), None if pr.conv2d.bias is None else pr.conv2d.bias.detach().float()
         w, b = E._fold_norm(w, b, getattr(pr, 'norm_layer', None), pr.norm, self.training)

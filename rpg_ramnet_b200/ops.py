@@ -152,7 +152,7 @@ def _workspace(device, nbytes: int):
 
 def conv_fwd(x0: torch.Tensor, x1: Optional[torch.Tensor], w_packed: torch.Tensor, bias: Optional[torch.Tensor],
              Cout: int, ksize: int, stride: int, epilogue: int, mma_kind: int, aux0=None, aux1=None,
-             round_tf32: bool = False, out0=None, out1=None):
+             round_tf32: bool = False, out0=None, out1=None, stash=None):
     """Implicit-GEMM convolution with fused epilogue.  Returns y0 or (y0, y1).
     `out0` / `out1`: optional preallocated NHWC outputs (persistent state buffers of the CUDA-graph runner)."""
     _check_nhwc(x0, 'conv_fwd x0')
@@ -191,7 +191,7 @@ def conv_fwd(x0: torch.Tensor, x1: Optional[torch.Tensor], w_packed: torch.Tenso
     ws = _workspace(dev, nws)
     with _Prof('conv', 2.0 * N * Ho * Wo * Cout * (C0 + C1) * ksize * ksize, dev):
         check(lib.ramnet_conv_fwd(_h(x0), ctypes.byref(d), _p(x0), _p(x1), _p(w_packed), _p(bias), _p(aux0),
-                                  _p(aux1), _p(y0), _p(y1), _p(ws), nws, _stream(x0)))
+                                  _p(aux1), _p(y0), _p(y1), _p(stash), _p(ws), nws, _stream(x0)))
     return (y0, y1) if (y1 is not None and epilogue != EPI_BIAS_RELU_PRED) else y0
 
 
@@ -253,3 +253,84 @@ def adam_step(p, g, m, v, step: int, lr=3e-4, beta1=0.9, beta2=0.999, eps=1e-8, 
             raise _lib.RamnetError('adam_step: flat contiguous fp32 buffers required')
     check(_lib.load().ramnet_adam_step(_h(p), _p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps,
                                        weight_decay, step, _stream(p)))
+
+
+# ------------------------------------------------------------------------------------------------
+# backward building blocks (include/ramnet_b200.h, "a-13")
+# ------------------------------------------------------------------------------------------------
+def pack_weights_dgrad(w_oihw: torch.Tensor, mma_kind: int, ci_begin: int, ci_count: int) -> torch.Tensor:
+    w = w_oihw.detach().contiguous().float()
+    Cout, Cin, k, _ = w.shape
+    out = torch.empty(Cout * ci_count * k * k, dtype=torch.float32, device=w.device)
+    check(_lib.load().ramnet_pack_weights_dgrad(_h(w), _p(w), _p(out), Cout, Cin, k, mma_kind, ci_begin, ci_count,
+                                                _stream(w)))
+    return out
+
+
+def conv_wgrad(dz, x0, x1, Cout, ksize, stride, dw, db):
+    """dw [Cout, C0+C1, k, k] += , db [Cout] += ."""
+    _check_nhwc(dz, 'conv_wgrad dz')
+    _check_nhwc(x0, 'conv_wgrad x0')
+    N, C0, H, W = x0.shape
+    C1 = 0 if x1 is None else x1.shape[1]
+    d = ConvDesc(N, H, W, C0, C1, Cout, ksize, stride, 0, 0, 0, 0)
+    with _Prof('wgrad', 2.0 * dz.shape[0] * dz.shape[2] * dz.shape[3] * Cout * (C0 + C1) * ksize * ksize, x0.device):
+        check(_lib.load().ramnet_conv_wgrad(_h(x0), ctypes.byref(d), _p(dz), _p(x0), _p(x1), _p(dw), _p(db), _stream(x0)))
+
+
+def head_conv_wgrad(x_nchw, dz, dw, db):
+    x = x_nchw.contiguous()
+    N, Cin, H, W = x.shape
+    _check_nhwc(dz, 'head_conv_wgrad dz')
+    with _Prof('head_wgrad', 2.0 * N * H * W * dz.shape[1] * Cin * 25, x.device):
+        check(_lib.load().ramnet_head_conv_wgrad(_h(x), _p(x), _p(dz), _p(dw), _p(db), N, Cin, H, W, dz.shape[1], _stream(x)))
+
+
+def zero_insert2x(x, Hout, Wout):
+    _check_nhwc(x, 'zero_insert2x x')
+    N, C, H, W = x.shape
+    y = empty_nhwc(N, C, Hout, Wout, x.device)
+    check(_lib.load().ramnet_zero_insert2x(_h(x), _p(x), _p(y), N, H, W, C, Hout, Wout, _stream(x)))
+    return y
+
+
+def relu_bwd(dy, y):
+    _check_nhwc(dy, 'relu_bwd dy')
+    _check_nhwc(y, 'relu_bwd y')
+    dz = empty_nhwc(*y.shape, y.device)
+    check(_lib.load().ramnet_relu_bwd(_h(y), _p(dy), _p(y), _p(dz), y.numel(), _stream(y)))
+    return dz
+
+
+def gru_out_bwd(dhn, h, u, o):
+    N, C, H, W = h.shape
+    dzo, dh = empty_nhwc(N, C, H, W, h.device), empty_nhwc(N, C, H, W, h.device)
+    dzru = empty_nhwc(N, 2 * C, H, W, h.device)
+    check(_lib.load().ramnet_gru_out_bwd(_h(h), _p(dhn), _p(h), _p(u), _p(o), _p(dzo), _p(dzru), _p(dh), N * H * W, C,
+                                         _stream(h)))
+    return dzo, dzru, dh
+
+
+def gru_ru_bwd(drh, h, r, dzru, dh):
+    N, C, H, W = h.shape
+    check(_lib.load().ramnet_gru_ru_bwd(_h(h), _p(drh), _p(h), _p(r), _p(dzru), _p(dh), N * H * W, C, _stream(h)))
+
+
+def pred_bwd(ddepth, depth, x, w):
+    _check_nhwc(x, 'pred_bwd x')
+    N, C, H, W = x.shape
+    dx = empty_nhwc(N, C, H, W, x.device)
+    dw = torch.zeros(C, dtype=torch.float32, device=x.device)
+    db = torch.zeros(1, dtype=torch.float32, device=x.device)
+    wv = w.detach().reshape(-1).contiguous().float()
+    check(_lib.load().ramnet_pred_bwd(_h(x), _p(ddepth.contiguous()), _p(depth.contiguous()), _p(x), _p(wv), _p(dx), _p(dw),
+                                      _p(db), N * H * W, C, _stream(x)))
+    return dx, dw, db
+
+
+def upsample2x_bwd(dy):
+    _check_nhwc(dy, 'upsample2x_bwd dy')
+    N, C, H2, W2 = dy.shape
+    dx = empty_nhwc(N, C, H2 // 2, W2 // 2, dy.device)
+    check(_lib.load().ramnet_upsample2x_bwd(_h(dy), _p(dy), _p(dx), N, H2 // 2, W2 // 2, C, _stream(dy)))
+    return dx

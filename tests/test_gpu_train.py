@@ -1,0 +1,200 @@
+"""GPU: the training path — hand-written backward kernels behind autograd.Function
+nodes vs torch autograd on the CPU oracle, the reference's own gradient digests, and the fused Adam step."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ramnet_oracle as O
+from helpers import GOLDEN, build_product_model, case_inputs
+
+pytestmark = pytest.mark.gpu
+KINDS = ['fp32', 'tf32']
+TOL = {'fp32': 3e-4, 'tf32': 1e-2}
+
+
+def dev():
+    return torch.device('cuda', 0)
+
+
+def nhwc(t):
+    return t.to(dev()).contiguous(memory_format=torch.channels_last)
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g) * scale
+
+
+def _rel(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return float((a - b).abs().max() / max(1e-12, float(b.abs().max())))
+
+
+@pytest.mark.parametrize('kind', KINDS)
+@pytest.mark.parametrize('shape', [
+    # N, H, W, C0, C1, Cout, k, stride, epilogue ('relu' | 'res')
+    (2, 12, 16, 32, 0, 64, 5, 2, 'relu'),
+    (1, 16, 16, 64, 0, 64, 3, 1, 'res'),
+    (2, 8, 12, 32, 32, 32, 3, 1, 'relu'),
+    (1, 16, 24, 64, 0, 32, 5, 1, 'relu'),
+])
+def test_conv_backward_vs_torch(kind, shape):
+    from rpg_ramnet_b200 import autograd as AG, ops
+    N, H, W, C0, C1, Cout, k, stride, epi = shape
+    kid = {'fp32': ops.MMA_FP32, 'tf32': ops.MMA_TF32}[kind]
+    x0, x1 = _rand((N, C0, H, W), 1), (_rand((N, C1, H, W), 2) if C1 else None)
+    w, b = _rand((Cout, C0 + C1, k, k), 3, (1.0 / ((C0 + C1) * k * k)) ** 0.5), _rand((Cout,), 4, 0.1)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    res = _rand((N, Cout, Ho, Wo), 5) if epi == 'res' else None
+    gy = _rand((N, Cout, Ho, Wo), 6)
+    # torch reference (CPU, double)
+    tx0 = x0.double().requires_grad_(True)
+    tx1 = x1.double().requires_grad_(True) if C1 else None
+    tw, tb = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    tres = res.double().requires_grad_(True) if res is not None else None
+    y = F.conv2d(tx0 if tx1 is None else torch.cat([tx0, tx1], 1), tw, tb, stride=stride, padding=k // 2)
+    y = torch.relu(y + tres) if tres is not None else torch.relu(y)
+    y.backward(gy.double())
+    # ours
+    gx0 = nhwc(x0).requires_grad_(True)
+    gx1 = nhwc(x1).requires_grad_(True) if C1 else None
+    gw, gb = w.to(dev()).requires_grad_(True), b.to(dev()).requires_grad_(True)
+    gres = nhwc(res).requires_grad_(True) if res is not None else None
+    wp = ops.pack_weights(gw, kid)
+    epi_id = ops.EPI_BIAS_RES_RELU if res is not None else ops.EPI_BIAS_RELU
+    out = AG.ConvFn.apply(gx0, gx1, gres, gw, gb, wp, epi_id, kid, stride, False)
+    assert _rel(out, y) <= TOL[kind]
+    out.backward(nhwc(gy))
+    assert _rel(gw.grad, tw.grad) <= TOL[kind]
+    assert _rel(gb.grad, tb.grad) <= TOL[kind]
+    assert _rel(gx0.grad, tx0.grad) <= TOL[kind]
+    if C1:
+        assert _rel(gx1.grad, tx1.grad) <= TOL[kind]
+    if res is not None:
+        assert _rel(gres.grad, tres.grad) <= TOL[kind]
+
+
+@pytest.mark.parametrize('kind', KINDS)
+@pytest.mark.parametrize('C,H,W,N', [(64, 8, 12, 2), (32, 10, 6, 1)])
+def test_gru_backward_vs_oracle(kind, C, H, W, N):
+    from rpg_ramnet_b200 import engine as E, ops
+    from rpg_ramnet_b200.model.submodules import ConvGRU
+    kid = {'fp32': ops.MMA_FP32, 'tf32': ops.MMA_TF32}[kind]
+    torch.manual_seed(C)
+    gru = ConvGRU(C, C, 3)
+    with torch.no_grad():
+        for g_ in (gru.reset_gate, gru.update_gate, gru.out_gate):
+            g_.bias.normal_(0, 0.2)
+    sd = {'g.' + k: v.detach().double().requires_grad_(True) for k, v in gru.state_dict().items()}
+    x, h, gy = _rand((N, C, H, W), 1), _rand((N, C, H, W), 2, 0.7), _rand((N, C, H, W), 3)
+    tx, th = x.double().requires_grad_(True), h.double().requires_grad_(True)
+    ref = O.conv_gru(sd, 'g', tx, th)
+    ref.backward(gy.double())
+    gru.to(dev())
+    gx, gh = nhwc(x).requires_grad_(True), nhwc(h).requires_grad_(True)
+    out = E.gru_layer(E.WeightCache(), 'g', gru, kid, gx, gh)
+    assert _rel(out, ref) <= TOL[kind]
+    out.backward(nhwc(gy))
+    assert _rel(gx.grad, tx.grad) <= TOL[kind]
+    assert _rel(gh.grad, th.grad) <= TOL[kind]
+    for name, mod in (('reset_gate', gru.reset_gate), ('update_gate', gru.update_gate), ('out_gate', gru.out_gate)):
+        assert _rel(mod.weight.grad, sd[f'g.{name}.weight'].grad) <= TOL[kind], name
+        assert _rel(mod.bias.grad, sd[f'g.{name}.bias'].grad) <= TOL[kind], name
+
+
+def test_head_upsample_pred_backward_vs_torch():
+    from rpg_ramnet_b200 import autograd as AG
+    # head conv
+    x = _rand((2, 5, 20, 36), 1)
+    w, b, gy = _rand((32, 5, 5, 5), 2, 0.2), _rand((32,), 3, 0.1), _rand((2, 32, 20, 36), 4)
+    tw, tb = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    torch.relu(F.conv2d(x.double(), tw, tb, padding=2)).backward(gy.double())
+    gw, gb = w.to(dev()).requires_grad_(True), b.to(dev()).requires_grad_(True)
+    AG.HeadConvFn.apply(x.to(dev()), gw, gb, False).backward(nhwc(gy))
+    assert _rel(gw.grad, tw.grad) <= 1e-4 and _rel(gb.grad, tb.grad) <= 1e-4
+    # skip-sum + bilinear x2
+    for (N, C, H, W) in [(1, 32, 5, 7), (2, 64, 8, 8), (1, 4, 1, 1)]:
+        a, s, g2 = _rand((N, C, H, W), 5), _rand((N, C, H, W), 6), _rand((N, C, 2 * H, 2 * W), 7)
+        ta, ts = a.double().requires_grad_(True), s.double().requires_grad_(True)
+        F.interpolate(ta + ts, scale_factor=2, mode='bilinear', align_corners=False).backward(g2.double())
+        ga, gs = nhwc(a).requires_grad_(True), nhwc(s).requires_grad_(True)
+        AG.UpsampleAddFn.apply(ga, gs, False).backward(nhwc(g2))
+        assert _rel(ga.grad, ta.grad) <= 1e-5 and _rel(gs.grad, ts.grad) <= 1e-5
+    # pred + sigmoid
+    xx, pw, pb, gd = _rand((2, 32, 9, 11), 8), _rand((1, 32, 1, 1), 9, 0.3), _rand((1,), 10), _rand((2, 1, 9, 11), 11)
+    tx, tw, tb = xx.double().requires_grad_(True), pw.double().requires_grad_(True), pb.double().requires_grad_(True)
+    torch.sigmoid(F.conv2d(tx, tw, tb)).backward(gd.double())
+    gx, gw, gb = nhwc(xx).requires_grad_(True), pw.to(dev()).requires_grad_(True), pb.to(dev()).requires_grad_(True)
+    AG.PredFn.apply(gx, gw, gb).backward(gd.to(dev()))
+    assert _rel(gx.grad, tx.grad) <= 1e-5 and _rel(gw.grad, tw.grad) <= 1e-4 and _rel(gb.grad, tb.grad) <= 1e-4
+
+
+@pytest.mark.parametrize('kind', KINDS)
+def test_model_gradients_match_reference(kind):
+    """Full BPTT over L=2 timesteps (4 passes), the trainer's loss mix (K_keys aliasing): loss value and all 68
+    parameter gradients vs the digests produced by the reference itself (tests/golden/grads_shipped.npz)."""
+    import rpg_ramnet_b200 as R
+    g = np.load(os.path.join(GOLDEN, 'grads_shipped.npz'))
+    meta = json.loads(str(g['meta']))
+    meta.update(arch='ERGB2DepthRecurrent')
+    model, cfg = build_product_model(meta, mma_kind=kind)
+    model.to('cuda:0')
+    seq = case_inputs(meta)
+    comp, wts = meta['loss_composition'], meta['loss_weights']
+    prev_super, prev_lstm = None, {'events0': None, 'image': None}
+    terms, keys = [], []
+    for item in seq:
+        preds, supers, lstm = model(item, prev_super, prev_lstm)
+        for key, p in preds.items():
+            if key in comp:
+                if key not in keys:
+                    keys.append(key)
+                terms.append(wts[comp.index(key)] * R.scale_invariant_loss(p, item['depth_' + key].to('cuda:0'), 1.0, 1.0))
+        prev_super, prev_lstm = supers['image'], lstm
+    loss = len(keys) * sum(terms) / float(len(seq))
+    assert abs(loss.item() - float(g['loss'])) <= (2e-5 if kind == 'fp32' else 5e-4)
+    loss.backward()
+    params = dict(model.named_parameters())
+    tol = 2e-3 if kind == 'fp32' else 3e-2
+    for i, n in enumerate(g['names']):
+        gr = params[str(n)].grad
+        assert gr is not None, n
+        l2 = float(gr.double().norm())
+        assert abs(l2 - g['grad_l2'][i]) <= tol * max(g['grad_l2'][i], 1e-7), (n, l2, g['grad_l2'][i])
+        ref_head = g['head/' + str(n)]
+        got = gr.flatten()[:16].cpu().numpy()
+        assert np.abs(got - ref_head).max() <= tol * max(float(np.abs(ref_head).max()), 1e-3 * g['grad_l2'][i], 1e-9), n
+
+
+def test_fused_adam_training_step_matches_torch_adam():
+    """Two optimisation steps: our fwd/bwd + FusedAdam vs the CPU oracle's autograd + torch.optim.Adam."""
+    import rpg_ramnet_b200 as R
+    g = np.load(os.path.join(GOLDEN, 'grads_shipped.npz'))
+    meta = json.loads(str(g['meta']))
+    meta.update(arch='ERGB2DepthRecurrent', H=32, W=32, B=1, L=1)
+    model, cfg = build_product_model(meta, mma_kind='fp32')
+    model.to('cuda:0')
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    ref_opt = torch.optim.Adam(list(sd.values()), lr=3e-4)
+    opt = R.FusedAdam(model.parameters(), lr=3e-4)
+    item = case_inputs(meta)[0]
+    states = {'events0': None, 'image': None}
+    for step in range(2):
+        opt.zero_grad()
+        preds, _, _ = model(item, None, states)
+        loss = sum(R.scale_invariant_loss(preds[k], item['depth_' + k].to('cuda:0')) for k in preds)
+        loss.backward()
+        opt.step()
+        ref_opt.zero_grad()
+        rp = O.ergb2depth_recurrent(sd, cfg, item, None, states)[0]
+        rl = sum(O.si_loss(rp[k], item['depth_' + k]) for k in rp)
+        rl.backward()
+        ref_opt.step()
+        assert abs(loss.item() - rl.item()) <= 2e-5, step
+    for n, p in model.named_parameters():
+        ref = sd[n].detach()
+        assert float((p.detach().cpu() - ref).abs().max()) <= 1e-5 + 2e-3 * 6e-4, n     # |update| <= 2 lr
