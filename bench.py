@@ -211,6 +211,102 @@ def main_reference(args):
     return 0
 
 
+
+# ------------------------------------------------------------------------------------------------
+# --mode train : BASELINE configs[2] per GPU (batch 4, seq 8, fwd + bwd + Adam, grad all-reduce under DP)
+# ------------------------------------------------------------------------------------------------
+def main_train(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    import rpg_ramnet_b200 as R
+    from rpg_ramnet_b200 import ops
+    from rpg_ramnet_b200.utils.synthetic import synth_sequence
+
+    model = build_model(torch, local, args.mma_kind, cuda_graphs=False).train()
+    opt = R.FusedAdam(model.parameters(), lr=3e-4)
+    items = synth_sequence(B, H, W, L, K_EVENTS, seed=2 + rank, with_targets=True)
+    items = [{k: v.to(dev) for k, v in it.items()} for it in items]
+    keys = ['events0', 'image']
+    exact = world > 1          # exact global-batch loss statistics under data parallelism
+
+    def step():
+        opt.zero_grad()
+        prev_super, prev_lstm = None, {'events0': None, 'image': None}
+        terms = []
+        for item in items:
+            preds, supers, lstm = model(item, prev_super, prev_lstm)
+            for k in keys:
+                terms.append(R.scale_invariant_loss(preds[k], item['depth_' + k], 1.0, 1.0, process_group=exact))
+            prev_super, prev_lstm = supers['image'], lstm
+        loss = len(keys) * sum(terms) / float(L)      # lstm_trainer.py loss aliasing
+        loss.backward()
+        opt.step()                                    # all-reduces the flat gradient buffer when world > 1
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    l0 = R.launch_count(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            loss = step()
+        e1.record()
+        barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = R.launch_count(local) - l0
+    ops.PROFILE = []
+    step()
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    by = {}
+    for k, f, a, b in prof:
+        t, fl = by.get(k, (0.0, 0.0))
+        by[k] = (t + a.elapsed_time(b), fl + f)
+    peaks, peak_src = read_peaks()
+    peak_tf = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops')))
+    conv_ms, conv_fl = by.get('conv', (0.0, 0.0))
+    wg_ms, wg_fl = by.get('wgrad', (0.0, 0.0))
+    if rank == 0:
+        line = {'metric': 'depth-maps/sec at 512x256, 5-bin voxel, seq=8 (fwd+bwd+Adam)',
+                'value': world * MAPS_PER_STEP * args.steps / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32' if args.mma_kind == 'tf32' else 'f32',
+                'data': 'synthetic', 'mode': 'train', 'loss': float(loss),
+                'config': {'workload': f'BASELINE configs[2] per GPU: RAM-Net shipped block, {W}x{H}, batch {B}/GPU, seq {L}, '
+                                       f'K=1, SI loss on events0+image, full BPTT, fused Adam(3e-4)',
+                           'parallelism': f'dp{world}: flat fp32 grad all-reduce (NCCL) + 3-double loss-statistics all-reduce'},
+                'clocks': clk.summary(), 'gpu_launches': launches,
+                'roofline': {'bound': 'tensor', 'kernel': 'conv_implicit_gemm fwd+dgrad (tcgen05)',
+                             'achieved': conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0, 'peak': peak_tf,
+                             'unit': 'TFLOP/s', 'frac': (conv_fl / (conv_ms * 1e-3) / 1e12 / peak_tf) if conv_ms else 0.0,
+                             'traffic': None, 'peak_source': peak_src, 'ms_per_step_in_kernel': conv_ms},
+                'wgrad': {'kernel': 'conv_wgrad_kernel (fp32 FFMA, split-K atomics) — first version',
+                          'achieved_tflops': wg_fl / (wg_ms * 1e-3) / 1e12 if wg_ms else 0.0, 'ms_per_step_in_kernel': wg_ms},
+                'other_kernels_ms_per_step': {k: v[0] for k, v in by.items() if k not in ('conv', 'wgrad')}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
 # ------------------------------------------------------------------------------------------------
 def main_ours(args):
     import torch
@@ -361,6 +457,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--mma-kind', default=os.environ.get('RAMNET_MMA_KIND', 'tf32'), choices=['tf32', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--mode', default='infer', choices=['infer', 'train'], help='train = fwd+bwd+Adam (BASELINE configs[2])')
     ap.add_argument('--no-graphs', action='store_true', help='issue every kernel from Python instead of CUDA-graph replay')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
@@ -373,7 +470,7 @@ def main():
                '--master-addr', '127.0.0.1', '--master-port', os.environ.get('MASTER_PORT', '29511'),
                os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
-    return main_ours(args)
+    return main_train(args) if args.mode == 'train' else main_ours(args)
 
 
 if __name__ == '__main__':
