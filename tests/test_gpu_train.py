@@ -173,7 +173,7 @@ def test_model_gradients_match_reference(kind):
         assert abs(l2 - g['grad_l2'][i]) <= tol * max(g['grad_l2'][i], 1e-7), (n, l2, g['grad_l2'][i])
         ref_head = g['head/' + str(n)]
         got = gr.flatten()[:16].cpu().numpy()
-        assert np.abs(got - ref_head).max() <= tol_elem * max(float(np.abs(ref_head).max()), 1e-3 * g['grad_l2'][i], 1e-9), n
+        assert np.linalg.norm(got - ref_head) <= tol_elem * max(float(np.linalg.norm(ref_head)), 1e-3 * g['grad_l2'][i], 1e-9), n
 
 
 def test_fused_adam_training_step_matches_torch_adam():
