@@ -186,14 +186,16 @@ int ramnet_pack_weights_dgrad(ramnet_handle *h, const float *w_oihw, float *w_pa
                               int ksize, int mma_kind, int ci_begin, int ci_count, void *stream);
 int ramnet_zero_insert2x(ramnet_handle *h, const float *x, float *y, int N, int H, int W, int C, int Hout,
                          int Wout, void *stream);
-/* dz = dy * (y > 0) */
-int ramnet_relu_bwd(ramnet_handle *h, const float *dy, const float *y, float *dz, int64_t n, void *stream);
+/* dz = dy * (y > 0).  flags & RAMNET_FLAG_ROUND_TF32 (here and in the GRU adjoints): round the dz outputs to TF32
+ * so that the tcgen05 dgrad / wgrad GEMMs that consume them truncate nothing. */
+int ramnet_relu_bwd(ramnet_handle *h, const float *dy, const float *y, float *dz, int64_t n, int flags,
+                    void *stream);
 /* ConvGRU adjoints (submodules.py:446-452).  gru_out_bwd: dzo = dh'*u*(1-o^2); columns [C,2C) of dzru =
  * dh'*(o-h)*u*(1-u); dh = dh'*(1-u).  gru_ru_bwd: columns [0,C) of dzru = drh*h*r*(1-r); dh += drh*r. */
 int ramnet_gru_out_bwd(ramnet_handle *h, const float *dhn, const float *hprev, const float *u, const float *o,
-                       float *dzo, float *dzru, float *dh, int64_t M, int C, void *stream);
+                       float *dzo, float *dzru, float *dh, int64_t M, int C, int flags, void *stream);
 int ramnet_gru_ru_bwd(ramnet_handle *h, const float *drh, const float *hprev, const float *r, float *dzru,
-                      float *dh, int64_t M, int C, void *stream);
+                      float *dh, int64_t M, int C, int flags, void *stream);
 /* pred + sigmoid adjoint: dx[m,c] = g*w[c], dw[c] += sum g*x[m,c], db += sum g, g = ddepth*s(1-s) */
 int ramnet_pred_bwd(ramnet_handle *h, const float *ddepth, const float *depth, const float *x, const float *w,
                     float *dx, float *dw, float *db, int64_t M, int C, void *stream);

@@ -62,11 +62,11 @@ class ConvFn(torch.autograd.Function):
         x0, x1, y, weight = ctx.saved_tensors
         epilogue, kind, stride, has_bias, has_res = ctx.cfg
         dy = _nhwc(dy)
-        dz = dy if epilogue == ops.EPI_BIAS else ops.relu_bwd(dy, y)
+        dz = dy if epilogue == ops.EPI_BIAS else ops.relu_bwd(dy, y, round_tf32=(kind == ops.MMA_TF32))
         Cout, Ct, k, _ = weight.shape
         dw = torch.zeros_like(weight, dtype=torch.float32)
         db = torch.zeros(Cout, dtype=torch.float32, device=y.device) if has_bias else None
-        ops.conv_wgrad(dz, x0, x1, Cout, k, stride, dw, db)
+        ops.conv_wgrad(dz, x0, x1, Cout, k, stride, dw, db, kind)
         C0 = x0.shape[1]
         dx0 = _dgrad(dz, weight, kind, stride, 0, C0, x0.shape[2:]) if ctx.needs_input_grad[0] else None
         dx1 = None
@@ -98,17 +98,18 @@ class GruFn(torch.autograd.Function):
         x, h, u, r, rh, o, w_r, w_u, w_o = ctx.saved_tensors
         kind = ctx.kind
         N, C, H, W = x.shape
-        dzo, dzru, dh = ops.gru_out_bwd(_nhwc(dhn), h, u, o)
+        tf32 = kind == ops.MMA_TF32
+        dzo, dzru, dh = ops.gru_out_bwd(_nhwc(dhn), h, u, o, round_tf32=tf32)
         dw_o = torch.zeros_like(w_o, dtype=torch.float32)
         db_o = torch.zeros(C, dtype=torch.float32, device=x.device)
-        ops.conv_wgrad(dzo, x, rh, C, 3, 1, dw_o, db_o)
+        ops.conv_wgrad(dzo, x, rh, C, 3, 1, dw_o, db_o, kind)
         dx = _dgrad(dzo, w_o, kind, 1, 0, C, (H, W))
         drh = _dgrad(dzo, w_o, kind, 1, C, C, (H, W))
-        ops.gru_ru_bwd(drh, h, r, dzru, dh)
+        ops.gru_ru_bwd(drh, h, r, dzru, dh, round_tf32=tf32)
         w_ru = torch.cat([w_r.detach(), w_u.detach()], 0)
         dw_ru = torch.zeros_like(w_ru, dtype=torch.float32)
         db_ru = torch.zeros(2 * C, dtype=torch.float32, device=x.device)
-        ops.conv_wgrad(dzru, x, h, 2 * C, 3, 1, dw_ru, db_ru)
+        ops.conv_wgrad(dzru, x, h, 2 * C, 3, 1, dw_ru, db_ru, kind)
         dx = dx + _dgrad(dzru, w_ru, kind, 1, 0, C, (H, W))
         dh = dh + _dgrad(dzru, w_ru, kind, 1, C, C, (H, W))
         return (dx if ctx.needs_input_grad[0] else None, dh if ctx.needs_input_grad[1] else None,

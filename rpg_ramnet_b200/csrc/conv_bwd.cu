@@ -144,11 +144,15 @@ __device__ __forceinline__ void st4(float *p, int64_t i, float4 v) { reinterpret
                 ([&](float A, float B) { return expr; })(a.z, b.z), ([&](float A, float B) { return expr; })(a.w, b.w))
 
 // dz = dy * (y > 0)
+__device__ __forceinline__ float4 rnd4(float4 v, int round) {
+    return round ? make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w)) : v;
+}
+
 __global__ void relu_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ y, float *__restrict__ dz,
-                                int64_t n4) {
+                                int64_t n4, int round) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         const float4 g = ld4(dy, i), v = ld4(y, i);
-        st4(dz, i, F4_MAP2(g, v, B > 0.f ? A : 0.f));
+        st4(dz, i, rnd4(F4_MAP2(g, v, B > 0.f ? A : 0.f), round));
     }
 }
 
@@ -156,7 +160,7 @@ __global__ void relu_bwd_kernel(const float *__restrict__ dy, const float *__res
 // written into the update half of dzru [M, 2C] (columns [C, 2C)), dh = dh'*(1-u).
 __global__ void gru_out_bwd_kernel(const float *__restrict__ dhn, const float *__restrict__ h, const float *__restrict__ u,
                                    const float *__restrict__ o, float *__restrict__ dzo, float *__restrict__ dzru,
-                                   float *__restrict__ dh, int64_t M, int C) {
+                                   float *__restrict__ dh, int64_t M, int C, int round) {
     const int C4 = C >> 2;
     const int64_t n4 = M * C4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -169,8 +173,8 @@ __global__ void gru_out_bwd_kernel(const float *__restrict__ dhn, const float *_
         b.x = g.x * (ov.x - hv.x) * uv.x * (1.f - uv.x); b.y = g.y * (ov.y - hv.y) * uv.y * (1.f - uv.y);
         b.z = g.z * (ov.z - hv.z) * uv.z * (1.f - uv.z); b.w = g.w * (ov.w - hv.w) * uv.w * (1.f - uv.w);
         d.x = g.x * (1.f - uv.x); d.y = g.y * (1.f - uv.y); d.z = g.z * (1.f - uv.z); d.w = g.w * (1.f - uv.w);
-        st4(dzo, i, a);
-        st4(dzru, m * (2 * C4) + C4 + c, b);
+        st4(dzo, i, rnd4(a, round));
+        st4(dzru, m * (2 * C4) + C4 + c, rnd4(b, round));
         st4(dh, i, d);
     }
 }
@@ -178,7 +182,7 @@ __global__ void gru_out_bwd_kernel(const float *__restrict__ dhn, const float *_
 // ConvGRU reset adjoint.  in: drh (grad of h*r), h, r.  out: dzr = drh*h*r*(1-r) into columns [0, C) of dzru,
 // dh += drh*r.
 __global__ void gru_ru_bwd_kernel(const float *__restrict__ drh, const float *__restrict__ h, const float *__restrict__ r,
-                                  float *__restrict__ dzru, float *__restrict__ dh, int64_t M, int C) {
+                                  float *__restrict__ dzru, float *__restrict__ dh, int64_t M, int C, int round) {
     const int C4 = C >> 2;
     const int64_t n4 = M * C4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -189,7 +193,7 @@ __global__ void gru_ru_bwd_kernel(const float *__restrict__ drh, const float *__
         a.x = g.x * hv.x * rv.x * (1.f - rv.x); a.y = g.y * hv.y * rv.y * (1.f - rv.y);
         a.z = g.z * hv.z * rv.z * (1.f - rv.z); a.w = g.w * hv.w * rv.w * (1.f - rv.w);
         d.x += g.x * rv.x; d.y += g.y * rv.y; d.z += g.z * rv.z; d.w += g.w * rv.w;
-        st4(dzru, m * (2 * C4) + c, a);
+        st4(dzru, m * (2 * C4) + c, rnd4(a, round));
         st4(dh, i, d);
     }
 }
@@ -325,11 +329,25 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(const float *__restrict
 int grid_for(ramnet_handle *h, int64_t n) { return (int)imin64((n + 255) / 256, (int64_t)h->sm_count * 16); }
 }  // namespace
 
+int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz, const float *x0, const float *x1,
+                    float *dw, cudaStream_t s);
+
 extern "C" int ramnet_conv_wgrad(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz, const float *x0,
                                  const float *x1, float *dw_oihw, float *db, void *stream) {
     RAMNET_CHECK_ARG(h && d && dz && x0 && dw_oihw, "conv_wgrad: NULL argument");
     RAMNET_CHECK_ARG(d->C0 % 4 == 0 && d->C1 % 4 == 0 && d->Cout % 4 == 0, "conv_wgrad: channel counts must be multiples of 4");
     RAMNET_CHECK_ARG((d->C1 == 0) == (x1 == nullptr), "conv_wgrad: x1 and C1 disagree");
+    if (db) {
+        const int64_t Mrows = (int64_t)d->N * conv_out_dim(d->H, d->stride) * conv_out_dim(d->W, d->stride);
+        const int rpb = 2048;
+        colsum_kernel<<<(unsigned)((Mrows + rpb - 1) / rpb), 256, 0, (cudaStream_t)stream>>>(dz, Mrows, d->Cout, db, rpb);
+        RAMNET_LAUNCH_CHECK(h);
+    }
+    if (d->mma_kind == RAMNET_MMA_TF32) {
+        const int rc = conv_wgrad_tf32(h, d, dz, x0, x1, dw_oihw, (cudaStream_t)stream);
+        if (rc != RAMNET_EUNSUPPORTED) return rc;      // unsupported shape: fp32 FFMA kernel below
+    }
+    db = nullptr;
     WgradGeom g;
     g.N = d->N; g.H = d->H; g.W = d->W; g.C0 = d->C0; g.C1 = d->C1; g.Cout = d->Cout; g.ks = d->ksize;
     g.stride = d->stride; g.pad = d->ksize / 2;
@@ -375,25 +393,28 @@ extern "C" int ramnet_pack_weights_dgrad(ramnet_handle *h, const float *w_oihw, 
     return RAMNET_OK;
 }
 
-extern "C" int ramnet_relu_bwd(ramnet_handle *h, const float *dy, const float *y, float *dz, int64_t n, void *stream) {
+extern "C" int ramnet_relu_bwd(ramnet_handle *h, const float *dy, const float *y, float *dz, int64_t n, int flags,
+                               void *stream) {
     RAMNET_CHECK_ARG(h && dy && y && dz && n > 0 && n % 4 == 0, "relu_bwd: bad argument");
-    relu_bwd_kernel<<<grid_for(h, n / 4), 256, 0, (cudaStream_t)stream>>>(dy, y, dz, n / 4);
+    relu_bwd_kernel<<<grid_for(h, n / 4), 256, 0, (cudaStream_t)stream>>>(dy, y, dz, n / 4, flags & RAMNET_FLAG_ROUND_TF32);
     RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;
 }
 
 extern "C" int ramnet_gru_out_bwd(ramnet_handle *h, const float *dhn, const float *hprev, const float *u, const float *o,
-                                  float *dzo, float *dzru, float *dh, int64_t M, int C, void *stream) {
+                                  float *dzo, float *dzru, float *dh, int64_t M, int C, int flags, void *stream) {
     RAMNET_CHECK_ARG(h && dhn && hprev && u && o && dzo && dzru && dh && M > 0 && C % 4 == 0, "gru_out_bwd: bad argument");
-    gru_out_bwd_kernel<<<grid_for(h, M * (C / 4)), 256, 0, (cudaStream_t)stream>>>(dhn, hprev, u, o, dzo, dzru, dh, M, C);
+    gru_out_bwd_kernel<<<grid_for(h, M * (C / 4)), 256, 0, (cudaStream_t)stream>>>(dhn, hprev, u, o, dzo, dzru, dh, M, C,
+                                                                                   flags & RAMNET_FLAG_ROUND_TF32);
     RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;
 }
 
 extern "C" int ramnet_gru_ru_bwd(ramnet_handle *h, const float *drh, const float *hprev, const float *r, float *dzru,
-                                 float *dh, int64_t M, int C, void *stream) {
+                                 float *dh, int64_t M, int C, int flags, void *stream) {
     RAMNET_CHECK_ARG(h && drh && hprev && r && dzru && dh && M > 0 && C % 4 == 0, "gru_ru_bwd: bad argument");
-    gru_ru_bwd_kernel<<<grid_for(h, M * (C / 4)), 256, 0, (cudaStream_t)stream>>>(drh, hprev, r, dzru, dh, M, C);
+    gru_ru_bwd_kernel<<<grid_for(h, M * (C / 4)), 256, 0, (cudaStream_t)stream>>>(drh, hprev, r, dzru, dh, M, C,
+                                                                                  flags & RAMNET_FLAG_ROUND_TF32);
     RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;
 }

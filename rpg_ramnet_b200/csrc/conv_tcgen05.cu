@@ -689,17 +689,211 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
     }
 }
 
+
+// ================================================================================================
+// Weight gradient on the tensor cores:  dW[tap][co][ci] += sum_pixels dZ[p][co] * X[p*stride + tap - pad][ci]
+//
+// The contraction (K) dimension is the PIXEL axis.  Both operands already sit in HBM as pixel rows of
+// 32 contiguous channels, so a TMA box {32 ch, 8 px, 8 rows} lands in shared memory as 64 K-rows of
+// 128 bytes: exactly the MN-major, 128B-swizzled UMMA operand layout (32 M/N elements contiguous,
+// K-groups of 8 rows = 1024 B).  Wider M/N are further 32-channel boxes LBO bytes apart.  One
+// tcgen05.mma (M=128, N<=128, K=8 pixels, a_major = b_major = MN) therefore consumes them directly —
+// no transposes anywhere.  The "M" operand is whichever of (dZ, X) has more channels, so small-Cout
+// layers do not waste the 128 rows.  CTA = (tap, M block, N block, pixel range): it streams its pixel
+// tiles through a TMA ring, accumulates in TMEM and flushes once with fp32 atomics into the
+// nn.Conv2d-layout gradient buffer (BPTT's sum over timesteps is the same += ).
+// ================================================================================================
+struct WgGeom {
+    int N, Ho, Wo;           // output pixel grid (dZ); X boxes are addressed through stride / tap shift
+    int Cout, C0, C1;
+    int ks, pad, stride;
+    int m_from_x;            // 1: M operand = X (input channels), N operand = dZ;  0: M = dZ, N = X
+    int Mch, Nch;            // channels of the M / N operand (Cout or C0+C1)
+    int BN;                  // N channels per CTA (multiple of 32, <= 128)
+    int m_blocks, n_blocks;
+    int tiles_x, tiles_y;    // 8x8 pixel tiles over (Wo, Ho)
+    int tiles_per_cta, total_tiles;
+    int stages;
+    int debug;               // RAMNET_WG_DEBUG experiments
+};
+
+constexpr int kWgTile = 64;                         // pixels per K tile (8 x 8)
+constexpr int kWgBox = kWgTile * kChunk * 4;        // 8 KB: one 32-channel box of one K tile
+
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;      // leading byte offset: next 32-channel block of M/N
+    d |= (uint64_t)(512 >> 4) << 32;            // stride byte offset: next group of 4 K rows (32-byte-atom swizzle)
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                     // SWIZZLE_128B_BASE32B: the only MN-major layout for 32-bit operands
+    return d;
+}
+
+__global__ void __launch_bounds__(kThreads) conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_dz,
+                                                                      const __grid_constant__ CUtensorMap map_x0,
+                                                                      const __grid_constant__ CUtensorMap map_x1,
+                                                                      WgGeom g, float *__restrict__ dw) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int a_boxes = 4, b_boxes = g.BN / kChunk;
+    const int stage_bytes = (a_boxes + b_boxes) * kWgBox;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)g.stages * stage_bytes);
+    uint64_t *empty_bar = full_bar + g.stages;
+    uint64_t *accum_bar = empty_bar + g.stages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // blockIdx.y -> (tap, m block, n block)
+    int t = blockIdx.y;
+    const int nb = t % g.n_blocks;
+    t /= g.n_blocks;
+    const int mb = t % g.m_blocks;
+    const int tap = t / g.m_blocks;
+    const int r = tap / g.ks, sx = tap % g.ks;
+    const int tile_begin = blockIdx.x * g.tiles_per_cta;
+    const int tile_end = min(tile_begin + g.tiles_per_cta, g.total_tiles);
+    const int ntile = tile_end - tile_begin;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < g.BN) tmem_cols <<= 1;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_dz);
+        prefetch_tmap(&map_x0);
+        prefetch_tmap(&map_x1);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < g.stages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        int stage = 0;
+        uint32_t phase = 0;
+        const int ry = r - g.pad, rx = sx - g.pad;
+        for (int it = 0; it < ntile; ++it) {
+            int tt = tile_begin + it;
+            const int txi = tt % g.tiles_x;
+            tt /= g.tiles_x;
+            const int tyi = tt % g.tiles_y;
+            const int img = tt / g.tiles_y;
+            const int ox0 = txi * 8, oy0 = tyi * 8;
+            mbar_wait(empty_bar + stage, phase ^ 1);
+            if (elect_one()) {
+                uint8_t *sa = smem + (size_t)stage * stage_bytes;
+                uint8_t *sb = sa + a_boxes * kWgBox;
+                mbar_expect_tx(full_bar + stage, (uint32_t)stage_bytes);
+                auto load_dz = [&](uint8_t *dst, int ch) {       // ch beyond Cout: zero-filled by TMA
+                    tma_load_4d(dst, &map_dz, full_bar + stage, ch, ox0, oy0, img);
+                };
+                auto load_x = [&](uint8_t *dst, int ch) {        // ch indexes the virtual concat [x0 | x1]
+                    const bool second = ch >= g.C0 && g.C1 > 0;
+                    const CUtensorMap *mx = second ? &map_x1 : &map_x0;
+                    const int c = second ? ch - g.C0 : ch;
+                    const int Csrc = second ? g.C1 : g.C0;
+                    if (ch >= g.C0 + g.C1) {                     // past the last channel: any OOB channel coordinate
+                        if (g.stride == 1) tma_load_4d(dst, mx, full_bar + stage, Csrc, ox0 + rx, oy0 + ry, img);
+                        else tma_load_5d(dst, mx, full_bar + stage, 2 * Csrc, ox0 + (rx >> 1), ry & 1, oy0 + (ry >> 1), img);
+                    } else if (g.stride == 1) {
+                        tma_load_4d(dst, mx, full_bar + stage, c, ox0 + rx, oy0 + ry, img);
+                    } else {
+                        tma_load_5d(dst, mx, full_bar + stage, (rx & 1) * Csrc + c, ox0 + (rx >> 1), ry & 1, oy0 + (ry >> 1), img);
+                    }
+                };
+                for (int q = 0; q < a_boxes; ++q) {
+                    const int ch = (mb * 4 + q) * kChunk;
+                    if (g.m_from_x) load_x(sa + q * kWgBox, ch); else load_dz(sa + q * kWgBox, ch);
+                }
+                for (int q = 0; q < b_boxes; ++q) {
+                    const int ch = nb * g.BN + q * kChunk;
+                    if (g.m_from_x) load_dz(sb + q * kWgBox, ch); else load_x(sb + q * kWgBox, ch);
+                }
+            }
+            __syncwarp();
+            if (++stage == g.stages) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        // idesc: kind::tf32, fp32 accumulate, A and B MN-major (bits 15, 16), M = 128, N = BN
+        uint32_t idesc = make_idesc_tf32(g.BN) | (1u << 15) | (1u << 16);
+        if (g.debug & 1) idesc &= ~(1u << 15);
+        if (g.debug & 2) idesc &= ~(1u << 16);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < ntile; ++it) {
+            mbar_wait(full_bar + stage, phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+            uint64_t adesc = make_smem_desc_mn(sa, kWgBox), bdesc = make_smem_desc_mn(sa + a_boxes * kWgBox, kWgBox);
+            if (g.debug & 4) {   // swapped LBO / SBO roles
+                adesc = (adesc & ~((0x3FFFull << 16) | (0x3FFFull << 32))) | ((uint64_t)(512 >> 4) << 16) | ((uint64_t)(kWgBox >> 4) << 32);
+                bdesc = (bdesc & ~((0x3FFFull << 16) | (0x3FFFull << 32))) | ((uint64_t)(512 >> 4) << 16) | ((uint64_t)(kWgBox >> 4) << 32);
+            }
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < kWgTile / 8; ++kk)      // 8 pixel rows = 1024 bytes per K step: +64 in the >>4 field
+                    umma_tf32(tmem_base, adesc + 64 * kk, bdesc + 64 * kk, idesc, (it | kk) != 0);
+                umma_commit(empty_bar + stage);
+                if (it == ntile - 1) umma_commit(accum_bar);
+            }
+            __syncwarp();
+            if (++stage == g.stages) { stage = 0; phase ^= 1; }
+        }
+    } else if (ntile > 0) {
+        // ---------------- epilogue: TMEM -> fp32 atomics into dW [Cout][Ct][ks][ks] ----------------
+        const int quarter = warp & 3;
+        const int mrow = mb * 128 + quarter * 32 + lane;          // channel of the M operand
+        const int taps = g.ks * g.ks, Ct = g.C0 + g.C1;
+        mbar_wait(accum_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        for (int c = 0; c < g.BN; c += 16) {
+            float v[16];
+            tmem_ld16(lane_addr + (uint32_t)c, v);
+            if (mrow < g.Mch) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int ncol = nb * g.BN + c + j;               // channel of the N operand
+                    if (ncol < g.Nch) {
+                        const int co = g.m_from_x ? ncol : mrow, ci = g.m_from_x ? mrow : ncol;
+                        atomicAdd(dw + ((int64_t)co * Ct + ci) * taps + tap, v[j]);
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int encode(ramnet_handle *h, CUtensorMap *map, const void *base, int rank, const cuuint64_t *dims,
-           const cuuint64_t *strides_bytes, const cuuint32_t *box) {
+           const cuuint64_t *strides_bytes, const cuuint32_t *box,
+           CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     cuuint32_t elem[5] = {1, 1, 1, 1, 1};
     CUresult r = ((EncodeTiledFn)h->encode_tiled)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
                                                   const_cast<void *>(base), dims, strides_bytes, box, elem,
-                                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return ramnet_set_error(RAMNET_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return RAMNET_OK;
@@ -707,18 +901,18 @@ int encode(ramnet_handle *h, CUtensorMap *map, const void *base, int rank, const
 
 // activation map: stride 1 -> (C, W, H, N); stride 2 -> (2C, W/2, 2, H/2, N)
 int encode_activation(ramnet_handle *h, CUtensorMap *map, const float *x, int N, int H, int W, int C, int stride,
-                      int TW, int TH) {
+                      int TW, int TH, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     if (stride == 1) {
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
         cuuint64_t str[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
         cuuint32_t box[4] = {kChunk, (cuuint32_t)TW, (cuuint32_t)TH, 1};
-        return encode(h, map, x, 4, dims, str, box);
+        return encode(h, map, x, 4, dims, str, box, swizzle);
     }
     cuuint64_t dims[5] = {(cuuint64_t)2 * C, (cuuint64_t)W / 2, 2, (cuuint64_t)H / 2, (cuuint64_t)N};
     cuuint64_t str[4] = {(cuuint64_t)2 * C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)2 * W * C * 4,
                          (cuuint64_t)H * W * C * 4};
     cuuint32_t box[5] = {kChunk, (cuuint32_t)TW, 1, (cuuint32_t)TH, 1};
-    return encode(h, map, x, 5, dims, str, box);
+    return encode(h, map, x, 5, dims, str, box, swizzle);
 }
 
 void pick_tile(int Ho, int Wo, int *TW, int *TH) {
@@ -873,6 +1067,68 @@ bool plan_halo(const ramnet_handle *h, const ramnet_conv_desc *d, HaloGeom *g) {
     return best >= 0;
 }
 }  // namespace
+
+
+// dW += dZ^T * im2col(X) on the tensor cores (see conv_wgrad_tcgen05_kernel).  Returns RAMNET_EUNSUPPORTED
+// for shapes the kernel does not cover; the caller then uses the fp32 FFMA kernel.
+int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz, const float *x0, const float *x1,
+                    float *dw, cudaStream_t s) {
+    if (d->C0 % kChunk || d->C1 % kChunk || d->Cout % 16) return RAMNET_EUNSUPPORTED;
+    if (d->stride == 2 && ((d->H | d->W) & 1)) return RAMNET_EUNSUPPORTED;
+    if ((((uintptr_t)dz | (uintptr_t)x0 | (uintptr_t)x1) & 15) != 0) return RAMNET_EUNSUPPORTED;
+    WgGeom g;
+    g.N = d->N; g.Ho = conv_out_dim(d->H, d->stride); g.Wo = conv_out_dim(d->W, d->stride);
+    g.Cout = d->Cout; g.C0 = d->C0; g.C1 = d->C1; g.ks = d->ksize; g.pad = d->ksize / 2; g.stride = d->stride;
+    const int Ct = d->C0 + d->C1;
+    g.m_from_x = Ct > d->Cout ? 1 : 0;                 // the operand with more channels fills the 128 MMA rows
+    g.Mch = g.m_from_x ? Ct : d->Cout;
+    g.Nch = g.m_from_x ? d->Cout : Ct;
+    g.BN = g.Nch >= 128 ? 128 : ((g.Nch + 31) / 32) * 32;
+    g.m_blocks = (g.Mch + 127) / 128;
+    g.n_blocks = (g.Nch + g.BN - 1) / g.BN;
+    g.tiles_x = (g.Wo + 7) / 8; g.tiles_y = (g.Ho + 7) / 8;
+    const int64_t total = (int64_t)g.tiles_x * g.tiles_y * g.N;
+    if (total > 0x7fffffff) return RAMNET_EUNSUPPORTED;
+    g.total_tiles = (int)total;
+    const int groups = d->ksize * d->ksize * g.m_blocks * g.n_blocks;
+    int64_t splits = ((int64_t)h->sm_count * 4 + groups - 1) / groups;      // ~4 CTAs per SM in total
+    if (splits > total) splits = total;
+    if (splits < 1) splits = 1;
+    g.tiles_per_cta = (int)((total + splits - 1) / splits);
+    splits = (total + g.tiles_per_cta - 1) / g.tiles_per_cta;
+    const int stage_bytes = (4 + g.BN / kChunk) * kWgBox;
+    g.debug = getenv("RAMNET_WG_DEBUG") ? atoi(getenv("RAMNET_WG_DEBUG")) : 0;
+    g.stages = (96 * 1024) / stage_bytes;      // two CTAs per SM
+    if (g.stages < 2) g.stages = 2;
+    if (g.stages > 6) g.stages = 6;
+
+    CUtensorMap mdz, m0, m1;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)g.Wo, (cuuint64_t)g.Ho, (cuuint64_t)d->N};
+        cuuint64_t str[3] = {(cuuint64_t)d->Cout * 4, (cuuint64_t)g.Wo * d->Cout * 4, (cuuint64_t)g.Ho * g.Wo * d->Cout * 4};
+        cuuint32_t box[4] = {kChunk, 8, 8, 1};
+        int rc = encode(h, &mdz, dz, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (rc) return rc;
+    }
+    int rc = encode_activation(h, &m0, x0, d->N, d->H, d->W, d->C0, d->stride, 8, 8, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+    if (x1) {
+        rc = encode_activation(h, &m1, x1, d->N, d->H, d->W, d->C1, d->stride, 8, 8, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (rc) return rc;
+    } else {
+        m1 = m0;
+    }
+    const size_t smem = (size_t)g.stages * stage_bytes + (2 * g.stages + 1) * 8 + 16 + 1024;
+    static size_t configured = 0;
+    if (smem > configured) {
+        RAMNET_CUDA(cudaFuncSetAttribute(conv_wgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid((unsigned)splits, (unsigned)groups);
+    conv_wgrad_tcgen05_kernel<<<grid, kThreads, smem, s>>>(mdz, m0, m1, g, dw);
+    RAMNET_LAUNCH_CHECK(h);
+    return RAMNET_OK;
+}
 
 size_t conv_tf32_workspace_bytes(const ramnet_conv_desc *) { return 0; }
 

@@ -267,13 +267,13 @@ def pack_weights_dgrad(w_oihw: torch.Tensor, mma_kind: int, ci_begin: int, ci_co
     return out
 
 
-def conv_wgrad(dz, x0, x1, Cout, ksize, stride, dw, db):
+def conv_wgrad(dz, x0, x1, Cout, ksize, stride, dw, db, mma_kind=MMA_FP32):
     """dw [Cout, C0+C1, k, k] += , db [Cout] += ."""
     _check_nhwc(dz, 'conv_wgrad dz')
     _check_nhwc(x0, 'conv_wgrad x0')
     N, C0, H, W = x0.shape
     C1 = 0 if x1 is None else x1.shape[1]
-    d = ConvDesc(N, H, W, C0, C1, Cout, ksize, stride, 0, 0, 0, 0)
+    d = ConvDesc(N, H, W, C0, C1, Cout, ksize, stride, 0, mma_kind, 0, 0)
     with _Prof('wgrad', 2.0 * dz.shape[0] * dz.shape[2] * dz.shape[3] * Cout * (C0 + C1) * ksize * ksize, x0.device):
         check(_lib.load().ramnet_conv_wgrad(_h(x0), ctypes.byref(d), _p(dz), _p(x0), _p(x1), _p(dw), _p(db), _stream(x0)))
 
@@ -294,26 +294,28 @@ def zero_insert2x(x, Hout, Wout):
     return y
 
 
-def relu_bwd(dy, y):
+def relu_bwd(dy, y, round_tf32=False):
     _check_nhwc(dy, 'relu_bwd dy')
     _check_nhwc(y, 'relu_bwd y')
     dz = empty_nhwc(*y.shape, y.device)
-    check(_lib.load().ramnet_relu_bwd(_h(y), _p(dy), _p(y), _p(dz), y.numel(), _stream(y)))
+    check(_lib.load().ramnet_relu_bwd(_h(y), _p(dy), _p(y), _p(dz), y.numel(), FLAG_ROUND_TF32 if round_tf32 else 0,
+                                      _stream(y)))
     return dz
 
 
-def gru_out_bwd(dhn, h, u, o):
+def gru_out_bwd(dhn, h, u, o, round_tf32=False):
     N, C, H, W = h.shape
     dzo, dh = empty_nhwc(N, C, H, W, h.device), empty_nhwc(N, C, H, W, h.device)
     dzru = empty_nhwc(N, 2 * C, H, W, h.device)
     check(_lib.load().ramnet_gru_out_bwd(_h(h), _p(dhn), _p(h), _p(u), _p(o), _p(dzo), _p(dzru), _p(dh), N * H * W, C,
-                                         _stream(h)))
+                                         FLAG_ROUND_TF32 if round_tf32 else 0, _stream(h)))
     return dzo, dzru, dh
 
 
-def gru_ru_bwd(drh, h, r, dzru, dh):
+def gru_ru_bwd(drh, h, r, dzru, dh, round_tf32=False):
     N, C, H, W = h.shape
-    check(_lib.load().ramnet_gru_ru_bwd(_h(h), _p(drh), _p(h), _p(r), _p(dzru), _p(dh), N * H * W, C, _stream(h)))
+    check(_lib.load().ramnet_gru_ru_bwd(_h(h), _p(drh), _p(h), _p(r), _p(dzru), _p(dh), N * H * W, C,
+                                        FLAG_ROUND_TF32 if round_tf32 else 0, _stream(h)))
 
 
 def pred_bwd(ddepth, depth, x, w):
