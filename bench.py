@@ -278,7 +278,7 @@ def main_train(args):
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
     by = {}
-    for k, f, a, b in prof:
+    for k, f, a, b in (p_[:4] for p_ in prof):
         t, fl = by.get(k, (0.0, 0.0))
         by[k] = (t + a.elapsed_time(b), fl + f)
     peaks, peak_src = read_peaks()
@@ -396,6 +396,7 @@ def main_ours(args):
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
     model.cuda_graphs = graphs_on
+    prof = [p_[:4] for p_ in prof]
     conv_ms = sum(a.elapsed_time(b) for (k, f, a, b) in prof if k == 'conv')
     conv_flops = sum(f for (k, f, _, _) in prof if k == 'conv')
     n_conv = sum(1 for p in prof if p[0] == 'conv')

@@ -178,8 +178,10 @@ int ramnet_round_tf32(ramnet_handle *h, const float *x, float *y, int64_t n, voi
  * ramnet_zero_insert2x); weight/bias gradient = ramnet_conv_wgrad, ACCUMULATED (+=) into buffers in
  * nn.Conv2d layout [Cout, C0+C1, k, k] / [Cout]; the rest are pointwise adjoints of the fused epilogues.
  * dz: gradient w.r.t. the GEMM output (pre-activation), NHWC [N, Ho, Wo, Cout]. */
+size_t ramnet_conv_wgrad_workspace_bytes(const ramnet_handle *h, const ramnet_conv_desc *d);
 int ramnet_conv_wgrad(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz, const float *x0,
-                      const float *x1, float *dw_oihw, float *db, void *stream);
+                      const float *x1, float *dw_oihw, float *db, void *workspace, size_t workspace_bytes,
+                      void *stream);
 int ramnet_head_conv_wgrad(ramnet_handle *h, const float *x_nchw, const float *dz_nhwc, float *dw_oihw,
                            float *db, int N, int Cin, int H, int W, int Cout, void *stream);
 int ramnet_pack_weights_dgrad(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin,

@@ -39,8 +39,9 @@ SIGNATURES = {
     'ramnet_conv_workspace_bytes': (c_size_t, [POINTER(ConvDesc)]),
     'ramnet_conv_fwd': (c_int, [c_void_p, POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'ramnet_conv_wgrad_workspace_bytes': (c_size_t, [c_void_p, POINTER(ConvDesc)]),
     'ramnet_conv_wgrad': (c_int, [c_void_p, POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                  c_void_p]),
+                                  c_void_p, c_size_t, c_void_p]),
     'ramnet_head_conv_wgrad': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                        c_int, c_void_p]),
     'ramnet_pack_weights_dgrad': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,

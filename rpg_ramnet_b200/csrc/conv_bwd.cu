@@ -330,10 +330,17 @@ int grid_for(ramnet_handle *h, int64_t n) { return (int)imin64((n + 255) / 256, 
 }  // namespace
 
 int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz, const float *x0, const float *x1,
-                    float *dw, cudaStream_t s);
+                    float *dw, void *workspace, size_t workspace_bytes, cudaStream_t s);
+size_t conv_wgrad_tf32_workspace(const ramnet_handle *h, const ramnet_conv_desc *d);
+
+extern "C" size_t ramnet_conv_wgrad_workspace_bytes(const ramnet_handle *h, const ramnet_conv_desc *d) {
+    if (!h || !d || d->mma_kind != RAMNET_MMA_TF32) return 0;
+    return conv_wgrad_tf32_workspace(h, d);
+}
 
 extern "C" int ramnet_conv_wgrad(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz, const float *x0,
-                                 const float *x1, float *dw_oihw, float *db, void *stream) {
+                                 const float *x1, float *dw_oihw, float *db, void *workspace, size_t workspace_bytes,
+                                 void *stream) {
     RAMNET_CHECK_ARG(h && d && dz && x0 && dw_oihw, "conv_wgrad: NULL argument");
     RAMNET_CHECK_ARG(d->C0 % 4 == 0 && d->C1 % 4 == 0 && d->Cout % 4 == 0, "conv_wgrad: channel counts must be multiples of 4");
     RAMNET_CHECK_ARG((d->C1 == 0) == (x1 == nullptr), "conv_wgrad: x1 and C1 disagree");
@@ -344,7 +351,7 @@ extern "C" int ramnet_conv_wgrad(ramnet_handle *h, const ramnet_conv_desc *d, co
         RAMNET_LAUNCH_CHECK(h);
     }
     if (d->mma_kind == RAMNET_MMA_TF32) {
-        const int rc = conv_wgrad_tf32(h, d, dz, x0, x1, dw_oihw, (cudaStream_t)stream);
+        const int rc = conv_wgrad_tf32(h, d, dz, x0, x1, dw_oihw, workspace, workspace_bytes, (cudaStream_t)stream);
         if (rc != RAMNET_EUNSUPPORTED) return rc;      // unsupported shape: fp32 FFMA kernel below
     }
     db = nullptr;

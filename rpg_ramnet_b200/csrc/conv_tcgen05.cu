@@ -733,7 +733,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t l
 __global__ void __launch_bounds__(kThreads) conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_dz,
                                                                       const __grid_constant__ CUtensorMap map_x0,
                                                                       const __grid_constant__ CUtensorMap map_x1,
-                                                                      WgGeom g, float *__restrict__ dw) {
+                                                                      WgGeom g, float *__restrict__ part) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int a_boxes = 4, b_boxes = g.BN / kChunk;
@@ -852,26 +852,19 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_tcgen05_kernel(const __gr
             if (++stage == g.stages) { stage = 0; phase ^= 1; }
         }
     } else if (ntile > 0) {
-        // ---------------- epilogue: TMEM -> fp32 atomics into dW [Cout][Ct][ks][ks] ----------------
+        // ---------------- epilogue: TMEM -> this CTA's partial tile part[split][group][128][BN] (plain stores) ----------------
         const int quarter = warp & 3;
-        const int mrow = mb * 128 + quarter * 32 + lane;          // channel of the M operand
-        const int taps = g.ks * g.ks, Ct = g.C0 + g.C1;
+        const int row = quarter * 32 + lane;
         mbar_wait(accum_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        float *dst = part + (((size_t)blockIdx.x * gridDim.y + blockIdx.y) * 128 + row) * g.BN;
         for (int c = 0; c < g.BN; c += 16) {
             float v[16];
             tmem_ld16(lane_addr + (uint32_t)c, v);
-            if (mrow < g.Mch) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int ncol = nb * g.BN + c + j;               // channel of the N operand
-                    if (ncol < g.Nch) {
-                        const int co = g.m_from_x ? ncol : mrow, ci = g.m_from_x ? mrow : ncol;
-                        atomicAdd(dw + ((int64_t)co * Ct + ci) * taps + tap, v[j]);
-                    }
-                }
-            }
+            for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4 *>(dst + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
@@ -1069,14 +1062,43 @@ bool plan_halo(const ramnet_handle *h, const ramnet_conv_desc *d, HaloGeom *g) {
 }  // namespace
 
 
+// Sums the per-CTA partial tiles over the pixel splits and accumulates into dW [Cout][Ct][ks][ks] (deterministic:
+// every gradient element is owned by one thread, no atomics).
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restrict__ part, float *__restrict__ dw, WgGeom g,
+                                                           int splits, int groups) {
+    const int taps = g.ks * g.ks, Ct = g.C0 + g.C1;
+    const int64_t total = (int64_t)groups * 128 * g.BN;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int col = (int)(i % g.BN);
+        const int row = (int)((i / g.BN) % 128);
+        int grp = (int)(i / ((int64_t)g.BN * 128));
+        const int nb = grp % g.n_blocks;
+        grp /= g.n_blocks;
+        const int mb = grp % g.m_blocks, tap = grp / g.m_blocks;
+        const int mch = mb * 128 + row, nch = nb * g.BN + col;
+        if (mch >= g.Mch || nch >= g.Nch) continue;
+        float acc = 0.f;
+        for (int sp = 0; sp < splits; ++sp) acc += part[(size_t)sp * total + i];
+        const int co = g.m_from_x ? nch : mch, ci = g.m_from_x ? mch : nch;
+        dw[((int64_t)co * Ct + ci) * taps + tap] += acc;
+    }
+}
+
+bool plan_wgrad(const ramnet_handle *h, const ramnet_conv_desc *d, WgGeom *gp, int *splits_out, int *groups_out);
+
+size_t conv_wgrad_tf32_workspace(const ramnet_handle *h, const ramnet_conv_desc *d) {
+    WgGeom g;
+    int splits, groups;
+    if (!plan_wgrad(h, d, &g, &splits, &groups)) return 0;
+    return (size_t)splits * groups * 128 * g.BN * sizeof(float);
+}
+
 // dW += dZ^T * im2col(X) on the tensor cores (see conv_wgrad_tcgen05_kernel).  Returns RAMNET_EUNSUPPORTED
 // for shapes the kernel does not cover; the caller then uses the fp32 FFMA kernel.
-int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz, const float *x0, const float *x1,
-                    float *dw, cudaStream_t s) {
-    if (d->C0 % kChunk || d->C1 % kChunk || d->Cout % 16) return RAMNET_EUNSUPPORTED;
-    if (d->stride == 2 && ((d->H | d->W) & 1)) return RAMNET_EUNSUPPORTED;
-    if ((((uintptr_t)dz | (uintptr_t)x0 | (uintptr_t)x1) & 15) != 0) return RAMNET_EUNSUPPORTED;
-    WgGeom g;
+bool plan_wgrad(const ramnet_handle *h, const ramnet_conv_desc *d, WgGeom *gp, int *splits_out, int *groups_out) {
+    if (d->C0 % kChunk || d->C1 % kChunk || d->Cout % 16) return false;
+    if (d->stride == 2 && ((d->H | d->W) & 1)) return false;
+    WgGeom &g = *gp;
     g.N = d->N; g.Ho = conv_out_dim(d->H, d->stride); g.Wo = conv_out_dim(d->W, d->stride);
     g.Cout = d->Cout; g.C0 = d->C0; g.C1 = d->C1; g.ks = d->ksize; g.pad = d->ksize / 2; g.stride = d->stride;
     const int Ct = d->C0 + d->C1;
@@ -1088,19 +1110,36 @@ int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz
     g.n_blocks = (g.Nch + g.BN - 1) / g.BN;
     g.tiles_x = (g.Wo + 7) / 8; g.tiles_y = (g.Ho + 7) / 8;
     const int64_t total = (int64_t)g.tiles_x * g.tiles_y * g.N;
-    if (total > 0x7fffffff) return RAMNET_EUNSUPPORTED;
+    if (total > 0x7fffffff) return false;
     g.total_tiles = (int)total;
     const int groups = d->ksize * d->ksize * g.m_blocks * g.n_blocks;
-    int64_t splits = ((int64_t)h->sm_count * 4 + groups - 1) / groups;      // ~4 CTAs per SM in total
-    if (splits > total) splits = total;
+    // ~4 CTAs per SM in total, but at least 16 pixel tiles (8K MMA cycles) per CTA so the partial-tile flush amortises
+    int64_t splits = ((int64_t)h->sm_count * 4 + groups - 1) / groups;
+    if (splits > total / 16) splits = total / 16;
     if (splits < 1) splits = 1;
     g.tiles_per_cta = (int)((total + splits - 1) / splits);
     splits = (total + g.tiles_per_cta - 1) / g.tiles_per_cta;
     const int stage_bytes = (4 + g.BN / kChunk) * kWgBox;
-    g.debug = getenv("RAMNET_WG_DEBUG") ? atoi(getenv("RAMNET_WG_DEBUG")) : 0;
-    g.stages = (96 * 1024) / stage_bytes;      // two CTAs per SM
+    g.debug = 0;
+    g.stages = (96 * 1024) / stage_bytes;      // two CTAs per SM (measured faster than one CTA with a deeper ring)
     if (g.stages < 2) g.stages = 2;
     if (g.stages > 6) g.stages = 6;
+    *splits_out = (int)splits;
+    *groups_out = groups;
+    return true;
+}
+
+int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz, const float *x0, const float *x1,
+                    float *dw, void *workspace, size_t workspace_bytes, cudaStream_t s) {
+    if ((((uintptr_t)dz | (uintptr_t)x0 | (uintptr_t)x1 | (uintptr_t)workspace) & 15) != 0) return RAMNET_EUNSUPPORTED;
+    WgGeom g;
+    int splits_i, groups;
+    if (!plan_wgrad(h, d, &g, &splits_i, &groups)) return RAMNET_EUNSUPPORTED;
+    const int64_t splits = splits_i;
+    const size_t need = (size_t)splits * groups * 128 * g.BN * sizeof(float);
+    RAMNET_CHECK_ARG(workspace != nullptr && workspace_bytes >= need,
+                     "conv_wgrad(tf32): workspace of %zu bytes required (ramnet_conv_wgrad_workspace_bytes)", need);
+    const int stage_bytes = (4 + g.BN / kChunk) * kWgBox;
 
     CUtensorMap mdz, m0, m1;
     {
@@ -1125,7 +1164,11 @@ int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz
         configured = smem;
     }
     dim3 grid((unsigned)splits, (unsigned)groups);
-    conv_wgrad_tcgen05_kernel<<<grid, kThreads, smem, s>>>(mdz, m0, m1, g, dw);
+    conv_wgrad_tcgen05_kernel<<<grid, kThreads, smem, s>>>(mdz, m0, m1, g, (float *)workspace);
+    RAMNET_LAUNCH_CHECK(h);
+    const int64_t elems = (int64_t)groups * 128 * g.BN;
+    wgrad_reduce_kernel<<<(unsigned)imin64((elems + 255) / 256, (int64_t)h->sm_count * 8), 256, 0, s>>>(
+        (const float *)workspace, dw, g, (int)splits, groups);
     RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;
 }

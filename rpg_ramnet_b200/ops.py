@@ -123,8 +123,8 @@ PROFILE = None
 
 
 class _Prof:
-    def __init__(self, kind, flops, dev):
-        self.kind, self.flops, self.dev = kind, flops, dev
+    def __init__(self, kind, flops, dev, tag=None):
+        self.kind, self.flops, self.dev, self.tag = kind, flops, dev, tag
 
     def __enter__(self):
         if PROFILE is not None:
@@ -134,7 +134,8 @@ class _Prof:
     def __exit__(self, *exc):
         if PROFILE is not None:
             self.b.record(torch.cuda.current_stream(self.dev))
-            PROFILE.append((self.kind, self.flops, self.a, self.b))
+            PROFILE.append((self.kind, self.flops, self.a, self.b) if self.tag is None else
+                           (self.kind, self.flops, self.a, self.b, self.tag))
 
 
 _workspaces = {}
@@ -189,7 +190,8 @@ def conv_fwd(x0: torch.Tensor, x1: Optional[torch.Tensor], w_packed: torch.Tenso
     lib = _lib.load()
     nws = lib.ramnet_conv_workspace_bytes(ctypes.byref(d))
     ws = _workspace(dev, nws)
-    with _Prof('conv', 2.0 * N * Ho * Wo * Cout * (C0 + C1) * ksize * ksize, dev):
+    with _Prof('conv', 2.0 * N * Ho * Wo * Cout * (C0 + C1) * ksize * ksize, dev,
+               tag=PROFILE is not None and f'conv {H}x{W} {C0}+{C1}->{Cout} k{ksize} s{stride} e{epilogue}'):
         check(lib.ramnet_conv_fwd(_h(x0), ctypes.byref(d), _p(x0), _p(x1), _p(w_packed), _p(bias), _p(aux0),
                                   _p(aux1), _p(y0), _p(y1), _p(stash), _p(ws), nws, _stream(x0)))
     return (y0, y1) if (y1 is not None and epilogue != EPI_BIAS_RELU_PRED) else y0
@@ -274,8 +276,13 @@ def conv_wgrad(dz, x0, x1, Cout, ksize, stride, dw, db, mma_kind=MMA_FP32):
     N, C0, H, W = x0.shape
     C1 = 0 if x1 is None else x1.shape[1]
     d = ConvDesc(N, H, W, C0, C1, Cout, ksize, stride, 0, mma_kind, 0, 0)
-    with _Prof('wgrad', 2.0 * dz.shape[0] * dz.shape[2] * dz.shape[3] * Cout * (C0 + C1) * ksize * ksize, x0.device):
-        check(_lib.load().ramnet_conv_wgrad(_h(x0), ctypes.byref(d), _p(dz), _p(x0), _p(x1), _p(dw), _p(db), _stream(x0)))
+    with _Prof('wgrad', 2.0 * dz.shape[0] * dz.shape[2] * dz.shape[3] * Cout * (C0 + C1) * ksize * ksize, x0.device,
+               tag=PROFILE is not None and f'wgrad {H}x{W} {C0}+{C1}->{Cout} k{ksize} s{stride}'):
+        lib = _lib.load()
+        nws = lib.ramnet_conv_wgrad_workspace_bytes(_h(x0), ctypes.byref(d))
+        ws = _workspace(x0.device, nws)
+        check(lib.ramnet_conv_wgrad(_h(x0), ctypes.byref(d), _p(dz), _p(x0), _p(x1), _p(dw), _p(db), _p(ws), nws,
+                                    _stream(x0)))
 
 
 def head_conv_wgrad(x_nchw, dz, dw, db):
