@@ -26,6 +26,10 @@
 
 #include "common.cuh"
 
+#ifndef RAMNET_EPI_WARPS
+#define RAMNET_EPI_WARPS 8
+#endif
+
 namespace {
 
 constexpr int kTileM = 128;        // UMMA M
@@ -319,8 +323,8 @@ struct HaloGeom {
     unsigned long long *prof; // RAMNET_PROF=1: per-role wait-cycle counters (debug), else nullptr
 };
 
-constexpr int kHaloThreads = 384;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = RAMNET_EPI_WARPS;          // epilogue warps (multiple of 4: one or more per TMEM lane quarter)
+constexpr int kHaloThreads = 128 + 32 * kEpiWarps;
 
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
@@ -576,9 +580,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
         }
     } else if (warp >= 4) {
         // ---------------- epilogue: software-pipelined TMEM -> registers -> fused math -> global ----------------
+        constexpr int kParts = kEpiWarps / 4;     // warps per lane quarter; part p takes chunks c = 16*(p + kParts*j)
         const int quarter = warp & 3, half = (warp - 4) >> 2;
         const int row = quarter * 32 + lane;      // M row: 8 pixels along x per group, 16 groups along y
-        const int nch = (g.BN / 16 - half + 1) / 2;   // this warp's 16-column chunks: c = 16*half + 32*j
+        const int nch = (g.BN / 16 - half + kParts - 1) / kParts;
         const int units = ntiles * nch;
         int li = 0;
         for (int item = blockIdx.x; item < g.items; item += gridDim.x, ++li) {
@@ -598,7 +603,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
                 const int ox = x0 + (tl & (g.PTX - 1)) * 8 + (row & 7), oy = y0 + (tl >> g.ptx_log2) * 16 + (row >> 3);
                 u.valid = oy < g.Ho && ox < g.Wo;
                 u.m = ((int64_t)img * g.Ho + oy) * g.Wo + ox;
-                u.col = half * 16 + 32 * j;
+                u.col = (half + kParts * j) * 16;
                 return u;
             };
             auto next_unit = [&](const Unit &u) { return (u.j + 1 < nch) ? make_unit(u.tl, u.j + 1) : make_unit(u.tl + 1, 0); };

@@ -84,6 +84,8 @@ class ERGB2DepthRecurrent(BaseERGB2Depth):
             s, pred = runner.run(which, x, prev_super_states)
             return s, {'encoders': [None] * net.num_encoders, 'state_comb': list(s)}, pred
         x = x.to(self.gpu, non_blocking=True)
+        if prev_super_states is None:
+            prev_super_states = self._zero_states(x.shape[0], x.shape[2], x.shape[3])
         return net._pass(which, x, prev_super_states, last)
 
     def _zero_states(self, B, H, W):
