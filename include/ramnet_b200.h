@@ -144,7 +144,8 @@ int ramnet_conv_fwd(ramnet_handle *h, const ramnet_conv_desc *d, const float *x0
                     const float *w_packed, const float *bias, const float *aux0, const float *aux1,
                     float *y0, float *y1, float *y2, void *workspace, size_t workspace_bytes, void *stream);
 /* y2 (may be NULL) is the training stash: RAMNET_EPI_GRU_RU writes r = sigmoid(reset), RAMNET_EPI_GRU_OUT
- * writes o = tanh(candidate) — the values autograd would have kept for backward. */
+ * writes o = tanh(candidate), RAMNET_EPI_LSTM writes the four post-activation gates [M, C, 4] — the values autograd
+ * would have kept for backward. */
 /* [Cout, Cin, k, k] fp32 (nn.Conv2d layout) -> the layout `mma_kind` consumes:
  *   FP32: [k*k][Cin][Cout]           TF32: [k*k][Cout][Cin], values rounded to TF32 (rna).
  * `lstm_interleave` != 0 permutes output channels to 4c+g (RAMNET_EPI_LSTM). */
@@ -198,6 +199,10 @@ int ramnet_gru_out_bwd(ramnet_handle *h, const float *dhn, const float *hprev, c
                        float *dzo, float *dzru, float *dh, int64_t M, int C, int flags, void *stream);
 int ramnet_gru_ru_bwd(ramnet_handle *h, const float *drh, const float *hprev, const float *r, float *dzru,
                       float *dh, int64_t M, int C, int flags, void *stream);
+/* ConvLSTM adjoint (submodules.py:341-356): gates = post-activation (i,f,o,g) [M,C,4] stashed by RAMNET_EPI_LSTM (y2);
+ * dz [M,4C] comes out in nn.Conv2d row order (gate-major); dh / dc may be NULL (no gradient through that output). */
+int ramnet_lstm_bwd(ramnet_handle *h, const float *dh, const float *dc, const float *gates, const float *c_prev,
+                    const float *c_new, float *dz, float *dc_prev, int64_t M, int C, int flags, void *stream);
 /* pred + sigmoid adjoint: dx[m,c] = g*w[c], dw[c] += sum g*x[m,c], db += sum g, g = ddepth*s(1-s) */
 int ramnet_pred_bwd(ramnet_handle *h, const float *ddepth, const float *depth, const float *x, const float *w,
                     float *dx, float *dw, float *db, int64_t M, int C, void *stream);

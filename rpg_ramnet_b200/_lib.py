@@ -52,6 +52,8 @@ SIGNATURES = {
                                    c_int64, c_int, c_int, c_void_p]),
     'ramnet_gru_ru_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
                                   c_void_p]),
+    'ramnet_lstm_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_int64, c_int, c_int, c_void_p]),
     'ramnet_pred_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int64, c_int, c_void_p]),
     'ramnet_upsample2x_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -117,6 +117,38 @@ class GruFn(torch.autograd.Function):
                 dw_o, db_o, None, None, None)
 
 
+class LstmFn(torch.autograd.Function):
+    """ConvLSTM.forward (submodules.py:318-358) as one fused convolution with gate-interleaved columns; backward =
+    one pointwise gate adjoint + the transposed GEMMs on the unpermuted Gates.weight."""
+
+    @staticmethod
+    def forward(ctx, x, h, c, weight, bias, pack, kind):
+        N, _, H, W = x.shape
+        C = weight.shape[0] // 4
+        gates = torch.empty((N, H, W, C, 4), dtype=torch.float32, device=x.device)
+        hn, cn = ops.conv_fwd(x, h, pack.w, pack.b, 4 * C, 3, 1, ops.EPI_LSTM, kind, aux0=c,
+                              round_tf32=(kind == ops.MMA_TF32), stash=gates)
+        ctx.save_for_backward(x, h, c, cn, gates, weight)
+        ctx.kind = kind
+        ctx.mark_non_differentiable()
+        return hn, cn
+
+    @staticmethod
+    def backward(ctx, dhn, dcn):
+        x, h, c, cn, gates, weight = ctx.saved_tensors
+        kind = ctx.kind
+        N, Cx, H, W = x.shape
+        C = weight.shape[0] // 4
+        dz, dc = ops.lstm_bwd(None if dhn is None else _nhwc(dhn), None if dcn is None else _nhwc(dcn), gates, c, cn,
+                              round_tf32=(kind == ops.MMA_TF32))
+        dw = torch.zeros_like(weight, dtype=torch.float32)
+        db = torch.zeros(4 * C, dtype=torch.float32, device=x.device)
+        ops.conv_wgrad(dz, x, h, 4 * C, 3, 1, dw, db, kind)
+        dx = _dgrad(dz, weight, kind, 1, 0, Cx, (H, W)) if ctx.needs_input_grad[0] else None
+        dh = _dgrad(dz, weight, kind, 1, Cx, C, (H, W)) if ctx.needs_input_grad[1] else None
+        return dx, dh, (dc if ctx.needs_input_grad[2] else None), dw, db, None, None
+
+
 class UpsampleAddFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, skip, round_tf32):

@@ -54,7 +54,7 @@ struct EpiParams {
     const float *aux1;  // u
     float *y0;
     float *y1;
-    float *y2;  // training stash: GRU_RU -> r, GRU_OUT -> o (candidate), else unused; may be nullptr
+    float *y2;  // training stash: GRU_RU -> r, GRU_OUT -> o (candidate), LSTM -> gates [M][C][4]; may be nullptr
     int Cout;   // GEMM N
     int flags;  // RAMNET_FLAG_*
 };
@@ -168,6 +168,7 @@ __device__ __forceinline__ void epilogue_finish(const EpiParams &p, int64_t m, i
             cn[q] = gf * cprev[q] + gi * gc;
             hn[q] = go * tanhf(cn[q]);
             if (rnd) hn[q] = round_tf32(hn[q]);
+            if (p.y2) *reinterpret_cast<float4 *>(p.y2 + (m * C + (n0 >> 2) + q) * 4) = make_float4(gi, gf, go, gc);
         }
         if constexpr (NV % 16 == 0) {
 #pragma unroll

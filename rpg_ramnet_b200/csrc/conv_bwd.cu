@@ -198,6 +198,31 @@ __global__ void gru_ru_bwd_kernel(const float *__restrict__ drh, const float *__
     }
 }
 
+// ConvLSTM adjoint (submodules.py:341-356).  gates: post-activation [M][C][4] = (i, f, o, g) as stashed by the forward
+// epilogue.  dz is written in the ORIGINAL nn.Conv2d row order (gate-major blocks: in | remember | out | cell) so that
+// the weight / data gradients use the unpermuted Gates.weight.
+__global__ void lstm_bwd_kernel(const float *__restrict__ dh, const float *__restrict__ dc, const float *__restrict__ gates,
+                                const float *__restrict__ c_prev, const float *__restrict__ c_new, float *__restrict__ dz,
+                                float *__restrict__ dc_prev, int64_t M, int C, int round) {
+    const int64_t n = M * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / C;
+        const int c = (int)(i % C);
+        const float4 g = *reinterpret_cast<const float4 *>(gates + i * 4);   // i, f, o, gc
+        const float tc = tanhf(c_new[i]);
+        const float gh = dh ? dh[i] : 0.f;
+        const float dct = (dc ? dc[i] : 0.f) + gh * g.z * (1.f - tc * tc);
+        float zi = dct * g.w * g.x * (1.f - g.x);
+        float zf = dct * c_prev[i] * g.y * (1.f - g.y);
+        float zo = gh * tc * g.z * (1.f - g.z);
+        float zg = dct * g.x * (1.f - g.w * g.w);
+        if (round) { zi = round_tf32(zi); zf = round_tf32(zf); zo = round_tf32(zo); zg = round_tf32(zg); }
+        float *row = dz + m * 4 * C;
+        row[c] = zi; row[C + c] = zf; row[2 * C + c] = zo; row[3 * C + c] = zg;
+        dc_prev[i] = dct * g.y;
+    }
+}
+
 // prediction head adjoint: dlogit = ddepth * s(1-s); dx[m, c] = dlogit[m] * w[c]; dw[c] += sum_m dlogit*x[m,c]; db += sum dlogit
 __global__ void __launch_bounds__(256) pred_bwd_kernel(const float *__restrict__ ddepth, const float *__restrict__ depth,
                                                        const float *__restrict__ x, const float *__restrict__ w,
@@ -457,5 +482,14 @@ extern "C" int ramnet_head_conv_wgrad(ramnet_handle *h, const float *x_nchw, con
         colsum_kernel<<<(unsigned)((M + rpb - 1) / rpb), 256, 0, (cudaStream_t)stream>>>(dz_nhwc, M, Cout, db, rpb);
         RAMNET_LAUNCH_CHECK(h);
     }
+    return RAMNET_OK;
+}
+
+extern "C" int ramnet_lstm_bwd(ramnet_handle *h, const float *dh, const float *dc, const float *gates, const float *c_prev,
+                               const float *c_new, float *dz, float *dc_prev, int64_t M, int C, int flags, void *stream) {
+    RAMNET_CHECK_ARG(h && gates && c_prev && c_new && dz && dc_prev && (dh || dc) && M > 0 && C > 0, "lstm_bwd: bad argument");
+    lstm_bwd_kernel<<<grid_for(h, M * C), 256, 0, (cudaStream_t)stream>>>(dh, dc, gates, c_prev, c_new, dz, dc_prev, M, C,
+                                                                         flags & RAMNET_FLAG_ROUND_TF32);
+    RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;
 }

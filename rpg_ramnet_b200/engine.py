@@ -233,8 +233,16 @@ def lstm_layer(cache, key, lstm, kind, x, state, out_state=None):
     p = pack_lstm(cache, key, lstm, kind)
     st = None if state is None else (state[0], state[1])
     if needs_grad(x, lstm.Gates.weight, lstm.Gates.bias, *(st or ())):
-        raise RamnetError('the ConvLSTM backward pass is not implemented yet: train the shipped ConvGRU configuration '
-                          'or run ConvLSTM models under torch.no_grad()')
+        from .autograd import LstmFn
+        C = p.Cout // 4
+        if st is None:
+            h = ops.zeros_nhwc(x.shape[0], C, x.shape[2], x.shape[3], x.device)
+            c = ops.zeros_nhwc(x.shape[0], C, x.shape[2], x.shape[3], x.device)
+        else:
+            h, c = ops.as_nhwc(st[0]), ops.as_nhwc(st[1])
+        if h.shape[2:] != x.shape[2:]:
+            raise RamnetError(f'ConvLSTM: state shape {tuple(h.shape)} does not match input {tuple(x.shape)}')
+        return LstmFn.apply(x, h, c, lstm.Gates.weight, lstm.Gates.bias, p, kind)
     return run_lstm(x, state, p, kind, out_state=out_state)
 
 

@@ -343,3 +343,12 @@ def upsample2x_bwd(dy):
     dx = empty_nhwc(N, C, H2 // 2, W2 // 2, dy.device)
     check(_lib.load().ramnet_upsample2x_bwd(_h(dy), _p(dy), _p(dx), N, H2 // 2, W2 // 2, C, _stream(dy)))
     return dx
+
+
+def lstm_bwd(dh, dc, gates, c_prev, c_new, round_tf32=False):
+    N, C, H, W = c_prev.shape
+    dz = empty_nhwc(N, 4 * C, H, W, c_prev.device)
+    dc_prev = empty_nhwc(N, C, H, W, c_prev.device)
+    check(_lib.load().ramnet_lstm_bwd(_h(c_prev), _p(dh), _p(dc), _p(gates), _p(c_prev), _p(c_new), _p(dz), _p(dc_prev),
+                                      N * H * W, C, FLAG_ROUND_TF32 if round_tf32 else 0, _stream(c_prev)))
+    return dz, dc_prev

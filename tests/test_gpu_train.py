@@ -108,6 +108,54 @@ def test_gru_backward_vs_oracle(kind, C, H, W, N):
         assert _rel(mod.bias.grad, sd[f'g.{name}.bias'].grad) <= TOL[kind], name
 
 
+@pytest.mark.parametrize('kind', KINDS)
+@pytest.mark.parametrize('C,H,W,N', [(64, 8, 12, 2), (32, 10, 6, 1)])
+def test_lstm_backward_vs_oracle(kind, C, H, W, N):
+    from rpg_ramnet_b200 import engine as E, ops
+    from rpg_ramnet_b200.model.submodules import ConvLSTM
+    kid = {'fp32': ops.MMA_FP32, 'tf32': ops.MMA_TF32}[kind]
+    torch.manual_seed(C + 1)
+    lstm = ConvLSTM(C, C, 3)
+    sd = {'l.' + k: v.detach().double().requires_grad_(True) for k, v in lstm.state_dict().items()}
+    x, h, c = _rand((N, C, H, W), 1), _rand((N, C, H, W), 2, 0.7), _rand((N, C, H, W), 3)
+    gh, gc = _rand((N, C, H, W), 4), _rand((N, C, H, W), 5)
+    tx, th, tc = (t.double().requires_grad_(True) for t in (x, h, c))
+    rh, rc = O.conv_lstm(sd, 'l', tx, (th, tc))
+    (rh * gh.double()).sum().add((rc * gc.double()).sum()).backward()
+    lstm.to(dev())
+    gx, ghh, gcc = (nhwc(t).requires_grad_(True) for t in (x, h, c))
+    oh, oc = E.lstm_layer(E.WeightCache(), 'l', lstm, kid, gx, (ghh, gcc))
+    assert _rel(oh, rh) <= TOL[kind] and _rel(oc, rc) <= TOL[kind]
+    ((oh * nhwc(gh)).sum() + (oc * nhwc(gc)).sum()).backward()
+    for ours, ref, nm in ((gx, tx, 'x'), (ghh, th, 'h'), (gcc, tc, 'c')):
+        assert _rel(ours.grad, ref.grad) <= TOL[kind], nm
+    assert _rel(lstm.Gates.weight.grad, sd['l.Gates.weight'].grad) <= TOL[kind]
+    assert _rel(lstm.Gates.bias.grad, sd['l.Gates.bias'].grad) <= TOL[kind]
+
+
+def test_lstm_state_model_trains_like_the_oracle():
+    """state_combination='convlstm' (the baselines' state update): loss and gradients of one timestep vs oracle autograd."""
+    import rpg_ramnet_b200 as R
+    from helpers import load_case
+    g, meta = load_case('lstm_state')
+    meta = dict(meta, H=32, W=32, B=1, L=1)
+    model, cfg = build_product_model(meta, mma_kind='fp32')
+    model.to('cuda:0')
+    item = case_inputs(meta)[0]
+    states = {'events0': None, 'image': None}
+    preds, _, _ = model(item, None, states)
+    loss = sum(R.scale_invariant_loss(preds[k], item['depth_' + k].to('cuda:0')) for k in preds)
+    loss.backward()
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    rp = O.ergb2depth_recurrent(sd, cfg, item, None, states)[0]
+    rl = sum(O.si_loss(rp[k], item['depth_' + k]) for k in rp)
+    rl.backward()
+    assert abs(loss.item() - rl.item()) <= 2e-5
+    for n, p in model.named_parameters():
+        assert p.grad is not None, n
+        assert _rel(p.grad, sd[n].grad) <= 2e-3, n
+
+
 def test_head_upsample_pred_backward_vs_torch():
     from rpg_ramnet_b200 import autograd as AG
     # head conv
