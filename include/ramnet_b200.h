@@ -203,9 +203,10 @@ int ramnet_gru_ru_bwd(ramnet_handle *h, const float *drh, const float *hprev, co
  * dz [M,4C] comes out in nn.Conv2d row order (gate-major); dh / dc may be NULL (no gradient through that output). */
 int ramnet_lstm_bwd(ramnet_handle *h, const float *dh, const float *dc, const float *gates, const float *c_prev,
                     const float *c_new, float *dz, float *dc_prev, int64_t M, int C, int flags, void *stream);
-/* pred + sigmoid adjoint: dx[m,c] = g*w[c], dw[c] += sum g*x[m,c], db += sum g, g = ddepth*s(1-s) */
-int ramnet_pred_bwd(ramnet_handle *h, const float *ddepth, const float *depth, const float *x, const float *w,
-                    float *dx, float *dw, float *db, int64_t M, int C, void *stream);
+/* pred + sigmoid adjoint: dx[m,c] = g*w[c] (= dskip), dw[c] += sum g*(x+skip)[m,c], db += sum g, g = ddepth*s(1-s);
+ * skip may be NULL */
+int ramnet_pred_bwd(ramnet_handle *h, const float *ddepth, const float *depth, const float *x, const float *skip,
+                    const float *w, float *dx, float *dw, float *db, int64_t M, int C, void *stream);
 /* adjoint of ramnet_upsample2x_add: dx (= dskip) [N,H,W,C] from dy [N,2H,2W,C] */
 int ramnet_upsample2x_bwd(ramnet_handle *h, const float *dy, float *dx, int N, int H, int W, int C,
                           void *stream);

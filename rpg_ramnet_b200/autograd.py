@@ -165,14 +165,14 @@ class PredFn(torch.autograd.Function):
     """1x1 pred conv + sigmoid."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
-        depth = ops.pred_sigmoid(x, None, weight.detach(), None if bias is None else bias.detach())
-        ctx.save_for_backward(x, depth, weight)
+    def forward(ctx, x, skip, weight, bias):
+        depth = ops.pred_sigmoid(x, skip, weight.detach(), None if bias is None else bias.detach())
+        ctx.save_for_backward(x, skip, depth, weight)
         ctx.has_bias = bias is not None
         return depth
 
     @staticmethod
     def backward(ctx, ddepth):
-        x, depth, weight = ctx.saved_tensors
-        dx, dw, db = ops.pred_bwd(ddepth, depth, x, weight)
-        return dx, dw.view(weight.shape), (db if ctx.has_bias else None)
+        x, skip, depth, weight = ctx.saved_tensors
+        dx, dw, db = ops.pred_bwd(ddepth, depth, x, weight, skip)
+        return dx, (dx if skip is not None else None), dw.view(weight.shape), (db if ctx.has_bias else None)

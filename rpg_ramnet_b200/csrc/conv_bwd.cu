@@ -225,7 +225,8 @@ __global__ void lstm_bwd_kernel(const float *__restrict__ dh, const float *__res
 
 // prediction head adjoint: dlogit = ddepth * s(1-s); dx[m, c] = dlogit[m] * w[c]; dw[c] += sum_m dlogit*x[m,c]; db += sum dlogit
 __global__ void __launch_bounds__(256) pred_bwd_kernel(const float *__restrict__ ddepth, const float *__restrict__ depth,
-                                                       const float *__restrict__ x, const float *__restrict__ w,
+                                                       const float *__restrict__ x, const float *__restrict__ skip,
+                                                       const float *__restrict__ w,
                                                        float *__restrict__ dx, float *__restrict__ dw,
                                                        float *__restrict__ db, int64_t M, int C) {
     extern __shared__ float sacc[];   // [C + 1]
@@ -244,7 +245,11 @@ __global__ void __launch_bounds__(256) pred_bwd_kernel(const float *__restrict__
         const float dl = ddepth[m] * s * (1.f - s);
         if (lane8 == 0) dbacc += dl;
         for (int c = lane8 * 4, j = 0; c < C; c += 32, j += 4) {
-            const float4 xv = *reinterpret_cast<const float4 *>(x + m * C + c);
+            float4 xv = *reinterpret_cast<const float4 *>(x + m * C + c);
+            if (skip) {
+                const float4 sv = *reinterpret_cast<const float4 *>(skip + m * C + c);
+                xv.x += sv.x; xv.y += sv.y; xv.z += sv.z; xv.w += sv.w;
+            }
             *reinterpret_cast<float4 *>(dx + m * C + c) = make_float4(dl * wreg[j], dl * wreg[j + 1], dl * wreg[j + 2], dl * wreg[j + 3]);
             dwreg[j] += dl * xv.x; dwreg[j + 1] += dl * xv.y; dwreg[j + 2] += dl * xv.z; dwreg[j + 3] += dl * xv.w;
         }
@@ -326,28 +331,29 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(const float *__restrict
         *reinterpret_cast<float4 *>(&dz_s[p * 32 + q * 4]) = v;
     }
     __syncthreads();
-    const int combo = tid >> 1, half = tid & 1;
-    if (combo >= Cin * 25) return;
-    const int ci = combo / 25, r = (combo % 25) / 5, sx = combo % 5;
-    float acc[16];
+    const int half = tid & 1;
+    for (int combo = tid >> 1; combo < Cin * 25; combo += 128) {      // 128 (ci, r, s) combos per sweep (Cin <= 8: 2 sweeps)
+        const int ci = combo / 25, r = (combo % 25) / 5, sx = combo % 5;
+        float acc[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-    for (int p = 0; p < HW_TH * HW_TW; ++p) {
-        const float v = in_s[(ci * IH + p / HW_TW + r) * IW + p % HW_TW + sx];
-        const float4 *d4 = reinterpret_cast<const float4 *>(&dz_s[p * 32 + half * 16]);
+        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+        for (int p = 0; p < HW_TH * HW_TW; ++p) {
+            const float v = in_s[(ci * IH + p / HW_TW + r) * IW + p % HW_TW + sx];
+            const float4 *d4 = reinterpret_cast<const float4 *>(&dz_s[p * 32 + half * 16]);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 g = d4[q];
-            acc[4 * q] = fmaf(v, g.x, acc[4 * q]);
-            acc[4 * q + 1] = fmaf(v, g.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(v, g.z, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(v, g.w, acc[4 * q + 3]);
+            for (int q = 0; q < 4; ++q) {
+                const float4 g = d4[q];
+                acc[4 * q] = fmaf(v, g.x, acc[4 * q]);
+                acc[4 * q + 1] = fmaf(v, g.y, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(v, g.z, acc[4 * q + 2]);
+                acc[4 * q + 3] = fmaf(v, g.w, acc[4 * q + 3]);
+            }
         }
-    }
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const int co = half * 16 + j;
-        if (co < Cout) atomicAdd(dw + (((int64_t)co * Cin + ci) * 5 + r) * 5 + sx, acc[j]);
+        for (int j = 0; j < 16; ++j) {
+            const int co = half * 16 + j;
+            if (co < Cout) atomicAdd(dw + (((int64_t)co * Cin + ci) * 5 + r) * 5 + sx, acc[j]);
+        }
     }
 }
 
@@ -451,11 +457,12 @@ extern "C" int ramnet_gru_ru_bwd(ramnet_handle *h, const float *drh, const float
     return RAMNET_OK;
 }
 
-extern "C" int ramnet_pred_bwd(ramnet_handle *h, const float *ddepth, const float *depth, const float *x, const float *w,
-                               float *dx, float *dw, float *db, int64_t M, int C, void *stream) {
+extern "C" int ramnet_pred_bwd(ramnet_handle *h, const float *ddepth, const float *depth, const float *x,
+                               const float *skip, const float *w, float *dx, float *dw, float *db, int64_t M, int C,
+                               void *stream) {
     RAMNET_CHECK_ARG(h && ddepth && depth && x && w && dx && dw && M > 0 && C % 4 == 0 && C <= 64, "pred_bwd: bad argument (C <= 64)");
     const int blocks = (int)imin64((M * 8 + 255) / 256, (int64_t)h->sm_count * 8);
-    pred_bwd_kernel<<<blocks, 256, (C + 1) * sizeof(float), (cudaStream_t)stream>>>(ddepth, depth, x, w, dx, dw, db, M, C);
+    pred_bwd_kernel<<<blocks, 256, (C + 1) * sizeof(float), (cudaStream_t)stream>>>(ddepth, depth, x, skip, w, dx, dw, db, M, C);
     RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;
 }

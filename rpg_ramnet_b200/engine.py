@@ -253,17 +253,17 @@ def upsample_add(x, skip, tf32):
     return ops.upsample2x_add(x, skip, round_tf32=tf32)
 
 
-def pred_layer(x, pred_conv, norm_mod, norm_kind, training, return_logits=False):
+def pred_layer(x, pred_conv, norm_mod, norm_kind, training, return_logits=False, skip=None):
     w = pred_conv.weight
     b = pred_conv.bias
-    if needs_grad(x, w, b):
+    if needs_grad(x, skip, w, b):
         _no_fold_in_training(norm_mod, norm_kind)
         if return_logits:
             raise RamnetError('return_logits is an inference-only debugging aid')
         from .autograd import PredFn
-        return PredFn.apply(x, w, b)
+        return PredFn.apply(x, skip, w, b)
     wf, bf = _fold_norm(w.detach().float(), None if b is None else b.detach().float(), norm_mod, norm_kind, training)
-    return ops.pred_sigmoid(x, None, wf, bf, want_logits=return_logits)
+    return ops.pred_sigmoid(x, skip, wf, bf, want_logits=return_logits)
 
 
 # ------------------------------------------------------------------------------------------

@@ -74,11 +74,7 @@ class UNet(BaseUNet):
         cache, n = self._wcache, self.num_encoders
         if x.dim() != 4 or x.shape[2] % (1 << n) or x.shape[3] % (1 << n):
             raise RamnetError(f'input {tuple(x.shape)}: H and W must be divisible by {1 << n}')
-        if E.needs_grad(*self.parameters()):
-            raise RamnetError('training the non-recurrent UNet baseline (pred on x + head) is not wired yet; '
-                              'call under torch.no_grad()')
-        hp = E.pack_head(cache, 'head', self.head.conv2d)
-        x = ops.head_conv(x.float(), hp.w, hp.b, round_tf32=tf32)
+        x = E.head_layer(cache, 'head', self.head.conv2d, x, tf32)
         head, blocks = x, []
         for i, enc in enumerate(self.encoders):
             x = E.conv_layer(cache, f'enc{i}', enc.conv2d, kind, x, ops.EPI_BIAS_RELU,
@@ -93,10 +89,8 @@ class UNet(BaseUNet):
             x = E.conv_layer(cache, f'res{i}/2', rb.conv2, kind, y, ops.EPI_BIAS_RES_RELU, res=x,
                              norm_mod=getattr(rb, 'bn2', None), norm_kind=rb.norm, training=self.training, round_out=True)
         for i, dec in enumerate(self.decoders):
-            up = ops.upsample2x_add(x, blocks[n - i - 1], round_tf32=tf32)
+            up = E.upsample_add(x, blocks[n - i - 1], tf32)
             x = E.conv_layer(cache, f'dec{i}', dec.conv2d, kind, up, ops.EPI_BIAS_RELU,
                              norm_mod=getattr(dec, 'norm_layer', None), norm_kind=dec.norm, training=self.training)
         pr = self.pred
-        w, b = pr.conv2d.weight.detach().float(), None if pr.conv2d.bias is None else pr.conv2d.bias.detach().float()
-        w, b = E._fold_norm(w, b, getattr(pr, 'norm_layer', None), pr.norm, self.training)
-        return ops.pred_sigmoid(x, head, w, b, want_logits=return_logits)
+        return E.pred_layer(x, pr.conv2d, getattr(pr, 'norm_layer', None), pr.norm, self.training, return_logits, skip=head)

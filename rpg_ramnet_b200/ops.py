@@ -325,14 +325,14 @@ def gru_ru_bwd(drh, h, r, dzru, dh, round_tf32=False):
                                         FLAG_ROUND_TF32 if round_tf32 else 0, _stream(h)))
 
 
-def pred_bwd(ddepth, depth, x, w):
+def pred_bwd(ddepth, depth, x, w, skip=None):
     _check_nhwc(x, 'pred_bwd x')
     N, C, H, W = x.shape
     dx = empty_nhwc(N, C, H, W, x.device)
     dw = torch.zeros(C, dtype=torch.float32, device=x.device)
     db = torch.zeros(1, dtype=torch.float32, device=x.device)
     wv = w.detach().reshape(-1).contiguous().float()
-    check(_lib.load().ramnet_pred_bwd(_h(x), _p(ddepth.contiguous()), _p(depth.contiguous()), _p(x), _p(wv), _p(dx), _p(dw),
+    check(_lib.load().ramnet_pred_bwd(_h(x), _p(ddepth.contiguous()), _p(depth.contiguous()), _p(x), _p(skip), _p(wv), _p(dx), _p(dw),
                                       _p(db), N * H * W, C, _stream(x)))
     return dx, dw, db
 
