@@ -187,8 +187,10 @@ int ramnet_head_conv_wgrad(ramnet_handle *h, const float *x_nchw, const float *d
                            float *db, int N, int Cin, int H, int W, int Cout, void *stream);
 int ramnet_pack_weights_dgrad(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin,
                               int ksize, int mma_kind, int ci_begin, int ci_count, void *stream);
-int ramnet_zero_insert2x(ramnet_handle *h, const float *x, float *y, int N, int H, int W, int C, int Hout,
-                         int Wout, void *stream);
+/* y[n, 2h, 2w, :] = x[n, h, w, :] (+ skip), zeros elsewhere: input of a stride-2 conv's data gradient and of the
+ * TransposedConvLayer decoder (submodules.py:38-66; skip = statenet.py:306-308's skip sum). */
+int ramnet_zero_insert2x(ramnet_handle *h, const float *x, const float *skip, float *y, int N, int H, int W, int C,
+                         int Hout, int Wout, void *stream);
 /* dz = dy * (y > 0).  flags & RAMNET_FLAG_ROUND_TF32 (here and in the GRU adjoints): round the dz outputs to TF32
  * so that the tcgen05 dgrad / wgrad GEMMs that consume them truncate nothing. */
 int ramnet_relu_bwd(ramnet_handle *h, const float *dy, const float *y, float *dz, int64_t n, int flags,

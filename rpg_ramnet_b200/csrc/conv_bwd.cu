@@ -100,8 +100,9 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float *__restrict__ d
 }
 
 // y[n, 2h, 2w, c] = x[n, h, w, c], zeros elsewhere (the input of a stride-2 conv's data gradient)
-__global__ void __launch_bounds__(256) zero_insert_kernel(const float4 *__restrict__ x, float4 *__restrict__ y, int N,
-                                                          int H, int W, int C4, int Hout, int Wout) {
+__global__ void __launch_bounds__(256) zero_insert_kernel(const float4 *__restrict__ x, const float4 *__restrict__ skip,
+                                                          float4 *__restrict__ y, int N, int H, int W, int C4, int Hout,
+                                                          int Wout) {
     const int64_t total = (int64_t)N * Hout * Wout * C4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % C4);
@@ -111,8 +112,14 @@ __global__ void __launch_bounds__(256) zero_insert_kernel(const float4 *__restri
         const int oy = (int)(p % Hout);
         const int n = (int)(p / Hout);
         float4 v = make_float4(0, 0, 0, 0);
-        if (!(ox & 1) && !(oy & 1) && (oy >> 1) < H && (ox >> 1) < W)
-            v = x[(((int64_t)n * H + (oy >> 1)) * W + (ox >> 1)) * C4 + c];
+        if (!(ox & 1) && !(oy & 1) && (oy >> 1) < H && (ox >> 1) < W) {
+            const int64_t o = (((int64_t)n * H + (oy >> 1)) * W + (ox >> 1)) * C4 + c;
+            v = x[o];
+            if (skip) {
+                const float4 sv = skip[o];
+                v.x += sv.x; v.y += sv.y; v.z += sv.z; v.w += sv.w;
+            }
+        }
         y[i] = v;
     }
 }
@@ -410,11 +417,11 @@ extern "C" int ramnet_conv_wgrad(ramnet_handle *h, const ramnet_conv_desc *d, co
     return RAMNET_OK;
 }
 
-extern "C" int ramnet_zero_insert2x(ramnet_handle *h, const float *x, float *y, int N, int H, int W, int C, int Hout,
-                                    int Wout, void *stream) {
+extern "C" int ramnet_zero_insert2x(ramnet_handle *h, const float *x, const float *skip, float *y, int N, int H, int W,
+                                    int C, int Hout, int Wout, void *stream) {
     RAMNET_CHECK_ARG(h && x && y && C % 4 == 0 && Hout >= 2 * H - 1 && Wout >= 2 * W - 1, "zero_insert2x: bad argument");
     const int64_t total = (int64_t)N * Hout * Wout * (C / 4);
-    zero_insert_kernel<<<grid_for(h, total), 256, 0, (cudaStream_t)stream>>>((const float4 *)x, (float4 *)y, N, H, W, C / 4,
+    zero_insert_kernel<<<grid_for(h, total), 256, 0, (cudaStream_t)stream>>>((const float4 *)x, (const float4 *)skip, (float4 *)y, N, H, W, C / 4,
                                                                             Hout, Wout);
     RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;

@@ -246,6 +246,32 @@ def lstm_layer(cache, key, lstm, kind, x, state, out_state=None):
     return run_lstm(x, state, p, kind, out_state=out_state)
 
 
+def transposed_conv_layer(cache, key, tconv, kind, x, skip=None, norm_mod=None, norm_kind=None, training=False):
+    """TransposedConvLayer.forward (submodules.py:38-66): ConvTranspose2d(k=5, stride 2, padding 2, output_padding 1)
+    + bias + ReLU.  A transposed convolution IS the data gradient of the stride-2 convolution with the same weight
+    tensor, so it runs as zero-insertion + the forward tensor-core kernel on tap-flipped, channel-transposed weights."""
+    w = tconv.weight                      # [Cin, Cout, k, k] == nn.Conv2d layout of the conv it is the adjoint of
+    if needs_grad(x, skip, w, tconv.bias):
+        raise RamnetError('training with use_upsample_conv=False (TransposedConvLayer) is not implemented')
+    if norm_kind in ('BN', 'IN') and norm_mod is not None:
+        raise RamnetError('TransposedConvLayer with BatchNorm/InstanceNorm is not implemented')
+    if tuple(tconv.stride) != (2, 2) or tuple(tconv.output_padding) != (1, 1) or \
+            tuple(tconv.padding) != (w.shape[2] // 2,) * 2:
+        raise RamnetError('TransposedConvLayer: only stride 2, padding k//2, output_padding 1 is implemented')
+    Cin, Cout = w.shape[0], w.shape[1]
+
+    def build():
+        p = Packed()
+        p.w = ops.pack_weights_dgrad(w.detach().float(), kind, 0, Cout)
+        p.b = None if tconv.bias is None else tconv.bias.detach().float().contiguous()
+        p.Cout, p.ksize, p.stride = Cout, w.shape[2], 1
+        return p
+    p = cache.get(key, [w, tconv.bias], (kind, 'tconv'), build)
+    N, _, H, W = x.shape
+    up = ops.zero_insert2x(x, 2 * H, 2 * W, skip=skip)      # skip sum fused into the zero insertion
+    return ops.conv_fwd(up, None, p.w, p.b, Cout, p.ksize, 1, ops.EPI_BIAS_RELU, kind)
+
+
 def upsample_add(x, skip, tf32):
     if needs_grad(x, skip):
         from .autograd import UpsampleAddFn

@@ -235,12 +235,14 @@ class StateNetPhasedRecurrent(BaseStateNet):
                              norm_kind=rb.norm, training=self.training, round_out=True)
             x = E.conv_layer(cache, f'res{i}/2', rb.conv2, kind, y, ops.EPI_BIAS_RES_RELU, res=x,
                              norm_mod=getattr(rb, 'bn2', None), norm_kind=rb.norm, training=self.training, round_out=True)
-        if not self.use_upsample_conv:
-            raise RamnetError('use_upsample_conv=False (TransposedConvLayer) is not implemented yet')
         pr = self.pred
         tf32 = kind == ops.MMA_TF32
         for i, dec in enumerate(self.decoders):
             skip = None if i == 0 else ops.as_nhwc(pick(super_states[n - i - 1]))
+            if not self.use_upsample_conv:        # TransposedConvLayer decoder (statenet.py:81-82)
+                x = E.transposed_conv_layer(cache, f'dec{i}', dec.transposed_conv2d, kind, x, skip,
+                                            getattr(dec, 'norm_layer', None), dec.norm, self.training)
+                continue
             up = E.upsample_add(x, skip, tf32)
             last = i == len(self.decoders) - 1
             fuse = last and tf32 and dec.conv2d.out_channels % 32 == 0 and dec.conv2d.out_channels <= 256 and \

@@ -293,11 +293,13 @@ def head_conv_wgrad(x_nchw, dz, dw, db):
         check(_lib.load().ramnet_head_conv_wgrad(_h(x), _p(x), _p(dz), _p(dw), _p(db), N, Cin, H, W, dz.shape[1], _stream(x)))
 
 
-def zero_insert2x(x, Hout, Wout):
+def zero_insert2x(x, Hout, Wout, skip=None):
     _check_nhwc(x, 'zero_insert2x x')
     N, C, H, W = x.shape
     y = empty_nhwc(N, C, Hout, Wout, x.device)
-    check(_lib.load().ramnet_zero_insert2x(_h(x), _p(x), _p(y), N, H, W, C, Hout, Wout, _stream(x)))
+    if skip is not None:
+        _check_nhwc(skip, 'zero_insert2x skip')
+    check(_lib.load().ramnet_zero_insert2x(_h(x), _p(x), _p(skip), _p(y), N, H, W, C, Hout, Wout, _stream(x)))
     return y
 
 

@@ -10,7 +10,7 @@ from helpers import (MODEL_CASES, build_product_model, case_inputs, flat_supers,
 
 pytestmark = pytest.mark.gpu
 
-SUPPORTED = [c for c in MODEL_CASES if c != 'transposed']
+SUPPORTED = list(MODEL_CASES)
 # north_star tolerance: fp32 depth maps within 1e-3 relative of the reference forward.
 REL_TOL = {'fp32': 1e-4, 'tf32': 1e-3}
 
