@@ -228,6 +228,16 @@ int ramnet_si_loss_grad(ramnet_handle *h, const float *pred, const float *target
                         const double *stats, float weight, float n_lambda, float scale, float *grad,
                         void *stream);
 
+/* ---- §8f-1  MultiScaleGradient loss -------------------------------------- *
+ * Replaces model/loss.py:22-70 (4 x AvgPool2d + kornia spatial_gradient + boolean-mask sums) for C = 1 maps
+ * [N,1,H,W]: stats[2*s] = sum |g|, stats[2*s+1] = count of non-NaN gradient entries at scale s (float64, zeroed by
+ * the callee); value = (1/S) sum_s stats[2s]/stats[2s+1] * N * 2; grad = d value / d pred * scale (0 at NaN). */
+int ramnet_msg_loss_stats(ramnet_handle *h, const float *pred, const float *target, int N, int H, int W,
+                          int start_scale, int scales, double *stats, void *stream);
+int ramnet_msg_loss_value(ramnet_handle *h, const double *stats, int N, int scales, float *loss_out, void *stream);
+int ramnet_msg_loss_grad(ramnet_handle *h, const float *pred, const float *target, int N, int H, int W,
+                         int start_scale, int scales, const double *stats, float scale, float *grad, void *stream);
+
 /* ---- a-14  Adam --------------------------------------------------------- *
  * Replaces torch.optim.Adam.step (built at base/base_trainer.py:36-37,
  * stepped at trainer/lstm_trainer.py:453) with one multi-tensor launch over a

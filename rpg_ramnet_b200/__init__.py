@@ -7,7 +7,7 @@ this package is the Python host side that mirrors the reference's operator inter
 """
 from ._lib import RamnetError, launch_count  # noqa: F401
 from .model import ERGB2Depth, ERGB2DepthRecurrent, StateNetPhasedRecurrent, UNet  # noqa: F401
-from .model.loss import scale_invariant_loss  # noqa: F401
+from .model.loss import MultiScaleGradient, multi_scale_grad_loss, scale_invariant_loss  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from .utils.event_tensor_utils import events_to_voxel_grid, events_to_voxel_grid_pytorch  # noqa: F401
 

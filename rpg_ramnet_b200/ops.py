@@ -354,3 +354,29 @@ def lstm_bwd(dh, dc, gates, c_prev, c_new, round_tf32=False):
     check(_lib.load().ramnet_lstm_bwd(_h(c_prev), _p(dh), _p(dc), _p(gates), _p(c_prev), _p(c_new), _p(dz), _p(dc_prev),
                                       N * H * W, C, FLAG_ROUND_TF32 if round_tf32 else 0, _stream(c_prev)))
     return dz, dc_prev
+
+
+def msg_loss_stats(pred, target, start_scale=1, scales=4):
+    pred, target = pred.contiguous(), target.contiguous()
+    N, C, H, W = pred.shape
+    if C != 1:
+        raise _lib.RamnetError('multi_scale_grad_loss: single-channel depth maps [N,1,H,W] expected')
+    stats = torch.empty(2 * scales, dtype=torch.float64, device=pred.device)
+    check(_lib.load().ramnet_msg_loss_stats(_h(pred), _p(pred), _p(target), N, H, W, start_scale, scales, _p(stats),
+                                            _stream(pred)))
+    return stats
+
+
+def msg_loss_value(stats, N, scales=4):
+    out = torch.empty((), dtype=torch.float32, device=stats.device)
+    check(_lib.load().ramnet_msg_loss_value(_h(stats), _p(stats), N, scales, _p(out), _stream(stats)))
+    return out
+
+
+def msg_loss_grad(pred, target, stats, start_scale=1, scales=4, scale=1.0):
+    pred, target = pred.contiguous(), target.contiguous()
+    N, C, H, W = pred.shape
+    grad = torch.empty_like(pred)
+    check(_lib.load().ramnet_msg_loss_grad(_h(pred), _p(pred), _p(target), N, H, W, start_scale, scales, _p(stats), scale,
+                                           _p(grad), _stream(pred)))
+    return grad

@@ -321,6 +321,27 @@ def test_si_loss_large_vs_oracle():
     assert abs(loss.item() - O.si_loss(p.double(), t.double()).item()) <= 1e-6
 
 
+@pytest.mark.parametrize('nan_patch', [False, True])
+def test_multi_scale_grad_loss_vs_oracle(nan_patch):
+    """Value and gradient vs the oracle restatement + torch autograd (kornia semantics are restated, see oracle docstring)."""
+    import rpg_ramnet_b200 as R
+    gen = torch.Generator().manual_seed(9)
+    p, t = torch.rand(2, 1, 64, 96, generator=gen), torch.rand(2, 1, 64, 96, generator=gen)
+    if nan_patch:
+        t[0, :, 5:23, 40:61] = float('nan')
+        t[1, :, 0:3, 0:9] = float('nan')
+    pr = p.clone().requires_grad_(True)
+    ref = O.multi_scale_grad_loss(pr, t)
+    ref.backward()
+    pg = p.to(dev()).requires_grad_(True)
+    loss = R.multi_scale_grad_loss(pg, t.to(dev()))
+    assert abs(loss.item() - ref.item()) <= 2e-6 * max(1.0, abs(ref.item()))
+    (2.5 * loss).backward()
+    got, want = pg.grad.cpu(), 2.5 * pr.grad
+    assert float((got - want).abs().max()) <= 1e-6 + 1e-4 * float(want.abs().max())
+    assert float(got[torch.isnan(t)].abs().max() if nan_patch else 0.0) == 0.0
+
+
 def test_adam_golden_trajectory():
     from rpg_ramnet_b200 import ops
     g = np.load(os.path.join(GOLDEN, 'adam.npz'))
