@@ -232,7 +232,8 @@ def main_train(args):
     from rpg_ramnet_b200.utils.synthetic import synth_sequence
 
     model = build_model(torch, local, args.mma_kind, cuda_graphs=False).train()
-    opt = R.FusedAdam(model.parameters(), lr=3e-4)
+    use_graph = not args.no_graphs
+    opt = R.FusedAdam(model.parameters(), lr=3e-4, capturable=use_graph)
     items = synth_sequence(B, H, W, L, K_EVENTS, seed=2 + rank, with_targets=True)
     items = [{k: v.to(dev) for k, v in it.items()} for it in items]
     keys = ['events0', 'image']
@@ -257,6 +258,28 @@ def main_train(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    eager_step = step
+    launches_per_step = None
+    if use_graph:
+        # whole training step (forward, BPTT backward, grad all-reduce, fused Adam) as ONE CUDA graph: the ~4000
+        # launches per step are otherwise bound by the Python / autograd host overhead, not by the GPU
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                eager_step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        l_before = R.launch_count(local)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_loss = eager_step()
+        launches_per_step = R.launch_count(local) - l_before
+
+        def step():                      # inputs live in static device tensors (`items`); new data would be copied into them
+            graph.replay()
+            return static_loss
+
     for _ in range(args.warmup):
         step()
     barrier()
@@ -273,8 +296,10 @@ def main_train(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     launches = R.launch_count(local) - l0
+    if launches_per_step is not None:
+        launches = launches_per_step * args.steps
     ops.PROFILE = []
-    step()
+    eager_step()
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
     by = {}
@@ -290,7 +315,7 @@ def main_train(args):
                 'value': world * MAPS_PER_STEP * args.steps / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32' if args.mma_kind == 'tf32' else 'f32',
-                'data': 'synthetic', 'mode': 'train', 'loss': float(loss),
+                'data': 'synthetic', 'mode': 'train', 'loss': float(loss), 'cuda_graph': use_graph,
                 'config': {'workload': f'BASELINE configs[2] per GPU: RAM-Net shipped block, {W}x{H}, batch {B}/GPU, seq {L}, '
                                        f'K=1, SI loss on events0+image, full BPTT, fused Adam(3e-4)',
                            'parallelism': f'dp{world}: flat fp32 grad all-reduce (NCCL) + 3-double loss-statistics all-reduce'},

@@ -246,6 +246,11 @@ int ramnet_msg_loss_grad(ramnet_handle *h, const float *pred, const float *targe
 int ramnet_adam_step(ramnet_handle *h, float *p, const float *g, float *m, float *v, int64_t n,
                      double lr, double beta1, double beta2, double eps, double weight_decay, int step,
                      void *stream);
+/* Same update with the 1-based step number kept in device memory: *step_counter is incremented, then used.  Lets a
+ * whole training step (forward, backward, optimiser) be captured in one CUDA graph and replayed. */
+int ramnet_adam_step_dev(ramnet_handle *h, float *p, const float *g, float *m, float *v, int64_t n, double lr,
+                         double beta1, double beta2, double eps, double weight_decay, int *step_counter,
+                         void *stream);
 
 #ifdef __cplusplus
 }

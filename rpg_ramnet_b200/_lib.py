@@ -74,6 +74,8 @@ SIGNATURES = {
     'ramnet_msg_loss_value': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'ramnet_msg_loss_grad': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_float,
                                      c_void_p, c_void_p]),
+    'ramnet_adam_step_dev': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double,
+                                     c_double, c_double, c_double, c_void_p, c_void_p]),
     'ramnet_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double,
                                  c_double, c_double, c_double, c_int, c_void_p]),
 }

@@ -719,7 +719,6 @@ struct WgGeom {
     int tiles_x, tiles_y;    // 8x8 pixel tiles over (Wo, Ho)
     int tiles_per_cta, total_tiles;
     int stages;
-    int debug;               // RAMNET_WG_DEBUG experiments
 };
 
 constexpr int kWgTile = 64;                         // pixels per K tile (8 x 8)
@@ -832,20 +831,14 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_tcgen05_kernel(const __gr
     } else if (warp == 1) {
         // ---------------- MMA issuer ----------------
         // idesc: kind::tf32, fp32 accumulate, A and B MN-major (bits 15, 16), M = 128, N = BN
-        uint32_t idesc = make_idesc_tf32(g.BN) | (1u << 15) | (1u << 16);
-        if (g.debug & 1) idesc &= ~(1u << 15);
-        if (g.debug & 2) idesc &= ~(1u << 16);
+        const uint32_t idesc = make_idesc_tf32(g.BN) | (1u << 15) | (1u << 16);
         int stage = 0;
         uint32_t phase = 0;
         for (int it = 0; it < ntile; ++it) {
             mbar_wait(full_bar + stage, phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-            uint64_t adesc = make_smem_desc_mn(sa, kWgBox), bdesc = make_smem_desc_mn(sa + a_boxes * kWgBox, kWgBox);
-            if (g.debug & 4) {   // swapped LBO / SBO roles
-                adesc = (adesc & ~((0x3FFFull << 16) | (0x3FFFull << 32))) | ((uint64_t)(512 >> 4) << 16) | ((uint64_t)(kWgBox >> 4) << 32);
-                bdesc = (bdesc & ~((0x3FFFull << 16) | (0x3FFFull << 32))) | ((uint64_t)(512 >> 4) << 16) | ((uint64_t)(kWgBox >> 4) << 32);
-            }
+            const uint64_t adesc = make_smem_desc_mn(sa, kWgBox), bdesc = make_smem_desc_mn(sa + a_boxes * kWgBox, kWgBox);
             if (elect_one()) {
 #pragma unroll
                 for (int kk = 0; kk < kWgTile / 8; ++kk)      // 8 pixel rows = 1024 bytes per K step: +64 in the >>4 field
@@ -1125,7 +1118,6 @@ bool plan_wgrad(const ramnet_handle *h, const ramnet_conv_desc *d, WgGeom *gp, i
     g.tiles_per_cta = (int)((total + splits - 1) / splits);
     splits = (total + g.tiles_per_cta - 1) / g.tiles_per_cta;
     const int stage_bytes = (4 + g.BN / kChunk) * kWgBox;
-    g.debug = 0;
     g.stages = (96 * 1024) / stage_bytes;      // two CTAs per SM (measured faster than one CTA with a deeper ring)
     if (g.stages < 2) g.stages = 2;
     if (g.stages > 6) g.stages = 6;

@@ -380,3 +380,9 @@ def msg_loss_grad(pred, target, stats, start_scale=1, scales=4, scale=1.0):
     check(_lib.load().ramnet_msg_loss_grad(_h(pred), _p(pred), _p(target), N, H, W, start_scale, scales, _p(stats), scale,
                                            _p(grad), _stream(pred)))
     return grad
+
+
+def adam_step_dev(p, g, m, v, step_counter, lr=3e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0):
+    """Graph-capturable fused Adam: `step_counter` is an int32 CUDA tensor holding the number of steps taken so far."""
+    check(_lib.load().ramnet_adam_step_dev(_h(p), _p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps,
+                                           weight_decay, _p(step_counter), _stream(p)))

@@ -14,7 +14,8 @@ from .distributed import all_reduce_flat_grads
 
 
 class FusedAdam:
-    def __init__(self, params, lr=3e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None):
+    def __init__(self, params, lr=3e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None,
+                 capturable=False):
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError('FusedAdam: no trainable parameters')
@@ -31,6 +32,9 @@ class FusedAdam:
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
         self.step_count = 0
+        # capturable=True keeps the step number on the device so that step() can live inside a captured CUDA graph
+        self.capturable = capturable
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         off = 0
         with torch.no_grad():
             for p, sz in zip(self.params, sizes):
@@ -59,8 +63,12 @@ class FusedAdam:
             off += ((p.numel() + 3) // 4) * 4
         all_reduce_flat_grads(self.flat_g, self.process_group)
         self.step_count += 1
-        ops.adam_step(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, self.step_count, lr=self.lr,
-                      beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay)
+        if self.capturable:
+            ops.adam_step_dev(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, self.step_dev, lr=self.lr,
+                              beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay)
+        else:
+            ops.adam_step(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, self.step_count, lr=self.lr,
+                          beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay)
         engine.bump_weight_epoch()       # packed weights / captured graphs are stale now
 
     def state_dict(self):
