@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradGeom g, const floa
     }
 }
 
-// db[c] += sum over rows of dz[M][C]
+// db[c] += sum over rows of dz[M][C]  (generic fallback: one thread per column, serial over the block's rows)
 __global__ void __launch_bounds__(256) colsum_kernel(const float *__restrict__ dz, int64_t M, int C,
                                                      float *__restrict__ db, int rows_per_block) {
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
@@ -96,6 +96,51 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float *__restrict__ d
         float acc = 0.f;
         for (int64_t r = r0; r < r1; ++r) acc += dz[r * C + c];
         atomicAdd(db + c, acc);
+    }
+}
+
+// Same, for C/4 a power of two <= 256: dz is read as one flat float4 stream (coalesced, every thread busy).  The grid
+// stride is a multiple of C/4, so a thread always lands on the same four columns; the block folds its 256 partial sums
+// through shared memory and issues one atomic per column.
+__global__ void __launch_bounds__(256) colsum4_kernel(const float4 *__restrict__ dz, int64_t total4, int C4,
+                                                      float *__restrict__ db) {
+    __shared__ float4 part[256];
+    float4 a0 = make_float4(0, 0, 0, 0), a1 = a0;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    for (; i + stride < total4; i += 2 * stride) {          // two independent loads in flight per thread
+        const float4 v0 = dz[i], v1 = dz[i + stride];
+        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+        a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+    }
+    if (i < total4) {
+        const float4 v0 = dz[i];
+        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+    }
+    part[threadIdx.x] = make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
+    __syncthreads();
+    if ((int)threadIdx.x < C4) {
+        float4 acc = part[threadIdx.x];
+        for (int j = threadIdx.x + C4; j < 256; j += C4) {
+            const float4 v = part[j];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        float *o = db + 4 * threadIdx.x;
+        atomicAdd(o, acc.x); atomicAdd(o + 1, acc.y); atomicAdd(o + 2, acc.z); atomicAdd(o + 3, acc.w);
+    }
+}
+
+static void launch_colsum(const ramnet_handle *h, const float *dz, int64_t M, int C, float *db, cudaStream_t s) {
+    const int C4 = C / 4;
+    if (C % 4 == 0 && C4 <= 256 && (C4 & (C4 - 1)) == 0 && (((uintptr_t)dz) & 15) == 0) {
+        const int64_t total4 = M * C4;
+        int64_t blocks = (total4 + 256 * 8 - 1) / (256 * 8);           // >= 8 float4 per thread
+        if (blocks > (int64_t)h->sm_count * 8) blocks = (int64_t)h->sm_count * 8;
+        if (blocks < 1) blocks = 1;
+        colsum4_kernel<<<(unsigned)blocks, 256, 0, s>>>((const float4 *)dz, total4, C4, db);
+    } else {
+        const int rpb = 2048;
+        colsum_kernel<<<(unsigned)((M + rpb - 1) / rpb), 256, 0, s>>>(dz, M, C, db, rpb);
     }
 }
 
@@ -384,8 +429,7 @@ extern "C" int ramnet_conv_wgrad(ramnet_handle *h, const ramnet_conv_desc *d, co
     RAMNET_CHECK_ARG((d->C1 == 0) == (x1 == nullptr), "conv_wgrad: x1 and C1 disagree");
     if (db) {
         const int64_t Mrows = (int64_t)d->N * conv_out_dim(d->H, d->stride) * conv_out_dim(d->W, d->stride);
-        const int rpb = 2048;
-        colsum_kernel<<<(unsigned)((Mrows + rpb - 1) / rpb), 256, 0, (cudaStream_t)stream>>>(dz, Mrows, d->Cout, db, rpb);
+        launch_colsum(h, dz, Mrows, d->Cout, db, (cudaStream_t)stream);
         RAMNET_LAUNCH_CHECK(h);
     }
     if (d->mma_kind == RAMNET_MMA_TF32) {
@@ -410,8 +454,7 @@ extern "C" int ramnet_conv_wgrad(ramnet_handle *h, const ramnet_conv_desc *d, co
     conv_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, dz, x0, x1, dw_oihw);
     RAMNET_LAUNCH_CHECK(h);
     if (db) {
-        const int rpb = 2048;
-        colsum_kernel<<<(unsigned)((g.M + rpb - 1) / rpb), 256, 0, (cudaStream_t)stream>>>(dz, g.M, d->Cout, db, rpb);
+        launch_colsum(h, dz, g.M, d->Cout, db, (cudaStream_t)stream);
         RAMNET_LAUNCH_CHECK(h);
     }
     return RAMNET_OK;
@@ -492,8 +535,7 @@ extern "C" int ramnet_head_conv_wgrad(ramnet_handle *h, const float *x_nchw, con
     RAMNET_LAUNCH_CHECK(h);
     if (db) {
         const int64_t M = (int64_t)N * H * W;
-        const int rpb = 2048;
-        colsum_kernel<<<(unsigned)((M + rpb - 1) / rpb), 256, 0, (cudaStream_t)stream>>>(dz_nhwc, M, Cout, db, rpb);
+        launch_colsum(h, dz_nhwc, M, Cout, db, (cudaStream_t)stream);
         RAMNET_LAUNCH_CHECK(h);
     }
     return RAMNET_OK;

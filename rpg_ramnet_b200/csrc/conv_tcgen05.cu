@@ -716,13 +716,15 @@ struct WgGeom {
     int Mch, Nch;            // channels of the M / N operand (Cout or C0+C1)
     int BN;                  // N channels per CTA (multiple of 32, <= 128)
     int m_blocks, n_blocks;
-    int tiles_x, tiles_y;    // 8x8 pixel tiles over (Wo, Ho)
+    int tiles_x, tiles_y;    // 8 x TR pixel tiles over (Wo, Ho)
     int tiles_per_cta, total_tiles;
     int stages;
+    int T;                   // filter taps per CTA: 1 (per-tap mode) or ks (one filter row: the X box carries a halo)
+    int TR;                  // image rows per K tile (8 or 4): a tile is 8 pixels x TR rows
+    int HXw;                 // width in pixels of the X box: 8 + T - 1
+    int a_box, b_box;        // bytes of one 32-channel box of the M / N operand
 };
 
-constexpr int kWgTile = 64;                         // pixels per K tile (8 x 8)
-constexpr int kWgBox = kWgTile * kChunk * 4;        // 8 KB: one 32-channel box of one K tile
 
 __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
     uint64_t d = 0;
@@ -741,7 +743,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_tcgen05_kernel(const __gr
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int a_boxes = 4, b_boxes = g.BN / kChunk;
-    const int stage_bytes = (a_boxes + b_boxes) * kWgBox;
+    const int stage_bytes = a_boxes * g.a_box + b_boxes * g.b_box;
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)g.stages * stage_bytes);
     uint64_t *empty_bar = full_bar + g.stages;
     uint64_t *accum_bar = empty_bar + g.stages;
@@ -753,13 +755,13 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_tcgen05_kernel(const __gr
     const int nb = t % g.n_blocks;
     t /= g.n_blocks;
     const int mb = t % g.m_blocks;
-    const int tap = t / g.m_blocks;
-    const int r = tap / g.ks, sx = tap % g.ks;
+    const int tap = t / g.m_blocks;                    // per-tap mode: tap index; row mode: filter row
+    const int r = g.T == 1 ? tap / g.ks : tap, sx = g.T == 1 ? tap % g.ks : 0;
     const int tile_begin = blockIdx.x * g.tiles_per_cta;
     const int tile_end = min(tile_begin + g.tiles_per_cta, g.total_tiles);
     const int ntile = tile_end - tile_begin;
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < g.BN) tmem_cols <<= 1;
+    while ((int)tmem_cols < g.T * g.BN) tmem_cols <<= 1;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_dz);
@@ -793,11 +795,11 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_tcgen05_kernel(const __gr
             tt /= g.tiles_x;
             const int tyi = tt % g.tiles_y;
             const int img = tt / g.tiles_y;
-            const int ox0 = txi * 8, oy0 = tyi * 8;
+            const int ox0 = txi * 8, oy0 = tyi * g.TR;
             mbar_wait(empty_bar + stage, phase ^ 1);
             if (elect_one()) {
                 uint8_t *sa = smem + (size_t)stage * stage_bytes;
-                uint8_t *sb = sa + a_boxes * kWgBox;
+                uint8_t *sb = sa + a_boxes * g.a_box;
                 mbar_expect_tx(full_bar + stage, (uint32_t)stage_bytes);
                 auto load_dz = [&](uint8_t *dst, int ch) {       // ch beyond Cout: zero-filled by TMA
                     tma_load_4d(dst, &map_dz, full_bar + stage, ch, ox0, oy0, img);
@@ -818,11 +820,11 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_tcgen05_kernel(const __gr
                 };
                 for (int q = 0; q < a_boxes; ++q) {
                     const int ch = (mb * 4 + q) * kChunk;
-                    if (g.m_from_x) load_x(sa + q * kWgBox, ch); else load_dz(sa + q * kWgBox, ch);
+                    if (g.m_from_x) load_x(sa + q * g.a_box, ch); else load_dz(sa + q * g.a_box, ch);
                 }
                 for (int q = 0; q < b_boxes; ++q) {
                     const int ch = nb * g.BN + q * kChunk;
-                    if (g.m_from_x) load_dz(sb + q * kWgBox, ch); else load_x(sb + q * kWgBox, ch);
+                    if (g.m_from_x) load_dz(sb + q * g.b_box, ch); else load_x(sb + q * g.b_box, ch);
                 }
             }
             __syncwarp();
@@ -838,11 +840,18 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_tcgen05_kernel(const __gr
             mbar_wait(full_bar + stage, phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-            const uint64_t adesc = make_smem_desc_mn(sa, kWgBox), bdesc = make_smem_desc_mn(sa + a_boxes * kWgBox, kWgBox);
+            const uint64_t adesc = make_smem_desc_mn(sa, (uint32_t)g.a_box);
+            const uint64_t bdesc = make_smem_desc_mn(sa + a_boxes * g.a_box, (uint32_t)g.b_box);
+            // address-field (>>4) steps: the X box rows are HXw pixels wide (halo in row mode), the dZ box rows 8 pixels
+            const uint32_t a_row = (uint32_t)(g.m_from_x ? g.HXw : 8) * 8u, b_row = (uint32_t)(g.m_from_x ? 8 : g.HXw) * 8u;
+            const uint32_t a_tap = g.m_from_x ? 8u : 0u, b_tap = g.m_from_x ? 0u : 8u;     // +1 pixel = 128 B per tap
             if (elect_one()) {
-#pragma unroll
-                for (int kk = 0; kk < kWgTile / 8; ++kk)      // 8 pixel rows = 1024 bytes per K step: +64 in the >>4 field
-                    umma_tf32(tmem_base, adesc + 64 * kk, bdesc + 64 * kk, idesc, (it | kk) != 0);
+                for (int tp = 0; tp < g.T; ++tp) {
+#pragma unroll 4
+                    for (int kk = 0; kk < g.TR; ++kk)             // one image row of 8 pixels (K = 8) per MMA
+                        umma_tf32(tmem_base + (uint32_t)(tp * g.BN), adesc + (uint64_t)(kk * a_row + tp * a_tap),
+                                  bdesc + (uint64_t)(kk * b_row + tp * b_tap), idesc, (it | kk) != 0);
+                }
                 umma_commit(empty_bar + stage);
                 if (it == ntile - 1) umma_commit(accum_bar);
             }
@@ -856,8 +865,9 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_tcgen05_kernel(const __gr
         mbar_wait(accum_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        float *dst = part + (((size_t)blockIdx.x * gridDim.y + blockIdx.y) * 128 + row) * g.BN;
-        for (int c = 0; c < g.BN; c += 16) {
+        const int ncols = g.T * g.BN;
+        float *dst = part + (((size_t)blockIdx.x * gridDim.y + blockIdx.y) * 128 + row) * ncols;
+        for (int c = 0; c < ncols; c += 16) {
             float v[16];
             tmem_ld16(lane_addr + (uint32_t)c, v);
 #pragma unroll
@@ -1064,16 +1074,17 @@ bool plan_halo(const ramnet_handle *h, const ramnet_conv_desc *d, HaloGeom *g) {
 // every gradient element is owned by one thread, no atomics).
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restrict__ part, float *__restrict__ dw, WgGeom g,
                                                            int splits, int groups) {
-    const int taps = g.ks * g.ks, Ct = g.C0 + g.C1;
-    const int64_t total = (int64_t)groups * 128 * g.BN;
+    const int taps = g.ks * g.ks, Ct = g.C0 + g.C1, ncols = g.T * g.BN;
+    const int64_t total = (int64_t)groups * 128 * ncols;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int col = (int)(i % g.BN);
-        const int row = (int)((i / g.BN) % 128);
-        int grp = (int)(i / ((int64_t)g.BN * 128));
+        const int cc = (int)(i % ncols);
+        const int row = (int)((i / ncols) % 128);
+        int grp = (int)(i / ((int64_t)ncols * 128));
         const int nb = grp % g.n_blocks;
         grp /= g.n_blocks;
-        const int mb = grp % g.m_blocks, tap = grp / g.m_blocks;
-        const int mch = mb * 128 + row, nch = nb * g.BN + col;
+        const int mb = grp % g.m_blocks, tr = grp / g.m_blocks;
+        const int tap = g.T == 1 ? tr : tr * g.ks + cc / g.BN;      // row mode: group = filter row, column block = tap in row
+        const int mch = mb * 128 + row, nch = nb * g.BN + cc % g.BN;
         if (mch >= g.Mch || nch >= g.Nch) continue;
         float acc = 0.f;
         for (int sp = 0; sp < splits; ++sp) acc += part[(size_t)sp * total + i];
@@ -1088,7 +1099,7 @@ size_t conv_wgrad_tf32_workspace(const ramnet_handle *h, const ramnet_conv_desc 
     WgGeom g;
     int splits, groups;
     if (!plan_wgrad(h, d, &g, &splits, &groups)) return 0;
-    return (size_t)splits * groups * 128 * g.BN * sizeof(float);
+    return (size_t)splits * groups * 128 * g.T * g.BN * sizeof(float);
 }
 
 // dW += dZ^T * im2col(X) on the tensor cores (see conv_wgrad_tcgen05_kernel).  Returns RAMNET_EUNSUPPORTED
@@ -1103,24 +1114,50 @@ bool plan_wgrad(const ramnet_handle *h, const ramnet_conv_desc *d, WgGeom *gp, i
     g.m_from_x = Ct > d->Cout ? 1 : 0;                 // the operand with more channels fills the 128 MMA rows
     g.Mch = g.m_from_x ? Ct : d->Cout;
     g.Nch = g.m_from_x ? d->Cout : Ct;
-    g.BN = g.Nch >= 128 ? 128 : ((g.Nch + 31) / 32) * 32;
+    // Row mode (stride 1): one CTA owns a whole filter row; the X box carries a (ks-1)-pixel halo and every tap of the row
+    // reads it through a shifted descriptor, so X and dZ are fetched ks times instead of ks*ks times.  The ks accumulators
+    // need ks*BN <= 512 TMEM columns.
+    g.T = (d->stride == 1 && d->ksize > 1 && !getenv("RAMNET_WGRAD_PER_TAP")) ? d->ksize : 1;
+    g.TR = g.T == 1 ? 8 : 4;
+    g.HXw = 8 + g.T - 1;
+    int bn_cap = g.T == 1 ? 128 : (g.T == 3 ? 128 : 64);
+    int ctas_per_sm = g.T == 1 ? 2 : 1;        // row mode: T*BN accumulator columns may take all of TMEM
+    int force_stages = 0;
+    if (const char *f = getenv("RAMNET_WGRAD_FORCE")) {          // "BN,TR,stages,ctas_per_sm" (tuning / tests)
+        int a = 0, b = 0, c = 0, e = 0;
+        if (sscanf(f, "%d,%d,%d,%d", &a, &b, &c, &e) == 4 && g.T > 1) {
+            if (a >= 32 && a % 32 == 0 && a * g.T <= 512) bn_cap = a;
+            if (b == 4 || b == 8) g.TR = b;
+            force_stages = c;
+            if (e == 1 || e == 2) ctas_per_sm = e;
+        }
+    }
+    g.BN = g.Nch >= bn_cap ? bn_cap : ((g.Nch + 31) / 32) * 32;
+    if (g.T * g.BN > 256) ctas_per_sm = 1;
+    const int x_box = g.HXw * g.TR * kChunk * 4, dz_box = 8 * g.TR * kChunk * 4;
+    g.a_box = g.m_from_x ? x_box : dz_box;
+    g.b_box = g.m_from_x ? dz_box : x_box;
     g.m_blocks = (g.Mch + 127) / 128;
     g.n_blocks = (g.Nch + g.BN - 1) / g.BN;
-    g.tiles_x = (g.Wo + 7) / 8; g.tiles_y = (g.Ho + 7) / 8;
+    g.tiles_x = (g.Wo + 7) / 8; g.tiles_y = (g.Ho + g.TR - 1) / g.TR;
     const int64_t total = (int64_t)g.tiles_x * g.tiles_y * g.N;
     if (total > 0x7fffffff) return false;
     g.total_tiles = (int)total;
-    const int groups = d->ksize * d->ksize * g.m_blocks * g.n_blocks;
-    // ~4 CTAs per SM in total, but at least 16 pixel tiles (8K MMA cycles) per CTA so the partial-tile flush amortises
+    const int groups = (g.T == 1 ? d->ksize * d->ksize : d->ksize) * g.m_blocks * g.n_blocks;
+    // ~4 CTAs per SM in total, but at least 1024 pixels (8K MMA cycles) per CTA so the partial-tile flush amortises
+    const int min_tiles = 1024 / (8 * g.TR);
     int64_t splits = ((int64_t)h->sm_count * 4 + groups - 1) / groups;
-    if (splits > total / 16) splits = total / 16;
+    if (splits > total / min_tiles) splits = total / min_tiles;
     if (splits < 1) splits = 1;
     g.tiles_per_cta = (int)((total + splits - 1) / splits);
     splits = (total + g.tiles_per_cta - 1) / g.tiles_per_cta;
-    const int stage_bytes = (4 + g.BN / kChunk) * kWgBox;
-    g.stages = (96 * 1024) / stage_bytes;      // two CTAs per SM (measured faster than one CTA with a deeper ring)
+    const int stage_bytes = 4 * g.a_box + (g.BN / kChunk) * g.b_box;
+    // per-tap mode: two CTAs per SM (measured faster than one CTA with a deeper ring)
+    g.stages = ((ctas_per_sm == 2 ? 96 : 200) * 1024) / stage_bytes;
+    if (force_stages > 0) g.stages = force_stages;
     if (g.stages < 2) g.stages = 2;
-    if (g.stages > 6) g.stages = 6;
+    if (g.stages > 8) g.stages = 8;
+    if ((size_t)g.stages * stage_bytes > 220 * 1024) return false;
     *splits_out = (int)splits;
     *groups_out = groups;
     return true;
@@ -1133,23 +1170,23 @@ int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz
     int splits_i, groups;
     if (!plan_wgrad(h, d, &g, &splits_i, &groups)) return RAMNET_EUNSUPPORTED;
     const int64_t splits = splits_i;
-    const size_t need = (size_t)splits * groups * 128 * g.BN * sizeof(float);
+    const size_t need = (size_t)splits * groups * 128 * g.T * g.BN * sizeof(float);
     RAMNET_CHECK_ARG(workspace != nullptr && workspace_bytes >= need,
                      "conv_wgrad(tf32): workspace of %zu bytes required (ramnet_conv_wgrad_workspace_bytes)", need);
-    const int stage_bytes = (4 + g.BN / kChunk) * kWgBox;
+    const int stage_bytes = 4 * g.a_box + (g.BN / kChunk) * g.b_box;
 
     CUtensorMap mdz, m0, m1;
     {
         cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)g.Wo, (cuuint64_t)g.Ho, (cuuint64_t)d->N};
         cuuint64_t str[3] = {(cuuint64_t)d->Cout * 4, (cuuint64_t)g.Wo * d->Cout * 4, (cuuint64_t)g.Ho * g.Wo * d->Cout * 4};
-        cuuint32_t box[4] = {kChunk, 8, 8, 1};
+        cuuint32_t box[4] = {kChunk, 8, (cuuint32_t)g.TR, 1};
         int rc = encode(h, &mdz, dz, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc) return rc;
     }
-    int rc = encode_activation(h, &m0, x0, d->N, d->H, d->W, d->C0, d->stride, 8, 8, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    int rc = encode_activation(h, &m0, x0, d->N, d->H, d->W, d->C0, d->stride, g.HXw, g.TR, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
     if (x1) {
-        rc = encode_activation(h, &m1, x1, d->N, d->H, d->W, d->C1, d->stride, 8, 8, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        rc = encode_activation(h, &m1, x1, d->N, d->H, d->W, d->C1, d->stride, g.HXw, g.TR, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc) return rc;
     } else {
         m1 = m0;
@@ -1163,7 +1200,7 @@ int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz
     dim3 grid((unsigned)splits, (unsigned)groups);
     conv_wgrad_tcgen05_kernel<<<grid, kThreads, smem, s>>>(mdz, m0, m1, g, (float *)workspace);
     RAMNET_LAUNCH_CHECK(h);
-    const int64_t elems = (int64_t)groups * 128 * g.BN;
+    const int64_t elems = (int64_t)groups * 128 * g.T * g.BN;
     wgrad_reduce_kernel<<<(unsigned)imin64((elems + 255) / 256, (int64_t)h->sm_count * 8), 256, 0, s>>>(
         (const float *)workspace, dw, g, (int)splits, groups);
     RAMNET_LAUNCH_CHECK(h);
