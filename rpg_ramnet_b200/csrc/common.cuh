@@ -36,6 +36,32 @@ int ramnet_set_error(int code, const char *fmt, ...);
         (h)->launches++;                                                                     \
     } while (0)
 
+// ---- programmatic dependent launch ----------------------------------------------
+// Kernels of one pass run back to back on one stream.  A kernel launched through ramnet_launch(pdl = true) may start
+// while its predecessor is still draining: its CTAs are placed as SMs free up and run their prologue (barrier init,
+// TMEM allocation, tensor-map prefetch) before pdl_wait(), which returns once the predecessor grid has completed and
+// its writes are visible.  Every global read or write of such a kernel sits after pdl_wait().  A kernel that never
+// calls pdl_launch_dependents() triggers implicitly when it exits (no overlap, no hazard).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool ramnet_pdl_enabled();   // api.cu: RAMNET_PDL=1 turns it on (off by default: measured no gain inside CUDA graphs)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t ramnet_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
+                                 Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && ramnet_pdl_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- device math --------------------------------------------------------------
 // Accurate (not --use_fast_math) transcendental forms: parity with torch.sigmoid / tanh
 // to ~1 ulp matters more here than the handful of SFU cycles.

@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(256) head_conv_kernel(const float *__restrict_
     float *in_s = smem;                       // [Cin][IH][IW]
     float *w_s = smem + IH * IW * MAX_CIN;    // [Cin*25][COB]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_wait();
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, n = blockIdx.z;
 
     for (int i = tid; i < Cin * IH * IW; i += 256) {
@@ -107,8 +108,8 @@ extern "C" int ramnet_head_conv(ramnet_handle *h, const float *x_nchw, const flo
     RAMNET_CHECK_ARG(N <= 65535 && (H + TH - 1) / TH <= 65535, "ramnet_head_conv: grid too large");
     dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, N);
     for (int co_base = 0; co_base < Cout; co_base += COB) {
-        head_conv_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, w_oihw, bias, y_nhwc, N, Cin, H, W, Cout,
-                                                                 co_base, (flags & RAMNET_FLAG_ROUND_TF32) != 0);
+        RAMNET_CUDA(ramnet_launch(head_conv_kernel, grid, dim3(256), 0, (cudaStream_t)stream, true, x_nchw, w_oihw, bias,
+                                  y_nhwc, N, Cin, H, W, Cout, co_base, (flags & RAMNET_FLAG_ROUND_TF32) != 0));
         RAMNET_LAUNCH_CHECK(h);
     }
     return RAMNET_OK;

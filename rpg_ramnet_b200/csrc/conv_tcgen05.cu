@@ -121,6 +121,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 }
+__host__ __device__ constexpr uint32_t make_idesc_tf32_m(int n, int m) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
     asm volatile(
@@ -319,7 +322,8 @@ struct HaloGeom {
     int BN, n_slices;        // GEMM columns per item, Cout / BN
     int a_stages, b_stages;
     int nbuf;                // TMEM accumulator buffers
-    int items;               // patches * n_slices
+    int pair;                // 1: CTA-pair mode (cta_group::2, M = 256): a work item is two patches x one BN-wide slice
+    int items;               // patches (pair mode: patch pairs) * n_slices
     unsigned long long *prof; // RAMNET_PROF=1: per-role wait-cycle counters (debug), else nullptr
 };
 
@@ -368,7 +372,94 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t *bar, uint32_t parity, bool
     }
 }
 
-template <int EPI>
+// ---- CTA-pair (cta_group::2) variants: the two CTAs of a cluster run ONE M=256 UMMA per instruction.  Each CTA owns
+// 128 accumulator rows (its own pixel tiles) and stages half of the weight tile; the tensor cores of both SMs read
+// both halves, so the weight bytes each SM pulls out of its shared memory per MMA are halved.  Only the leader
+// (cluster rank 0) issues MMAs; every TMA load of either CTA reports to the LEADER's full barrier, and every
+// tcgen05.commit is multicast to the barrier at the same offset in both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t leader_smem_addr(const void *p) {     // shared::cluster address of p in CTA rank 0
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_u32(p)));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <bool PAIR>
+__device__ __forceinline__ void halo_tma_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    if constexpr (PAIR) {
+        asm volatile(
+            "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+            ::"r"(smem_u32(dst)), "l"(map), "r"(leader_smem_addr(bar)), "r"(c0), "r"(c1), "r"(c2)
+            : "memory");
+    } else {
+        tma_load_3d(dst, map, bar, c0, c1, c2);
+    }
+}
+template <bool PAIR>
+__device__ __forceinline__ void halo_tma_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    if constexpr (PAIR) {
+        asm volatile(
+            "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+            ::"r"(smem_u32(dst)), "l"(map), "r"(leader_smem_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+            : "memory");
+    } else {
+        tma_load_4d(dst, map, bar, c0, c1, c2, c3);
+    }
+}
+template <bool PAIR>
+__device__ __forceinline__ void halo_tma_5d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+    if constexpr (PAIR) {
+        asm volatile(
+            "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+            "[%2];" ::"r"(smem_u32(dst)), "l"(map), "r"(leader_smem_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+            : "memory");
+    } else {
+        tma_load_5d(dst, map, bar, c0, c1, c2, c3, c4);
+    }
+}
+template <bool PAIR>
+__device__ __forceinline__ void halo_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (PAIR) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        umma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
+    }
+}
+template <bool PAIR>
+__device__ __forceinline__ void halo_commit(uint64_t *bar) {
+    if constexpr (PAIR) {
+        asm volatile(
+            "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+            ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+            : "memory");
+    } else {
+        umma_commit(bar);
+    }
+}
+// epilogue -> MMA issuer hand-back of an accumulator buffer: the issuer lives in the leader CTA
+template <bool PAIR>
+__device__ __forceinline__ void halo_arrive_leader(uint64_t *bar) {
+    if constexpr (PAIR) {
+        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_smem_addr(bar)) : "memory");
+    } else {
+        mbar_arrive(bar);
+    }
+}
+
+template <int EPI, bool PAIR>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(const __grid_constant__ CUtensorMap map_x0,
                                                                             const __grid_constant__ CUtensorMap map_x1,
                                                                             const __grid_constant__ CUtensorMap map_w,
@@ -378,7 +469,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
     const int plane_bytes = g.HX * g.HY * kChunk * 4;
     const int a_bytes = g.nplanes * plane_bytes;             // TMA transaction bytes per halo stage
     const int a_stride = g.nplanes * g.plane_stride;
-    const int b_bytes = g.BN * kChunk * 4;
+    const int bn_local = PAIR ? g.BN / 2 : g.BN;             // weight rows staged by this CTA
+    const int b_bytes = bn_local * kChunk * 4;
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // persistent worker = CTA or CTA pair
+    const int nworkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     uint8_t *smem_b = smem + (size_t)g.a_stages * a_stride;
     uint64_t *a_full = reinterpret_cast<uint64_t *>(smem_b + (size_t)g.b_stages * b_bytes);
     uint64_t *a_empty = a_full + g.a_stages;
@@ -390,6 +486,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
     uint32_t *tap_tab = tmem_slot + 2;           // [ks*ks] halo offset of each filter tap, in 16-byte units
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Persistent grid (<= one CTA per SM, all resident): let the next kernel of the stream start its prologue on the
+    // SMs this grid leaves idle / as its CTAs retire.
+    pdl_launch_dependents();
     const int ntiles = g.PTX * g.PTY;
     const int chunks0 = g.C0 / kChunk, chunks = (g.C0 + g.C1) / kChunk;
     const int taps = g.ks * g.ks;
@@ -406,7 +505,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < g.a_stages; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
         for (int s = 0; s < g.b_stages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, kEpiWarps); }
+        for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, kEpiWarps * (PAIR ? 2 : 1)); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 3) {
@@ -424,24 +523,35 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
             }
             tap_tab[lane] = (uint32_t)off;
         }
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(tmem_cols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PAIR) {     // collective over the same warp of both CTAs; both get the same TMEM address
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(tmem_cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(tmem_cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // everything above touched only kernel parameters, shared memory and TMEM
 
     const bool prof = g.prof != nullptr;
     unsigned long long w0 = 0, w1 = 0, w2 = 0;
     const long long t_start = clock64();
 
     // item -> (Cout slice, image, patch origin); consecutive items share the weight slice (L2 reuse)
+    const int patches_w = PAIR ? (patches + 1) >> 1 : patches;   // patches (pair mode: patch pairs) per Cout slice
     auto decode = [&](int item, int &n0, int &img, int &x0, int &y0) {
-        const int slice = item / patches;
-        int t = item - slice * patches;
+        const int slice = item / patches_w;
+        int t = item - slice * patches_w;
+        if constexpr (PAIR) t = 2 * t + (int)cta_rank;           // an odd patch count leaves img == N: all out of bounds
         const int pxi = t % g.patches_x;
         t /= g.patches_x;
         const int pyi = t % g.patches_y;
@@ -455,25 +565,25 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
         // ---------------- halo producer: one box per (item, 32-channel chunk) ----------------
         int stage = 0;
         uint32_t phase = 0;
-        for (int item = blockIdx.x; item < g.items; item += gridDim.x) {
+        for (int item = worker; item < g.items; item += nworkers) {
             int n0, img, x0, y0;
             decode(item, n0, img, x0, y0);
             for (int ch = 0; ch < chunks; ++ch) {
                 mbar_wait_t(a_empty + stage, phase ^ 1, prof, w0);
                 if (elect_one()) {
-                    mbar_expect_tx(a_full + stage, (uint32_t)a_bytes);
+                    if (leader) mbar_expect_tx(a_full + stage, (uint32_t)a_bytes * (PAIR ? 2u : 1u));
                     const bool second = ch >= chunks0;
                     const CUtensorMap *mx = second ? &map_x1 : &map_x0;
                     const int c = (second ? ch - chunks0 : ch) * kChunk;
                     uint8_t *dst = smem + (size_t)stage * a_stride;
                     if (g.stride == 1) {
-                        tma_load_4d(dst, mx, a_full + stage, c, x0 + g.lo, y0 + g.lo, img);
+                        halo_tma_4d<PAIR>(dst, mx, a_full + stage, c, x0 + g.lo, y0 + g.lo, img);
                     } else {
                         const int Csrc = second ? g.C1 : g.C0;
 #pragma unroll
                         for (int pl = 0; pl < 4; ++pl)   // (py, px) parity planes of the 5-D view (2C, W/2, 2, H/2, N)
-                            tma_load_5d(dst + (size_t)pl * g.plane_stride, mx, a_full + stage, (pl & 1) * Csrc + c,
-                                        x0 + g.lo, pl >> 1, y0 + g.lo, img);
+                            halo_tma_5d<PAIR>(dst + (size_t)pl * g.plane_stride, mx, a_full + stage, (pl & 1) * Csrc + c,
+                                              x0 + g.lo, pl >> 1, y0 + g.lo, img);
                     }
                 }
                 __syncwarp();
@@ -485,14 +595,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
         // ---------------- weight producer: one [BN x 32] tile per (item, chunk, tap) ----------------
         int stage = 0;
         uint32_t phase = 0;
-        for (int item = blockIdx.x; item < g.items; item += gridDim.x) {
-            const int n0 = (item / patches) * g.BN;
+        for (int item = worker; item < g.items; item += nworkers) {
+            const int n0 = (item / patches_w) * g.BN + (int)cta_rank * bn_local;   // pair mode: this CTA's half of the slice
             for (int ch = 0; ch < chunks; ++ch) {
                 for (int tap = 0; tap < taps; ++tap) {
                     mbar_wait_t(b_empty + stage, phase ^ 1, prof, w0);
                     if (elect_one()) {
-                        mbar_expect_tx(b_full + stage, (uint32_t)b_bytes);
-                        tma_load_3d(smem_b + (size_t)stage * b_bytes, &map_w, b_full + stage, ch * kChunk, n0, tap);
+                        if (leader) mbar_expect_tx(b_full + stage, (uint32_t)b_bytes * (PAIR ? 2u : 1u));
+                        halo_tma_3d<PAIR>(smem_b + (size_t)stage * b_bytes, &map_w, b_full + stage, ch * kChunk, n0, tap);
                     }
                     __syncwarp();
                     if (++stage == g.b_stages) { stage = 0; phase ^= 1; }
@@ -501,8 +611,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
         }
         if (prof && lane == 0) atomicAdd(g.prof + 5, w0);
     } else if (warp == 1) {
+      if (leader) {
         // ---------------- MMA issuer: warp-uniform loops, no divisions, one elected lane issues ----------------
-        const uint32_t idesc = make_idesc_tf32(g.BN);
+        const uint32_t idesc = make_idesc_tf32_m(g.BN, PAIR ? 256 : 128);
         // descriptor bits above the 14-bit start-address field: LBO=16 B, SBO = one halo row, version 1, SWIZZLE_128B
         const uint64_t a_hi = ((uint64_t)1 << 16) | ((uint64_t)((uint32_t)g.HX * 128u >> 4) << 32) | ((uint64_t)1 << 46) |
                               ((uint64_t)2 << 61);
@@ -516,7 +627,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
         uint32_t pa = 0, pb = 0;
         int li = 0;   // local item counter
         int ready = 0;   // weight stages known to be full, starting at sb
-        for (int item = blockIdx.x; item < g.items; item += gridDim.x, ++li) {
+        for (int item = worker; item < g.items; item += nworkers, ++li) {
             const int buf = (g.nbuf == 2) ? (li & 1) : 0;
             const uint32_t use = (uint32_t)((g.nbuf == 2) ? (li >> 1) : li);
             mbar_wait_t(acc_empty + buf, (use & 1) ^ 1, prof, w2);          // epilogue has drained this buffer
@@ -554,19 +665,19 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
                                     const uint64_t adesc = a_hi | (uint64_t)(tap16 + tile_off16[tl]);
 #pragma unroll
                                     for (int kk = 0; kk < kChunk / 8; ++kk)
-                                        umma_tf32(acc_base + (uint32_t)(tl * g.BN), adesc + 2 * kk, bdesc + 2 * kk,
-                                                  idesc, (first | (uint32_t)kk) != 0);
+                                        halo_umma<PAIR>(acc_base + (uint32_t)(tl * g.BN), adesc + 2 * kk, bdesc + 2 * kk,
+                                                        idesc, (first | (uint32_t)kk) != 0);
                                 }
                             }
-                            umma_commit(b_empty + sb);
+                            halo_commit<PAIR>(b_empty + sb);
                         }
                         __syncwarp();
                         if (++sb == g.b_stages) { sb = 0; pb ^= 1; }
                     }
                 }
                 if (elect_one()) {
-                    umma_commit(a_empty + sa);
-                    if (ch == chunks - 1) umma_commit(acc_full + buf);
+                    halo_commit<PAIR>(a_empty + sa);
+                    if (ch == chunks - 1) halo_commit<PAIR>(acc_full + buf);
                 }
                 __syncwarp();
                 if (++sa == g.a_stages) { sa = 0; pa ^= 1; }
@@ -578,6 +689,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
             atomicAdd(g.prof + 2, w1);
             atomicAdd(g.prof + 3, w2);
         }
+      }
     } else if (warp >= 4) {
         // ---------------- epilogue: software-pipelined TMEM -> registers -> fused math -> global ----------------
         constexpr int kParts = kEpiWarps / 4;     // warps per lane quarter; part p takes chunks c = 16*(p + kParts*j)
@@ -586,7 +698,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
         const int nch = (g.BN / 16 - half + kParts - 1) / kParts;
         const int units = ntiles * nch;
         int li = 0;
-        for (int item = blockIdx.x; item < g.items; item += gridDim.x, ++li) {
+        for (int item = worker; item < g.items; item += nworkers, ++li) {
             int n0, img, x0, y0;
             decode(item, n0, img, x0, y0);
             const int buf = (g.nbuf == 2) ? (li & 1) : 0;
@@ -601,7 +713,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
                 Unit u;
                 u.tl = tl; u.j = j;
                 const int ox = x0 + (tl & (g.PTX - 1)) * 8 + (row & 7), oy = y0 + (tl >> g.ptx_log2) * 16 + (row >> 3);
-                u.valid = oy < g.Ho && ox < g.Wo;
+                u.valid = oy < g.Ho && ox < g.Wo && img < g.N;
                 u.m = ((int64_t)img * g.Ho + oy) * g.Wo + ox;
                 u.col = (half + kParts * j) * 16;
                 return u;
@@ -630,7 +742,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
                                 dot = fmaf(fmaxf(__uint_as_float(r[4 * q + 3]) + bb.w, 0.f), ww.w, dot);
                             }
                         }
-                        if (oy < g.Ho && ox < g.Wo) {
+                        if (oy < g.Ho && ox < g.Wo && img < g.N) {
                             const int64_t m = ((int64_t)img * g.Ho + oy) * g.Wo + ox;
                             const float logit = dot + __ldg(ep.aux1);
                             if (ep.y1) ep.y1[m] = logit;
@@ -678,7 +790,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
             // all tcgen05.ld of this warp have completed (waited above): hand the buffer back to the MMA warp
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (elect_one()) mbar_arrive(acc_empty + buf);
+            if (elect_one()) halo_arrive_leader<PAIR>(acc_empty + buf);
             __syncwarp();
         }
         if (prof && lane == 0) {
@@ -688,9 +800,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();   // neither CTA retires while the other may still read its smem / signal its barriers
     if (warp == 3) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+        if constexpr (PAIR)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
     }
 }
 
@@ -940,15 +1056,62 @@ int launch(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap &m1, const
     return RAMNET_OK;
 }
 
+template <int EPI, bool PAIR>
+int launch_halo_pair(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap &m1, const CUtensorMap &mw,
+                     const HaloGeom &g, const EpiParams &ep, size_t smem, cudaStream_t s) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        RAMNET_CUDA(cudaFuncSetAttribute(conv_tcgen05_halo_kernel<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+        configured = smem;
+    }
+    const int pairs = g.items < h->sm_count / 2 ? g.items : h->sm_count / 2;   // persistent: one CTA pair per TPC
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kHaloThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static const bool do_prof = getenv("RAMNET_PROF") != nullptr;      // debug only: synchronises and prints
+    if (do_prof) {
+        static unsigned long long *buf = nullptr;
+        if (!buf) cudaMalloc(&buf, 64);
+        cudaMemsetAsync(buf, 0, 64, s);
+        HaloGeom gp = g;
+        gp.prof = buf;
+        RAMNET_CUDA(cudaLaunchKernelEx(&cfg, conv_tcgen05_halo_kernel<EPI, true>, m0, m1, mw, gp, ep));
+        unsigned long long hbuf[8];
+        cudaMemcpyAsync(hbuf, buf, 64, cudaMemcpyDeviceToHost, s);
+        cudaStreamSynchronize(s);
+        const double n = pairs;     // MMA counters: one issuer per pair; producer / epilogue counters: two CTAs per pair
+        fprintf(stderr, "[ramnet-prof] pairs=%d items=%d per-pair kcycles: mma_total=%.1f wait_a_full=%.1f wait_b_full=%.1f "
+                        "wait_acc_empty=%.1f | prodA_wait_empty=%.1f prodB_wait_empty=%.1f | epi(avg of warps) "
+                        "wait_acc_full=%.1f total=%.1f\n",
+                pairs, g.items, hbuf[0] / n / 1e3, hbuf[1] / n / 1e3, hbuf[2] / n / 1e3, hbuf[3] / n / 1e3, hbuf[4] / n / 2e3,
+                hbuf[5] / n / 2e3, hbuf[6] / n / 16e3, hbuf[7] / n / 16e3);
+    } else {
+        RAMNET_CUDA(cudaLaunchKernelEx(&cfg, conv_tcgen05_halo_kernel<EPI, true>, m0, m1, mw, g, ep));
+    }
+    RAMNET_LAUNCH_CHECK(h);
+    return RAMNET_OK;
+}
+
 template <int EPI>
 int launch_halo(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap &m1, const CUtensorMap &mw,
                 const HaloGeom &g, const EpiParams &ep, cudaStream_t s) {
     const size_t a_stride = (size_t)g.nplanes * g.plane_stride;
-    const size_t smem = g.a_stages * a_stride + (size_t)g.b_stages * g.BN * kChunk * 4 +
+    const size_t smem = g.a_stages * a_stride + (size_t)g.b_stages * (g.pair ? g.BN / 2 : g.BN) * kChunk * 4 +
                         (2 * g.a_stages + 2 * g.b_stages + 4) * 8 + 16 + 32 * 4 + 1024;
+    if (g.pair) return launch_halo_pair<EPI, true>(h, m0, m1, mw, g, ep, smem, s);
     static size_t configured = 0;
     if (smem > configured) {
-        RAMNET_CUDA(cudaFuncSetAttribute(conv_tcgen05_halo_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        RAMNET_CUDA(cudaFuncSetAttribute(conv_tcgen05_halo_kernel<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
         configured = smem;
     }
@@ -960,7 +1123,7 @@ int launch_halo(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap &m1, 
         cudaMemsetAsync(buf, 0, 64, s);
         HaloGeom gp = g;
         gp.prof = buf;
-        conv_tcgen05_halo_kernel<EPI><<<grid, kHaloThreads, smem, s>>>(m0, m1, mw, gp, ep);
+        conv_tcgen05_halo_kernel<EPI, false><<<grid, kHaloThreads, smem, s>>>(m0, m1, mw, gp, ep);
         unsigned long long hbuf[8];
         cudaMemcpyAsync(hbuf, buf, 64, cudaMemcpyDeviceToHost, s);
         cudaStreamSynchronize(s);
@@ -971,7 +1134,7 @@ int launch_halo(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap &m1, 
                 grid, g.items, hbuf[0] / n / 1e3, hbuf[1] / n / 1e3, hbuf[2] / n / 1e3, hbuf[3] / n / 1e3, hbuf[4] / n / 1e3,
                 hbuf[5] / n / 1e3, hbuf[6] / n / 8e3, hbuf[7] / n / 8e3);
     } else {
-        conv_tcgen05_halo_kernel<EPI><<<grid, kHaloThreads, smem, s>>>(m0, m1, mw, g, ep);
+        RAMNET_CUDA(ramnet_launch(conv_tcgen05_halo_kernel<EPI, false>, dim3(grid), dim3(kHaloThreads), smem, s, true, m0, m1, mw, g, ep));
     }
     RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;
@@ -986,8 +1149,10 @@ int halo_mode_env() {
     return mode;
 }
 
-bool fill_halo(const ramnet_conv_desc *d, HaloGeom *g, int ptx, int pty, int bn, int a_st, int b_st) {
+bool fill_halo(const ramnet_conv_desc *d, HaloGeom *g, int ptx, int pty, int bn, int a_st, int b_st, int pair = 0) {
     if (d->Cout % bn || ptx * pty > 4 || ptx * pty * bn > 512 || (ptx & (ptx - 1))) return false;
+    if (pair && (bn % 16 || bn < 32)) return false;          // cta_group::2: N in steps of 16; each CTA stages bn/2 rows
+    g->pair = pair;
     g->N = d->N; g->H = d->H; g->W = d->W; g->Cout = d->Cout; g->C0 = d->C0; g->C1 = d->C1;
     g->Ho = conv_out_dim(d->H, d->stride); g->Wo = conv_out_dim(d->W, d->stride);
     g->ks = d->ksize; g->pad = d->ksize / 2; g->stride = d->stride; g->prof = nullptr;
@@ -1001,13 +1166,14 @@ bool fill_halo(const ramnet_conv_desc *d, HaloGeom *g, int ptx, int pty, int bn,
     if (g->HX > 256 || g->HY > 256) return false;
     g->BN = bn; g->n_slices = d->Cout / bn;
     g->patches_x = (g->Wo + ptx * 8 - 1) / (ptx * 8); g->patches_y = (g->Ho + pty * 16 - 1) / (pty * 16);
-    const int64_t items = (int64_t)g->patches_x * g->patches_y * d->N * g->n_slices;
+    const int64_t npatch = (int64_t)g->patches_x * g->patches_y * d->N;
+    const int64_t items = (pair ? (npatch + 1) / 2 : npatch) * g->n_slices;
     if (items > 0x7fffffff) return false;
     g->items = (int)items;
     g->nbuf = (2 * ptx * pty * bn <= 512) ? 2 : 1;
     g->plane_stride = (int)(((size_t)g->HX * g->HY * kChunk * 4 + 1023) & ~(size_t)1023);
     const size_t a_stride = (size_t)g->nplanes * g->plane_stride;
-    const size_t b_bytes = (size_t)bn * kChunk * 4;
+    const size_t b_bytes = (size_t)(pair ? bn / 2 : bn) * kChunk * 4;
     const size_t budget = 222 * 1024;
     if (a_st <= 0) {   // automatic pipeline depths
         a_st = 2;
@@ -1032,15 +1198,17 @@ bool fill_halo(const ramnet_conv_desc *d, HaloGeom *g, int ptx, int pty, int bn,
 double halo_cost(const ramnet_handle *h, const ramnet_conv_desc *d, const HaloGeom &g) {
     const int ntiles = g.PTX * g.PTY, chunks = (d->C0 + d->C1) / kChunk, taps = d->ksize * d->ksize;
     const double halo_bytes = (double)g.nplanes * g.HX * g.HY * 128.0;
-    const double smem_tap = (ntiles * 4.0 * (128 + g.BN) * 32.0 + g.BN * 128.0 + halo_bytes / taps) / 128.0;
+    const double bn_l = g.pair ? g.BN / 2.0 : (double)g.BN;     // weight rows read from / written to THIS SM's shared memory
+    const double smem_tap = (ntiles * 4.0 * (128 + bn_l) * 32.0 + bn_l * 128.0 + halo_bytes / taps) / 128.0;
     const double math_tap = ntiles * 4.0 * g.BN / 2.0;
     const double tap = (smem_tap > math_tap ? smem_tap : math_tap) + 20.0;
     const double mma = (double)chunks * taps * tap;
-    const double l2 = (double)chunks * (halo_bytes + (double)taps * g.BN * 128.0) / 50.0;
+    const double l2 = (double)chunks * (halo_bytes + (double)taps * bn_l * 128.0) / 50.0;
     const double main = mma > l2 ? mma : l2;
     const double epi = (double)ntiles * (g.BN / 32.0 + 0.5) * 900.0 + 500.0;
     const double per_item = g.nbuf == 2 ? (main > epi ? main : epi) + 300.0 : main + epi;
-    const int64_t rounds = (g.items + h->sm_count - 1) / h->sm_count;
+    const int workers = g.pair ? h->sm_count / 2 : h->sm_count;
+    const int64_t rounds = (g.items + workers - 1) / workers;
     return (double)rounds * per_item + (g.nbuf == 2 ? epi : 0.0) + 4000.0;
 }
 
@@ -1050,21 +1218,33 @@ bool plan_halo(const ramnet_handle *h, const ramnet_conv_desc *d, HaloGeom *g) {
     if (halo_mode_env() & 4) return false;           // RAMNET_HALO_MODE=4: force the per-tap kernel (A/B tests)
     if (d->ksize == 1) return false;
     if (d->stride == 2 && ((d->H | d->W) & 1)) return false;
-    if (const char *f = getenv("RAMNET_HALO_FORCE")) {   // tuning aid: "PTX,PTY,BN,a_stages,b_stages"
-        int ptx, pty, bn, ast, bst;
-        if (sscanf(f, "%d,%d,%d,%d,%d", &ptx, &pty, &bn, &ast, &bst) == 5 && fill_halo(d, g, ptx, pty, bn, ast, bst))
+    if (const char *f = getenv("RAMNET_HALO_FORCE")) {   // tuning aid: "PTX,PTY,BN,a_stages,b_stages[,pair]"
+        int ptx, pty, bn, ast, bst, pr = 0;
+        if (sscanf(f, "%d,%d,%d,%d,%d,%d", &ptx, &pty, &bn, &ast, &bst, &pr) >= 5 && fill_halo(d, g, ptx, pty, bn, ast, bst, pr))
             return true;
     }
+    // RAMNET_PAIR: 0 = single-CTA MMAs only, 1 (default) = cost model decides, 2 = CTA pairs wherever a configuration fits
+    static const int pair_mode = [] { const char *e = getenv("RAMNET_PAIR"); return e ? atoi(e) : 1; }();
     static const int shapes[][2] = {{2, 1}, {1, 1}, {4, 1}, {2, 2}, {1, 2}};
     double best = -1;
     HaloGeom cand;
-    for (const auto &sh : shapes)
-        for (int bn = 256; bn >= 16; bn >>= 1) {
-            if (d->epilogue == RAMNET_EPI_BIAS_RELU_PRED && bn != d->Cout) continue;   // one slice: whole-row reduction
-            if (!fill_halo(d, &cand, sh[0], sh[1], bn, 0, 0)) continue;
-            const double c = halo_cost(h, d, cand);
-            if (best < 0 || c < best) { best = c; *g = cand; }
-        }
+    for (int pair = (pair_mode == 2 ? 1 : 0); pair <= (pair_mode >= 1 ? 1 : 0); ++pair)
+        for (const auto &sh : shapes)
+            for (int bn = 256; bn >= 16; bn >>= 1) {
+                if (d->epilogue == RAMNET_EPI_BIAS_RELU_PRED && bn != d->Cout) continue;   // one slice: whole-row reduction
+                if (!fill_halo(d, &cand, sh[0], sh[1], bn, 0, 0, pair)) continue;
+                const double c = halo_cost(h, d, cand);
+                if (best < 0 || c < best) { best = c; *g = cand; }
+            }
+    if (best < 0 && pair_mode == 2) {     // nothing fits as a pair: single-CTA configurations
+        for (const auto &sh : shapes)
+            for (int bn = 256; bn >= 16; bn >>= 1) {
+                if (d->epilogue == RAMNET_EPI_BIAS_RELU_PRED && bn != d->Cout) continue;
+                if (!fill_halo(d, &cand, sh[0], sh[1], bn, 0, 0, 0)) continue;
+                const double c = halo_cost(h, d, cand);
+                if (best < 0 || c < best) { best = c; *g = cand; }
+            }
+    }
     return best >= 0;
 }
 }  // namespace
@@ -1222,9 +1402,9 @@ int conv_fwd_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *x0, 
         return ramnet_set_error(RAMNET_EUNSUPPORTED, "conv_fwd: no halo-kernel configuration for the fused prediction epilogue");
     if (halo_ok) {
         if (getenv("RAMNET_DEBUG"))
-            fprintf(stderr, "[ramnet] halo plan s%d %dx%d C=%d+%d->%d k%d: tiles %dx%d HX=%d HY=%d BN=%d a_st=%d b_st=%d nbuf=%d items=%d\n",
+            fprintf(stderr, "[ramnet] halo plan s%d %dx%d C=%d+%d->%d k%d: tiles %dx%d HX=%d HY=%d BN=%d a_st=%d b_st=%d nbuf=%d items=%d pair=%d\n",
                     d->stride, d->H, d->W, d->C0, d->C1, d->Cout, d->ksize, hg.PTX, hg.PTY, hg.HX, hg.HY, hg.BN, hg.a_stages,
-                    hg.b_stages, hg.nbuf, hg.items);
+                    hg.b_stages, hg.nbuf, hg.items, hg.pair);
         CUtensorMap m0, m1, mw;
         auto enc_act = [&](CUtensorMap *m, const float *x, int C) {
             if (d->stride == 1) {
@@ -1251,7 +1431,7 @@ int conv_fwd_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *x0, 
         const int Ct = d->C0 + d->C1, taps = d->ksize * d->ksize;
         cuuint64_t wd[3] = {(cuuint64_t)Ct, (cuuint64_t)d->Cout, (cuuint64_t)taps};
         cuuint64_t ws[2] = {(cuuint64_t)Ct * 4, (cuuint64_t)Ct * d->Cout * 4};
-        cuuint32_t wb[3] = {kChunk, (cuuint32_t)hg.BN, 1};
+        cuuint32_t wb[3] = {kChunk, (cuuint32_t)(hg.pair ? hg.BN / 2 : hg.BN), 1};
         rc = encode(h, &mw, wp, 3, wd, ws, wb);
         if (rc) return rc;
         switch (d->epilogue) {

@@ -313,6 +313,10 @@ class GraphRunner:
         self.x_in, self.graphs = {}, {}
         self.param_sig = None
         self.pool = None
+        # host inputs: staged H2D on a copy stream into a 2-slot ring per pass type, so the copy of the next pass
+        # runs under the kernels of the current one (the reference copies on the compute stream, model.py:177,200)
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.slot_ctr = {}
 
     def _alloc_states(self):
         out = []
@@ -364,20 +368,56 @@ class GraphRunner:
                 for t, f in zip(mine, self._flat(prev_super)):
                     t.copy_(f)
         dst = 1 - src
-        xin = self.x_in.get(which)
-        if xin is None or xin.shape != x.shape:
-            xin = torch.empty(tuple(x.shape), dtype=torch.float32, device=self.device)
-            self.x_in[which] = xin
-            self.graphs = {k: v for k, v in self.graphs.items() if k[0] != which}
-        xin.copy_(x, non_blocking=True)
-        key = (which, src)
+        slot = self.stage(which, x)
+        if slot is None:                    # ring full of inputs staged ahead but never consumed: drop them
+            for sl in self.x_in[which]:
+                sl['staged_for'] = None
+            slot = self.stage(which, x)
+        cur = torch.cuda.current_stream(self.device)
+        if slot['ready'] is not None:
+            cur.wait_event(slot['ready'])
+            slot['ready'] = None
+        key = (which, src, slot['idx'])
         entry = self.graphs.get(key)
         if entry is None:
-            entry = self._capture(which, xin, src, dst)
+            entry = self._capture(which, slot['buf'], src, dst)
             self.graphs[key] = entry
         graph, pred = entry
         graph.replay()
+        slot['done'].record(cur)            # the staging slot may be overwritten once this pass has read it
+        slot['staged_for'] = None
         return self.sets[dst], pred.clone()
+
+    def stage(self, which, x):
+        """Brings the input of the next `which` pass into a staging slot and returns the slot.  Host tensors go
+        over the copy stream (asynchronously when pinned); device tensors are copied on the compute stream.
+        Idempotent per tensor: forward() stages the inputs of later passes ahead of time."""
+        ring = self.x_in.get(which)
+        if ring is None or ring[0]['buf'].shape != x.shape:
+            ring = [{'buf': torch.empty(tuple(x.shape), dtype=torch.float32, device=self.device), 'idx': i,
+                     'ready': None, 'done': torch.cuda.Event(), 'staged_for': None} for i in range(2)]
+            self.x_in[which] = ring
+            self.slot_ctr[which] = 0
+            self.graphs = {k: v for k, v in self.graphs.items() if k[0] != which}
+        for slot in ring:
+            if slot['staged_for'] is x:
+                return slot
+        slot = ring[self.slot_ctr[which] & 1]
+        if slot['staged_for'] is not None:      # both slots hold inputs that have not been consumed yet
+            return None
+        self.slot_ctr[which] += 1
+        slot['staged_for'] = x
+        if x.is_cuda:
+            slot['buf'].copy_(x, non_blocking=True)
+            slot['ready'] = None
+        else:
+            cs = self.copy_stream
+            cs.wait_event(slot['done'])         # last reader of this slot (no-op before its first use)
+            with torch.cuda.stream(cs):
+                slot['buf'].copy_(x, non_blocking=True)
+                slot['ready'] = torch.cuda.Event()
+                slot['ready'].record(cs)
+        return slot
 
     def _capture(self, which, xin, src, dst):
         net = self.net

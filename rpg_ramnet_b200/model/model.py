@@ -74,19 +74,31 @@ class ERGB2DepthRecurrent(BaseERGB2Depth):
     def _run_pass(self, which, x, prev_super_states, last):
         """forward_events / forward_images + forward_decoder, eagerly or as one CUDA-graph replay."""
         net = self.statenetphasedrecurrent
-        if self.cuda_graphs and net.graph_capable() and not self.training:
-            B, _, H, W = x.shape
-            key = (B, H, W)
-            runner = self._runners.get(key)
-            if runner is None:
-                from ..engine import GraphRunner
-                runner = self._runners[key] = GraphRunner(net, B, H, W, self.gpu)
-            s, pred = runner.run(which, x, prev_super_states)
+        if self._graphs_active():
+            s, pred = self._runner(x).run(which, x, prev_super_states)
             return s, {'encoders': [None] * net.num_encoders, 'state_comb': list(s)}, pred
         x = x.to(self.gpu, non_blocking=True)
         if prev_super_states is None:
             prev_super_states = self._zero_states(x.shape[0], x.shape[2], x.shape[3])
         return net._pass(which, x, prev_super_states, last)
+
+    def _graphs_active(self):
+        return self.cuda_graphs and self.statenetphasedrecurrent.graph_capable() and not self.training
+
+    def _runner(self, x):
+        B, _, H, W = x.shape
+        key = (B, H, W)
+        runner = self._runners.get(key)
+        if runner is None:
+            from ..engine import GraphRunner
+            runner = self._runners[key] = GraphRunner(self.statenetphasedrecurrent, B, H, W, self.gpu)
+        return runner
+
+    def _stage_ahead(self, plan):
+        """CUDA-graph mode: start the host-to-device copies of the passes still to run (engine.GraphRunner.stage)."""
+        if self._graphs_active():
+            for which, x in plan:
+                self._runner(x).stage(which, x)
 
     def _zero_states(self, B, H, W):
         """model.py:146-159, allocated on the device directly (the reference builds them on the host
@@ -105,7 +117,7 @@ class ERGB2DepthRecurrent(BaseERGB2Depth):
     def forward(self, item, prev_super_states, prev_states_lstm):
         net = self.statenetphasedrecurrent
         predictions, super_states, states_lstm = {}, {}, {}
-        if prev_super_states is None and not (self.cuda_graphs and net.graph_capable() and not self.training):
+        if prev_super_states is None and not self._graphs_active():
             B, _, H, W = item['image'].shape
             prev_super_states = self._zero_states(B, H, W)
         bl, K = self.baseline, self.every_x_rgb_frame
@@ -116,9 +128,11 @@ class ERGB2DepthRecurrent(BaseERGB2Depth):
                 n_event_passes, last = K - 1, prev_states_lstm['image']
             else:                                  # model.py:170-172
                 n_event_passes, last = K, prev_states_lstm['events{}'.format(K - 1)]
+            which = 'images' if (bl == 'ergb0' or bl == 'e') else 'events'   # baselines have no event encoder
+            plan = [(which, item['events{}'.format(k)]) for k in range(n_event_passes)] + [('images', item['image'])]
             for k in range(n_event_passes):
                 key = 'events{}'.format(k)
-                which = 'images' if (bl == 'ergb0' or bl == 'e') else 'events'   # baselines have no event encoder
+                self._stage_ahead(plan[k:])
                 s, l, predictions[key] = self._run_pass(which, item[key], prev_super_states, last)
                 super_states[key], states_lstm[key] = s, l
                 prev_super_states, last = s, l
