@@ -324,7 +324,7 @@ def main_train(args):
                              'achieved': conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0, 'peak': peak_tf,
                              'unit': 'TFLOP/s', 'frac': (conv_fl / (conv_ms * 1e-3) / 1e12 / peak_tf) if conv_ms else 0.0,
                              'traffic': None, 'peak_source': peak_src, 'ms_per_step_in_kernel': conv_ms},
-                'wgrad': {'kernel': 'conv_wgrad_tcgen05_kernel (MN-major tf32 UMMA, one filter row per CTA over a halo box, partial-tile reduce)',
+                'wgrad': {'kernel': 'conv_wgrad_packed_kernel (MN-major tf32 UMMA, filter taps packed into the MMA N dimension, deterministic two-pass reduce) + conv_wgrad_tcgen05_kernel for stride 2',
                           'achieved_tflops': wg_fl / (wg_ms * 1e-3) / 1e12 if wg_ms else 0.0, 'ms_per_step_in_kernel': wg_ms},
                 'other_kernels_ms_per_step': {k: v[0] for k, v in by.items() if k not in ('conv', 'wgrad')}}
         print(json.dumps(line))

@@ -999,6 +999,196 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_tcgen05_kernel(const __gr
     }
 }
 
+// ================================================================================================
+// Tap-packed weight gradient (stride-1 convolutions).
+//
+// The kernel above spends one MMA per filter tap.  Here the operand that is shifted by the tap (the "N" operand: one
+// 32-channel box of X or of dZ carrying a 2-D halo) feeds ALL ks taps of a filter row to one MMA: N-block j of an
+// MN-major operand starts LBO bytes after block j-1, so LBO = 128 B (one pixel) makes block j the same box shifted by
+// j pixels -> N = ks*32 columns = (tap s, channel c).  The filter row is a descriptor start shifted by whole halo
+// rows and owns its own ks*32 accumulator columns.  One CTA = (128 channels of the M operand, one 32-channel box of
+// the N operand, a group of <= 3 filter rows, a pixel range): every loaded byte is used for ks * rows taps, the
+// MMAs are N = 96 / 160 wide (math-bound instead of shared-memory-bound) and the operand traffic per FLOP drops
+// ~3x against the filter-row kernel.
+//   m_from_x = 0:  M = dZ tile (no halo),  N = X box at (x0 - pad, y0 - pad + u0);   tap (r, s) = (u, j)
+//   m_from_x = 1:  M = X tile (no halo),   N = dZ box at (x0 + pad - (ks-1), y0 + pad - (ks-1) + u0); tap = (ks-1-u, ks-1-j)
+// (u = halo row shift, j = N block).  Out-of-bounds pixels of either box are zero-filled by TMA = zero padding.
+// ================================================================================================
+struct WpGeom {
+    int N, H, W;             // pixel grid (stride 1: same for X and dZ)
+    int Cout, C0, C1;
+    int ks, pad;
+    int m_from_x;
+    int Mch, Nch;            // channels of the M / N operand
+    int m_blocks, n_boxes;   // ceil(Mch / 128), Nch / 32
+    int RG, row_groups;      // halo row shifts per CTA, ceil(ks / RG)
+    int TR;                  // image rows per K tile (tile = 8 px x TR rows)
+    int HXw, HYw;            // N-operand box: (8 + ks - 1) px x (TR + RG - 1) rows
+    int tiles_x, tiles_y, tiles_per_cta, total_tiles;
+    int stages, stage_bytes;
+    int ncols;               // accumulator columns per CTA = RG * ks * 32 (workspace row pitch)
+    unsigned long long *prof; // RAMNET_PROF=1: cycle counters (debug), else nullptr
+};
+
+__global__ void __launch_bounds__(kThreads) conv_wgrad_packed_kernel(const __grid_constant__ CUtensorMap map_dz,
+                                                                     const __grid_constant__ CUtensorMap map_x0,
+                                                                     const __grid_constant__ CUtensorMap map_x1,
+                                                                     WpGeom g, float *__restrict__ part) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int m_box = g.TR * 8 * kChunk * 4;              // one 32-channel box of the M operand (TR KB)
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)g.stages * g.stage_bytes);
+    uint64_t *empty_bar = full_bar + g.stages;
+    uint64_t *accum_bar = empty_bar + g.stages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // blockIdx.y -> (row group, m block, n box)
+    int t = blockIdx.y;
+    const int nb = t % g.n_boxes;
+    t /= g.n_boxes;
+    const int mb = t % g.m_blocks;
+    const int rg = t / g.m_blocks;
+    const int u0 = rg * g.RG;
+    const int rows = min(g.RG, g.ks - u0);                 // halo row shifts handled here
+    const int tile_begin = blockIdx.x * g.tiles_per_cta;
+    const int tile_end = min(tile_begin + g.tiles_per_cta, g.total_tiles);
+    const int ntile = tile_end - tile_begin;
+    const int ncb = g.ks * kChunk;                         // accumulator columns per row shift = UMMA N
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < g.ncols) tmem_cols <<= 1;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_dz);
+        prefetch_tmap(&map_x0);
+        prefetch_tmap(&map_x1);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < g.stages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const bool prof = g.prof != nullptr;
+    unsigned long long wcyc = 0;
+    const long long t_start = clock64();
+
+    if (warp == 0) {
+        // ---------------- TMA producer: 4 M boxes + 1 haloed N box per K tile ----------------
+        int stage = 0;
+        uint32_t phase = 0;
+        const int nbytes = g.HXw * g.HYw * kChunk * 4;     // the box always carries RG - 1 halo rows
+        // origin of the N box relative to the tile origin
+        const int nx = g.m_from_x ? g.pad - (g.ks - 1) : -g.pad;
+        const int ny = nx + u0;
+        for (int it = 0; it < ntile; ++it) {
+            int tt = tile_begin + it;
+            const int txi = tt % g.tiles_x;
+            tt /= g.tiles_x;
+            const int tyi = tt % g.tiles_y;
+            const int img = tt / g.tiles_y;
+            const int x0 = txi * 8, y0 = tyi * g.TR;
+            mbar_wait_t(empty_bar + stage, phase ^ 1, prof, wcyc);
+            if (elect_one()) {
+                uint8_t *sa = smem + (size_t)stage * g.stage_bytes;
+                uint8_t *sb = sa + 4 * m_box;
+                mbar_expect_tx(full_bar + stage, (uint32_t)(4 * m_box + nbytes));
+                auto load_x = [&](uint8_t *dst, int ch, int x, int y) {   // ch indexes the virtual concat [x0 | x1]; past its end: zeros
+                    const bool second = ch >= g.C0 && g.C1 > 0;
+                    const CUtensorMap *mx = second ? &map_x1 : &map_x0;
+                    const int Csrc = second ? g.C1 : g.C0;
+                    const int c = ch >= g.C0 + g.C1 ? Csrc : (second ? ch - g.C0 : ch);
+                    tma_load_4d(dst, mx, full_bar + stage, c, x, y, img);
+                };
+                for (int q = 0; q < 4; ++q) {
+                    const int ch = (mb * 4 + q) * kChunk;
+                    if (g.m_from_x) load_x(sa + q * m_box, ch, x0, y0);
+                    else tma_load_4d(sa + q * m_box, &map_dz, full_bar + stage, ch, x0, y0, img);   // ch >= Cout: zeros
+                }
+                if (g.m_from_x) tma_load_4d(sb, &map_dz, full_bar + stage, nb * kChunk, x0 + nx, y0 + ny, img);
+                else load_x(sb, nb * kChunk, x0 + nx, y0 + ny);
+            }
+            __syncwarp();
+            if (++stage == g.stages) { stage = 0; phase ^= 1; }
+        }
+        if (prof && lane == 0) atomicAdd(g.prof + 0, wcyc);
+    } else if (warp == 1) {
+        // ---------------- MMA issuer: rows x TR MMAs of N = ks*32 per K tile ----------------
+        const uint32_t idesc = make_idesc_tf32(ncb) | (1u << 15) | (1u << 16);     // A and B MN-major
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < ntile; ++it) {
+            mbar_wait_t(full_bar + stage, phase, prof, wcyc);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = smem_u32(smem + (size_t)stage * g.stage_bytes);
+            const uint64_t adesc = make_smem_desc_mn(sa, (uint32_t)m_box);          // M blocks: next 32-channel box
+            const uint64_t bdesc = make_smem_desc_mn(sa + 4 * m_box, 128u);         // N blocks: the box shifted by one pixel
+            if (elect_one()) {
+                for (int u = 0; u < rows; ++u) {
+#pragma unroll 4
+                    for (int kk = 0; kk < g.TR; ++kk)          // one image row of 8 pixels (K = 8) per MMA
+                        umma_tf32(tmem_base + (uint32_t)(u * ncb), adesc + (uint64_t)(kk * 64),
+                                  bdesc + (uint64_t)((kk + u) * g.HXw * 8), idesc, (it | kk) != 0);
+                }
+                umma_commit(empty_bar + stage);
+                if (it == ntile - 1) umma_commit(accum_bar);
+            }
+            __syncwarp();
+            if (++stage == g.stages) { stage = 0; phase ^= 1; }
+        }
+        if (prof && lane == 0) {
+            atomicAdd(g.prof + 1, wcyc);
+            atomicAdd(g.prof + 2, (unsigned long long)(clock64() - t_start));
+        }
+    } else if (ntile > 0) {
+        // ---------------- epilogue: TMEM -> part[split][group][128][ncols] (plain stores) ----------------
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        mbar_wait(accum_bar, 0);
+        const long long t_epi = clock64();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        // column-major tile [col][128 rows]: the 32 lanes of a warp hold 32 consecutive rows of one column -> every store
+        // instruction writes one full 128-byte line
+        float *dst = part + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * 128 * g.ncols + row;
+        uint32_t ra[16], rb[16];
+        const int nchunk = rows * ncb / 16;
+        tmem_ld16_issue(lane_addr, ra);
+        for (int ci = 0; ci < nchunk; ci += 2) {
+            tmem_ld_wait(ra);
+            if (ci + 1 < nchunk) tmem_ld16_issue(lane_addr + (uint32_t)((ci + 1) * 16), rb);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dst[(size_t)(ci * 16 + j) * 128] = __uint_as_float(ra[j]);
+            if (ci + 1 < nchunk) {
+                tmem_ld_wait(rb);
+                if (ci + 2 < nchunk) tmem_ld16_issue(lane_addr + (uint32_t)((ci + 2) * 16), ra);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) dst[(size_t)((ci + 1) * 16 + j) * 128] = __uint_as_float(rb[j]);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (prof && threadIdx.x == 64) {
+            atomicAdd(g.prof + 3, (unsigned long long)(clock64() - t_epi));
+            atomicAdd(g.prof + 4, (unsigned long long)(clock64() - t_start));
+            atomicAdd(g.prof + 5, 1ull);
+        }
+    }
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -1273,11 +1463,161 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restri
     }
 }
 
+// Reduction of the tap-packed partial tiles, two passes (deterministic: fixed summation order, no atomics).
+// Pass 1 sums the pixel splits element-wise into the split-0 tile: a block owns 64 consecutive elements and its four
+// thread rows each take every fourth split, so the column-major tiles are read as full 256-byte runs.
+__global__ void __launch_bounds__(256) wgrad_packed_sum_kernel(float *__restrict__ part, int64_t total, int splits) {
+    __shared__ float red[4][64];
+    const int e = threadIdx.x & 63, q = threadIdx.x >> 6;
+    for (int64_t base = (int64_t)blockIdx.x * 64; base < total; base += (int64_t)gridDim.x * 64) {
+        const int64_t i = base + e;
+        float acc = 0.f;
+        if (i < total) {
+            float a0 = 0.f, a1 = 0.f;
+            int sp = q;
+            for (; sp + 4 < splits; sp += 8) {
+                a0 += part[(size_t)sp * total + i];
+                a1 += part[(size_t)(sp + 4) * total + i];
+            }
+            if (sp < splits) a0 += part[(size_t)sp * total + i];
+            acc = a0 + a1;
+        }
+        red[q][e] = acc;
+        __syncthreads();
+        if (q == 0 && i < total) part[i] = (red[0][e] + red[1][e]) + (red[2][e] + red[3][e]);
+        __syncthreads();
+    }
+}
+
+// Pass 2 adds the summed tiles into dW [Cout][Ct][ks][ks].  A block takes 32 accumulator rows of one group, stages
+// them in shared memory and writes them back in dW order, where they form contiguous runs (m_from_x = 0: for one
+// output channel, 32 input channels x the group's filter rows; m_from_x = 1: for one output channel, 32 input
+// channels x the group's filter rows, taps reversed).
+constexpr int kWpPitch = 32 * 33 + 1;   // shared-memory words per (row shift, tap) plane: conflict-free both ways
+__global__ void __launch_bounds__(1024) wgrad_packed_scatter_kernel(const float *__restrict__ sum, float *__restrict__ dw,
+                                                                   WpGeom g, int groups) {
+    extern __shared__ float plane[];    // [RG * ks][32 c32][33] (+1 per plane)
+    const int taps = g.ks * g.ks, Ct = g.C0 + g.C1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int unit = blockIdx.x; unit < groups * 4; unit += gridDim.x) {
+        const int rb = unit & 3;
+        int grp = unit >> 2;
+        const float *tile = sum + (size_t)grp * 128 * g.ncols + rb * 32;
+        const int nb = grp % g.n_boxes;
+        grp /= g.n_boxes;
+        const int mb = grp % g.m_blocks, rg = grp / g.m_blocks;
+        const int u0 = rg * g.RG;
+        const int nu = min(g.RG, g.ks - u0);              // valid row shifts of this group
+        const int nt = nu * g.ks;                         // taps held by this tile
+        __syncthreads();
+        for (int col = warp; col < nt * kChunk; col += (int)(blockDim.x >> 5))  // col = (u * ks + j) * 32 + c32
+            plane[(col >> 5) * kWpPitch + (col & 31) * 33 + lane] = tile[(size_t)col * 128 + lane];
+        __syncthreads();
+        const int m0 = mb * 128 + rb * 32, n0 = nb * kChunk;
+        const int count = 32 * 32 * nt;
+        // m_from_x = 1: row = ci, c32 = co, the run covers filter rows ks-u0-nu .. ks-1-u0 with (u, j) in reverse order
+        // m_from_x = 0: row = co, c32 = ci, the run covers filter rows u0 .. u0+nu-1
+        const int tap0 = g.m_from_x ? (g.ks - u0 - nu) * g.ks : u0 * g.ks;
+        for (int ob = threadIdx.x; ob < count; ob += (int)blockDim.x * 4) {   // 4 independent read-modify-writes in flight
+            float v[4], dcur[4];
+            int64_t addr[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int o = ob + k * (int)blockDim.x;
+                addr[k] = -1;
+                if (o < count) {
+                    const int t = o % nt;                     // tap offset inside the contiguous run (dW order)
+                    const int mid = (o / nt) & 31, outer = o / (nt * 32);
+                    const int row = g.m_from_x ? mid : outer, c32 = g.m_from_x ? outer : mid;
+                    const int src_t = g.m_from_x ? nt - 1 - t : t;
+                    const int mch = m0 + row, nch = n0 + c32;
+                    if (mch < g.Mch && nch < g.Nch) {
+                        const int co = g.m_from_x ? nch : mch, ci = g.m_from_x ? mch : nch;
+                        addr[k] = ((int64_t)co * Ct + ci) * taps + tap0 + t;
+                        v[k] = plane[src_t * kWpPitch + c32 * 33 + row];
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dcur[k] = addr[k] >= 0 ? dw[addr[k]] : 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (addr[k] >= 0) dw[addr[k]] = dcur[k] + v[k];
+        }
+    }
+}
+
+bool plan_wgrad_packed(const ramnet_handle *h, const ramnet_conv_desc *d, WpGeom *gp, int *splits_out, int *groups_out) {
+    static const int version = [] { const char *e = getenv("RAMNET_WGRAD_V"); return e ? atoi(e) : 2; }();
+    if (version < 2) return false;                       // RAMNET_WGRAD_V=1: filter-row kernel everywhere (A/B runs)
+    if (d->stride != 1 || (d->ksize != 3 && d->ksize != 5)) return false;
+    if (d->C0 % kChunk || d->C1 % kChunk || d->Cout % kChunk) return false;
+    WpGeom &g = *gp;
+    g.N = d->N; g.H = d->H; g.W = d->W; g.Cout = d->Cout; g.C0 = d->C0; g.C1 = d->C1; g.ks = d->ksize; g.pad = d->ksize / 2;
+    const int Ct = d->C0 + d->C1;
+    g.m_from_x = Ct > d->Cout ? 1 : 0;                   // the operand with more channels fills the 128 MMA rows
+    g.Mch = g.m_from_x ? Ct : d->Cout;
+    g.Nch = g.m_from_x ? d->Cout : Ct;
+    g.m_blocks = (g.Mch + 127) / 128;
+    g.n_boxes = g.Nch / kChunk;
+    g.RG = 3;                                            // 3 * ks * 32 = 288 / 480 accumulator columns
+    g.TR = 8;                                            // 64-pixel K tiles: measured 10-15 % faster than 32 (fewer barrier round trips)
+    int ctas_per_sm_total = 2, smem_budget = 200 * 1024;
+    if (const char *f = getenv("RAMNET_WGP")) {          // tuning aid: "TR,RG,total CTAs per SM,smem KB"
+        int a = 0, b = 0, c = 0, e = 0;
+        if (sscanf(f, "%d,%d,%d,%d", &a, &b, &c, &e) == 4) {
+            if (a == 4 || a == 8) g.TR = a;
+            if (b >= 1 && b <= 3 && b * g.ks * kChunk <= 512) g.RG = b;
+            if (c >= 1) ctas_per_sm_total = c;
+            if (e >= 32 && e <= 200) smem_budget = e * 1024;
+        }
+    }
+    g.prof = nullptr;
+    g.row_groups = (g.ks + g.RG - 1) / g.RG;
+    g.HXw = 8 + g.ks - 1; g.HYw = g.TR + g.RG - 1;
+    g.ncols = g.RG * g.ks * kChunk;
+    g.tiles_x = (g.W + 7) / 8; g.tiles_y = (g.H + g.TR - 1) / g.TR;
+    const int64_t total = (int64_t)g.tiles_x * g.tiles_y * g.N;
+    if (total > 0x7fffffff) return false;
+    g.total_tiles = (int)total;
+    const int groups = g.row_groups * g.m_blocks * g.n_boxes;
+    // One CTA per SM at a time (the accumulators take all of TMEM).  Pick the pixel split that minimises
+    //   waves * (K tiles per CTA + fixed prologue/epilogue cost) + reduction traffic,
+    // in units of one K tile (~1 us): a wave that fills only a few SMs costs as much as a full one.
+    int64_t splits = 1;
+    {
+        double best = -1;
+        const int64_t max_splits = total / 8 > 0 ? total / 8 : 1;
+        for (int waves = 1; waves <= ctas_per_sm_total; ++waves) {
+            int64_t sp = ((int64_t)h->sm_count * waves) / groups;
+            if (sp < 1) sp = 1;
+            if (sp > max_splits) sp = max_splits;
+            const int64_t tpc = (total + sp - 1) / sp;
+            sp = (total + tpc - 1) / tpc;
+            const int64_t w = (sp * groups + h->sm_count - 1) / h->sm_count;
+            const double cost = (double)w * ((double)tpc * g.TR / 8.0 + 3.7) + 0.05 * (double)(sp * groups);
+            if (best < 0 || cost < best) { best = cost; splits = sp; }
+        }
+    }
+    g.tiles_per_cta = (int)((total + splits - 1) / splits);
+    splits = (total + g.tiles_per_cta - 1) / g.tiles_per_cta;
+    const int nbox = g.HXw * g.HYw * kChunk * 4;
+    g.stage_bytes = 4 * g.TR * 8 * kChunk * 4 + ((nbox + 1023) & ~1023);
+    g.stages = smem_budget / g.stage_bytes;
+    if (g.stages > 8) g.stages = 8;
+    if (g.stages < 2) return false;
+    *splits_out = (int)splits;
+    *groups_out = groups;
+    return true;
+}
+
 bool plan_wgrad(const ramnet_handle *h, const ramnet_conv_desc *d, WgGeom *gp, int *splits_out, int *groups_out);
 
 size_t conv_wgrad_tf32_workspace(const ramnet_handle *h, const ramnet_conv_desc *d) {
-    WgGeom g;
+    WpGeom p;
     int splits, groups;
+    if (plan_wgrad_packed(h, d, &p, &splits, &groups)) return (size_t)splits * groups * 128 * p.ncols * sizeof(float);
+    WgGeom g;
     if (!plan_wgrad(h, d, &g, &splits, &groups)) return 0;
     return (size_t)splits * groups * 128 * g.T * g.BN * sizeof(float);
 }
@@ -1346,6 +1686,88 @@ bool plan_wgrad(const ramnet_handle *h, const ramnet_conv_desc *d, WgGeom *gp, i
 int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz, const float *x0, const float *x1,
                     float *dw, void *workspace, size_t workspace_bytes, cudaStream_t s) {
     if ((((uintptr_t)dz | (uintptr_t)x0 | (uintptr_t)x1 | (uintptr_t)workspace) & 15) != 0) return RAMNET_EUNSUPPORTED;
+    {
+        WpGeom p;
+        int psplits, pgroups;
+        if (plan_wgrad_packed(h, d, &p, &psplits, &pgroups)) {
+            const size_t need = (size_t)psplits * pgroups * 128 * p.ncols * sizeof(float);
+            RAMNET_CHECK_ARG(workspace != nullptr && workspace_bytes >= need,
+                             "conv_wgrad(tf32): workspace of %zu bytes required (ramnet_conv_wgrad_workspace_bytes)", need);
+            CUtensorMap mdz, m0, m1;
+            const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+            auto enc = [&](CUtensorMap *m, const float *base, int C, bool n_operand) {
+                cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+                cuuint64_t str[3] = {(cuuint64_t)C * 4, (cuuint64_t)d->W * C * 4, (cuuint64_t)d->H * d->W * C * 4};
+                cuuint32_t box[4] = {kChunk, (cuuint32_t)(n_operand ? p.HXw : 8), (cuuint32_t)(n_operand ? p.HYw : p.TR), 1};
+                return encode(h, m, base, 4, dims, str, box, sw);
+            };
+            int rc = enc(&mdz, dz, d->Cout, p.m_from_x != 0);
+            if (rc) return rc;
+            rc = enc(&m0, x0, d->C0, p.m_from_x == 0);
+            if (rc) return rc;
+            if (x1) {
+                rc = enc(&m1, x1, d->C1, p.m_from_x == 0);
+                if (rc) return rc;
+            } else {
+                m1 = m0;
+            }
+            const size_t smem = (size_t)p.stages * p.stage_bytes + (2 * p.stages + 1) * 8 + 16 + 1024;
+            static size_t configured = 0;
+            if (smem > configured) {
+                RAMNET_CUDA(cudaFuncSetAttribute(conv_wgrad_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured = smem;
+            }
+            if (getenv("RAMNET_DEBUG"))
+                fprintf(stderr, "[ramnet] wgrad packed %dx%d C=%d+%d->%d k%d: m_from_x=%d groups=%d splits=%d tiles/cta=%d stages=%d\n",
+                        d->H, d->W, d->C0, d->C1, d->Cout, d->ksize, p.m_from_x, pgroups, psplits, p.tiles_per_cta, p.stages);
+            dim3 grid((unsigned)psplits, (unsigned)pgroups);
+            static const bool do_prof = getenv("RAMNET_PROF") != nullptr;      // debug only: synchronises and prints
+            static unsigned long long *pbuf = nullptr;
+            cudaEvent_t ev[3];
+            if (do_prof) {
+                if (!pbuf) cudaMalloc(&pbuf, 64);
+                cudaMemsetAsync(pbuf, 0, 64, s);
+                p.prof = pbuf;
+                for (auto &e : ev) cudaEventCreate(&e);
+                cudaEventRecord(ev[0], s);
+            }
+            conv_wgrad_packed_kernel<<<grid, kThreads, smem, s>>>(mdz, m0, m1, p, (float *)workspace);
+            RAMNET_LAUNCH_CHECK(h);
+            if (do_prof) cudaEventRecord(ev[1], s);
+            const int64_t elems = (int64_t)pgroups * 128 * p.ncols;
+            if (psplits > 1) {
+                wgrad_packed_sum_kernel<<<(unsigned)imin64((elems + 63) / 64, (int64_t)h->sm_count * 8), 256, 0, s>>>(
+                    (float *)workspace, elems, psplits);
+                RAMNET_LAUNCH_CHECK(h);
+            }
+            const size_t sc_smem = (size_t)p.RG * p.ks * kWpPitch * sizeof(float);
+            static size_t sc_configured = 0;
+            if (sc_smem > sc_configured) {
+                RAMNET_CUDA(cudaFuncSetAttribute(wgrad_packed_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
+                sc_configured = sc_smem;
+            }
+            wgrad_packed_scatter_kernel<<<(unsigned)imin64((int64_t)pgroups * 4, (int64_t)h->sm_count * 2), 1024, sc_smem, s>>>(
+                (const float *)workspace, dw, p, pgroups);
+            RAMNET_LAUNCH_CHECK(h);
+            if (do_prof) {
+                cudaEventRecord(ev[2], s);
+                unsigned long long hb[8];
+                cudaMemcpyAsync(hb, pbuf, 64, cudaMemcpyDeviceToHost, s);
+                cudaStreamSynchronize(s);
+                float t01 = 0, t12 = 0;
+                cudaEventElapsedTime(&t01, ev[0], ev[1]);
+                cudaEventElapsedTime(&t12, ev[1], ev[2]);
+                const double n = hb[5] ? (double)hb[5] : 1.0;
+                fprintf(stderr, "[ramnet-prof] wgrad packed %dx%d C=%d+%d->%d k%d TR=%d RG=%d groups=%d splits=%d tiles/cta=%d stages=%d | "
+                                "kernel %.1f us, reduce %.1f us | per-CTA kcycles: prod_wait_empty=%.1f mma_wait_full=%.1f mma_total=%.1f "
+                                "epilogue=%.1f cta_total=%.1f (n=%llu)\n",
+                        d->H, d->W, d->C0, d->C1, d->Cout, d->ksize, p.TR, p.RG, pgroups, psplits, p.tiles_per_cta, p.stages,
+                        t01 * 1e3, t12 * 1e3, hb[0] / n / 1e3, hb[1] / n / 1e3, hb[2] / n / 1e3, hb[3] / n / 1e3, hb[4] / n / 1e3, hb[5]);
+                for (auto &e : ev) cudaEventDestroy(e);
+            }
+            return RAMNET_OK;
+        }
+    }
     WgGeom g;
     int splits_i, groups;
     if (!plan_wgrad(h, d, &g, &splits_i, &groups)) return RAMNET_EUNSUPPORTED;

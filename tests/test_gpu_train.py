@@ -43,6 +43,9 @@ def _rel(a, b):
     (1, 16, 16, 64, 0, 64, 3, 1, 'res'),
     (2, 8, 12, 32, 32, 32, 3, 1, 'relu'),
     (1, 16, 24, 64, 0, 32, 5, 1, 'relu'),
+    (1, 10, 20, 32, 0, 64, 5, 1, 'relu'),      # tap-packed wgrad, M = dZ, ragged tiles in y and x
+    (2, 6, 8, 64, 64, 160, 3, 1, 'relu'),      # two M blocks (the second one partial), virtual concat as the N operand
+    (1, 12, 8, 160, 0, 32, 3, 1, 'relu'),      # M = X with a partial second block
 ])
 def test_conv_backward_vs_torch(kind, shape):
     from rpg_ramnet_b200 import autograd as AG, ops
