@@ -1015,25 +1015,41 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_tcgen05_kernel(const __gr
 // (u = halo row shift, j = N block).  Out-of-bounds pixels of either box are zero-filled by TMA = zero padding.
 // ================================================================================================
 struct WpGeom {
-    int N, H, W;             // pixel grid (stride 1: same for X and dZ)
+    int N, H, W;             // pixel grid of dZ (= of X for stride 1, = of each input parity plane for stride 2)
     int Cout, C0, C1;
-    int ks, pad;
+    int ks;                  // filter size of the convolution (dW is [Cout][Ct][ks][ks])
+    int kh, kw;              // taps of THIS problem: ks x ks (stride 1) or the 3x3 / 3x2 / 2x3 / 2x2 sub-filter of one parity class
+    int oy, ox;              // origin of the N box relative to the tile origin (before the row-group offset)
+    int r0, dr, s0, ds;      // filter tap of (row shift u, N block j): (r0 + dr*u, s0 + ds*j)
+    int x5d, py, px;         // stride 2: X is read through the 5-D parity view (2C, W/2, 2, H/2, N), plane (py, px)
     int m_from_x;
     int Mch, Nch;            // channels of the M / N operand
     int m_blocks, n_boxes;   // ceil(Mch / 128), Nch / 32
-    int RG, row_groups;      // halo row shifts per CTA, ceil(ks / RG)
+    int RG, row_groups;      // halo row shifts per CTA, ceil(kh / RG)
     int TR;                  // image rows per K tile (tile = 8 px x TR rows)
-    int HXw, HYw;            // N-operand box: (8 + ks - 1) px x (TR + RG - 1) rows
+    int HXw, HYw;            // N-operand box: (8 + kw - 1) px x (TR + RG - 1) rows
     int tiles_x, tiles_y, tiles_per_cta, total_tiles;
     int stages, stage_bytes;
-    int ncols;               // accumulator columns per CTA = RG * ks * 32 (workspace row pitch)
+    int ncols;               // accumulator columns per CTA = RG * kw * 32 (workspace row pitch)
     unsigned long long *prof; // RAMNET_PROF=1: cycle counters (debug), else nullptr
+};
+
+// The problems of one layer (1, or the 4 parity classes of a stride-2 layer) run as ONE launch: blockIdx.z selects the
+// problem.  They share the tensor maps (N boxes sized for the largest sub-filter), the split / group counts and the
+// workspace pitch, so the three launches (MMA, split sum, scatter) are paid once per layer.
+struct WpBatch {
+    WpGeom g[4];
+    int n;
+    long long part_stride;   // floats between the workspaces of consecutive problems
 };
 
 __global__ void __launch_bounds__(kThreads) conv_wgrad_packed_kernel(const __grid_constant__ CUtensorMap map_dz,
                                                                      const __grid_constant__ CUtensorMap map_x0,
                                                                      const __grid_constant__ CUtensorMap map_x1,
-                                                                     WpGeom g, float *__restrict__ part) {
+                                                                     const __grid_constant__ WpBatch batch,
+                                                                     float *__restrict__ part) {
+    const WpGeom &g = batch.g[blockIdx.z];
+    part += (size_t)blockIdx.z * batch.part_stride;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int m_box = g.TR * 8 * kChunk * 4;              // one 32-channel box of the M operand (TR KB)
@@ -1050,11 +1066,11 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_packed_kernel(const __gri
     const int mb = t % g.m_blocks;
     const int rg = t / g.m_blocks;
     const int u0 = rg * g.RG;
-    const int rows = min(g.RG, g.ks - u0);                 // halo row shifts handled here
+    const int rows = min(g.RG, g.kh - u0);                 // halo row shifts handled here
     const int tile_begin = blockIdx.x * g.tiles_per_cta;
     const int tile_end = min(tile_begin + g.tiles_per_cta, g.total_tiles);
     const int ntile = tile_end - tile_begin;
-    const int ncb = g.ks * kChunk;                         // accumulator columns per row shift = UMMA N
+    const int ncb = g.kw * kChunk;                         // accumulator columns per row shift = UMMA N
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < g.ncols) tmem_cols <<= 1;
 
@@ -1088,8 +1104,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_packed_kernel(const __gri
         uint32_t phase = 0;
         const int nbytes = g.HXw * g.HYw * kChunk * 4;     // the box always carries RG - 1 halo rows
         // origin of the N box relative to the tile origin
-        const int nx = g.m_from_x ? g.pad - (g.ks - 1) : -g.pad;
-        const int ny = nx + u0;
+        const int nx = g.ox, ny = g.oy + u0;
         for (int it = 0; it < ntile; ++it) {
             int tt = tile_begin + it;
             const int txi = tt % g.tiles_x;
@@ -1106,8 +1121,10 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_packed_kernel(const __gri
                     const bool second = ch >= g.C0 && g.C1 > 0;
                     const CUtensorMap *mx = second ? &map_x1 : &map_x0;
                     const int Csrc = second ? g.C1 : g.C0;
-                    const int c = ch >= g.C0 + g.C1 ? Csrc : (second ? ch - g.C0 : ch);
-                    tma_load_4d(dst, mx, full_bar + stage, c, x, y, img);
+                    const bool past = ch >= g.C0 + g.C1;
+                    const int c = past ? Csrc : (second ? ch - g.C0 : ch);
+                    if (g.x5d) tma_load_5d(dst, mx, full_bar + stage, past ? 2 * Csrc : g.px * Csrc + c, x, g.py, y, img);
+                    else tma_load_4d(dst, mx, full_bar + stage, c, x, y, img);
                 };
                 for (int q = 0; q < 4; ++q) {
                     const int ch = (mb * 4 + q) * kChunk;
@@ -1466,7 +1483,9 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restri
 // Reduction of the tap-packed partial tiles, two passes (deterministic: fixed summation order, no atomics).
 // Pass 1 sums the pixel splits element-wise into the split-0 tile: a block owns 64 consecutive elements and its four
 // thread rows each take every fourth split, so the column-major tiles are read as full 256-byte runs.
-__global__ void __launch_bounds__(256) wgrad_packed_sum_kernel(float *__restrict__ part, int64_t total, int splits) {
+__global__ void __launch_bounds__(256) wgrad_packed_sum_kernel(float *__restrict__ part, int64_t total, int splits,
+                                                               long long part_stride) {
+    part += (size_t)blockIdx.y * part_stride;      // blockIdx.y = problem of the batch
     __shared__ float red[4][64];
     const int e = threadIdx.x & 63, q = threadIdx.x >> 6;
     for (int64_t base = (int64_t)blockIdx.x * 64; base < total; base += (int64_t)gridDim.x * 64) {
@@ -1490,13 +1509,14 @@ __global__ void __launch_bounds__(256) wgrad_packed_sum_kernel(float *__restrict
 }
 
 // Pass 2 adds the summed tiles into dW [Cout][Ct][ks][ks].  A block takes 32 accumulator rows of one group, stages
-// them in shared memory and writes them back in dW order, where they form contiguous runs (m_from_x = 0: for one
-// output channel, 32 input channels x the group's filter rows; m_from_x = 1: for one output channel, 32 input
-// channels x the group's filter rows, taps reversed).
+// them in shared memory and writes them back ordered (output channel, input channel, tap), where for a stride-1 layer
+// they form contiguous runs (for one output channel: 32 input channels x the group's filter rows).
 constexpr int kWpPitch = 32 * 33 + 1;   // shared-memory words per (row shift, tap) plane: conflict-free both ways
 __global__ void __launch_bounds__(1024) wgrad_packed_scatter_kernel(const float *__restrict__ sum, float *__restrict__ dw,
-                                                                   WpGeom g, int groups) {
-    extern __shared__ float plane[];    // [RG * ks][32 c32][33] (+1 per plane)
+                                                                   const __grid_constant__ WpBatch batch, int groups) {
+    const WpGeom &g = batch.g[blockIdx.y];
+    sum += (size_t)blockIdx.y * batch.part_stride;
+    extern __shared__ float plane[];    // [RG * kw][32 c32][33] (+1 per plane)
     const int taps = g.ks * g.ks, Ct = g.C0 + g.C1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int unit = blockIdx.x; unit < groups * 4; unit += gridDim.x) {
@@ -1507,17 +1527,14 @@ __global__ void __launch_bounds__(1024) wgrad_packed_scatter_kernel(const float 
         grp /= g.n_boxes;
         const int mb = grp % g.m_blocks, rg = grp / g.m_blocks;
         const int u0 = rg * g.RG;
-        const int nu = min(g.RG, g.ks - u0);              // valid row shifts of this group
-        const int nt = nu * g.ks;                         // taps held by this tile
+        const int nu = min(g.RG, g.kh - u0);              // valid row shifts of this group
+        const int nt = nu * g.kw;                         // taps held by this tile
         __syncthreads();
-        for (int col = warp; col < nt * kChunk; col += (int)(blockDim.x >> 5))  // col = (u * ks + j) * 32 + c32
+        for (int col = warp; col < nt * kChunk; col += (int)(blockDim.x >> 5))  // col = (u * kw + j) * 32 + c32
             plane[(col >> 5) * kWpPitch + (col & 31) * 33 + lane] = tile[(size_t)col * 128 + lane];
         __syncthreads();
         const int m0 = mb * 128 + rb * 32, n0 = nb * kChunk;
         const int count = 32 * 32 * nt;
-        // m_from_x = 1: row = ci, c32 = co, the run covers filter rows ks-u0-nu .. ks-1-u0 with (u, j) in reverse order
-        // m_from_x = 0: row = co, c32 = ci, the run covers filter rows u0 .. u0+nu-1
-        const int tap0 = g.m_from_x ? (g.ks - u0 - nu) * g.ks : u0 * g.ks;
         for (int ob = threadIdx.x; ob < count; ob += (int)blockDim.x * 4) {   // 4 independent read-modify-writes in flight
             float v[4], dcur[4];
             int64_t addr[4];
@@ -1526,15 +1543,16 @@ __global__ void __launch_bounds__(1024) wgrad_packed_scatter_kernel(const float 
                 const int o = ob + k * (int)blockDim.x;
                 addr[k] = -1;
                 if (o < count) {
-                    const int t = o % nt;                     // tap offset inside the contiguous run (dW order)
+                    const int t = o % nt;                     // (row shift, N block) of the tile, fastest index
                     const int mid = (o / nt) & 31, outer = o / (nt * 32);
-                    const int row = g.m_from_x ? mid : outer, c32 = g.m_from_x ? outer : mid;
-                    const int src_t = g.m_from_x ? nt - 1 - t : t;
+                    const int row = g.m_from_x ? mid : outer, c32 = g.m_from_x ? outer : mid;   // -> (co, ci, tap) order
                     const int mch = m0 + row, nch = n0 + c32;
                     if (mch < g.Mch && nch < g.Nch) {
+                        const int u = u0 + t / g.kw, j = t % g.kw;
+                        const int tap = (g.r0 + g.dr * u) * g.ks + g.s0 + g.ds * j;
                         const int co = g.m_from_x ? nch : mch, ci = g.m_from_x ? mch : nch;
-                        addr[k] = ((int64_t)co * Ct + ci) * taps + tap0 + t;
-                        v[k] = plane[src_t * kWpPitch + c32 * 33 + row];
+                        addr[k] = ((int64_t)co * Ct + ci) * taps + tap;
+                        v[k] = plane[t * kWpPitch + c32 * 33 + row];
                     }
                 }
             }
@@ -1547,35 +1565,71 @@ __global__ void __launch_bounds__(1024) wgrad_packed_scatter_kernel(const float 
     }
 }
 
-bool plan_wgrad_packed(const ramnet_handle *h, const ramnet_conv_desc *d, WpGeom *gp, int *splits_out, int *groups_out) {
+// Number of tap-packed problems a layer decomposes into: 1 (stride 1), 4 (stride 2: one per input parity class), 0 = not covered.
+int wgrad_packed_problems(const ramnet_conv_desc *d) {
     static const int version = [] { const char *e = getenv("RAMNET_WGRAD_V"); return e ? atoi(e) : 2; }();
-    if (version < 2) return false;                       // RAMNET_WGRAD_V=1: filter-row kernel everywhere (A/B runs)
-    if (d->stride != 1 || (d->ksize != 3 && d->ksize != 5)) return false;
-    if (d->C0 % kChunk || d->C1 % kChunk || d->Cout % kChunk) return false;
+    if (version < 2) return 0;                           // RAMNET_WGRAD_V=1: filter-row kernel everywhere (A/B runs)
+    if (d->ksize != 3 && d->ksize != 5) return 0;
+    if (d->C0 % kChunk || d->C1 % kChunk || d->Cout % kChunk) return 0;
+    if (d->stride == 1) return 1;
+    if (d->stride == 2 && !((d->H | d->W) & 1) && !getenv("RAMNET_WGRAD_S2_OLD")) return 4;
+    return 0;
+}
+
+// Plans problem `cls` of a layer.  Stride 2: dW[r][s] = sum dZ[oy][ox] * X[2 oy + r - pad][2 ox + s - pad]; with
+// r - pad = 2 dy + py the taps of one row parity py read the input parity plane P_py[y'][x'] = X[2 y' + py][..] at
+// oy + dy, i.e. a stride-1 problem between dZ and the plane with the sub-filter {r : (r - pad) mod 2 = py}.
+bool plan_wgrad_packed(const ramnet_handle *h, const ramnet_conv_desc *d, int cls, int nprob, WpGeom *gp, int *splits_out,
+                       int *groups_out) {
     WpGeom &g = *gp;
-    g.N = d->N; g.H = d->H; g.W = d->W; g.Cout = d->Cout; g.C0 = d->C0; g.C1 = d->C1; g.ks = d->ksize; g.pad = d->ksize / 2;
-    const int Ct = d->C0 + d->C1;
+    g.N = d->N; g.Cout = d->Cout; g.C0 = d->C0; g.C1 = d->C1; g.ks = d->ksize;
+    const int pad = d->ksize / 2, Ct = d->C0 + d->C1;
     g.m_from_x = Ct > d->Cout ? 1 : 0;                   // the operand with more channels fills the 128 MMA rows
+    if (d->stride == 1) {
+        g.H = d->H; g.W = d->W; g.kh = g.kw = g.ks; g.x5d = 0; g.py = g.px = 0;
+        if (g.m_from_x) { g.oy = g.ox = pad - (g.ks - 1); g.r0 = g.s0 = g.ks - 1; g.dr = g.ds = -1; }
+        else { g.oy = g.ox = -pad; g.r0 = g.s0 = 0; g.dr = g.ds = 1; }
+    } else {
+        g.H = d->H / 2; g.W = d->W / 2; g.x5d = 1; g.py = cls >> 1; g.px = cls & 1;
+        // taps of parity q along one axis: r = rmin + 2 i, shifts dy = (r - pad - q) / 2 = dmin + i
+        auto axis = [&](int q, int *k, int *rmin, int *dmin) {
+            *rmin = ((pad + q) & 1);                      // smallest r with (r - pad) mod 2 == q
+            *k = (g.ks - 1 - *rmin) / 2 + 1;
+            const int a = *rmin - pad - q;                // even
+            *dmin = a >= 0 ? a / 2 : -((-a) / 2);
+        };
+        int rmin, smin, dymin, dxmin;
+        axis(g.py, &g.kh, &rmin, &dymin);
+        axis(g.px, &g.kw, &smin, &dxmin);
+        if (g.m_from_x) {     // N = dZ shifted by -(dy, dx): box origin = -(dmax), shift u <-> dy = dmax - u
+            g.oy = -(dymin + g.kh - 1); g.ox = -(dxmin + g.kw - 1);
+            g.r0 = rmin + 2 * (g.kh - 1); g.dr = -2; g.s0 = smin + 2 * (g.kw - 1); g.ds = -2;
+        } else {              // N = plane shifted by (dy, dx): box origin = dmin, shift u <-> dy = dmin + u
+            g.oy = dymin; g.ox = dxmin;
+            g.r0 = rmin; g.dr = 2; g.s0 = smin; g.ds = 2;
+        }
+    }
     g.Mch = g.m_from_x ? Ct : d->Cout;
     g.Nch = g.m_from_x ? d->Cout : Ct;
     g.m_blocks = (g.Mch + 127) / 128;
     g.n_boxes = g.Nch / kChunk;
-    g.RG = 3;                                            // 3 * ks * 32 = 288 / 480 accumulator columns
+    g.RG = 3;                                            // 3 * kw * 32 <= 480 accumulator columns
     g.TR = 8;                                            // 64-pixel K tiles: measured 10-15 % faster than 32 (fewer barrier round trips)
     int ctas_per_sm_total = 2, smem_budget = 200 * 1024;
     if (const char *f = getenv("RAMNET_WGP")) {          // tuning aid: "TR,RG,total CTAs per SM,smem KB"
         int a = 0, b = 0, c = 0, e = 0;
         if (sscanf(f, "%d,%d,%d,%d", &a, &b, &c, &e) == 4) {
             if (a == 4 || a == 8) g.TR = a;
-            if (b >= 1 && b <= 3 && b * g.ks * kChunk <= 512) g.RG = b;
+            if (b >= 1 && b <= 3 && b * g.kw * kChunk <= 512) g.RG = b;
             if (c >= 1) ctas_per_sm_total = c;
             if (e >= 32 && e <= 200) smem_budget = e * 1024;
         }
     }
+    if (g.RG > g.kh) g.RG = g.kh;
     g.prof = nullptr;
-    g.row_groups = (g.ks + g.RG - 1) / g.RG;
-    g.HXw = 8 + g.ks - 1; g.HYw = g.TR + g.RG - 1;
-    g.ncols = g.RG * g.ks * kChunk;
+    g.row_groups = (g.kh + g.RG - 1) / g.RG;
+    g.HXw = 8 + g.kw - 1; g.HYw = g.TR + g.RG - 1;
+    g.ncols = g.RG * g.kw * kChunk;
     g.tiles_x = (g.W + 7) / 8; g.tiles_y = (g.H + g.TR - 1) / g.TR;
     const int64_t total = (int64_t)g.tiles_x * g.tiles_y * g.N;
     if (total > 0x7fffffff) return false;
@@ -1589,13 +1643,13 @@ bool plan_wgrad_packed(const ramnet_handle *h, const ramnet_conv_desc *d, WpGeom
         double best = -1;
         const int64_t max_splits = total / 8 > 0 ? total / 8 : 1;
         for (int waves = 1; waves <= ctas_per_sm_total; ++waves) {
-            int64_t sp = ((int64_t)h->sm_count * waves) / groups;
+            int64_t sp = ((int64_t)h->sm_count * waves) / ((int64_t)groups * nprob);   // the problems of a layer share one launch
             if (sp < 1) sp = 1;
             if (sp > max_splits) sp = max_splits;
             const int64_t tpc = (total + sp - 1) / sp;
             sp = (total + tpc - 1) / tpc;
-            const int64_t w = (sp * groups + h->sm_count - 1) / h->sm_count;
-            const double cost = (double)w * ((double)tpc * g.TR / 8.0 + 3.7) + 0.05 * (double)(sp * groups);
+            const int64_t w = (sp * groups * nprob + h->sm_count - 1) / h->sm_count;
+            const double cost = (double)w * ((double)tpc * g.TR / 8.0 + 3.7) + 0.05 * (double)(sp * groups * nprob);
             if (best < 0 || cost < best) { best = cost; splits = sp; }
         }
     }
@@ -1611,12 +1665,47 @@ bool plan_wgrad_packed(const ramnet_handle *h, const ramnet_conv_desc *d, WpGeom
     return true;
 }
 
+// Plans every problem of a layer and unifies what the shared launch needs (N box, workspace pitch, pipeline depth).
+bool plan_wgrad_batch(const ramnet_handle *h, const ramnet_conv_desc *d, WpBatch *b, int *splits_out, int *groups_out) {
+    b->n = wgrad_packed_problems(d);
+    if (b->n == 0) return false;
+    int splits = 0, groups = 0;
+    for (int cls = 0; cls < b->n; ++cls) {
+        int sp, gr;
+        if (!plan_wgrad_packed(h, d, cls, b->n, &b->g[cls], &sp, &gr)) return false;
+        if (cls == 0) { splits = sp; groups = gr; }
+        else if (sp != splits || gr != groups || b->g[cls].tiles_per_cta != b->g[0].tiles_per_cta) return false;
+    }
+    WpGeom &g0 = b->g[0];
+    for (int cls = 1; cls < b->n; ++cls) {
+        const WpGeom &g = b->g[cls];
+        if (g.HXw > g0.HXw) g0.HXw = g.HXw;
+        if (g.HYw > g0.HYw) g0.HYw = g.HYw;
+        if (g.ncols > g0.ncols) g0.ncols = g.ncols;
+        if (g.stage_bytes > g0.stage_bytes) g0.stage_bytes = g.stage_bytes;
+        if (g.stages < g0.stages) g0.stages = g.stages;
+    }
+    const int nbox = g0.HXw * g0.HYw * kChunk * 4;
+    g0.stage_bytes = 4 * g0.TR * 8 * kChunk * 4 + ((nbox + 1023) & ~1023);
+    while (g0.stages > 2 && (size_t)g0.stages * g0.stage_bytes > 200 * 1024) --g0.stages;
+    for (int cls = 1; cls < b->n; ++cls) {
+        WpGeom &g = b->g[cls];
+        g.HXw = g0.HXw; g.HYw = g0.HYw; g.ncols = g0.ncols; g.stage_bytes = g0.stage_bytes; g.stages = g0.stages;
+    }
+    b->part_stride = (long long)splits * groups * 128 * g0.ncols;
+    *splits_out = splits;
+    *groups_out = groups;
+    return true;
+}
+
 bool plan_wgrad(const ramnet_handle *h, const ramnet_conv_desc *d, WgGeom *gp, int *splits_out, int *groups_out);
 
 size_t conv_wgrad_tf32_workspace(const ramnet_handle *h, const ramnet_conv_desc *d) {
-    WpGeom p;
     int splits, groups;
-    if (plan_wgrad_packed(h, d, &p, &splits, &groups)) return (size_t)splits * groups * 128 * p.ncols * sizeof(float);
+    {
+        WpBatch b;
+        if (plan_wgrad_batch(h, d, &b, &splits, &groups)) return (size_t)b.n * b.part_stride * sizeof(float);
+    }
     WgGeom g;
     if (!plan_wgrad(h, d, &g, &splits, &groups)) return 0;
     return (size_t)splits * groups * 128 * g.T * g.BN * sizeof(float);
@@ -1686,87 +1775,102 @@ bool plan_wgrad(const ramnet_handle *h, const ramnet_conv_desc *d, WgGeom *gp, i
 int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz, const float *x0, const float *x1,
                     float *dw, void *workspace, size_t workspace_bytes, cudaStream_t s) {
     if ((((uintptr_t)dz | (uintptr_t)x0 | (uintptr_t)x1 | (uintptr_t)workspace) & 15) != 0) return RAMNET_EUNSUPPORTED;
-    {
-        WpGeom p;
-        int psplits, pgroups;
-        if (plan_wgrad_packed(h, d, &p, &psplits, &pgroups)) {
-            const size_t need = (size_t)psplits * pgroups * 128 * p.ncols * sizeof(float);
-            RAMNET_CHECK_ARG(workspace != nullptr && workspace_bytes >= need,
-                             "conv_wgrad(tf32): workspace of %zu bytes required (ramnet_conv_wgrad_workspace_bytes)", need);
-            CUtensorMap mdz, m0, m1;
-            const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-            auto enc = [&](CUtensorMap *m, const float *base, int C, bool n_operand) {
+    WpBatch batch;
+    int psplits, pgroups;
+    if (plan_wgrad_batch(h, d, &batch, &psplits, &pgroups)) {
+        const WpGeom &p = batch.g[0];
+        const size_t need = (size_t)batch.n * batch.part_stride * sizeof(float);
+        RAMNET_CHECK_ARG(workspace != nullptr && workspace_bytes >= need,
+                         "conv_wgrad(tf32): workspace of %zu bytes required (ramnet_conv_wgrad_workspace_bytes)", need);
+        CUtensorMap mdz, m0, m1;
+        const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+        {
+            cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)d->N};
+            cuuint64_t str[3] = {(cuuint64_t)d->Cout * 4, (cuuint64_t)p.W * d->Cout * 4, (cuuint64_t)p.H * p.W * d->Cout * 4};
+            cuuint32_t box[4] = {kChunk, (cuuint32_t)(p.m_from_x ? p.HXw : 8), (cuuint32_t)(p.m_from_x ? p.HYw : p.TR), 1};
+            int rc = encode(h, &mdz, dz, 4, dims, str, box, sw);
+            if (rc) return rc;
+        }
+        auto enc_x = [&](CUtensorMap *m, const float *base, int C) {
+            const cuuint32_t bw = (cuuint32_t)(p.m_from_x ? 8 : p.HXw), bh = (cuuint32_t)(p.m_from_x ? p.TR : p.HYw);
+            if (!p.x5d) {
                 cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
                 cuuint64_t str[3] = {(cuuint64_t)C * 4, (cuuint64_t)d->W * C * 4, (cuuint64_t)d->H * d->W * C * 4};
-                cuuint32_t box[4] = {kChunk, (cuuint32_t)(n_operand ? p.HXw : 8), (cuuint32_t)(n_operand ? p.HYw : p.TR), 1};
+                cuuint32_t box[4] = {kChunk, bw, bh, 1};
                 return encode(h, m, base, 4, dims, str, box, sw);
-            };
-            int rc = enc(&mdz, dz, d->Cout, p.m_from_x != 0);
+            }
+            // stride 2: parity view (2C, W/2, 2, H/2, N); one box = a patch of one parity plane
+            cuuint64_t dims[5] = {(cuuint64_t)2 * C, (cuuint64_t)d->W / 2, 2, (cuuint64_t)d->H / 2, (cuuint64_t)d->N};
+            cuuint64_t str[4] = {(cuuint64_t)2 * C * 4, (cuuint64_t)d->W * C * 4, (cuuint64_t)2 * d->W * C * 4,
+                                 (cuuint64_t)d->H * d->W * C * 4};
+            cuuint32_t box[5] = {kChunk, bw, 1, bh, 1};
+            return encode(h, m, base, 5, dims, str, box, sw);
+        };
+        int rc = enc_x(&m0, x0, d->C0);
+        if (rc) return rc;
+        if (x1) {
+            rc = enc_x(&m1, x1, d->C1);
             if (rc) return rc;
-            rc = enc(&m0, x0, d->C0, p.m_from_x == 0);
-            if (rc) return rc;
-            if (x1) {
-                rc = enc(&m1, x1, d->C1, p.m_from_x == 0);
-                if (rc) return rc;
-            } else {
-                m1 = m0;
-            }
-            const size_t smem = (size_t)p.stages * p.stage_bytes + (2 * p.stages + 1) * 8 + 16 + 1024;
-            static size_t configured = 0;
-            if (smem > configured) {
-                RAMNET_CUDA(cudaFuncSetAttribute(conv_wgrad_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                configured = smem;
-            }
-            if (getenv("RAMNET_DEBUG"))
-                fprintf(stderr, "[ramnet] wgrad packed %dx%d C=%d+%d->%d k%d: m_from_x=%d groups=%d splits=%d tiles/cta=%d stages=%d\n",
-                        d->H, d->W, d->C0, d->C1, d->Cout, d->ksize, p.m_from_x, pgroups, psplits, p.tiles_per_cta, p.stages);
-            dim3 grid((unsigned)psplits, (unsigned)pgroups);
-            static const bool do_prof = getenv("RAMNET_PROF") != nullptr;      // debug only: synchronises and prints
-            static unsigned long long *pbuf = nullptr;
-            cudaEvent_t ev[3];
-            if (do_prof) {
-                if (!pbuf) cudaMalloc(&pbuf, 64);
-                cudaMemsetAsync(pbuf, 0, 64, s);
-                p.prof = pbuf;
-                for (auto &e : ev) cudaEventCreate(&e);
-                cudaEventRecord(ev[0], s);
-            }
-            conv_wgrad_packed_kernel<<<grid, kThreads, smem, s>>>(mdz, m0, m1, p, (float *)workspace);
-            RAMNET_LAUNCH_CHECK(h);
-            if (do_prof) cudaEventRecord(ev[1], s);
-            const int64_t elems = (int64_t)pgroups * 128 * p.ncols;
-            if (psplits > 1) {
-                wgrad_packed_sum_kernel<<<(unsigned)imin64((elems + 63) / 64, (int64_t)h->sm_count * 8), 256, 0, s>>>(
-                    (float *)workspace, elems, psplits);
-                RAMNET_LAUNCH_CHECK(h);
-            }
-            const size_t sc_smem = (size_t)p.RG * p.ks * kWpPitch * sizeof(float);
-            static size_t sc_configured = 0;
-            if (sc_smem > sc_configured) {
-                RAMNET_CUDA(cudaFuncSetAttribute(wgrad_packed_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
-                sc_configured = sc_smem;
-            }
-            wgrad_packed_scatter_kernel<<<(unsigned)imin64((int64_t)pgroups * 4, (int64_t)h->sm_count * 2), 1024, sc_smem, s>>>(
-                (const float *)workspace, dw, p, pgroups);
-            RAMNET_LAUNCH_CHECK(h);
-            if (do_prof) {
-                cudaEventRecord(ev[2], s);
-                unsigned long long hb[8];
-                cudaMemcpyAsync(hb, pbuf, 64, cudaMemcpyDeviceToHost, s);
-                cudaStreamSynchronize(s);
-                float t01 = 0, t12 = 0;
-                cudaEventElapsedTime(&t01, ev[0], ev[1]);
-                cudaEventElapsedTime(&t12, ev[1], ev[2]);
-                const double n = hb[5] ? (double)hb[5] : 1.0;
-                fprintf(stderr, "[ramnet-prof] wgrad packed %dx%d C=%d+%d->%d k%d TR=%d RG=%d groups=%d splits=%d tiles/cta=%d stages=%d | "
-                                "kernel %.1f us, reduce %.1f us | per-CTA kcycles: prod_wait_empty=%.1f mma_wait_full=%.1f mma_total=%.1f "
-                                "epilogue=%.1f cta_total=%.1f (n=%llu)\n",
-                        d->H, d->W, d->C0, d->C1, d->Cout, d->ksize, p.TR, p.RG, pgroups, psplits, p.tiles_per_cta, p.stages,
-                        t01 * 1e3, t12 * 1e3, hb[0] / n / 1e3, hb[1] / n / 1e3, hb[2] / n / 1e3, hb[3] / n / 1e3, hb[4] / n / 1e3, hb[5]);
-                for (auto &e : ev) cudaEventDestroy(e);
-            }
-            return RAMNET_OK;
+        } else {
+            m1 = m0;
         }
+        const size_t smem = (size_t)p.stages * p.stage_bytes + (2 * p.stages + 1) * 8 + 16 + 1024;
+        static size_t configured = 0;
+        if (smem > configured) {
+            RAMNET_CUDA(cudaFuncSetAttribute(conv_wgrad_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        if (getenv("RAMNET_DEBUG"))
+            fprintf(stderr, "[ramnet] wgrad packed %dx%d C=%d+%d->%d k%d s%d: problems=%d m_from_x=%d groups=%d splits=%d tiles/cta=%d stages=%d\n",
+                    d->H, d->W, d->C0, d->C1, d->Cout, d->ksize, d->stride, batch.n, p.m_from_x, pgroups, psplits, p.tiles_per_cta,
+                    p.stages);
+        dim3 grid((unsigned)psplits, (unsigned)pgroups, (unsigned)batch.n);
+        static const bool do_prof = getenv("RAMNET_PROF") != nullptr;      // debug only: synchronises and prints
+        static unsigned long long *pbuf = nullptr;
+        cudaEvent_t ev[3];
+        if (do_prof) {
+            if (!pbuf) cudaMalloc(&pbuf, 64);
+            cudaMemsetAsync(pbuf, 0, 64, s);
+            for (int c = 0; c < batch.n; ++c) batch.g[c].prof = pbuf;
+            for (auto &e : ev) cudaEventCreate(&e);
+            cudaEventRecord(ev[0], s);
+        }
+        conv_wgrad_packed_kernel<<<grid, kThreads, smem, s>>>(mdz, m0, m1, batch, (float *)workspace);
+        RAMNET_LAUNCH_CHECK(h);
+        if (do_prof) cudaEventRecord(ev[1], s);
+        const int64_t elems = (int64_t)pgroups * 128 * p.ncols;
+        if (psplits > 1) {
+            dim3 sgrid((unsigned)imin64((elems + 63) / 64, (int64_t)h->sm_count * 8), (unsigned)batch.n);
+            wgrad_packed_sum_kernel<<<sgrid, 256, 0, s>>>((float *)workspace, elems, psplits, batch.part_stride);
+            RAMNET_LAUNCH_CHECK(h);
+        }
+        const size_t sc_smem = (size_t)3 * 5 * kWpPitch * sizeof(float);       // up to 3 row shifts x 5 taps
+        static bool sc_configured = false;
+        if (!sc_configured) {
+            RAMNET_CUDA(cudaFuncSetAttribute(wgrad_packed_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
+            sc_configured = true;
+        }
+        dim3 cgrid((unsigned)imin64((int64_t)pgroups * 4, (int64_t)h->sm_count * 2), (unsigned)batch.n);
+        wgrad_packed_scatter_kernel<<<cgrid, 1024, sc_smem, s>>>((const float *)workspace, dw, batch, pgroups);
+        RAMNET_LAUNCH_CHECK(h);
+        if (do_prof) {
+            cudaEventRecord(ev[2], s);
+            unsigned long long hb[8];
+            cudaMemcpyAsync(hb, pbuf, 64, cudaMemcpyDeviceToHost, s);
+            cudaStreamSynchronize(s);
+            float t01 = 0, t12 = 0;
+            cudaEventElapsedTime(&t01, ev[0], ev[1]);
+            cudaEventElapsedTime(&t12, ev[1], ev[2]);
+            const double n = hb[5] ? (double)hb[5] : 1.0;
+            fprintf(stderr, "[ramnet-prof] wgrad packed %dx%d C=%d+%d->%d k%d s%d problems=%d TR=%d RG=%d groups=%d splits=%d tiles/cta=%d stages=%d | "
+                            "kernel %.1f us, reduce %.1f us | per-CTA kcycles: prod_wait_empty=%.1f mma_wait_full=%.1f mma_total=%.1f "
+                            "epilogue=%.1f cta_total=%.1f (n=%llu)\n",
+                    d->H, d->W, d->C0, d->C1, d->Cout, d->ksize, d->stride, batch.n, p.TR, p.RG, pgroups, psplits, p.tiles_per_cta,
+                    p.stages, t01 * 1e3, t12 * 1e3, hb[0] / n / 1e3, hb[1] / n / 1e3, hb[2] / n / 1e3, hb[3] / n / 1e3,
+                    hb[4] / n / 1e3, hb[5]);
+            for (auto &e : ev) cudaEventDestroy(e);
+        }
+        return RAMNET_OK;
     }
     WgGeom g;
     int splits_i, groups;

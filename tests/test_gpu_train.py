@@ -46,6 +46,8 @@ def _rel(a, b):
     (1, 10, 20, 32, 0, 64, 5, 1, 'relu'),      # tap-packed wgrad, M = dZ, ragged tiles in y and x
     (2, 6, 8, 64, 64, 160, 3, 1, 'relu'),      # two M blocks (the second one partial), virtual concat as the N operand
     (1, 12, 8, 160, 0, 32, 3, 1, 'relu'),      # M = X with a partial second block
+    (1, 16, 24, 64, 0, 32, 5, 2, 'relu'),      # stride 2, tap-packed per input parity class, M = parity plane of X
+    (2, 8, 16, 32, 0, 32, 3, 2, 'relu'),       # stride 2, 3x3: sub-filters 1x1 / 1x2 / 2x1 / 2x2
 ])
 def test_conv_backward_vs_torch(kind, shape):
     from rpg_ramnet_b200 import autograd as AG, ops
