@@ -187,6 +187,13 @@ int ramnet_head_conv_wgrad(ramnet_handle *h, const float *x_nchw, const float *d
                            float *db, int N, int Cin, int H, int W, int Cout, void *stream);
 int ramnet_pack_weights_dgrad(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin,
                               int ksize, int mma_kind, int ci_begin, int ci_count, void *stream);
+/* Sub-pixel data gradient of a stride-2 conv (TF32 path): dX [N, H, W, ci_count] from dZ [N, H/2, W/2, Cout] as four
+ * stride-1 convolutions of dZ, one per input-pixel parity, with the 3x3 / 3x2 / 2x3 / 2x2 (5x5) sub-filters that
+ * ramnet_pack_weights_dgrad_s2 lays out back to back -- no zero insertion, a quarter of its MACs. */
+int ramnet_pack_weights_dgrad_s2(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin,
+                                 int ksize, int ci_begin, int ci_count, void *stream);
+int ramnet_conv_dgrad_s2(ramnet_handle *h, const float *dz, const float *w_packed_s2, float *dx, int N, int H,
+                         int W, int Cout, int ci_count, int ksize, int flags, void *stream);
 /* y[n, 2h, 2w, :] = x[n, h, w, :] (+ skip), zeros elsewhere: input of a stride-2 conv's data gradient and of the
  * TransposedConvLayer decoder (submodules.py:38-66; skip = statenet.py:306-308's skip sum). */
 int ramnet_zero_insert2x(ramnet_handle *h, const float *x, const float *skip, float *y, int N, int H, int W, int C,

@@ -37,12 +37,40 @@ class HeadConvFn(torch.autograd.Function):
         return None, dw, db, None
 
 
+# Data-gradient weight packs live on the parameter object itself and are rebuilt when it changes (same token as
+# engine.WeightCache: in-place version counter + the epoch the fused Adam bumps).  BPTT calls every layer's backward
+# L*(K+1) times per step with the same weights, so all but the first call reuse the pack.  (Keyed on the object, not
+# on data_ptr: a new tensor that recycles a freed address must never see a stale pack.)
+def _cached_pack(weight, tag, builder):
+    from . import engine
+    tok = (weight.data_ptr(), weight._version, engine._WEIGHT_EPOCH)
+    packs = getattr(weight, '_ramnet_dgrad_packs', None)
+    if packs is None:
+        packs = {}
+        try:
+            weight._ramnet_dgrad_packs = packs
+        except AttributeError:
+            return builder()
+    hit = packs.get(tag)
+    if hit is not None and hit[0] == tok:
+        return hit[1]
+    packed = builder()
+    packs[tag] = (tok, packed)
+    return packed
+
+
 def _dgrad(dz, weight, kind, stride, ci_begin, ci_count, in_hw):
     """Data gradient w.r.t. input channels [ci_begin, ci_begin+ci_count) of a conv with nn.Conv2d weight `weight`."""
-    k = weight.shape[2]
-    wp = ops.pack_weights_dgrad(weight, kind, ci_begin, ci_count)
+    Cout, _, k, _ = weight.shape
+    H, W = int(in_hw[0]), int(in_hw[1])
+    if (stride == 2 and kind == ops.MMA_TF32 and k in (3, 5) and H % 2 == 0 and W % 2 == 0 and Cout % 32 == 0
+            and ci_count % 32 == 0):
+        # sub-pixel decomposition: four stride-1 convolutions of dZ, one per input parity (no zero insertion)
+        wp = _cached_pack(weight, ('s2', ci_begin, ci_count), lambda: ops.pack_weights_dgrad_s2(weight, ci_begin, ci_count))
+        return ops.conv_dgrad_s2(dz, wp, ci_count, k, H, W)
+    wp = _cached_pack(weight, (kind, ci_begin, ci_count), lambda: ops.pack_weights_dgrad(weight, kind, ci_begin, ci_count))
     if stride == 2:
-        dz = ops.zero_insert2x(dz, in_hw[0], in_hw[1])
+        dz = ops.zero_insert2x(dz, H, W)
     return ops.conv_fwd(dz, None, wp, None, ci_count, k, 1, ops.EPI_BIAS, kind)
 
 

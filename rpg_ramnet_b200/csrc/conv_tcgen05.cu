@@ -308,11 +308,21 @@ __global__ void __launch_bounds__(kThreads) conv_tcgen05_kernel(const __grid_con
 // the tcgen05.ld and the global aux loads (bias, h, u, c, residual) of chunk k+1 are in flight while
 // chunk k is computed and stored.
 // ================================================================================================
+// Optional generalisation of a stride-1 halo launch: a kh x kw tap set anchored at (lo_y, lo_x) and an output written
+// through a strided view (used by the sub-pixel data gradient of stride-2 convolutions: one launch per input parity).
+struct RectSpec {
+    int kh, kw, lo_y, lo_x;
+    int out_sy, out_sx, out_oy, out_ox, out_H, out_W;
+};
+
 struct HaloGeom {
     int N, H, W, Cout;       // input height / width
     int Ho, Wo;              // output height / width
     int C0, C1;
     int ks, pad, stride;
+    int kh, kw;              // taps along y / x (ks x ks unless a RectSpec narrows a stride-1 launch)
+    int lo_y, lo_x;          // stride 1: offset of tap (0, 0) relative to the output pixel (-pad for a centred filter)
+    int out_sy, out_sx, out_oy, out_ox, out_H, out_W;   // output pixel (oy, ox) lands at (oy*out_sy + out_oy, ox*out_sx + out_ox)
     int nplanes;             // 1 (stride 1) or 4 (stride 2: input parity planes (py, px))
     int plane_stride;        // bytes between parity planes inside one halo stage (multiple of 1024)
     int lo;                  // first halo row/column relative to the patch origin (floor(-pad/stride))
@@ -491,7 +501,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
     pdl_launch_dependents();
     const int ntiles = g.PTX * g.PTY;
     const int chunks0 = g.C0 / kChunk, chunks = (g.C0 + g.C1) / kChunk;
-    const int taps = g.ks * g.ks;
+    const int taps = g.kh * g.kw;
     const int patches = g.patches_x * g.patches_y * g.N;
     const int acc_cols = ntiles * g.BN;          // TMEM columns of one accumulator buffer
     uint32_t tmem_cols = 32;
@@ -511,8 +521,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
     if (warp == 3) {
         // tap (r, s) -> where its A tile starts inside a halo stage.  Stride 1: one plane, shift (r, s).
         // Stride 2: input row 2*oy + (r - pad) = 2*(oy + dy) + py -> parity plane (py, px), shift (dy, dx).
-        if (lane < g.ks * g.ks) {
-            const int r = lane / g.ks, sx = lane % g.ks;
+        if (lane < g.kh * g.kw) {
+            const int r = lane / g.kw, sx = lane % g.kw;
             int off;
             if (g.stride == 1) {
                 off = (r * g.HX + sx) * 8;
@@ -577,7 +587,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
                     const int c = (second ? ch - chunks0 : ch) * kChunk;
                     uint8_t *dst = smem + (size_t)stage * a_stride;
                     if (g.stride == 1) {
-                        halo_tma_4d<PAIR>(dst, mx, a_full + stage, c, x0 + g.lo, y0 + g.lo, img);
+                        halo_tma_4d<PAIR>(dst, mx, a_full + stage, c, x0 + g.lo_x, y0 + g.lo_y, img);
                     } else {
                         const int Csrc = second ? g.C1 : g.C0;
 #pragma unroll
@@ -636,8 +646,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
             for (int ch = 0; ch < chunks; ++ch) {
                 mbar_wait_t(a_full + sa, pa, prof, w0);
                 const uint32_t a16 = (smem_u32(smem + (size_t)sa * a_stride) & 0x3FFFFu) >> 4;
-                for (int r = 0, tap = 0; r < g.ks; ++r) {
-                    for (int sx = 0; sx < g.ks; ++sx, ++tap) {
+                for (int r = 0, tap = 0; r < g.kh; ++r) {
+                    for (int sx = 0; sx < g.kw; ++sx, ++tap) {
                         // One barrier round trip (~100+ cycles even when complete) tells us about EVERY weight stage:
                         // lane i polls the stage i slots ahead; the ballot gives the run of ready stages.
                         if (ready == 0) {
@@ -714,7 +724,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
                 u.tl = tl; u.j = j;
                 const int ox = x0 + (tl & (g.PTX - 1)) * 8 + (row & 7), oy = y0 + (tl >> g.ptx_log2) * 16 + (row >> 3);
                 u.valid = oy < g.Ho && ox < g.Wo && img < g.N;
-                u.m = ((int64_t)img * g.Ho + oy) * g.Wo + ox;
+                u.m = ((int64_t)img * g.out_H + oy * g.out_sy + g.out_oy) * g.out_W + ox * g.out_sx + g.out_ox;
                 u.col = (half + kParts * j) * 16;
                 return u;
             };
@@ -743,7 +753,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
                             }
                         }
                         if (oy < g.Ho && ox < g.Wo && img < g.N) {
-                            const int64_t m = ((int64_t)img * g.Ho + oy) * g.Wo + ox;
+                            const int64_t m = ((int64_t)img * g.out_H + oy * g.out_sy + g.out_oy) * g.out_W + ox * g.out_sx + g.out_ox;
                             const float logit = dot + __ldg(ep.aux1);
                             if (ep.y1) ep.y1[m] = logit;
                             ep.y0[m] = sigmoidf_(logit);
@@ -1356,7 +1366,8 @@ int halo_mode_env() {
     return mode;
 }
 
-bool fill_halo(const ramnet_conv_desc *d, HaloGeom *g, int ptx, int pty, int bn, int a_st, int b_st, int pair = 0) {
+bool fill_halo(const ramnet_conv_desc *d, const RectSpec *rect, HaloGeom *g, int ptx, int pty, int bn, int a_st, int b_st,
+               int pair = 0) {
     if (d->Cout % bn || ptx * pty > 4 || ptx * pty * bn > 512 || (ptx & (ptx - 1))) return false;
     if (pair && (bn % 16 || bn < 32)) return false;          // cta_group::2: N in steps of 16; each CTA stages bn/2 rows
     g->pair = pair;
@@ -1370,6 +1381,15 @@ bool fill_halo(const ramnet_conv_desc *d, HaloGeom *g, int ptx, int pty, int bn,
     const int hi = fdiv(d->ksize - 1 - g->pad, d->stride);
     g->PTX = ptx; g->PTY = pty; g->ptx_log2 = ptx == 4 ? 2 : (ptx == 2 ? 1 : 0);
     g->HX = ptx * 8 + (hi - g->lo); g->HY = pty * 16 + (hi - g->lo);
+    g->kh = g->kw = d->ksize; g->lo_y = g->lo_x = g->lo;
+    g->out_sy = g->out_sx = 1; g->out_oy = g->out_ox = 0; g->out_H = g->Ho; g->out_W = g->Wo;
+    if (rect) {               // stride-1 launch with a rectangular tap set and / or a strided output view
+        if (d->stride != 1) return false;
+        g->kh = rect->kh; g->kw = rect->kw; g->lo_y = rect->lo_y; g->lo_x = rect->lo_x;
+        g->out_sy = rect->out_sy; g->out_sx = rect->out_sx; g->out_oy = rect->out_oy; g->out_ox = rect->out_ox;
+        g->out_H = rect->out_H; g->out_W = rect->out_W;
+        g->HX = ptx * 8 + rect->kw - 1; g->HY = pty * 16 + rect->kh - 1;
+    }
     if (g->HX > 256 || g->HY > 256) return false;
     g->BN = bn; g->n_slices = d->Cout / bn;
     g->patches_x = (g->Wo + ptx * 8 - 1) / (ptx * 8); g->patches_y = (g->Ho + pty * 16 - 1) / (pty * 16);
@@ -1403,7 +1423,7 @@ bool fill_halo(const ramnet_conv_desc *d, HaloGeom *g, int ptx, int pty, int bn,
 //  - the epilogue is hidden under the next item when TMEM is double-buffered;
 //  - persistent scheduling => ceil(items / SMs) rounds.
 double halo_cost(const ramnet_handle *h, const ramnet_conv_desc *d, const HaloGeom &g) {
-    const int ntiles = g.PTX * g.PTY, chunks = (d->C0 + d->C1) / kChunk, taps = d->ksize * d->ksize;
+    const int ntiles = g.PTX * g.PTY, chunks = (d->C0 + d->C1) / kChunk, taps = g.kh * g.kw;
     const double halo_bytes = (double)g.nplanes * g.HX * g.HY * 128.0;
     const double bn_l = g.pair ? g.BN / 2.0 : (double)g.BN;     // weight rows read from / written to THIS SM's shared memory
     const double smem_tap = (ntiles * 4.0 * (128 + bn_l) * 32.0 + bn_l * 128.0 + halo_bytes / taps) / 128.0;
@@ -1421,13 +1441,13 @@ double halo_cost(const ramnet_handle *h, const ramnet_conv_desc *d, const HaloGe
 
 // Chooses patch shape, BN and pipeline depths for the halo kernel; returns false when the layer
 // should stay on the per-tap kernel (stride 2, 1x1, or no configuration fits shared memory).
-bool plan_halo(const ramnet_handle *h, const ramnet_conv_desc *d, HaloGeom *g) {
-    if (halo_mode_env() & 4) return false;           // RAMNET_HALO_MODE=4: force the per-tap kernel (A/B tests)
-    if (d->ksize == 1) return false;
+bool plan_halo(const ramnet_handle *h, const ramnet_conv_desc *d, const RectSpec *rect, HaloGeom *g) {
+    if ((halo_mode_env() & 4) && !rect) return false;   // RAMNET_HALO_MODE=4: force the per-tap kernel (A/B tests)
+    if (d->ksize == 1 && !rect) return false;
     if (d->stride == 2 && ((d->H | d->W) & 1)) return false;
     if (const char *f = getenv("RAMNET_HALO_FORCE")) {   // tuning aid: "PTX,PTY,BN,a_stages,b_stages[,pair]"
         int ptx, pty, bn, ast, bst, pr = 0;
-        if (sscanf(f, "%d,%d,%d,%d,%d,%d", &ptx, &pty, &bn, &ast, &bst, &pr) >= 5 && fill_halo(d, g, ptx, pty, bn, ast, bst, pr))
+        if (sscanf(f, "%d,%d,%d,%d,%d,%d", &ptx, &pty, &bn, &ast, &bst, &pr) >= 5 && fill_halo(d, rect, g, ptx, pty, bn, ast, bst, pr))
             return true;
     }
     // RAMNET_PAIR: 0 = single-CTA MMAs only, 1 (default) = cost model decides, 2 = CTA pairs wherever a configuration fits
@@ -1439,7 +1459,7 @@ bool plan_halo(const ramnet_handle *h, const ramnet_conv_desc *d, HaloGeom *g) {
         for (const auto &sh : shapes)
             for (int bn = 256; bn >= 16; bn >>= 1) {
                 if (d->epilogue == RAMNET_EPI_BIAS_RELU_PRED && bn != d->Cout) continue;   // one slice: whole-row reduction
-                if (!fill_halo(d, &cand, sh[0], sh[1], bn, 0, 0, pair)) continue;
+                if (!fill_halo(d, rect, &cand, sh[0], sh[1], bn, 0, 0, pair)) continue;
                 const double c = halo_cost(h, d, cand);
                 if (best < 0 || c < best) { best = c; *g = cand; }
             }
@@ -1447,7 +1467,7 @@ bool plan_halo(const ramnet_handle *h, const ramnet_conv_desc *d, HaloGeom *g) {
         for (const auto &sh : shapes)
             for (int bn = 256; bn >= 16; bn >>= 1) {
                 if (d->epilogue == RAMNET_EPI_BIAS_RELU_PRED && bn != d->Cout) continue;
-                if (!fill_halo(d, &cand, sh[0], sh[1], bn, 0, 0, 0)) continue;
+                if (!fill_halo(d, rect, &cand, sh[0], sh[1], bn, 0, 0, 0)) continue;
                 const double c = halo_cost(h, d, cand);
                 if (best < 0 || c < best) { best = c; *g = cand; }
             }
@@ -1915,15 +1935,25 @@ int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz
 
 size_t conv_tf32_workspace_bytes(const ramnet_conv_desc *) { return 0; }
 
+int conv_fwd_tf32_rect(ramnet_handle *h, const ramnet_conv_desc *d, const RectSpec *rect, const float *x0, const float *x1,
+                       const float *wp, const EpiParams &ep, cudaStream_t s);
+
 int conv_fwd_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *x0, const float *x1, const float *wp,
                   const EpiParams &ep, void *, size_t, cudaStream_t s) {
+    return conv_fwd_tf32_rect(h, d, nullptr, x0, x1, wp, ep, s);
+}
+
+int conv_fwd_tf32_rect(ramnet_handle *h, const ramnet_conv_desc *d, const RectSpec *rect, const float *x0, const float *x1,
+                       const float *wp, const EpiParams &ep, cudaStream_t s) {
     RAMNET_CHECK_ARG(d->C0 % kChunk == 0 && d->C1 % kChunk == 0,
                      "conv_fwd(tf32): C0=%d, C1=%d must be multiples of 32 (one 128-byte swizzle row)", d->C0, d->C1);
     RAMNET_CHECK_ARG(d->Cout % 16 == 0, "conv_fwd(tf32): Cout=%d must be a multiple of 16", d->Cout);
     RAMNET_CHECK_ARG(d->stride == 1 || (d->H % 2 == 0 && d->W % 2 == 0), "conv_fwd(tf32): stride 2 needs even H, W");
     RAMNET_CHECK_ARG((((uintptr_t)x0 | (uintptr_t)x1 | (uintptr_t)wp) & 15) == 0, "conv_fwd(tf32): 16-byte alignment");
     HaloGeom hg;
-    const bool halo_ok = plan_halo(h, d, &hg);
+    const bool halo_ok = plan_halo(h, d, rect, &hg);
+    if (!halo_ok && rect)
+        return ramnet_set_error(RAMNET_EUNSUPPORTED, "conv_fwd: no halo-kernel configuration for a rectangular / strided launch");
     if (!halo_ok && d->epilogue == RAMNET_EPI_BIAS_RELU_PRED)
         return ramnet_set_error(RAMNET_EUNSUPPORTED, "conv_fwd: no halo-kernel configuration for the fused prediction epilogue");
     if (halo_ok) {
@@ -1954,7 +1984,7 @@ int conv_fwd_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *x0, 
         } else {
             m1 = m0;
         }
-        const int Ct = d->C0 + d->C1, taps = d->ksize * d->ksize;
+        const int Ct = d->C0 + d->C1, taps = hg.kh * hg.kw;
         cuuint64_t wd[3] = {(cuuint64_t)Ct, (cuuint64_t)d->Cout, (cuuint64_t)taps};
         cuuint64_t ws[2] = {(cuuint64_t)Ct * 4, (cuuint64_t)Ct * d->Cout * 4};
         cuuint32_t wb[3] = {kChunk, (cuuint32_t)(hg.pair ? hg.BN / 2 : hg.BN), 1};
@@ -2020,4 +2050,90 @@ int conv_fwd_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *x0, 
         case RAMNET_EPI_LSTM: return launch<RAMNET_EPI_LSTM>(h, m0, m1, mw, g, ep, s);
     }
     return ramnet_set_error(RAMNET_EINVAL, "conv_fwd(tf32): unreachable");
+}
+
+
+// ================================================================================================
+// Sub-pixel data gradient of a stride-2 convolution (replaces zero insertion + a full-resolution conv, which spends
+// 4x the MACs on inserted zeros).  dX[y][x] = sum_{r,s} dZ[(y + pad - r)/2][(x + pad - s)/2] W[r][s] over the taps
+// for which the divisions are exact: with y = 2y' + py and r - pad = 2dy + py, the input pixels of row parity py see
+// only the filter rows {r : (r - pad) mod 2 = py} and dX_py[y'] = sum_dy dZ[y' - dy] W[r(dy)].  Each of the 4 input
+// parities is therefore a stride-1 convolution of dZ with a 3x3 / 3x2 / 2x3 / 2x2 sub-filter (5x5, pad 2) whose output
+// is written into one parity plane of dX: four halo-kernel launches with a RectSpec.
+// ================================================================================================
+namespace {
+struct S2Axis { int k[2], rmin[2], dmin[2]; };
+__host__ __device__ inline S2Axis s2_axis(int ks) {
+    S2Axis a;
+    const int pad = ks / 2;
+    for (int q = 0; q < 2; ++q) {
+        a.rmin[q] = (pad + q) & 1;
+        a.k[q] = (ks - 1 - a.rmin[q]) / 2 + 1;
+        const int e = a.rmin[q] - pad - q;               // even
+        a.dmin[q] = e >= 0 ? e / 2 : -((-e) / 2);
+    }
+    return a;
+}
+
+// w_oihw [Cout][Cin][ks][ks] -> for class c = py*2+px: [tap (a, b)][ci_count][Cout] (K-major B operand of the data
+// gradient GEMM, K = Cout), Wsub[a][b] = W[rmin_py + 2(kh-1-a)][rmin_px + 2(kw-1-b)], classes back to back.
+__global__ void pack_dgrad_s2_kernel(const float *__restrict__ w, float *__restrict__ out, int Cout, int Cin, int ks,
+                                     int ci_begin, int ci_count) {
+    const S2Axis ax = s2_axis(ks);
+    const int taps = ks * ks;
+    const int64_t per_tap = (int64_t)ci_count * Cout, total = per_tap * taps;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int t = (int)(i / per_tap);                       // tap index in the concatenated class order
+        const int64_t rem = i - (int64_t)t * per_tap;
+        const int cil = (int)(rem / Cout), co = (int)(rem % Cout);
+        int cls = 0;
+        for (; cls < 4; ++cls) {
+            const int n = ax.k[cls >> 1] * ax.k[cls & 1];
+            if (t < n) break;
+            t -= n;
+        }
+        const int py = cls >> 1, px = cls & 1, kw = ax.k[px];
+        const int a = t / kw, b = t % kw;
+        const int r = ax.rmin[py] + 2 * (ax.k[py] - 1 - a), sx = ax.rmin[px] + 2 * (kw - 1 - b);
+        out[i] = round_tf32(w[((int64_t)co * Cin + ci_begin + cil) * taps + r * ks + sx]);
+    }
+}
+}  // namespace
+
+extern "C" int ramnet_pack_weights_dgrad_s2(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin,
+                                            int ksize, int ci_begin, int ci_count, void *stream) {
+    RAMNET_CHECK_ARG(h && w_oihw && w_packed && Cout > 0 && Cin > 0 && (ksize == 3 || ksize == 5) && ci_begin >= 0 &&
+                         ci_count > 0 && ci_begin + ci_count <= Cin,
+                     "pack_weights_dgrad_s2: bad argument");
+    const int64_t total = (int64_t)Cout * ci_count * ksize * ksize;
+    const int blocks = (int)imin64((total + 255) / 256, (int64_t)h->sm_count * 8);
+    pack_dgrad_s2_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, w_packed, Cout, Cin, ksize, ci_begin, ci_count);
+    RAMNET_LAUNCH_CHECK(h);
+    return RAMNET_OK;
+}
+
+extern "C" int ramnet_conv_dgrad_s2(ramnet_handle *h, const float *dz, const float *w_packed_s2, float *dx, int N, int H,
+                                    int W, int Cout, int ci_count, int ksize, int flags, void *stream) {
+    RAMNET_CHECK_ARG(h && dz && w_packed_s2 && dx, "conv_dgrad_s2: NULL argument");
+    RAMNET_CHECK_ARG(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "conv_dgrad_s2: input H=%d, W=%d must be even", H, W);
+    RAMNET_CHECK_ARG((ksize == 3 || ksize == 5) && Cout % 32 == 0 && ci_count % 32 == 0,
+                     "conv_dgrad_s2: ksize 3/5, Cout and ci_count multiples of 32 (got k=%d, Cout=%d, ci_count=%d)", ksize, Cout, ci_count);
+    const S2Axis ax = s2_axis(ksize);
+    ramnet_conv_desc d;
+    memset(&d, 0, sizeof(d));
+    d.N = N; d.H = H / 2; d.W = W / 2; d.C0 = Cout; d.C1 = 0; d.Cout = ci_count; d.ksize = ksize; d.stride = 1;
+    d.epilogue = RAMNET_EPI_BIAS; d.mma_kind = RAMNET_MMA_TF32; d.flags = flags;
+    EpiParams ep{nullptr, nullptr, nullptr, dx, nullptr, nullptr, ci_count, flags};
+    const float *wp = w_packed_s2;
+    for (int cls = 0; cls < 4; ++cls) {
+        const int py = cls >> 1, px = cls & 1;
+        RectSpec r;
+        r.kh = ax.k[py]; r.kw = ax.k[px];
+        r.lo_y = -(ax.dmin[py] + r.kh - 1); r.lo_x = -(ax.dmin[px] + r.kw - 1);
+        r.out_sy = r.out_sx = 2; r.out_oy = py; r.out_ox = px; r.out_H = H; r.out_W = W;
+        const int rc = conv_fwd_tf32_rect(h, &d, &r, dz, nullptr, wp, ep, (cudaStream_t)stream);
+        if (rc) return rc;
+        wp += (size_t)r.kh * r.kw * ci_count * Cout;
+    }
+    return RAMNET_OK;
 }

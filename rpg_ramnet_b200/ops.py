@@ -269,6 +269,27 @@ def pack_weights_dgrad(w_oihw: torch.Tensor, mma_kind: int, ci_begin: int, ci_co
     return out
 
 
+def pack_weights_dgrad_s2(w_oihw: torch.Tensor, ci_begin: int, ci_count: int) -> torch.Tensor:
+    """Sub-filters of the four input parities of a stride-2 conv, for conv_dgrad_s2 (TF32 path)."""
+    w = w_oihw.detach().contiguous().float()
+    Cout, Cin, k, _ = w.shape
+    out = torch.empty(Cout * ci_count * k * k, dtype=torch.float32, device=w.device)
+    check(_lib.load().ramnet_pack_weights_dgrad_s2(_h(w), _p(w), _p(out), Cout, Cin, k, ci_begin, ci_count, _stream(w)))
+    return out
+
+
+def conv_dgrad_s2(dz, w_packed_s2, ci_count, ksize, H, W):
+    """Data gradient [N, ci_count, H, W] of a stride-2 conv from dz [N, Cout, H/2, W/2]: four sub-pixel convolutions."""
+    _check_nhwc(dz, 'conv_dgrad_s2 dz')
+    N, Cout, Ho, Wo = dz.shape
+    dx = empty_nhwc(N, ci_count, H, W, dz.device)
+    with _Prof('conv', 2.0 * N * Ho * Wo * Cout * ci_count * ksize * ksize, dz.device,
+               tag=PROFILE is not None and f'dgrad_s2 {H}x{W} {Cout}->{ci_count} k{ksize}'):
+        check(_lib.load().ramnet_conv_dgrad_s2(_h(dz), _p(dz), _p(w_packed_s2), _p(dx), N, H, W, Cout, ci_count, ksize, 0,
+                                               _stream(dz)))
+    return dx
+
+
 def conv_wgrad(dz, x0, x1, Cout, ksize, stride, dw, db, mma_kind=MMA_FP32):
     """dw [Cout, C0+C1, k, k] += , db [Cout] += ."""
     _check_nhwc(dz, 'conv_wgrad dz')
