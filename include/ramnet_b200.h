@@ -166,6 +166,17 @@ int ramnet_upsample2x_add(ramnet_handle *h, const float *x, const float *skip, f
 int ramnet_pred_sigmoid(ramnet_handle *h, const float *x, const float *skip, const float *w,
                         const float *bias, float *logits, float *depth, int64_t M, int C, void *stream);
 
+/* Tensor-core head conv (TF32 mode, 5*Cin <= 32): ramnet_head_im2row unrolls the five horizontal taps into a
+ * 32-channel NHWC tensor xe[n][y][x][dx*Cin + ci] = x[n][ci][y][x+dx-2]; ramnet_head_conv_tc then runs the remaining
+ * 5x1 conv (+bias, ReLU) on tcgen05 with ramnet_pack_weights_head weights.  Same reference call sites as
+ * ramnet_head_conv. */
+int ramnet_head_im2row(ramnet_handle *h, const float *x_nchw, float *xe_nhwc32, int N, int Cin, int H, int W,
+                       void *stream);
+int ramnet_pack_weights_head(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin,
+                             void *stream);
+int ramnet_head_conv_tc(ramnet_handle *h, const float *xe_nhwc32, const float *w_packed, const float *bias,
+                        float *y_nhwc, int N, int H, int W, int Cout, int flags, void *stream);
+
 /* ---- layout helpers ----------------------------------------------------- */
 int ramnet_nchw_to_nhwc(ramnet_handle *h, const float *x, float *y, int N, int C, int H, int W,
                         int flags, void *stream);
@@ -185,6 +196,12 @@ int ramnet_conv_wgrad(ramnet_handle *h, const ramnet_conv_desc *d, const float *
                       void *stream);
 int ramnet_head_conv_wgrad(ramnet_handle *h, const float *x_nchw, const float *dz_nhwc, float *dw_oihw,
                            float *db, int N, int Cin, int H, int W, int Cout, void *stream);
+/* Head conv weight gradient on the tensor cores (TF32 path): xe = ramnet_head_im2row's tensor, dw in the head's
+ * [Cout][Cin][5][5] layout (Cout % 32 == 0), accumulated (+=). */
+size_t ramnet_head_conv_wgrad_tc_workspace_bytes(const ramnet_handle *h, int N, int Cin, int H, int W, int Cout);
+int ramnet_head_conv_wgrad_tc(ramnet_handle *h, const float *xe_nhwc32, const float *dz_nhwc, float *dw_oihw,
+                              float *db, int N, int Cin, int H, int W, int Cout, void *workspace,
+                              size_t workspace_bytes, void *stream);
 int ramnet_pack_weights_dgrad(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin,
                               int ksize, int mma_kind, int ci_begin, int ci_count, void *stream);
 /* Sub-pixel data gradient of a stride-2 conv (TF32 path): dX [N, H, W, ci_count] from dZ [N, H/2, W/2, Cout] as four

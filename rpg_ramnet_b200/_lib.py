@@ -46,6 +46,13 @@ SIGNATURES = {
                                        c_int, c_void_p]),
     'ramnet_pack_weights_dgrad': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                           c_void_p]),
+    'ramnet_head_im2row': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'ramnet_pack_weights_head': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    'ramnet_head_conv_tc': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                    c_void_p]),
+    'ramnet_head_conv_wgrad_tc_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int, c_int, c_int]),
+    'ramnet_head_conv_wgrad_tc': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                          c_void_p, c_size_t, c_void_p]),
     'ramnet_pack_weights_dgrad_s2': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'ramnet_conv_dgrad_s2': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p]),

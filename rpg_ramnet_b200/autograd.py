@@ -21,7 +21,15 @@ class HeadConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, round_tf32):
-        y = ops.head_conv(x, weight.detach(), None if bias is None else bias.detach(), round_tf32)
+        Cout, Cin, k, _ = weight.shape
+        b = None if bias is None else bias.detach()
+        ctx.tc = bool(round_tf32) and k == 5 and ops.head_tc_ok(Cin, Cout)
+        if ctx.tc:      # TF32 mode: tensor-core path over the horizontally unrolled input (kept for the weight gradient)
+            x = ops.head_im2row(x)
+            wp = _cached_pack(weight, 'head', lambda: ops.pack_weights_head(weight))
+            y = ops.head_conv_tc(x, wp, b, Cin, Cout, True)
+        else:
+            y = ops.head_conv(x, weight.detach(), b, round_tf32)
         ctx.save_for_backward(x, y)
         ctx.has_bias = bias is not None
         ctx.wshape = weight.shape
@@ -30,10 +38,13 @@ class HeadConvFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, y = ctx.saved_tensors
-        dz = ops.relu_bwd(_nhwc(dy), y)
+        dz = ops.relu_bwd(_nhwc(dy), y, round_tf32=ctx.tc)
         dw = torch.zeros(ctx.wshape, dtype=torch.float32, device=y.device)
         db = torch.zeros(ctx.wshape[0], dtype=torch.float32, device=y.device) if ctx.has_bias else None
-        ops.head_conv_wgrad(x, dz, dw, db)
+        if ctx.tc:
+            ops.head_conv_wgrad_tc(x, dz, dw, db, ctx.wshape[1])
+        else:
+            ops.head_conv_wgrad(x, dz, dw, db)
         return None, dw, db, None
 
 

@@ -413,12 +413,41 @@ int grid_for(ramnet_handle *h, int64_t n) { return (int)imin64((n + 255) / 256, 
 }  // namespace
 
 int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz, const float *x0, const float *x1,
-                    float *dw, void *workspace, size_t workspace_bytes, cudaStream_t s);
-size_t conv_wgrad_tf32_workspace(const ramnet_handle *h, const ramnet_conv_desc *d);
+                    float *dw, void *workspace, size_t workspace_bytes, cudaStream_t s, int head_cin = 0);
+size_t conv_wgrad_tf32_workspace(const ramnet_handle *h, const ramnet_conv_desc *d, int head_cin = 0);
 
 extern "C" size_t ramnet_conv_wgrad_workspace_bytes(const ramnet_handle *h, const ramnet_conv_desc *d) {
     if (!h || !d || d->mma_kind != RAMNET_MMA_TF32) return 0;
     return conv_wgrad_tf32_workspace(h, d);
+}
+
+// Head conv weight gradient on the tensor cores: X is ramnet_head_im2row's unrolled tensor, so this is the tap-packed
+// wgrad of a 5x1 conv over 32 channels whose scatter writes the head's [Cout][Cin][5][5] layout.
+static ramnet_conv_desc head_wgrad_desc(int N, int H, int W, int Cout) {
+    ramnet_conv_desc d;
+    memset(&d, 0, sizeof(d));
+    d.N = N; d.H = H; d.W = W; d.C0 = 32; d.C1 = 0; d.Cout = Cout; d.ksize = 5; d.stride = 1;
+    d.epilogue = RAMNET_EPI_BIAS; d.mma_kind = RAMNET_MMA_TF32;
+    return d;
+}
+
+extern "C" size_t ramnet_head_conv_wgrad_tc_workspace_bytes(const ramnet_handle *h, int N, int Cin, int H, int W, int Cout) {
+    if (!h || Cin < 1 || 5 * Cin > 32 || Cout <= 0 || Cout % 32) return 0;
+    const ramnet_conv_desc d = head_wgrad_desc(N, H, W, Cout);
+    return conv_wgrad_tf32_workspace(h, &d, Cin);
+}
+
+extern "C" int ramnet_head_conv_wgrad_tc(ramnet_handle *h, const float *xe_nhwc32, const float *dz_nhwc, float *dw_oihw,
+                                         float *db, int N, int Cin, int H, int W, int Cout, void *workspace,
+                                         size_t workspace_bytes, void *stream) {
+    RAMNET_CHECK_ARG(h && xe_nhwc32 && dz_nhwc && dw_oihw, "head_conv_wgrad_tc: NULL argument");
+    RAMNET_CHECK_ARG(Cin >= 1 && 5 * Cin <= 32 && Cout > 0 && Cout % 32 == 0, "head_conv_wgrad_tc: needs 5*Cin <= 32 and Cout %% 32 == 0 (got %d, %d)", Cin, Cout);
+    if (db) {
+        launch_colsum(h, dz_nhwc, (int64_t)N * H * W, Cout, db, (cudaStream_t)stream);
+        RAMNET_LAUNCH_CHECK(h);
+    }
+    const ramnet_conv_desc d = head_wgrad_desc(N, H, W, Cout);
+    return conv_wgrad_tf32(h, &d, dz_nhwc, xe_nhwc32, nullptr, dw_oihw, workspace, workspace_bytes, (cudaStream_t)stream, Cin);
 }
 
 extern "C" int ramnet_conv_wgrad(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz, const float *x0,

@@ -1032,6 +1032,7 @@ struct WpGeom {
     int oy, ox;              // origin of the N box relative to the tile origin (before the row-group offset)
     int r0, dr, s0, ds;      // filter tap of (row shift u, N block j): (r0 + dr*u, s0 + ds*j)
     int x5d, py, px;         // stride 2: X is read through the 5-D parity view (2C, W/2, 2, H/2, N), plane (py, px)
+    int head_cin;            // > 0: X is ramnet_head_im2row's tensor (channel = dx*Cin + ci) and dW is the head's [Cout][Cin][5][5]
     int m_from_x;
     int Mch, Nch;            // channels of the M / N operand
     int m_blocks, n_boxes;   // ceil(Mch / 128), Nch / 32
@@ -1571,7 +1572,12 @@ __global__ void __launch_bounds__(1024) wgrad_packed_scatter_kernel(const float 
                         const int u = u0 + t / g.kw, j = t % g.kw;
                         const int tap = (g.r0 + g.dr * u) * g.ks + g.s0 + g.ds * j;
                         const int co = g.m_from_x ? nch : mch, ci = g.m_from_x ? mch : nch;
-                        addr[k] = ((int64_t)co * Ct + ci) * taps + tap;
+                        if (g.head_cin > 0) {          // unrolled head input: channel ci = dx*Cin + ci'
+                            const int dx = ci / g.head_cin, cih = ci - dx * g.head_cin;
+                            if (dx < 5) addr[k] = ((int64_t)co * g.head_cin + cih) * taps + tap + dx;
+                        } else {
+                            addr[k] = ((int64_t)co * Ct + ci) * taps + tap;
+                        }
                         v[k] = plane[t * kWpPitch + c32 * 33 + row];
                     }
                 }
@@ -1600,8 +1606,9 @@ int wgrad_packed_problems(const ramnet_conv_desc *d) {
 // r - pad = 2 dy + py the taps of one row parity py read the input parity plane P_py[y'][x'] = X[2 y' + py][..] at
 // oy + dy, i.e. a stride-1 problem between dZ and the plane with the sub-filter {r : (r - pad) mod 2 = py}.
 bool plan_wgrad_packed(const ramnet_handle *h, const ramnet_conv_desc *d, int cls, int nprob, WpGeom *gp, int *splits_out,
-                       int *groups_out) {
+                       int *groups_out, int head_cin = 0) {
     WpGeom &g = *gp;
+    g.head_cin = head_cin;
     g.N = d->N; g.Cout = d->Cout; g.C0 = d->C0; g.C1 = d->C1; g.ks = d->ksize;
     const int pad = d->ksize / 2, Ct = d->C0 + d->C1;
     g.m_from_x = Ct > d->Cout ? 1 : 0;                   // the operand with more channels fills the 128 MMA rows
@@ -1609,6 +1616,10 @@ bool plan_wgrad_packed(const ramnet_handle *h, const ramnet_conv_desc *d, int cl
         g.H = d->H; g.W = d->W; g.kh = g.kw = g.ks; g.x5d = 0; g.py = g.px = 0;
         if (g.m_from_x) { g.oy = g.ox = pad - (g.ks - 1); g.r0 = g.s0 = g.ks - 1; g.dr = g.ds = -1; }
         else { g.oy = g.ox = -pad; g.r0 = g.s0 = 0; g.dr = g.ds = 1; }
+        if (head_cin > 0) {   // horizontal taps already live in the channel axis: a ks x 1 problem, no x shift
+            if (g.m_from_x) return false;
+            g.kw = 1; g.ox = 0; g.s0 = 0; g.ds = 0;
+        }
     } else {
         g.H = d->H / 2; g.W = d->W / 2; g.x5d = 1; g.py = cls >> 1; g.px = cls & 1;
         // taps of parity q along one axis: r = rmin + 2 i, shifts dy = (r - pad - q) / 2 = dmin + i
@@ -1686,13 +1697,14 @@ bool plan_wgrad_packed(const ramnet_handle *h, const ramnet_conv_desc *d, int cl
 }
 
 // Plans every problem of a layer and unifies what the shared launch needs (N box, workspace pitch, pipeline depth).
-bool plan_wgrad_batch(const ramnet_handle *h, const ramnet_conv_desc *d, WpBatch *b, int *splits_out, int *groups_out) {
+bool plan_wgrad_batch(const ramnet_handle *h, const ramnet_conv_desc *d, WpBatch *b, int *splits_out, int *groups_out,
+                      int head_cin = 0) {
     b->n = wgrad_packed_problems(d);
     if (b->n == 0) return false;
     int splits = 0, groups = 0;
     for (int cls = 0; cls < b->n; ++cls) {
         int sp, gr;
-        if (!plan_wgrad_packed(h, d, cls, b->n, &b->g[cls], &sp, &gr)) return false;
+        if (!plan_wgrad_packed(h, d, cls, b->n, &b->g[cls], &sp, &gr, head_cin)) return false;
         if (cls == 0) { splits = sp; groups = gr; }
         else if (sp != splits || gr != groups || b->g[cls].tiles_per_cta != b->g[0].tiles_per_cta) return false;
     }
@@ -1720,12 +1732,13 @@ bool plan_wgrad_batch(const ramnet_handle *h, const ramnet_conv_desc *d, WpBatch
 
 bool plan_wgrad(const ramnet_handle *h, const ramnet_conv_desc *d, WgGeom *gp, int *splits_out, int *groups_out);
 
-size_t conv_wgrad_tf32_workspace(const ramnet_handle *h, const ramnet_conv_desc *d) {
+size_t conv_wgrad_tf32_workspace(const ramnet_handle *h, const ramnet_conv_desc *d, int head_cin) {
     int splits, groups;
     {
         WpBatch b;
-        if (plan_wgrad_batch(h, d, &b, &splits, &groups)) return (size_t)b.n * b.part_stride * sizeof(float);
+        if (plan_wgrad_batch(h, d, &b, &splits, &groups, head_cin)) return (size_t)b.n * b.part_stride * sizeof(float);
     }
+    if (head_cin > 0) return 0;
     WgGeom g;
     if (!plan_wgrad(h, d, &g, &splits, &groups)) return 0;
     return (size_t)splits * groups * 128 * g.T * g.BN * sizeof(float);
@@ -1793,11 +1806,11 @@ bool plan_wgrad(const ramnet_handle *h, const ramnet_conv_desc *d, WgGeom *gp, i
 }
 
 int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz, const float *x0, const float *x1,
-                    float *dw, void *workspace, size_t workspace_bytes, cudaStream_t s) {
+                    float *dw, void *workspace, size_t workspace_bytes, cudaStream_t s, int head_cin) {
     if ((((uintptr_t)dz | (uintptr_t)x0 | (uintptr_t)x1 | (uintptr_t)workspace) & 15) != 0) return RAMNET_EUNSUPPORTED;
     WpBatch batch;
     int psplits, pgroups;
-    if (plan_wgrad_batch(h, d, &batch, &psplits, &pgroups)) {
+    if (plan_wgrad_batch(h, d, &batch, &psplits, &pgroups, head_cin)) {
         const WpGeom &p = batch.g[0];
         const size_t need = (size_t)batch.n * batch.part_stride * sizeof(float);
         RAMNET_CHECK_ARG(workspace != nullptr && workspace_bytes >= need,
@@ -1892,6 +1905,7 @@ int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz
         }
         return RAMNET_OK;
     }
+    if (head_cin > 0) return RAMNET_EUNSUPPORTED;
     WgGeom g;
     int splits_i, groups;
     if (!plan_wgrad(h, d, &g, &splits_i, &groups)) return RAMNET_EUNSUPPORTED;
@@ -2136,4 +2150,106 @@ extern "C" int ramnet_conv_dgrad_s2(ramnet_handle *h, const float *dz, const flo
         wp += (size_t)r.kh * r.kw * ci_count * Cout;
     }
     return RAMNET_OK;
+}
+
+
+// ================================================================================================
+// Head convolution on the tensor cores (TF32 mode, 5*Cin <= 32).
+// The raw network input is NCHW with 1..6 channels: no 32-channel pixel rows for TMA / UMMA.  ramnet_head_im2row
+// unrolls the five HORIZONTAL taps into the channel axis, Xe[n][y][x][dx*Cin + ci] = X[n][ci][y][x + dx - 2] (zero
+// outside, zero-padded to 32 channels, rounded to TF32), which turns the 5x5 conv into a 5x1 conv over a 32-channel NHWC
+// tensor: the halo kernel with a RectSpec {kh = 5, kw = 1}, K = 5 * 32, weights [r][co][dx*Cin + ci].  The unrolled
+// tensor costs one extra 128 B/pixel write + read, far less than the fp32 FFMA pipe the direct kernel is bound by.
+// ================================================================================================
+namespace {
+template <int CIN>
+__global__ void __launch_bounds__(256) head_im2row_kernel(const float *__restrict__ x, float *__restrict__ xe, int N, int H,
+                                                          int W) {
+    __shared__ float tile[8][32][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wtiles = (W + 31) / 32;
+    const int64_t ntile = (int64_t)N * H * wtiles;
+    for (int c = 5 * CIN; c < 32; ++c) tile[warp][lane][c] = 0.f;      // channel padding: written once
+    for (int64_t t = (int64_t)blockIdx.x * 8 + warp; t < ntile; t += (int64_t)gridDim.x * 8) {
+        const int xt = (int)(t % wtiles);
+        const int y = (int)((t / wtiles) % H);
+        const int n = (int)(t / ((int64_t)wtiles * H));
+        const int px = xt * 32 + lane;
+        const float *row = x + ((int64_t)n * CIN * H + y) * W;          // channel ci of this image row: row + ci*H*W
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) {
+            const int sx = px + dx - 2;
+            const bool ok = sx >= 0 && sx < W;
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci)
+                tile[warp][lane][dx * CIN + ci] = ok ? round_tf32(__ldg(row + (int64_t)ci * H * W + sx)) : 0.f;
+        }
+        __syncwarp();
+        float4 *dst = reinterpret_cast<float4 *>(xe + (((int64_t)n * H + y) * W + (int64_t)xt * 32) * 32);
+        const int npx = min(32, W - xt * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int f = i * 32 + lane, p = f >> 3, q = f & 7;      // 16-byte piece q of pixel p: 512 contiguous bytes per store
+            if (p < npx) dst[f] = make_float4(tile[warp][p][4 * q], tile[warp][p][4 * q + 1], tile[warp][p][4 * q + 2],
+                                              tile[warp][p][4 * q + 3]);
+        }
+        __syncwarp();
+    }
+}
+
+// w_oihw [Cout][Cin][5][5] -> [r][Cout][32] with column dx*Cin + ci (K-major B operand), TF32-rounded, zero-padded
+__global__ void pack_head_kernel(const float *__restrict__ w, float *__restrict__ out, int Cout, int Cin) {
+    const int total = 5 * Cout * 32;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c = i & 31, co = (i >> 5) % Cout, r = i / (32 * Cout);
+        float v = 0.f;
+        if (c < 5 * Cin) {
+            const int dx = c / Cin, ci = c - dx * Cin;
+            v = round_tf32(w[(((int64_t)co * Cin + ci) * 5 + r) * 5 + dx]);
+        }
+        out[i] = v;
+    }
+}
+}  // namespace
+
+extern "C" int ramnet_head_im2row(ramnet_handle *h, const float *x_nchw, float *xe_nhwc32, int N, int Cin, int H, int W,
+                                  void *stream) {
+    RAMNET_CHECK_ARG(h && x_nchw && xe_nhwc32 && N > 0 && H > 0 && W > 0, "head_im2row: bad argument");
+    RAMNET_CHECK_ARG(Cin >= 1 && 5 * Cin <= 32, "head_im2row: 5*Cin = %d must fit one 32-channel pixel row", 5 * Cin);
+    const int64_t ntile = (int64_t)N * H * ((W + 31) / 32);
+    const int blocks = (int)imin64((ntile + 7) / 8, (int64_t)h->sm_count * 8);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (Cin) {
+        case 1: head_im2row_kernel<1><<<blocks, 256, 0, s>>>(x_nchw, xe_nhwc32, N, H, W); break;
+        case 2: head_im2row_kernel<2><<<blocks, 256, 0, s>>>(x_nchw, xe_nhwc32, N, H, W); break;
+        case 3: head_im2row_kernel<3><<<blocks, 256, 0, s>>>(x_nchw, xe_nhwc32, N, H, W); break;
+        case 4: head_im2row_kernel<4><<<blocks, 256, 0, s>>>(x_nchw, xe_nhwc32, N, H, W); break;
+        case 5: head_im2row_kernel<5><<<blocks, 256, 0, s>>>(x_nchw, xe_nhwc32, N, H, W); break;
+        default: head_im2row_kernel<6><<<blocks, 256, 0, s>>>(x_nchw, xe_nhwc32, N, H, W); break;
+    }
+    RAMNET_LAUNCH_CHECK(h);
+    return RAMNET_OK;
+}
+
+extern "C" int ramnet_pack_weights_head(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin,
+                                        void *stream) {
+    RAMNET_CHECK_ARG(h && w_oihw && w_packed && Cout > 0 && Cin >= 1 && 5 * Cin <= 32, "pack_weights_head: bad argument");
+    pack_head_kernel<<<(5 * Cout * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w_oihw, w_packed, Cout, Cin);
+    RAMNET_LAUNCH_CHECK(h);
+    return RAMNET_OK;
+}
+
+extern "C" int ramnet_head_conv_tc(ramnet_handle *h, const float *xe_nhwc32, const float *w_packed, const float *bias,
+                                   float *y_nhwc, int N, int H, int W, int Cout, int flags, void *stream) {
+    RAMNET_CHECK_ARG(h && xe_nhwc32 && w_packed && y_nhwc && N > 0 && H > 0 && W > 0, "head_conv_tc: bad argument");
+    RAMNET_CHECK_ARG(Cout > 0 && Cout % 32 == 0, "head_conv_tc: Cout=%d must be a multiple of 32", Cout);
+    ramnet_conv_desc d;
+    memset(&d, 0, sizeof(d));
+    d.N = N; d.H = H; d.W = W; d.C0 = 32; d.C1 = 0; d.Cout = Cout; d.ksize = 5; d.stride = 1;
+    d.epilogue = RAMNET_EPI_BIAS_RELU; d.mma_kind = RAMNET_MMA_TF32; d.flags = flags;
+    RectSpec r;
+    r.kh = 5; r.kw = 1; r.lo_y = -2; r.lo_x = 0;
+    r.out_sy = r.out_sx = 1; r.out_oy = r.out_ox = 0; r.out_H = H; r.out_W = W;
+    EpiParams ep{bias, nullptr, nullptr, y_nhwc, nullptr, nullptr, Cout, flags};
+    return conv_fwd_tf32_rect(h, &d, &r, xe_nhwc32, nullptr, w_packed, ep, (cudaStream_t)stream);
 }

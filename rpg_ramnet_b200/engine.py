@@ -111,15 +111,17 @@ def pack_conv(cache: WeightCache, key, conv, kind: int, norm_mod=None, norm_kind
     return cache.get(key, [conv.weight, conv.bias] + _norm_sources(norm_mod), (kind, training), build)
 
 
-def pack_head(cache: WeightCache, key, conv) -> Packed:
+def pack_head(cache: WeightCache, key, conv, tc: bool = False) -> Packed:
     """Head conv keeps nn.Conv2d's [Cout,Cin,5,5] layout (ramnet_head_conv reads it directly)."""
     def build():
         p = Packed()
         p.w = conv.weight.detach().float().contiguous()
         p.b = None if conv.bias is None else conv.bias.detach().float().contiguous()
         p.Cout, p.ksize, p.stride = conv.weight.shape[0], conv.weight.shape[2], 1
+        if tc:      # tensor-core path: [r][Cout][dx*Cin + ci]
+            p.w = ops.pack_weights_head(p.w)
         return p
-    return cache.get(key, [conv.weight, conv.bias], (), build)
+    return cache.get(key, [conv.weight, conv.bias], (tc,), build)
 
 
 def pack_gru(cache: WeightCache, key, gru, kind: int):
@@ -200,6 +202,10 @@ def head_layer(cache, key, conv, x, tf32):
     if needs_grad(conv.weight, conv.bias):
         from .autograd import HeadConvFn
         return HeadConvFn.apply(x.float().contiguous(), conv.weight, conv.bias, tf32)
+    Cout, Cin = conv.weight.shape[0], conv.weight.shape[1]
+    if tf32 and conv.weight.shape[2] == 5 and ops.head_tc_ok(Cin, Cout):
+        hp = pack_head(cache, key, conv, tc=True)
+        return ops.head_conv_tc(ops.head_im2row(x.float()), hp.w, hp.b, Cin, Cout, round_tf32=True)
     hp = pack_head(cache, key, conv)
     return ops.head_conv(x.float(), hp.w, hp.b, round_tf32=tf32)
 

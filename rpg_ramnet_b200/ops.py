@@ -5,6 +5,7 @@ strides, i.e. the memory is NHWC as include/ramnet_b200.h specifies.  PyTorch is
 memory and streams only.
 """
 import ctypes
+import os
 from typing import Optional
 
 import torch
@@ -106,6 +107,40 @@ def head_conv(x_nchw: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], 
     with _Prof('head_conv', 2.0 * N * H * W * Cout * Cin * 25, x.device):
         check(_lib.load().ramnet_head_conv(_h(x), _p(x), _p(w), _p(b), _p(y), N, Cin, H, W, Cout,
                                            FLAG_ROUND_TF32 if round_tf32 else 0, _stream(x)))
+    return y
+
+
+def head_tc_ok(Cin: int, Cout: int) -> bool:
+    """The tensor-core head path covers 5*Cin <= 32 (Cin <= 6: every shipped configuration) and Cout % 32 == 0."""
+    return 5 * Cin <= 32 and Cout % 32 == 0 and os.environ.get('RAMNET_HEAD_TC', '1') != '0'
+
+
+def pack_weights_head(w_oihw: torch.Tensor) -> torch.Tensor:
+    w = w_oihw.detach().contiguous().float()
+    Cout, Cin = w.shape[0], w.shape[1]
+    out = torch.empty(5 * Cout * 32, dtype=torch.float32, device=w.device)
+    check(_lib.load().ramnet_pack_weights_head(_h(w), _p(w), _p(out), Cout, Cin, _stream(w)))
+    return out
+
+
+def head_im2row(x_nchw: torch.Tensor) -> torch.Tensor:
+    """[N, Cin, H, W] -> NHWC [N, 32, H, W]: channel dx*Cin + ci holds x[ci] shifted by dx - 2 (TF32-rounded)."""
+    x = x_nchw.contiguous()
+    N, Cin, H, W = x.shape
+    xe = empty_nhwc(N, 32, H, W, x.device)
+    with _Prof('head_conv', 0.0, x.device):
+        check(_lib.load().ramnet_head_im2row(_h(x), _p(x), _p(xe), N, Cin, H, W, _stream(x)))
+    return xe
+
+
+def head_conv_tc(xe: torch.Tensor, w_packed: torch.Tensor, b: Optional[torch.Tensor], Cin: int, Cout: int,
+                 round_tf32: bool) -> torch.Tensor:
+    _check_nhwc(xe, 'head_conv_tc xe')
+    N, _, H, W = xe.shape
+    y = empty_nhwc(N, Cout, H, W, xe.device)
+    with _Prof('head_conv', 2.0 * N * H * W * Cout * Cin * 25, xe.device):
+        check(_lib.load().ramnet_head_conv_tc(_h(xe), _p(xe), _p(w_packed), _p(b), _p(y), N, H, W, Cout,
+                                              FLAG_ROUND_TF32 if round_tf32 else 0, _stream(xe)))
     return y
 
 
@@ -312,6 +347,20 @@ def head_conv_wgrad(x_nchw, dz, dw, db):
     _check_nhwc(dz, 'head_conv_wgrad dz')
     with _Prof('head_wgrad', 2.0 * N * H * W * dz.shape[1] * Cin * 25, x.device):
         check(_lib.load().ramnet_head_conv_wgrad(_h(x), _p(x), _p(dz), _p(dw), _p(db), N, Cin, H, W, dz.shape[1], _stream(x)))
+
+
+def head_conv_wgrad_tc(xe, dz, dw, db, Cin):
+    """Head conv weight gradient from the unrolled input (head_im2row): dw [Cout, Cin, 5, 5] +=, db [Cout] +=."""
+    _check_nhwc(xe, 'head_conv_wgrad_tc xe')
+    _check_nhwc(dz, 'head_conv_wgrad_tc dz')
+    N, _, H, W = xe.shape
+    Cout = dz.shape[1]
+    with _Prof('head_wgrad', 2.0 * N * H * W * Cout * Cin * 25, xe.device):
+        lib = _lib.load()
+        nws = lib.ramnet_head_conv_wgrad_tc_workspace_bytes(_h(xe), N, Cin, H, W, Cout)
+        ws = _workspace(xe.device, nws)
+        check(lib.ramnet_head_conv_wgrad_tc(_h(xe), _p(xe), _p(dz), _p(dw), _p(db), N, Cin, H, W, Cout, _p(ws), nws,
+                                            _stream(xe)))
 
 
 def zero_insert2x(x, Hout, Wout, skip=None):

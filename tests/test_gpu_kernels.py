@@ -258,6 +258,29 @@ def test_head_conv(Cin, H, W, N):
     assert (y.cpu() - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize('Cin,H,W,N', [(1, 32, 48, 2), (5, 40, 33, 1), (6, 8, 8, 3), (5, 256, 512, 1)])
+def test_head_conv_tensor_core(Cin, H, W, N):
+    """im2row (5 horizontal taps -> channels) + 5x1 tcgen05 conv vs torch on TF32-rounded operands."""
+    from rpg_ramnet_b200 import ops
+    x = _rand((N, Cin, H, W), 5)
+    w, b = _rand((32, Cin, 5, 5), 6, 0.2), _rand((32,), 7, 0.1)
+    def rna(t):      # cvt.rna.tf32.f32 on the host: round to nearest, ties away from zero, 10-bit mantissa
+        b = t.contiguous().view(torch.int32)
+        return ((b + 0x1000) & ~0x1fff).view(torch.float32)
+    xr, wr = rna(x), rna(w)
+    xe = ops.head_im2row(x.to(dev()))
+    # the unrolled tensor: channel dx*Cin + ci = x[ci] shifted by dx - 2, zero outside / beyond 5*Cin
+    pad = F.pad(xr, (2, 2))
+    for dx in range(5):
+        for ci in range(Cin):
+            assert torch.equal(xe[:, dx * Cin + ci].cpu(), pad[:, ci, :, dx:dx + W])
+    assert float(xe[:, 5 * Cin:].abs().max()) == 0.0
+    ref = torch.relu(F.conv2d(xr.double(), wr.double(), b.double(), padding=2)).float()
+    y = ops.head_conv_tc(xe, ops.pack_weights_head(w.to(dev())), b.to(dev()), Cin, 32, round_tf32=False)
+    assert ops._is_nhwc(y)
+    assert (y.cpu() - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+
+
 @pytest.mark.parametrize('with_skip', [False, True])
 @pytest.mark.parametrize('N,C,H,W', [(1, 32, 8, 8), (2, 64, 5, 7), (1, 256, 32, 43), (1, 4, 1, 1)])
 def test_upsample2x_add(with_skip, N, C, H, W):

@@ -204,6 +204,19 @@ def test_head_upsample_pred_backward_vs_torch():
     gw, gb = w.to(dev()).requires_grad_(True), b.to(dev()).requires_grad_(True)
     AG.HeadConvFn.apply(x.to(dev()), gw, gb, False).backward(nhwc(gy))
     assert _rel(gw.grad, tw.grad) <= 1e-4 and _rel(gb.grad, tb.grad) <= 1e-4
+    # TF32 mode: tensor-core head (unrolled input) forward + tap-packed weight gradient, vs torch in double
+    for cin, (H, W) in [(1, (16, 24)), (5, (20, 36)), (6, (12, 40))]:
+        xh, wh, bh = _rand((2, cin, H, W), 21), _rand((32, cin, 5, 5), 22, 0.2), _rand((32,), 23, 0.1)
+        gyh = _rand((2, 32, H, W), 24)
+        twh, tbh = wh.double().requires_grad_(True), bh.double().requires_grad_(True)
+        ty = torch.relu(F.conv2d(xh.double(), twh, tbh, padding=2))
+        ty.backward(gyh.double())
+        gwh, gbh = wh.to(dev()).requires_grad_(True), bh.to(dev()).requires_grad_(True)
+        yh = AG.HeadConvFn.apply(xh.to(dev()), gwh, gbh, True)
+        assert _rel(yh, ty) <= 2e-3, cin
+        yh.backward(nhwc(gyh))
+        # TF32 operands + the ReLU mask taken from the TF32 forward: same tolerance as the other tensor-core gradients
+        assert _rel(gwh.grad, twh.grad) <= TOL['tf32'] / 4 and _rel(gbh.grad, tbh.grad) <= TOL['tf32'] / 4, cin
     # skip-sum + bilinear x2
     for (N, C, H, W) in [(1, 32, 5, 7), (2, 64, 8, 8), (1, 4, 1, 1)]:
         a, s, g2 = _rand((N, C, H, W), 5), _rand((N, C, H, W), 6), _rand((N, C, 2 * H, 2 * W), 7)
