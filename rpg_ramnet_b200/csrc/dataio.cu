@@ -1,0 +1,141 @@
+// Device side of the loader -> network wire format and of the trainer's per-step metrics
+// (SURVEY.md §8f ranks 2 and 3).  All of it is streaming HBM work: one or two passes over a
+// [bins, H, W] voxel grid or a [N, 1, H, W] depth map, statistics reduced in float64 on the
+// device so the host never has to pull a full tensor back.
+//
+//   ramnet_voxel_normalize   RAM_Net/data_loader/event_dataset.py:144-151 (twins:
+//                            dataset_asynchronous.py:300-308, utils/event_tensor_utils.py:52-66):
+//                            mean / stddev of the NON-ZERO voxels -> (x - mean) / stddev on them
+//   ramnet_depth_to_label    RAM_Net/data_loader/dataset.py:296-305: metric depth -> normalised
+//                            log depth in [0, 1], NaN (no ground truth) preserved
+//   ramnet_depth_metrics     RAM_Net/model/metric.py:8-57 as called by
+//                            trainer/lstm_trainer.py:100-106,291-294: masked error sums per sample
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void block_reduce_add(double *vals, int nvals, double *out) {
+    // vals: per-thread partial sums (registers, nvals <= 8); atomically adds the block totals to out[0..nvals)
+    __shared__ double sh[8][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = 0; k < nvals; ++k) {
+        double v = vals[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sh[k][warp] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        for (int k = 0; k < nvals; ++k) {
+            double v = lane < 8 ? sh[k][lane] : 0.0;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) atomicAdd(out + k, v);
+        }
+    }
+}
+
+// stats[0] = sum, stats[1] = sum of squares, stats[2] = count over the non-zero voxels
+__global__ void __launch_bounds__(256) voxel_stats_kernel(const float *__restrict__ grid, int64_t n, double *__restrict__ stats) {
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float x = grid[i];
+        if (x != 0.f) {          // np.nonzero: NaN counts as non-zero, exactly as the reference
+            v[0] += (double)x;
+            v[1] += (double)x * (double)x;
+            v[2] += 1.0;
+        }
+    }
+    block_reduce_add(v, 3, stats);
+}
+
+__global__ void __launch_bounds__(256) voxel_normalize_kernel(float *__restrict__ grid, int64_t n, const double *__restrict__ stats) {
+    const double cnt = stats[2];
+    if (!(cnt > 0.0)) return;                               // event_dataset.py:147 `if mask[0].size > 0`
+    const double mean = stats[0] / cnt;
+    double var = stats[1] / cnt - mean * mean;              // population variance (np.std, ddof = 0)
+    if (var < 0.0) var = 0.0;
+    const double sd = sqrt(var);
+    if (!(sd > 0.0)) return;                                // :149 `if stddev > 0`
+    const float m = (float)mean, inv = (float)(1.0 / sd);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float x = grid[i];
+        if (x != 0.f) grid[i] = (x - m) * inv;
+    }
+}
+
+// label = clip(1 + log(clip(d, 0, clip) / clip) / reg, 0, 1); NaN stays NaN (np.clip / np.log propagate it)
+__global__ void __launch_bounds__(256) depth_label_kernel(const float *__restrict__ depth, float *__restrict__ label, int64_t n,
+                                                          float clip_distance, float reg_factor) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float d = depth[i];
+        float y = d;
+        if (d == d) {
+            const float c = fminf(fmaxf(d, 0.f), clip_distance) / clip_distance;
+            y = 1.0f + logf(c) / reg_factor;                // log(0) = -inf -> clipped to 0 below
+            y = fminf(fmaxf(y, 0.f), 1.0f);
+        }
+        label[i] = y;
+    }
+}
+
+// Per sample s (blockIdx.y), over its HW pixels, out[s*8 + k]:
+//   0: count of non-NaN (target - pred)      1: sum |d| / (target + eps)      2: sum d^2 / (target^2 + eps)
+//   3: sum d^2                               4: sum |d|
+//   5: count of non-NaN target               6: sum (pred - target)^2 over non-NaN target        7: unused
+__global__ void __launch_bounds__(256) depth_metrics_kernel(const float *__restrict__ pred, const float *__restrict__ target,
+                                                            int64_t hw, float eps, double *__restrict__ out) {
+    const float *p = pred + (int64_t)blockIdx.y * hw, *t = target + (int64_t)blockIdx.y * hw;
+    double v[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < hw; i += (int64_t)gridDim.x * blockDim.x) {
+        const float ti = t[i], pi = p[i];
+        const float d = fabsf(ti - pi);
+        if (d == d) {
+            v[0] += 1.0;
+            v[1] += (double)(d / (ti + eps));
+            v[2] += (double)(d * d / (ti * ti + eps));
+            v[3] += (double)d * (double)d;
+            v[4] += (double)d;
+        }
+        if (ti == ti) {
+            const double e = (double)pi - (double)ti;
+            v[5] += 1.0;
+            v[6] += e * e;
+        }
+    }
+    block_reduce_add(v, 7, out + (int64_t)blockIdx.y * 8);
+}
+}  // namespace
+
+extern "C" int ramnet_voxel_normalize(ramnet_handle *h, float *grid, int64_t n, double *stats, void *stream) {
+    RAMNET_CHECK_ARG(h && grid && stats && n > 0, "voxel_normalize: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    RAMNET_CUDA(cudaMemsetAsync(stats, 0, 3 * sizeof(double), s));
+    const int blocks = (int)imin64((n + 255) / 256, (int64_t)h->sm_count * 8);
+    voxel_stats_kernel<<<blocks, 256, 0, s>>>(grid, n, stats);
+    RAMNET_LAUNCH_CHECK(h);
+    voxel_normalize_kernel<<<blocks, 256, 0, s>>>(grid, n, stats);
+    RAMNET_LAUNCH_CHECK(h);
+    return RAMNET_OK;
+}
+
+extern "C" int ramnet_depth_to_label(ramnet_handle *h, const float *depth, float *label, int64_t n, float clip_distance,
+                                     float reg_factor, void *stream) {
+    RAMNET_CHECK_ARG(h && depth && label && n > 0 && clip_distance > 0.f && reg_factor != 0.f, "depth_to_label: bad argument");
+    const int blocks = (int)imin64((n + 255) / 256, (int64_t)h->sm_count * 8);
+    depth_label_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(depth, label, n, clip_distance, reg_factor);
+    RAMNET_LAUNCH_CHECK(h);
+    return RAMNET_OK;
+}
+
+extern "C" int ramnet_depth_metrics(ramnet_handle *h, const float *pred, const float *target, int N, int64_t hw, float eps,
+                                    double *out, void *stream) {
+    RAMNET_CHECK_ARG(h && pred && target && out && N > 0 && N <= 65535 && hw > 0, "depth_metrics: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    RAMNET_CUDA(cudaMemsetAsync(out, 0, (size_t)N * 8 * sizeof(double), s));
+    int bx = (int)imin64((hw + 255) / 256, (int64_t)h->sm_count * 8 / N + 1);
+    if (bx < 1) bx = 1;
+    depth_metrics_kernel<<<dim3((unsigned)bx, (unsigned)N), 256, 0, s>>>(pred, target, hw, eps, out);
+    RAMNET_LAUNCH_CHECK(h);
+    return RAMNET_OK;
+}

@@ -110,6 +110,37 @@ def head_conv(x_nchw: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], 
     return y
 
 
+def voxel_normalize_(grid: torch.Tensor) -> torch.Tensor:
+    """In place: (x - mean) / stddev over the non-zero voxels (event_dataset.py:144-151)."""
+    if not (grid.is_cuda and grid.dtype == torch.float32 and grid.is_contiguous()):
+        raise _lib.RamnetError('voxel_normalize_: contiguous float32 CUDA tensor required')
+    stats = torch.empty(3, dtype=torch.float64, device=grid.device)
+    check(_lib.load().ramnet_voxel_normalize(_h(grid), _p(grid), grid.numel(), _p(stats), _stream(grid)))
+    return grid
+
+
+def depth_to_label(depth: torch.Tensor, clip_distance: float, reg_factor: float) -> torch.Tensor:
+    """Metric depth -> normalised log depth in [0, 1] (dataset.py:296-305); NaN pixels stay NaN."""
+    d = depth.contiguous().float()
+    if not d.is_cuda:
+        raise _lib.RamnetError('depth_to_label: CUDA tensor required')
+    out = torch.empty_like(d)
+    check(_lib.load().ramnet_depth_to_label(_h(d), _p(d), _p(out), d.numel(), float(clip_distance), float(reg_factor),
+                                            _stream(d)))
+    return out
+
+
+def depth_metric_sums(pred: torch.Tensor, target: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    """[N, 8] float64 masked error sums of a [N, 1, H, W] prediction / target pair (see ramnet_depth_metrics)."""
+    p, t = pred.detach().contiguous().float(), target.detach().contiguous().float()
+    if not (p.is_cuda and t.is_cuda) or p.shape != t.shape or p.dim() != 4 or p.shape[1] != 1:
+        raise _lib.RamnetError('depth_metric_sums: two [N, 1, H, W] CUDA tensors required')
+    N, hw = p.shape[0], p.shape[2] * p.shape[3]
+    out = torch.empty((N, 8), dtype=torch.float64, device=p.device)
+    check(_lib.load().ramnet_depth_metrics(_h(p), _p(p), _p(t), N, hw, float(eps), _p(out), _stream(p)))
+    return out
+
+
 def head_tc_ok(Cin: int, Cout: int) -> bool:
     """The tensor-core head path covers 5*Cin <= 32 (Cin <= 6: every shipped configuration) and Cout % 32 == 0."""
     return 5 * Cin <= 32 and Cout % 32 == 0 and os.environ.get('RAMNET_HEAD_TC', '1') != '0'

@@ -29,3 +29,18 @@ def events_to_voxel_grid(events, num_bins, width, height, device=None):
 def events_to_voxel_grid_pytorch(events, num_bins, width, height, device):
     """Same entry point name as the reference's torch variant (:120)."""
     return events_to_voxel_grid(events, num_bins, width, height, device=device)
+
+
+def normalize_voxel_grid(voxel_grid):
+    """Device twin of the loaders' normalisation (data_loader/event_dataset.py:144-151,
+    dataset_asynchronous.py:300-308 `normalize_voxelgrid`, utils/event_tensor_utils.py:52-66): the mean and
+    stddev of the NON-ZERO voxels become (0, 1); zeros stay zero; nothing happens when there are no events or
+    the stddev is 0.  In place on a float32 CUDA tensor (as the reference mutates its array), returns it."""
+    return ops.voxel_normalize_(voxel_grid)
+
+
+def depth_to_log_label(depth, clip_distance, reg_factor):
+    """Device twin of the label transform in data_loader/dataset.py:296-305: clip to `clip_distance`,
+    normalise, `1 + log(d) / reg_factor`, clip to [0, 1]; NaN (no ground truth) is preserved for the
+    loss's mask (model/loss.py:7-8)."""
+    return ops.depth_to_label(depth, clip_distance, reg_factor)

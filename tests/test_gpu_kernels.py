@@ -391,3 +391,37 @@ def test_conv_argument_errors():
         ops.conv_fwd(x, None, w, None, 32, 3, 1, ops.EPI_GRU_OUT, ops.MMA_FP32)   # missing aux
     with pytest.raises(R.RamnetError):
         ops.conv_fwd(x.cpu(), None, w, None, 32, 3, 1, ops.EPI_BIAS, ops.MMA_FP32)  # CPU tensor: no fallback
+
+
+# ----------------------------------------------------------------------------- loader wire format / trainer metrics
+def test_voxel_normalize_label_and_metrics_on_device():
+    """device twins of the loader normalisation, the log-depth label transform and the trainer's
+    metrics vs the reference's own outputs (tests/golden/dataio.npz) and the numpy oracle."""
+    import rpg_ramnet_b200 as R
+    from rpg_ramnet_b200.model import metric as M
+    from rpg_ramnet_b200.utils.event_tensor_utils import depth_to_log_label, normalize_voxel_grid
+    from oracle import dataio_oracle as D
+    g = np.load(os.path.join(GOLDEN, 'dataio.npz'))
+    cases = D.synth_cases(0)
+    for k in ('vox_sparse', 'vox_zero', 'vox_const'):
+        x = torch.from_numpy(cases[k].copy()).to(dev())
+        y = normalize_voxel_grid(x)
+        assert y.data_ptr() == x.data_ptr()                                   # in place, like the reference
+        ref = g[k + '_numpy']
+        np.testing.assert_allclose(y.cpu().numpy(), ref, rtol=1e-5, atol=2e-6)    # float64 vs numpy-float32 statistics
+        np.testing.assert_array_equal(y.cpu().numpy() == 0, ref == 0)
+    big = (torch.randn(5, 256, 512, generator=torch.Generator().manual_seed(3)) *
+           (torch.rand(5, 256, 512, generator=torch.Generator().manual_seed(4)) < 0.1)).float()
+    np.testing.assert_allclose(normalize_voxel_grid(big.clone().to(dev())).cpu().numpy(),
+                               D.normalize_voxel_grid(big.numpy()), rtol=1e-4, atol=1e-5)
+    for clip, reg in ((80.0, 3.70378), (1000.0, 6.2044)):
+        lab = depth_to_log_label(torch.from_numpy(cases['depth']).to(dev()), clip, reg).cpu().numpy()
+        ref = g[f'label_{int(clip)}']
+        assert np.array_equal(np.isnan(lab), np.isnan(ref))
+        np.testing.assert_allclose(np.nan_to_num(lab), np.nan_to_num(ref), rtol=0, atol=2e-7 * 8)   # logf vs np.log: a few ulp
+    p, t = torch.from_numpy(cases['metric_pred']).to(dev()), torch.from_numpy(cases['metric_target']).to(dev())
+    names = ['mse', 'abs_rel_diff', 'scale_invariant_error', 'median_error', 'squ_rel_diff', 'rms_linear', 'mean_error']
+    vals = M.eval_metrics(p, t, names)
+    for n, v in zip(names, vals):
+        np.testing.assert_allclose(v, float(g['metric_' + n]), rtol=2e-5, err_msg=n)
+        np.testing.assert_allclose(getattr(M, n)(p, t), v, rtol=1e-12)
