@@ -180,13 +180,14 @@ int ramnet_head_conv_tc(ramnet_handle *h, const float *xe_nhwc32, const float *w
 /* ---- f-2 / f-3  loader wire format and trainer metrics on the device ---- *
  * ramnet_voxel_normalize: in place, mean / stddev of the NON-ZERO voxels -> (x - mean) / stddev on them
  *   (data_loader/event_dataset.py:144-151, dataset_asynchronous.py:300-308, utils/event_tensor_utils.py:52-66);
- *   stats = 3 doubles of device scratch (sum, sum of squares, count), left filled.
+ *   `batch` grids of n voxels each, normalised independently in one launch pair; stats = 3 doubles per grid of
+ *   device scratch (sum, sum of squares, count), left filled.
  * ramnet_depth_to_label: metric depth -> clip(1 + log(clip(d, 0, clip)/clip) / reg_factor, 0, 1), NaN preserved
  *   (data_loader/dataset.py:296-305).
  * ramnet_depth_metrics: masked error sums of model/metric.py:8-57 per sample over hw pixels, out[s*8 + k]:
  *   0 count(~nan |t-p|), 1 sum |d|/(t+eps), 2 sum d^2/(t^2+eps), 3 sum d^2, 4 sum |d|, 5 count(~nan t),
  *   6 sum (p-t)^2 over ~nan t, 7 unused (replaces the full-map D2H + numpy of trainer/lstm_trainer.py:100-106). */
-int ramnet_voxel_normalize(ramnet_handle *h, float *grid, int64_t n, double *stats, void *stream);
+int ramnet_voxel_normalize(ramnet_handle *h, float *grid, int64_t n, int batch, double *stats, void *stream);
 int ramnet_depth_to_label(ramnet_handle *h, const float *depth, float *label, int64_t n, float clip_distance,
                           float reg_factor, void *stream);
 int ramnet_depth_metrics(ramnet_handle *h, const float *pred, const float *target, int N, int64_t hw, float eps,

@@ -131,6 +131,15 @@ __device__ __forceinline__ void epilogue_prefetch(const EpiParams &p, int64_t m,
     }
 }
 
+// 256-bit store (sm_100: STG.E.256): one instruction per full 32-byte sector.  The epilogue's access pattern is one
+// thread = one pixel row, so a warp store touches 32 different 128-byte lines whatever its width; halving the number of
+// store instructions halves the LSU / L1 cycles the epilogue takes away from the shared-memory-bound mainloop.
+__device__ __forceinline__ void st_global_v8(float *dst, const float (&a)[8]) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "f"(a[0]), "f"(a[1]), "f"(a[2]),
+                 "f"(a[3]), "f"(a[4]), "f"(a[5]), "f"(a[6]), "f"(a[7])
+                 : "memory");
+}
+
 template <int EPI, int NV>
 __device__ __forceinline__ void epilogue_finish(const EpiParams &p, int64_t m, int n0, float (&v)[NV],
                                                 const EpiAux<NV> &x) {
@@ -143,21 +152,37 @@ __device__ __forceinline__ void epilogue_finish(const EpiParams &p, int64_t m, i
         if (rnd) { a = round_tf32(a); b = round_tf32(b); c = round_tf32(c); d = round_tf32(d); }
         *reinterpret_cast<float4 *>(dst) = make_float4(a, b, c, d);
     };
+    // NV consecutive outputs of one pixel: 32-byte stores when NV allows (rows are 64-byte aligned: Cout % 16 == 0)
+    auto store_row = [&](float *dst, const float (&o)[NV]) {
+        if constexpr (NV % 8 == 0) {
+#pragma unroll
+            for (int j = 0; j < NV; j += 8) {
+                float t[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) t[q] = rnd ? round_tf32(o[j + q]) : o[j + q];
+                st_global_v8(dst + j, t);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NV; j += 4) st4(dst + j, o[j], o[j + 1], o[j + 2], o[j + 3]);
+        }
+    };
     if constexpr (EPI == RAMNET_EPI_BIAS) {
-#pragma unroll
-        for (int j = 0; j < NV; j += 4) st4(p.y0 + m * p.Cout + n0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        store_row(p.y0 + m * p.Cout + n0, v);
     } else if constexpr (EPI == RAMNET_EPI_BIAS_RELU) {
+        float o[NV];
 #pragma unroll
-        for (int j = 0; j < NV; j += 4)
-            st4(p.y0 + m * p.Cout + n0 + j, fmaxf(v[j], 0.f), fmaxf(v[j + 1], 0.f), fmaxf(v[j + 2], 0.f),
-                fmaxf(v[j + 3], 0.f));
+        for (int j = 0; j < NV; ++j) o[j] = fmaxf(v[j], 0.f);
+        store_row(p.y0 + m * p.Cout + n0, o);
     } else if constexpr (EPI == RAMNET_EPI_BIAS_RES_RELU) {
+        float o[NV];
 #pragma unroll
         for (int j = 0; j < NV; j += 4) {
             const float4 r = x.a[j / 4];
-            st4(p.y0 + m * p.Cout + n0 + j, fmaxf(v[j] + r.x, 0.f), fmaxf(v[j + 1] + r.y, 0.f),
-                fmaxf(v[j + 2] + r.z, 0.f), fmaxf(v[j + 3] + r.w, 0.f));
+            o[j] = fmaxf(v[j] + r.x, 0.f); o[j + 1] = fmaxf(v[j + 1] + r.y, 0.f);
+            o[j + 2] = fmaxf(v[j + 2] + r.z, 0.f); o[j + 3] = fmaxf(v[j + 3] + r.w, 0.f);
         }
+        store_row(p.y0 + m * p.Cout + n0, o);
     } else if constexpr (EPI == RAMNET_EPI_GRU_RU) {
         const int C = p.Cout >> 1;
         if (n0 < C) {  // reset gate -> y1 = h * r
@@ -175,14 +200,16 @@ __device__ __forceinline__ void epilogue_finish(const EpiParams &p, int64_t m, i
                     make_float4(sigmoidf_(v[j]), sigmoidf_(v[j + 1]), sigmoidf_(v[j + 2]), sigmoidf_(v[j + 3]));
         }
     } else if constexpr (EPI == RAMNET_EPI_GRU_OUT) {
+        float hn[NV];
 #pragma unroll
         for (int j = 0; j < NV; j += 4) {
             const float4 h = x.a[j / 4], u = x.b[j / 4];
             const float o0 = tanhf(v[j]), o1 = tanhf(v[j + 1]), o2 = tanhf(v[j + 2]), o3 = tanhf(v[j + 3]);
             if (p.y2) *reinterpret_cast<float4 *>(p.y2 + m * p.Cout + n0 + j) = make_float4(o0, o1, o2, o3);
-            st4(p.y0 + m * p.Cout + n0 + j, h.x * (1.f - u.x) + o0 * u.x, h.y * (1.f - u.y) + o1 * u.y,
-                h.z * (1.f - u.z) + o2 * u.z, h.w * (1.f - u.w) + o3 * u.w);
+            hn[j] = h.x * (1.f - u.x) + o0 * u.x; hn[j + 1] = h.y * (1.f - u.y) + o1 * u.y;
+            hn[j + 2] = h.z * (1.f - u.z) + o2 * u.z; hn[j + 3] = h.w * (1.f - u.w) + o3 * u.w;
         }
+        store_row(p.y0 + m * p.Cout + n0, hn);
     } else if constexpr (EPI == RAMNET_EPI_LSTM) {
         const int C = p.Cout >> 2;
         const float *cprev = reinterpret_cast<const float *>(&x.a[0]);

@@ -1964,6 +1964,9 @@ int conv_fwd_tf32_rect(ramnet_handle *h, const ramnet_conv_desc *d, const RectSp
     RAMNET_CHECK_ARG(d->Cout % 16 == 0, "conv_fwd(tf32): Cout=%d must be a multiple of 16", d->Cout);
     RAMNET_CHECK_ARG(d->stride == 1 || (d->H % 2 == 0 && d->W % 2 == 0), "conv_fwd(tf32): stride 2 needs even H, W");
     RAMNET_CHECK_ARG((((uintptr_t)x0 | (uintptr_t)x1 | (uintptr_t)wp) & 15) == 0, "conv_fwd(tf32): 16-byte alignment");
+    RAMNET_CHECK_ARG((((uintptr_t)ep.y0 | (uintptr_t)ep.y1 | (uintptr_t)ep.y2 | (uintptr_t)ep.aux0 | (uintptr_t)ep.aux1) & 31) == 0 ||
+                         d->epilogue == RAMNET_EPI_BIAS_RELU_PRED,
+                     "conv_fwd(tf32): outputs and epilogue operands must be 32-byte aligned (256-bit stores)");
     HaloGeom hg;
     const bool halo_ok = plan_halo(h, d, rect, &hg);
     if (!halo_ok && rect)

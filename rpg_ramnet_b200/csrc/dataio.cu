@@ -36,7 +36,10 @@ __device__ __forceinline__ void block_reduce_add(double *vals, int nvals, double
 }
 
 // stats[0] = sum, stats[1] = sum of squares, stats[2] = count over the non-zero voxels
+// blockIdx.y = sample of a batch of grids (n voxels each, statistics per sample)
 __global__ void __launch_bounds__(256) voxel_stats_kernel(const float *__restrict__ grid, int64_t n, double *__restrict__ stats) {
+    grid += (int64_t)blockIdx.y * n;
+    stats += blockIdx.y * 3;
     double v[3] = {0.0, 0.0, 0.0};
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float x = grid[i];
@@ -50,6 +53,8 @@ __global__ void __launch_bounds__(256) voxel_stats_kernel(const float *__restric
 }
 
 __global__ void __launch_bounds__(256) voxel_normalize_kernel(float *__restrict__ grid, int64_t n, const double *__restrict__ stats) {
+    grid += (int64_t)blockIdx.y * n;
+    stats += blockIdx.y * 3;
     const double cnt = stats[2];
     if (!(cnt > 0.0)) return;                               // event_dataset.py:147 `if mask[0].size > 0`
     const double mean = stats[0] / cnt;
@@ -107,11 +112,12 @@ __global__ void __launch_bounds__(256) depth_metrics_kernel(const float *__restr
 }
 }  // namespace
 
-extern "C" int ramnet_voxel_normalize(ramnet_handle *h, float *grid, int64_t n, double *stats, void *stream) {
-    RAMNET_CHECK_ARG(h && grid && stats && n > 0, "voxel_normalize: bad argument");
+extern "C" int ramnet_voxel_normalize(ramnet_handle *h, float *grid, int64_t n, int batch, double *stats, void *stream) {
+    RAMNET_CHECK_ARG(h && grid && stats && n > 0 && batch > 0 && batch <= 65535, "voxel_normalize: bad argument");
     cudaStream_t s = (cudaStream_t)stream;
-    RAMNET_CUDA(cudaMemsetAsync(stats, 0, 3 * sizeof(double), s));
-    const int blocks = (int)imin64((n + 255) / 256, (int64_t)h->sm_count * 8);
+    RAMNET_CUDA(cudaMemsetAsync(stats, 0, (size_t)batch * 3 * sizeof(double), s));
+    int bx = (int)imin64((n + 255) / 256, (int64_t)h->sm_count * 8 / batch + 1);
+    const dim3 blocks((unsigned)(bx < 1 ? 1 : bx), (unsigned)batch);
     voxel_stats_kernel<<<blocks, 256, 0, s>>>(grid, n, stats);
     RAMNET_LAUNCH_CHECK(h);
     voxel_normalize_kernel<<<blocks, 256, 0, s>>>(grid, n, stats);

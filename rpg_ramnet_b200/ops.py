@@ -114,8 +114,9 @@ def voxel_normalize_(grid: torch.Tensor) -> torch.Tensor:
     """In place: (x - mean) / stddev over the non-zero voxels (event_dataset.py:144-151)."""
     if not (grid.is_cuda and grid.dtype == torch.float32 and grid.is_contiguous()):
         raise _lib.RamnetError('voxel_normalize_: contiguous float32 CUDA tensor required')
-    stats = torch.empty(3, dtype=torch.float64, device=grid.device)
-    check(_lib.load().ramnet_voxel_normalize(_h(grid), _p(grid), grid.numel(), _p(stats), _stream(grid)))
+    batch = grid.shape[0] if grid.dim() == 4 else 1        # [B, bins, H, W]: every sample on its own statistics
+    stats = torch.empty(3 * batch, dtype=torch.float64, device=grid.device)
+    check(_lib.load().ramnet_voxel_normalize(_h(grid), _p(grid), grid.numel() // batch, batch, _p(stats), _stream(grid)))
     return grid
 
 

@@ -35,7 +35,8 @@ def normalize_voxel_grid(voxel_grid):
     """Device twin of the loaders' normalisation (data_loader/event_dataset.py:144-151,
     dataset_asynchronous.py:300-308 `normalize_voxelgrid`, utils/event_tensor_utils.py:52-66): the mean and
     stddev of the NON-ZERO voxels become (0, 1); zeros stay zero; nothing happens when there are no events or
-    the stddev is 0.  In place on a float32 CUDA tensor (as the reference mutates its array), returns it."""
+    the stddev is 0.  In place on a float32 CUDA tensor (as the reference mutates its array), returns it.
+    A 4-D [B, bins, H, W] tensor is a batch of grids, each normalised on its own statistics in one launch pair."""
     return ops.voxel_normalize_(voxel_grid)
 
 

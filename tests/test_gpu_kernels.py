@@ -414,6 +414,10 @@ def test_voxel_normalize_label_and_metrics_on_device():
            (torch.rand(5, 256, 512, generator=torch.Generator().manual_seed(4)) < 0.1)).float()
     np.testing.assert_allclose(normalize_voxel_grid(big.clone().to(dev())).cpu().numpy(),
                                D.normalize_voxel_grid(big.numpy()), rtol=1e-4, atol=1e-5)
+    batch = torch.stack([big, big * 2.0 + (big != 0).float(), torch.zeros_like(big)]).to(dev())
+    out = normalize_voxel_grid(batch.clone()).cpu().numpy()             # per-sample statistics in one launch pair
+    for i in range(3):
+        np.testing.assert_allclose(out[i], D.normalize_voxel_grid(batch[i].cpu().numpy()), rtol=1e-4, atol=1e-5)
     for clip, reg in ((80.0, 3.70378), (1000.0, 6.2044)):
         lab = depth_to_log_label(torch.from_numpy(cases['depth']).to(dev()), clip, reg).cpu().numpy()
         ref = g[f'label_{int(clip)}']

@@ -44,7 +44,7 @@ tgt = D.depth_to_log_label(depth, 80.0, 3.70378)
 vg, dg, pg, tg = (torch.from_numpy(a).to(dev) for a in (vox, depth, pred, tgt))
 names = ['mse', 'abs_rel_diff', 'scale_invariant_error']
 rows = [
-    ('voxel_normalize (batch of 32 grids, one call each)', lambda: [ops.voxel_normalize_(vg[i]) for i in range(B)],
+    ('voxel_normalize (batch of 32 grids, one launch pair)', lambda: ops.voxel_normalize_(vg),
      lambda: [D.normalize_voxel_grid(vox[i]) for i in range(B)], vox.nbytes * 3),
     ('depth_to_label [32,1,256,512]', lambda: ops.depth_to_label(dg, 80.0, 3.70378),
      lambda: D.depth_to_log_label(depth, 80.0, 3.70378), depth.nbytes * 2),
