@@ -331,6 +331,7 @@ struct HaloGeom {
     int patches_x, patches_y;
     int BN, n_slices;        // GEMM columns per item, Cout / BN
     int a_stages, b_stages;
+    int tpg;                 // filter taps per weight stage: one TMA box / one barrier round trip / one commit per tpg taps
     int nbuf;                // TMEM accumulator buffers
     int pair;                // 1: CTA-pair mode (cta_group::2, M = 256): a work item is two patches x one BN-wide slice
     int items;               // patches (pair mode: patch pairs) * n_slices
@@ -480,7 +481,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
     const int a_bytes = g.nplanes * plane_bytes;             // TMA transaction bytes per halo stage
     const int a_stride = g.nplanes * g.plane_stride;
     const int bn_local = PAIR ? g.BN / 2 : g.BN;             // weight rows staged by this CTA
-    const int b_bytes = bn_local * kChunk * 4;
+    const int b_tile = bn_local * kChunk * 4;                // one tap's weight tile
+    const int b_bytes = g.tpg * b_tile;                      // one weight stage = tpg consecutive taps
     const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
     const bool leader = cta_rank == 0;
     const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // persistent worker = CTA or CTA pair
@@ -608,7 +610,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
         for (int item = worker; item < g.items; item += nworkers) {
             const int n0 = (item / patches_w) * g.BN + (int)cta_rank * bn_local;   // pair mode: this CTA's half of the slice
             for (int ch = 0; ch < chunks; ++ch) {
-                for (int tap = 0; tap < taps; ++tap) {
+                for (int tap = 0; tap < taps; tap += g.tpg) {     // one box = tpg taps x bn_local rows x 32 channels
                     mbar_wait_t(b_empty + stage, phase ^ 1, prof, w0);
                     if (elect_one()) {
                         if (leader) mbar_expect_tx(b_full + stage, (uint32_t)b_bytes * (PAIR ? 2u : 1u));
@@ -646,29 +648,33 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
             for (int ch = 0; ch < chunks; ++ch) {
                 mbar_wait_t(a_full + sa, pa, prof, w0);
                 const uint32_t a16 = (smem_u32(smem + (size_t)sa * a_stride) & 0x3FFFFu) >> 4;
-                for (int r = 0, tap = 0; r < g.kh; ++r) {
-                    for (int sx = 0; sx < g.kw; ++sx, ++tap) {
-                        // One barrier round trip (~100+ cycles even when complete) tells us about EVERY weight stage:
-                        // lane i polls the stage i slots ahead; the ballot gives the run of ready stages.
-                        if (ready == 0) {
-                            const long long tw = prof ? clock64() : 0;
-                            int j = sb + lane;
-                            uint32_t pj = pb;
-                            if (j >= g.b_stages) { j -= g.b_stages; pj ^= 1; }
-                            uint32_t mask;
-                            do {
-                                const bool ok = lane < g.b_stages && mbar_test(b_full + j, pj);
-                                mask = __ballot_sync(0xffffffffu, ok);
-                            } while (!(mask & 1u));
-                            ready = __ffs(~mask) - 1;          // consecutive ready stages starting at sb
-                            if (prof) w1 += (unsigned long long)(clock64() - tw);
-                        }
-                        --ready;
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + (size_t)sb * b_bytes));
-                        const uint32_t tap16 = a16 + tap_tab[tap];
-                        const uint32_t first = (uint32_t)(ch | r | sx);
-                        if (elect_one()) {
+                for (int tap0 = 0; tap0 < taps; tap0 += g.tpg) {
+                    // One barrier round trip (~100+ cycles even when complete) tells us about EVERY weight stage:
+                    // lane i polls the stage i slots ahead; the ballot gives the run of ready stages.
+                    if (ready == 0) {
+                        const long long tw = prof ? clock64() : 0;
+                        int j = sb + lane;
+                        uint32_t pj = pb;
+                        if (j >= g.b_stages) { j -= g.b_stages; pj ^= 1; }
+                        uint32_t mask;
+                        do {
+                            const bool ok = lane < g.b_stages && mbar_test(b_full + j, pj);
+                            mask = __ballot_sync(0xffffffffu, ok);
+                        } while (!(mask & 1u));
+                        ready = __ffs(~mask) - 1;          // consecutive ready stages starting at sb
+                        if (prof) w1 += (unsigned long long)(clock64() - tw);
+                    }
+                    --ready;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t b_base = smem_u32(smem_b + (size_t)sb * b_bytes);
+                    if (elect_one()) {
+                        // the whole tap group from one thread: no barrier, fence or commit between its taps (measured: the
+                        // per-tap round trip cost ~300 cycles in pair mode, more than the MMAs of a 1-tile tap)
+                        for (int t = 0; t < g.tpg; ++t) {
+                            const int tap = tap0 + t;
+                            const uint64_t bdesc = make_smem_desc(b_base + (uint32_t)(t * b_tile));
+                            const uint32_t tap16 = a16 + tap_tab[tap];
+                            const uint32_t first = (uint32_t)(ch | tap);
 #pragma unroll
                             for (int tl = 0; tl < 4; ++tl) {
                                 if (tl < ntiles) {
@@ -679,11 +685,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
                                                         idesc, (first | (uint32_t)kk) != 0);
                                 }
                             }
-                            halo_commit<PAIR>(b_empty + sb);
                         }
-                        __syncwarp();
-                        if (++sb == g.b_stages) { sb = 0; pb ^= 1; }
+                        halo_commit<PAIR>(b_empty + sb);
                     }
+                    __syncwarp();
+                    if (++sb == g.b_stages) { sb = 0; pb ^= 1; }
                 }
                 if (elect_one()) {
                     halo_commit<PAIR>(a_empty + sa);
@@ -1324,7 +1330,7 @@ template <int EPI>
 int launch_halo(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap &m1, const CUtensorMap &mw,
                 const HaloGeom &g, const EpiParams &ep, cudaStream_t s) {
     const size_t a_stride = (size_t)g.nplanes * g.plane_stride;
-    const size_t smem = g.a_stages * a_stride + (size_t)g.b_stages * (g.pair ? g.BN / 2 : g.BN) * kChunk * 4 +
+    const size_t smem = g.a_stages * a_stride + (size_t)g.b_stages * g.tpg * (g.pair ? g.BN / 2 : g.BN) * kChunk * 4 +
                         (2 * g.a_stages + 2 * g.b_stages + 4) * 8 + 16 + 32 * 4 + 1024;
     if (g.pair) return launch_halo_pair<EPI, true>(h, m0, m1, mw, g, ep, smem, s);
     static size_t configured = 0;
@@ -1401,14 +1407,32 @@ bool fill_halo(const ramnet_conv_desc *d, const RectSpec *rect, HaloGeom *g, int
     g->nbuf = (2 * ptx * pty * bn <= 512) ? 2 : 1;
     g->plane_stride = (int)(((size_t)g->HX * g->HY * kChunk * 4 + 1023) & ~(size_t)1023);
     const size_t a_stride = (size_t)g->nplanes * g->plane_stride;
-    const size_t b_bytes = (size_t)(pair ? bn / 2 : bn) * kChunk * 4;
+    const size_t b_tile = (size_t)(pair ? bn / 2 : bn) * kChunk * 4;
     const size_t budget = 222 * 1024;
-    if (a_st <= 0) {   // automatic pipeline depths
+    const bool auto_depth = a_st <= 0;
+    if (auto_depth) {
         a_st = 2;
-        if (budget < a_st * a_stride + 3 * b_bytes) a_st = 1;
-        if (budget < a_st * a_stride + 3 * b_bytes) return false;
+        if (budget < a_st * a_stride + 3 * b_tile) a_st = 1;
+        if (budget < a_st * a_stride + 3 * b_tile) return false;
+    }
+    // taps per weight stage: all of them, one filter row, or one -- the largest that keeps a stage <= 40 KB and
+    // leaves room for three stages (RAMNET_HALO_TPG overrides for A/B runs)
+    const int taps = g->kh * g->kw;
+    static const int tpg_env = [] { const char *e = getenv("RAMNET_HALO_TPG"); return e ? atoi(e) : 0; }();
+    const int cand[3] = {taps, g->kw, 1};
+    int tpg = 1;
+    for (int c : cand) {
+        if (c < 1 || taps % c) continue;
+        if (tpg_env > 0 && c > tpg_env) continue;
+        if ((size_t)c * b_tile <= 40 * 1024 && a_st * a_stride + 3 * (size_t)c * b_tile <= budget) { tpg = c; break; }
+    }
+    g->tpg = tpg;
+    const size_t b_bytes = (size_t)tpg * b_tile;
+    if (auto_depth) {
         b_st = (int)((budget - a_st * a_stride) / b_bytes);
         if (b_st > 10) b_st = 10;
+    } else if (a_st * a_stride + b_st * b_bytes > budget) {
+        b_st = (int)((budget - a_st * a_stride) / b_bytes);     // forced depths are in single-tap stages: clamp
     }
     if (a_st * a_stride + b_st * b_bytes > budget || b_st < 2) return false;
     g->a_stages = a_st; g->b_stages = b_st;
@@ -1429,7 +1453,13 @@ double halo_cost(const ramnet_handle *h, const ramnet_conv_desc *d, const HaloGe
     const double bn_l = g.pair ? g.BN / 2.0 : (double)g.BN;     // weight rows read from / written to THIS SM's shared memory
     const double smem_tap = (ntiles * 4.0 * (128 + bn_l) * 32.0 + bn_l * 128.0 + halo_bytes / taps) / 128.0;
     const double math_tap = ntiles * 4.0 * g.BN / 2.0;
-    const double tap = (smem_tap > math_tap ? smem_tap : math_tap) + 20.0;
+    // The issuing thread runs beside the (asynchronous) tensor pipe: per weight stage a barrier poll + fence + commit
+    // (multicast across the pair: ~300 clk measured, ~60 single), shared by tpg taps, plus ~26 clk per MMA issued.
+    // A tap costs whichever is slower (RAMNET_PROF: 410 / 514 clk per tap for 1 / 2 tiles of N = 64 in pair mode).
+    const double issue_tap = (g.pair ? 300.0 : 60.0) / g.tpg + 26.0 * 4.0 * ntiles;
+    double tap = smem_tap > math_tap ? smem_tap : math_tap;
+    if (issue_tap > tap) tap = issue_tap;
+    tap += 10.0;
     const double mma = (double)chunks * taps * tap;
     const double l2 = (double)chunks * (halo_bytes + (double)taps * bn_l * 128.0) / 50.0;
     const double main = mma > l2 ? mma : l2;
@@ -1437,7 +1467,11 @@ double halo_cost(const ramnet_handle *h, const ramnet_conv_desc *d, const HaloGe
     const double per_item = g.nbuf == 2 ? (main > epi ? main : epi) + 300.0 : main + epi;
     const int workers = g.pair ? h->sm_count / 2 : h->sm_count;
     const int64_t rounds = (g.items + workers - 1) / workers;
-    return (double)rounds * per_item + (g.nbuf == 2 ? epi : 0.0) + 4000.0;
+    double cost = (double)rounds * per_item + (g.nbuf == 2 ? epi : 0.0) + 4000.0;
+    // stride 2: one 4-plane halo per item and a single K chunk for the first encoder -- the halo fetch is exposed and the
+    // model above underestimates both modes by ~2x; measured (enc0, 32->64): pair 2x1 55 us vs single 1x1 67 us
+    if (d->stride == 2 && !g.pair) cost *= 1.25;
+    return cost;
 }
 
 // Chooses patch shape, BN and pipeline depths for the halo kernel; returns false when the layer
@@ -1975,9 +2009,9 @@ int conv_fwd_tf32_rect(ramnet_handle *h, const ramnet_conv_desc *d, const RectSp
         return ramnet_set_error(RAMNET_EUNSUPPORTED, "conv_fwd: no halo-kernel configuration for the fused prediction epilogue");
     if (halo_ok) {
         if (getenv("RAMNET_DEBUG"))
-            fprintf(stderr, "[ramnet] halo plan s%d %dx%d C=%d+%d->%d k%d: tiles %dx%d HX=%d HY=%d BN=%d a_st=%d b_st=%d nbuf=%d items=%d pair=%d\n",
+            fprintf(stderr, "[ramnet] halo plan s%d %dx%d C=%d+%d->%d k%d: tiles %dx%d HX=%d HY=%d BN=%d a_st=%d b_st=%d tpg=%d nbuf=%d items=%d pair=%d\n",
                     d->stride, d->H, d->W, d->C0, d->C1, d->Cout, d->ksize, hg.PTX, hg.PTY, hg.HX, hg.HY, hg.BN, hg.a_stages,
-                    hg.b_stages, hg.nbuf, hg.items, hg.pair);
+                    hg.b_stages, hg.tpg, hg.nbuf, hg.items, hg.pair);
         CUtensorMap m0, m1, mw;
         auto enc_act = [&](CUtensorMap *m, const float *x, int C) {
             if (d->stride == 1) {
@@ -2004,7 +2038,7 @@ int conv_fwd_tf32_rect(ramnet_handle *h, const ramnet_conv_desc *d, const RectSp
         const int Ct = d->C0 + d->C1, taps = hg.kh * hg.kw;
         cuuint64_t wd[3] = {(cuuint64_t)Ct, (cuuint64_t)d->Cout, (cuuint64_t)taps};
         cuuint64_t ws[2] = {(cuuint64_t)Ct * 4, (cuuint64_t)Ct * d->Cout * 4};
-        cuuint32_t wb[3] = {kChunk, (cuuint32_t)(hg.pair ? hg.BN / 2 : hg.BN), 1};
+        cuuint32_t wb[3] = {kChunk, (cuuint32_t)(hg.pair ? hg.BN / 2 : hg.BN), (cuuint32_t)hg.tpg};
         rc = encode(h, &mw, wp, 3, wd, ws, wb);
         if (rc) return rc;
         switch (d->epilogue) {
