@@ -320,11 +320,11 @@ def main_train(args):
                                        f'K=1, SI loss on events0+image, full BPTT, fused Adam(3e-4)',
                            'parallelism': f'dp{world}: flat fp32 grad all-reduce (NCCL) + 3-double loss-statistics all-reduce'},
                 'clocks': clk.summary(), 'gpu_launches': launches,
-                'roofline': {'bound': 'tensor', 'kernel': 'conv_implicit_gemm fwd+dgrad (tcgen05)',
+                'roofline': {'bound': 'tensor', 'kernel': 'conv_tcgen05_halo_kernel fwd + dgrad (implicit GEMM, tcgen05 kind::tf32, cta_group::2 pairs where planned)',
                              'achieved': conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0, 'peak': peak_tf,
                              'unit': 'TFLOP/s', 'frac': (conv_fl / (conv_ms * 1e-3) / 1e12 / peak_tf) if conv_ms else 0.0,
                              'traffic': None, 'peak_source': peak_src, 'ms_per_step_in_kernel': conv_ms},
-                'wgrad': {'kernel': 'conv_wgrad_packed_kernel (MN-major tf32 UMMA, filter taps packed into the MMA N dimension, deterministic two-pass reduce) + conv_wgrad_tcgen05_kernel for stride 2',
+                'wgrad': {'kernel': 'conv_wgrad_packed_kernel (MN-major tf32 UMMA, filter taps packed into the MMA N dimension, stride-2 layers as 4 parity classes in one launch, deterministic two-pass reduce)',
                           'achieved_tflops': wg_fl / (wg_ms * 1e-3) / 1e12 if wg_ms else 0.0, 'ms_per_step_in_kernel': wg_ms},
                 'other_kernels_ms_per_step': {k: v[0] for k, v in by.items() if k not in ('conv', 'wgrad')}}
         print(json.dumps(line))
@@ -446,7 +446,7 @@ def main_ours(args):
     for f in sorted(glob.glob(os.path.join(ROOT, 'profiles', '*conv_traffic.json'))):
         t = json.load(open(f))
         traffic, traffic_src = t.get('bytes_per_launch'), t.get('source')
-    roofline = {'bound': 'tensor', 'kernel': 'conv_implicit_gemm (ramnet_conv_fwd, all instances)',
+    roofline = {'bound': 'tensor', 'kernel': 'conv_tcgen05_halo_kernel (ramnet_conv_fwd, all instances: implicit GEMM, tcgen05 kind::tf32, cta_group::2 pairs where planned)',
                 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
                 'traffic': traffic, 'traffic_unit': 'DRAM bytes per conv launch (read+write), ncu', 'traffic_source': traffic_src, 'peak_source': peak_src + ', bf16 sustained; kind::tf32 nominal peak is half of bf16',
                 'launches_per_step': n_conv, 'ms_per_step_in_kernel': conv_ms,
