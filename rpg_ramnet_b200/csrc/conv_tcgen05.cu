@@ -1039,6 +1039,8 @@ struct WpGeom {
     int r0, dr, s0, ds;      // filter tap of (row shift u, N block j): (r0 + dr*u, s0 + ds*j)
     int x5d, py, px;         // stride 2: X is read through the 5-D parity view (2C, W/2, 2, H/2, N), plane (py, px)
     int head_cin;            // > 0: X is ramnet_head_im2row's tensor (channel = dx*Cin + ci) and dW is the head's [Cout][Cin][5][5]
+    int mfold;               // 1: the M operand has only 64 channels; MMA rows 64..127 hold the SAME channels read RG image rows
+                             // higher, i.e. the filter rows u + RG: one CTA covers 2*RG row shifts and no MMA row is wasted
     int m_from_x;
     int Mch, Nch;            // channels of the M / N operand
     int m_blocks, n_boxes;   // ceil(Mch / 128), Nch / 32
@@ -1144,9 +1146,10 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_packed_kernel(const __gri
                     else tma_load_4d(dst, mx, full_bar + stage, c, x, y, img);
                 };
                 for (int q = 0; q < 4; ++q) {
-                    const int ch = (mb * 4 + q) * kChunk;
-                    if (g.m_from_x) load_x(sa + q * m_box, ch, x0, y0);
-                    else tma_load_4d(sa + q * m_box, &map_dz, full_bar + stage, ch, x0, y0, img);   // ch >= Cout: zeros
+                    int ch = (mb * 4 + q) * kChunk, ym = y0;
+                    if (g.mfold && q >= 2) { ch -= 2 * kChunk; ym -= g.RG; }      // second copy of the 64 channels, RG rows up
+                    if (g.m_from_x) load_x(sa + q * m_box, ch, x0, ym);
+                    else tma_load_4d(sa + q * m_box, &map_dz, full_bar + stage, ch, x0, ym, img);   // ch >= Cout: zeros
                 }
                 if (g.m_from_x) tma_load_4d(sb, &map_dz, full_bar + stage, nb * kChunk, x0 + nx, y0 + ny, img);
                 else load_x(sb, nb * kChunk, x0 + nx, y0 + ny);
@@ -1568,9 +1571,13 @@ __global__ void __launch_bounds__(256) wgrad_packed_sum_kernel(float *__restrict
 // they form contiguous runs (for one output channel: 32 input channels x the group's filter rows).
 constexpr int kWpPitch = 32 * 33 + 1;   // shared-memory words per (row shift, tap) plane: conflict-free both ways
 __global__ void __launch_bounds__(1024) wgrad_packed_scatter_kernel(const float *__restrict__ sum, float *__restrict__ dw,
-                                                                   const __grid_constant__ WpBatch batch, int groups) {
+                                                                   const __grid_constant__ WpBatch batch, int groups,
+                                                                   int splits) {
+    // splits > 1: the pixel splits have not been summed by pass 1 (few splits: summing them while staging the tile
+    // saves a launch and a pass over the workspace); the order of the additions is fixed either way
     const WpGeom &g = batch.g[blockIdx.y];
     sum += (size_t)blockIdx.y * batch.part_stride;
+    const size_t split_stride = (size_t)groups * 128 * g.ncols;
     extern __shared__ float plane[];    // [RG * kw][32 c32][33] (+1 per plane)
     const int taps = g.ks * g.ks, Ct = g.C0 + g.C1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1585,8 +1592,12 @@ __global__ void __launch_bounds__(1024) wgrad_packed_scatter_kernel(const float 
         const int nu = min(g.RG, g.kh - u0);              // valid row shifts of this group
         const int nt = nu * g.kw;                         // taps held by this tile
         __syncthreads();
-        for (int col = warp; col < nt * kChunk; col += (int)(blockDim.x >> 5))  // col = (u * kw + j) * 32 + c32
-            plane[(col >> 5) * kWpPitch + (col & 31) * 33 + lane] = tile[(size_t)col * 128 + lane];
+        for (int col = warp; col < nt * kChunk; col += (int)(blockDim.x >> 5)) {  // col = (u * kw + j) * 32 + c32
+            const float *src = tile + (size_t)col * 128 + lane;
+            float acc = src[0];
+            for (int sp = 1; sp < splits; ++sp) acc += src[(size_t)sp * split_stride];
+            plane[(col >> 5) * kWpPitch + (col & 31) * 33 + lane] = acc;
+        }
         __syncthreads();
         const int m0 = mb * 128 + rb * 32, n0 = nb * kChunk;
         const int count = 32 * 32 * nt;
@@ -1601,9 +1612,10 @@ __global__ void __launch_bounds__(1024) wgrad_packed_scatter_kernel(const float 
                     const int t = o % nt;                     // (row shift, N block) of the tile, fastest index
                     const int mid = (o / nt) & 31, outer = o / (nt * 32);
                     const int row = g.m_from_x ? mid : outer, c32 = g.m_from_x ? outer : mid;   // -> (co, ci, tap) order
-                    const int mch = m0 + row, nch = n0 + c32;
-                    if (mch < g.Mch && nch < g.Nch) {
-                        const int u = u0 + t / g.kw, j = t % g.kw;
+                    int mch = m0 + row, nch = n0 + c32, ufold = 0;
+                    if (g.mfold && mch >= 64) { mch -= 64; ufold = g.RG; }        // rows 64..127: same channels, filter rows u + RG
+                    if (mch < g.Mch && nch < g.Nch && u0 + t / g.kw + ufold < g.kh) {
+                        const int u = u0 + t / g.kw + ufold, j = t % g.kw;
                         const int tap = (g.r0 + g.dr * u) * g.ks + g.s0 + g.ds * j;
                         const int co = g.m_from_x ? nch : mch, ci = g.m_from_x ? mch : nch;
                         if (g.head_cin > 0) {          // unrolled head input: channel ci = dx*Cin + ci'
@@ -1693,9 +1705,16 @@ bool plan_wgrad_packed(const ramnet_handle *h, const ramnet_conv_desc *d, int cl
     if (g.RG > g.kh) g.RG = g.kh;
     g.prof = nullptr;
     g.row_groups = (g.kh + g.RG - 1) / g.RG;
+    // 64-channel M operand with more filter rows than one CTA holds (dec2: 64 -> 32, 5x5): fold the second row group
+    // into the idle upper half of the 128 MMA rows instead of running it as a second, half-empty CTA group
+    // (RAMNET_WGRAD_FOLD=1 opts in: written after the round's GPU budget was spent, not yet validated on hardware.)
+    static const bool fold_on = [] { const char *e = getenv("RAMNET_WGRAD_FOLD"); return e && e[0] == '1'; }();
+    g.mfold = (fold_on && d->stride == 1 && head_cin == 0 && g.Mch == 64 && g.kh > g.RG && g.kh <= 2 * g.RG) ? 1 : 0;
+    if (g.mfold) g.row_groups = 1;
     g.HXw = 8 + g.kw - 1; g.HYw = g.TR + g.RG - 1;
     g.ncols = g.RG * g.kw * kChunk;
-    g.tiles_x = (g.W + 7) / 8; g.tiles_y = (g.H + g.TR - 1) / g.TR;
+    // folded rows read the M operand RG rows above the tile: RG extra rows of tiles at the bottom cover its last rows
+    g.tiles_x = (g.W + 7) / 8; g.tiles_y = (g.H + (g.mfold ? g.RG : 0) + g.TR - 1) / g.TR;
     const int64_t total = (int64_t)g.tiles_x * g.tiles_y * g.N;
     if (total > 0x7fffffff) return false;
     g.total_tiles = (int)total;
@@ -1906,7 +1925,11 @@ int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz
         RAMNET_LAUNCH_CHECK(h);
         if (do_prof) cudaEventRecord(ev[1], s);
         const int64_t elems = (int64_t)pgroups * 128 * p.ncols;
-        if (psplits > 1) {
+        // few splits: summed inside the scatter kernel (RAMNET_WGRAD_FUSED_SUM=1 opts in: written after the round's GPU
+        // budget was spent, not yet validated on hardware; the default runs the separate sum pass)
+        static const bool fuse_on = [] { const char *e = getenv("RAMNET_WGRAD_FUSED_SUM"); return e && e[0] == '1'; }();
+        const bool fused_sum = fuse_on && psplits <= 16;
+        if (psplits > 1 && !fused_sum) {
             dim3 sgrid((unsigned)imin64((elems + 63) / 64, (int64_t)h->sm_count * 8), (unsigned)batch.n);
             wgrad_packed_sum_kernel<<<sgrid, 256, 0, s>>>((float *)workspace, elems, psplits, batch.part_stride);
             RAMNET_LAUNCH_CHECK(h);
@@ -1918,7 +1941,8 @@ int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz
             sc_configured = true;
         }
         dim3 cgrid((unsigned)imin64((int64_t)pgroups * 4, (int64_t)h->sm_count * 2), (unsigned)batch.n);
-        wgrad_packed_scatter_kernel<<<cgrid, 1024, sc_smem, s>>>((const float *)workspace, dw, batch, pgroups);
+        wgrad_packed_scatter_kernel<<<cgrid, 1024, sc_smem, s>>>((const float *)workspace, dw, batch, pgroups,
+                                                                 fused_sum ? psplits : 1);
         RAMNET_LAUNCH_CHECK(h);
         if (do_prof) {
             cudaEventRecord(ev[2], s);
