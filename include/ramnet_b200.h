@@ -193,6 +193,11 @@ int ramnet_depth_to_label(ramnet_handle *h, const float *depth, float *label, in
 int ramnet_depth_metrics(ramnet_handle *h, const float *pred, const float *target, int N, int64_t hw, float eps,
                          double *out, void *stream);
 
+/* Planner introspection, host only (no CUDA call, no handle): the configuration the forward halo kernel and the
+ * tap-packed weight gradient would use for `d` on a device with `sm_count` SMs, as one line of key=value pairs
+ * written to buf; returns its length.  For tests (planner invariants without a GPU) and tuning. */
+int ramnet_plan_describe(const ramnet_conv_desc *d, int sm_count, char *buf, size_t buf_bytes);
+
 /* ---- layout helpers ----------------------------------------------------- */
 int ramnet_nchw_to_nhwc(ramnet_handle *h, const float *x, float *y, int N, int C, int H, int W,
                         int flags, void *stream);

@@ -46,6 +46,7 @@ SIGNATURES = {
                                        c_int, c_void_p]),
     'ramnet_pack_weights_dgrad': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                           c_void_p]),
+    'ramnet_plan_describe': (c_int, [POINTER(ConvDesc), c_int, c_char_p, c_size_t]),
     'ramnet_voxel_normalize': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     'ramnet_depth_to_label': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_void_p]),
     'ramnet_depth_metrics': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float, c_void_p, c_void_p]),

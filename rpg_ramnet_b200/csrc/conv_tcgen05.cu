@@ -2314,3 +2314,48 @@ extern "C" int ramnet_head_conv_tc(ramnet_handle *h, const float *xe_nhwc32, con
     EpiParams ep{bias, nullptr, nullptr, y_nhwc, nullptr, nullptr, Cout, flags};
     return conv_fwd_tf32_rect(h, &d, &r, xe_nhwc32, nullptr, w_packed, ep, (cudaStream_t)stream);
 }
+
+
+// ================================================================================================
+// Planner introspection (host only, no CUDA call): what the forward halo kernel and the tap-packed weight gradient
+// would launch for a layer on a device with `sm_count` SMs.  Used by tests/test_planner.py to check the planners'
+// invariants (shared memory, TMEM columns, divisibility) over a sweep of shapes without a GPU, and by humans to see
+// why a layer got its configuration.  Writes one line of `key=value` pairs; returns its length (0 when nothing fits).
+// ================================================================================================
+extern "C" int ramnet_plan_describe(const ramnet_conv_desc *d, int sm_count, char *buf, size_t buf_bytes) {
+    if (!d || !buf || buf_bytes == 0 || sm_count <= 0) return 0;
+    ramnet_handle h;
+    memset(&h, 0, sizeof(h));
+    h.device = -1;
+    h.sm_count = sm_count;
+    int n = 0;
+    auto put = [&](const char *fmt, auto... args) {
+        if ((size_t)n < buf_bytes) n += snprintf(buf + n, buf_bytes - (size_t)n, fmt, args...);
+    };
+    buf[0] = 0;
+    HaloGeom g;
+    const bool tf32_ok = d->C0 % kChunk == 0 && d->C1 % kChunk == 0 && d->Cout % 16 == 0 && d->C0 > 0 &&
+                         (d->stride == 1 || (d->H % 2 == 0 && d->W % 2 == 0));
+    if (tf32_ok && plan_halo(&h, d, nullptr, &g)) {
+        const size_t a_stride = (size_t)g.nplanes * g.plane_stride;
+        const size_t smem = g.a_stages * a_stride + (size_t)g.b_stages * g.tpg * (g.pair ? g.BN / 2 : g.BN) * kChunk * 4 +
+                            (2 * g.a_stages + 2 * g.b_stages + 4) * 8 + 16 + 32 * 4 + 1024;
+        put("halo=1 pair=%d ptx=%d pty=%d hx=%d hy=%d bn=%d a_stages=%d b_stages=%d tpg=%d taps=%d nbuf=%d items=%d "
+            "tmem_cols=%d smem=%zu nplanes=%d ", g.pair, g.PTX, g.PTY, g.HX, g.HY, g.BN, g.a_stages, g.b_stages, g.tpg,
+            g.kh * g.kw, g.nbuf, g.items, g.nbuf * g.PTX * g.PTY * g.BN, smem, g.nplanes);
+    } else {
+        put("halo=0 ");
+    }
+    WpBatch b;
+    int splits = 0, groups = 0;
+    if (plan_wgrad_batch(&h, d, &b, &splits, &groups)) {
+        const WpGeom &p = b.g[0];
+        const size_t smem = (size_t)p.stages * p.stage_bytes + (2 * p.stages + 1) * 8 + 16 + 1024;
+        put("wgrad=1 problems=%d m_from_x=%d rg=%d tr=%d ncols=%d groups=%d splits=%d tiles_per_cta=%d total_tiles=%d stages=%d "
+            "smem=%zu workspace=%zu hxw=%d hyw=%d", b.n, p.m_from_x, p.RG, p.TR, p.ncols, groups, splits, p.tiles_per_cta,
+            p.total_tiles, p.stages, smem, (size_t)b.n * (size_t)b.part_stride * sizeof(float), p.HXw, p.HYw);
+    } else {
+        put("wgrad=0");
+    }
+    return n;
+}
