@@ -76,8 +76,11 @@ enum {
 };
 
 enum {
-    RAMNET_FLAG_ROUND_TF32 = 1 /* round every stored output to TF32 (rna) so a
-                                  following kind::tf32 MMA truncates nothing */
+    RAMNET_FLAG_ROUND_TF32 = 1, /* round every stored output to TF32 (rna) so a
+                                   following kind::tf32 MMA truncates nothing */
+    RAMNET_FLAG_HPACK = 2       /* ramnet_conv_fwd: w_packed is in ramnet_pack_weights_hpack's layout (horizontal taps as
+                                   GEMM columns); stride 1, ksize 3/5, bias / relu / residual / pred epilogues.
+                                   Opt-in (RAMNET_HPACK=1 on the Python side), not yet validated on hardware. */
 };
 
 /* One implicit-GEMM convolution:  y[m, n] = epi( sum_{tap,c} x[pix(m,tap), c] * w[tap, n, c] ).
@@ -149,6 +152,10 @@ int ramnet_conv_fwd(ramnet_handle *h, const ramnet_conv_desc *d, const float *x0
 /* [Cout, Cin, k, k] fp32 (nn.Conv2d layout) -> the layout `mma_kind` consumes:
  *   FP32: [k*k][Cin][Cout]           TF32: [k*k][Cout][Cin], values rounded to TF32 (rna).
  * `lstm_interleave` != 0 permutes output channels to 4c+g (RAMNET_EPI_LSTM). */
+/* [Cout, Cin, k, k] -> [r][slice * k * cs + s * cs + co_l][Cin] with cs = 32 (16 when Cout % 32 != 0), TF32-rounded:
+ * the layout RAMNET_FLAG_HPACK launches read (csrc/conv_tcgen05.cu fill_hpack; tests/test_hpack_index_algebra.py). */
+int ramnet_pack_weights_hpack(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin,
+                              int ksize, void *stream);
 int ramnet_pack_weights(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin,
                         int ksize, int mma_kind, int lstm_interleave, void *stream);
 

@@ -137,6 +137,7 @@ static int validate_desc(const ramnet_conv_desc *d) {
     RAMNET_CHECK_ARG(d->Cout > 0 && d->Cout % 4 == 0, "conv: Cout=%d must be a positive multiple of 4", d->Cout);
     RAMNET_CHECK_ARG(d->epilogue >= RAMNET_EPI_BIAS && d->epilogue <= RAMNET_EPI_BIAS_RELU_PRED, "conv: bad epilogue %d", d->epilogue);
     RAMNET_CHECK_ARG(d->mma_kind == RAMNET_MMA_FP32 || d->mma_kind == RAMNET_MMA_TF32, "conv: bad mma_kind %d", d->mma_kind);
+    RAMNET_CHECK_ARG(!(d->flags & RAMNET_FLAG_HPACK) || d->mma_kind == RAMNET_MMA_TF32, "conv: RAMNET_FLAG_HPACK needs mma_kind=TF32");
     if (d->epilogue == RAMNET_EPI_GRU_RU) RAMNET_CHECK_ARG(d->Cout % 8 == 0, "conv: GRU_RU needs Cout = 2C with C%%4 == 0");
     if (d->epilogue == RAMNET_EPI_LSTM) RAMNET_CHECK_ARG(d->Cout % 16 == 0, "conv: LSTM needs Cout = 4C with C%%4 == 0");
     return RAMNET_OK;

@@ -332,6 +332,8 @@ struct HaloGeom {
     int BN, n_slices;        // GEMM columns per item, Cout / BN
     int a_stages, b_stages;
     int tpg;                 // filter taps per weight stage: one TMA box / one barrier round trip / one commit per tpg taps
+    int hpack, cs, kwp;      // hpack: the kwp horizontal taps are GEMM columns (N = kwp * cs) of kh row-shifted MMAs over a
+                             // 32 px x 4 row tile; the epilogue sums the taps across the lanes of an image row (see fill_hpack)
     int nbuf;                // TMEM accumulator buffers
     int pair;                // 1: CTA-pair mode (cta_group::2, M = 256): a work item is two patches x one BN-wide slice
     int items;               // patches (pair mode: patch pairs) * n_slices
@@ -470,7 +472,7 @@ __device__ __forceinline__ void halo_arrive_leader(uint64_t *bar) {
     }
 }
 
-template <int EPI, bool PAIR>
+template <int EPI, bool PAIR, bool HPACK = false>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(const __grid_constant__ CUtensorMap map_x0,
                                                                             const __grid_constant__ CUtensorMap map_x1,
                                                                             const __grid_constant__ CUtensorMap map_w,
@@ -568,8 +570,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
         t /= g.patches_x;
         const int pyi = t % g.patches_y;
         img = t / g.patches_y;
-        x0 = pxi * g.PTX * 8;
-        y0 = pyi * g.PTY * 16;
+        if constexpr (HPACK) {   // tiles of 32 columns overlap by kwp - 1; the first starts kwp/2 columns left of the image
+            x0 = pxi * (32 - (g.kwp - 1)) - (g.kwp >> 1);
+            y0 = pyi * g.PTY * 4;
+        } else {
+            x0 = pxi * g.PTX * 8;
+            y0 = pyi * g.PTY * 16;
+        }
         n0 = slice * g.BN;
     };
 
@@ -627,13 +634,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
         // ---------------- MMA issuer: warp-uniform loops, no divisions, one elected lane issues ----------------
         const uint32_t idesc = make_idesc_tf32_m(g.BN, PAIR ? 256 : 128);
         // descriptor bits above the 14-bit start-address field: LBO=16 B, SBO = one halo row, version 1, SWIZZLE_128B
-        const uint64_t a_hi = ((uint64_t)1 << 16) | ((uint64_t)((uint32_t)g.HX * 128u >> 4) << 32) | ((uint64_t)1 << 46) |
-                              ((uint64_t)2 << 61);
+        // hpack: an M tile is 4 image rows of 32 pixels = 16 consecutive 8-pixel groups of the dense 32-wide box (SBO = 1 KB)
+        const uint32_t sbo = HPACK ? 1024u : (uint32_t)g.HX * 128u;
+        const uint64_t a_hi = ((uint64_t)1 << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
         uint32_t tile_off16[4];   // (tile origin inside the halo buffer) / 16 bytes
 #pragma unroll
         for (int tl = 0; tl < 4; ++tl) {
             const int tx = tl & (g.PTX - 1), ty = tl >> g.ptx_log2;
-            tile_off16[tl] = (uint32_t)((ty * 16 * g.HX + tx * 8) * 8);
+            tile_off16[tl] = HPACK ? (uint32_t)(tl * 4 * g.HX * 8) : (uint32_t)((ty * 16 * g.HX + tx * 8) * 8);
         }
         int sa = 0, sb = 0;
         uint32_t pa = 0, pb = 0;
@@ -736,7 +744,60 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
             };
             auto next_unit = [&](const Unit &u) { return (u.j + 1 < nch) ? make_unit(u.tl, u.j + 1) : make_unit(u.tl + 1, 0); };
 
-            if constexpr (EPI == RAMNET_EPI_BIAS_RELU_PRED) {
+            if constexpr (HPACK) {
+                // thread = output pixel (image row `quarter` of the tile, column `lane`); accumulator column s * cs + co holds
+                // tap s of channel co for the pixel of the SAME lane: the output is the sum over s of lane + s - kwp/2
+                if constexpr (EPI == RAMNET_EPI_BIAS || EPI == RAMNET_EPI_BIAS_RELU || EPI == RAMNET_EPI_BIAS_RES_RELU ||
+                              EPI == RAMNET_EPI_BIAS_RELU_PRED) {
+                    constexpr bool kPred = EPI == RAMNET_EPI_BIAS_RELU_PRED;
+                    const int padx = g.kwp >> 1, cs = g.cs;
+                    const int nch0 = (n0 / g.BN) * cs;                      // first output channel of this slice
+                    if (!kPred || half == 0) {
+                        for (int tl = 0; tl < ntiles; ++tl) {
+                            const int ox = x0 + lane, oy = y0 + tl * 4 + quarter;
+                            const bool valid = lane >= padx && lane < 32 - padx && ox >= 0 && ox < g.Wo && oy < g.Ho && img < g.N;
+                            const int64_t m = ((int64_t)img * g.Ho + oy) * g.Wo + ox;
+                            float dot = 0.f;
+                            for (int c0 = kPred ? 0 : half * 16; c0 < cs; c0 += kPred ? 16 : 16 * kParts) {
+                                float acc[16];
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+                                for (int sx = 0; sx < g.kwp; ++sx) {
+                                    uint32_t r[16];
+                                    tmem_ld16_issue(lane_base + (uint32_t)(tl * g.BN + sx * cs + c0), r);
+                                    tmem_ld_wait(r);
+                                    const int src = (lane + sx - padx) & 31;   // out-of-tile sources only feed invalid lanes
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) acc[j] += __shfl_sync(0xffffffffu, __uint_as_float(r[j]), src);
+                                }
+                                if constexpr (kPred) {
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        const float4 bb = ep.bias ? __ldg(reinterpret_cast<const float4 *>(ep.bias + nch0 + c0) + q)
+                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                                        const float4 ww = __ldg(reinterpret_cast<const float4 *>(ep.aux0 + nch0 + c0) + q);
+                                        dot = fmaf(fmaxf(acc[4 * q] + bb.x, 0.f), ww.x, dot);
+                                        dot = fmaf(fmaxf(acc[4 * q + 1] + bb.y, 0.f), ww.y, dot);
+                                        dot = fmaf(fmaxf(acc[4 * q + 2] + bb.z, 0.f), ww.z, dot);
+                                        dot = fmaf(fmaxf(acc[4 * q + 3] + bb.w, 0.f), ww.w, dot);
+                                    }
+                                } else if (valid) {
+                                    EpiAux<16> xa;
+                                    epilogue_prefetch<EPI, 16>(ep, m, nch0 + c0, xa);
+                                    epilogue_finish<EPI, 16>(ep, m, nch0 + c0, acc, xa);
+                                }
+                            }
+                            if constexpr (kPred) {
+                                if (valid) {
+                                    const float logit = dot + __ldg(ep.aux1);
+                                    if (ep.y1) ep.y1[m] = logit;
+                                    ep.y0[m] = sigmoidf_(logit);
+                                }
+                            }
+                        }
+                    }
+                }
+            } else if constexpr (EPI == RAMNET_EPI_BIAS_RELU_PRED) {
                 // fused 1x1 prediction head: every row's BN = Cout activations are reduced in registers by the
                 // first warp of each lane quarter; the 32-channel decoder output never leaves the SM
                 if (half == 0) {
@@ -1283,12 +1344,12 @@ int launch(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap &m1, const
     return RAMNET_OK;
 }
 
-template <int EPI, bool PAIR>
+template <int EPI, bool PAIR, bool HP = false>
 int launch_halo_pair(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap &m1, const CUtensorMap &mw,
                      const HaloGeom &g, const EpiParams &ep, size_t smem, cudaStream_t s) {
     static size_t configured = 0;
     if (smem > configured) {
-        RAMNET_CUDA(cudaFuncSetAttribute(conv_tcgen05_halo_kernel<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        RAMNET_CUDA(cudaFuncSetAttribute(conv_tcgen05_halo_kernel<EPI, true, HP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
         configured = smem;
     }
@@ -1312,7 +1373,7 @@ int launch_halo_pair(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap 
         cudaMemsetAsync(buf, 0, 64, s);
         HaloGeom gp = g;
         gp.prof = buf;
-        RAMNET_CUDA(cudaLaunchKernelEx(&cfg, conv_tcgen05_halo_kernel<EPI, true>, m0, m1, mw, gp, ep));
+        RAMNET_CUDA(cudaLaunchKernelEx(&cfg, conv_tcgen05_halo_kernel<EPI, true, HP>, m0, m1, mw, gp, ep));
         unsigned long long hbuf[8];
         cudaMemcpyAsync(hbuf, buf, 64, cudaMemcpyDeviceToHost, s);
         cudaStreamSynchronize(s);
@@ -1323,22 +1384,22 @@ int launch_halo_pair(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap 
                 pairs, g.items, hbuf[0] / n / 1e3, hbuf[1] / n / 1e3, hbuf[2] / n / 1e3, hbuf[3] / n / 1e3, hbuf[4] / n / 2e3,
                 hbuf[5] / n / 2e3, hbuf[6] / n / 16e3, hbuf[7] / n / 16e3);
     } else {
-        RAMNET_CUDA(cudaLaunchKernelEx(&cfg, conv_tcgen05_halo_kernel<EPI, true>, m0, m1, mw, g, ep));
+        RAMNET_CUDA(cudaLaunchKernelEx(&cfg, conv_tcgen05_halo_kernel<EPI, true, HP>, m0, m1, mw, g, ep));
     }
     RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;
 }
 
-template <int EPI>
+template <int EPI, bool HP = false>
 int launch_halo(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap &m1, const CUtensorMap &mw,
                 const HaloGeom &g, const EpiParams &ep, cudaStream_t s) {
     const size_t a_stride = (size_t)g.nplanes * g.plane_stride;
     const size_t smem = g.a_stages * a_stride + (size_t)g.b_stages * g.tpg * (g.pair ? g.BN / 2 : g.BN) * kChunk * 4 +
                         (2 * g.a_stages + 2 * g.b_stages + 4) * 8 + 16 + 32 * 4 + 1024;
-    if (g.pair) return launch_halo_pair<EPI, true>(h, m0, m1, mw, g, ep, smem, s);
+    if (g.pair) return launch_halo_pair<EPI, true, HP>(h, m0, m1, mw, g, ep, smem, s);
     static size_t configured = 0;
     if (smem > configured) {
-        RAMNET_CUDA(cudaFuncSetAttribute(conv_tcgen05_halo_kernel<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        RAMNET_CUDA(cudaFuncSetAttribute(conv_tcgen05_halo_kernel<EPI, false, HP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
         configured = smem;
     }
@@ -1350,7 +1411,7 @@ int launch_halo(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap &m1, 
         cudaMemsetAsync(buf, 0, 64, s);
         HaloGeom gp = g;
         gp.prof = buf;
-        conv_tcgen05_halo_kernel<EPI, false><<<grid, kHaloThreads, smem, s>>>(m0, m1, mw, gp, ep);
+        conv_tcgen05_halo_kernel<EPI, false, HP><<<grid, kHaloThreads, smem, s>>>(m0, m1, mw, gp, ep);
         unsigned long long hbuf[8];
         cudaMemcpyAsync(hbuf, buf, 64, cudaMemcpyDeviceToHost, s);
         cudaStreamSynchronize(s);
@@ -1361,7 +1422,7 @@ int launch_halo(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap &m1, 
                 grid, g.items, hbuf[0] / n / 1e3, hbuf[1] / n / 1e3, hbuf[2] / n / 1e3, hbuf[3] / n / 1e3, hbuf[4] / n / 1e3,
                 hbuf[5] / n / 1e3, hbuf[6] / n / 8e3, hbuf[7] / n / 8e3);
     } else {
-        RAMNET_CUDA(ramnet_launch(conv_tcgen05_halo_kernel<EPI, false>, dim3(grid), dim3(kHaloThreads), smem, s, true, m0, m1, mw, g, ep));
+        RAMNET_CUDA(ramnet_launch(conv_tcgen05_halo_kernel<EPI, false, HP>, dim3(grid), dim3(kHaloThreads), smem, s, true, m0, m1, mw, g, ep));
     }
     RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;
@@ -1391,6 +1452,7 @@ bool fill_halo(const ramnet_conv_desc *d, const RectSpec *rect, HaloGeom *g, int
     const int hi = fdiv(d->ksize - 1 - g->pad, d->stride);
     g->PTX = ptx; g->PTY = pty; g->ptx_log2 = ptx == 4 ? 2 : (ptx == 2 ? 1 : 0);
     g->HX = ptx * 8 + (hi - g->lo); g->HY = pty * 16 + (hi - g->lo);
+    g->hpack = 0; g->cs = 0; g->kwp = 0;
     g->kh = g->kw = d->ksize; g->lo_y = g->lo_x = g->lo;
     g->out_sy = g->out_sx = 1; g->out_oy = g->out_ox = 0; g->out_H = g->Ho; g->out_W = g->Wo;
     if (rect) {               // stride-1 launch with a rectangular tap set and / or a strided output view
@@ -1440,6 +1502,56 @@ bool fill_halo(const ramnet_conv_desc *d, const RectSpec *rect, HaloGeom *g, int
     if (a_st * a_stride + b_st * b_bytes > budget || b_st < 2) return false;
     g->a_stages = a_st; g->b_stages = b_st;
     return true;
+}
+
+// hpack configuration (RAMNET_FLAG_HPACK: weights packed by ramnet_pack_weights_hpack).  For a stride-1 ks x ks conv with
+// few output channels the ks horizontal taps become GEMM columns: per 32-channel chunk ks row-shifted MMAs of
+// N = ks * cs over a 32 px x 4 row tile instead of ks*ks MMAs of N = cs, and the epilogue adds the taps up across the
+// lanes of an image row (warp shuffles).  Index algebra: tests/test_hpack_index_algebra.py.
+bool fill_hpack(const ramnet_conv_desc *d, HaloGeom *g, int pty, int cs, int pair) {
+    const int ks = d->ksize, bn = ks * cs;
+    if (d->stride != 1 || (ks != 3 && ks != 5) || cs % 16 || d->Cout % cs || bn > 256 || pty < 1 || pty > 4) return false;
+    if (pair && (bn % 16 || (bn / 2) % 8)) return false;
+    if (pty * bn > 512) return false;
+    g->pair = pair;
+    g->N = d->N; g->H = d->H; g->W = d->W; g->Cout = d->Cout; g->C0 = d->C0; g->C1 = d->C1;
+    g->Ho = d->H; g->Wo = d->W;
+    g->ks = ks; g->pad = ks / 2; g->stride = 1; g->prof = nullptr; g->nplanes = 1; g->lo = -g->pad;
+    g->hpack = 1; g->cs = cs; g->kwp = ks;
+    g->kh = ks; g->kw = 1;                      // "taps" of the weight pipeline = filter rows
+    g->lo_y = -g->pad; g->lo_x = 0;
+    g->out_sy = g->out_sx = 1; g->out_oy = g->out_ox = 0; g->out_H = g->Ho; g->out_W = g->Wo;
+    g->PTX = 1; g->PTY = pty; g->ptx_log2 = 0;
+    g->HX = 32; g->HY = 4 * pty + ks - 1;
+    g->BN = bn; g->n_slices = d->Cout / cs;
+    g->patches_x = (g->Wo + (32 - (ks - 1)) - 1) / (32 - (ks - 1));
+    g->patches_y = (g->Ho + 4 * pty - 1) / (4 * pty);
+    const int64_t npatch = (int64_t)g->patches_x * g->patches_y * d->N;
+    const int64_t items = (pair ? (npatch + 1) / 2 : npatch) * g->n_slices;
+    if (items > 0x7fffffff) return false;
+    g->items = (int)items;
+    g->nbuf = (2 * pty * bn <= 512) ? 2 : 1;
+    g->plane_stride = (int)(((size_t)g->HX * g->HY * kChunk * 4 + 1023) & ~(size_t)1023);
+    const size_t a_stride = g->plane_stride, b_tile = (size_t)(pair ? bn / 2 : bn) * kChunk * 4, budget = 222 * 1024;
+    const int a_st = 2;
+    int tpg = 1;
+    const int cand[2] = {ks, 1};                // a whole chunk's filter rows in one weight stage when it fits
+    for (int c : cand)
+        if ((size_t)c * b_tile <= 56 * 1024 && a_st * a_stride + 3 * (size_t)c * b_tile <= budget) { tpg = c; break; }
+    g->tpg = tpg;
+    int b_st = (int)((budget - a_st * a_stride) / ((size_t)tpg * b_tile));
+    if (b_st > 10) b_st = 10;
+    if (b_st < 2) return false;
+    g->a_stages = a_st; g->b_stages = b_st;
+    return true;
+}
+
+bool plan_hpack(const ramnet_handle *h, const ramnet_conv_desc *d, HaloGeom *g) {
+    static const int pair_mode = [] { const char *e = getenv("RAMNET_PAIR"); return e ? atoi(e) : 1; }();
+    const int cs = d->Cout % 32 == 0 ? 32 : 16;
+    if (d->epilogue == RAMNET_EPI_BIAS_RELU_PRED && cs != d->Cout) return false;    // one slice: whole-row reduction
+    if (pair_mode >= 1 && fill_hpack(d, g, 1, cs, 1)) return true;
+    return fill_hpack(d, g, 1, cs, 0);
 }
 
 // Cycle model of one launch (per SM), from measurements on B200:
@@ -2026,16 +2138,24 @@ int conv_fwd_tf32_rect(ramnet_handle *h, const ramnet_conv_desc *d, const RectSp
                          d->epilogue == RAMNET_EPI_BIAS_RELU_PRED,
                      "conv_fwd(tf32): outputs and epilogue operands must be 32-byte aligned (256-bit stores)");
     HaloGeom hg;
-    const bool halo_ok = plan_halo(h, d, rect, &hg);
+    const bool want_hpack = (d->flags & RAMNET_FLAG_HPACK) != 0;
+    if (want_hpack) {
+        const bool epi_ok = d->epilogue == RAMNET_EPI_BIAS || d->epilogue == RAMNET_EPI_BIAS_RELU ||
+                            d->epilogue == RAMNET_EPI_BIAS_RES_RELU || d->epilogue == RAMNET_EPI_BIAS_RELU_PRED;
+        if (rect || !epi_ok || !plan_hpack(h, d, &hg))
+            return ramnet_set_error(RAMNET_EUNSUPPORTED, "conv_fwd: RAMNET_FLAG_HPACK weights but no hpack configuration for "
+                                    "this layer (stride 1, ksize 3/5, bias / relu / residual / pred epilogues only)");
+    }
+    const bool halo_ok = want_hpack || plan_halo(h, d, rect, &hg);
     if (!halo_ok && rect)
         return ramnet_set_error(RAMNET_EUNSUPPORTED, "conv_fwd: no halo-kernel configuration for a rectangular / strided launch");
     if (!halo_ok && d->epilogue == RAMNET_EPI_BIAS_RELU_PRED)
         return ramnet_set_error(RAMNET_EUNSUPPORTED, "conv_fwd: no halo-kernel configuration for the fused prediction epilogue");
     if (halo_ok) {
         if (getenv("RAMNET_DEBUG"))
-            fprintf(stderr, "[ramnet] halo plan s%d %dx%d C=%d+%d->%d k%d: tiles %dx%d HX=%d HY=%d BN=%d a_st=%d b_st=%d tpg=%d nbuf=%d items=%d pair=%d\n",
+            fprintf(stderr, "[ramnet] halo plan s%d %dx%d C=%d+%d->%d k%d: tiles %dx%d HX=%d HY=%d BN=%d a_st=%d b_st=%d tpg=%d nbuf=%d items=%d pair=%d hpack=%d\n",
                     d->stride, d->H, d->W, d->C0, d->C1, d->Cout, d->ksize, hg.PTX, hg.PTY, hg.HX, hg.HY, hg.BN, hg.a_stages,
-                    hg.b_stages, hg.tpg, hg.nbuf, hg.items, hg.pair);
+                    hg.b_stages, hg.tpg, hg.nbuf, hg.items, hg.pair, hg.hpack);
         CUtensorMap m0, m1, mw;
         auto enc_act = [&](CUtensorMap *m, const float *x, int C) {
             if (d->stride == 1) {
@@ -2060,11 +2180,21 @@ int conv_fwd_tf32_rect(ramnet_handle *h, const ramnet_conv_desc *d, const RectSp
             m1 = m0;
         }
         const int Ct = d->C0 + d->C1, taps = hg.kh * hg.kw;
-        cuuint64_t wd[3] = {(cuuint64_t)Ct, (cuuint64_t)d->Cout, (cuuint64_t)taps};
-        cuuint64_t ws[2] = {(cuuint64_t)Ct * 4, (cuuint64_t)Ct * d->Cout * 4};
+        const int wrows = hg.hpack ? d->Cout * hg.kwp : d->Cout;        // hpack: rows (slice, tap s, channel) per filter row
+        cuuint64_t wd[3] = {(cuuint64_t)Ct, (cuuint64_t)wrows, (cuuint64_t)taps};
+        cuuint64_t ws[2] = {(cuuint64_t)Ct * 4, (cuuint64_t)Ct * wrows * 4};
         cuuint32_t wb[3] = {kChunk, (cuuint32_t)(hg.pair ? hg.BN / 2 : hg.BN), (cuuint32_t)hg.tpg};
         rc = encode(h, &mw, wp, 3, wd, ws, wb);
         if (rc) return rc;
+        if (hg.hpack) {
+            switch (d->epilogue) {
+                case RAMNET_EPI_BIAS: return launch_halo<RAMNET_EPI_BIAS, true>(h, m0, m1, mw, hg, ep, s);
+                case RAMNET_EPI_BIAS_RELU: return launch_halo<RAMNET_EPI_BIAS_RELU, true>(h, m0, m1, mw, hg, ep, s);
+                case RAMNET_EPI_BIAS_RES_RELU: return launch_halo<RAMNET_EPI_BIAS_RES_RELU, true>(h, m0, m1, mw, hg, ep, s);
+                case RAMNET_EPI_BIAS_RELU_PRED: return launch_halo<RAMNET_EPI_BIAS_RELU_PRED, true>(h, m0, m1, mw, hg, ep, s);
+                default: return ramnet_set_error(RAMNET_EUNSUPPORTED, "conv_fwd: hpack epilogue");
+            }
+        }
         switch (d->epilogue) {
             case RAMNET_EPI_BIAS: return launch_halo<RAMNET_EPI_BIAS>(h, m0, m1, mw, hg, ep, s);
             case RAMNET_EPI_BIAS_RELU: return launch_halo<RAMNET_EPI_BIAS_RELU>(h, m0, m1, mw, hg, ep, s);
@@ -2358,4 +2488,35 @@ extern "C" int ramnet_plan_describe(const ramnet_conv_desc *d, int sm_count, cha
         put("wgrad=0");
     }
     return n;
+}
+
+
+// w_oihw [Cout][Cin][ks][ks] -> hpack layout [r][slice * ks * cs + s * cs + co_l][Cin] (K-major B operand, TF32-rounded):
+// the weight tile of filter row r holds, for every output-channel slice of cs channels, the ks horizontal taps as
+// consecutive groups of cs GEMM columns.
+namespace {
+__global__ void pack_hpack_kernel(const float *__restrict__ w, float *__restrict__ out, int Cout, int Cin, int ks, int cs) {
+    const int64_t total = (int64_t)ks * ks * Cout * Cin;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cin);
+        int64_t t = i / Cin;
+        const int row = (int)(t % ((int64_t)ks * Cout));      // slice * ks * cs + s * cs + co_l
+        const int r = (int)(t / ((int64_t)ks * Cout));
+        const int slice = row / (ks * cs), rem = row % (ks * cs), sx = rem / cs, col = rem % cs;
+        const int co = slice * cs + col;
+        out[i] = round_tf32(w[(((int64_t)co * Cin + c) * ks + r) * ks + sx]);
+    }
+}
+}  // namespace
+
+extern "C" int ramnet_pack_weights_hpack(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin,
+                                         int ksize, void *stream) {
+    RAMNET_CHECK_ARG(h && w_oihw && w_packed && Cout > 0 && Cout % 16 == 0 && Cin > 0 && (ksize == 3 || ksize == 5),
+                     "pack_weights_hpack: bad argument");
+    const int cs = Cout % 32 == 0 ? 32 : 16;
+    const int64_t total = (int64_t)ksize * ksize * Cout * Cin;
+    pack_hpack_kernel<<<(unsigned)imin64((total + 255) / 256, (int64_t)h->sm_count * 8), 256, 0, (cudaStream_t)stream>>>(
+        w_oihw, w_packed, Cout, Cin, ksize, cs);
+    RAMNET_LAUNCH_CHECK(h);
+    return RAMNET_OK;
 }

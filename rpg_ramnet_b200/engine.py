@@ -104,11 +104,13 @@ def pack_conv(cache: WeightCache, key, conv, kind: int, norm_mod=None, norm_kind
         w, b = conv.weight.detach().float(), None if conv.bias is None else conv.bias.detach().float()
         w, b = _fold_norm(w, b, norm_mod, norm_kind, training)
         p = Packed()
-        p.w = ops.pack_weights(w, kind)
+        hp = ops.hpack_eligible(w.shape[0], w.shape[2], conv.stride[0], kind)
+        p.w = ops.pack_weights_hpack(w) if hp else ops.pack_weights(w, kind)
         p.b = None if b is None else b.contiguous()
         p.Cout, p.ksize, p.stride = w.shape[0], w.shape[2], conv.stride[0]
         return p
-    return cache.get(key, [conv.weight, conv.bias] + _norm_sources(norm_mod), (kind, training), build)
+    hp_key = ops.hpack_eligible(conv.weight.shape[0], conv.weight.shape[2], conv.stride[0], kind)
+    return cache.get(key, [conv.weight, conv.bias] + _norm_sources(norm_mod), (kind, training, hp_key), build)
 
 
 def pack_head(cache: WeightCache, key, conv, tc: bool = False) -> Packed:

@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._lib import (ConvDesc, EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RELU_PRED, EPI_BIAS_RES_RELU, EPI_GRU_OUT, EPI_GRU_RU,  # noqa
                    EPI_LSTM,
-                   FLAG_ROUND_TF32, MMA_FP32, MMA_TF32, check)
+                   FLAG_HPACK, FLAG_ROUND_TF32, MMA_FP32, MMA_TF32, check)
 
 
 def _stream(t: torch.Tensor):
@@ -176,6 +176,23 @@ def head_conv_tc(xe: torch.Tensor, w_packed: torch.Tensor, b: Optional[torch.Ten
     return y
 
 
+def hpack_eligible(Cout: int, ksize: int, stride: int, mma_kind: int) -> bool:
+    """Layers the horizontal-tap-packed forward (RAMNET_FLAG_HPACK) is meant for: few output channels at stride 1, where a
+    128 x 32 x 8 MMA per tap is bound by the A-operand shared-memory reads.  Opt-in (RAMNET_HPACK=1): written after the
+    round's GPU budget was spent, validated on the CPU only (tests/test_hpack_index_algebra.py)."""
+    return (os.environ.get('RAMNET_HPACK', '0') == '1' and mma_kind == MMA_TF32 and stride == 1 and ksize in (3, 5)
+            and Cout == 32)
+
+
+def pack_weights_hpack(w_oihw: torch.Tensor) -> torch.Tensor:
+    w = w_oihw.detach().contiguous().float()
+    Cout, Cin, k, _ = w.shape
+    out = torch.empty(w.numel(), dtype=torch.float32, device=w.device)
+    check(_lib.load().ramnet_pack_weights_hpack(_h(w), _p(w), _p(out), Cout, Cin, k, _stream(w)))
+    out._ramnet_hpack = True          # conv_fwd sets RAMNET_FLAG_HPACK for weights packed this way
+    return out
+
+
 def pack_weights(w_oihw: torch.Tensor, mma_kind: int, lstm_interleave: bool = False) -> torch.Tensor:
     w = w_oihw.detach().contiguous().float()
     Cout, Cin, k, _ = w.shape
@@ -253,7 +270,8 @@ def conv_fwd(x0: torch.Tensor, x1: Optional[torch.Tensor], w_packed: torch.Tenso
         for a, nm in ((aux0, 'aux0'), (aux1, 'aux1')):
             if a is not None:
                 _check_nhwc(a, 'conv_fwd ' + nm)
-    d = ConvDesc(N, H, W, C0, C1, Cout, ksize, stride, epilogue, mma_kind, FLAG_ROUND_TF32 if round_tf32 else 0, 0)
+    flags = (FLAG_ROUND_TF32 if round_tf32 else 0) | (FLAG_HPACK if getattr(w_packed, '_ramnet_hpack', False) else 0)
+    d = ConvDesc(N, H, W, C0, C1, Cout, ksize, stride, epilogue, mma_kind, flags, 0)
     lib = _lib.load()
     nws = lib.ramnet_conv_workspace_bytes(ctypes.byref(d))
     ws = _workspace(dev, nws)
