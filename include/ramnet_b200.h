@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RAMNET_ABI_VERSION 1
+#define RAMNET_ABI_VERSION 2
 
 enum {
     RAMNET_OK = 0,
@@ -272,13 +272,15 @@ int ramnet_upsample2x_bwd(ramnet_handle *h, const float *dy, float *dx, int N, i
  * grad[i] = scale * (2w/n)(d_i - lambda*mean(d)), 0 where d is NaN, reading n
  * and mean from `stats` on the device (no host sync).  For data-parallel
  * exact-loss mode all-reduce `stats` between the two calls. */
+#define RAMNET_LOSS_LOG_SPACE 1 /* d = log(pred) - log(target): scale_invariant_log_loss, model/loss.py:12-15 */
 int ramnet_si_loss_stats(ramnet_handle *h, const float *pred, const float *target, int64_t n,
-                         double *stats, void *stream);
+                         double *stats, int flags, void *stream);
 int ramnet_si_loss_value(ramnet_handle *h, const double *stats, float weight, float n_lambda,
                          float *loss_out, void *stream);
+/* scale_dev (nullable): device scalar multiplied into `scale` (autograd's grad_output, never read on the host). */
 int ramnet_si_loss_grad(ramnet_handle *h, const float *pred, const float *target, int64_t n,
-                        const double *stats, float weight, float n_lambda, float scale, float *grad,
-                        void *stream);
+                        const double *stats, float weight, float n_lambda, float scale,
+                        const float *scale_dev, int flags, float *grad, void *stream);
 
 /* ---- §8f-1  MultiScaleGradient loss -------------------------------------- *
  * Replaces model/loss.py:22-70 (4 x AvgPool2d + kornia spatial_gradient + boolean-mask sums) for C = 1 maps
@@ -287,8 +289,14 @@ int ramnet_si_loss_grad(ramnet_handle *h, const float *pred, const float *target
 int ramnet_msg_loss_stats(ramnet_handle *h, const float *pred, const float *target, int N, int H, int W,
                           int start_scale, int scales, double *stats, void *stream);
 int ramnet_msg_loss_value(ramnet_handle *h, const double *stats, int N, int scales, float *loss_out, void *stream);
+/* n_batch: batch size the value was normalised with (0 = N; the global batch when `stats` were all-reduced). */
 int ramnet_msg_loss_grad(ramnet_handle *h, const float *pred, const float *target, int N, int H, int W,
-                         int start_scale, int scales, const double *stats, float scale, float *grad, void *stream);
+                         int start_scale, int scales, const double *stats, int n_batch, float scale,
+                         const float *scale_dev, float *grad, void *stream);
+/* preview=True branch (model/loss.py:46-47, TensorBoard only): out [N,1,H/pool,W/pool] = kornia sobel magnitude
+ * sqrt(gx^2 + gy^2 + 1e-6) of AvgPool2d(pool)(pred - target). */
+int ramnet_msg_sobel_preview(ramnet_handle *h, const float *pred, const float *target, int N, int H, int W,
+                             int pool, float *out, void *stream);
 
 /* ---- a-14  Adam --------------------------------------------------------- *
  * Replaces torch.optim.Adam.step (built at base/base_trainer.py:36-37,
@@ -298,11 +306,13 @@ int ramnet_msg_loss_grad(ramnet_handle *h, const float *pred, const float *targe
 int ramnet_adam_step(ramnet_handle *h, float *p, const float *g, float *m, float *v, int64_t n,
                      double lr, double beta1, double beta2, double eps, double weight_decay, int step,
                      void *stream);
-/* Same update with the 1-based step number kept in device memory: *step_counter is incremented, then used.  Lets a
- * whole training step (forward, backward, optimiser) be captured in one CUDA graph and replayed. */
+/* Same update with the 1-based step number kept in device memory: *step_counter is incremented (when `increment`),
+ * then used.  Lets a whole training step (forward, backward, optimiser) be captured in one CUDA graph and replayed.
+ * A step split into several launches over slices of the flat buffer (bucketed gradient all-reduce) passes
+ * increment = 1 for its first slice only. */
 int ramnet_adam_step_dev(ramnet_handle *h, float *p, const float *g, float *m, float *v, int64_t n, double lr,
                          double beta1, double beta2, double eps, double weight_decay, int *step_counter,
-                         void *stream);
+                         int increment, void *stream);
 
 #ifdef __cplusplus
 }

@@ -16,6 +16,7 @@ MMA_FP32, MMA_TF32 = 0, 1
 EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RES_RELU, EPI_GRU_RU, EPI_GRU_OUT, EPI_LSTM, EPI_BIAS_RELU_PRED = range(7)
 FLAG_ROUND_TF32 = 1
 FLAG_HPACK = 2
+LOSS_LOG_SPACE = 1
 
 
 class ConvDesc(ctypes.Structure):
@@ -82,22 +83,23 @@ SIGNATURES = {
     'ramnet_nchw_to_nhwc': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'ramnet_nhwc_to_nchw': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'ramnet_round_tf32': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
-    'ramnet_si_loss_stats': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    'ramnet_si_loss_stats': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     'ramnet_si_loss_value': (c_int, [c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p]),
     'ramnet_si_loss_grad': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float, c_float,
-                                    c_void_p, c_void_p]),
+                                    c_void_p, c_int, c_void_p, c_void_p]),
     'ramnet_msg_loss_stats': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'ramnet_msg_loss_value': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
-    'ramnet_msg_loss_grad': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_float,
-                                     c_void_p, c_void_p]),
+    'ramnet_msg_loss_grad': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                                     c_float, c_void_p, c_void_p, c_void_p]),
+    'ramnet_msg_sobel_preview': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'ramnet_adam_step_dev': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double,
-                                     c_double, c_double, c_double, c_void_p, c_void_p]),
+                                     c_double, c_double, c_double, c_void_p, c_int, c_void_p]),
     'ramnet_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double,
                                  c_double, c_double, c_double, c_int, c_void_p]),
 }
 
 _lib = None
-_lock = threading.Lock()
+_lock = threading.RLock()      # re-entrant: check() -> load() may run under handle()'s lock
 _handles = {}
 
 
@@ -124,18 +126,28 @@ def load():
 
 def check(rc: int):
     if rc != 0:
-        raise RamnetError(f'libramnet error {rc}: {load().ramnet_last_error().decode()}')
+        lib = _lib if _lib is not None else load()
+        raise RamnetError(f'libramnet error {rc}: {lib.ramnet_last_error().decode()}')
 
 
 def handle(device_index: int) -> c_void_p:
-    """One ramnet_handle per CUDA device per process."""
+    """One ramnet_handle per CUDA device per process.  Raises RamnetError (never blocks) when the device is missing,
+    out of range or not sm_100: ramnet_create runs outside the lock and its error string is read from the already
+    loaded library."""
     lib = load()
+    h = _handles.get(device_index)
+    if h is not None:
+        return h
+    new = c_void_p()
+    rc = lib.ramnet_create(int(device_index), ctypes.byref(new))
+    if rc != 0:
+        raise RamnetError(f'libramnet error {rc}: {lib.ramnet_last_error().decode()}')
     with _lock:
         h = _handles.get(device_index)
         if h is None:
-            h = c_void_p()
-            check(lib.ramnet_create(int(device_index), ctypes.byref(h)))
-            _handles[device_index] = h
+            _handles[device_index] = h = new
+        else:                                   # another thread won the race
+            lib.ramnet_destroy(new)
     return h
 
 

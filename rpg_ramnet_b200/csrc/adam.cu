@@ -74,12 +74,15 @@ __global__ void __launch_bounds__(256) adam_dev_step_kernel(float *__restrict__ 
 
 extern "C" int ramnet_adam_step_dev(ramnet_handle *h, float *p, const float *g, float *m, float *v, int64_t n, double lr,
                                     double beta1, double beta2, double eps, double weight_decay, int *step_counter,
-                                    void *stream) {
+                                    int increment, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && p && g && m && v && step_counter && n > 0, "adam_step_dev: bad argument");
     RAMNET_CHECK_ARG((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0,
                      "adam_step_dev: buffers must be 16-byte aligned");
-    adam_bump_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_counter);
-    RAMNET_LAUNCH_CHECK(h);
+    if (increment) {   // the first slice of a bucketed step increments; the other slices of the same step only read
+        adam_bump_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_counter);
+        RAMNET_LAUNCH_CHECK(h);
+    }
     const int blocks = (int)imin64(((n >> 2) + 255) / 256 + 1, (int64_t)h->sm_count * 8);
     adam_dev_step_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, (float)eps,
                                                                    (float)weight_decay, step_counter);
@@ -89,6 +92,7 @@ extern "C" int ramnet_adam_step_dev(ramnet_handle *h, float *p, const float *g, 
 
 extern "C" int ramnet_adam_step(ramnet_handle *h, float *p, const float *g, float *m, float *v, int64_t n, double lr,
                                 double beta1, double beta2, double eps, double weight_decay, int step, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && p && g && m && v, "adam_step: NULL argument");
     RAMNET_CHECK_ARG(n > 0 && step >= 1, "adam_step: n=%lld step=%d", (long long)n, step);
     RAMNET_CHECK_ARG((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0,

@@ -27,7 +27,9 @@ extern "C" int ramnet_create(int device, ramnet_handle **out) {
     if (prop.major != 10)
         return ramnet_set_error(RAMNET_EDEVICE, "ramnet_create: device %d is sm_%d%d; this library is sm_100a only",
                                 device, prop.major, prop.minor);
-    RAMNET_CUDA(cudaSetDevice(device));
+    // the handle is bound to `device`, but the caller's current device is left as it was: every entry point switches
+    // to h->device for the duration of the call (RAMNET_DEVICE_GUARD) and restores the previous one
+    ramnet_device_guard guard(device);
     ramnet_handle *h = new ramnet_handle();
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
@@ -138,6 +140,7 @@ __global__ void __launch_bounds__(256) upsample2x_add_kernel(const float4 *__res
 
 extern "C" int ramnet_upsample2x_add(ramnet_handle *h, const float *x, const float *skip, float *y, int N, int H,
                                      int W, int C, int flags, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && x && y, "ramnet_upsample2x_add: NULL argument");
     RAMNET_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "ramnet_upsample2x_add: bad shape N=%d H=%d W=%d C=%d (C%%4)", N, H, W, C);
     const int64_t total = (int64_t)N * H * ((W + kUpStrip - 1) / kUpStrip) * (C / 4);
@@ -187,6 +190,7 @@ __global__ void __launch_bounds__(256) pred_sigmoid_kernel(const float *__restri
 
 extern "C" int ramnet_pred_sigmoid(ramnet_handle *h, const float *x, const float *skip, const float *w,
                                    const float *bias, float *logits, float *depth, int64_t M, int C, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && x && w && (logits || depth), "ramnet_pred_sigmoid: NULL argument");
     RAMNET_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0, "ramnet_pred_sigmoid: bad shape M=%lld C=%d (C%%4)", (long long)M, C);
     const int blocks = (int)imin64((M * 8 + 255) / 256, (int64_t)h->sm_count * 16);
@@ -230,12 +234,14 @@ static int launch_transpose(ramnet_handle *h, const float *x, float *y, int batc
 
 extern "C" int ramnet_nchw_to_nhwc(ramnet_handle *h, const float *x, float *y, int N, int C, int H, int W, int flags,
                                    void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && x && y && N > 0 && C > 0 && H > 0 && W > 0, "ramnet_nchw_to_nhwc: bad argument");
     return launch_transpose(h, x, y, N, C, H * W, (flags & RAMNET_FLAG_ROUND_TF32) != 0, stream);
 }
 
 extern "C" int ramnet_nhwc_to_nchw(ramnet_handle *h, const float *x, float *y, int N, int C, int H, int W,
                                    void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && x && y && N > 0 && C > 0 && H > 0 && W > 0, "ramnet_nhwc_to_nchw: bad argument");
     return launch_transpose(h, x, y, N, H * W, C, 0, stream);
 }
@@ -246,6 +252,7 @@ __global__ void round_tf32_kernel(const float *__restrict__ x, float *__restrict
 }
 
 extern "C" int ramnet_round_tf32(ramnet_handle *h, const float *x, float *y, int64_t n, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && x && y && n >= 0, "ramnet_round_tf32: bad argument");
     if (n == 0) return RAMNET_OK;
     const int blocks = (int)imin64((n + 255) / 256, (int64_t)h->sm_count * 16);
@@ -279,6 +286,7 @@ __global__ void pack_weights_kernel(const float *__restrict__ w, float *__restri
 
 extern "C" int ramnet_pack_weights(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin, int ksize,
                                    int mma_kind, int lstm_interleave, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && w_oihw && w_packed, "ramnet_pack_weights: NULL argument");
     RAMNET_CHECK_ARG(Cout > 0 && Cin > 0 && (ksize == 1 || ksize == 3 || ksize == 5), "ramnet_pack_weights: bad shape");
     RAMNET_CHECK_ARG(mma_kind == RAMNET_MMA_FP32 || mma_kind == RAMNET_MMA_TF32, "ramnet_pack_weights: bad mma_kind");

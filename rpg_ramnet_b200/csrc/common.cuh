@@ -36,6 +36,25 @@ int ramnet_set_error(int code, const char *fmt, ...);
         (h)->launches++;                                                                     \
     } while (0)
 
+// ---- device selection -------------------------------------------------------------
+// The reference selects its GPU only through tensor placement (config['gpu'] -> .to(self.gpu), no set_device), so the
+// caller's current device can differ from the handle's.  Every entry point that takes a handle makes h->device current
+// for the duration of the call and restores the previous device on return; cudaGetDevice / cudaSetDevice on the
+// already-current device are host-side no-ops (~100 ns).
+struct ramnet_device_guard {
+    int prev = -1;
+    bool switched = false;
+    explicit ramnet_device_guard(int device) {
+        if (device < 0 || cudaGetDevice(&prev) != cudaSuccess) return;
+        if (prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+    }
+    explicit ramnet_device_guard(const ramnet_handle *h) : ramnet_device_guard(h ? h->device : -1) {}
+    ~ramnet_device_guard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+#define RAMNET_DEVICE_GUARD(h) ramnet_device_guard ramnet_guard__(h)
+
 // ---- programmatic dependent launch ----------------------------------------------
 // Kernels of one pass run back to back on one stream.  A kernel launched through ramnet_launch(pdl = true) may start
 // while its predecessor is still draining: its CTAs are placed as SMs free up and run their prologue (barrier init,

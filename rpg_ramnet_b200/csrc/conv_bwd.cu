@@ -417,6 +417,7 @@ int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz
 size_t conv_wgrad_tf32_workspace(const ramnet_handle *h, const ramnet_conv_desc *d, int head_cin = 0);
 
 extern "C" size_t ramnet_conv_wgrad_workspace_bytes(const ramnet_handle *h, const ramnet_conv_desc *d) {
+    RAMNET_DEVICE_GUARD(h);
     if (!h || !d || d->mma_kind != RAMNET_MMA_TF32) return 0;
     return conv_wgrad_tf32_workspace(h, d);
 }
@@ -432,6 +433,7 @@ static ramnet_conv_desc head_wgrad_desc(int N, int H, int W, int Cout) {
 }
 
 extern "C" size_t ramnet_head_conv_wgrad_tc_workspace_bytes(const ramnet_handle *h, int N, int Cin, int H, int W, int Cout) {
+    RAMNET_DEVICE_GUARD(h);
     if (!h || Cin < 1 || 5 * Cin > 32 || Cout <= 0 || Cout % 32) return 0;
     const ramnet_conv_desc d = head_wgrad_desc(N, H, W, Cout);
     return conv_wgrad_tf32_workspace(h, &d, Cin);
@@ -440,6 +442,7 @@ extern "C" size_t ramnet_head_conv_wgrad_tc_workspace_bytes(const ramnet_handle 
 extern "C" int ramnet_head_conv_wgrad_tc(ramnet_handle *h, const float *xe_nhwc32, const float *dz_nhwc, float *dw_oihw,
                                          float *db, int N, int Cin, int H, int W, int Cout, void *workspace,
                                          size_t workspace_bytes, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && xe_nhwc32 && dz_nhwc && dw_oihw, "head_conv_wgrad_tc: NULL argument");
     RAMNET_CHECK_ARG(Cin >= 1 && 5 * Cin <= 32 && Cout > 0 && Cout % 32 == 0, "head_conv_wgrad_tc: needs 5*Cin <= 32 and Cout %% 32 == 0 (got %d, %d)", Cin, Cout);
     if (db) {
@@ -453,6 +456,7 @@ extern "C" int ramnet_head_conv_wgrad_tc(ramnet_handle *h, const float *xe_nhwc3
 extern "C" int ramnet_conv_wgrad(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz, const float *x0,
                                  const float *x1, float *dw_oihw, float *db, void *workspace, size_t workspace_bytes,
                                  void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && d && dz && x0 && dw_oihw, "conv_wgrad: NULL argument");
     RAMNET_CHECK_ARG(d->C0 % 4 == 0 && d->C1 % 4 == 0 && d->Cout % 4 == 0, "conv_wgrad: channel counts must be multiples of 4");
     RAMNET_CHECK_ARG((d->C1 == 0) == (x1 == nullptr), "conv_wgrad: x1 and C1 disagree");
@@ -491,6 +495,7 @@ extern "C" int ramnet_conv_wgrad(ramnet_handle *h, const ramnet_conv_desc *d, co
 
 extern "C" int ramnet_zero_insert2x(ramnet_handle *h, const float *x, const float *skip, float *y, int N, int H, int W,
                                     int C, int Hout, int Wout, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && x && y && C % 4 == 0 && Hout >= 2 * H - 1 && Wout >= 2 * W - 1, "zero_insert2x: bad argument");
     const int64_t total = (int64_t)N * Hout * Wout * (C / 4);
     zero_insert_kernel<<<grid_for(h, total), 256, 0, (cudaStream_t)stream>>>((const float4 *)x, (const float4 *)skip, (float4 *)y, N, H, W, C / 4,
@@ -501,6 +506,7 @@ extern "C" int ramnet_zero_insert2x(ramnet_handle *h, const float *x, const floa
 
 extern "C" int ramnet_pack_weights_dgrad(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin,
                                          int ksize, int mma_kind, int ci_begin, int ci_count, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && w_oihw && w_packed && ci_begin >= 0 && ci_count > 0 && ci_begin + ci_count <= Cin,
                      "pack_weights_dgrad: bad argument");
     const int64_t total = (int64_t)Cout * ci_count * ksize * ksize;
@@ -512,6 +518,7 @@ extern "C" int ramnet_pack_weights_dgrad(ramnet_handle *h, const float *w_oihw, 
 
 extern "C" int ramnet_relu_bwd(ramnet_handle *h, const float *dy, const float *y, float *dz, int64_t n, int flags,
                                void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && dy && y && dz && n > 0 && n % 4 == 0, "relu_bwd: bad argument");
     relu_bwd_kernel<<<grid_for(h, n / 4), 256, 0, (cudaStream_t)stream>>>(dy, y, dz, n / 4, flags & RAMNET_FLAG_ROUND_TF32);
     RAMNET_LAUNCH_CHECK(h);
@@ -520,6 +527,7 @@ extern "C" int ramnet_relu_bwd(ramnet_handle *h, const float *dy, const float *y
 
 extern "C" int ramnet_gru_out_bwd(ramnet_handle *h, const float *dhn, const float *hprev, const float *u, const float *o,
                                   float *dzo, float *dzru, float *dh, int64_t M, int C, int flags, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && dhn && hprev && u && o && dzo && dzru && dh && M > 0 && C % 4 == 0, "gru_out_bwd: bad argument");
     gru_out_bwd_kernel<<<grid_for(h, M * (C / 4)), 256, 0, (cudaStream_t)stream>>>(dhn, hprev, u, o, dzo, dzru, dh, M, C,
                                                                                    flags & RAMNET_FLAG_ROUND_TF32);
@@ -529,6 +537,7 @@ extern "C" int ramnet_gru_out_bwd(ramnet_handle *h, const float *dhn, const floa
 
 extern "C" int ramnet_gru_ru_bwd(ramnet_handle *h, const float *drh, const float *hprev, const float *r, float *dzru,
                                  float *dh, int64_t M, int C, int flags, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && drh && hprev && r && dzru && dh && M > 0 && C % 4 == 0, "gru_ru_bwd: bad argument");
     gru_ru_bwd_kernel<<<grid_for(h, M * (C / 4)), 256, 0, (cudaStream_t)stream>>>(drh, hprev, r, dzru, dh, M, C,
                                                                                   flags & RAMNET_FLAG_ROUND_TF32);
@@ -539,6 +548,7 @@ extern "C" int ramnet_gru_ru_bwd(ramnet_handle *h, const float *drh, const float
 extern "C" int ramnet_pred_bwd(ramnet_handle *h, const float *ddepth, const float *depth, const float *x,
                                const float *skip, const float *w, float *dx, float *dw, float *db, int64_t M, int C,
                                void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && ddepth && depth && x && w && dx && dw && M > 0 && C % 4 == 0 && C <= 64, "pred_bwd: bad argument (C <= 64)");
     const int blocks = (int)imin64((M * 8 + 255) / 256, (int64_t)h->sm_count * 8);
     pred_bwd_kernel<<<blocks, 256, (C + 1) * sizeof(float), (cudaStream_t)stream>>>(ddepth, depth, x, skip, w, dx, dw, db, M, C);
@@ -548,6 +558,7 @@ extern "C" int ramnet_pred_bwd(ramnet_handle *h, const float *ddepth, const floa
 
 extern "C" int ramnet_upsample2x_bwd(ramnet_handle *h, const float *dy, float *dx, int N, int H, int W, int C,
                                      void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && dy && dx && N > 0 && H > 0 && W > 0 && C % 4 == 0, "upsample2x_bwd: bad argument");
     const int64_t total = (int64_t)N * H * W * (C / 4);
     upsample2x_bwd_kernel<<<grid_for(h, total), 256, 0, (cudaStream_t)stream>>>((const float4 *)dy, (float4 *)dx, N, H, W, C / 4);
@@ -557,6 +568,7 @@ extern "C" int ramnet_upsample2x_bwd(ramnet_handle *h, const float *dy, float *d
 
 extern "C" int ramnet_head_conv_wgrad(ramnet_handle *h, const float *x_nchw, const float *dz_nhwc, float *dw_oihw,
                                       float *db, int N, int Cin, int H, int W, int Cout, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && x_nchw && dz_nhwc && dw_oihw, "head_conv_wgrad: NULL argument");
     RAMNET_CHECK_ARG(Cin >= 1 && Cin <= 8 && Cout % 4 == 0 && Cout <= 32, "head_conv_wgrad: Cin in [1,8], Cout <= 32 (multiple of 4)");
     dim3 grid((W + HW_TW - 1) / HW_TW, (H + HW_TH - 1) / HW_TH, N);
@@ -572,6 +584,7 @@ extern "C" int ramnet_head_conv_wgrad(ramnet_handle *h, const float *x_nchw, con
 
 extern "C" int ramnet_lstm_bwd(ramnet_handle *h, const float *dh, const float *dc, const float *gates, const float *c_prev,
                                const float *c_new, float *dz, float *dc_prev, int64_t M, int C, int flags, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && gates && c_prev && c_new && dz && dc_prev && (dh || dc) && M > 0 && C > 0, "lstm_bwd: bad argument");
     lstm_bwd_kernel<<<grid_for(h, M * C), 256, 0, (cudaStream_t)stream>>>(dh, dc, gates, c_prev, c_new, dz, dc_prev, M, C,
                                                                          flags & RAMNET_FLAG_ROUND_TF32);

@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(256) head_conv_kernel(const float *__restrict_
 
 extern "C" int ramnet_head_conv(ramnet_handle *h, const float *x_nchw, const float *w_oihw, const float *bias,
                                 float *y_nhwc, int N, int Cin, int H, int W, int Cout, int flags, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && x_nchw && w_oihw && y_nhwc, "ramnet_head_conv: NULL argument");
     RAMNET_CHECK_ARG(N > 0 && H > 0 && W > 0, "ramnet_head_conv: bad shape N=%d H=%d W=%d", N, H, W);
     RAMNET_CHECK_ARG(Cin >= 1 && Cin <= MAX_CIN, "ramnet_head_conv: Cin=%d not in [1,%d]", Cin, MAX_CIN);

@@ -152,6 +152,7 @@ extern "C" int ramnet_conv_fwd(ramnet_handle *h, const ramnet_conv_desc *d, cons
                                const float *w_packed, const float *bias, const float *aux0, const float *aux1,
                                float *y0, float *y1, float *y2, void *workspace, size_t workspace_bytes,
                                void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h != nullptr, "conv_fwd: handle is NULL");
     int rc = validate_desc(d);
     if (rc) return rc;

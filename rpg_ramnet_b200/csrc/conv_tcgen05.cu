@@ -1819,8 +1819,8 @@ bool plan_wgrad_packed(const ramnet_handle *h, const ramnet_conv_desc *d, int cl
     g.row_groups = (g.kh + g.RG - 1) / g.RG;
     // 64-channel M operand with more filter rows than one CTA holds (dec2: 64 -> 32, 5x5): fold the second row group
     // into the idle upper half of the 128 MMA rows instead of running it as a second, half-empty CTA group
-    // (RAMNET_WGRAD_FOLD=1 opts in: written after the round's GPU budget was spent, not yet validated on hardware.)
-    static const bool fold_on = [] { const char *e = getenv("RAMNET_WGRAD_FOLD"); return e && e[0] == '1'; }();
+    // (dec2 182 -> 121 us per call on B200, profiles/r02_first_call_experimental_paths.txt; RAMNET_WGRAD_FOLD=0 disables)
+    static const bool fold_on = [] { const char *e = getenv("RAMNET_WGRAD_FOLD"); return !(e && e[0] == '0'); }();
     g.mfold = (fold_on && d->stride == 1 && head_cin == 0 && g.Mch == 64 && g.kh > g.RG && g.kh <= 2 * g.RG) ? 1 : 0;
     if (g.mfold) g.row_groups = 1;
     g.HXw = 8 + g.kw - 1; g.HYw = g.TR + g.RG - 1;
@@ -2037,9 +2037,9 @@ int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz
         RAMNET_LAUNCH_CHECK(h);
         if (do_prof) cudaEventRecord(ev[1], s);
         const int64_t elems = (int64_t)pgroups * 128 * p.ncols;
-        // few splits: summed inside the scatter kernel (RAMNET_WGRAD_FUSED_SUM=1 opts in: written after the round's GPU
-        // budget was spent, not yet validated on hardware; the default runs the separate sum pass)
-        static const bool fuse_on = [] { const char *e = getenv("RAMNET_WGRAD_FUSED_SUM"); return e && e[0] == '1'; }();
+        // few splits: summed inside the scatter kernel (one pass 1355 -> 1251 us on B200; RAMNET_WGRAD_FUSED_SUM=0 runs
+        // the separate sum pass)
+        static const bool fuse_on = [] { const char *e = getenv("RAMNET_WGRAD_FUSED_SUM"); return !(e && e[0] == '0'); }();
         const bool fused_sum = fuse_on && psplits <= 16;
         if (psplits > 1 && !fused_sum) {
             dim3 sgrid((unsigned)imin64((elems + 63) / 64, (int64_t)h->sm_count * 8), (unsigned)batch.n);
@@ -2307,6 +2307,7 @@ __global__ void pack_dgrad_s2_kernel(const float *__restrict__ w, float *__restr
 
 extern "C" int ramnet_pack_weights_dgrad_s2(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin,
                                             int ksize, int ci_begin, int ci_count, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && w_oihw && w_packed && Cout > 0 && Cin > 0 && (ksize == 3 || ksize == 5) && ci_begin >= 0 &&
                          ci_count > 0 && ci_begin + ci_count <= Cin,
                      "pack_weights_dgrad_s2: bad argument");
@@ -2319,6 +2320,7 @@ extern "C" int ramnet_pack_weights_dgrad_s2(ramnet_handle *h, const float *w_oih
 
 extern "C" int ramnet_conv_dgrad_s2(ramnet_handle *h, const float *dz, const float *w_packed_s2, float *dx, int N, int H,
                                     int W, int Cout, int ci_count, int ksize, int flags, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && dz && w_packed_s2 && dx, "conv_dgrad_s2: NULL argument");
     RAMNET_CHECK_ARG(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "conv_dgrad_s2: input H=%d, W=%d must be even", H, W);
     RAMNET_CHECK_ARG((ksize == 3 || ksize == 5) && Cout % 32 == 0 && ci_count % 32 == 0,
@@ -2405,6 +2407,7 @@ __global__ void pack_head_kernel(const float *__restrict__ w, float *__restrict_
 
 extern "C" int ramnet_head_im2row(ramnet_handle *h, const float *x_nchw, float *xe_nhwc32, int N, int Cin, int H, int W,
                                   void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && x_nchw && xe_nhwc32 && N > 0 && H > 0 && W > 0, "head_im2row: bad argument");
     RAMNET_CHECK_ARG(Cin >= 1 && 5 * Cin <= 32, "head_im2row: 5*Cin = %d must fit one 32-channel pixel row", 5 * Cin);
     const int64_t ntile = (int64_t)N * H * ((W + 31) / 32);
@@ -2424,6 +2427,7 @@ extern "C" int ramnet_head_im2row(ramnet_handle *h, const float *x_nchw, float *
 
 extern "C" int ramnet_pack_weights_head(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin,
                                         void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && w_oihw && w_packed && Cout > 0 && Cin >= 1 && 5 * Cin <= 32, "pack_weights_head: bad argument");
     pack_head_kernel<<<(5 * Cout * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w_oihw, w_packed, Cout, Cin);
     RAMNET_LAUNCH_CHECK(h);
@@ -2432,6 +2436,7 @@ extern "C" int ramnet_pack_weights_head(ramnet_handle *h, const float *w_oihw, f
 
 extern "C" int ramnet_head_conv_tc(ramnet_handle *h, const float *xe_nhwc32, const float *w_packed, const float *bias,
                                    float *y_nhwc, int N, int H, int W, int Cout, int flags, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && xe_nhwc32 && w_packed && y_nhwc && N > 0 && H > 0 && W > 0, "head_conv_tc: bad argument");
     RAMNET_CHECK_ARG(Cout > 0 && Cout % 32 == 0, "head_conv_tc: Cout=%d must be a multiple of 32", Cout);
     ramnet_conv_desc d;
@@ -2511,6 +2516,7 @@ __global__ void pack_hpack_kernel(const float *__restrict__ w, float *__restrict
 
 extern "C" int ramnet_pack_weights_hpack(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin,
                                          int ksize, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && w_oihw && w_packed && Cout > 0 && Cout % 16 == 0 && Cin > 0 && (ksize == 3 || ksize == 5),
                      "pack_weights_hpack: bad argument");
     const int cs = Cout % 32 == 0 ? 32 : 16;

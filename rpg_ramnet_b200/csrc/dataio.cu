@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(256) depth_metrics_kernel(const float *__restr
 }  // namespace
 
 extern "C" int ramnet_voxel_normalize(ramnet_handle *h, float *grid, int64_t n, int batch, double *stats, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && grid && stats && n > 0 && batch > 0 && batch <= 65535, "voxel_normalize: bad argument");
     cudaStream_t s = (cudaStream_t)stream;
     RAMNET_CUDA(cudaMemsetAsync(stats, 0, (size_t)batch * 3 * sizeof(double), s));
@@ -127,6 +128,7 @@ extern "C" int ramnet_voxel_normalize(ramnet_handle *h, float *grid, int64_t n, 
 
 extern "C" int ramnet_depth_to_label(ramnet_handle *h, const float *depth, float *label, int64_t n, float clip_distance,
                                      float reg_factor, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && depth && label && n > 0 && clip_distance > 0.f && reg_factor != 0.f, "depth_to_label: bad argument");
     const int blocks = (int)imin64((n + 255) / 256, (int64_t)h->sm_count * 8);
     depth_label_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(depth, label, n, clip_distance, reg_factor);
@@ -136,6 +138,7 @@ extern "C" int ramnet_depth_to_label(ramnet_handle *h, const float *depth, float
 
 extern "C" int ramnet_depth_metrics(ramnet_handle *h, const float *pred, const float *target, int N, int64_t hw, float eps,
                                     double *out, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && pred && target && out && N > 0 && N <= 65535 && hw > 0, "depth_metrics: bad argument");
     cudaStream_t s = (cudaStream_t)stream;
     RAMNET_CUDA(cudaMemsetAsync(out, 0, (size_t)N * 8 * sizeof(double), s));

@@ -9,10 +9,12 @@
 #include "common.cuh"
 
 __global__ void __launch_bounds__(256) si_stats_kernel(const float *__restrict__ pred, const float *__restrict__ target,
-                                                       int64_t n, double *__restrict__ stats) {
+                                                       int64_t n, double *__restrict__ stats, int log_space) {
     double s1 = 0.0, s2 = 0.0, cnt = 0.0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float d = pred[i] - target[i];
+        // loss.py:7 (difference of the network's normalised log depths) or loss.py:13 (scale_invariant_log_loss: the
+        // logarithm is taken here; log of a non-positive value is NaN / -inf exactly as torch.log)
+        const float d = log_space ? logf(pred[i]) - logf(target[i]) : pred[i] - target[i];
         if (d == d) {  // ~isnan(log_diff), loss.py:8
             s1 += (double)d;
             s2 += (double)d * (double)d;
@@ -55,29 +57,37 @@ __global__ void si_value_kernel(const double *__restrict__ stats, float weight, 
 
 __global__ void __launch_bounds__(256) si_grad_kernel(const float *__restrict__ pred, const float *__restrict__ target,
                                                       int64_t n, const double *__restrict__ stats, float weight,
-                                                      float n_lambda, float scale, float *__restrict__ grad) {
+                                                      float n_lambda, float scale, const float *__restrict__ scale_dev,
+                                                      int log_space, float *__restrict__ grad) {
     const double cnt = stats[2];
     const float mean = (float)(stats[0] / cnt);
-    const float k = (float)(2.0 * (double)weight * (double)scale / cnt);
+    // scale_dev: the upstream gradient d total / d loss_term as a device scalar (autograd's grad_output), so that no
+    // separate elementwise multiply over the map and no host read-back is needed
+    const double up = (double)scale * (scale_dev ? (double)*scale_dev : 1.0);
+    const float k = (float)(2.0 * (double)weight * up / cnt);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float d = pred[i] - target[i];
-        grad[i] = (d == d) ? k * (d - n_lambda * mean) : 0.f;
+        const float p = pred[i];
+        const float d = log_space ? logf(p) - logf(target[i]) : p - target[i];
+        const float g = k * (d - n_lambda * mean);
+        grad[i] = (d == d) ? (log_space ? g / p : g) : 0.f;
     }
 }
 
 extern "C" int ramnet_si_loss_stats(ramnet_handle *h, const float *pred, const float *target, int64_t n, double *stats,
-                                    void *stream) {
+                                    int flags, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && pred && target && stats && n > 0, "si_loss_stats: bad argument");
     cudaStream_t s = (cudaStream_t)stream;
     RAMNET_CUDA(cudaMemsetAsync(stats, 0, 3 * sizeof(double), s));
     const int blocks = (int)imin64((n + 255) / 256, (int64_t)h->sm_count * 8);
-    si_stats_kernel<<<blocks, 256, 0, s>>>(pred, target, n, stats);
+    si_stats_kernel<<<blocks, 256, 0, s>>>(pred, target, n, stats, (flags & RAMNET_LOSS_LOG_SPACE) ? 1 : 0);
     RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;
 }
 
 extern "C" int ramnet_si_loss_value(ramnet_handle *h, const double *stats, float weight, float n_lambda, float *loss_out,
                                     void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && stats && loss_out, "si_loss_value: bad argument");
     si_value_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(stats, weight, n_lambda, loss_out);
     RAMNET_LAUNCH_CHECK(h);
@@ -85,11 +95,13 @@ extern "C" int ramnet_si_loss_value(ramnet_handle *h, const double *stats, float
 }
 
 extern "C" int ramnet_si_loss_grad(ramnet_handle *h, const float *pred, const float *target, int64_t n,
-                                   const double *stats, float weight, float n_lambda, float scale, float *grad,
-                                   void *stream) {
+                                   const double *stats, float weight, float n_lambda, float scale,
+                                   const float *scale_dev, int flags, float *grad, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && pred && target && stats && grad && n > 0, "si_loss_grad: bad argument");
     const int blocks = (int)imin64((n + 255) / 256, (int64_t)h->sm_count * 8);
-    si_grad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pred, target, n, stats, weight, n_lambda, scale, grad);
+    si_grad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pred, target, n, stats, weight, n_lambda, scale, scale_dev,
+                                                             (flags & RAMNET_LOSS_LOG_SPACE) ? 1 : 0, grad);
     RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;
 }
@@ -161,11 +173,14 @@ __global__ void msg_value_kernel(const double *__restrict__ stats, int N, int sc
 
 __global__ void __launch_bounds__(256) msg_grad_kernel(const float *__restrict__ pred, const float *__restrict__ target,
                                                        int N, int H, int W, int k, const double *__restrict__ stats,
-                                                       int scales, float gscale, float *__restrict__ grad) {
+                                                       int scales, int n_batch, float gscale,
+                                                       const float *__restrict__ scale_dev, float *__restrict__ grad) {
     const int hp = H / k, wp = W / k;
     const int64_t total = (int64_t)N * hp * wp;
     // d loss / d g = sign(g) * B * 2 / (count * scales); Sobel /8; avg-pool adjoint 1/k^2
-    const float coef = gscale * (float)((double)N * 2.0 / (stats[1] * (double)scales)) * 0.125f / (float)(k * k);
+    // (B = n_batch: the GLOBAL batch size when the statistics were all-reduced over data-parallel ranks)
+    const float up = gscale * (scale_dev ? *scale_dev : 1.f);
+    const float coef = up * (float)((double)n_batch * 2.0 / (stats[1] * (double)scales)) * 0.125f / (float)(k * k);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int qx = (int)(i % wp), qy = (int)((i / wp) % hp), n = (int)(i / ((int64_t)wp * hp));
         float gx, gy;
@@ -188,6 +203,7 @@ __global__ void __launch_bounds__(256) msg_grad_kernel(const float *__restrict__
 
 extern "C" int ramnet_msg_loss_stats(ramnet_handle *h, const float *pred, const float *target, int N, int H, int W,
                                      int start_scale, int scales, double *stats, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && pred && target && stats && N > 0 && H > 0 && W > 0 && scales > 0 && scales <= 8 && start_scale >= 1,
                      "msg_loss_stats: bad argument");
     RAMNET_CHECK_ARG(H % (start_scale << (scales - 1)) == 0 && W % (start_scale << (scales - 1)) == 0,
@@ -205,6 +221,7 @@ extern "C" int ramnet_msg_loss_stats(ramnet_handle *h, const float *pred, const 
 }
 
 extern "C" int ramnet_msg_loss_value(ramnet_handle *h, const double *stats, int N, int scales, float *loss_out, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && stats && loss_out && scales > 0, "msg_loss_value: bad argument");
     msg_value_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(stats, N, scales, loss_out);
     RAMNET_LAUNCH_CHECK(h);
@@ -212,7 +229,9 @@ extern "C" int ramnet_msg_loss_value(ramnet_handle *h, const double *stats, int 
 }
 
 extern "C" int ramnet_msg_loss_grad(ramnet_handle *h, const float *pred, const float *target, int N, int H, int W,
-                                    int start_scale, int scales, const double *stats, float scale, float *grad, void *stream) {
+                                    int start_scale, int scales, const double *stats, int n_batch, float scale,
+                                    const float *scale_dev, float *grad, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && pred && target && stats && grad && N > 0 && scales > 0 && scales <= 8 && start_scale >= 1,
                      "msg_loss_grad: bad argument");
     cudaStream_t s = (cudaStream_t)stream;
@@ -221,8 +240,35 @@ extern "C" int ramnet_msg_loss_grad(ramnet_handle *h, const float *pred, const f
         const int k = start_scale << sc;
         const int64_t total = (int64_t)N * (H / k) * (W / k);
         msg_grad_kernel<<<(int)imin64((total + 255) / 256, (int64_t)h->sm_count * 8), 256, 0, s>>>(
-            pred, target, N, H, W, k, stats + 2 * sc, scales, scale, grad);
+            pred, target, N, H, W, k, stats + 2 * sc, scales, n_batch > 0 ? n_batch : N, scale, scale_dev, grad);
         RAMNET_LAUNCH_CHECK(h);
     }
+    return RAMNET_OK;
+}
+
+// preview=True branch of MultiScaleGradient.forward (loss.py:46-47): kornia `sobel` = gradient magnitude
+// sqrt(gx^2 + gy^2 + eps), eps = 1e-6, of the pooled difference at one scale.  Logging only (TensorBoard previews,
+// lstm_trainer.py:162-165); the bicubic resize that follows stays a host-side torch call.
+__global__ void __launch_bounds__(256) msg_sobel_mag_kernel(const float *__restrict__ pred, const float *__restrict__ target,
+                                                            int N, int H, int W, int k, float *__restrict__ out) {
+    const int hp = H / k, wp = W / k;
+    const int64_t total = (int64_t)N * hp * wp;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int qx = (int)(i % wp), qy = (int)((i / wp) % hp), n = (int)(i / ((int64_t)wp * hp));
+        float gx, gy;
+        msg_sobel(pred, target, n, H, W, k, hp, wp, qy, qx, gx, gy);
+        out[i] = sqrtf(gx * gx + gy * gy + 1e-6f);   // NaN where any pooled neighbour is NaN, as the reference
+    }
+}
+
+extern "C" int ramnet_msg_sobel_preview(ramnet_handle *h, const float *pred, const float *target, int N, int H, int W,
+                                        int pool, float *out, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
+    RAMNET_CHECK_ARG(h && pred && target && out && N > 0 && H > 0 && W > 0 && pool >= 1 && H % pool == 0 && W % pool == 0,
+                     "msg_sobel_preview: bad argument");
+    const int64_t total = (int64_t)N * (H / pool) * (W / pool);
+    msg_sobel_mag_kernel<<<(int)imin64((total + 255) / 256, (int64_t)h->sm_count * 8), 256, 0, (cudaStream_t)stream>>>(
+        pred, target, N, H, W, pool, out);
+    RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;
 }

@@ -91,6 +91,7 @@ static int check_args(ramnet_handle *h, const double *events, int64_t n, int bin
 
 extern "C" int ramnet_voxel_grid(ramnet_handle *h, const double *events, int64_t n, int bins, int width, int height,
                                  float *grid, int32_t *oob_count, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     int rc = check_args(h, events, n, bins, width, height);
     if (rc) return rc;
     RAMNET_CHECK_ARG(grid != nullptr, "voxel_grid: grid is NULL");
@@ -109,6 +110,7 @@ extern "C" int ramnet_voxel_grid(ramnet_handle *h, const double *events, int64_t
 extern "C" int ramnet_voxel_votes(ramnet_handle *h, const double *events, int64_t n, int bins, int width, int height,
                                   int64_t *idx_left, float *val_left, int64_t *idx_right, float *val_right,
                                   void *stream) {
+    RAMNET_DEVICE_GUARD(h);
     int rc = check_args(h, events, n, bins, width, height);
     if (rc) return rc;
     if (n == 0) return RAMNET_OK;

@@ -54,3 +54,51 @@ def all_reduce_flat_grads(flat_grad: torch.Tensor, group: Optional[dist.ProcessG
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
     return flat_grad
+
+
+def dp_world_size(group: Optional[dist.ProcessGroup] = None) -> int:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(None if group in (None, True) else group)
+    return 1
+
+
+class BucketedAllReduce:
+    """Sum of the flat gradient buffer in `n_buckets` contiguous slices on a side stream.
+
+    `launch()` enqueues every slice's all-reduce on the communication stream (after the gradients written on the
+    current stream so far) and yields `(lo, hi, ready)` per slice in order; `ready()` makes the current stream wait for
+    THAT slice only, so the consumer of slice k (its Adam launch) runs while slices k+1.. are still on the wire.  With
+    one rank (or one bucket and no process group) nothing is enqueued and `ready` is a no-op.  Works on CPU tensors
+    (gloo, synchronous) for the host-logic tests.  Inside CUDA-graph capture the side stream forks from and joins back
+    into the capturing stream through the recorded events, so the captured graph carries the same overlap."""
+
+    def __init__(self, flat: torch.Tensor, n_buckets: int = 4, group: Optional[dist.ProcessGroup] = None):
+        self.flat, self.group = flat, (None if group in (None, True) else group)
+        n = flat.numel()
+        n_buckets = max(1, min(int(n_buckets), max(1, n // 4)))
+        # 16-byte aligned cuts so every slice keeps the vector alignment the Adam kernel checks
+        cuts = sorted({0, n} | {((n * k // n_buckets) // 4) * 4 for k in range(1, n_buckets)})
+        self.spans = [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+        self.stream = torch.cuda.Stream(device=flat.device) if flat.is_cuda else None
+
+    def launch(self):
+        if dp_world_size(self.group) <= 1:
+            for lo, hi in self.spans[:1]:
+                yield 0, self.flat.numel(), (lambda: None)
+            return
+        if self.stream is None:                 # CPU (gloo): synchronous
+            for lo, hi in self.spans:
+                dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+                yield lo, hi, (lambda: None)
+            return
+        cur = torch.cuda.current_stream(self.flat.device)
+        self.stream.wait_stream(cur)            # gradients are final on the compute stream
+        events = []
+        with torch.cuda.stream(self.stream):
+            for lo, hi in self.spans:
+                dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+                events.append(ev)
+        for (lo, hi), ev in zip(self.spans, events):
+            yield lo, hi, (lambda ev=ev: cur.wait_event(ev))

@@ -11,9 +11,22 @@ NaN convention (as upstream): target pixels without ground truth are NaN and are
 prediction is finite (a sigmoid output), so the reference's two masks (`~isnan(|t - p|)` and
 `~isnan(t)`, metric.py:9-10) coincide.
 """
+import numpy as np
 import torch
 
 from .. import ops
+
+
+def _dev(x, like=None):
+    """LSTMTrainer._eval_metrics hands numpy arrays to the metric functions (lstm_trainer.py:100-106); tensors may live
+    on the host or the device.  Everything is reduced on the GPU: host inputs are uploaded (the optional
+    `_eval_metrics` override of INTEGRATION.md §5 avoids that round trip)."""
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    if not x.is_cuda:
+        dev = like.device if (like is not None and like.is_cuda) else torch.device('cuda', torch.cuda.current_device())
+        x = x.to(dev, non_blocking=True)
+    return x
 
 __all__ = ['abs_rel_diff', 'squ_rel_diff', 'rms_linear', 'scale_invariant_error', 'mean_error', 'median_error', 'mse',
            'eval_metrics']
@@ -40,6 +53,8 @@ def _from_sums(name, s):
 
 def _median_error(y_input, y_target):
     """metric.py:31-33.  A selection, not a sum: sorted on the device, only the middle values are read back."""
+    y_input = _dev(y_input)
+    y_target = _dev(y_target, y_input)
     d = (y_target.detach().float() - y_input.detach().float()).abs().flatten()
     d = d[~torch.isnan(d)]
     n = d.numel()
@@ -53,6 +68,8 @@ def eval_metrics(y_input, y_target, names):
     """All of `names` (functions or their names) for one prediction / target pair: the device twin of
     LSTMTrainer._eval_metrics (trainer/lstm_trainer.py:100-106).  Returns a list of floats."""
     names = [n if isinstance(n, str) else n.__name__ for n in names]
+    y_input = _dev(y_input)
+    y_target = _dev(y_target, y_input)
     sums = None
     out = []
     for n in names:
@@ -66,11 +83,13 @@ def eval_metrics(y_input, y_target, names):
 
 
 def abs_rel_diff(y_input, y_target, eps=1e-6):
-    return _from_sums('abs_rel_diff', ops.depth_metric_sums(y_input, y_target, eps).cpu())
+    y_input = _dev(y_input)
+    return _from_sums('abs_rel_diff', ops.depth_metric_sums(y_input, _dev(y_target, y_input), eps).cpu())
 
 
 def squ_rel_diff(y_input, y_target, eps=1e-6):
-    return _from_sums('squ_rel_diff', ops.depth_metric_sums(y_input, y_target, eps).cpu())
+    y_input = _dev(y_input)
+    return _from_sums('squ_rel_diff', ops.depth_metric_sums(y_input, _dev(y_target, y_input), eps).cpu())
 
 
 def rms_linear(y_input, y_target):

@@ -178,9 +178,9 @@ def head_conv_tc(xe: torch.Tensor, w_packed: torch.Tensor, b: Optional[torch.Ten
 
 def hpack_eligible(Cout: int, ksize: int, stride: int, mma_kind: int) -> bool:
     """Layers the horizontal-tap-packed forward (RAMNET_FLAG_HPACK) is meant for: few output channels at stride 1, where a
-    128 x 32 x 8 MMA per tap is bound by the A-operand shared-memory reads.  Opt-in (RAMNET_HPACK=1): written after the
-    round's GPU budget was spent, validated on the CPU only (tests/test_hpack_index_algebra.py)."""
-    return (os.environ.get('RAMNET_HPACK', '0') == '1' and mma_kind == MMA_TF32 and stride == 1 and ksize in (3, 5)
+    128 x 32 x 8 MMA per tap is bound by the A-operand shared-memory reads.  Default on since round 2 (validated on
+    hardware: tests/test_gpu_experimental.py, profiles/r02_first_call_experimental_paths.txt); RAMNET_HPACK=0 disables."""
+    return (os.environ.get('RAMNET_HPACK', '1') != '0' and mma_kind == MMA_TF32 and stride == 1 and ksize in (3, 5)
             and Cout == 32)
 
 
@@ -312,24 +312,33 @@ def pred_sigmoid(x: torch.Tensor, skip: Optional[torch.Tensor], w: torch.Tensor,
     return (depth, logits) if want_logits else depth
 
 
-def si_loss_stats(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+def si_loss_stats(pred: torch.Tensor, target: torch.Tensor, out: Optional[torch.Tensor] = None,
+                  log_space: bool = False) -> torch.Tensor:
+    """(sum d, sum d^2, n) in float64; `out`: optional [3] slice of a larger statistics buffer (batched exchange)."""
     pred, target = pred.contiguous(), target.contiguous()
-    stats = torch.empty(3, dtype=torch.float64, device=pred.device)
-    check(_lib.load().ramnet_si_loss_stats(_h(pred), _p(pred), _p(target), pred.numel(), _p(stats), _stream(pred)))
+    stats = torch.empty(3, dtype=torch.float64, device=pred.device) if out is None else out
+    check(_lib.load().ramnet_si_loss_stats(_h(pred), _p(pred), _p(target), pred.numel(), _p(stats),
+                                           _lib.LOSS_LOG_SPACE if log_space else 0, _stream(pred)))
     return stats
 
 
-def si_loss_value(stats: torch.Tensor, weight: float, n_lambda: float) -> torch.Tensor:
-    out = torch.empty((), dtype=torch.float32, device=stats.device)
+def si_loss_value(stats: torch.Tensor, weight: float, n_lambda: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty((), dtype=torch.float32, device=stats.device)
     check(_lib.load().ramnet_si_loss_value(_h(stats), _p(stats), weight, n_lambda, _p(out), _stream(stats)))
     return out
 
 
-def si_loss_grad(pred, target, stats, weight: float, n_lambda: float, scale: float = 1.0) -> torch.Tensor:
+def si_loss_grad(pred, target, stats, weight: float, n_lambda: float, scale: float = 1.0,
+                 scale_dev: Optional[torch.Tensor] = None, log_space: bool = False) -> torch.Tensor:
+    """`scale_dev`: optional float32 device scalar (autograd's grad_output) multiplied in by the kernel."""
     pred, target = pred.contiguous(), target.contiguous()
     grad = torch.empty_like(pred)
+    if scale_dev is not None and (scale_dev.dtype != torch.float32 or not scale_dev.is_cuda):
+        scale_dev = scale_dev.to(device=pred.device, dtype=torch.float32)
     check(_lib.load().ramnet_si_loss_grad(_h(pred), _p(pred), _p(target), pred.numel(), _p(stats), weight, n_lambda,
-                                          scale, _p(grad), _stream(pred)))
+                                          scale, _p(scale_dev), _lib.LOSS_LOG_SPACE if log_space else 0, _p(grad),
+                                          _stream(pred)))
     return grad
 
 
@@ -493,16 +502,30 @@ def msg_loss_value(stats, N, scales=4):
     return out
 
 
-def msg_loss_grad(pred, target, stats, start_scale=1, scales=4, scale=1.0):
+def msg_loss_grad(pred, target, stats, start_scale=1, scales=4, scale=1.0, n_batch=0, scale_dev=None):
     pred, target = pred.contiguous(), target.contiguous()
     N, C, H, W = pred.shape
     grad = torch.empty_like(pred)
-    check(_lib.load().ramnet_msg_loss_grad(_h(pred), _p(pred), _p(target), N, H, W, start_scale, scales, _p(stats), scale,
-                                           _p(grad), _stream(pred)))
+    if scale_dev is not None and (scale_dev.dtype != torch.float32 or not scale_dev.is_cuda):
+        scale_dev = scale_dev.to(device=pred.device, dtype=torch.float32)
+    check(_lib.load().ramnet_msg_loss_grad(_h(pred), _p(pred), _p(target), N, H, W, start_scale, scales, _p(stats),
+                                           int(n_batch), scale, _p(scale_dev), _p(grad), _stream(pred)))
     return grad
 
 
-def adam_step_dev(p, g, m, v, step_counter, lr=3e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0):
-    """Graph-capturable fused Adam: `step_counter` is an int32 CUDA tensor holding the number of steps taken so far."""
+def msg_sobel_preview(pred, target, pool: int) -> torch.Tensor:
+    """[N,1,H/pool,W/pool] Sobel magnitude of AvgPool2d(pool)(pred - target) (MultiScaleGradient preview=True)."""
+    pred, target = pred.detach().contiguous().float(), target.detach().contiguous().float()
+    N, C, H, W = pred.shape
+    if C != 1:
+        raise _lib.RamnetError('msg_sobel_preview: single-channel depth maps [N,1,H,W] expected')
+    out = torch.empty((N, 1, H // pool, W // pool), dtype=torch.float32, device=pred.device)
+    check(_lib.load().ramnet_msg_sobel_preview(_h(pred), _p(pred), _p(target), N, H, W, int(pool), _p(out), _stream(pred)))
+    return out
+
+
+def adam_step_dev(p, g, m, v, step_counter, lr=3e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, increment=True):
+    """Graph-capturable fused Adam: `step_counter` is an int32 CUDA tensor holding the number of steps taken so far
+    (incremented by this call when `increment`; later slices of the same step pass False)."""
     check(_lib.load().ramnet_adam_step_dev(_h(p), _p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps,
-                                           weight_decay, _p(step_counter), _stream(p)))
+                                           weight_decay, _p(step_counter), int(bool(increment)), _stream(p)))

@@ -28,8 +28,23 @@ def test_library_builds_and_exports_header_symbols():
 
 def test_version_and_error_string_without_gpu():
     lib = _lib.load()
-    assert lib.ramnet_version() == 1
+    hdr = open(os.path.join(ROOT, 'include', 'ramnet_b200.h')).read()
+    assert lib.ramnet_version() == int(re.search(r'#define RAMNET_ABI_VERSION (\d+)', hdr).group(1))
     assert isinstance(lib.ramnet_last_error(), bytes)
+
+
+def test_handle_raises_instead_of_hanging_without_a_gpu():
+    """handle() used to call check() under a non-reentrant lock and deadlock when ramnet_create failed."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip('needs a box without a GPU')
+    code = ('from rpg_ramnet_b200 import _lib\n'
+            'try:\n    _lib.handle(0)\nexcept _lib.RamnetError as e:\n    print("RAISED", e)\n')
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=120, cwd=ROOT)
+    assert 'RAISED' in r.stdout, r.stdout + r.stderr
 
 
 def test_sass_is_sm100a_only():

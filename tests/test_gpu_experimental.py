@@ -1,18 +1,14 @@
-"""GPU tests of the paths written after round 1's GPU budget was spent (default OFF in the product, so these tests are
-skipped unless RAMNET_TEST_EXPERIMENTAL=1): hpack forward (RAMNET_FLAG_HPACK), 64-channel row folding and the fused split
-sum of the tap-packed weight gradient.  First thing to run in round 2:
-
-    RAMNET_TEST_EXPERIMENTAL=1 RAMNET_WGRAD_FOLD=1 RAMNET_WGRAD_FUSED_SUM=1 python -m pytest tests/test_gpu_experimental.py -m gpu -x -q
-"""
+"""GPU tests of the hpack forward (RAMNET_FLAG_HPACK), the 64-channel row folding and the fused split sum of the
+tap-packed weight gradient.  Written at the end of round 1, validated on hardware as the first call of round 2
+(profiles/r02_first_call_experimental_paths.txt) and on by default since (RAMNET_HPACK=0 / RAMNET_WGRAD_FOLD=0 /
+RAMNET_WGRAD_FUSED_SUM=0 switch them off)."""
 import os
 
 import pytest
 import torch
 import torch.nn.functional as F
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('RAMNET_TEST_EXPERIMENTAL', '0') != '1',
-                                 reason='experimental paths are opt-in (RAMNET_TEST_EXPERIMENTAL=1)')]
+pytestmark = [pytest.mark.gpu]
 
 
 def dev():
@@ -56,7 +52,7 @@ def test_hpack_forward_vs_torch(N, Cin, H, W, k, epi):
 
 @pytest.mark.parametrize('shape', [(1, 16, 24, 64, 32, 5), (1, 10, 20, 32, 64, 5), (2, 8, 16, 64, 64, 3)])
 def test_wgrad_fold_and_fused_sum_vs_torch(shape):
-    """Run with RAMNET_WGRAD_FOLD=1 RAMNET_WGRAD_FUSED_SUM=1 in the environment (read once by the library)."""
+    """Folding and the fused sum are the defaults (the library reads RAMNET_WGRAD_FOLD / _FUSED_SUM once)."""
     from rpg_ramnet_b200 import ops
     N, H, W, Ct, Cout, k = shape
     g = torch.Generator().manual_seed(sum(shape))

@@ -15,3 +15,6 @@ export RAMNET_TEST_EXPERIMENTAL=1
 (RAMNET_WGRAD_FOLD=1 RAMNET_WGRAD_FUSED_SUM=1 timeout 300 python -m pytest tests/test_gpu_train.py -m gpu -x -q 2>&1 | tail -15) > gpurun_out/r2_train_tests_fold.log
 (RAMNET_WGRAD_FOLD=1 RAMNET_WGRAD_FUSED_SUM=1 RAMNET_HPACK=1 timeout 300 python bench.py --mode train --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null) > gpurun_out/r2_bench_train_all.json
 tail -3 gpurun_out/r2_experimental_tests.log gpurun_out/r2_model_tests_hpack.log gpurun_out/r2_train_tests_fold.log 2>/dev/null | cat
+# sanitizer feasibility probe (memcheck on the smoke path)
+(timeout 420 compute-sanitizer --tool memcheck --print-limit 20 python __graft_entry__.py smoke 2>&1 | tail -40) > gpurun_out/r2_sanitizer_memcheck_smoke.log
+tail -5 gpurun_out/r2_sanitizer_memcheck_smoke.log
