@@ -146,7 +146,9 @@ def run_sequence(model, items):
 # reference arm: the reference's own CPU implementation of the path = the oracle port (torch CPU
 # conv2d / interpolate exactly as the reference's nn.Modules call them), all host threads.
 # ------------------------------------------------------------------------------------------------
-def cpu_port_rate(torch, n_timesteps, threads, warm=True):
+def oracle_sequence(torch, n_timesteps, threads, seed=2):
+    """The oracle port on the bench workload (same seeded inputs as the CUDA arm): per-timestep depth maps and
+    wall-clock seconds.  Used by the cpu_baseline leg (timing) and by the parity gate (outputs)."""
     from oracle import ramnet_oracle as O
     torch.set_num_threads(threads)
     cfg = dict(MODEL_CFG, gpu=0)
@@ -155,18 +157,17 @@ def cpu_port_rate(torch, n_timesteps, threads, warm=True):
     with contextlib.redirect_stdout(io.StringIO()):
         m = R.ERGB2DepthRecurrent(cfg)            # parameter container only; never run
     sd = {k: v.detach() for k, v in m.state_dict().items()}
-    items = O.synth_sequence(B, H, W, n_timesteps + (1 if warm else 0), K_EVENTS, seed=2, with_targets=False)
+    items = O.synth_sequence(B, H, W, n_timesteps, K_EVENTS, seed=seed, with_targets=False)
     prev_super, prev_lstm = None, {'events0': None, 'image': None}
-    t0 = None
+    preds, secs = [], []
     with torch.no_grad():
-        for i, item in enumerate(items):
-            if i == (1 if warm else 0):
-                t0 = time.perf_counter()
-            _, supers, lstm = O.ergb2depth_recurrent(sd, cfg, item, prev_super, prev_lstm)
+        for item in items:
+            t0 = time.perf_counter()
+            p, supers, lstm = O.ergb2depth_recurrent(sd, cfg, item, prev_super, prev_lstm)
+            secs.append(time.perf_counter() - t0)
+            preds.append(p)
             prev_super, prev_lstm = supers['image'], lstm
-    dt = time.perf_counter() - t0
-    maps = n_timesteps * B * (K_EVENTS + 1)
-    return maps / dt, dt
+    return preds, secs
 
 
 def main_reference(args):
@@ -211,46 +212,67 @@ def main_reference(args):
     return 0
 
 
-
-# ------------------------------------------------------------------------------------------------
-# --mode train : BASELINE configs[2] per GPU (batch 4, seq 8, fwd + bwd + Adam, grad all-reduce under DP)
-# ------------------------------------------------------------------------------------------------
-def main_train(args):
-    import torch
+def setup_dist(torch):
     import torch.distributed as dist
-
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
+    return world, rank, local, torch.device('cuda', local)
+
+
+def teardown_dist(torch, graphs=()):
+    """Captured NCCL collectives pin the communicator: NCCL ties a captured graph to its comm through a CUDA user
+    object, and ncclCommDestroy (inside destroy_process_group) waits until every such graph is gone — the hang round 1
+    papered over with os._exit.  So: drain, destroy the graph objects FIRST, then tear the group down."""
+    import gc
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    for g in graphs:
+        try:
+            g.reset()
+        except Exception:
+            pass
+    gc.collect()
+    torch.cuda.synchronize()
+    if dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# training leg: BASELINE configs[2] per GPU (batch 4, seq 8, fwd + bwd + Adam, grad all-reduce under DP)
+# ------------------------------------------------------------------------------------------------
+def train_leg(args, torch, world, rank, local, dev, graphs):
+    import torch.distributed as dist
     import rpg_ramnet_b200 as R
     from rpg_ramnet_b200 import ops
+    from rpg_ramnet_b200.model.loss import SILossBatch
     from rpg_ramnet_b200.utils.synthetic import synth_sequence
 
     model = build_model(torch, local, args.mma_kind, cuda_graphs=False).train()
     use_graph = not args.no_graphs
-    opt = R.FusedAdam(model.parameters(), lr=3e-4, capturable=use_graph)
+    opt = R.FusedAdam(model.parameters(), lr=3e-4, capturable=use_graph, n_buckets=args.buckets)
     items = synth_sequence(B, H, W, L, K_EVENTS, seed=2 + rank, with_targets=True)
     items = [{k: v.to(dev) for k, v in it.items()} for it in items]
     keys = ['events0', 'image']
-    exact = world > 1          # exact global-batch loss statistics under data parallelism
 
     def step():
         opt.zero_grad()
         prev_super, prev_lstm = None, {'events0': None, 'image': None}
-        terms = []
+        # ONE exchange of the 3 x 16 loss statistics per step (exact global-batch loss under data parallelism, SURVEY §8e)
+        batch = SILossBatch(L * len(keys), dev)
         for item in items:
             preds, supers, lstm = model(item, prev_super, prev_lstm)
             for k in keys:
-                terms.append(R.scale_invariant_loss(preds[k], item['depth_' + k], 1.0, 1.0, process_group=exact))
+                batch.add(preds[k], item['depth_' + k], 1.0, 1.0)
             prev_super, prev_lstm = supers['image'], lstm
-        loss = len(keys) * sum(terms) / float(L)      # lstm_trainer.py loss aliasing
+        loss = len(keys) * batch.finish().sum() / float(L)      # lstm_trainer.py loss aliasing (SURVEY §3.1)
         loss.backward()
-        opt.step()                                    # all-reduces the flat gradient buffer when world > 1
+        opt.step()              # bucketed all-reduce of the flat gradient buffer (side stream) + per-bucket fused Adam
         return loss
 
     def barrier():
@@ -274,6 +296,7 @@ def main_train(args):
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             static_loss = eager_step()
+        graphs.append(graph)
         launches_per_step = R.launch_count(local) - l_before
 
         def step():                      # inputs live in static device tensors (`items`); new data would be copied into them
@@ -298,6 +321,31 @@ def main_train(args):
     launches = R.launch_count(local) - l0
     if launches_per_step is not None:
         launches = launches_per_step * args.steps
+    loss_val = float(loss)
+
+    # the collective on its own: the bucketed all-reduce of the flat fp32 gradient buffer, CUDA events, max over ranks
+    ar = None
+    if world > 1:
+        nbytes = opt.flat_g.numel() * 4
+        for _ in range(3):
+            for _lo, _hi, ready in opt._reducer.launch():
+                ready()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        a0.record()
+        for _ in range(reps):
+            for _lo, _hi, ready in opt._reducer.launch():
+                ready()
+        a1.record()
+        barrier()
+        t = torch.tensor([a0.elapsed_time(a1) / reps], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ar_ms = float(t.item())
+        ar = {'ms': ar_ms, 'bytes': nbytes, 'buckets': len(opt._reducer.spans),
+              'bus_gbs': 2.0 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9,
+              'link_peak_gbs': 900.0, 'what': 'flat fp32 gradient buffer, NCCL all-reduce (sum) on a side stream'}
+
     ops.PROFILE = []
     eager_step()
     torch.cuda.synchronize()
@@ -310,49 +358,53 @@ def main_train(args):
     peak_tf = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops')))
     conv_ms, conv_fl = by.get('conv', (0.0, 0.0))
     wg_ms, wg_fl = by.get('wgrad', (0.0, 0.0))
+    del model, opt, items
+    return {'metric': 'depth-maps/sec at 512x256, 5-bin voxel, seq=8 (fwd+bwd+Adam)',
+            'maps_per_s': world * MAPS_PER_STEP * args.steps / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'loss': loss_val,
+            'cuda_graph': use_graph, 'scaling': 'weak',
+            'workload': f'BASELINE configs[2] per GPU: RAM-Net shipped block, {W}x{H}, batch {B}/GPU, seq {L}, K=1, '
+                        f'SI loss on events0+image, full BPTT, fused Adam(3e-4)',
+            'parallelism': f'dp{world}: bucketed flat fp32 grad all-reduce (NCCL, side stream, per-bucket Adam) + ONE '
+                           f'{3 * L * len(keys)}-double loss-statistics all-reduce per step',
+            'allreduce_ms': None if ar is None else ar['ms'], 'allreduce_bus_gbs': None if ar is None else ar['bus_gbs'],
+            'allreduce': ar, 'clocks': clk.summary(), 'launches': launches,
+            'algorithmic_tflop_per_step': 3.0 * MAPS_PER_STEP * conv_flops_per_map() / 1e12,
+            'conv_fwd_dgrad': {'achieved_tflops': conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0,
+                               'frac_of_bf16_sustained': (conv_fl / (conv_ms * 1e-3) / 1e12 / peak_tf) if conv_ms else 0.0,
+                               'ms_per_step_in_kernel': conv_ms},
+            'wgrad': {'kernel': 'conv_wgrad_packed_kernel (MN-major tf32 UMMA, filter taps packed into the MMA N dimension)',
+                      'achieved_tflops': wg_fl / (wg_ms * 1e-3) / 1e12 if wg_ms else 0.0, 'ms_per_step_in_kernel': wg_ms},
+            'other_kernels_ms_per_step': {k: v[0] for k, v in by.items() if k not in ('conv', 'wgrad')}}
+
+
+def main_train(args):
+    """--mode train: only the training leg, printed as its own JSON line (development aid)."""
+    import torch
+    world, rank, local, dev = setup_dist(torch)
+    graphs = []
+    t = train_leg(args, torch, world, rank, local, dev, graphs)
     if rank == 0:
-        line = {'metric': 'depth-maps/sec at 512x256, 5-bin voxel, seq=8 (fwd+bwd+Adam)',
-                'value': world * MAPS_PER_STEP * args.steps / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world,
-                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
-                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32' if args.mma_kind == 'tf32' else 'f32',
-                'data': 'synthetic', 'mode': 'train', 'loss': float(loss), 'cuda_graph': use_graph,
-                'config': {'workload': f'BASELINE configs[2] per GPU: RAM-Net shipped block, {W}x{H}, batch {B}/GPU, seq {L}, '
-                                       f'K=1, SI loss on events0+image, full BPTT, fused Adam(3e-4)',
-                           'parallelism': f'dp{world}: flat fp32 grad all-reduce (NCCL) + 3-double loss-statistics all-reduce'},
-                'clocks': clk.summary(), 'gpu_launches': launches,
-                'roofline': {'bound': 'tensor', 'kernel': 'conv_tcgen05_halo_kernel fwd + dgrad (implicit GEMM, tcgen05 kind::tf32, cta_group::2 pairs where planned)',
-                             'achieved': conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0, 'peak': peak_tf,
-                             'unit': 'TFLOP/s', 'frac': (conv_fl / (conv_ms * 1e-3) / 1e12 / peak_tf) if conv_ms else 0.0,
-                             'traffic': None, 'peak_source': peak_src, 'ms_per_step_in_kernel': conv_ms},
-                'wgrad': {'kernel': 'conv_wgrad_packed_kernel (MN-major tf32 UMMA, filter taps packed into the MMA N dimension, stride-2 layers as 4 parity classes in one launch, deterministic two-pass reduce)',
-                          'achieved_tflops': wg_fl / (wg_ms * 1e-3) / 1e12 if wg_ms else 0.0, 'ms_per_step_in_kernel': wg_ms},
-                'other_kernels_ms_per_step': {k: v[0] for k, v in by.items() if k not in ('conv', 'wgrad')}}
-        print(json.dumps(line))
-    if world > 1:
+        t['value'] = t['maps_per_s']
+        t['mode'] = 'train'
+        print(json.dumps(t))
         sys.stdout.flush()
-        sys.stderr.flush()
-        barrier()
-        if use_graph:
-            # Measured on 2 GPUs: with the NCCL all-reduces captured inside the step graph, destroy_process_group()
-            # never returns (the line above was printed, then the job sat until the harness killed it).  Every rank has
-            # reported and synchronised, so leave without tearing the communicator down.
-            os._exit(0)
-        dist.destroy_process_group()
+    teardown_dist(torch, graphs)
     return 0
 
+
 # ------------------------------------------------------------------------------------------------
+def rel_err(torch, got, want):
+    """max |got - want| / |want| over a depth map pair (north_star: fp32 depth outputs within 1e-3 relative)."""
+    want = want.double()
+    return float(((got.double().cpu() - want).abs() / want.abs().clamp_min(1e-12)).max())
+
+
 def main_ours(args):
     import torch
     import torch.distributed as dist
 
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    if world > 1:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
+    world, rank, local, dev = setup_dist(torch)
 
     import rpg_ramnet_b200 as R
     from rpg_ramnet_b200 import ops
@@ -385,7 +437,7 @@ def main_ours(args):
 
     def step_resident():
         with torch.no_grad():
-            run_sequence(model, dev_items)
+            return run_sequence(model, dev_items)
 
     host_out = [torch.empty((B, 1, H, W), dtype=torch.float32).pin_memory() for _ in range(L * (K_EVENTS + 1))]
 
@@ -429,6 +481,44 @@ def main_ours(args):
     ms_e2e = timed(step_e2e, args.steps)
     value_e2e = world * MAPS_PER_STEP * args.steps / (ms_e2e * 1e-3)
 
+    # ---- parity gate on the benched shape and on the very paths that were timed: the depth maps of the
+    # first PARITY_T timesteps of (a) the graph-replay resident path and (b) the staged-H2D end-to-end path against the
+    # oracle port on the same seeded inputs.  Rank 0 checks its own shard (seed 2); > 1e-3 relative fails the run.
+    parity, cpu_baseline, oracle_secs = None, None, None
+    PARITY_T = 2
+    if rank == 0 and not args.no_parity:
+        threads = os.cpu_count() or 1
+        # cpu_baseline: a bounded sample of ~10 s of host work (16 timesteps = 128 depth maps at ~14 maps/s on 16 cores)
+        n_t = PARITY_T + (15 if (world == 1 and not args.no_cpu_baseline) else 0)
+        o_preds, oracle_secs = oracle_sequence(torch, n_t, threads, seed=2)
+        res = step_resident()
+        torch.cuda.synchronize()
+        step_e2e()
+        worst_res, worst_e2e, n_maps, i = 0.0, 0.0, 0, 0
+        for t in range(PARITY_T):
+            for k, want in o_preds[t].items():
+                worst_res = max(worst_res, rel_err(torch, res[t][k], want))
+                worst_e2e = max(worst_e2e, rel_err(torch, host_out[i], want))
+                i += 1
+                n_maps += want.shape[0]
+        parity = {'max_rel_err': max(worst_res, worst_e2e), 'max_rel_err_resident_graph_path': worst_res,
+                  'max_rel_err_e2e_staged_path': worst_e2e, 'maps_checked': n_maps, 'tolerance': 1e-3,
+                  'oracle': 'oracle/ramnet_oracle.py (CPU fp32 port pinned on the reference at <= 2e-6)',
+                  'what': f'first {PARITY_T} timesteps ({n_maps} depth maps, {W}x{H}, batch {B}) of the benched sequence, '
+                          'both timed paths'}
+        if n_t > PARITY_T:      # the extra timestep(s) after the warm ones are the CPU baseline sample
+            dt = sum(oracle_secs[1:])
+            rate = (n_t - 1) * B * (K_EVENTS + 1) / dt
+            cpu_baseline = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                            'sample': f'{n_t - 1} timesteps ({(n_t - 1) * 2} passes, batch {B}, {W}x{H}) after 1 warm-up '
+                                      f'timestep of the same workload; oracle port = torch CPU fp32 conv2d/interpolate, {dt:.1f} s'}
+    elif rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        _, secs = oracle_sequence(torch, 3, threads, seed=2)
+        dt = sum(secs[1:])
+        cpu_baseline = {'value': 2 * B * (K_EVENTS + 1) / dt, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                        'sample': f'2 timesteps (4 passes, batch {B}, {W}x{H}) after 1 warm-up timestep; oracle port, {dt:.1f} s'}
+
     # roofline of the dominant kernel family (the implicit-GEMM convolution): every conv launch of one
     # instrumented step bracketed by CUDA events on the launching stream.
     peaks, peak_src = read_peaks()
@@ -445,6 +535,7 @@ def main_ours(args):
     n_conv = sum(1 for p in prof if p[0] == 'conv')
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     peak_tf = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops')))
+    tf32_peak, _ = ops.tf32_pipe_rate(local)      # the pipe the kernel actually uses, measured now at this clock
     other = {}
     for k, f, a, b in prof:
         if k != 'conv':
@@ -456,19 +547,19 @@ def main_ours(args):
         traffic, traffic_src = t.get('bytes_per_launch'), t.get('source')
     roofline = {'bound': 'tensor', 'kernel': 'conv_tcgen05_halo_kernel (ramnet_conv_fwd, all instances: implicit GEMM, tcgen05 kind::tf32, cta_group::2 pairs where planned)',
                 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
-                'traffic': traffic, 'traffic_unit': 'DRAM bytes per conv launch (read+write), ncu', 'traffic_source': traffic_src, 'peak_source': peak_src + ', bf16 sustained; kind::tf32 nominal peak is half of bf16',
+                'peak_tf32_measured': tf32_peak, 'frac_of_tf32_pipe': achieved / tf32_peak if tf32_peak else None,
+                'peak_tf32_source': 'ramnet_tf32_pipe_rate: back-to-back tcgen05.mma kind::tf32 128x256x8 on all SMs, measured in this run',
+                'frac_of_step': MAPS_PER_STEP * conv_flops_per_map() / (ms / args.steps * 1e-3) / 1e12 / peak_tf,
+                'traffic': traffic, 'traffic_unit': 'DRAM bytes per conv launch (read+write), ncu', 'traffic_source': traffic_src,
+                'peak_source': peak_src + ', bf16 sustained (the kernel runs kind::tf32, whose pipe rate is peak_tf32_measured)',
                 'launches_per_step': n_conv, 'ms_per_step_in_kernel': conv_ms,
                 'algorithmic_gflop_per_step': conv_flops / 1e9,
                 'other_kernels_ms_per_step': other, 'mma_kind': args.mma_kind}
 
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        rate, dt = cpu_port_rate(torch, n_timesteps=2, threads=threads)
-        cpu_baseline = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                        'sample': f'2 timesteps (4 passes, batch {B}, {W}x{H}) after 1 warm-up timestep of the same '
-                                  f'workload; oracle port = torch CPU fp32 conv2d/interpolate, {dt:.1f} s'}
-
+    graphs = []
+    for runner in getattr(model, '_runners', {}).values():
+        graphs.extend(g for g, _ in runner.graphs.values())
+    line = None
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
@@ -476,7 +567,8 @@ def main_ours(args):
                 'config': {'workload': f'BASELINE configs[1]: RAM-Net shipped block (ConvGRU state, 3 encoders, base 32) '
                                        f'forward, {W}x{H}, 5-bin voxel + 1 frame, batch {B}/GPU, seq {L}, K=1 '
                                        f'-> {MAPS_PER_STEP} depth maps per step per GPU',
-                           'parallelism': f'dp{world} (batch sharded, no collective)',
+                           'parallelism': f'dp{world} (forward: batch sharded, no collective; the `train` object is '
+                                          f'BASELINE configs[2] with the NCCL gradient all-reduce)',
                            'l2': 'per-step working set (>4 GB of activations) exceeds the 126 MB L2; no explicit flush',
                            'random_init_weights': 'torch.manual_seed(0), reference construction order',
                            'cuda_graphs': not args.no_graphs},
@@ -485,12 +577,27 @@ def main_ours(args):
                         'ms_per_step': ms_e2e / args.steps,
                         'api': 'ERGB2DepthRecurrent.forward(item, prev_super_states, prev_states_lstm) with pinned '
                                'host tensors; depth maps copied back to pinned host memory'},
-                'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
+                'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'parity': parity,
                 'algorithmic_gflop_per_map': conv_flops_per_map() / 1e9}
+    # ---- BASELINE configs[2]: fwd + bwd + Adam with the NCCL gradient all-reduce, attached to the same line -------
+    del dev_items
+    model._runners = {}
+    train = None
+    if not args.no_train:
+        barrier()
+        train = train_leg(args, torch, world, rank, local, dev, graphs)
+    rc = 0
+    if rank == 0:
+        line['train'] = train
+        if train is not None:
+            line['gpu_launches_train'] = train['launches']
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+        sys.stdout.flush()
+        if parity is not None and not (parity['max_rel_err'] <= 1e-3):
+            sys.stderr.write(f'PARITY FAILURE: max rel err {parity["max_rel_err"]:.3e} > 1e-3 on the benched shape\n')
+            rc = 3
+    teardown_dist(torch, graphs)
+    return rc
 
 
 def main():
@@ -501,6 +608,9 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--mma-kind', default=os.environ.get('RAMNET_MMA_KIND', 'tf32'), choices=['tf32', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-parity', action='store_true', help='skip the oracle parity gate on the benched shape')
+    ap.add_argument('--no-train', action='store_true', help='skip the training leg (BASELINE configs[2])')
+    ap.add_argument('--buckets', type=int, default=4, help='slices of the flat gradient all-reduce')
     ap.add_argument('--mode', default='infer', choices=['infer', 'train'], help='train = fwd+bwd+Adam (BASELINE configs[2])')
     ap.add_argument('--no-graphs', action='store_true', help='issue every kernel from Python instead of CUDA-graph replay')
     args = ap.parse_args()

@@ -314,6 +314,12 @@ int ramnet_adam_step_dev(ramnet_handle *h, float *p, const float *g, float *m, f
                          double beta1, double beta2, double eps, double weight_decay, int *step_counter,
                          int increment, void *stream);
 
+/* ---- measurement utility (not on the path) ---------------------------------- *
+ * Live ceiling of the tensor pipe the convolutions use: tcgen05.mma kind::tf32 128x256x8 issued back to back from
+ * shared memory, one CTA per SM, timed with CUDA events on the legacy stream (synchronises).  bench.py reports the
+ * roofline fraction against this number next to the bf16 figure of MEASURED_PEAKS.json. */
+int ramnet_tf32_pipe_rate(ramnet_handle *h, double *tflops_out, double *ms_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,6 +91,59 @@ def voxel_grid_votes(events: np.ndarray, num_bins: int, width: int, height: int)
     return il, pol * (1.0 - dts), ir, pol * dts
 
 
+
+# --------------------------------------------------------------------------
+# every dense contraction of the path goes through _conv2d so that the tests can also ask "what would exact arithmetic
+# on TF32-ROUNDED OPERANDS give?" (the error model of tcgen05.mma kind::tf32 with fp32 accumulate).  The
+# default is plain fp32 F.conv2d — the reference's arithmetic.  Inside `tf32_operands()` the input and the weight of
+# every conv are rounded to TF32 (round-to-nearest-away on 13 mantissa bits, the product's cvt.rna.tf32) in the
+# forward pass, and the gradient arriving at the conv output is rounded the same way in the backward pass (the
+# product rounds dZ before its dgrad / wgrad GEMMs); rounding is straight-through for autograd.
+# --------------------------------------------------------------------------
+_TF32_OPERANDS = False
+
+
+def rna_tf32(t: Tensor) -> Tensor:
+    return ((t.detach().contiguous().view(torch.int32) + 0x1000) & ~0x1fff).view(torch.float32)
+
+
+class _RoundFwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return rna_tf32(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _RoundBwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y):
+        return y.view_as(y)
+
+    @staticmethod
+    def backward(ctx, g):
+        return rna_tf32(g)
+
+
+class tf32_operands:
+    """Context manager: conv operands (and conv-output gradients) rounded to TF32."""
+
+    def __enter__(self):
+        global _TF32_OPERANDS
+        self.prev, _TF32_OPERANDS = _TF32_OPERANDS, True
+
+    def __exit__(self, *exc):
+        global _TF32_OPERANDS
+        _TF32_OPERANDS = self.prev
+
+
+def _conv2d(x, w, b=None, **kw):
+    if _TF32_OPERANDS and x.dtype == torch.float32:
+        return _RoundBwd.apply(F.conv2d(_RoundFwd.apply(x), _RoundFwd.apply(w), b, **kw))
+    return F.conv2d(x, w, b, **kw)
+
 # --------------------------------------------------------------------------
 # a-2/a-3  ConvLayer                    RAM_Net/model/submodules.py:8-35
 # --------------------------------------------------------------------------
@@ -110,7 +163,7 @@ def conv_layer(sd: StateDict, prefix: str, x: Tensor, stride: int, padding: int,
                relu: bool = True, norm: Optional[str] = None) -> Tensor:
     """ConvLayer.forward (submodules.py:26-35): conv (+bias unless BN, :13)
     -> optional norm -> optional relu."""
-    y = F.conv2d(x, sd[prefix + '.conv2d.weight'], sd.get(prefix + '.conv2d.bias'),
+    y = _conv2d(x, sd[prefix + '.conv2d.weight'], sd.get(prefix + '.conv2d.bias'),
                  stride=stride, padding=padding)
     if norm in ('BN', 'IN'):
         y = _norm_eval(sd, prefix + '.norm_layer', y, norm)
@@ -123,7 +176,7 @@ def conv_layer(sd: StateDict, prefix: str, x: Tensor, stride: int, padding: int,
 def upsample_conv_layer(sd: StateDict, prefix: str, x: Tensor, norm: Optional[str] = None) -> Tensor:
     """bilinear x2 (align_corners=False, :88) -> 5x5 s1 p2 conv -> norm -> relu."""
     up = F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=False)
-    y = F.conv2d(up, sd[prefix + '.conv2d.weight'], sd.get(prefix + '.conv2d.bias'), stride=1, padding=2)
+    y = _conv2d(up, sd[prefix + '.conv2d.weight'], sd.get(prefix + '.conv2d.bias'), stride=1, padding=2)
     if norm in ('BN', 'IN'):
         y = _norm_eval(sd, prefix + '.norm_layer', y, norm)
     return torch.relu(y)
@@ -144,11 +197,11 @@ def transposed_conv_layer(sd: StateDict, prefix: str, x: Tensor, norm: Optional[
 # a-6  ResidualBlock                    submodules.py:182-215
 # --------------------------------------------------------------------------
 def residual_block(sd: StateDict, prefix: str, x: Tensor, norm: Optional[str] = None) -> Tensor:
-    y = F.conv2d(x, sd[prefix + '.conv1.weight'], sd.get(prefix + '.conv1.bias'), padding=1)
+    y = _conv2d(x, sd[prefix + '.conv1.weight'], sd.get(prefix + '.conv1.bias'), padding=1)
     if norm in ('BN', 'IN'):
         y = _norm_eval(sd, prefix + '.bn1', y, norm) if norm == 'BN' else F.instance_norm(y)
     y = torch.relu(y)
-    y = F.conv2d(y, sd[prefix + '.conv2.weight'], sd.get(prefix + '.conv2.bias'), padding=1)
+    y = _conv2d(y, sd[prefix + '.conv2.weight'], sd.get(prefix + '.conv2.bias'), padding=1)
     if norm in ('BN', 'IN'):
         y = _norm_eval(sd, prefix + '.bn2', y, norm) if norm == 'BN' else F.instance_norm(y)
     return torch.relu(y + x)
@@ -163,9 +216,9 @@ def conv_gru(sd: StateDict, prefix: str, x: Tensor, h: Optional[Tensor]) -> Tens
     if h is None:
         h = torch.zeros_like(x)
     xh = torch.cat([x, h], 1)
-    u = torch.sigmoid(F.conv2d(xh, sd[prefix + '.update_gate.weight'], sd[prefix + '.update_gate.bias'], padding=1))
-    r = torch.sigmoid(F.conv2d(xh, sd[prefix + '.reset_gate.weight'], sd[prefix + '.reset_gate.bias'], padding=1))
-    o = torch.tanh(F.conv2d(torch.cat([x, h * r], 1), sd[prefix + '.out_gate.weight'],
+    u = torch.sigmoid(_conv2d(xh, sd[prefix + '.update_gate.weight'], sd[prefix + '.update_gate.bias'], padding=1))
+    r = torch.sigmoid(_conv2d(xh, sd[prefix + '.reset_gate.weight'], sd[prefix + '.reset_gate.bias'], padding=1))
+    o = torch.tanh(_conv2d(torch.cat([x, h * r], 1), sd[prefix + '.out_gate.weight'],
                             sd[prefix + '.out_gate.bias'], padding=1))
     return h * (1 - u) + o * u
 
@@ -183,7 +236,7 @@ def conv_lstm(sd: StateDict, prefix: str, x: Tensor,
         c = h.clone()
     else:
         h, c = state
-    g = F.conv2d(torch.cat([x, h], 1), sd[prefix + '.Gates.weight'], sd[prefix + '.Gates.bias'], padding=1)
+    g = _conv2d(torch.cat([x, h], 1), sd[prefix + '.Gates.weight'], sd[prefix + '.Gates.bias'], padding=1)
     gi, gf, go, gc = g.chunk(4, 1)
     c2 = torch.sigmoid(gf) * c + torch.sigmoid(gi) * torch.tanh(gc)
     h2 = torch.sigmoid(go) * torch.tanh(c2)

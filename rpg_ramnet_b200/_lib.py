@@ -94,6 +94,7 @@ SIGNATURES = {
     'ramnet_msg_sobel_preview': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'ramnet_adam_step_dev': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double,
                                      c_double, c_double, c_double, c_void_p, c_int, c_void_p]),
+    'ramnet_tf32_pipe_rate': (c_int, [c_void_p, POINTER(c_double), POINTER(c_double)]),
     'ramnet_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double,
                                  c_double, c_double, c_double, c_int, c_void_p]),
 }

@@ -1576,7 +1576,9 @@ double halo_cost(const ramnet_handle *h, const ramnet_conv_desc *d, const HaloGe
     if (issue_tap > tap) tap = issue_tap;
     tap += 10.0;
     const double mma = (double)chunks * taps * tap;
-    const double l2 = (double)chunks * (halo_bytes + (double)taps * bn_l * 128.0) / 50.0;
+    // L2 -> SM bytes per clock per SM the model assumes (RAMNET_L2_BPC overrides for tuning runs)
+    static const double l2_bpc = [] { const char *e = getenv("RAMNET_L2_BPC"); return e ? atof(e) : 50.0; }();
+    const double l2 = (double)chunks * (halo_bytes + (double)taps * bn_l * 128.0) / l2_bpc;
     const double main = mma > l2 ? mma : l2;
     const double epi = (double)ntiles * (g.BN / 32.0 + 0.5) * 900.0 + 500.0;
     const double per_item = g.nbuf == 2 ? (main > epi ? main : epi) + 300.0 : main + epi;

@@ -311,8 +311,9 @@ class GraphRunner:
 
     Aliasing contract: the state tensors returned by a pass ARE these persistent buffers; they stay
     valid until the second-next pass overwrites them (callers that carry only the latest state —
-    trainer/lstm_trainer.py:380, test.py:380 — are unaffected).  Depth maps are returned as fresh
-    tensors."""
+    trainer/lstm_trainer.py:380, test.py:380 — are unaffected).  A caller that hands back the OLDER of the two
+    sets (state kept for two or more passes, already overwritten) gets a RamnetError instead of silently reading
+    recycled memory; clone the states to keep them longer.  Depth maps are returned as fresh tensors."""
 
     def __init__(self, net, B, H, W, device):
         self.net, self.B, self.H, self.W, self.device = net, B, H, W, device
@@ -325,6 +326,7 @@ class GraphRunner:
         # runs under the kernels of the current one (the reference copies on the compute stream, model.py:177,200)
         self.copy_stream = torch.cuda.Stream(device=device)
         self.slot_ctr = {}
+        self.last_dst = None        # buffer set the most recent pass wrote (the only one a caller may hand back)
 
     def _alloc_states(self):
         out = []
@@ -366,6 +368,10 @@ class GraphRunner:
             self.graphs.clear()
             self.param_sig = sig
         src = self._which_set(prev_super)
+        if src is not None and self.last_dst is not None and src != self.last_dst:
+            raise RamnetError('cuda_graphs: the states passed in are the runner\'s buffer set that the previous pass has '
+                              'already overwritten (states returned by a pass are valid for one further pass only); '
+                              'clone() states that must live longer')
         if src is None:                     # foreign or initial state: bring it into set 0
             src = 0
             mine = self._flat(self.sets[0])
@@ -394,6 +400,7 @@ class GraphRunner:
         graph.replay()
         slot['done'].record(cur)            # the staging slot may be overwritten once this pass has read it
         slot['staged_for'] = None
+        self.last_dst = dst
         return self.sets[dst], pred.clone()
 
     def stage(self, which, x):

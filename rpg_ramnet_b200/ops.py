@@ -180,8 +180,10 @@ def hpack_eligible(Cout: int, ksize: int, stride: int, mma_kind: int) -> bool:
     """Layers the horizontal-tap-packed forward (RAMNET_FLAG_HPACK) is meant for: few output channels at stride 1, where a
     128 x 32 x 8 MMA per tap is bound by the A-operand shared-memory reads.  Default on since round 2 (validated on
     hardware: tests/test_gpu_experimental.py, profiles/r02_first_call_experimental_paths.txt); RAMNET_HPACK=0 disables."""
-    return (os.environ.get('RAMNET_HPACK', '1') != '0' and mma_kind == MMA_TF32 and stride == 1 and ksize in (3, 5)
-            and Cout == 32)
+    if os.environ.get('RAMNET_HPACK', '1') == '0' or mma_kind != MMA_TF32 or stride != 1 or ksize not in (3, 5):
+        return False
+    # Cout > 32 runs as Cout / 32 column slices (the A operand is re-read once per slice): RAMNET_HPACK_MAXC bounds it
+    return Cout % 32 == 0 and Cout <= int(os.environ.get('RAMNET_HPACK_MAXC', '32'))
 
 
 def pack_weights_hpack(w_oihw: torch.Tensor) -> torch.Tensor:
@@ -222,17 +224,23 @@ class _Prof:
                            (self.kind, self.flops, self.a, self.b, self.tag))
 
 
-_workspaces = {}
+_workspaces = {}      # (device, stream) -> [buffers, newest last]
 
 
 def _workspace(device, nbytes: int):
+    """Scratch for the kernels that need one (wgrad partial tiles), one growable buffer per (device, stream): kernels
+    on one stream are ordered, so they can share it; different streams never do.  A buffer that is outgrown is KEPT
+    alive for the life of the process — a captured CUDA graph may have baked its address in, and handing it back to
+    the caching allocator would let graph replays scribble over other tensors (growth is geometric, so the retired
+    buffers sum to less than the live one)."""
     if nbytes == 0:
         return None
-    ws = _workspaces.get(device)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        _workspaces[device] = ws
-    return ws
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    bufs = _workspaces.setdefault(key, [])
+    if not bufs or bufs[-1].numel() < nbytes:
+        grow = max(nbytes, 2 * bufs[-1].numel() if bufs else 0)
+        bufs.append(torch.empty(grow, dtype=torch.uint8, device=device))
+    return bufs[-1]
 
 
 def conv_fwd(x0: torch.Tensor, x1: Optional[torch.Tensor], w_packed: torch.Tensor, bias: Optional[torch.Tensor],
@@ -529,3 +537,10 @@ def adam_step_dev(p, g, m, v, step_counter, lr=3e-4, beta1=0.9, beta2=0.999, eps
     (incremented by this call when `increment`; later slices of the same step pass False)."""
     check(_lib.load().ramnet_adam_step_dev(_h(p), _p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps,
                                            weight_decay, _p(step_counter), int(bool(increment)), _stream(p)))
+
+
+def tf32_pipe_rate(device_index: int = 0):
+    """(TFLOP/s, ms) of back-to-back tcgen05.mma kind::tf32 128x256x8 on every SM, measured now (synchronises)."""
+    tf, ms = ctypes.c_double(), ctypes.c_double()
+    check(_lib.load().ramnet_tf32_pipe_rate(_lib.handle(device_index), ctypes.byref(tf), ctypes.byref(ms)))
+    return tf.value, ms.value

@@ -68,3 +68,49 @@ def test_shard_item_rejects_ragged_batches():
     from rpg_ramnet_b200 import distributed as D
     with pytest.raises(ValueError):
         D.shard_item({'image': torch.zeros(3, 1, 4, 4)}, 0, 2)
+
+
+def _bucket_worker(rank, world, port, ret):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from rpg_ramnet_b200 import distributed as D
+    from rpg_ramnet_b200.model.loss import _resolve_group
+    flat = torch.arange(1003, dtype=torch.float32) * (rank + 1)
+    red = D.BucketedAllReduce(flat, n_buckets=4)
+    spans = []
+    for lo, hi, ready in red.launch():
+        ready()
+        spans.append((lo, hi))
+    # default loss semantics under data parallelism: global statistics (None), local only on request (False)
+    ret[rank] = dict(flat=flat.numpy(), spans=spans, auto=_resolve_group(None)[0], off=_resolve_group(False)[0],
+                     world=D.dp_world_size())
+    dist.destroy_process_group()
+
+
+def test_bucketed_flat_gradient_all_reduce_world2():
+    """The bucketed all-reduce of FusedAdam: contiguous 16-byte aligned slices that cover the buffer exactly once, each
+    summed over the ranks; the loss's process_group default resolves to the global-statistics exchange when
+    world_size > 1 (summed gradients are only right for global-statistics losses)."""
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_bucket_worker, args=(world, port, ret), nprocs=world, join=True)
+    want = np.arange(1003, dtype=np.float32) * 3.0
+    for r in range(world):
+        np.testing.assert_array_equal(ret[r]['flat'], want)
+        spans = ret[r]['spans']
+        assert len(spans) == 4 and spans[0][0] == 0 and spans[-1][1] == 1003
+        assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+        assert all(lo % 4 == 0 for lo, _ in spans)
+        assert ret[r]['auto'] is True and ret[r]['off'] is False and ret[r]['world'] == 2
+
+
+def test_single_process_defaults_are_local():
+    from rpg_ramnet_b200 import distributed as D
+    from rpg_ramnet_b200.model.loss import _resolve_group
+    assert D.dp_world_size() == 1
+    assert _resolve_group(None) == (False, None) and _resolve_group(True) == (False, None)
+    flat = torch.ones(10)
+    out = list(D.BucketedAllReduce(flat, 4).launch())
+    assert [(lo, hi) for lo, hi, _ in out] == [(0, 10)]

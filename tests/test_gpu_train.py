@@ -1,5 +1,6 @@
 """GPU: the training path — hand-written backward kernels behind autograd.Function
 nodes vs torch autograd on the CPU oracle, the reference's own gradient digests, and the fused Adam step."""
+import contextlib
 import json
 import os
 
@@ -315,3 +316,114 @@ def test_fused_adam_training_step_matches_torch_adam():
     for n, p in model.named_parameters():
         ref = sd[n].detach()
         assert float((p.detach().cpu() - ref).abs().max()) <= 1e-5 + 2e-3 * 6e-4, n     # |update| <= 2 lr
+
+
+def _oracle_grads(meta, cfg, seq, sd, tf32):
+    comp, wts = meta['loss_composition'], meta['loss_weights']
+    ctx = O.tf32_operands() if tf32 else contextlib.nullcontext()
+    with ctx:
+        o_s, o_l = None, {'events0': None, 'image': None}
+        terms, keys = [], []
+        for item in seq:
+            preds, supers, lstm = O.ergb2depth_recurrent(sd, cfg, item, o_s, o_l)
+            for key, p in preds.items():
+                if key in comp:
+                    if key not in keys:
+                        keys.append(key)
+                    terms.append(wts[comp.index(key)] * O.si_loss(p, item['depth_' + key], 1.0, 1.0))
+            o_s, o_l = supers['image'], lstm
+        loss = len(keys) * sum(terms) / float(len(seq))
+        loss.backward()
+    return loss
+
+
+def test_tf32_gradients_match_tf32_operand_oracle():
+    """the default (TF32) mode's gradients against the oracle evaluated on TF32-ROUNDED OPERANDS
+    (oracle.tf32_operands: exact fp32 accumulation of rounded conv inputs / weights / output gradients — the
+    arithmetic tcgen05 kind::tf32 performs).  What is left is accumulation order and the handful of ReLU masks whose
+    pre-activation sits within rounding of zero, so the bound is an order of magnitude tighter than against the
+    unrounded fp32 reference digests: 5e-3 on per-tensor norms, 2e-2 relative Frobenius on whole tensors."""
+    g = np.load(os.path.join(GOLDEN, 'grads_shipped.npz'))
+    meta = json.loads(str(g['meta']))
+    meta.update(arch='ERGB2DepthRecurrent')
+    model, cfg = build_product_model(meta, mma_kind='tf32')
+    model.to('cuda:0')
+    seq = case_inputs(meta)
+    comp, wts = meta['loss_composition'], meta['loss_weights']
+    prev_super, prev_lstm = None, {'events0': None, 'image': None}
+    terms, keys = [], []
+    for item in seq:
+        preds, supers, lstm = model(item, prev_super, prev_lstm)
+        for key, p in preds.items():
+            if key in comp:
+                if key not in keys:
+                    keys.append(key)
+                terms.append(wts[comp.index(key)] * R_loss()(p, item['depth_' + key].to('cuda:0'), 1.0, 1.0))
+        prev_super, prev_lstm = supers['image'], lstm
+    loss = len(keys) * sum(terms) / float(len(seq))
+    loss.backward()
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    ref_loss = _oracle_grads(meta, cfg, seq, sd, tf32=True)
+    assert abs(loss.item() - ref_loss.item()) <= 5e-5
+    worst_norm, worst_fro = 0.0, 0.0
+    for n, p in model.named_parameters():
+        a, b = p.grad.detach().cpu().double(), sd[n].grad.double()
+        nb = float(b.norm())
+        worst_norm = max(worst_norm, abs(float(a.norm()) - nb) / max(nb, 1e-12))
+        worst_fro = max(worst_fro, float((a - b).norm()) / max(nb, 1e-12))
+    print(f'tf32 vs tf32-operand oracle: worst norm err {worst_norm:.3e}, worst relative Frobenius {worst_fro:.3e}')
+    assert worst_norm <= 5e-3 and worst_fro <= 2e-2, (worst_norm, worst_fro)
+
+
+def R_loss():
+    import rpg_ramnet_b200 as R
+    return R.scale_invariant_loss
+
+
+def test_tf32_adam_trajectory_three_steps_vs_fp32_oracle():
+    """Three optimisation steps in the DEFAULT mode (TF32 tensor cores, fused Adam) against the fp32 CPU oracle +
+    torch.optim.Adam.  Adam normalises every update to ~lr, so an entry moves by at most lr per step whatever the
+    gradient error; the stated bound: loss within 5e-4 at every step, parameters within 3 x lr x 0.25 of the oracle's
+    after three steps (an update can flip direction only where the gradient is ~0)."""
+    import rpg_ramnet_b200 as R
+    g = np.load(os.path.join(GOLDEN, 'grads_shipped.npz'))
+    meta = json.loads(str(g['meta']))
+    meta.update(arch='ERGB2DepthRecurrent', H=64, W=64, B=2, L=2)
+    model, cfg = build_product_model(meta, mma_kind='tf32')
+    model.to('cuda:0')
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    init = {k: v.detach().clone() for k, v in sd.items()}
+    lr = 3e-4
+    ref_opt = torch.optim.Adam(list(sd.values()), lr=lr)
+    opt = R.FusedAdam(model.parameters(), lr=lr)
+    seq = case_inputs(meta)
+    for step in range(3):
+        opt.zero_grad()
+        prev_s, prev_l = None, {'events0': None, 'image': None}
+        terms = []
+        for item in seq:
+            preds, supers, lstm = model(item, prev_s, prev_l)
+            terms += [R.scale_invariant_loss(preds[k], item['depth_' + k].to('cuda:0')) for k in preds]
+            prev_s, prev_l = supers['image'], lstm
+        loss = 2 * sum(terms) / float(len(seq))
+        loss.backward()
+        opt.step()
+        ref_opt.zero_grad()
+        o_s, o_l = None, {'events0': None, 'image': None}
+        rterms = []
+        for item in seq:
+            rp, rs, rl_ = O.ergb2depth_recurrent(sd, cfg, item, o_s, o_l)
+            rterms += [O.si_loss(rp[k], item['depth_' + k]) for k in rp]
+            o_s, o_l = rs['image'], rl_
+        rl = 2 * sum(rterms) / float(len(seq))
+        rl.backward()
+        ref_opt.step()
+        assert abs(loss.item() - rl.item()) <= 5e-4, (step, loss.item(), rl.item())
+    worst, moved = 0.0, 0.0
+    for n, p in model.named_parameters():
+        ref = sd[n].detach()
+        worst = max(worst, float((p.detach().cpu() - ref).abs().max()))
+        moved = max(moved, float((ref - init[n]).abs().max()))
+    print(f'tf32 trajectory: max |p - p_ref| = {worst:.3e} after 3 steps (parameters moved up to {moved:.3e})')
+    assert moved >= 2.5 * lr                      # the steps really happened
+    assert worst <= 3 * lr * 0.25 + 1e-6, worst

@@ -62,7 +62,8 @@ def main():
         x1s = [ops.empty_nhwc(B, C1, H, W, dev).normal_() for _ in range(nbuf)] if C1 else [None] * nbuf
         Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
         w = torch.randn(Cout, C0 + C1, k, k, device=dev) * 0.02
-        wp = ops.pack_weights(w, kind)
+        hp = epi == ops.EPI_BIAS_RELU and ops.hpack_eligible(Cout, k, stride, kind)
+        wp = ops.pack_weights_hpack(w) if hp else ops.pack_weights(w, kind)
         b = torch.zeros(Cout, device=dev)
         Cs = Cout // 2 if epi == ops.EPI_GRU_RU else Cout
         aux0 = ops.empty_nhwc(B, Cs, Ho, Wo, dev).normal_() if epi in (ops.EPI_GRU_RU, ops.EPI_GRU_OUT) else None

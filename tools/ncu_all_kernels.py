@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""One eager pass over EVERY kernel of the library at the bench shape, for `ncu` (launch list with time and DRAM
+bytes per kernel): config 2 forward timestep, config 3 training step (L=1), voxel grid at 1e6 / 1e7 events, the
+multi-scale gradient loss, the data-IO kernels.  tools/ncu_kernel_table.py turns the CSV into profiles/r02_ncu_all_kernels.txt."""
+import contextlib
+import io
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import rpg_ramnet_b200 as R  # noqa: E402
+from rpg_ramnet_b200.utils.event_tensor_utils import depth_to_log_label, normalize_voxel_grid  # noqa: E402
+from rpg_ramnet_b200.utils.synthetic import synth_events, synth_sequence  # noqa: E402
+
+B, H, W = 4, 256, 512
+cfg = dict(num_bins_rgb=1, num_bins_events=5, skip_type='sum', recurrent_block_type='conv', state_combination='convgru',
+           num_encoders=3, base_num_channels=32, num_residual_blocks=2, use_upsample_conv=True, norm='none',
+           every_x_rgb_frame=1, gpu=0)
+torch.manual_seed(0)
+with contextlib.redirect_stdout(io.StringIO()):
+    model = R.ERGB2DepthRecurrent(cfg)
+model.train().to('cuda:0')
+opt = R.FusedAdam(model.parameters(), lr=3e-4)
+seq = synth_sequence(B, H, W, 1, 1, seed=2, with_targets=True)
+seq = [{k: v.to('cuda:0') for k, v in it.items()} for it in seq]
+for rep in range(2):                  # rep 0 warms the weight caches / attributes; ncu's --launch-skip drops it
+    torch.cuda.nvtx.range_push(f'step{rep}')
+    opt.zero_grad()
+    preds, supers, lstm = model(seq[0], None, {'events0': None, 'image': None})
+    terms = [R.scale_invariant_loss(preds[k], seq[0]['depth_' + k]) for k in preds]
+    terms += [0.25 * R.multi_scale_grad_loss(preds[k], seq[0]['depth_' + k]) for k in preds]
+    sum(terms).backward()
+    opt.step()
+    for n in (1000000, 10000000):
+        ev = torch.from_numpy(synth_events(n, W, H, seed=0)).to('cuda:0')
+        g = R.events_to_voxel_grid(ev, 5, W, H)
+    grids = torch.randn(32, 5, H, W, device='cuda:0') * (torch.rand(32, 5, H, W, device='cuda:0') < 0.1)
+    normalize_voxel_grid(grids)
+    depth = torch.rand(32, 1, H, W, device='cuda:0') * 100
+    lab = depth_to_log_label(depth, 80.0, 3.70378)
+    from rpg_ramnet_b200.model.metric import eval_metrics
+    eval_metrics(torch.rand(32, 1, H, W, device='cuda:0'), lab, ['mse', 'abs_rel_diff', 'scale_invariant_error'])
+    torch.cuda.synchronize()
+    torch.cuda.nvtx.range_pop()
+print('launches', R.launch_count(0))
