@@ -85,6 +85,20 @@ inline cudaError_t ramnet_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block
 // Accurate (not --use_fast_math) transcendental forms: parity with torch.sigmoid / tanh
 // to ~1 ulp matters more here than the handful of SFU cycles.
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// FAST = the TF32 tensor-core kernels: ex2.approx / rcp.approx forms (abs error ~1e-7, two orders of magnitude below the
+// TF32 operand rounding those kernels already carry); the FP32 strict-parity kernels keep the accurate forms.  The gate
+// epilogues are issue- and LSU-bound (RAMNET_PROF: the MMA warp waits for the accumulator buffer on the full-resolution
+// GRU layers), and expf + IEEE division cost ~25 instructions per element against ~6 for these.
+template <bool FAST>
+__device__ __forceinline__ float sigmoid_t(float x) {
+    if constexpr (FAST) return __fdividef(1.0f, 1.0f + __expf(-x));
+    else return sigmoidf_(x);
+}
+template <bool FAST>
+__device__ __forceinline__ float tanh_t(float x) {
+    if constexpr (FAST) return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x));   // e -> inf: 1; e -> 0: -1
+    else return tanhf(x);
+}
 
 __device__ __forceinline__ float round_tf32(float x) {
     uint32_t r;
@@ -159,7 +173,7 @@ __device__ __forceinline__ void st_global_v8(float *dst, const float (&a)[8]) {
                  : "memory");
 }
 
-template <int EPI, int NV>
+template <int EPI, int NV, bool FAST = false>
 __device__ __forceinline__ void epilogue_finish(const EpiParams &p, int64_t m, int n0, float (&v)[NV],
                                                 const EpiAux<NV> &x) {
 #pragma unroll
@@ -208,7 +222,7 @@ __device__ __forceinline__ void epilogue_finish(const EpiParams &p, int64_t m, i
 #pragma unroll
             for (int j = 0; j < NV; j += 4) {
                 const float4 h = x.a[j / 4];
-                const float r0 = sigmoidf_(v[j]), r1 = sigmoidf_(v[j + 1]), r2 = sigmoidf_(v[j + 2]), r3 = sigmoidf_(v[j + 3]);
+                const float r0 = sigmoid_t<FAST>(v[j]), r1 = sigmoid_t<FAST>(v[j + 1]), r2 = sigmoid_t<FAST>(v[j + 2]), r3 = sigmoid_t<FAST>(v[j + 3]);
                 if (p.y2) *reinterpret_cast<float4 *>(p.y2 + m * C + n0 + j) = make_float4(r0, r1, r2, r3);
                 st4(p.y1 + m * C + n0 + j, h.x * r0, h.y * r1, h.z * r2, h.w * r3);
             }
@@ -216,14 +230,14 @@ __device__ __forceinline__ void epilogue_finish(const EpiParams &p, int64_t m, i
 #pragma unroll
             for (int j = 0; j < NV; j += 4)
                 *reinterpret_cast<float4 *>(p.y0 + m * C + (n0 - C) + j) =
-                    make_float4(sigmoidf_(v[j]), sigmoidf_(v[j + 1]), sigmoidf_(v[j + 2]), sigmoidf_(v[j + 3]));
+                    make_float4(sigmoid_t<FAST>(v[j]), sigmoid_t<FAST>(v[j + 1]), sigmoid_t<FAST>(v[j + 2]), sigmoid_t<FAST>(v[j + 3]));
         }
     } else if constexpr (EPI == RAMNET_EPI_GRU_OUT) {
         float hn[NV];
 #pragma unroll
         for (int j = 0; j < NV; j += 4) {
             const float4 h = x.a[j / 4], u = x.b[j / 4];
-            const float o0 = tanhf(v[j]), o1 = tanhf(v[j + 1]), o2 = tanhf(v[j + 2]), o3 = tanhf(v[j + 3]);
+            const float o0 = tanh_t<FAST>(v[j]), o1 = tanh_t<FAST>(v[j + 1]), o2 = tanh_t<FAST>(v[j + 2]), o3 = tanh_t<FAST>(v[j + 3]);
             if (p.y2) *reinterpret_cast<float4 *>(p.y2 + m * p.Cout + n0 + j) = make_float4(o0, o1, o2, o3);
             hn[j] = h.x * (1.f - u.x) + o0 * u.x; hn[j + 1] = h.y * (1.f - u.y) + o1 * u.y;
             hn[j + 2] = h.z * (1.f - u.z) + o2 * u.z; hn[j + 3] = h.w * (1.f - u.w) + o3 * u.w;
@@ -235,10 +249,10 @@ __device__ __forceinline__ void epilogue_finish(const EpiParams &p, int64_t m, i
         float hn[NV / 4], cn[NV / 4];
 #pragma unroll
         for (int q = 0; q < NV / 4; ++q) {
-            const float gi = sigmoidf_(v[4 * q]), gf = sigmoidf_(v[4 * q + 1]);
-            const float go = sigmoidf_(v[4 * q + 2]), gc = tanhf(v[4 * q + 3]);
+            const float gi = sigmoid_t<FAST>(v[4 * q]), gf = sigmoid_t<FAST>(v[4 * q + 1]);
+            const float go = sigmoid_t<FAST>(v[4 * q + 2]), gc = tanh_t<FAST>(v[4 * q + 3]);
             cn[q] = gf * cprev[q] + gi * gc;
-            hn[q] = go * tanhf(cn[q]);
+            hn[q] = go * tanh_t<FAST>(cn[q]);
             if (rnd) hn[q] = round_tf32(hn[q]);
             if (p.y2) *reinterpret_cast<float4 *>(p.y2 + (m * C + (n0 >> 2) + q) * 4) = make_float4(gi, gf, go, gc);
         }

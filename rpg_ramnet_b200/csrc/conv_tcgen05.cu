@@ -784,14 +784,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
                                 } else if (valid) {
                                     EpiAux<16> xa;
                                     epilogue_prefetch<EPI, 16>(ep, m, nch0 + c0, xa);
-                                    epilogue_finish<EPI, 16>(ep, m, nch0 + c0, acc, xa);
+                                    epilogue_finish<EPI, 16, true>(ep, m, nch0 + c0, acc, xa);
                                 }
                             }
                             if constexpr (kPred) {
                                 if (valid) {
                                     const float logit = dot + __ldg(ep.aux1);
                                     if (ep.y1) ep.y1[m] = logit;
-                                    ep.y0[m] = sigmoidf_(logit);
+                                    ep.y0[m] = sigmoid_t<true>(logit);
                                 }
                             }
                         }
@@ -823,7 +823,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
                             const int64_t m = ((int64_t)img * g.out_H + oy * g.out_sy + g.out_oy) * g.out_W + ox * g.out_sx + g.out_ox;
                             const float logit = dot + __ldg(ep.aux1);
                             if (ep.y1) ep.y1[m] = logit;
-                            ep.y0[m] = sigmoidf_(logit);
+                            ep.y0[m] = sigmoid_t<true>(logit);
                         }
                     }
                 }
@@ -845,7 +845,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
                         float v[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]);
-                        epilogue_finish<EPI, 16>(ep, ua.m, n0 + ua.col, v, xa);
+                        epilogue_finish<EPI, 16, true>(ep, ua.m, n0 + ua.col, v, xa);
                     }
                     if (u + 1 < units) {
                         tmem_ld_wait(rb);
@@ -858,7 +858,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
                             float v[16];
 #pragma unroll
                             for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rb[i]);
-                            epilogue_finish<EPI, 16>(ep, ub.m, n0 + ub.col, v, xb);
+                            epilogue_finish<EPI, 16, true>(ep, ub.m, n0 + ub.col, v, xb);
                         }
                     }
                 }
@@ -1359,13 +1359,15 @@ int launch_halo_pair(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap 
     cfg.blockDim = dim3(kHaloThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // RAMNET_PDL=1: prologue under the predecessor's tail
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = ramnet_pdl_enabled() ? 2 : 1;
     static const bool do_prof = getenv("RAMNET_PROF") != nullptr;      // debug only: synchronises and prints
     if (do_prof) {
         static unsigned long long *buf = nullptr;
@@ -1580,7 +1582,16 @@ double halo_cost(const ramnet_handle *h, const ramnet_conv_desc *d, const HaloGe
     static const double l2_bpc = [] { const char *e = getenv("RAMNET_L2_BPC"); return e ? atof(e) : 50.0; }();
     const double l2 = (double)chunks * (halo_bytes + (double)taps * bn_l * 128.0) / l2_bpc;
     const double main = mma > l2 ? mma : l2;
-    const double epi = (double)ntiles * (g.BN / 32.0 + 0.5) * 900.0 + 500.0;
+    // epilogue of one item, calibrated on RAMNET_PROF (total - mma_total of single-round layers, round 2): cycles per
+    // accumulator column of a 128-row tile: ~57 for bias / relu / residual, ~115 for the GRU reset/update gates
+    // (two outputs + h), ~150 for the GRU candidate / LSTM (two aux operands, blend).  Opt-in (RAMNET_EPI_MODEL=1): measured
+    // on B200 the plans it picks are SLOWER (one pass 895 -> 941 us, profiles/r02_epilogue_model_ab.txt), so the
+    // round-1 model stays the default.
+    static const bool epi_v2 = [] { const char *e = getenv("RAMNET_EPI_MODEL"); return e && e[0] == '1'; }();
+    const double k_epi = d->epilogue == RAMNET_EPI_GRU_RU ? 115.0
+                         : (d->epilogue == RAMNET_EPI_GRU_OUT || d->epilogue == RAMNET_EPI_LSTM) ? 150.0 : 57.0;
+    const double epi = epi_v2 ? (double)ntiles * g.BN * k_epi + 1500.0
+                              : (double)ntiles * (g.BN / 32.0 + 0.5) * 900.0 + 500.0;
     const double per_item = g.nbuf == 2 ? (main > epi ? main : epi) + 300.0 : main + epi;
     const int workers = g.pair ? h->sm_count / 2 : h->sm_count;
     const int64_t rounds = (g.items + workers - 1) / workers;

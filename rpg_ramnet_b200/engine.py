@@ -98,18 +98,20 @@ def _norm_sources(nm):
     return [getattr(nm, a, None) for a in ('running_mean', 'running_var', 'weight', 'bias')]
 
 
-def pack_conv(cache: WeightCache, key, conv, kind: int, norm_mod=None, norm_kind=None, training=False) -> Packed:
-    """nn.Conv2d (+ folded eval norm) -> Packed for ramnet_conv_fwd."""
+def pack_conv(cache: WeightCache, key, conv, kind: int, norm_mod=None, norm_kind=None, training=False,
+              hpack_ok=False) -> Packed:
+    """nn.Conv2d (+ folded eval norm) -> Packed for ramnet_conv_fwd.  `hpack_ok`: the caller's epilogue is one the
+    horizontal-tap-packed kernel implements (bias / relu / residual / fused pred), so eligible layers may use it."""
     def build():
         w, b = conv.weight.detach().float(), None if conv.bias is None else conv.bias.detach().float()
         w, b = _fold_norm(w, b, norm_mod, norm_kind, training)
         p = Packed()
-        hp = ops.hpack_eligible(w.shape[0], w.shape[2], conv.stride[0], kind)
+        hp = hpack_ok and ops.hpack_eligible(w.shape[0], w.shape[2], conv.stride[0], kind)
         p.w = ops.pack_weights_hpack(w) if hp else ops.pack_weights(w, kind)
         p.b = None if b is None else b.contiguous()
         p.Cout, p.ksize, p.stride = w.shape[0], w.shape[2], conv.stride[0]
         return p
-    hp_key = ops.hpack_eligible(conv.weight.shape[0], conv.weight.shape[2], conv.stride[0], kind)
+    hp_key = hpack_ok and ops.hpack_eligible(conv.weight.shape[0], conv.weight.shape[2], conv.stride[0], kind)
     return cache.get(key, [conv.weight, conv.bias] + _norm_sources(norm_mod), (kind, training, hp_key), build)
 
 
@@ -214,7 +216,8 @@ def head_layer(cache, key, conv, x, tf32):
 
 def conv_layer(cache, key, conv, kind, x, epilogue, x1=None, res=None, norm_mod=None, norm_kind=None, training=False,
                round_out=False):
-    p = pack_conv(cache, key, conv, kind, norm_mod, norm_kind, training)
+    p = pack_conv(cache, key, conv, kind, norm_mod, norm_kind, training,
+                  hpack_ok=epilogue in (ops.EPI_BIAS, ops.EPI_BIAS_RELU, ops.EPI_BIAS_RES_RELU) and x1 is None)
     if needs_grad(x, x1, res, conv.weight, conv.bias):
         _no_fold_in_training(norm_mod, norm_kind)
         from .autograd import ConvFn

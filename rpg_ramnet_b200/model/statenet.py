@@ -250,7 +250,7 @@ class StateNetPhasedRecurrent(BaseStateNet):
             if fuse:
                 # last decoder + pred + sigmoid in one kernel: the 32-channel full-resolution tensor is never written
                 p = E.pack_conv(cache, f'dec{i}', dec.conv2d, kind, getattr(dec, 'norm_layer', None), dec.norm,
-                                self.training)
+                                self.training, hpack_ok=True)
                 pw, pb = pr.conv2d.weight.detach().float(), None if pr.conv2d.bias is None else pr.conv2d.bias.detach().float()
                 pw, pb = E._fold_norm(pw, pb, getattr(pr, 'norm_layer', None), pr.norm, self.training)
                 N, _, Hh, Ww = up.shape
