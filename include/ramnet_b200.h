@@ -72,15 +72,23 @@ enum {
      * t = relu(acc + b) is never written; y0[m] = sigmoid(sum_n t[n]*aux0[n] + aux1[0]) (depth,
      * [N,1,H,W]); y1[m] (may be NULL) = the logit.  aux0 = pred weight [Cout], aux1 = pred bias [1].
      * TF32 path only, Cout a multiple of 32 and <= 256 (one Cout slice per tile). */
-    RAMNET_EPI_BIAS_RELU_PRED = 6
+    RAMNET_EPI_BIAS_RELU_PRED = 6,
+    /* y0 = relu(acc + b) + aux0: a decoder layer that also forms the NEXT decoder's skip sum (statenet.py:15-16,306-308,
+     * `x + super_state`), so that the sum never needs its own pass.  aux0 has the output's shape. */
+    RAMNET_EPI_BIAS_RELU_ADD = 7
 };
 
 enum {
     RAMNET_FLAG_ROUND_TF32 = 1, /* round every stored output to TF32 (rna) so a
                                    following kind::tf32 MMA truncates nothing */
-    RAMNET_FLAG_HPACK = 2       /* ramnet_conv_fwd: w_packed is in ramnet_pack_weights_hpack's layout (horizontal taps as
+    RAMNET_FLAG_HPACK = 2,      /* ramnet_conv_fwd: w_packed is in ramnet_pack_weights_hpack's layout (horizontal taps as
                                    GEMM columns); stride 1, ksize 3/5, bias / relu / residual / pred epilogues.
-                                   Opt-in (RAMNET_HPACK=1 on the Python side), not yet validated on hardware. */
+                                   Default for Cout = 32 layers since round 2 (RAMNET_HPACK=0 on the Python side disables). */
+    RAMNET_FLAG_UPCONV = 4      /* ramnet_conv_fwd: bilinear x2 (align_corners=False) FOLLOWED BY the 5x5 stride-1 convolution
+                                   (UpsampleConvLayer.forward, submodules.py:87-97) in one launch on the LOW-resolution
+                                   input: desc.H/W are the input's, y0 is [N, Cout, 2H, 2W].  w_packed comes from
+                                   ramnet_pack_weights_upconv (collapsed taps of the 4 output phases + border segments).
+                                   Epilogues: BIAS_RELU, BIAS_RELU_ADD, BIAS_RELU_PRED.  TF32 path, x1 = NULL. */
 };
 
 /* One implicit-GEMM convolution:  y[m, n] = epi( sum_{tap,c} x[pix(m,tap), c] * w[tap, n, c] ).
@@ -156,6 +164,12 @@ int ramnet_conv_fwd(ramnet_handle *h, const ramnet_conv_desc *d, const float *x0
  * the layout RAMNET_FLAG_HPACK launches read (csrc/conv_tcgen05.cu fill_hpack; tests/test_hpack_index_algebra.py). */
 int ramnet_pack_weights_hpack(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin,
                               int ksize, void *stream);
+/* [Cout, Cin, 5, 5] -> the RAMNET_FLAG_UPCONV layout [tap][4 * Cout][Cin], TF32-rounded: for every tap of the main
+ * segment (5x5 window on the low-resolution input) and of the 8 border segments (first / last row, first / last column,
+ * 4 corners) the 5x5 filter collapsed through the bilinear x2 coefficients, one block of Cout rows per output phase
+ * (py, px).  ramnet_upconv_packed_floats gives the size of w_packed in floats. */
+int64_t ramnet_upconv_packed_floats(int Cout, int Cin);
+int ramnet_pack_weights_upconv(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin, void *stream);
 int ramnet_pack_weights(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin,
                         int ksize, int mma_kind, int lstm_interleave, void *stream);
 

@@ -13,9 +13,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libramnet_sm100a.so')
 
 MMA_FP32, MMA_TF32 = 0, 1
-EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RES_RELU, EPI_GRU_RU, EPI_GRU_OUT, EPI_LSTM, EPI_BIAS_RELU_PRED = range(7)
+EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RES_RELU, EPI_GRU_RU, EPI_GRU_OUT, EPI_LSTM, EPI_BIAS_RELU_PRED, EPI_BIAS_RELU_ADD = range(8)
 FLAG_ROUND_TF32 = 1
 FLAG_HPACK = 2
+FLAG_UPCONV = 4
 LOSS_LOG_SPACE = 1
 
 
@@ -49,6 +50,8 @@ SIGNATURES = {
     'ramnet_pack_weights_dgrad': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                           c_void_p]),
     'ramnet_pack_weights_hpack': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'ramnet_upconv_packed_floats': (c_int64, [c_int, c_int]),
+    'ramnet_pack_weights_upconv': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'ramnet_plan_describe': (c_int, [POINTER(ConvDesc), c_int, c_char_p, c_size_t]),
     'ramnet_voxel_normalize': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     'ramnet_depth_to_label': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_void_p]),

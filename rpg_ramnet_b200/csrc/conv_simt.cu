@@ -135,9 +135,10 @@ static int validate_desc(const ramnet_conv_desc *d) {
     RAMNET_CHECK_ARG(d->C0 > 0 && d->C0 % 16 == 0 && d->C1 >= 0 && d->C1 % 16 == 0,
                      "conv: channel counts C0=%d C1=%d must be multiples of 16", d->C0, d->C1);
     RAMNET_CHECK_ARG(d->Cout > 0 && d->Cout % 4 == 0, "conv: Cout=%d must be a positive multiple of 4", d->Cout);
-    RAMNET_CHECK_ARG(d->epilogue >= RAMNET_EPI_BIAS && d->epilogue <= RAMNET_EPI_BIAS_RELU_PRED, "conv: bad epilogue %d", d->epilogue);
+    RAMNET_CHECK_ARG(d->epilogue >= RAMNET_EPI_BIAS && d->epilogue <= RAMNET_EPI_BIAS_RELU_ADD, "conv: bad epilogue %d", d->epilogue);
     RAMNET_CHECK_ARG(d->mma_kind == RAMNET_MMA_FP32 || d->mma_kind == RAMNET_MMA_TF32, "conv: bad mma_kind %d", d->mma_kind);
     RAMNET_CHECK_ARG(!(d->flags & RAMNET_FLAG_HPACK) || d->mma_kind == RAMNET_MMA_TF32, "conv: RAMNET_FLAG_HPACK needs mma_kind=TF32");
+    RAMNET_CHECK_ARG(!(d->flags & RAMNET_FLAG_UPCONV) || d->mma_kind == RAMNET_MMA_TF32, "conv: RAMNET_FLAG_UPCONV needs mma_kind=TF32");
     if (d->epilogue == RAMNET_EPI_GRU_RU) RAMNET_CHECK_ARG(d->Cout % 8 == 0, "conv: GRU_RU needs Cout = 2C with C%%4 == 0");
     if (d->epilogue == RAMNET_EPI_LSTM) RAMNET_CHECK_ARG(d->Cout % 16 == 0, "conv: LSTM needs Cout = 4C with C%%4 == 0");
     return RAMNET_OK;
@@ -160,6 +161,11 @@ extern "C" int ramnet_conv_fwd(ramnet_handle *h, const ramnet_conv_desc *d, cons
     RAMNET_CHECK_ARG((d->C1 == 0) == (x1 == nullptr), "conv_fwd: x1 and C1 disagree");
     switch (d->epilogue) {
         case RAMNET_EPI_BIAS_RES_RELU: RAMNET_CHECK_ARG(aux0, "conv_fwd: residual epilogue needs aux0"); break;
+        case RAMNET_EPI_BIAS_RELU_ADD:
+            RAMNET_CHECK_ARG(aux0, "conv_fwd: relu+add epilogue needs aux0");
+            if (d->mma_kind != RAMNET_MMA_TF32)
+                return ramnet_set_error(RAMNET_EUNSUPPORTED, "conv_fwd: the relu+add epilogue is implemented on the TF32 path only");
+            break;
         case RAMNET_EPI_GRU_RU: RAMNET_CHECK_ARG(aux0 && y1, "conv_fwd: GRU_RU needs aux0 (h) and y1"); break;
         case RAMNET_EPI_GRU_OUT: RAMNET_CHECK_ARG(aux0 && aux1, "conv_fwd: GRU_OUT needs aux0 (h) and aux1 (u)"); break;
         case RAMNET_EPI_LSTM: RAMNET_CHECK_ARG(aux0 && y1, "conv_fwd: LSTM needs aux0 (c) and y1"); break;

@@ -315,6 +315,22 @@ struct RectSpec {
     int out_sy, out_sx, out_oy, out_ox, out_H, out_W;
 };
 
+// Up-conv mode (RAMNET_FLAG_UPCONV): bilinear x2 (align_corners=False) + 5x5 conv as ONE 5x5 convolution over the
+// LOW-resolution tensor with 4 * Cout output columns (phase-major [py][px][co], weights collapsed at pack time) and a
+// depth-to-space store.  Zero padding applies in the HIGH-resolution domain and the bilinear clamp replicates the edge,
+// so near the image border the collapsed weights differ; the difference only involves the first / last row and column
+// of the input and is added by extra K segments that read edge-only VIEWS of the same tensor (a tensor map whose
+// bounds are that row / column / corner pixel: everything else is TMA zero fill) with their own collapsed taps.
+constexpr int kMaxUpSeg = 9;      // main, top, bottom, left, right, 4 corners
+struct UpSeg {
+    int tap0;                // first tap of this segment in the packed weight tensor
+    int ntaps;               // taps (multiple of tpg; corners are padded with zero taps)
+    int kh, kw, lo_y, lo_x;  // tap window: tap i -> (lo_y + i / kw, lo_x + i % kw) relative to the output pixel
+    int vx, vy;              // origin of the view in full-tensor coordinates
+    int cond;                // border bits a patch / tile must touch: 1 top, 2 bottom, 4 left, 8 right
+};
+struct UpMaps { CUtensorMap m[kMaxUpSeg - 1]; };
+
 struct HaloGeom {
     int N, H, W, Cout;       // input height / width
     int Ho, Wo;              // output height / width
@@ -335,6 +351,11 @@ struct HaloGeom {
     int hpack, cs, kwp;      // hpack: the kwp horizontal taps are GEMM columns (N = kwp * cs) of kh row-shifted MMAs over a
                              // 32 px x 4 row tile; the epilogue sums the taps across the lanes of an image row (see fill_hpack)
     int nbuf;                // TMEM accumulator buffers
+    int up;                  // 1: up-conv mode; Cout is then 4 * up_cout GEMM columns
+    int up_cout;             // output channels of the up-conv (columns per phase)
+    int nseg;                // K segments (1 + border views)
+    int total_taps;          // taps of all segments
+    UpSeg seg[kMaxUpSeg];
     int pair;                // 1: CTA-pair mode (cta_group::2, M = 256): a work item is two patches x one BN-wide slice
     int items;               // patches (pair mode: patch pairs) * n_slices
     unsigned long long *prof; // RAMNET_PROF=1: per-role wait-cycle counters (debug), else nullptr
@@ -472,11 +493,12 @@ __device__ __forceinline__ void halo_arrive_leader(uint64_t *bar) {
     }
 }
 
-template <int EPI, bool PAIR, bool HPACK = false>
+template <int EPI, bool PAIR, bool HPACK = false, bool UP = false>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(const __grid_constant__ CUtensorMap map_x0,
                                                                             const __grid_constant__ CUtensorMap map_x1,
                                                                             const __grid_constant__ CUtensorMap map_w,
-                                                                            HaloGeom g, EpiParams ep) {
+                                                                            const __grid_constant__ UpMaps upm,
+                                                                            const __grid_constant__ HaloGeom g, EpiParams ep) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int plane_bytes = g.HX * g.HY * kChunk * 4;
@@ -525,7 +547,17 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
     if (warp == 3) {
         // tap (r, s) -> where its A tile starts inside a halo stage.  Stride 1: one plane, shift (r, s).
         // Stride 2: input row 2*oy + (r - pad) = 2*(oy + dy) + py -> parity plane (py, px), shift (dy, dx).
-        if (lane < g.kh * g.kw) {
+        if constexpr (UP) {
+            // every segment's box is anchored at its own tap window, so tap i of a segment sits (i / kw, i % kw) pixels
+            // into the halo stage; padding taps (corner segments) point at the origin and carry zero weights
+            for (int i = lane; i < g.total_taps; i += 32) {
+                int sg = 0;
+                while (sg + 1 < g.nseg && i >= g.seg[sg + 1].tap0) ++sg;
+                const int loc = i - g.seg[sg].tap0;
+                const int r = loc / g.seg[sg].kw, sx = loc % g.seg[sg].kw;
+                tap_tab[i] = loc < g.seg[sg].kh * g.seg[sg].kw ? (uint32_t)((r * g.HX + sx) * 8) : 0u;
+            }
+        } else if (lane < g.kh * g.kw) {
             const int r = lane / g.kw, sx = lane % g.kw;
             int off;
             if (g.stride == 1) {
@@ -562,10 +594,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
 
     // item -> (Cout slice, image, patch origin); consecutive items share the weight slice (L2 reuse)
     const int patches_w = PAIR ? (patches + 1) >> 1 : patches;   // patches (pair mode: patch pairs) per Cout slice
-    auto decode = [&](int item, int &n0, int &img, int &x0, int &y0) {
+    auto decode_r = [&](int item, int rank, int &n0, int &img, int &x0, int &y0) {
         const int slice = item / patches_w;
         int t = item - slice * patches_w;
-        if constexpr (PAIR) t = 2 * t + (int)cta_rank;           // an odd patch count leaves img == N: all out of bounds
+        if constexpr (PAIR) t = 2 * t + rank;                    // an odd patch count leaves img == N: all out of bounds
         const int pxi = t % g.patches_x;
         t /= g.patches_x;
         const int pyi = t % g.patches_y;
@@ -579,6 +611,36 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
         }
         n0 = slice * g.BN;
     };
+    auto decode = [&](int item, int &n0, int &img, int &x0, int &y0) { decode_r(item, (int)cta_rank, n0, img, x0, y0); };
+    // up-conv: which image borders a rectangle touches (bit 1 top, 2 bottom, 4 left, 8 right): the rows / columns whose
+    // outputs need the border segments are the first two and the last two of the low-resolution image
+    auto border_bits = [&](int x0, int y0, int w, int h) {
+        int f = 0;
+        if (y0 == 0) f |= 1;
+        if (y0 + h > g.H - 2 && y0 < g.H) f |= 2;
+        if (x0 == 0) f |= 4;
+        if (x0 + w > g.W - 2 && x0 < g.W) f |= 8;
+        return f;
+    };
+    // Border bits of a work item's patch and of each of its tiles.  In pair mode ONE instruction stream serves both
+    // CTAs, so every role of both CTAs uses the union over the two patches; the CTA whose patch does not touch that
+    // border reads nothing but TMA zero fill from the edge view, i.e. contributes zero.
+    auto item_bits = [&](int item, int &pf, int (&tf)[4]) {
+        pf = 0;
+#pragma unroll
+        for (int tl = 0; tl < 4; ++tl) tf[tl] = 0;
+        for (int rk = 0; rk < (PAIR ? 2 : 1); ++rk) {
+            int n0, img, x0, y0;
+            decode_r(item, rk, n0, img, x0, y0);
+            if (img >= g.N) continue;
+            pf |= border_bits(x0, y0, g.PTX * 8, g.PTY * 16);
+#pragma unroll
+            for (int tl = 0; tl < 4; ++tl)
+                if (tl < g.PTX * g.PTY)
+                    tf[tl] |= border_bits(x0 + (tl & (g.PTX - 1)) * 8, y0 + (tl >> g.ptx_log2) * 16, 8, 16);
+        }
+    };
+    const int nseg = UP ? g.nseg : 1;
 
     if (warp == 0) {
         // ---------------- halo producer: one box per (item, 32-channel chunk) ----------------
@@ -587,6 +649,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
         for (int item = worker; item < g.items; item += nworkers) {
             int n0, img, x0, y0;
             decode(item, n0, img, x0, y0);
+            int pf = 0, tf[4];
+            if constexpr (UP) item_bits(item, pf, tf);
+            for (int sg = 0; sg < nseg; ++sg) {
+            if (UP && sg > 0 && (g.seg[sg].cond & ~pf)) continue;
             for (int ch = 0; ch < chunks; ++ch) {
                 mbar_wait_t(a_empty + stage, phase ^ 1, prof, w0);
                 if (elect_one()) {
@@ -595,7 +661,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
                     const CUtensorMap *mx = second ? &map_x1 : &map_x0;
                     const int c = (second ? ch - chunks0 : ch) * kChunk;
                     uint8_t *dst = smem + (size_t)stage * a_stride;
-                    if (g.stride == 1) {
+                    if constexpr (UP) {
+                        const UpSeg &us = g.seg[sg];
+                        halo_tma_4d<PAIR>(dst, sg == 0 ? &map_x0 : &upm.m[sg - 1], a_full + stage, c, x0 + us.lo_x - us.vx,
+                                          y0 + us.lo_y - us.vy, img);
+                    } else if (g.stride == 1) {
                         halo_tma_4d<PAIR>(dst, mx, a_full + stage, c, x0 + g.lo_x, y0 + g.lo_y, img);
                     } else {
                         const int Csrc = second ? g.C1 : g.C0;
@@ -608,6 +678,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
                 __syncwarp();
                 if (++stage == g.a_stages) { stage = 0; phase ^= 1; }
             }
+            }
         }
         if (prof && lane == 0) atomicAdd(g.prof + 4, w0);
     } else if (warp == 2) {
@@ -616,16 +687,23 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
         uint32_t phase = 0;
         for (int item = worker; item < g.items; item += nworkers) {
             const int n0 = (item / patches_w) * g.BN + (int)cta_rank * bn_local;   // pair mode: this CTA's half of the slice
+            int pf = 0, tf[4];
+            if constexpr (UP) item_bits(item, pf, tf);
+            for (int sg = 0; sg < nseg; ++sg) {
+            if (UP && sg > 0 && (g.seg[sg].cond & ~pf)) continue;
+            const int seg_taps = UP ? g.seg[sg].ntaps : taps, seg_tap0 = UP ? g.seg[sg].tap0 : 0;
             for (int ch = 0; ch < chunks; ++ch) {
-                for (int tap = 0; tap < taps; tap += g.tpg) {     // one box = tpg taps x bn_local rows x 32 channels
+                for (int tap = 0; tap < seg_taps; tap += g.tpg) {     // one box = tpg taps x bn_local rows x 32 channels
                     mbar_wait_t(b_empty + stage, phase ^ 1, prof, w0);
                     if (elect_one()) {
                         if (leader) mbar_expect_tx(b_full + stage, (uint32_t)b_bytes * (PAIR ? 2u : 1u));
-                        halo_tma_3d<PAIR>(smem_b + (size_t)stage * b_bytes, &map_w, b_full + stage, ch * kChunk, n0, tap);
+                        halo_tma_3d<PAIR>(smem_b + (size_t)stage * b_bytes, &map_w, b_full + stage, ch * kChunk, n0,
+                                          seg_tap0 + tap);
                     }
                     __syncwarp();
                     if (++stage == g.b_stages) { stage = 0; phase ^= 1; }
                 }
+            }
             }
         }
         if (prof && lane == 0) atomicAdd(g.prof + 5, w0);
@@ -653,10 +731,22 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
             mbar_wait_t(acc_empty + buf, (use & 1) ^ 1, prof, w2);          // epilogue has drained this buffer
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t acc_base = tmem_base + (uint32_t)(buf * acc_cols);
+            int pf = 0, tf[4] = {0, 0, 0, 0};
+            if constexpr (UP) item_bits(item, pf, tf);
+            for (int sg = 0; sg < nseg; ++sg) {
+            if (UP && sg > 0 && (g.seg[sg].cond & ~pf)) continue;
+            const int seg_taps = UP ? g.seg[sg].ntaps : taps, seg_tap0 = UP ? g.seg[sg].tap0 : 0;
+            uint32_t tmask = 0xFu;     // tiles of the patch this segment contributes to (border segments: border tiles only)
+            if (UP && sg > 0) {
+                tmask = 0;
+#pragma unroll
+                for (int tl = 0; tl < 4; ++tl)
+                    if (!(g.seg[sg].cond & ~tf[tl])) tmask |= 1u << tl;
+            }
             for (int ch = 0; ch < chunks; ++ch) {
                 mbar_wait_t(a_full + sa, pa, prof, w0);
                 const uint32_t a16 = (smem_u32(smem + (size_t)sa * a_stride) & 0x3FFFFu) >> 4;
-                for (int tap0 = 0; tap0 < taps; tap0 += g.tpg) {
+                for (int tap0 = 0; tap0 < seg_taps; tap0 += g.tpg) {
                     // One barrier round trip (~100+ cycles even when complete) tells us about EVERY weight stage:
                     // lane i polls the stage i slots ahead; the ballot gives the run of ready stages.
                     if (ready == 0) {
@@ -681,11 +771,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
                         for (int t = 0; t < g.tpg; ++t) {
                             const int tap = tap0 + t;
                             const uint64_t bdesc = make_smem_desc(b_base + (uint32_t)(t * b_tile));
-                            const uint32_t tap16 = a16 + tap_tab[tap];
-                            const uint32_t first = (uint32_t)(ch | tap);
+                            const uint32_t tap16 = a16 + tap_tab[seg_tap0 + tap];
+                            const uint32_t first = (uint32_t)(sg | ch | tap);
 #pragma unroll
                             for (int tl = 0; tl < 4; ++tl) {
-                                if (tl < ntiles) {
+                                if (tl < ntiles && ((tmask >> tl) & 1u)) {
                                     const uint64_t adesc = a_hi | (uint64_t)(tap16 + tile_off16[tl]);
 #pragma unroll
                                     for (int kk = 0; kk < kChunk / 8; ++kk)
@@ -699,13 +789,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
                     __syncwarp();
                     if (++sb == g.b_stages) { sb = 0; pb ^= 1; }
                 }
-                if (elect_one()) {
-                    halo_commit<PAIR>(a_empty + sa);
-                    if (ch == chunks - 1) halo_commit<PAIR>(acc_full + buf);
-                }
+                if (elect_one()) halo_commit<PAIR>(a_empty + sa);
                 __syncwarp();
                 if (++sa == g.a_stages) { sa = 0; pa ^= 1; }
             }
+            }
+            if (elect_one()) halo_commit<PAIR>(acc_full + buf);      // every MMA of the item has been issued
+            __syncwarp();
         }
         if (prof && lane == 0) {
             atomicAdd(g.prof + 0, (unsigned long long)(clock64() - t_start));
@@ -732,14 +822,23 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
             const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * acc_cols);
 
             // unit u -> (tile tl, chunk j); walked incrementally
-            struct Unit { int tl, j; int64_t m; bool valid; int col; };
+            struct Unit { int tl, j; int64_t m; bool valid; int col; int nn; };
             auto make_unit = [&](int tl, int j) {
                 Unit u;
                 u.tl = tl; u.j = j;
                 const int ox = x0 + (tl & (g.PTX - 1)) * 8 + (row & 7), oy = y0 + (tl >> g.ptx_log2) * 16 + (row >> 3);
                 u.valid = oy < g.Ho && ox < g.Wo && img < g.N;
-                u.m = ((int64_t)img * g.out_H + oy * g.out_sy + g.out_oy) * g.out_W + ox * g.out_sx + g.out_ox;
                 u.col = (half + kParts * j) * 16;
+                if constexpr (UP) {
+                    // depth-to-space: GEMM column (phase, co) of low-resolution pixel (oy, ox) is channel co of the
+                    // high-resolution pixel (2 oy + py, 2 ox + px); a 16-column unit never straddles two phases
+                    const int n = n0 + u.col, phase = n / g.up_cout;
+                    u.nn = n - phase * g.up_cout;
+                    u.m = ((int64_t)img * (2 * g.Ho) + 2 * oy + (phase >> 1)) * (2 * g.Wo) + 2 * ox + (phase & 1);
+                } else {
+                    u.nn = n0 + u.col;
+                    u.m = ((int64_t)img * g.out_H + oy * g.out_sy + g.out_oy) * g.out_W + ox * g.out_sx + g.out_ox;
+                }
                 return u;
             };
             auto next_unit = [&](const Unit &u) { return (u.j + 1 < nch) ? make_unit(u.tl, u.j + 1) : make_unit(u.tl + 1, 0); };
@@ -797,6 +896,39 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
                         }
                     }
                 }
+            } else if constexpr (EPI == RAMNET_EPI_BIAS_RELU_PRED && UP) {
+                // up-conv + fused 1x1 prediction head: the BN = 4 * Cout columns of a low-resolution pixel are its four
+                // high-resolution phases; each phase's Cout activations are reduced to one depth value in registers
+                const int nph = kParts >= 2 ? 2 : 4;        // two warps per lane quarter split the phases
+                if (half < 2) {
+                    for (int tl = 0; tl < ntiles; ++tl) {
+                        const int ox = x0 + (tl & (g.PTX - 1)) * 8 + (row & 7), oy = y0 + (tl >> g.ptx_log2) * 16 + (row >> 3);
+                        for (int ph = half * nph; ph < 4 && ph < half * nph + nph; ++ph) {
+                            float dot = 0.f;
+                            for (int c = 0; c < g.up_cout; c += 16) {
+                                uint32_t r[16];
+                                tmem_ld16_issue(lane_base + (uint32_t)(tl * g.BN + ph * g.up_cout + c), r);
+                                tmem_ld_wait(r);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float4 bb = ep.bias ? __ldg(reinterpret_cast<const float4 *>(ep.bias + c) + q)
+                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                                    const float4 ww = __ldg(reinterpret_cast<const float4 *>(ep.aux0 + c) + q);
+                                    dot = fmaf(fmaxf(__uint_as_float(r[4 * q]) + bb.x, 0.f), ww.x, dot);
+                                    dot = fmaf(fmaxf(__uint_as_float(r[4 * q + 1]) + bb.y, 0.f), ww.y, dot);
+                                    dot = fmaf(fmaxf(__uint_as_float(r[4 * q + 2]) + bb.z, 0.f), ww.z, dot);
+                                    dot = fmaf(fmaxf(__uint_as_float(r[4 * q + 3]) + bb.w, 0.f), ww.w, dot);
+                                }
+                            }
+                            if (oy < g.Ho && ox < g.Wo && img < g.N) {
+                                const int64_t m = ((int64_t)img * (2 * g.Ho) + 2 * oy + (ph >> 1)) * (2 * g.Wo) + 2 * ox + (ph & 1);
+                                const float logit = dot + __ldg(ep.aux1);
+                                if (ep.y1) ep.y1[m] = logit;
+                                ep.y0[m] = sigmoid_t<true>(logit);
+                            }
+                        }
+                    }
+                }
             } else if constexpr (EPI == RAMNET_EPI_BIAS_RELU_PRED) {
                 // fused 1x1 prediction head: every row's BN = Cout activations are reduced in registers by the
                 // first warp of each lane quarter; the 32-channel decoder output never leaves the SM
@@ -833,32 +965,32 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
             if (units > 0) {
                 Unit ua = make_unit(0, 0), ub = ua;
                 tmem_ld16_issue(lane_base + (uint32_t)(ua.tl * g.BN + ua.col), ra);
-                if (ua.valid) epilogue_prefetch<EPI, 16>(ep, ua.m, n0 + ua.col, xa);
+                if (ua.valid) epilogue_prefetch<EPI, 16>(ep, ua.m, ua.nn, xa);
                 for (int u = 0; u < units; u += 2) {
                     tmem_ld_wait(ra);
                     if (u + 1 < units) {
                         ub = next_unit(ua);
                         tmem_ld16_issue(lane_base + (uint32_t)(ub.tl * g.BN + ub.col), rb);
-                        if (ub.valid) epilogue_prefetch<EPI, 16>(ep, ub.m, n0 + ub.col, xb);
+                        if (ub.valid) epilogue_prefetch<EPI, 16>(ep, ub.m, ub.nn, xb);
                     }
                     if (ua.valid) {
                         float v[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]);
-                        epilogue_finish<EPI, 16, true>(ep, ua.m, n0 + ua.col, v, xa);
+                        epilogue_finish<EPI, 16, true>(ep, ua.m, ua.nn, v, xa);
                     }
                     if (u + 1 < units) {
                         tmem_ld_wait(rb);
                         if (u + 2 < units) {
                             ua = next_unit(ub);
                             tmem_ld16_issue(lane_base + (uint32_t)(ua.tl * g.BN + ua.col), ra);
-                            if (ua.valid) epilogue_prefetch<EPI, 16>(ep, ua.m, n0 + ua.col, xa);
+                            if (ua.valid) epilogue_prefetch<EPI, 16>(ep, ua.m, ua.nn, xa);
                         }
                         if (ub.valid) {
                             float v[16];
 #pragma unroll
                             for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rb[i]);
-                            epilogue_finish<EPI, 16, true>(ep, ub.m, n0 + ub.col, v, xb);
+                            epilogue_finish<EPI, 16, true>(ep, ub.m, ub.nn, v, xb);
                         }
                     }
                 }
@@ -1344,12 +1476,17 @@ int launch(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap &m1, const
     return RAMNET_OK;
 }
 
-template <int EPI, bool PAIR, bool HP = false>
+const UpMaps &no_up_maps() {
+    static UpMaps z = {};
+    return z;
+}
+
+template <int EPI, bool PAIR, bool HP = false, bool UP = false>
 int launch_halo_pair(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap &m1, const CUtensorMap &mw,
-                     const HaloGeom &g, const EpiParams &ep, size_t smem, cudaStream_t s) {
+                     const HaloGeom &g, const EpiParams &ep, size_t smem, cudaStream_t s, const UpMaps &um = no_up_maps()) {
     static size_t configured = 0;
     if (smem > configured) {
-        RAMNET_CUDA(cudaFuncSetAttribute(conv_tcgen05_halo_kernel<EPI, true, HP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        RAMNET_CUDA(cudaFuncSetAttribute(conv_tcgen05_halo_kernel<EPI, true, HP, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
         configured = smem;
     }
@@ -1375,7 +1512,7 @@ int launch_halo_pair(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap 
         cudaMemsetAsync(buf, 0, 64, s);
         HaloGeom gp = g;
         gp.prof = buf;
-        RAMNET_CUDA(cudaLaunchKernelEx(&cfg, conv_tcgen05_halo_kernel<EPI, true, HP>, m0, m1, mw, gp, ep));
+        RAMNET_CUDA(cudaLaunchKernelEx(&cfg, conv_tcgen05_halo_kernel<EPI, true, HP, UP>, m0, m1, mw, um, gp, ep));
         unsigned long long hbuf[8];
         cudaMemcpyAsync(hbuf, buf, 64, cudaMemcpyDeviceToHost, s);
         cudaStreamSynchronize(s);
@@ -1386,22 +1523,22 @@ int launch_halo_pair(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap 
                 pairs, g.items, hbuf[0] / n / 1e3, hbuf[1] / n / 1e3, hbuf[2] / n / 1e3, hbuf[3] / n / 1e3, hbuf[4] / n / 2e3,
                 hbuf[5] / n / 2e3, hbuf[6] / n / 16e3, hbuf[7] / n / 16e3);
     } else {
-        RAMNET_CUDA(cudaLaunchKernelEx(&cfg, conv_tcgen05_halo_kernel<EPI, true, HP>, m0, m1, mw, g, ep));
+        RAMNET_CUDA(cudaLaunchKernelEx(&cfg, conv_tcgen05_halo_kernel<EPI, true, HP, UP>, m0, m1, mw, um, g, ep));
     }
     RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;
 }
 
-template <int EPI, bool HP = false>
+template <int EPI, bool HP = false, bool UP = false>
 int launch_halo(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap &m1, const CUtensorMap &mw,
-                const HaloGeom &g, const EpiParams &ep, cudaStream_t s) {
+                const HaloGeom &g, const EpiParams &ep, cudaStream_t s, const UpMaps &um = no_up_maps()) {
     const size_t a_stride = (size_t)g.nplanes * g.plane_stride;
     const size_t smem = g.a_stages * a_stride + (size_t)g.b_stages * g.tpg * (g.pair ? g.BN / 2 : g.BN) * kChunk * 4 +
-                        (2 * g.a_stages + 2 * g.b_stages + 4) * 8 + 16 + 32 * 4 + 1024;
-    if (g.pair) return launch_halo_pair<EPI, true, HP>(h, m0, m1, mw, g, ep, smem, s);
+                        (2 * g.a_stages + 2 * g.b_stages + 4) * 8 + 16 + 96 * 4 + 1024;
+    if (g.pair) return launch_halo_pair<EPI, true, HP, UP>(h, m0, m1, mw, g, ep, smem, s, um);
     static size_t configured = 0;
     if (smem > configured) {
-        RAMNET_CUDA(cudaFuncSetAttribute(conv_tcgen05_halo_kernel<EPI, false, HP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        RAMNET_CUDA(cudaFuncSetAttribute(conv_tcgen05_halo_kernel<EPI, false, HP, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
         configured = smem;
     }
@@ -1413,7 +1550,7 @@ int launch_halo(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap &m1, 
         cudaMemsetAsync(buf, 0, 64, s);
         HaloGeom gp = g;
         gp.prof = buf;
-        conv_tcgen05_halo_kernel<EPI, false, HP><<<grid, kHaloThreads, smem, s>>>(m0, m1, mw, gp, ep);
+        conv_tcgen05_halo_kernel<EPI, false, HP, UP><<<grid, kHaloThreads, smem, s>>>(m0, m1, mw, um, gp, ep);
         unsigned long long hbuf[8];
         cudaMemcpyAsync(hbuf, buf, 64, cudaMemcpyDeviceToHost, s);
         cudaStreamSynchronize(s);
@@ -1424,7 +1561,7 @@ int launch_halo(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap &m1, 
                 grid, g.items, hbuf[0] / n / 1e3, hbuf[1] / n / 1e3, hbuf[2] / n / 1e3, hbuf[3] / n / 1e3, hbuf[4] / n / 1e3,
                 hbuf[5] / n / 1e3, hbuf[6] / n / 8e3, hbuf[7] / n / 8e3);
     } else {
-        RAMNET_CUDA(ramnet_launch(conv_tcgen05_halo_kernel<EPI, false, HP>, dim3(grid), dim3(kHaloThreads), smem, s, true, m0, m1, mw, g, ep));
+        RAMNET_CUDA(ramnet_launch(conv_tcgen05_halo_kernel<EPI, false, HP, UP>, dim3(grid), dim3(kHaloThreads), smem, s, true, m0, m1, mw, um, g, ep));
     }
     RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;
@@ -1440,7 +1577,7 @@ int halo_mode_env() {
 }
 
 bool fill_halo(const ramnet_conv_desc *d, const RectSpec *rect, HaloGeom *g, int ptx, int pty, int bn, int a_st, int b_st,
-               int pair = 0) {
+               int pair = 0, int max_tpg = 0) {
     if (d->Cout % bn || ptx * pty > 4 || ptx * pty * bn > 512 || (ptx & (ptx - 1))) return false;
     if (pair && (bn % 16 || bn < 32)) return false;          // cta_group::2: N in steps of 16; each CTA stages bn/2 rows
     g->pair = pair;
@@ -1455,6 +1592,7 @@ bool fill_halo(const ramnet_conv_desc *d, const RectSpec *rect, HaloGeom *g, int
     g->PTX = ptx; g->PTY = pty; g->ptx_log2 = ptx == 4 ? 2 : (ptx == 2 ? 1 : 0);
     g->HX = ptx * 8 + (hi - g->lo); g->HY = pty * 16 + (hi - g->lo);
     g->hpack = 0; g->cs = 0; g->kwp = 0;
+    g->up = 0; g->up_cout = 0; g->nseg = 1; g->total_taps = d->ksize * d->ksize;
     g->kh = g->kw = d->ksize; g->lo_y = g->lo_x = g->lo;
     g->out_sy = g->out_sx = 1; g->out_oy = g->out_ox = 0; g->out_H = g->Ho; g->out_W = g->Wo;
     if (rect) {               // stride-1 launch with a rectangular tap set and / or a strided output view
@@ -1491,6 +1629,7 @@ bool fill_halo(const ramnet_conv_desc *d, const RectSpec *rect, HaloGeom *g, int
     for (int c : cand) {
         if (c < 1 || taps % c) continue;
         if (tpg_env > 0 && c > tpg_env) continue;
+        if (max_tpg > 0 && c > max_tpg) continue;
         if ((size_t)c * b_tile <= 40 * 1024 && a_st * a_stride + 3 * (size_t)c * b_tile <= budget) { tpg = c; break; }
     }
     g->tpg = tpg;
@@ -1520,6 +1659,7 @@ bool fill_hpack(const ramnet_conv_desc *d, HaloGeom *g, int pty, int cs, int pai
     g->Ho = d->H; g->Wo = d->W;
     g->ks = ks; g->pad = ks / 2; g->stride = 1; g->prof = nullptr; g->nplanes = 1; g->lo = -g->pad;
     g->hpack = 1; g->cs = cs; g->kwp = ks;
+    g->up = 0; g->up_cout = 0; g->nseg = 1; g->total_taps = ks;
     g->kh = ks; g->kw = 1;                      // "taps" of the weight pipeline = filter rows
     g->lo_y = -g->pad; g->lo_x = 0;
     g->out_sy = g->out_sx = 1; g->out_oy = g->out_ox = 0; g->out_H = g->Ho; g->out_W = g->Wo;
@@ -2132,6 +2272,168 @@ int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz
 
 size_t conv_tf32_workspace_bytes(const ramnet_conv_desc *) { return 0; }
 
+
+// ================================================================================================
+// Up-conv (RAMNET_FLAG_UPCONV): UpsampleConvLayer.forward (submodules.py:87-97) = bilinear x2 + 5x5 conv in one launch on
+// the low-resolution input.  out[2m+py, 2q+px] = sum_{t,u} W[t,u] Upad[2m+py+t, 2q+px+u]; every row of the upsampled
+// image U is a fixed 2-tap combination of input rows (.25/.75), so per output phase (py, px) the 5x5 filter collapses
+// onto a 5x5 window of the LOW-resolution input (one row and one column of it are zero): one GEMM with
+// N = 4 * Cout columns [py][px][co] over the small tensor.  What the 4x tensor cost (written by upsample2x_add, read back
+// 25 times by the conv) disappears, and the narrow decoders (Cout = 32 / 64) run N = 128 / 256 wide MMAs.
+// Border: U's clamp replicates the edge and the conv's zero padding applies to U, not to the input.  The uniform
+// collapse over the zero-padded input is therefore wrong in output rows 0..2 / 2H-3..2H-1 (same for columns), by terms
+// that only involve input row 0 / H-1 (column 0 / W-1):
+//     corr[0] = .25 (W[0] - W[-1]) x0,   corr[1] = .25 (W[-1] - W[-2]) x0,   corr[2] = .25 W[-2] x0      (1-D, top)
+// and mirrored at the bottom; in 2-D  exact = (M + D)y (x) (M + D)x  gives four edge and four corner terms.  Each is
+// one more K segment of the same launch: its A operand is the SAME box read through a tensor map whose bounds are just
+// that row / column / pixel (everything else is zero fill) and its taps carry the collapsed D coefficients.  Only
+// border patches run them, and only their border tiles issue MMAs.  The algebra is checked against
+// F.conv2d(F.interpolate(x)) in fp64 by tests/test_upconv_algebra.py (exact to 1e-14, down to 2x2 inputs).
+// ================================================================================================
+// taps per segment: main 25, edges 10, corners 4 + 1 zero tap (so that every segment is a multiple of tpg in {1, 5})
+__host__ __device__ inline int up_seg_taps(int sg) { return sg == 0 ? 25 : (sg <= 4 ? 10 : 5); }
+constexpr int kUpTotalTaps = 85;
+
+// coefficient of input row m + r in upsampled row 2m + p + t (uniform bilinear x2 formula)
+__host__ __device__ inline float up_cu(int p, int t, int r) {
+    const int sft = p + t;
+    if ((sft & 1) == 0) {
+        const int e = sft >> 1;
+        if (r == e - 1) return 0.25f;
+        if (r == e) return 0.75f;
+    } else {
+        const int e = (sft - 1) >> 1;
+        if (r == e) return 0.75f;
+        if (r == e + 1) return 0.25f;
+    }
+    return 0.f;
+}
+// top / left border correction: coefficient of the FIRST input row for output phase p of low-res row r rows below it
+__host__ __device__ inline float up_dT(int p, int t, int r) {
+    if (r == 0) {
+        if (p == 0) return t == 0 ? 0.25f : (t == -1 ? -0.25f : 0.f);
+        return t == -1 ? 0.25f : (t == -2 ? -0.25f : 0.f);
+    }
+    if (r == -1 && p == 0 && t == -2) return 0.25f;
+    return 0.f;
+}
+__host__ __device__ inline float up_dB(int p, int t, int r) { return up_dT(1 - p, -t, -r); }   // mirror image
+
+// segment sg: tap window and which 1-D operators apply along y / x (0 uniform, 1 first-row, 2 last-row correction)
+__host__ __device__ inline void up_seg_shape(int sg, int &kh, int &kw, int &lo_y, int &lo_x, int &fy, int &fx) {
+    const int ymode = (sg == 1 || sg == 5 || sg == 6) ? 1 : ((sg == 2 || sg == 7 || sg == 8) ? 2 : 0);
+    const int xmode = (sg == 3 || sg == 5 || sg == 7) ? 1 : ((sg == 4 || sg == 6 || sg == 8) ? 2 : 0);
+    fy = ymode; fx = xmode;
+    kh = ymode ? 2 : 5; lo_y = ymode == 0 ? -2 : (ymode == 1 ? -1 : 0);
+    kw = xmode ? 2 : 5; lo_x = xmode == 0 ? -2 : (xmode == 1 ? -1 : 0);
+}
+
+__global__ void pack_upconv_kernel(const float *__restrict__ w, float *__restrict__ out, int Cout, int Cin) {
+    const int64_t total = (int64_t)kUpTotalTaps * 4 * Cout * Cin;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % Cin);
+        int64_t q = i / Cin;
+        const int row = (int)(q % (4 * Cout));
+        int tap = (int)(q / (4 * Cout));
+        int sg = 0;
+        while (tap >= up_seg_taps(sg)) { tap -= up_seg_taps(sg); ++sg; }
+        int kh, kw, lo_y, lo_x, fy, fx;
+        up_seg_shape(sg, kh, kw, lo_y, lo_x, fy, fx);
+        float acc = 0.f;
+        if (tap < kh * kw) {
+            const int r = lo_y + tap / kw, sx = lo_x + tap % kw;
+            const int phase = row / Cout, co = row % Cout, py = phase >> 1, px = phase & 1;
+            const float *wc = w + ((int64_t)co * Cin + ci) * 25;
+            for (int t = -2; t <= 2; ++t) {
+                const float a = fy == 0 ? up_cu(py, t, r) : (fy == 1 ? up_dT(py, t, r) : up_dB(py, t, r));
+                if (a == 0.f) continue;
+                for (int u = -2; u <= 2; ++u) {
+                    const float b = fx == 0 ? up_cu(px, u, sx) : (fx == 1 ? up_dT(px, u, sx) : up_dB(px, u, sx));
+                    if (b != 0.f) acc = fmaf(a * b, wc[(t + 2) * 5 + (u + 2)], acc);     // a * b is exact (powers of two x 3, 9)
+                }
+            }
+        }
+        out[i] = round_tf32(acc);
+    }
+}
+
+int conv_up_fwd_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *x0, const float *wp, EpiParams ep,
+                     cudaStream_t s) {
+    RAMNET_CHECK_ARG(d->ksize == 5 && d->stride == 1 && d->C1 == 0, "conv_fwd(upconv): 5x5 stride-1 single-source layers only");
+    RAMNET_CHECK_ARG(d->C0 % kChunk == 0 && d->Cout % 16 == 0 && 4 * d->Cout <= 512, "conv_fwd(upconv): C0 %% 32, Cout %% 16, Cout <= 128");
+    RAMNET_CHECK_ARG(d->H >= 2 && d->W >= 2, "conv_fwd(upconv): input must be at least 2 x 2");
+    RAMNET_CHECK_ARG(d->epilogue == RAMNET_EPI_BIAS_RELU || d->epilogue == RAMNET_EPI_BIAS_RELU_ADD ||
+                         d->epilogue == RAMNET_EPI_BIAS_RELU_PRED || d->epilogue == RAMNET_EPI_BIAS,
+                     "conv_fwd(upconv): bias / relu / relu+add / fused-pred epilogues only");
+    ramnet_conv_desc du = *d;
+    du.Cout = 4 * d->Cout;            // GEMM columns
+    HaloGeom hg;
+    static const int pair_mode = [] { const char *e = getenv("RAMNET_PAIR"); return e ? atoi(e) : 1; }();
+    static const int shapes[][2] = {{2, 1}, {1, 1}, {4, 1}, {2, 2}, {1, 2}};
+    double best = -1;
+    HaloGeom cand;
+    if (const char *f = getenv("RAMNET_UP_FORCE")) {      // tuning aid: "PTX,PTY,BN,pair"
+        int ptx, pty, bn, pr = 0;
+        if (sscanf(f, "%d,%d,%d,%d", &ptx, &pty, &bn, &pr) >= 3 && fill_halo(&du, nullptr, &cand, ptx, pty, bn, 0, 0, pr, 5)) {
+            best = 0; hg = cand;
+        }
+    }
+    for (int pass = 0; pass < 2 && best < 0; ++pass)      // second pass: single-CTA configurations when pairs are forced but none fits
+        for (int pair = (pair_mode == 2 && pass == 0 ? 1 : 0); pair <= (pair_mode >= 1 ? 1 : 0); ++pair)
+            for (const auto &sh : shapes)
+                for (int bn = 128; bn >= 64; bn >>= 1) {      // <= 128 columns per item: a stage then holds a whole filter row
+                                                              // (tpg = 5); measured dec1: BN 256 / tpg 1 118 us, BN 128 / tpg 5 107 us
+                    if (bn % d->Cout && d->Cout % bn) continue;                       // 16-column units never straddle a phase anyway
+                    if (d->epilogue == RAMNET_EPI_BIAS_RELU_PRED && bn != du.Cout) continue;   // all four phases in one item
+                    if (sh[0] * sh[1] > 2) continue;          // measured: 4-tile patches lose TMEM double buffering (dec2 116 vs 92 us)
+                    if (!fill_halo(&du, nullptr, &cand, sh[0], sh[1], bn, 0, 0, pair, 5)) continue;
+                    const double c = halo_cost(h, &du, cand);
+                    if (best < 0 || c < best) { best = c; hg = cand; }
+                }
+    if (best < 0) return ramnet_set_error(RAMNET_EUNSUPPORTED, "conv_fwd(upconv): no halo configuration fits");
+    hg.up = 1; hg.up_cout = d->Cout; hg.nseg = kMaxUpSeg; hg.total_taps = kUpTotalTaps;
+    int tap0 = 0;
+    for (int sg = 0; sg < kMaxUpSeg; ++sg) {
+        UpSeg &u = hg.seg[sg];
+        int fy, fx;
+        up_seg_shape(sg, u.kh, u.kw, u.lo_y, u.lo_x, fy, fx);
+        u.tap0 = tap0; u.ntaps = up_seg_taps(sg); tap0 += up_seg_taps(sg);
+        u.vy = fy == 2 ? d->H - 1 : 0; u.vx = fx == 2 ? d->W - 1 : 0;
+        u.cond = (fy == 1 ? 1 : (fy == 2 ? 2 : 0)) | (fx == 1 ? 4 : (fx == 2 ? 8 : 0));
+    }
+    if (getenv("RAMNET_DEBUG"))
+        fprintf(stderr, "[ramnet] upconv plan %dx%d C=%d->%d (N=%d): tiles %dx%d HX=%d HY=%d BN=%d a_st=%d b_st=%d tpg=%d nbuf=%d items=%d pair=%d\n",
+                d->H, d->W, d->C0, d->Cout, du.Cout, hg.PTX, hg.PTY, hg.HX, hg.HY, hg.BN, hg.a_stages, hg.b_stages, hg.tpg,
+                hg.nbuf, hg.items, hg.pair);
+    CUtensorMap m0, mw;
+    UpMaps um;
+    const int C = d->C0;
+    const cuuint64_t str[3] = {(cuuint64_t)C * 4, (cuuint64_t)d->W * C * 4, (cuuint64_t)d->H * d->W * C * 4};
+    const cuuint32_t box[4] = {kChunk, (cuuint32_t)hg.HX, (cuuint32_t)hg.HY, 1};
+    for (int sg = 0; sg < kMaxUpSeg; ++sg) {
+        const UpSeg &u = hg.seg[sg];
+        // the view: rows [vy, vy + vh), columns [vx, vx + vw) of every image; same strides, shifted base
+        const int vh = (u.cond & 3) ? 1 : d->H, vw = (u.cond & 12) ? 1 : d->W;
+        const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)vw, (cuuint64_t)vh, (cuuint64_t)d->N};
+        const float *base = x0 + ((int64_t)u.vy * d->W + u.vx) * C;
+        const int rc = encode(h, sg == 0 ? &m0 : &um.m[sg - 1], base, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    const cuuint64_t wd[3] = {(cuuint64_t)C, (cuuint64_t)du.Cout, (cuuint64_t)kUpTotalTaps};
+    const cuuint64_t wst[2] = {(cuuint64_t)C * 4, (cuuint64_t)C * du.Cout * 4};
+    const cuuint32_t wb[3] = {kChunk, (cuuint32_t)(hg.pair ? hg.BN / 2 : hg.BN), (cuuint32_t)hg.tpg};
+    int rc = encode(h, &mw, wp, 3, wd, wst, wb);
+    if (rc) return rc;
+    ep.Cout = d->Cout;                // pixel pitch of the high-resolution output / aux operands
+    switch (d->epilogue) {
+        case RAMNET_EPI_BIAS: return launch_halo<RAMNET_EPI_BIAS, false, true>(h, m0, m0, mw, hg, ep, s, um);
+        case RAMNET_EPI_BIAS_RELU: return launch_halo<RAMNET_EPI_BIAS_RELU, false, true>(h, m0, m0, mw, hg, ep, s, um);
+        case RAMNET_EPI_BIAS_RELU_ADD: return launch_halo<RAMNET_EPI_BIAS_RELU_ADD, false, true>(h, m0, m0, mw, hg, ep, s, um);
+        case RAMNET_EPI_BIAS_RELU_PRED: return launch_halo<RAMNET_EPI_BIAS_RELU_PRED, false, true>(h, m0, m0, mw, hg, ep, s, um);
+    }
+    return ramnet_set_error(RAMNET_EINVAL, "conv_fwd(upconv): unreachable");
+}
+
 int conv_fwd_tf32_rect(ramnet_handle *h, const ramnet_conv_desc *d, const RectSpec *rect, const float *x0, const float *x1,
                        const float *wp, const EpiParams &ep, cudaStream_t s);
 
@@ -2150,6 +2452,10 @@ int conv_fwd_tf32_rect(ramnet_handle *h, const ramnet_conv_desc *d, const RectSp
     RAMNET_CHECK_ARG((((uintptr_t)ep.y0 | (uintptr_t)ep.y1 | (uintptr_t)ep.y2 | (uintptr_t)ep.aux0 | (uintptr_t)ep.aux1) & 31) == 0 ||
                          d->epilogue == RAMNET_EPI_BIAS_RELU_PRED,
                      "conv_fwd(tf32): outputs and epilogue operands must be 32-byte aligned (256-bit stores)");
+    if (d->flags & RAMNET_FLAG_UPCONV) {
+        RAMNET_CHECK_ARG(!rect && !x1, "conv_fwd(upconv): single source, no rectangular tap set");
+        return conv_up_fwd_tf32(h, d, x0, wp, ep, s);
+    }
     HaloGeom hg;
     const bool want_hpack = (d->flags & RAMNET_FLAG_HPACK) != 0;
     if (want_hpack) {
@@ -2216,6 +2522,7 @@ int conv_fwd_tf32_rect(ramnet_handle *h, const ramnet_conv_desc *d, const RectSp
             case RAMNET_EPI_GRU_OUT: return launch_halo<RAMNET_EPI_GRU_OUT>(h, m0, m1, mw, hg, ep, s);
             case RAMNET_EPI_LSTM: return launch_halo<RAMNET_EPI_LSTM>(h, m0, m1, mw, hg, ep, s);
             case RAMNET_EPI_BIAS_RELU_PRED: return launch_halo<RAMNET_EPI_BIAS_RELU_PRED>(h, m0, m1, mw, hg, ep, s);
+            case RAMNET_EPI_BIAS_RELU_ADD: return launch_halo<RAMNET_EPI_BIAS_RELU_ADD>(h, m0, m1, mw, hg, ep, s);
         }
     }
     TcGeom g;
@@ -2526,6 +2833,20 @@ __global__ void pack_hpack_kernel(const float *__restrict__ w, float *__restrict
     }
 }
 }  // namespace
+
+extern "C" int64_t ramnet_upconv_packed_floats(int Cout, int Cin) { return (int64_t)kUpTotalTaps * 4 * Cout * Cin; }
+
+extern "C" int ramnet_pack_weights_upconv(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin,
+                                          void *stream) {
+    RAMNET_DEVICE_GUARD(h);
+    RAMNET_CHECK_ARG(h && w_oihw && w_packed && Cout > 0 && Cout % 16 == 0 && Cin > 0 && Cin % 32 == 0,
+                     "pack_weights_upconv: bad argument");
+    const int64_t total = ramnet_upconv_packed_floats(Cout, Cin);
+    pack_upconv_kernel<<<(unsigned)imin64((total + 255) / 256, (int64_t)h->sm_count * 8), 256, 0, (cudaStream_t)stream>>>(
+        w_oihw, w_packed, Cout, Cin);
+    RAMNET_LAUNCH_CHECK(h);
+    return RAMNET_OK;
+}
 
 extern "C" int ramnet_pack_weights_hpack(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin,
                                          int ksize, void *stream) {

@@ -115,6 +115,19 @@ def pack_conv(cache: WeightCache, key, conv, kind: int, norm_mod=None, norm_kind
     return cache.get(key, [conv.weight, conv.bias] + _norm_sources(norm_mod), (kind, training, hp_key), build)
 
 
+def pack_upconv(cache: WeightCache, key, conv, norm_mod=None, norm_kind=None, training=False) -> Packed:
+    """Decoder nn.Conv2d (+ folded eval norm) -> collapsed up-conv taps for ops.conv_up_fwd (RAMNET_FLAG_UPCONV)."""
+    def build():
+        w, b = conv.weight.detach().float(), None if conv.bias is None else conv.bias.detach().float()
+        w, b = _fold_norm(w, b, norm_mod, norm_kind, training)
+        p = Packed()
+        p.w = ops.pack_weights_upconv(w)
+        p.b = None if b is None else b.contiguous()
+        p.Cout, p.ksize, p.stride = w.shape[0], w.shape[2], 1
+        return p
+    return cache.get(key + '/up', [conv.weight, conv.bias] + _norm_sources(norm_mod), ('upconv', training), build)
+
+
 def pack_head(cache: WeightCache, key, conv, tc: bool = False) -> Packed:
     """Head conv keeps nn.Conv2d's [Cout,Cin,5,5] layout (ramnet_head_conv reads it directly)."""
     def build():

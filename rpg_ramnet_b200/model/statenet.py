@@ -237,28 +237,66 @@ class StateNetPhasedRecurrent(BaseStateNet):
                              norm_mod=getattr(rb, 'bn2', None), norm_kind=rb.norm, training=self.training, round_out=True)
         pr = self.pred
         tf32 = kind == ops.MMA_TF32
+        nd = len(self.decoders)
+
+        def skip_of(i):
+            return None if i == 0 or i >= nd else ops.as_nhwc(pick(super_states[n - i - 1]))
+
+        def grad_free(dec):
+            return not E.needs_grad(x, dec.conv2d.weight, dec.conv2d.bias, pr.conv2d.weight, pr.conv2d.bias)
+
+        # Up-conv decoders (inference, TF32): bilinear x2 + 5x5 conv in ONE launch on the low-resolution tensor
+        # (ops.conv_up_fwd); the skip sum a decoder needs is formed by the epilogue of the layer before it
+        # (EPI_BIAS_RELU_ADD), so neither the 4x tensor nor the sum is ever written on its own.
+        up_mode = [self.use_upsample_conv and tf32 and grad_free(dec) and
+                   ops.upconv_eligible(dec.conv2d.in_channels, dec.conv2d.out_channels, dec.conv2d.kernel_size[0], kind)
+                   for dec in self.decoders]
+        skip_added = False          # x already holds x + skip of the decoder about to run
         for i, dec in enumerate(self.decoders):
-            skip = None if i == 0 else ops.as_nhwc(pick(super_states[n - i - 1]))
+            skip = None if skip_added else skip_of(i)
+            skip_added = False
             if not self.use_upsample_conv:        # TransposedConvLayer decoder (statenet.py:81-82)
                 x = E.transposed_conv_layer(cache, f'dec{i}', dec.transposed_conv2d, kind, x, skip,
                                             getattr(dec, 'norm_layer', None), dec.norm, self.training)
                 continue
-            up = E.upsample_add(x, skip, tf32)
-            last = i == len(self.decoders) - 1
-            fuse = last and tf32 and dec.conv2d.out_channels % 32 == 0 and dec.conv2d.out_channels <= 256 and \
-                not E.needs_grad(up, dec.conv2d.weight, dec.conv2d.bias, pr.conv2d.weight, pr.conv2d.bias)
+            last = i == nd - 1
+            next_up = (not last) and up_mode[i + 1]
+            nm, nk = getattr(dec, 'norm_layer', None), dec.norm
+            fuse = last and tf32 and dec.conv2d.out_channels % 32 == 0 and dec.conv2d.out_channels <= 256 and grad_free(dec)
             if fuse:
-                # last decoder + pred + sigmoid in one kernel: the 32-channel full-resolution tensor is never written
-                p = E.pack_conv(cache, f'dec{i}', dec.conv2d, kind, getattr(dec, 'norm_layer', None), dec.norm,
-                                self.training, hpack_ok=True)
                 pw, pb = pr.conv2d.weight.detach().float(), None if pr.conv2d.bias is None else pr.conv2d.bias.detach().float()
                 pw, pb = E._fold_norm(pw, pb, getattr(pr, 'norm_layer', None), pr.norm, self.training)
+                pbias = pb if pb is not None else torch.zeros(1, dtype=torch.float32, device=x.device)
+                pw, pbias = pw.reshape(-1).contiguous(), pbias.reshape(-1).contiguous()
+            if up_mode[i]:
+                if skip is not None:              # unreachable: the layer before an up-conv decoder always forms its skip sum
+                    raise RamnetError('internal: up-conv decoder reached without its skip sum')
+                p = E.pack_upconv(cache, f'dec{i}', dec.conv2d, nm, nk, self.training)
+                if fuse:
+                    N, _, Hh, Ww = x.shape
+                    logits = torch.empty((N, 1, 2 * Hh, 2 * Ww), dtype=torch.float32, device=x.device) if return_logits else None
+                    depth = ops.conv_up_fwd(x, p.w, p.b, p.Cout, ops.EPI_BIAS_RELU_PRED, aux0=pw, aux1=pbias, out1=logits)
+                    return (depth, logits) if return_logits else depth
+                if next_up:
+                    x = ops.conv_up_fwd(x, p.w, p.b, p.Cout, ops.EPI_BIAS_RELU_ADD, aux0=skip_of(i + 1), round_tf32=True)
+                    skip_added = True
+                else:
+                    x = ops.conv_up_fwd(x, p.w, p.b, p.Cout, ops.EPI_BIAS_RELU)
+                continue
+            up = E.upsample_add(x, skip, tf32)
+            if fuse:
+                # last decoder + pred + sigmoid in one kernel: the 32-channel full-resolution tensor is never written
+                p = E.pack_conv(cache, f'dec{i}', dec.conv2d, kind, nm, nk, self.training, hpack_ok=True)
                 N, _, Hh, Ww = up.shape
-                pbias = pb if pb is not None else torch.zeros(1, dtype=torch.float32, device=up.device)
                 logits = torch.empty((N, 1, Hh, Ww), dtype=torch.float32, device=up.device) if return_logits else None
                 depth = ops.conv_fwd(up, None, p.w, p.b, p.Cout, p.ksize, p.stride, ops.EPI_BIAS_RELU_PRED, kind,
-                                     aux0=pw.reshape(-1).contiguous(), aux1=pbias.reshape(-1).contiguous(), out1=logits)
+                                     aux0=pw, aux1=pbias, out1=logits)
                 return (depth, logits) if return_logits else depth
-            x = E.conv_layer(cache, f'dec{i}', dec.conv2d, kind, up, ops.EPI_BIAS_RELU,
-                             norm_mod=getattr(dec, 'norm_layer', None), norm_kind=dec.norm, training=self.training)
+            if next_up:
+                x = E.conv_layer(cache, f'dec{i}', dec.conv2d, kind, up, ops.EPI_BIAS_RELU_ADD, res=skip_of(i + 1),
+                                 norm_mod=nm, norm_kind=nk, training=self.training, round_out=True)
+                skip_added = True
+            else:
+                x = E.conv_layer(cache, f'dec{i}', dec.conv2d, kind, up, ops.EPI_BIAS_RELU,
+                                 norm_mod=nm, norm_kind=nk, training=self.training)
         return E.pred_layer(x, pr.conv2d, getattr(pr, 'norm_layer', None), pr.norm, self.training, return_logits)

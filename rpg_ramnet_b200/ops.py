@@ -11,9 +11,8 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (ConvDesc, EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RELU_PRED, EPI_BIAS_RES_RELU, EPI_GRU_OUT, EPI_GRU_RU,  # noqa
-                   EPI_LSTM,
-                   FLAG_HPACK, FLAG_ROUND_TF32, MMA_FP32, MMA_TF32, check)
+from ._lib import (ConvDesc, EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RELU_ADD, EPI_BIAS_RELU_PRED, EPI_BIAS_RES_RELU, EPI_GRU_OUT,  # noqa
+                   EPI_GRU_RU, EPI_LSTM, FLAG_HPACK, FLAG_ROUND_TF32, FLAG_UPCONV, MMA_FP32, MMA_TF32, check)
 
 
 def _stream(t: torch.Tensor):
@@ -193,6 +192,53 @@ def pack_weights_hpack(w_oihw: torch.Tensor) -> torch.Tensor:
     check(_lib.load().ramnet_pack_weights_hpack(_h(w), _p(w), _p(out), Cout, Cin, k, _stream(w)))
     out._ramnet_hpack = True          # conv_fwd sets RAMNET_FLAG_HPACK for weights packed this way
     return out
+
+
+def upconv_eligible(Cin: int, Cout: int, ksize: int, mma_kind: int) -> bool:
+    """Layers ramnet_conv_fwd can run in up-conv mode (bilinear x2 + 5x5 conv in one launch on the low-resolution input,
+    RAMNET_FLAG_UPCONV): TF32, 5x5, Cin % 32 == 0, 4 * Cout GEMM columns <= 512.  RAMNET_UPCONV=0 disables;
+    RAMNET_UPCONV_MAXC bounds Cout (default 64: the two narrow decoders, where N = 4 * Cout turns 32 / 64-column MMAs
+    into 128 / 256-column ones; the 128-channel decoder gains nothing from wider MMAs and pays the border segments)."""
+    if os.environ.get('RAMNET_UPCONV', '1') == '0' or mma_kind != MMA_TF32 or ksize != 5:
+        return False
+    return Cin % 32 == 0 and Cout % 16 == 0 and Cout <= int(os.environ.get('RAMNET_UPCONV_MAXC', '64'))
+
+
+def pack_weights_upconv(w_oihw: torch.Tensor) -> torch.Tensor:
+    w = w_oihw.detach().contiguous().float()
+    Cout, Cin, k, _ = w.shape
+    if k != 5:
+        raise _lib.RamnetError('pack_weights_upconv: 5x5 filters only')
+    lib = _lib.load()
+    out = torch.empty(int(lib.ramnet_upconv_packed_floats(Cout, Cin)), dtype=torch.float32, device=w.device)
+    check(lib.ramnet_pack_weights_upconv(_h(w), _p(w), _p(out), Cout, Cin, _stream(w)))
+    out._ramnet_upconv = True
+    return out
+
+
+def conv_up_fwd(x: torch.Tensor, w_packed_up: torch.Tensor, bias: Optional[torch.Tensor], Cout: int, epilogue: int,
+                aux0=None, aux1=None, round_tf32: bool = False, out1=None):
+    """UpsampleConvLayer.forward (submodules.py:87-97) without the 4x tensor: y = epi(conv5x5(bilinear_up2x(x)) + b) from
+    the LOW-resolution x [N, Cin, H, W] -> [N, Cout, 2H, 2W] (EPI_BIAS_RELU_PRED: depth [N, 1, 2H, 2W]).
+    EPI_BIAS_RELU_ADD adds aux0 ([N, Cout, 2H, 2W], the next decoder's skip state) after the ReLU."""
+    _check_nhwc(x, 'conv_up_fwd x')
+    N, Cin, H, W = x.shape
+    dev = x.device
+    if epilogue == EPI_BIAS_RELU_PRED:
+        y0 = torch.empty((N, 1, 2 * H, 2 * W), dtype=torch.float32, device=dev)
+    else:
+        y0 = empty_nhwc(N, Cout, 2 * H, 2 * W, dev)
+        if aux0 is not None:
+            _check_nhwc(aux0, 'conv_up_fwd aux0')
+            if tuple(aux0.shape) != (N, Cout, 2 * H, 2 * W):
+                raise _lib.RamnetError(f'conv_up_fwd: aux0 shape {tuple(aux0.shape)} != {(N, Cout, 2 * H, 2 * W)}')
+    flags = FLAG_UPCONV | (FLAG_ROUND_TF32 if round_tf32 else 0)
+    d = ConvDesc(N, H, W, Cin, 0, Cout, 5, 1, epilogue, MMA_TF32, flags, 0)
+    with _Prof('conv', 2.0 * N * (2 * H) * (2 * W) * Cout * Cin * 25, dev,      # algorithmic FLOPs of the reference graph
+               tag=PROFILE is not None and f'upconv {H}x{W} {Cin}->{Cout} e{epilogue}'):
+        check(_lib.load().ramnet_conv_fwd(_h(x), ctypes.byref(d), _p(x), None, _p(w_packed_up), _p(bias), _p(aux0), _p(aux1),
+                                          _p(y0), _p(out1), None, None, 0, _stream(x)))
+    return y0
 
 
 def pack_weights(w_oihw: torch.Tensor, mma_kind: int, lstm_interleave: bool = False) -> torch.Tensor:

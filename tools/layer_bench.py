@@ -34,6 +34,13 @@ LAYERS = [
     ('dec1 5x5 128->64', 128, 256, 128, 0, 64, 5, 1, ops.EPI_BIAS_RELU),
     ('dec2 5x5 64->32', 256, 512, 64, 0, 32, 5, 1, ops.EPI_BIAS_RELU),
 ]
+# up-conv mode (bilinear x2 + 5x5 conv in one launch on the low-resolution input): name, H_lo, W_lo, Cin, Cout, epilogue
+UP_LAYERS = [
+    ('dec0 upconv 256->128', 32, 64, 256, 128, ops.EPI_BIAS_RELU),
+    ('dec1 upconv 128->64', 64, 128, 128, 64, ops.EPI_BIAS_RELU),
+    ('dec2 upconv 64->32', 128, 256, 64, 32, ops.EPI_BIAS_RELU),
+    ('dec2 upconv 64->32 +pred', 128, 256, 64, 32, ops.EPI_BIAS_RELU_PRED),
+]
 MULT = {'res 3x3 256->256 (x4)': 4}
 
 
@@ -88,8 +95,35 @@ def main():
         total_ms += mult * us / 1e3
         total_fl += mult * fl
         print(f'{name:34s} {fl / 1e9:8.2f} {us:9.1f} {tf:8.1f} {tf / peak:6.3f}')
-    print(f'{"sum over one pass (convs only)":34s} {total_fl / 1e9:8.2f} {total_ms * 1e3:9.1f} '
-          f'{total_fl / total_ms / 1e9:8.1f} {total_fl / total_ms / 1e9 / peak:6.3f}')
+    if total_ms > 0:
+      print(f'{"sum over one pass (convs only)":34s} {total_fl / 1e9:8.2f} {total_ms * 1e3:9.1f} '
+            f'{total_fl / total_ms / 1e9:8.1f} {total_fl / total_ms / 1e9 / peak:6.3f}')
+    for name, H, W, Cin, Cout, epi in UP_LAYERS:
+        if args.only and args.only not in name:
+            continue
+        nbuf = 4
+        xs = [ops.empty_nhwc(B, Cin, H, W, dev).normal_() for _ in range(nbuf)]
+        w = torch.randn(Cout, Cin, 5, 5, device=dev) * 0.02
+        wp = ops.pack_weights_upconv(w)
+        b = torch.zeros(Cout, device=dev)
+        pw, pb = torch.randn(Cout, device=dev), torch.zeros(1, device=dev)
+
+        def run(i):
+            if epi == ops.EPI_BIAS_RELU_PRED:
+                return ops.conv_up_fwd(xs[i % nbuf], wp, b, Cout, epi, aux0=pw, aux1=pb)
+            return ops.conv_up_fwd(xs[i % nbuf], wp, b, Cout, epi)
+        for i in range(3):
+            run(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.iters):
+            run(i)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / args.iters
+        fl = 2.0 * B * (2 * H) * (2 * W) * Cout * Cin * 25
+        print(f'{name:34s} {fl / 1e9:8.2f} {us:9.1f} {fl / us / 1e6:8.1f} {fl / us / 1e6 / peak:6.3f}')
 
 
 if __name__ == '__main__':
