@@ -75,7 +75,10 @@ enum {
     RAMNET_EPI_BIAS_RELU_PRED = 6,
     /* y0 = relu(acc + b) + aux0: a decoder layer that also forms the NEXT decoder's skip sum (statenet.py:15-16,306-308,
      * `x + super_state`), so that the sum never needs its own pass.  aux0 has the output's shape. */
-    RAMNET_EPI_BIAS_RELU_ADD = 7
+    RAMNET_EPI_BIAS_RELU_ADD = 7,
+    /* y0 = acc + b + aux0 (no activation): a data gradient accumulated onto the gradient another path already
+     * produced (ConvGRU: dx and dh each receive two contributions); y0 may alias aux0. */
+    RAMNET_EPI_BIAS_ADD = 8
 };
 
 enum {
@@ -233,9 +236,16 @@ int ramnet_round_tf32(ramnet_handle *h, const float *x, float *y, int64_t n, voi
  * nn.Conv2d layout [Cout, C0+C1, k, k] / [Cout]; the rest are pointwise adjoints of the fused epilogues.
  * dz: gradient w.r.t. the GEMM output (pre-activation), NHWC [N, Ho, Wo, Cout]. */
 size_t ramnet_conv_wgrad_workspace_bytes(const ramnet_handle *h, const ramnet_conv_desc *d);
+/* `mode`: BPTT produces the weight gradient of one layer once per pass (L * (K+1) times per step, trainer/lstm_trainer.py:
+ * 256-272 then :450).  FULL does everything per call.  The deferred modes keep the layer's partial tiles in a
+ * caller-owned `workspace` that lives for the whole step: PARTIAL_FIRST overwrites it, PARTIAL_ADD accumulates into it
+ * (both run only the tensor-core kernel; dw / db are not touched), FINALIZE (dz, x0, x1 ignored) runs the split sum +
+ * scatter once and accumulates into dw.  The deferred modes return RAMNET_EUNSUPPORTED for shapes the tap-packed
+ * TF32 kernel does not cover (use FULL there). */
+enum { RAMNET_WGRAD_FULL = 0, RAMNET_WGRAD_PARTIAL_FIRST = 1, RAMNET_WGRAD_PARTIAL_ADD = 2, RAMNET_WGRAD_FINALIZE = 3 };
 int ramnet_conv_wgrad(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz, const float *x0,
                       const float *x1, float *dw_oihw, float *db, void *workspace, size_t workspace_bytes,
-                      void *stream);
+                      int mode, void *stream);
 int ramnet_head_conv_wgrad(ramnet_handle *h, const float *x_nchw, const float *dz_nhwc, float *dw_oihw,
                            float *db, int N, int Cin, int H, int W, int Cout, void *stream);
 /* Head conv weight gradient on the tensor cores (TF32 path): xe = ramnet_head_im2row's tensor, dw in the head's
@@ -243,7 +253,7 @@ int ramnet_head_conv_wgrad(ramnet_handle *h, const float *x_nchw, const float *d
 size_t ramnet_head_conv_wgrad_tc_workspace_bytes(const ramnet_handle *h, int N, int Cin, int H, int W, int Cout);
 int ramnet_head_conv_wgrad_tc(ramnet_handle *h, const float *xe_nhwc32, const float *dz_nhwc, float *dw_oihw,
                               float *db, int N, int Cin, int H, int W, int Cout, void *workspace,
-                              size_t workspace_bytes, void *stream);
+                              size_t workspace_bytes, int mode, void *stream);
 int ramnet_pack_weights_dgrad(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin,
                               int ksize, int mma_kind, int ci_begin, int ci_count, void *stream);
 /* Sub-pixel data gradient of a stride-2 conv (TF32 path): dX [N, H, W, ci_count] from dZ [N, H/2, W/2, Cout] as four
@@ -259,18 +269,22 @@ int ramnet_zero_insert2x(ramnet_handle *h, const float *x, const float *skip, fl
                          int Hout, int Wout, void *stream);
 /* dz = dy * (y > 0).  flags & RAMNET_FLAG_ROUND_TF32 (here and in the GRU adjoints): round the dz outputs to TF32
  * so that the tcgen05 dgrad / wgrad GEMMs that consume them truncate nothing. */
-int ramnet_relu_bwd(ramnet_handle *h, const float *dy, const float *y, float *dz, int64_t n, int flags,
-                    void *stream);
+/* db (nullable, [C]) here and in the gate adjoints: the bias gradient db[c] += sum_pixels dz[., c] fused into the same
+ * pass (atomic accumulation, so it can point straight at bias.grad across the passes of BPTT). */
+int ramnet_relu_bwd(ramnet_handle *h, const float *dy, const float *y, float *dz, int64_t n, int C, float *db,
+                    int flags, void *stream);
 /* ConvGRU adjoints (submodules.py:446-452).  gru_out_bwd: dzo = dh'*u*(1-o^2); columns [C,2C) of dzru =
  * dh'*(o-h)*u*(1-u); dh = dh'*(1-u).  gru_ru_bwd: columns [0,C) of dzru = drh*h*r*(1-r); dh += drh*r. */
 int ramnet_gru_out_bwd(ramnet_handle *h, const float *dhn, const float *hprev, const float *u, const float *o,
-                       float *dzo, float *dzru, float *dh, int64_t M, int C, int flags, void *stream);
+                       float *dzo, float *dzru, float *dh, float *db_o /* [C] */, float *db_ru /* [2C], rows [C,2C) */,
+                       int64_t M, int C, int flags, void *stream);
 int ramnet_gru_ru_bwd(ramnet_handle *h, const float *drh, const float *hprev, const float *r, float *dzru,
-                      float *dh, int64_t M, int C, int flags, void *stream);
+                      float *dh, float *db_ru /* [2C], rows [0,C) */, int64_t M, int C, int flags, void *stream);
 /* ConvLSTM adjoint (submodules.py:341-356): gates = post-activation (i,f,o,g) [M,C,4] stashed by RAMNET_EPI_LSTM (y2);
  * dz [M,4C] comes out in nn.Conv2d row order (gate-major); dh / dc may be NULL (no gradient through that output). */
 int ramnet_lstm_bwd(ramnet_handle *h, const float *dh, const float *dc, const float *gates, const float *c_prev,
-                    const float *c_new, float *dz, float *dc_prev, int64_t M, int C, int flags, void *stream);
+                    const float *c_new, float *dz, float *dc_prev, float *db /* [4C], nn.Conv2d row order */, int64_t M,
+                    int C, int flags, void *stream);
 /* pred + sigmoid adjoint: dx[m,c] = g*w[c] (= dskip), dw[c] += sum g*(x+skip)[m,c], db += sum g, g = ddepth*s(1-s);
  * skip may be NULL */
 int ramnet_pred_bwd(ramnet_handle *h, const float *ddepth, const float *depth, const float *x, const float *skip,

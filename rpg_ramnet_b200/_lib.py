@@ -13,11 +13,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libramnet_sm100a.so')
 
 MMA_FP32, MMA_TF32 = 0, 1
-EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RES_RELU, EPI_GRU_RU, EPI_GRU_OUT, EPI_LSTM, EPI_BIAS_RELU_PRED, EPI_BIAS_RELU_ADD = range(8)
+EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RES_RELU, EPI_GRU_RU, EPI_GRU_OUT, EPI_LSTM, EPI_BIAS_RELU_PRED, EPI_BIAS_RELU_ADD, EPI_BIAS_ADD = range(9)
 FLAG_ROUND_TF32 = 1
 FLAG_HPACK = 2
 FLAG_UPCONV = 4
 LOSS_LOG_SPACE = 1
+WGRAD_FULL, WGRAD_PARTIAL_FIRST, WGRAD_PARTIAL_ADD, WGRAD_FINALIZE = range(4)
+RAMNET_EUNSUPPORTED = -3
 
 
 class ConvDesc(ctypes.Structure):
@@ -44,7 +46,7 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ramnet_conv_wgrad_workspace_bytes': (c_size_t, [c_void_p, POINTER(ConvDesc)]),
     'ramnet_conv_wgrad': (c_int, [c_void_p, POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                  c_void_p, c_size_t, c_void_p]),
+                                  c_void_p, c_size_t, c_int, c_void_p]),
     'ramnet_head_conv_wgrad': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                        c_int, c_void_p]),
     'ramnet_pack_weights_dgrad': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
@@ -62,19 +64,19 @@ SIGNATURES = {
                                     c_void_p]),
     'ramnet_head_conv_wgrad_tc_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int, c_int, c_int]),
     'ramnet_head_conv_wgrad_tc': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                          c_void_p, c_size_t, c_void_p]),
+                                          c_void_p, c_size_t, c_int, c_void_p]),
     'ramnet_pack_weights_dgrad_s2': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'ramnet_conv_dgrad_s2': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p]),
     'ramnet_zero_insert2x': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p]),
-    'ramnet_relu_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    'ramnet_relu_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p]),
     'ramnet_gru_out_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                   c_int64, c_int, c_int, c_void_p]),
-    'ramnet_gru_ru_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
+                                   c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    'ramnet_gru_ru_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
                                   c_void_p]),
     'ramnet_lstm_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                c_int64, c_int, c_int, c_void_p]),
+                                c_void_p, c_int64, c_int, c_int, c_void_p]),
     'ramnet_pred_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_int64, c_int, c_void_p]),
     'ramnet_upsample2x_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

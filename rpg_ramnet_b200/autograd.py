@@ -2,10 +2,20 @@
 
 The reference trains by calling loss.backward() through ATen/cuDNN autograd (trainer/lstm_trainer.py:450,
 full BPTT, states never detached).  Here every fused forward op is one autograd node whose backward
-issues our own kernels: pointwise adjoint of the fused epilogue -> weight/bias gradient
-(ramnet_conv_wgrad, accumulated in nn.Conv2d layout) -> data gradient (the forward tcgen05 kernel on dZ
-with tap-flipped, channel-transposed weights).  autograd only does the graph bookkeeping (BPTT order,
-gradient accumulation into .grad), so torch.optim / our fused Adam see ordinary .grad tensors.
+issues our own kernels: pointwise adjoint of the fused epilogue (which also folds in the bias gradient) ->
+weight gradient (tap-packed tcgen05 kernel) -> data gradient (the forward tcgen05 kernel on dZ with tap-flipped,
+channel-transposed weights).  autograd only does the graph bookkeeping (BPTT order).
+
+Parameter gradients do not travel through autograd's AccumulateGrad.  BPTT runs every layer's backward once per pass —
+L * (K + 1) times per step — and round 1 paid per call for a zero-filled dW tensor, the split sum + scatter of the
+weight-gradient partial tiles, a column-sum pass over dZ for the bias and an AccumulateGrad add.  Now:
+  * bias gradients are accumulated by the pointwise adjoint itself (atomics) straight into `bias.grad`;
+  * weight gradients accumulate as PARTIAL TILES in a per-layer workspace across the passes (`ops.WgradAccumulator`:
+    the kernel's epilogue adds to what is there) and the split sum + scatter runs ONCE per step, into `weight.grad`,
+    from a callback autograd runs when the backward pass ends (so `.grad` is complete when `loss.backward()`
+    returns, whatever optimizer follows; with FusedAdam `.grad` is a view of its flat buffer).
+Shapes the tap-packed kernel does not cover, FP32 mode, or RAMNET_WGRAD_DEFER=0 fall back to one full
+`ramnet_conv_wgrad` per call, accumulated into `.grad` directly.
 """
 import torch
 
@@ -14,6 +24,106 @@ from . import ops
 
 def _nhwc(g):
     return ops.as_nhwc(g)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# gradient sinks
+# ------------------------------------------------------------------------------------------------------------------
+def _grad_of(p):
+    """`p.grad` as a dense fp32 tensor we may accumulate into in place (created on first use)."""
+    if p.grad is None or p.grad.dtype != torch.float32 or not p.grad.is_contiguous():
+        g = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.contiguous_format)
+        if p.grad is not None:
+            g.copy_(p.grad)
+        p.grad = g
+    return p.grad
+
+
+class _Deferred:
+    """Per-process registry of the weight-gradient accumulators that hold partial tiles of the running backward pass."""
+    pending = []            # (accumulator, targets) with targets = [(parameter, row_begin, row_end)] in dW row order
+    queued = False
+
+    @classmethod
+    def note(cls, acc, targets):
+        if not any(a is acc for a, _ in cls.pending):
+            cls.pending.append((acc, targets))
+        if not cls.queued:
+            cls.queued = True
+            torch.autograd.Variable._execution_engine.queue_callback(cls.flush)
+
+    @classmethod
+    def flush(cls):
+        """End of the backward pass: one split sum + scatter per layer, accumulated into the parameters' .grad."""
+        pending, cls.pending, cls.queued = cls.pending, [], False
+        with torch.no_grad():
+            for acc, targets in pending:
+                if len(targets) == 1:
+                    acc.finalize(_grad_of(targets[0][0]))
+                    continue
+                rows = targets[-1][2]
+                p0 = targets[0][0]
+                tmp = torch.zeros((rows,) + tuple(p0.shape[1:]), dtype=torch.float32, device=p0.device)
+                acc.finalize(tmp)
+                for p, lo, hi in targets:          # a fused conv over several nn.Parameters (ConvGRU reset | update gates)
+                    _grad_of(p).add_(tmp[lo:hi])
+
+
+def _accumulator(weight, tag, builder):
+    """The layer's WgradAccumulator, cached on the parameter object per (tag = shapes of the call)."""
+    accs = getattr(weight, '_ramnet_wgrad_accs', None)
+    if accs is None:
+        accs = {}
+        try:
+            weight._ramnet_wgrad_accs = accs
+        except AttributeError:
+            return None, True
+    if tag in accs:
+        return accs[tag], False
+    acc = builder()                    # runs the first partial launch itself (probe) or returns None
+    accs[tag] = acc
+    return acc, True
+
+
+def _weight_grad(weights, dz, x0, x1, Cout, k, stride, kind, head=None):
+    """dW of one fused conv.  `weights`: [(parameter, row_begin, row_end)].  Deferred when possible, else a full
+    conv_wgrad accumulated into .grad now."""
+    w0 = weights[0][0]
+    tag = (tuple(dz.shape), tuple(x0.shape), None if x1 is None else tuple(x1.shape), stride, kind, head)
+    if head is None:
+        acc, fresh = _accumulator(w0, tag, lambda: ops.wgrad_accumulator(x0, x1, dz, Cout, k, stride, kind))
+    else:
+        acc, fresh = _accumulator(w0, tag, lambda: ops.head_wgrad_accumulator(x0, dz, head))
+    if acc is not None:
+        if not fresh:
+            acc.add(dz, x0, x1)
+        _Deferred.note(acc, weights)
+        return
+    with torch.no_grad():
+        if len(weights) == 1 and head is None:
+            ops.conv_wgrad(dz, x0, x1, Cout, k, stride, _grad_of(w0), None, kind)
+        elif head is not None:
+            ops.head_conv_wgrad_tc(x0, dz, _grad_of(w0), None, head)
+        else:
+            tmp = torch.zeros((Cout,) + tuple(w0.shape[1:]), dtype=torch.float32, device=w0.device)
+            ops.conv_wgrad(dz, x0, x1, Cout, k, stride, tmp, None, kind)
+            for p, lo, hi in weights:
+                _grad_of(p).add_(tmp[lo:hi])
+
+
+def _bias_sink(bias, C):
+    """Where the pointwise adjoint accumulates the bias gradient: bias.grad itself when the kernel can fold the column
+    sums in (256 % (C/4) == 0), else None (the caller then sums dz separately)."""
+    if bias is None:
+        return None
+    return _grad_of(bias) if ops.colsum_fusable(C) else None
+
+
+def _bias_fallback(bias, dz):
+    """Bias gradient for channel counts the fused column sum does not cover."""
+    if bias is not None and not ops.colsum_fusable(dz.shape[1]):
+        with torch.no_grad():
+            _grad_of(bias).add_(dz.sum(dim=(0, 2, 3)))
 
 
 class HeadConvFn(torch.autograd.Function):
@@ -31,30 +141,30 @@ class HeadConvFn(torch.autograd.Function):
         else:
             y = ops.head_conv(x, weight.detach(), b, round_tf32)
         ctx.save_for_backward(x, y)
-        ctx.has_bias = bias is not None
-        ctx.wshape = weight.shape
+        ctx.weight, ctx.bias = weight, bias
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, y = ctx.saved_tensors
-        dz = ops.relu_bwd(_nhwc(dy), y, round_tf32=ctx.tc)
-        dw = torch.zeros(ctx.wshape, dtype=torch.float32, device=y.device)
-        db = torch.zeros(ctx.wshape[0], dtype=torch.float32, device=y.device) if ctx.has_bias else None
+        weight, bias = ctx.weight, ctx.bias
+        dz = ops.relu_bwd(_nhwc(dy), y, round_tf32=ctx.tc, db=_bias_sink(bias, y.shape[1]))
+        _bias_fallback(bias, dz)
         if ctx.tc:
-            ops.head_conv_wgrad_tc(x, dz, dw, db, ctx.wshape[1])
+            _weight_grad([(weight, 0, weight.shape[0])], dz, x, None, weight.shape[0], 5, 1, ops.MMA_TF32, head=weight.shape[1])
         else:
-            ops.head_conv_wgrad(x, dz, dw, db)
-        return None, dw, db, None
+            with torch.no_grad():
+                ops.head_conv_wgrad(x, dz, _grad_of(weight), None)
+        return None, None, None, None
 
 
 # Data-gradient weight packs live on the parameter object itself and are rebuilt when it changes (same token as
 # engine.WeightCache: in-place version counter + the epoch the fused Adam bumps).  BPTT calls every layer's backward
 # L*(K+1) times per step with the same weights, so all but the first call reuse the pack.  (Keyed on the object, not
 # on data_ptr: a new tensor that recycles a freed address must never see a stale pack.)
-def _cached_pack(weight, tag, builder):
+def _cached_pack(weight, tag, builder, also=()):
     from . import engine
-    tok = (weight.data_ptr(), weight._version, engine._WEIGHT_EPOCH)
+    tok = (weight.data_ptr(), weight._version, engine._WEIGHT_EPOCH) + tuple((w.data_ptr(), w._version) for w in also)
     packs = getattr(weight, '_ramnet_dgrad_packs', None)
     if packs is None:
         packs = {}
@@ -70,19 +180,27 @@ def _cached_pack(weight, tag, builder):
     return packed
 
 
-def _dgrad(dz, weight, kind, stride, ci_begin, ci_count, in_hw):
-    """Data gradient w.r.t. input channels [ci_begin, ci_begin+ci_count) of a conv with nn.Conv2d weight `weight`."""
+def _dgrad(dz, weight, kind, stride, ci_begin, ci_count, in_hw, add=None, key_weight=None, also=()):
+    """Data gradient w.r.t. input channels [ci_begin, ci_begin+ci_count) of a conv with nn.Conv2d weight `weight`.
+    `add`: a gradient already produced for the same tensor; the contribution is accumulated onto it IN PLACE by the
+    kernel's epilogue (EPI_BIAS_ADD) instead of a separate elementwise add.  `key_weight` / `also`: the parameter
+    object(s) the pack cache hangs on when `weight` is a temporary (the concatenated ConvGRU reset | update weight)."""
     Cout, _, k, _ = weight.shape
     H, W = int(in_hw[0]), int(in_hw[1])
+    kw = weight if key_weight is None else key_weight
     if (stride == 2 and kind == ops.MMA_TF32 and k in (3, 5) and H % 2 == 0 and W % 2 == 0 and Cout % 32 == 0
             and ci_count % 32 == 0):
         # sub-pixel decomposition: four stride-1 convolutions of dZ, one per input parity (no zero insertion)
-        wp = _cached_pack(weight, ('s2', ci_begin, ci_count), lambda: ops.pack_weights_dgrad_s2(weight, ci_begin, ci_count))
-        return ops.conv_dgrad_s2(dz, wp, ci_count, k, H, W)
-    wp = _cached_pack(weight, (kind, ci_begin, ci_count), lambda: ops.pack_weights_dgrad(weight, kind, ci_begin, ci_count))
+        wp = _cached_pack(kw, ('s2', ci_begin, ci_count), lambda: ops.pack_weights_dgrad_s2(weight, ci_begin, ci_count), also)
+        dx = ops.conv_dgrad_s2(dz, wp, ci_count, k, H, W)
+        return dx if add is None else add.add_(dx)
+    wp = _cached_pack(kw, (kind, ci_begin, ci_count), lambda: ops.pack_weights_dgrad(weight, kind, ci_begin, ci_count), also)
     if stride == 2:
         dz = ops.zero_insert2x(dz, H, W)
-    return ops.conv_fwd(dz, None, wp, None, ci_count, k, 1, ops.EPI_BIAS, kind)
+    if add is not None and kind == ops.MMA_TF32:
+        return ops.conv_fwd(dz, None, wp, None, ci_count, k, 1, ops.EPI_BIAS_ADD, kind, aux0=add, out0=add)
+    dx = ops.conv_fwd(dz, None, wp, None, ci_count, k, 1, ops.EPI_BIAS, kind)
+    return dx if add is None else add.add_(dx)
 
 
 class ConvFn(torch.autograd.Function):
@@ -92,27 +210,34 @@ class ConvFn(torch.autograd.Function):
     def forward(ctx, x0, x1, res, weight, bias, packed_w, epilogue, kind, stride, round_out):
         y = ops.conv_fwd(x0, x1, packed_w, None if bias is None else bias.detach(), weight.shape[0], weight.shape[2],
                          stride, epilogue, kind, aux0=res, round_tf32=round_out)
-        ctx.save_for_backward(x0, x1, y, weight)
-        ctx.cfg = (epilogue, kind, stride, bias is not None, res is not None)
+        ctx.save_for_backward(x0, x1, y)
+        ctx.weight, ctx.bias = weight, bias
+        ctx.cfg = (epilogue, kind, stride, res is not None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x0, x1, y, weight = ctx.saved_tensors
-        epilogue, kind, stride, has_bias, has_res = ctx.cfg
+        x0, x1, y = ctx.saved_tensors
+        weight, bias = ctx.weight, ctx.bias
+        epilogue, kind, stride, has_res = ctx.cfg
         dy = _nhwc(dy)
-        dz = dy if epilogue == ops.EPI_BIAS else ops.relu_bwd(dy, y, round_tf32=(kind == ops.MMA_TF32))
         Cout, Ct, k, _ = weight.shape
-        dw = torch.zeros_like(weight, dtype=torch.float32)
-        db = torch.zeros(Cout, dtype=torch.float32, device=y.device) if has_bias else None
-        ops.conv_wgrad(dz, x0, x1, Cout, k, stride, dw, db, kind)
+        if epilogue == ops.EPI_BIAS:
+            dz = dy
+            if bias is not None:
+                with torch.no_grad():
+                    _grad_of(bias).add_(dz.sum(dim=(0, 2, 3)))
+        else:
+            dz = ops.relu_bwd(dy, y, round_tf32=(kind == ops.MMA_TF32), db=_bias_sink(bias, Cout))
+            _bias_fallback(bias, dz)
+        _weight_grad([(weight, 0, Cout)], dz, x0, x1, Cout, k, stride, kind)
         C0 = x0.shape[1]
         dx0 = _dgrad(dz, weight, kind, stride, 0, C0, x0.shape[2:]) if ctx.needs_input_grad[0] else None
         dx1 = None
         if x1 is not None and ctx.needs_input_grad[1]:
             dx1 = _dgrad(dz, weight, kind, stride, C0, Ct - C0, x1.shape[2:])
         dres = dz if (has_res and ctx.needs_input_grad[2]) else None
-        return dx0, dx1, dres, dw, db, None, None, None, None, None
+        return dx0, dx1, dres, None, None, None, None, None, None, None
 
 
 class GruFn(torch.autograd.Function):
@@ -128,32 +253,60 @@ class GruFn(torch.autograd.Function):
         u, rh = ops.conv_fwd(x, h, ru_pack.w, ru_pack.b, 2 * C, 3, 1, ops.EPI_GRU_RU, kind, aux0=h, round_tf32=tf32, stash=r)
         hn = ops.conv_fwd(x, rh, out_pack.w, out_pack.b, C, 3, 1, ops.EPI_GRU_OUT, kind, aux0=h, aux1=u, round_tf32=tf32,
                           stash=o)
-        ctx.save_for_backward(x, h, u, r, rh, o, w_r, w_u, w_o)
+        ctx.save_for_backward(x, h, u, r, rh, o)
+        ctx.params = (w_r, b_r, w_u, b_u, w_o, b_o)
         ctx.kind = kind
         return hn
 
     @staticmethod
     def backward(ctx, dhn):
-        x, h, u, r, rh, o, w_r, w_u, w_o = ctx.saved_tensors
+        x, h, u, r, rh, o = ctx.saved_tensors
+        w_r, b_r, w_u, b_u, w_o, b_o = ctx.params
         kind = ctx.kind
         N, C, H, W = x.shape
         tf32 = kind == ops.MMA_TF32
-        dzo, dzru, dh = ops.gru_out_bwd(_nhwc(dhn), h, u, o, round_tf32=tf32)
-        dw_o = torch.zeros_like(w_o, dtype=torch.float32)
-        db_o = torch.zeros(C, dtype=torch.float32, device=x.device)
-        ops.conv_wgrad(dzo, x, rh, C, 3, 1, dw_o, db_o, kind)
+        fuse = ops.colsum_fusable(C)
+        # bias gradients of the fused [reset | update] conv land in one [2C] scratch (two parameters own its halves)
+        db_ru = torch.zeros(2 * C, dtype=torch.float32, device=x.device) if (fuse and (b_r is not None or b_u is not None)) else None
+        dzo, dzru, dh = ops.gru_out_bwd(_nhwc(dhn), h, u, o, round_tf32=tf32,
+                                        db_o=_bias_sink(b_o, C) if fuse else None, db_ru=db_ru)
+        _weight_grad([(w_o, 0, C)], dzo, x, rh, C, 3, 1, kind)
         dx = _dgrad(dzo, w_o, kind, 1, 0, C, (H, W))
         drh = _dgrad(dzo, w_o, kind, 1, C, C, (H, W))
-        ops.gru_ru_bwd(drh, h, r, dzru, dh, round_tf32=tf32)
-        w_ru = torch.cat([w_r.detach(), w_u.detach()], 0)
-        dw_ru = torch.zeros_like(w_ru, dtype=torch.float32)
-        db_ru = torch.zeros(2 * C, dtype=torch.float32, device=x.device)
-        ops.conv_wgrad(dzru, x, h, 2 * C, 3, 1, dw_ru, db_ru, kind)
-        dx = dx + _dgrad(dzru, w_ru, kind, 1, 0, C, (H, W))
-        dh = dh + _dgrad(dzru, w_ru, kind, 1, C, C, (H, W))
+        ops.gru_ru_bwd(drh, h, r, dzru, dh, round_tf32=tf32, db_ru=db_ru)
+        with torch.no_grad():
+            if db_ru is not None:
+                if b_r is not None:
+                    _grad_of(b_r).add_(db_ru[:C])
+                if b_u is not None:
+                    _grad_of(b_u).add_(db_ru[C:])
+            elif not fuse:
+                if b_o is not None:
+                    _grad_of(b_o).add_(dzo.sum(dim=(0, 2, 3)))
+                s = dzru.sum(dim=(0, 2, 3))
+                if b_r is not None:
+                    _grad_of(b_r).add_(s[:C])
+                if b_u is not None:
+                    _grad_of(b_u).add_(s[C:])
+        _weight_grad([(w_r, 0, C), (w_u, C, 2 * C)], dzru, x, h, 2 * C, 3, 1, kind)
+        # the concatenated [reset | update] weight only exists to be re-packed for the data gradient: build it when a
+        # pack is actually missing (once per optimizer step), not on every backward call
+        w_ru = _LazyCat(w_r, w_u)
+        dx = _dgrad(dzru, w_ru, kind, 1, 0, C, (H, W), add=dx, key_weight=w_r, also=(w_u,))
+        dh = _dgrad(dzru, w_ru, kind, 1, C, C, (H, W), add=dh, key_weight=w_r, also=(w_u,))
         return (dx if ctx.needs_input_grad[0] else None, dh if ctx.needs_input_grad[1] else None,
-                dw_ru[:C].contiguous(), db_ru[:C].contiguous(), dw_ru[C:].contiguous(), db_ru[C:].contiguous(),
-                dw_o, db_o, None, None, None)
+                None, None, None, None, None, None, None, None, None)
+
+
+class _LazyCat:
+    """torch.cat([w_r, w_u]) materialised only if a packer reads it (`.detach()` / `.shape`)."""
+
+    def __init__(self, a, b):
+        self.a, self.b = a, b
+        self.shape = (a.shape[0] + b.shape[0],) + tuple(a.shape[1:])
+
+    def detach(self):
+        return torch.cat([self.a.detach(), self.b.detach()], 0)
 
 
 class LstmFn(torch.autograd.Function):
@@ -167,25 +320,25 @@ class LstmFn(torch.autograd.Function):
         gates = torch.empty((N, H, W, C, 4), dtype=torch.float32, device=x.device)
         hn, cn = ops.conv_fwd(x, h, pack.w, pack.b, 4 * C, 3, 1, ops.EPI_LSTM, kind, aux0=c,
                               round_tf32=(kind == ops.MMA_TF32), stash=gates)
-        ctx.save_for_backward(x, h, c, cn, gates, weight)
+        ctx.save_for_backward(x, h, c, cn, gates)
+        ctx.weight, ctx.bias = weight, bias
         ctx.kind = kind
         ctx.mark_non_differentiable()
         return hn, cn
 
     @staticmethod
     def backward(ctx, dhn, dcn):
-        x, h, c, cn, gates, weight = ctx.saved_tensors
+        x, h, c, cn, gates = ctx.saved_tensors
+        weight, bias = ctx.weight, ctx.bias
         kind = ctx.kind
         N, Cx, H, W = x.shape
         C = weight.shape[0] // 4
         dz, dc = ops.lstm_bwd(None if dhn is None else _nhwc(dhn), None if dcn is None else _nhwc(dcn), gates, c, cn,
-                              round_tf32=(kind == ops.MMA_TF32))
-        dw = torch.zeros_like(weight, dtype=torch.float32)
-        db = torch.zeros(4 * C, dtype=torch.float32, device=x.device)
-        ops.conv_wgrad(dz, x, h, 4 * C, 3, 1, dw, db, kind)
+                              round_tf32=(kind == ops.MMA_TF32), db=None if bias is None else _grad_of(bias))
+        _weight_grad([(weight, 0, 4 * C)], dz, x, h, 4 * C, 3, 1, kind)
         dx = _dgrad(dz, weight, kind, 1, 0, Cx, (H, W)) if ctx.needs_input_grad[0] else None
         dh = _dgrad(dz, weight, kind, 1, Cx, C, (H, W)) if ctx.needs_input_grad[1] else None
-        return dx, dh, (dc if ctx.needs_input_grad[2] else None), dw, db, None, None
+        return dx, dh, (dc if ctx.needs_input_grad[2] else None), None, None, None, None
 
 
 class UpsampleAddFn(torch.autograd.Function):
@@ -206,12 +359,17 @@ class PredFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, skip, weight, bias):
         depth = ops.pred_sigmoid(x, skip, weight.detach(), None if bias is None else bias.detach())
-        ctx.save_for_backward(x, skip, depth, weight)
-        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, skip, depth)
+        ctx.weight, ctx.bias = weight, bias
         return depth
 
     @staticmethod
     def backward(ctx, ddepth):
-        x, skip, depth, weight = ctx.saved_tensors
+        x, skip, depth = ctx.saved_tensors
+        weight, bias = ctx.weight, ctx.bias
         dx, dw, db = ops.pred_bwd(ddepth, depth, x, weight, skip)
-        return dx, (dx if skip is not None else None), dw.view(weight.shape), (db if ctx.has_bias else None)
+        with torch.no_grad():
+            _grad_of(weight).add_(dw.view(weight.shape))
+            if bias is not None:
+                _grad_of(bias).add_(db)
+        return dx, (dx if skip is not None else None), None, None

@@ -135,7 +135,7 @@ __device__ __forceinline__ void epilogue_prefetch(const EpiParams &p, int64_t m,
 #pragma unroll
     for (int j = 0; j < NV / 4; ++j)
         x.bias[j] = p.bias ? __ldg(reinterpret_cast<const float4 *>(p.bias + n0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-    if constexpr (EPI == RAMNET_EPI_BIAS_RES_RELU || EPI == RAMNET_EPI_BIAS_RELU_ADD) {
+    if constexpr (EPI == RAMNET_EPI_BIAS_RES_RELU || EPI == RAMNET_EPI_BIAS_RELU_ADD || EPI == RAMNET_EPI_BIAS_ADD) {
 #pragma unroll
         for (int j = 0; j < NV / 4; ++j) x.a[j] = *(reinterpret_cast<const float4 *>(p.aux0 + m * p.Cout + n0) + j);
     } else if constexpr (EPI == RAMNET_EPI_GRU_RU) {
@@ -214,6 +214,14 @@ __device__ __forceinline__ void epilogue_finish(const EpiParams &p, int64_t m, i
             const float4 r = x.a[j / 4];
             o[j] = fmaxf(v[j] + r.x, 0.f); o[j + 1] = fmaxf(v[j + 1] + r.y, 0.f);
             o[j + 2] = fmaxf(v[j + 2] + r.z, 0.f); o[j + 3] = fmaxf(v[j + 3] + r.w, 0.f);
+        }
+        store_row(p.y0 + m * p.Cout + n0, o);
+    } else if constexpr (EPI == RAMNET_EPI_BIAS_ADD) {
+        float o[NV];
+#pragma unroll
+        for (int j = 0; j < NV; j += 4) {
+            const float4 r = x.a[j / 4];
+            o[j] = v[j] + r.x; o[j + 1] = v[j + 1] + r.y; o[j + 2] = v[j + 2] + r.z; o[j + 3] = v[j + 3] + r.w;
         }
         store_row(p.y0 + m * p.Cout + n0, o);
     } else if constexpr (EPI == RAMNET_EPI_BIAS_RELU_ADD) {

@@ -200,19 +200,61 @@ __device__ __forceinline__ float4 rnd4(float4 v, int round) {
     return round ? make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w)) : v;
 }
 
-__global__ void relu_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ y, float *__restrict__ dz,
-                                int64_t n4, int round) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        const float4 g = ld4(dy, i), v = ld4(y, i);
-        st4(dz, i, rnd4(F4_MAP2(g, v, B > 0.f ? A : 0.f), round));
+// Bias gradient fused into the pointwise adjoints: db[c] += sum over pixels of dz[., c].  The kernels below walk the
+// [M, C] tensor as a flat float4 stream with a grid stride that is a multiple of 256, so when 256 % (C/4) == 0 a thread
+// only ever sees ONE column quad (threadIdx.x % (C/4)): it keeps a float4 running sum in registers, the block folds the
+// 256 sums through shared memory and issues one atomicAdd per column.  This replaces a separate pass over dz per
+// backward call (colsum4_kernel: 34 launches x 22 us per timestep of the bench's training step, ncu round 2).
+__device__ __forceinline__ void f4_acc(float4 &a, const float4 &v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+__device__ __forceinline__ void block_colsum_atomic(float4 *part, const float4 &a, int C4, float *__restrict__ db) {
+    __syncthreads();                      // `part` may still be read by a previous fold
+    part[threadIdx.x] = a;
+    __syncthreads();
+    if ((int)threadIdx.x < C4) {
+        float4 acc = part[threadIdx.x];
+        for (int j = threadIdx.x + C4; j < 256; j += C4) f4_acc(acc, part[j]);
+        float *o = db + 4 * threadIdx.x;
+        atomicAdd(o, acc.x); atomicAdd(o + 1, acc.y); atomicAdd(o + 2, acc.z); atomicAdd(o + 3, acc.w);
     }
+}
+static inline bool colsum_fusable(int C) { return C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0; }
+
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ y,
+                                                       float *__restrict__ dz, int64_t n4, int round, int C4,
+                                                       float *__restrict__ db) {
+    __shared__ float4 part[256];
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {          // four independent load pairs in flight per thread
+        float4 g[4], v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { g[q] = ld4(dy, i + q * stride); v[q] = ld4(y, i + q * stride); }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 z = rnd4(F4_MAP2(g[q], v[q], B > 0.f ? A : 0.f), round);
+            st4(dz, i + q * stride, z);
+            f4_acc(sum, z);
+        }
+    }
+    for (; i < n4; i += stride) {
+        const float4 g = ld4(dy, i), v = ld4(y, i);
+        const float4 z = rnd4(F4_MAP2(g, v, B > 0.f ? A : 0.f), round);
+        st4(dz, i, z);
+        f4_acc(sum, z);
+    }
+    if (db) block_colsum_atomic(part, sum, C4, db);
 }
 
 // ConvGRU candidate+blend adjoint.  in: dh' (dhn), h, u, o.  out: dzo = dh'*u*(1-o^2), dzu = dh'*(o-h)*u*(1-u)
 // written into the update half of dzru [M, 2C] (columns [C, 2C)), dh = dh'*(1-u).
-__global__ void gru_out_bwd_kernel(const float *__restrict__ dhn, const float *__restrict__ h, const float *__restrict__ u,
-                                   const float *__restrict__ o, float *__restrict__ dzo, float *__restrict__ dzru,
-                                   float *__restrict__ dh, int64_t M, int C, int round) {
+__global__ void __launch_bounds__(256) gru_out_bwd_kernel(const float *__restrict__ dhn, const float *__restrict__ h,
+                                                          const float *__restrict__ u, const float *__restrict__ o,
+                                                          float *__restrict__ dzo, float *__restrict__ dzru,
+                                                          float *__restrict__ dh, int64_t M, int C, int round,
+                                                          float *__restrict__ db_o, float *__restrict__ db_ru) {
+    __shared__ float4 part[256];
+    float4 sum_o = make_float4(0.f, 0.f, 0.f, 0.f), sum_u = sum_o;
     const int C4 = C >> 2;
     const int64_t n4 = M * C4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -225,16 +267,24 @@ __global__ void gru_out_bwd_kernel(const float *__restrict__ dhn, const float *_
         b.x = g.x * (ov.x - hv.x) * uv.x * (1.f - uv.x); b.y = g.y * (ov.y - hv.y) * uv.y * (1.f - uv.y);
         b.z = g.z * (ov.z - hv.z) * uv.z * (1.f - uv.z); b.w = g.w * (ov.w - hv.w) * uv.w * (1.f - uv.w);
         d.x = g.x * (1.f - uv.x); d.y = g.y * (1.f - uv.y); d.z = g.z * (1.f - uv.z); d.w = g.w * (1.f - uv.w);
-        st4(dzo, i, rnd4(a, round));
-        st4(dzru, m * (2 * C4) + C4 + c, rnd4(b, round));
+        a = rnd4(a, round); b = rnd4(b, round);
+        st4(dzo, i, a);
+        st4(dzru, m * (2 * C4) + C4 + c, b);
         st4(dh, i, d);
+        f4_acc(sum_o, a); f4_acc(sum_u, b);
     }
+    if (db_o) block_colsum_atomic(part, sum_o, C4, db_o);
+    if (db_ru) block_colsum_atomic(part, sum_u, C4, db_ru + C);       // update gate = rows [C, 2C) of the fused RU conv
 }
 
 // ConvGRU reset adjoint.  in: drh (grad of h*r), h, r.  out: dzr = drh*h*r*(1-r) into columns [0, C) of dzru,
 // dh += drh*r.
-__global__ void gru_ru_bwd_kernel(const float *__restrict__ drh, const float *__restrict__ h, const float *__restrict__ r,
-                                  float *__restrict__ dzru, float *__restrict__ dh, int64_t M, int C, int round) {
+__global__ void __launch_bounds__(256) gru_ru_bwd_kernel(const float *__restrict__ drh, const float *__restrict__ h,
+                                                         const float *__restrict__ r, float *__restrict__ dzru,
+                                                         float *__restrict__ dh, int64_t M, int C, int round,
+                                                         float *__restrict__ db_ru) {
+    __shared__ float4 part[256];
+    float4 sum_r = make_float4(0.f, 0.f, 0.f, 0.f);
     const int C4 = C >> 2;
     const int64_t n4 = M * C4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -245,17 +295,24 @@ __global__ void gru_ru_bwd_kernel(const float *__restrict__ drh, const float *__
         a.x = g.x * hv.x * rv.x * (1.f - rv.x); a.y = g.y * hv.y * rv.y * (1.f - rv.y);
         a.z = g.z * hv.z * rv.z * (1.f - rv.z); a.w = g.w * hv.w * rv.w * (1.f - rv.w);
         d.x += g.x * rv.x; d.y += g.y * rv.y; d.z += g.z * rv.z; d.w += g.w * rv.w;
-        st4(dzru, m * (2 * C4) + c, rnd4(a, round));
+        a = rnd4(a, round);
+        st4(dzru, m * (2 * C4) + c, a);
         st4(dh, i, d);
+        f4_acc(sum_r, a);
     }
+    if (db_ru) block_colsum_atomic(part, sum_r, C4, db_ru);          // reset gate = rows [0, C)
 }
 
 // ConvLSTM adjoint (submodules.py:341-356).  gates: post-activation [M][C][4] = (i, f, o, g) as stashed by the forward
 // epilogue.  dz is written in the ORIGINAL nn.Conv2d row order (gate-major blocks: in | remember | out | cell) so that
 // the weight / data gradients use the unpermuted Gates.weight.
-__global__ void lstm_bwd_kernel(const float *__restrict__ dh, const float *__restrict__ dc, const float *__restrict__ gates,
-                                const float *__restrict__ c_prev, const float *__restrict__ c_new, float *__restrict__ dz,
-                                float *__restrict__ dc_prev, int64_t M, int C, int round) {
+__global__ void __launch_bounds__(256) lstm_bwd_kernel(const float *__restrict__ dh, const float *__restrict__ dc,
+                                                       const float *__restrict__ gates, const float *__restrict__ c_prev,
+                                                       const float *__restrict__ c_new, float *__restrict__ dz,
+                                                       float *__restrict__ dc_prev, int64_t M, int C, int round,
+                                                       float *__restrict__ db) {
+    __shared__ float4 part[256];
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);      // (in, remember, out, cell) of this thread's channel (256 % C == 0)
     const int64_t n = M * C;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t m = i / C;
@@ -272,6 +329,17 @@ __global__ void lstm_bwd_kernel(const float *__restrict__ dh, const float *__res
         float *row = dz + m * 4 * C;
         row[c] = zi; row[C + c] = zf; row[2 * C + c] = zo; row[3 * C + c] = zg;
         dc_prev[i] = dct * g.y;
+        sum.x += zi; sum.y += zf; sum.z += zo; sum.w += zg;
+    }
+    if (db) {
+        part[threadIdx.x] = sum;
+        __syncthreads();
+        if ((int)threadIdx.x < C) {
+            float4 acc = part[threadIdx.x];
+            for (int j = threadIdx.x + C; j < 256; j += C) f4_acc(acc, part[j]);
+            atomicAdd(db + threadIdx.x, acc.x); atomicAdd(db + C + threadIdx.x, acc.y);
+            atomicAdd(db + 2 * C + threadIdx.x, acc.z); atomicAdd(db + 3 * C + threadIdx.x, acc.w);
+        }
     }
 }
 
@@ -410,10 +478,16 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(const float *__restrict
 }
 
 int grid_for(ramnet_handle *h, int64_t n) { return (int)imin64((n + 255) / 256, (int64_t)h->sm_count * 16); }
+// Launches that fold a bias gradient in end with one atomicAdd per column per BLOCK; with the wide grid above that was
+// 2368 blocks x C adds onto 1 KB of addresses and cost ~50 us per launch (ncu, round 2: relu_bwd 13 -> 67 us).  Four
+// blocks per SM keep the kernels at the HBM rate (several independent loads in flight per thread) with 4x fewer atomics.
+int grid_for_colsum(ramnet_handle *h, int64_t n, bool fused) {
+    return fused ? (int)imin64((n + 255) / 256, (int64_t)h->sm_count * 4) : grid_for(h, n);
+}
 }  // namespace
 
 int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz, const float *x0, const float *x1,
-                    float *dw, void *workspace, size_t workspace_bytes, cudaStream_t s, int head_cin = 0);
+                    float *dw, void *workspace, size_t workspace_bytes, cudaStream_t s, int head_cin, int mode);
 size_t conv_wgrad_tf32_workspace(const ramnet_handle *h, const ramnet_conv_desc *d, int head_cin = 0);
 
 extern "C" size_t ramnet_conv_wgrad_workspace_bytes(const ramnet_handle *h, const ramnet_conv_desc *d) {
@@ -441,24 +515,34 @@ extern "C" size_t ramnet_head_conv_wgrad_tc_workspace_bytes(const ramnet_handle 
 
 extern "C" int ramnet_head_conv_wgrad_tc(ramnet_handle *h, const float *xe_nhwc32, const float *dz_nhwc, float *dw_oihw,
                                          float *db, int N, int Cin, int H, int W, int Cout, void *workspace,
-                                         size_t workspace_bytes, void *stream) {
+                                         size_t workspace_bytes, int mode, void *stream) {
     RAMNET_DEVICE_GUARD(h);
-    RAMNET_CHECK_ARG(h && xe_nhwc32 && dz_nhwc && dw_oihw, "head_conv_wgrad_tc: NULL argument");
+    RAMNET_CHECK_ARG(h && (mode == RAMNET_WGRAD_FINALIZE || (xe_nhwc32 && dz_nhwc)) &&
+                         (mode == RAMNET_WGRAD_PARTIAL_FIRST || mode == RAMNET_WGRAD_PARTIAL_ADD || dw_oihw),
+                     "head_conv_wgrad_tc: NULL argument");
     RAMNET_CHECK_ARG(Cin >= 1 && 5 * Cin <= 32 && Cout > 0 && Cout % 32 == 0, "head_conv_wgrad_tc: needs 5*Cin <= 32 and Cout %% 32 == 0 (got %d, %d)", Cin, Cout);
-    if (db) {
+    if (db && dz_nhwc && mode != RAMNET_WGRAD_FINALIZE) {
         launch_colsum(h, dz_nhwc, (int64_t)N * H * W, Cout, db, (cudaStream_t)stream);
         RAMNET_LAUNCH_CHECK(h);
     }
     const ramnet_conv_desc d = head_wgrad_desc(N, H, W, Cout);
-    return conv_wgrad_tf32(h, &d, dz_nhwc, xe_nhwc32, nullptr, dw_oihw, workspace, workspace_bytes, (cudaStream_t)stream, Cin);
+    return conv_wgrad_tf32(h, &d, dz_nhwc, xe_nhwc32, nullptr, dw_oihw, workspace, workspace_bytes, (cudaStream_t)stream, Cin,
+                           mode);
 }
 
 extern "C" int ramnet_conv_wgrad(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz, const float *x0,
                                  const float *x1, float *dw_oihw, float *db, void *workspace, size_t workspace_bytes,
-                                 void *stream) {
+                                 int mode, void *stream) {
     RAMNET_DEVICE_GUARD(h);
-    RAMNET_CHECK_ARG(h && d && dz && x0 && dw_oihw, "conv_wgrad: NULL argument");
+    RAMNET_CHECK_ARG(h && d && mode >= RAMNET_WGRAD_FULL && mode <= RAMNET_WGRAD_FINALIZE, "conv_wgrad: NULL argument / bad mode");
     RAMNET_CHECK_ARG(d->C0 % 4 == 0 && d->C1 % 4 == 0 && d->Cout % 4 == 0, "conv_wgrad: channel counts must be multiples of 4");
+    if (mode != RAMNET_WGRAD_FULL) {        // deferred modes: the tap-packed TF32 kernel only, no bias gradient here
+        RAMNET_CHECK_ARG(d->mma_kind == RAMNET_MMA_TF32 && !db, "conv_wgrad: deferred modes need mma_kind=TF32 and db=NULL");
+        RAMNET_CHECK_ARG(mode == RAMNET_WGRAD_FINALIZE ? dw_oihw != nullptr : (dz && x0 && (d->C1 == 0) == (x1 == nullptr)),
+                         "conv_wgrad: NULL argument");
+        return conv_wgrad_tf32(h, d, dz, x0, x1, dw_oihw, workspace, workspace_bytes, (cudaStream_t)stream, 0, mode);
+    }
+    RAMNET_CHECK_ARG(dz && x0 && dw_oihw, "conv_wgrad: NULL argument");
     RAMNET_CHECK_ARG((d->C1 == 0) == (x1 == nullptr), "conv_wgrad: x1 and C1 disagree");
     if (db) {
         const int64_t Mrows = (int64_t)d->N * conv_out_dim(d->H, d->stride) * conv_out_dim(d->W, d->stride);
@@ -466,7 +550,8 @@ extern "C" int ramnet_conv_wgrad(ramnet_handle *h, const ramnet_conv_desc *d, co
         RAMNET_LAUNCH_CHECK(h);
     }
     if (d->mma_kind == RAMNET_MMA_TF32) {
-        const int rc = conv_wgrad_tf32(h, d, dz, x0, x1, dw_oihw, workspace, workspace_bytes, (cudaStream_t)stream);
+        const int rc = conv_wgrad_tf32(h, d, dz, x0, x1, dw_oihw, workspace, workspace_bytes, (cudaStream_t)stream, 0,
+                                       RAMNET_WGRAD_FULL);
         if (rc != RAMNET_EUNSUPPORTED) return rc;      // unsupported shape: fp32 FFMA kernel below
     }
     db = nullptr;
@@ -516,31 +601,41 @@ extern "C" int ramnet_pack_weights_dgrad(ramnet_handle *h, const float *w_oihw, 
     return RAMNET_OK;
 }
 
-extern "C" int ramnet_relu_bwd(ramnet_handle *h, const float *dy, const float *y, float *dz, int64_t n, int flags,
-                               void *stream) {
+extern "C" int ramnet_relu_bwd(ramnet_handle *h, const float *dy, const float *y, float *dz, int64_t n, int C, float *db,
+                               int flags, void *stream) {
     RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && dy && y && dz && n > 0 && n % 4 == 0, "relu_bwd: bad argument");
-    relu_bwd_kernel<<<grid_for(h, n / 4), 256, 0, (cudaStream_t)stream>>>(dy, y, dz, n / 4, flags & RAMNET_FLAG_ROUND_TF32);
+    RAMNET_CHECK_ARG(!db || (C > 0 && n % C == 0), "relu_bwd: db needs the channel count C (n %% C == 0)");
+    const bool fuse = db && colsum_fusable(C);
+    relu_bwd_kernel<<<grid_for_colsum(h, n / 4, fuse), 256, 0, (cudaStream_t)stream>>>(dy, y, dz, n / 4, flags & RAMNET_FLAG_ROUND_TF32,
+                                                                         fuse ? C / 4 : 1, fuse ? db : nullptr);
     RAMNET_LAUNCH_CHECK(h);
+    if (db && !fuse) {
+        launch_colsum(h, dz, n / C, C, db, (cudaStream_t)stream);
+        RAMNET_LAUNCH_CHECK(h);
+    }
     return RAMNET_OK;
 }
 
 extern "C" int ramnet_gru_out_bwd(ramnet_handle *h, const float *dhn, const float *hprev, const float *u, const float *o,
-                                  float *dzo, float *dzru, float *dh, int64_t M, int C, int flags, void *stream) {
+                                  float *dzo, float *dzru, float *dh, float *db_o, float *db_ru, int64_t M, int C, int flags,
+                                  void *stream) {
     RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && dhn && hprev && u && o && dzo && dzru && dh && M > 0 && C % 4 == 0, "gru_out_bwd: bad argument");
-    gru_out_bwd_kernel<<<grid_for(h, M * (C / 4)), 256, 0, (cudaStream_t)stream>>>(dhn, hprev, u, o, dzo, dzru, dh, M, C,
-                                                                                   flags & RAMNET_FLAG_ROUND_TF32);
+    RAMNET_CHECK_ARG((!db_o && !db_ru) || colsum_fusable(C), "gru_out_bwd: fused bias gradients need 256 %% (C/4) == 0");
+    gru_out_bwd_kernel<<<grid_for_colsum(h, M * (C / 4), db_o || db_ru), 256, 0, (cudaStream_t)stream>>>(
+        dhn, hprev, u, o, dzo, dzru, dh, M, C, flags & RAMNET_FLAG_ROUND_TF32, db_o, db_ru);
     RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;
 }
 
 extern "C" int ramnet_gru_ru_bwd(ramnet_handle *h, const float *drh, const float *hprev, const float *r, float *dzru,
-                                 float *dh, int64_t M, int C, int flags, void *stream) {
+                                 float *dh, float *db_ru, int64_t M, int C, int flags, void *stream) {
     RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && drh && hprev && r && dzru && dh && M > 0 && C % 4 == 0, "gru_ru_bwd: bad argument");
-    gru_ru_bwd_kernel<<<grid_for(h, M * (C / 4)), 256, 0, (cudaStream_t)stream>>>(drh, hprev, r, dzru, dh, M, C,
-                                                                                  flags & RAMNET_FLAG_ROUND_TF32);
+    RAMNET_CHECK_ARG(!db_ru || colsum_fusable(C), "gru_ru_bwd: the fused bias gradient needs 256 %% (C/4) == 0");
+    gru_ru_bwd_kernel<<<grid_for_colsum(h, M * (C / 4), db_ru != nullptr), 256, 0, (cudaStream_t)stream>>>(
+        drh, hprev, r, dzru, dh, M, C, flags & RAMNET_FLAG_ROUND_TF32, db_ru);
     RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;
 }
@@ -583,11 +678,17 @@ extern "C" int ramnet_head_conv_wgrad(ramnet_handle *h, const float *x_nchw, con
 }
 
 extern "C" int ramnet_lstm_bwd(ramnet_handle *h, const float *dh, const float *dc, const float *gates, const float *c_prev,
-                               const float *c_new, float *dz, float *dc_prev, int64_t M, int C, int flags, void *stream) {
+                               const float *c_new, float *dz, float *dc_prev, float *db, int64_t M, int C, int flags,
+                               void *stream) {
     RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && gates && c_prev && c_new && dz && dc_prev && (dh || dc) && M > 0 && C > 0, "lstm_bwd: bad argument");
-    lstm_bwd_kernel<<<grid_for(h, M * C), 256, 0, (cudaStream_t)stream>>>(dh, dc, gates, c_prev, c_new, dz, dc_prev, M, C,
-                                                                         flags & RAMNET_FLAG_ROUND_TF32);
+    const bool fuse = db && C <= 256 && 256 % C == 0;
+    lstm_bwd_kernel<<<grid_for_colsum(h, M * C, fuse), 256, 0, (cudaStream_t)stream>>>(dh, dc, gates, c_prev, c_new, dz, dc_prev, M, C,
+                                                                                      flags & RAMNET_FLAG_ROUND_TF32, fuse ? db : nullptr);
     RAMNET_LAUNCH_CHECK(h);
+    if (db && !fuse) {
+        launch_colsum(h, dz, M, 4 * C, db, (cudaStream_t)stream);
+        RAMNET_LAUNCH_CHECK(h);
+    }
     return RAMNET_OK;
 }

@@ -135,7 +135,7 @@ static int validate_desc(const ramnet_conv_desc *d) {
     RAMNET_CHECK_ARG(d->C0 > 0 && d->C0 % 16 == 0 && d->C1 >= 0 && d->C1 % 16 == 0,
                      "conv: channel counts C0=%d C1=%d must be multiples of 16", d->C0, d->C1);
     RAMNET_CHECK_ARG(d->Cout > 0 && d->Cout % 4 == 0, "conv: Cout=%d must be a positive multiple of 4", d->Cout);
-    RAMNET_CHECK_ARG(d->epilogue >= RAMNET_EPI_BIAS && d->epilogue <= RAMNET_EPI_BIAS_RELU_ADD, "conv: bad epilogue %d", d->epilogue);
+    RAMNET_CHECK_ARG(d->epilogue >= RAMNET_EPI_BIAS && d->epilogue <= RAMNET_EPI_BIAS_ADD, "conv: bad epilogue %d", d->epilogue);
     RAMNET_CHECK_ARG(d->mma_kind == RAMNET_MMA_FP32 || d->mma_kind == RAMNET_MMA_TF32, "conv: bad mma_kind %d", d->mma_kind);
     RAMNET_CHECK_ARG(!(d->flags & RAMNET_FLAG_HPACK) || d->mma_kind == RAMNET_MMA_TF32, "conv: RAMNET_FLAG_HPACK needs mma_kind=TF32");
     RAMNET_CHECK_ARG(!(d->flags & RAMNET_FLAG_UPCONV) || d->mma_kind == RAMNET_MMA_TF32, "conv: RAMNET_FLAG_UPCONV needs mma_kind=TF32");
@@ -161,8 +161,9 @@ extern "C" int ramnet_conv_fwd(ramnet_handle *h, const ramnet_conv_desc *d, cons
     RAMNET_CHECK_ARG((d->C1 == 0) == (x1 == nullptr), "conv_fwd: x1 and C1 disagree");
     switch (d->epilogue) {
         case RAMNET_EPI_BIAS_RES_RELU: RAMNET_CHECK_ARG(aux0, "conv_fwd: residual epilogue needs aux0"); break;
+        case RAMNET_EPI_BIAS_ADD:
         case RAMNET_EPI_BIAS_RELU_ADD:
-            RAMNET_CHECK_ARG(aux0, "conv_fwd: relu+add epilogue needs aux0");
+            RAMNET_CHECK_ARG(aux0, "conv_fwd: add epilogues need aux0");
             if (d->mma_kind != RAMNET_MMA_TF32)
                 return ramnet_set_error(RAMNET_EUNSUPPORTED, "conv_fwd: the relu+add epilogue is implemented on the TF32 path only");
             break;

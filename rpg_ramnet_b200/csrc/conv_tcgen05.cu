@@ -484,12 +484,18 @@ __device__ __forceinline__ void halo_commit(uint64_t *bar) {
     }
 }
 // epilogue -> MMA issuer hand-back of an accumulator buffer: the issuer lives in the leader CTA
+// RELAXED arrive: what the MMA warp must not overtake are this warp's tcgen05.ld reads of the accumulator, and those
+// have completed (tcgen05.wait::ld returned their data) before the arrive in program order.  The default / .release
+// forms order ALL of the warp's prior memory operations first -- SASS: MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in pair mode --
+// i.e. they wait until every global store of the item's epilogue has been acknowledged by L2 before the accumulator
+// buffer is handed back (ncu source view, round 2: ~9 % of all warp-stall samples of the gru0 kernel sat on that
+// sequence).  The stores need no ordering with the next item's MMAs.
 template <bool PAIR>
 __device__ __forceinline__ void halo_arrive_leader(uint64_t *bar) {
     if constexpr (PAIR) {
-        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_smem_addr(bar)) : "memory");
+        asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_smem_addr(bar)) : "memory");
     } else {
-        mbar_arrive(bar);
+        asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
     }
 }
 
@@ -1252,6 +1258,8 @@ struct WpGeom {
 struct WpBatch {
     WpGeom g[4];
     int n;
+    int accumulate;          // 1: the epilogue ADDS this launch's partial tiles to what the workspace holds (BPTT: the same
+                             // layer's weight gradient is produced once per pass; the split sum + scatter then runs once per step)
     long long part_stride;   // floats between the workspaces of consecutive problems
 };
 
@@ -1396,13 +1404,29 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_packed_kernel(const __gri
         for (int ci = 0; ci < nchunk; ci += 2) {
             tmem_ld_wait(ra);
             if (ci + 1 < nchunk) tmem_ld16_issue(lane_addr + (uint32_t)((ci + 1) * 16), rb);
+            if (batch.accumulate) {      // 16 coalesced 128-byte loads in flight, then add + store
+                float old[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) dst[(size_t)(ci * 16 + j) * 128] = __uint_as_float(ra[j]);
+                for (int j = 0; j < 16; ++j) old[j] = dst[(size_t)(ci * 16 + j) * 128];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) dst[(size_t)(ci * 16 + j) * 128] = old[j] + __uint_as_float(ra[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) dst[(size_t)(ci * 16 + j) * 128] = __uint_as_float(ra[j]);
+            }
             if (ci + 1 < nchunk) {
                 tmem_ld_wait(rb);
                 if (ci + 2 < nchunk) tmem_ld16_issue(lane_addr + (uint32_t)((ci + 2) * 16), ra);
+                if (batch.accumulate) {
+                    float old[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) dst[(size_t)((ci + 1) * 16 + j) * 128] = __uint_as_float(rb[j]);
+                    for (int j = 0; j < 16; ++j) old[j] = dst[(size_t)((ci + 1) * 16 + j) * 128];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) dst[(size_t)((ci + 1) * 16 + j) * 128] = old[j] + __uint_as_float(rb[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) dst[(size_t)((ci + 1) * 16 + j) * 128] = __uint_as_float(rb[j]);
+                }
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -2123,18 +2147,26 @@ bool plan_wgrad(const ramnet_handle *h, const ramnet_conv_desc *d, WgGeom *gp, i
     return true;
 }
 
+// mode (RAMNET_WGRAD_*): FULL = partial tiles + split sum + scatter into dw (+=); PARTIAL_FIRST / PARTIAL_ADD = only the
+// tensor-core kernel, whose epilogue overwrites / adds to the partial tiles in `workspace` (which the caller keeps for the
+// layer across the passes of a step); FINALIZE = only the split sum + scatter of what the workspace holds.
 int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz, const float *x0, const float *x1,
-                    float *dw, void *workspace, size_t workspace_bytes, cudaStream_t s, int head_cin) {
+                    float *dw, void *workspace, size_t workspace_bytes, cudaStream_t s, int head_cin, int mode) {
     if ((((uintptr_t)dz | (uintptr_t)x0 | (uintptr_t)x1 | (uintptr_t)workspace) & 15) != 0) return RAMNET_EUNSUPPORTED;
     WpBatch batch;
     int psplits, pgroups;
     if (plan_wgrad_batch(h, d, &batch, &psplits, &pgroups, head_cin)) {
+        batch.accumulate = mode == RAMNET_WGRAD_PARTIAL_ADD ? 1 : 0;
         const WpGeom &p = batch.g[0];
         const size_t need = (size_t)batch.n * batch.part_stride * sizeof(float);
         RAMNET_CHECK_ARG(workspace != nullptr && workspace_bytes >= need,
                          "conv_wgrad(tf32): workspace of %zu bytes required (ramnet_conv_wgrad_workspace_bytes)", need);
         CUtensorMap mdz, m0, m1;
         const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+        static const bool do_prof = getenv("RAMNET_PROF") != nullptr;      // debug only: synchronises and prints
+        static unsigned long long *pbuf = nullptr;
+        cudaEvent_t ev[3];
+        if (mode != RAMNET_WGRAD_FINALIZE) {
         {
             cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)d->N};
             cuuint64_t str[3] = {(cuuint64_t)d->Cout * 4, (cuuint64_t)p.W * d->Cout * 4, (cuuint64_t)p.H * p.W * d->Cout * 4};
@@ -2176,9 +2208,6 @@ int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz
                     d->H, d->W, d->C0, d->C1, d->Cout, d->ksize, d->stride, batch.n, p.m_from_x, pgroups, psplits, p.tiles_per_cta,
                     p.stages);
         dim3 grid((unsigned)psplits, (unsigned)pgroups, (unsigned)batch.n);
-        static const bool do_prof = getenv("RAMNET_PROF") != nullptr;      // debug only: synchronises and prints
-        static unsigned long long *pbuf = nullptr;
-        cudaEvent_t ev[3];
         if (do_prof) {
             if (!pbuf) cudaMalloc(&pbuf, 64);
             cudaMemsetAsync(pbuf, 0, 64, s);
@@ -2189,6 +2218,10 @@ int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz
         conv_wgrad_packed_kernel<<<grid, kThreads, smem, s>>>(mdz, m0, m1, batch, (float *)workspace);
         RAMNET_LAUNCH_CHECK(h);
         if (do_prof) cudaEventRecord(ev[1], s);
+        if (do_prof && mode != RAMNET_WGRAD_FULL) { cudaStreamSynchronize(s); for (auto &e : ev) cudaEventDestroy(e); }
+        }   // mode != FINALIZE
+        if (mode == RAMNET_WGRAD_PARTIAL_FIRST || mode == RAMNET_WGRAD_PARTIAL_ADD) return RAMNET_OK;
+        RAMNET_CHECK_ARG(dw != nullptr, "conv_wgrad(tf32): dw is NULL");
         const int64_t elems = (int64_t)pgroups * 128 * p.ncols;
         // few splits: summed inside the scatter kernel (one pass 1355 -> 1251 us on B200; RAMNET_WGRAD_FUSED_SUM=0 runs
         // the separate sum pass)
@@ -2209,7 +2242,7 @@ int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz
         wgrad_packed_scatter_kernel<<<cgrid, 1024, sc_smem, s>>>((const float *)workspace, dw, batch, pgroups,
                                                                  fused_sum ? psplits : 1);
         RAMNET_LAUNCH_CHECK(h);
-        if (do_prof) {
+        if (do_prof && mode == RAMNET_WGRAD_FULL) {
             cudaEventRecord(ev[2], s);
             unsigned long long hb[8];
             cudaMemcpyAsync(hb, pbuf, 64, cudaMemcpyDeviceToHost, s);
@@ -2228,7 +2261,7 @@ int conv_wgrad_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *dz
         }
         return RAMNET_OK;
     }
-    if (head_cin > 0) return RAMNET_EUNSUPPORTED;
+    if (head_cin > 0 || mode != RAMNET_WGRAD_FULL) return RAMNET_EUNSUPPORTED;      // the deferred modes exist for the tap-packed kernel only
     WgGeom g;
     int splits_i, groups;
     if (!plan_wgrad(h, d, &g, &splits_i, &groups)) return RAMNET_EUNSUPPORTED;
@@ -2468,8 +2501,9 @@ int conv_fwd_tf32_rect(ramnet_handle *h, const ramnet_conv_desc *d, const RectSp
     const bool halo_ok = want_hpack || plan_halo(h, d, rect, &hg);
     if (!halo_ok && rect)
         return ramnet_set_error(RAMNET_EUNSUPPORTED, "conv_fwd: no halo-kernel configuration for a rectangular / strided launch");
-    if (!halo_ok && d->epilogue == RAMNET_EPI_BIAS_RELU_PRED)
-        return ramnet_set_error(RAMNET_EUNSUPPORTED, "conv_fwd: no halo-kernel configuration for the fused prediction epilogue");
+    if (!halo_ok && (d->epilogue == RAMNET_EPI_BIAS_RELU_PRED || d->epilogue == RAMNET_EPI_BIAS_RELU_ADD ||
+                     d->epilogue == RAMNET_EPI_BIAS_ADD))
+        return ramnet_set_error(RAMNET_EUNSUPPORTED, "conv_fwd: no halo-kernel configuration for the fused prediction / add epilogues");
     if (halo_ok) {
         if (getenv("RAMNET_DEBUG"))
             fprintf(stderr, "[ramnet] halo plan s%d %dx%d C=%d+%d->%d k%d: tiles %dx%d HX=%d HY=%d BN=%d a_st=%d b_st=%d tpg=%d nbuf=%d items=%d pair=%d hpack=%d\n",
@@ -2523,6 +2557,7 @@ int conv_fwd_tf32_rect(ramnet_handle *h, const ramnet_conv_desc *d, const RectSp
             case RAMNET_EPI_LSTM: return launch_halo<RAMNET_EPI_LSTM>(h, m0, m1, mw, hg, ep, s);
             case RAMNET_EPI_BIAS_RELU_PRED: return launch_halo<RAMNET_EPI_BIAS_RELU_PRED>(h, m0, m1, mw, hg, ep, s);
             case RAMNET_EPI_BIAS_RELU_ADD: return launch_halo<RAMNET_EPI_BIAS_RELU_ADD>(h, m0, m1, mw, hg, ep, s);
+            case RAMNET_EPI_BIAS_ADD: return launch_halo<RAMNET_EPI_BIAS_ADD>(h, m0, m1, mw, hg, ep, s);
         }
     }
     TcGeom g;

@@ -11,7 +11,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (ConvDesc, EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RELU_ADD, EPI_BIAS_RELU_PRED, EPI_BIAS_RES_RELU, EPI_GRU_OUT,  # noqa
+from ._lib import (ConvDesc, EPI_BIAS, EPI_BIAS_ADD, EPI_BIAS_RELU, EPI_BIAS_RELU_ADD, EPI_BIAS_RELU_PRED, EPI_BIAS_RES_RELU, EPI_GRU_OUT,  # noqa
                    EPI_GRU_RU, EPI_LSTM, FLAG_HPACK, FLAG_ROUND_TF32, FLAG_UPCONV, MMA_FP32, MMA_TF32, check)
 
 
@@ -451,7 +451,91 @@ def conv_wgrad(dz, x0, x1, Cout, ksize, stride, dw, db, mma_kind=MMA_FP32):
         nws = lib.ramnet_conv_wgrad_workspace_bytes(_h(x0), ctypes.byref(d))
         ws = _workspace(x0.device, nws)
         check(lib.ramnet_conv_wgrad(_h(x0), ctypes.byref(d), _p(dz), _p(x0), _p(x1), _p(dw), _p(db), _p(ws), nws,
-                                    _stream(x0)))
+                                    _lib.WGRAD_FULL, _stream(x0)))
+
+
+class WgradAccumulator:
+    """Weight gradient of ONE layer accumulated over the passes of a training step (BPTT calls the layer's backward once
+    per pass): `add()` runs only the tensor-core kernel, whose epilogue writes (first call) or adds (later calls) its
+    partial tiles into a workspace this object owns; `finalize(dw)` runs the split sum + scatter ONCE and accumulates
+    into dw [Cout, C0+C1, k, k].  Built by `wgrad_accumulator()`, which returns None for shapes the tap-packed TF32
+    kernel does not cover (callers then use conv_wgrad per call)."""
+
+    def __init__(self, desc, nws, device, head=None):
+        self.desc, self.nws, self.head = desc, nws, head
+        self.ws = torch.empty(max(nws, 16), dtype=torch.uint8, device=device)
+        self.dirty = False
+        self.flops = 0.0
+
+    def add(self, dz, x0, x1=None):
+        lib, d = _lib.load(), self.desc
+        mode = _lib.WGRAD_PARTIAL_ADD if self.dirty else _lib.WGRAD_PARTIAL_FIRST
+        with _Prof('wgrad', self.flops, x0.device, tag=PROFILE is not None and f'wgrad-acc {d.H}x{d.W} {d.C0}+{d.C1}->{d.Cout}'):
+            if self.head is not None:
+                N, Cin, H, W, Cout = self.head
+                check(lib.ramnet_head_conv_wgrad_tc(_h(x0), _p(x0), _p(dz), None, None, N, Cin, H, W, Cout, _p(self.ws),
+                                                    self.nws, mode, _stream(x0)))
+            else:
+                check(lib.ramnet_conv_wgrad(_h(x0), ctypes.byref(d), _p(dz), _p(x0), _p(x1), None, None, _p(self.ws),
+                                            self.nws, mode, _stream(x0)))
+        self.dirty = True
+
+    def finalize(self, dw):
+        if not self.dirty:
+            return
+        lib, d = _lib.load(), self.desc
+        with _Prof('wgrad_finalize', 0.0, dw.device):
+            if self.head is not None:
+                N, Cin, H, W, Cout = self.head
+                check(lib.ramnet_head_conv_wgrad_tc(_h(dw), None, None, _p(dw), None, N, Cin, H, W, Cout, _p(self.ws),
+                                                    self.nws, _lib.WGRAD_FINALIZE, _stream(dw)))
+            else:
+                check(lib.ramnet_conv_wgrad(_h(dw), ctypes.byref(d), None, None, None, _p(dw), None, _p(self.ws), self.nws,
+                                            _lib.WGRAD_FINALIZE, _stream(dw)))
+        self.dirty = False
+
+
+def wgrad_accumulator(x0, x1, dz, Cout, ksize, stride, mma_kind):
+    """WgradAccumulator for the layer whose backward sees (dz, x0, x1) of these shapes, or None when unsupported."""
+    if mma_kind != MMA_TF32 or os.environ.get('RAMNET_WGRAD_DEFER', '1') == '0':
+        return None
+    N, C0, H, W = x0.shape
+    C1 = 0 if x1 is None else x1.shape[1]
+    d = ConvDesc(N, H, W, C0, C1, Cout, ksize, stride, 0, mma_kind, 0, 0)
+    lib = _lib.load()
+    nws = lib.ramnet_conv_wgrad_workspace_bytes(_h(x0), ctypes.byref(d))
+    if nws == 0:
+        return None
+    acc = WgradAccumulator(d, nws, x0.device)
+    acc.flops = 2.0 * dz.shape[0] * dz.shape[2] * dz.shape[3] * Cout * (C0 + C1) * ksize * ksize
+    # probe once: the deferred modes exist for the tap-packed kernel only
+    rc = lib.ramnet_conv_wgrad(_h(x0), ctypes.byref(d), _p(dz), _p(x0), _p(x1), None, None, _p(acc.ws), nws,
+                               _lib.WGRAD_PARTIAL_FIRST, _stream(x0))
+    if rc == _lib.RAMNET_EUNSUPPORTED:
+        return None
+    check(rc)
+    acc.dirty = True
+    return acc
+
+
+def head_wgrad_accumulator(xe, dz, Cin):
+    if os.environ.get('RAMNET_WGRAD_DEFER', '1') == '0':
+        return None
+    N, _, H, W = xe.shape
+    Cout = dz.shape[1]
+    lib = _lib.load()
+    nws = lib.ramnet_head_conv_wgrad_tc_workspace_bytes(_h(xe), N, Cin, H, W, Cout)
+    if nws == 0:
+        return None
+    acc = WgradAccumulator(ConvDesc(N, H, W, 32, 0, Cout, 5, 1, 0, MMA_TF32, 0, 0), nws, xe.device, head=(N, Cin, H, W, Cout))
+    acc.flops = 2.0 * N * H * W * Cout * Cin * 25
+    rc = lib.ramnet_head_conv_wgrad_tc(_h(xe), _p(xe), _p(dz), None, None, N, Cin, H, W, Cout, _p(acc.ws), nws,
+                                       _lib.WGRAD_PARTIAL_FIRST, _stream(xe))
+    if rc == _lib.RAMNET_EUNSUPPORTED:
+        return None
+    check(rc)
+    acc.dirty = True
+    return acc
 
 
 def head_conv_wgrad(x_nchw, dz, dw, db):
@@ -473,7 +557,7 @@ def head_conv_wgrad_tc(xe, dz, dw, db, Cin):
         nws = lib.ramnet_head_conv_wgrad_tc_workspace_bytes(_h(xe), N, Cin, H, W, Cout)
         ws = _workspace(xe.device, nws)
         check(lib.ramnet_head_conv_wgrad_tc(_h(xe), _p(xe), _p(dz), _p(dw), _p(db), N, Cin, H, W, Cout, _p(ws), nws,
-                                            _stream(xe)))
+                                            _lib.WGRAD_FULL, _stream(xe)))
 
 
 def zero_insert2x(x, Hout, Wout, skip=None):
@@ -486,27 +570,33 @@ def zero_insert2x(x, Hout, Wout, skip=None):
     return y
 
 
-def relu_bwd(dy, y, round_tf32=False):
+def relu_bwd(dy, y, round_tf32=False, db=None):
+    """dz = dy * (y > 0); db [C] (optional) += column sums of dz (the layer's bias gradient, fused)."""
     _check_nhwc(dy, 'relu_bwd dy')
     _check_nhwc(y, 'relu_bwd y')
     dz = empty_nhwc(*y.shape, y.device)
-    check(_lib.load().ramnet_relu_bwd(_h(y), _p(dy), _p(y), _p(dz), y.numel(), FLAG_ROUND_TF32 if round_tf32 else 0,
-                                      _stream(y)))
+    check(_lib.load().ramnet_relu_bwd(_h(y), _p(dy), _p(y), _p(dz), y.numel(), y.shape[1], _p(db),
+                                      FLAG_ROUND_TF32 if round_tf32 else 0, _stream(y)))
     return dz
 
 
-def gru_out_bwd(dhn, h, u, o, round_tf32=False):
+def colsum_fusable(C: int) -> bool:
+    """The pointwise adjoints can fold the bias gradient in when 256 % (C/4) == 0 (every shipped layer)."""
+    return C % 4 == 0 and C // 4 <= 256 and 256 % (C // 4) == 0
+
+
+def gru_out_bwd(dhn, h, u, o, round_tf32=False, db_o=None, db_ru=None):
     N, C, H, W = h.shape
     dzo, dh = empty_nhwc(N, C, H, W, h.device), empty_nhwc(N, C, H, W, h.device)
     dzru = empty_nhwc(N, 2 * C, H, W, h.device)
-    check(_lib.load().ramnet_gru_out_bwd(_h(h), _p(dhn), _p(h), _p(u), _p(o), _p(dzo), _p(dzru), _p(dh), N * H * W, C,
-                                         FLAG_ROUND_TF32 if round_tf32 else 0, _stream(h)))
+    check(_lib.load().ramnet_gru_out_bwd(_h(h), _p(dhn), _p(h), _p(u), _p(o), _p(dzo), _p(dzru), _p(dh), _p(db_o), _p(db_ru),
+                                         N * H * W, C, FLAG_ROUND_TF32 if round_tf32 else 0, _stream(h)))
     return dzo, dzru, dh
 
 
-def gru_ru_bwd(drh, h, r, dzru, dh, round_tf32=False):
+def gru_ru_bwd(drh, h, r, dzru, dh, round_tf32=False, db_ru=None):
     N, C, H, W = h.shape
-    check(_lib.load().ramnet_gru_ru_bwd(_h(h), _p(drh), _p(h), _p(r), _p(dzru), _p(dh), N * H * W, C,
+    check(_lib.load().ramnet_gru_ru_bwd(_h(h), _p(drh), _p(h), _p(r), _p(dzru), _p(dh), _p(db_ru), N * H * W, C,
                                         FLAG_ROUND_TF32 if round_tf32 else 0, _stream(h)))
 
 
@@ -530,12 +620,12 @@ def upsample2x_bwd(dy):
     return dx
 
 
-def lstm_bwd(dh, dc, gates, c_prev, c_new, round_tf32=False):
+def lstm_bwd(dh, dc, gates, c_prev, c_new, round_tf32=False, db=None):
     N, C, H, W = c_prev.shape
     dz = empty_nhwc(N, 4 * C, H, W, c_prev.device)
     dc_prev = empty_nhwc(N, C, H, W, c_prev.device)
     check(_lib.load().ramnet_lstm_bwd(_h(c_prev), _p(dh), _p(dc), _p(gates), _p(c_prev), _p(c_new), _p(dz), _p(dc_prev),
-                                      N * H * W, C, FLAG_ROUND_TF32 if round_tf32 else 0, _stream(c_prev)))
+                                      _p(db), N * H * W, C, FLAG_ROUND_TF32 if round_tf32 else 0, _stream(c_prev)))
     return dz, dc_prev
 
 
