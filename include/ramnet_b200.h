@@ -135,6 +135,17 @@ int ramnet_voxel_grid(ramnet_handle *h, const double *events, int64_t n, int bin
                       int height, float *grid, int32_t *oob_count, void *stream);
 /* Debug/parity twin: writes the un-accumulated vote stream instead of
  * scattering it (idx = -1 for a dropped vote). Arrays of length n. */
+/* Same result with two extensions.  (1) `workspace` (nullable; ramnet_voxel_grid_workspace_bytes bytes, 16-byte
+ * aligned): for large event counts the votes accumulate in a pixel-major [H*W][8] buffer where both votes of an event
+ * are one 128-bit vector reduction, then a second pass lays the grid out as [bins, H, W] (bins <= 8).  (2) `stats`
+ * (nullable, 3 doubles, zeroed by the callee): sum, sum of squares and count of the NON-ZERO voxels, gathered while the
+ * grid is produced; with RAMNET_VOXEL_NORMALIZE the grid is then normalised in place exactly as the loaders do
+ * (data_loader/event_dataset.py:144-151, dataset_asynchronous.py:300-308): scatter -> normalise in one call. */
+#define RAMNET_VOXEL_NORMALIZE 1
+size_t ramnet_voxel_grid_workspace_bytes(int num_bins, int width, int height);
+int ramnet_voxel_grid_ex(ramnet_handle *h, const double *events, int64_t n, int num_bins, int width, int height,
+                         float *grid, int32_t *oob_count, void *workspace, size_t workspace_bytes, double *stats,
+                         int flags, void *stream);
 int ramnet_voxel_votes(ramnet_handle *h, const double *events, int64_t n, int bins, int width,
                        int height, int64_t *idx_left, float *val_left, int64_t *idx_right,
                        float *val_right, void *stream);

@@ -37,6 +37,9 @@ SIGNATURES = {
     'ramnet_sm_count': (c_int, [c_void_p]),
     'ramnet_launch_count': (c_int64, [c_void_p]),
     'ramnet_voxel_grid': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'ramnet_voxel_grid_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'ramnet_voxel_grid_ex': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+                                     c_void_p, c_int, c_void_p]),
     'ramnet_voxel_votes': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
     'ramnet_head_conv': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -21,6 +21,8 @@ struct Vote {
     int64_t il, ir;  // flat voxel index or -1
     float vl, vr;
     bool oob;
+    int64_t pix;     // x + y * width
+    int ti;          // left time bin
 };
 
 __device__ __forceinline__ Vote event_vote(const double *__restrict__ ev, int64_t i, double t0, double dT, int bins,
@@ -42,6 +44,8 @@ __device__ __forceinline__ Vote event_vote(const double *__restrict__ ev, int64_
     const bool inb = (x >= 0) & (x < width) & (y >= 0) & (y < height) & (ti >= 0);
     v.oob = !inb;
     const int64_t base = x + y * width;
+    v.pix = base;
+    v.ti = (int)(ti < 0 ? -1 : (ti > 0x7fffffff ? 0x7fffffff : ti));
     v.il = (inb && ti < bins) ? base + ti * plane : -1;            // :107-109
     v.ir = (inb && ti + 1 < bins) ? base + (ti + 1) * plane : -1;  // :111-113
     return v;
@@ -76,6 +80,121 @@ __global__ void __launch_bounds__(256) voxel_votes_kernel(const double *__restri
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const Vote v = event_vote(ev, i, t0, dT, bins, width, height);
         il[i] = v.il; vl[i] = v.vl; ir[i] = v.ir; vr[i] = v.vr;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Packed accumulation for large event counts.  At 1e7 events the kernel above is bound by the ~2e7 fp32 reductions
+// the L2 has to resolve (147 us against a 49 us HBM floor, profiles/r01_voxel_bench.json), not by the event stream.
+// Both votes of an event go to the SAME pixel, time bins ti and ti + 1, so with the bins of a pixel adjacent in memory
+// (accumulator [H*W][8] floats, one 32-byte sector per pixel) they are ONE vector reduction
+// (red.global.add.v4.f32 -> REDG.E.ADD.F32x4: slots ti%4, ti%4+1 carry the votes, the others +0.0) unless the pair
+// straddles the two quads (ti % 4 == 3), which takes the two scalar reductions.  A second pass transposes the
+// accumulator into the reference's [bins, H, W] layout and can fold in the statistics of the non-zero voxels that the
+// loaders' normalisation needs (event_dataset.py:144-151), so that "scatter -> normalise" never re-reads the grid for them.
+// Per-voxel accumulation order differs from the kernel above only in which votes are summed first: same tolerance
+// (<= 1 ulp per accumulation, fp32 atomics reorder sums either way), indices bit-exact.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(256) voxel_grid_packed_kernel(const double *__restrict__ ev, int64_t n, int bins, int width,
+                                                                int height, float *__restrict__ acc,
+                                                                int32_t *__restrict__ oob_count) {
+    const double t0 = __ldg(ev);
+    double dT = __dsub_rn(__ldg(ev + 4 * (n - 1)), t0);
+    if (dT == 0.0) dT = 1.0;
+    int oob = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const Vote v = event_vote(ev, i, t0, dT, bins, width, height);
+        oob += v.oob;
+        if (v.il < 0 && v.ir < 0) continue;
+        float *cell = acc + v.pix * 8;
+        const int j = v.ti & 3;
+        if (v.il >= 0 && v.ir >= 0 && j != 3) {
+            float *quad = cell + (v.ti & ~3);
+            if (j == 0) red_add_v4(quad, v.vl, v.vr, 0.f, 0.f);
+            else if (j == 1) red_add_v4(quad, 0.f, v.vl, v.vr, 0.f);
+            else red_add_v4(quad, 0.f, 0.f, v.vl, v.vr);
+        } else {
+            if (v.il >= 0) red_add_f32(cell + v.ti, v.vl);
+            if (v.ir >= 0) red_add_f32(cell + v.ti + 1, v.vr);
+        }
+    }
+    if (oob_count != nullptr && oob) atomicAdd(oob_count, oob);
+}
+
+// acc [H*W][8] -> grid [bins][H*W]; stats (nullable) += (sum, sum of squares, count) of the non-zero voxels
+__global__ void __launch_bounds__(256) voxel_unpack_kernel(const float4 *__restrict__ acc, float *__restrict__ grid, int bins,
+                                                           int64_t hw, double *__restrict__ stats) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < hw; p += (int64_t)gridDim.x * blockDim.x) {
+        const float4 a = acc[2 * p], b = acc[2 * p + 1];
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < bins) {
+                grid[(int64_t)k * hw + p] = v[k];
+                if (v[k] != 0.f) { s0 += (double)v[k]; s1 += (double)v[k] * (double)v[k]; s2 += 1.0; }
+            }
+    }
+    if (stats != nullptr) {
+        __shared__ double sh[3][8];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane == 0) { sh[0][warp] = s0; sh[1][warp] = s1; sh[2][warp] = s2; }
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            double t = 0.0;
+            for (int w = 0; w < 8; ++w) t += sh[threadIdx.x][w];
+            atomicAdd(stats + threadIdx.x, t);
+        }
+    }
+}
+
+// stats of the non-zero voxels of a finished [bins*H*W] grid (path without the packed accumulator)
+__global__ void __launch_bounds__(256) voxel_nz_stats_kernel(const float *__restrict__ grid, int64_t n, double *__restrict__ stats) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float x = grid[i];
+        if (x != 0.f) { s0 += (double)x; s1 += (double)x * (double)x; s2 += 1.0; }
+    }
+    __shared__ double sh[3][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) { sh[0][warp] = s0; sh[1][warp] = s1; sh[2][warp] = s2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sh[threadIdx.x][w];
+        atomicAdd(stats + threadIdx.x, t);
+    }
+}
+
+// (x - mean) / stddev on the non-zero voxels, nothing when there are none or the stddev is 0 (event_dataset.py:144-151)
+__global__ void __launch_bounds__(256) voxel_apply_norm_kernel(float *__restrict__ grid, int64_t n, const double *__restrict__ stats) {
+    const double cnt = stats[2];
+    if (!(cnt > 0.0)) return;
+    const double mean = stats[0] / cnt;
+    double var = stats[1] / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double sd = sqrt(var);
+    if (!(sd > 0.0)) return;
+    const float m = (float)mean, inv = (float)(1.0 / sd);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float x = grid[i];
+        if (x != 0.f) grid[i] = (x - m) * inv;
     }
 }
 
@@ -119,5 +238,55 @@ extern "C" int ramnet_voxel_votes(ramnet_handle *h, const double *events, int64_
     voxel_votes_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(events, n, bins, width, height, idx_left, val_left,
                                                                 idx_right, val_right);
     RAMNET_LAUNCH_CHECK(h);
+    return RAMNET_OK;
+}
+
+extern "C" size_t ramnet_voxel_grid_workspace_bytes(int bins, int width, int height) {
+    return (bins > 0 && bins <= 8 && width > 0 && height > 0) ? (size_t)width * height * 8 * sizeof(float) : 0;
+}
+
+// events -> grid (+ optional statistics of the non-zero voxels, + optional normalisation) in one call.
+// workspace (nullable, ramnet_voxel_grid_workspace_bytes): enables the packed accumulator for n >= packed_min events.
+extern "C" int ramnet_voxel_grid_ex(ramnet_handle *h, const double *events, int64_t n, int bins, int width, int height,
+                                    float *grid, int32_t *oob_count, void *workspace, size_t workspace_bytes,
+                                    double *stats, int flags, void *stream) {
+    RAMNET_DEVICE_GUARD(h);
+    int rc = check_args(h, events, n, bins, width, height);
+    if (rc) return rc;
+    RAMNET_CHECK_ARG(grid != nullptr, "voxel_grid: grid is NULL");
+    RAMNET_CHECK_ARG(!(flags & RAMNET_VOXEL_NORMALIZE) || stats, "voxel_grid: normalisation needs the stats buffer (3 doubles)");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t hw = (int64_t)width * height, total = hw * bins;
+    if (oob_count) RAMNET_CUDA(cudaMemsetAsync(oob_count, 0, sizeof(int32_t), s));
+    if (stats) RAMNET_CUDA(cudaMemsetAsync(stats, 0, 3 * sizeof(double), s));
+    static const int64_t packed_min = [] { const char *e = getenv("RAMNET_VOXEL_PACKED_MIN"); return e ? atoll(e) : 1500000ll; }();
+    const size_t need = ramnet_voxel_grid_workspace_bytes(bins, width, height);
+    const bool packed = workspace != nullptr && need > 0 && workspace_bytes >= need && n >= packed_min &&
+                        (((uintptr_t)workspace) & 15) == 0;
+    const int pw_blocks = (int)imin64((total + 255) / 256, (int64_t)h->sm_count * 8);
+    if (packed) {
+        RAMNET_CUDA(cudaMemsetAsync(workspace, 0, need, s));
+        voxel_grid_packed_kernel<<<(int)imin64((n + 255) / 256, (int64_t)h->sm_count * 8), 256, 0, s>>>(
+            events, n, bins, width, height, (float *)workspace, oob_count);
+        RAMNET_LAUNCH_CHECK(h);
+        voxel_unpack_kernel<<<(int)imin64((hw + 255) / 256, (int64_t)h->sm_count * 8), 256, 0, s>>>(
+            (const float4 *)workspace, grid, bins, hw, stats);
+        RAMNET_LAUNCH_CHECK(h);
+    } else {
+        RAMNET_CUDA(cudaMemsetAsync(grid, 0, sizeof(float) * (size_t)total, s));
+        if (n > 0) {
+            voxel_grid_kernel<<<(int)imin64((n + 255) / 256, (int64_t)h->sm_count * 8), 256, 0, s>>>(events, n, bins, width,
+                                                                                                    height, grid, oob_count);
+            RAMNET_LAUNCH_CHECK(h);
+        }
+        if (stats && n > 0) {
+            voxel_nz_stats_kernel<<<pw_blocks, 256, 0, s>>>(grid, total, stats);
+            RAMNET_LAUNCH_CHECK(h);
+        }
+    }
+    if ((flags & RAMNET_VOXEL_NORMALIZE) && n > 0) {
+        voxel_apply_norm_kernel<<<pw_blocks, 256, 0, s>>>(grid, total, stats);
+        RAMNET_LAUNCH_CHECK(h);
+    }
     return RAMNET_OK;
 }

@@ -86,6 +86,24 @@ def voxel_grid(events: torch.Tensor, num_bins: int, width: int, height: int,
     return grid
 
 
+def voxel_grid_ex(events: torch.Tensor, num_bins: int, width: int, height: int, normalize: bool = False,
+                  want_stats: bool = False):
+    """events -> [num_bins, height, width] fp32 through ramnet_voxel_grid_ex: packed accumulation for large event
+    counts, optional fused statistics of the non-zero voxels / in-place normalisation (event_dataset.py:144-151).
+    Returns grid or (grid, stats[3] float64: sum, sum of squares, count of non-zero voxels)."""
+    if events.dtype != torch.float64 or events.dim() != 2 or events.shape[1] != 4 or not events.is_contiguous():
+        raise _lib.RamnetError('voxel_grid: events must be a contiguous [n,4] float64 tensor')
+    dev = events.device
+    lib = _lib.load()
+    grid = torch.empty((num_bins, height, width), dtype=torch.float32, device=dev)
+    nws = lib.ramnet_voxel_grid_workspace_bytes(num_bins, width, height)
+    ws = _workspace(dev, nws) if nws and events.shape[0] >= 1000000 else None
+    stats = torch.empty(3, dtype=torch.float64, device=dev) if (normalize or want_stats) else None
+    check(lib.ramnet_voxel_grid_ex(_h(events), _p(events), events.shape[0], num_bins, width, height, _p(grid), None, _p(ws),
+                                   nws if ws is not None else 0, _p(stats), 1 if normalize else 0, _stream(events)))
+    return (grid, stats) if want_stats else grid
+
+
 def voxel_votes(events: torch.Tensor, num_bins: int, width: int, height: int):
     n = events.shape[0]
     dev = events.device

@@ -11,7 +11,9 @@ import torch
 from .. import ops
 
 
-def events_to_voxel_grid(events, num_bins, width, height, device=None):
+def events_to_voxel_grid(events, num_bins, width, height, device=None, normalize=False):
+    """`normalize=True` (extension): also applies the loaders' normalisation (mean / stddev of the non-zero voxels,
+    data_loader/event_dataset.py:144-151) in the same call — the statistics are gathered while the grid is written."""
     assert events.shape[1] == 4
     assert num_bins > 0
     assert width > 0
@@ -23,7 +25,7 @@ def events_to_voxel_grid(events, num_bins, width, height, device=None):
     if device is None:
         device = ev.device if ev.is_cuda else torch.device('cuda', torch.cuda.current_device())
     ev = ev.to(device=device, dtype=torch.float64, non_blocking=True).contiguous()
-    return ops.voxel_grid(ev, int(num_bins), int(width), int(height))
+    return ops.voxel_grid_ex(ev, int(num_bins), int(width), int(height), normalize=bool(normalize))
 
 
 def events_to_voxel_grid_pytorch(events, num_bins, width, height, device):

@@ -82,6 +82,51 @@ def test_voxel_grid_seeded(n, hot):
     assert np.all(np.abs(out - ref) <= tol)
 
 
+@pytest.mark.parametrize('n,hot', [(2_000_000, False), (2_000_000, True)])
+def test_voxel_grid_packed_accumulator_vs_oracle(n, hot):
+    """>= 1.5e6 events take the packed path of ramnet_voxel_grid_ex (pixel-major accumulator, both votes of an event in
+    one 128-bit vector reduction, then a transpose into [bins, H, W]): same indices, sums to accumulation order."""
+    from rpg_ramnet_b200 import ops
+    W, H, B = 512, 256, 5
+    ev = O.synth_events(n, W, H, seed=11, hot=hot)
+    evd = torch.from_numpy(ev).to(dev())
+    out, stats = ops.voxel_grid_ex(evd, B, W, H, want_stats=True)
+    out = out.cpu().numpy()
+    ref = O.voxel_grid(ev, B, W, H)
+    cnt = np.zeros(B * H * W)
+    il, _, ir, _ = O.voxel_grid_votes(ev, B, W, H)
+    np.add.at(cnt, il[il >= 0], 1)
+    np.add.at(cnt, ir[ir >= 0], 1)
+    cnt = cnt.reshape(B, H, W)
+    tol = 1.2e-7 * np.maximum(cnt, 1) ** 1.5 * 2
+    assert np.all(np.abs(out - ref) <= tol)
+    assert np.array_equal(out[cnt == 0], np.zeros_like(out[cnt == 0]))
+    # the direct kernel (small-n path) on the same events agrees to accumulation order as well
+    direct = ops.voxel_grid(evd, B, W, H).cpu().numpy()
+    assert np.all(np.abs(out - direct) <= 2 * tol)
+    # fused statistics of the non-zero voxels
+    nz = out[out != 0].astype(np.float64)
+    st = stats.cpu().numpy()
+    assert st[2] == nz.size
+    np.testing.assert_allclose(st[:2], [nz.sum(), (nz ** 2).sum()], rtol=1e-9)
+
+
+@pytest.mark.parametrize('n', [50_000, 2_000_000])
+def test_voxel_grid_scatter_then_normalise_in_one_call(n):
+    """events -> grid -> loaders' normalisation (event_dataset.py:144-151) in one C call, both paths,
+    against the numpy oracle of the two reference steps."""
+    import rpg_ramnet_b200 as R
+    from oracle import dataio_oracle as D
+    W, H, B = 512, 256, 5
+    ev = O.synth_events(n, W, H, seed=13)
+    out = R.events_to_voxel_grid(ev, B, W, H, normalize=True).cpu().numpy()
+    ref = D.normalize_voxel_grid(O.voxel_grid(ev, B, W, H))
+    assert np.array_equal(out == 0, ref == 0)
+    np.testing.assert_allclose(out, ref, rtol=2e-5, atol=2e-5)
+    nz = out[out != 0].astype(np.float64)
+    assert abs(nz.mean()) <= 1e-4 and abs(nz.std() - 1.0) <= 1e-4
+
+
 def test_voxel_grid_full_size_properties():
     """BASELINE config 5 at 10M events: size-independent properties instead of a CPU replay."""
     import rpg_ramnet_b200 as R
