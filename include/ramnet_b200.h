@@ -276,8 +276,9 @@ int ramnet_conv_dgrad_s2(ramnet_handle *h, const float *dz, const float *w_packe
                          int W, int Cout, int ci_count, int ksize, int flags, void *stream);
 /* y[n, 2h, 2w, :] = x[n, h, w, :] (+ skip), zeros elsewhere: input of a stride-2 conv's data gradient and of the
  * TransposedConvLayer decoder (submodules.py:38-66; skip = statenet.py:306-308's skip sum). */
-int ramnet_zero_insert2x(ramnet_handle *h, const float *x, const float *skip, float *y, int N, int H, int W, int C,
-                         int Hout, int Wout, void *stream);
+int ramnet_zero_insert2x(ramnet_handle *h, const float *x, const float *skip, float *y,
+                         float *sum_out /* nullable: dense x + skip [N,H,W,C] */, int N, int H, int W, int C, int Hout,
+                         int Wout, void *stream);
 /* dz = dy * (y > 0).  flags & RAMNET_FLAG_ROUND_TF32 (here and in the GRU adjoints): round the dz outputs to TF32
  * so that the tcgen05 dgrad / wgrad GEMMs that consume them truncate nothing. */
 /* db (nullable, [C]) here and in the gate adjoints: the bias gradient db[c] += sum_pixels dz[., c] fused into the same
@@ -352,6 +353,16 @@ int ramnet_adam_step(ramnet_handle *h, float *p, const float *g, float *m, float
 int ramnet_adam_step_dev(ramnet_handle *h, float *p, const float *g, float *m, float *v, int64_t n, double lr,
                          double beta1, double beta2, double eps, double weight_decay, int *step_counter,
                          int increment, void *stream);
+
+/* ---- §8f-4  test.py output stage ------------------------------------------- *
+ * Replaces the per-map host work of RAM_Net/test.py:259-360,365-379 for N maps [N, 1, H, W] (hw = H*W): grey (nullable,
+ * [N, hw] uint8) = cv2.imwrite's 8-bit conversion of depth * 255; bgr (nullable, [N, hw, 3] uint8) = make_colormap
+ * (test.py:31-38) through the caller's 256 x 3 RGB LUT (the reference's matplotlib color mapper sampled at i/255);
+ * scale_sums (nullable, [N, 2] doubles, needs target) = (sum p t, sum p p) in metric space, p = clip * exp(reg (d - 1))
+ * (test.py:370-376).  scratch: N * 4 uint32. */
+int ramnet_depth_output(ramnet_handle *h, const float *depth, const float *target, int N, int64_t hw,
+                        const float *lut_rgb256, unsigned char *grey, unsigned char *bgr, double *scale_sums,
+                        float reg_factor, float clip_distance, unsigned *scratch, void *stream);
 
 /* ---- measurement utility (not on the path) ---------------------------------- *
  * Live ceiling of the tensor pipe the convolutions use: tcgen05.mma kind::tf32 128x256x8 issued back to back from

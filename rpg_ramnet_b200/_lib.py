@@ -71,8 +71,8 @@ SIGNATURES = {
     'ramnet_pack_weights_dgrad_s2': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'ramnet_conv_dgrad_s2': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p]),
-    'ramnet_zero_insert2x': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
-                                     c_void_p]),
+    'ramnet_zero_insert2x': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                     c_int, c_void_p]),
     'ramnet_relu_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p]),
     'ramnet_gru_out_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
@@ -102,6 +102,8 @@ SIGNATURES = {
     'ramnet_msg_sobel_preview': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'ramnet_adam_step_dev': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double,
                                      c_double, c_double, c_double, c_void_p, c_int, c_void_p]),
+    'ramnet_depth_output': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_float, c_float, c_void_p, c_void_p]),
     'ramnet_tf32_pipe_rate': (c_int, [c_void_p, POINTER(c_double), POINTER(c_double)]),
     'ramnet_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double,
                                  c_double, c_double, c_double, c_int, c_void_p]),

@@ -341,6 +341,40 @@ class LstmFn(torch.autograd.Function):
         return dx, dh, (dc if ctx.needs_input_grad[2] else None), None, None, None, None
 
 
+class TransposedConvFn(torch.autograd.Function):
+    """TransposedConvLayer.forward (submodules.py:38-66, norm-free): relu(ConvTranspose2d(k, stride 2, padding k//2,
+    output_padding 1)(x + skip) + b).  A transposed convolution is the data gradient of the stride-2 convolution that
+    shares its weight tensor W [Cin, Cout, k, k] (nn.Conv2d layout of a Cout -> Cin conv), so
+      forward  = zero insertion + the stride-1 kernel on tap-flipped, channel-transposed weights,
+      d input  = that stride-2 convolution applied to dZ (the forward kernel, plain packing of W),
+      d weight = the stride-2 conv's weight gradient with the roles swapped: "dZ" operand = x + skip, "X" operand = dZ."""
+
+    @staticmethod
+    def forward(ctx, x, skip, weight, bias, packed_w, kind):
+        Cin, Cout, k, _ = weight.shape
+        N, _, H, W = x.shape
+        up, xs = ops.zero_insert2x(x, 2 * H, 2 * W, skip=skip, want_sum=True)
+        y = ops.conv_fwd(up, None, packed_w, None if bias is None else bias.detach(), Cout, k, 1, ops.EPI_BIAS_RELU, kind)
+        ctx.save_for_backward(xs, y)
+        ctx.weight, ctx.bias, ctx.kind, ctx.has_skip = weight, bias, kind, skip is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xs, y = ctx.saved_tensors
+        weight, bias, kind = ctx.weight, ctx.bias, ctx.kind
+        Cin, Cout, k, _ = weight.shape
+        dz = ops.relu_bwd(_nhwc(dy), y, round_tf32=(kind == ops.MMA_TF32), db=_bias_sink(bias, Cout))
+        _bias_fallback(bias, dz)
+        _weight_grad([(weight, 0, Cin)], xs, dz, None, Cin, k, 2, kind)
+        dx = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            wp = _cached_pack(weight, ('tconv_dx', kind), lambda: ops.pack_weights(weight, kind))
+            dx = ops.conv_fwd(dz, None, wp, None, Cin, k, 2, ops.EPI_BIAS, kind)
+        return (dx if ctx.needs_input_grad[0] else None, dx if (ctx.has_skip and ctx.needs_input_grad[1]) else None,
+                None, None, None, None)
+
+
 class UpsampleAddFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, skip, round_tf32):

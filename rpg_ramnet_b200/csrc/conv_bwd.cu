@@ -146,8 +146,8 @@ static void launch_colsum(const ramnet_handle *h, const float *dz, int64_t M, in
 
 // y[n, 2h, 2w, c] = x[n, h, w, c], zeros elsewhere (the input of a stride-2 conv's data gradient)
 __global__ void __launch_bounds__(256) zero_insert_kernel(const float4 *__restrict__ x, const float4 *__restrict__ skip,
-                                                          float4 *__restrict__ y, int N, int H, int W, int C4, int Hout,
-                                                          int Wout) {
+                                                          float4 *__restrict__ y, float4 *__restrict__ sum_out, int N, int H,
+                                                          int W, int C4, int Hout, int Wout) {
     const int64_t total = (int64_t)N * Hout * Wout * C4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % C4);
@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(256) zero_insert_kernel(const float4 *__restri
                 const float4 sv = skip[o];
                 v.x += sv.x; v.y += sv.y; v.z += sv.z; v.w += sv.w;
             }
+            if (sum_out) sum_out[o] = v;       // the dense x + skip (training: the operand of the weight gradient)
         }
         y[i] = v;
     }
@@ -578,13 +579,13 @@ extern "C" int ramnet_conv_wgrad(ramnet_handle *h, const ramnet_conv_desc *d, co
     return RAMNET_OK;
 }
 
-extern "C" int ramnet_zero_insert2x(ramnet_handle *h, const float *x, const float *skip, float *y, int N, int H, int W,
-                                    int C, int Hout, int Wout, void *stream) {
+extern "C" int ramnet_zero_insert2x(ramnet_handle *h, const float *x, const float *skip, float *y, float *sum_out, int N,
+                                    int H, int W, int C, int Hout, int Wout, void *stream) {
     RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && x && y && C % 4 == 0 && Hout >= 2 * H - 1 && Wout >= 2 * W - 1, "zero_insert2x: bad argument");
     const int64_t total = (int64_t)N * Hout * Wout * (C / 4);
-    zero_insert_kernel<<<grid_for(h, total), 256, 0, (cudaStream_t)stream>>>((const float4 *)x, (const float4 *)skip, (float4 *)y, N, H, W, C / 4,
-                                                                            Hout, Wout);
+    zero_insert_kernel<<<grid_for(h, total), 256, 0, (cudaStream_t)stream>>>((const float4 *)x, (const float4 *)skip, (float4 *)y,
+                                                                            (float4 *)sum_out, N, H, W, C / 4, Hout, Wout);
     RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;
 }

@@ -275,8 +275,6 @@ def transposed_conv_layer(cache, key, tconv, kind, x, skip=None, norm_mod=None, 
     + bias + ReLU.  A transposed convolution IS the data gradient of the stride-2 convolution with the same weight
     tensor, so it runs as zero-insertion + the forward tensor-core kernel on tap-flipped, channel-transposed weights."""
     w = tconv.weight                      # [Cin, Cout, k, k] == nn.Conv2d layout of the conv it is the adjoint of
-    if needs_grad(x, skip, w, tconv.bias):
-        raise RamnetError('training with use_upsample_conv=False (TransposedConvLayer) is not implemented')
     if norm_kind in ('BN', 'IN') and norm_mod is not None:
         raise RamnetError('TransposedConvLayer with BatchNorm/InstanceNorm is not implemented')
     if tuple(tconv.stride) != (2, 2) or tuple(tconv.output_padding) != (1, 1) or \
@@ -291,6 +289,9 @@ def transposed_conv_layer(cache, key, tconv, kind, x, skip=None, norm_mod=None, 
         p.Cout, p.ksize, p.stride = Cout, w.shape[2], 1
         return p
     p = cache.get(key, [w, tconv.bias], (kind, 'tconv'), build)
+    if needs_grad(x, skip, w, tconv.bias):
+        from .autograd import TransposedConvFn
+        return TransposedConvFn.apply(x, skip, w, tconv.bias, p.w, kind)
     N, _, H, W = x.shape
     up = ops.zero_insert2x(x, 2 * H, 2 * W, skip=skip)      # skip sum fused into the zero insertion
     return ops.conv_fwd(up, None, p.w, p.b, Cout, p.ksize, 1, ops.EPI_BIAS_RELU, kind)

@@ -578,14 +578,16 @@ def head_conv_wgrad_tc(xe, dz, dw, db, Cin):
                                             _lib.WGRAD_FULL, _stream(xe)))
 
 
-def zero_insert2x(x, Hout, Wout, skip=None):
+def zero_insert2x(x, Hout, Wout, skip=None, want_sum=False):
+    """y[n, 2h, 2w] = x[n, h, w] (+ skip), zeros elsewhere; `want_sum`: also return the dense x + skip."""
     _check_nhwc(x, 'zero_insert2x x')
     N, C, H, W = x.shape
     y = empty_nhwc(N, C, Hout, Wout, x.device)
     if skip is not None:
         _check_nhwc(skip, 'zero_insert2x skip')
-    check(_lib.load().ramnet_zero_insert2x(_h(x), _p(x), _p(skip), _p(y), N, H, W, C, Hout, Wout, _stream(x)))
-    return y
+    xs = empty_nhwc(N, C, H, W, x.device) if want_sum else None
+    check(_lib.load().ramnet_zero_insert2x(_h(x), _p(x), _p(skip), _p(y), _p(xs), N, H, W, C, Hout, Wout, _stream(x)))
+    return (y, xs) if want_sum else y
 
 
 def relu_bwd(dy, y, round_tf32=False, db=None):

@@ -227,3 +227,34 @@ def test_graph_runner_rejects_stale_states():
         with pytest.raises(R.RamnetError):
             model(seq[2], old, lstm)
         model(seq[2], s1['image'], lstm)                    # the latest states are fine
+
+
+def test_inference_output_stage_matches_test_py_restatement():
+    """grey / colour-map PNG payloads and the metric-space scale of test.py:259-290,365-379 produced on
+    the device (ramnet_depth_output) vs the numpy restatement of those lines (oracle/dataio_oracle.py)."""
+    from oracle import dataio_oracle as D
+    from rpg_ramnet_b200.utils.inference_output import colormap_lut, depth_outputs
+    g = torch.Generator().manual_seed(21)
+    pred = torch.rand(3, 1, 64, 96, generator=g)
+    pred[1] = 0.37                                    # constant map: max - min == 0
+    gt = torch.rand(3, 1, 64, 96, generator=g)
+    gt[2, :, 5:20, 7:30] = float('nan')               # GT with NaN: make_colormap collapses to a constant image
+    lut = colormap_lut()
+    reg, clip = 3.70378, 80.0
+    grey, bgr, scale = depth_outputs(pred.to(dev()), lut=lut, target=gt.to(dev()), reg_factor=reg, clip_distance=clip)
+    grey_gt, bgr_gt, _ = depth_outputs(gt.to(dev()), lut=lut)
+    for n in range(3):
+        want_grey = D.grey_png_payload(pred[n].numpy())
+        got = grey[n].cpu().numpy()
+        assert np.abs(got.astype(int) - want_grey.astype(int)).max() <= 1 and (got != want_grey).mean() <= 1e-3
+        for img, out in ((pred[n].numpy(), bgr[n]), (gt[n].numpy(), bgr_gt[n])):
+            want = D.make_colormap_payload(img, lut)
+            o = out.cpu().numpy()
+            assert o.shape == want.shape
+            # a LUT index may differ by one where x * 256 sits on an integer boundary (fp32 division order)
+            assert (np.abs(o.astype(int) - want.astype(int)).max(axis=-1) > 3).mean() <= 2e-3
+        if n < 2:
+            want_scale = D.metric_scale(pred[n, 0].numpy(), gt[n, 0].numpy(), reg, clip)
+            assert abs(float(scale[n]) - float(want_scale)) <= 1e-5 * abs(float(want_scale))
+    assert torch.isnan(scale[2])                       # NaN in the target propagates, as in the reference
+    assert float(bgr_gt[2].reshape(-1, 3).float().std(0).max()) == 0.0      # one colour for the NaN-carrying ground truth

@@ -439,3 +439,40 @@ def test_tf32_adam_trajectory_three_steps_vs_fp32_oracle():
     assert moved >= 2.5 * lr                      # the steps really happened
     assert worst <= 2 * 3 * lr * 1.05, worst
     assert rel <= 0.25, rel                       # measured on B200: 0.15
+
+
+@pytest.mark.parametrize('kind', KINDS)
+def test_transposed_conv_decoder_trains(kind):
+    """use_upsample_conv=False (TransposedConvLayer decoders, submodules.py:38-66, statenet.py:81-82) through training:
+    loss and every parameter gradient of one timestep against torch autograd on the CPU oracle (which calls
+    F.conv_transpose2d as the reference does)."""
+    import rpg_ramnet_b200 as R
+    g, meta = np.load(os.path.join(GOLDEN, 'model_transposed.npz')), None
+    meta = json.loads(str(g['meta']))
+    meta = dict(meta, H=32, W=48, B=2, L=1)
+    model, cfg = build_product_model(meta, mma_kind=kind)
+    assert cfg.get('use_upsample_conv') is False
+    model.train().to('cuda:0')
+    seq = O.synth_sequence(2, 32, 48, 1, cfg.get('every_x_rgb_frame', 1), seed=9, with_targets=True)
+    K = cfg.get('every_x_rgb_frame', 1)
+    lstm = {f'events{k}': None for k in range(K)}
+    lstm['image'] = None
+    preds, _, _ = model(seq[0], None, lstm)
+    loss = sum(R.scale_invariant_loss(preds[k], seq[0]['depth_' + k].to('cuda:0')) for k in preds)
+    loss.backward()
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    rp = O.ergb2depth_recurrent(sd, cfg, seq[0], None, dict(lstm))[0]
+    rl = sum(O.si_loss(rp[k], seq[0]['depth_' + k]) for k in rp)
+    rl.backward()
+    assert abs(loss.item() - rl.item()) <= (2e-5 if kind == 'fp32' else 5e-4)
+    tol = 2e-3 if kind == 'fp32' else 8e-2        # measured worst (head_rgb bias, norm 1e-4): 6.3e-2
+    n_dec = 0
+    gmax = max(float(v.grad.double().norm()) for v in sd.values() if v.grad is not None)
+    for n, p in model.named_parameters():
+        if sd[n].grad is None:
+            continue
+        a, b = p.grad.detach().cpu().double(), sd[n].grad.double()
+        # tiny-norm tensors far from the loss (head biases, 1e-4 of the largest gradient) only measure TF32 rounding noise
+        assert float((a - b).norm()) <= tol * float(b.norm()) + (0 if kind == 'fp32' else 1e-4 * gmax) + 1e-9, n
+        n_dec += 'transposed_conv2d' in n
+    assert n_dec >= 4          # the transposed-conv weights and biases really received gradients
