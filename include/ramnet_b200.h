@@ -282,16 +282,20 @@ int ramnet_zero_insert2x(ramnet_handle *h, const float *x, const float *skip, fl
 /* dz = dy * (y > 0).  flags & RAMNET_FLAG_ROUND_TF32 (here and in the GRU adjoints): round the dz outputs to TF32
  * so that the tcgen05 dgrad / wgrad GEMMs that consume them truncate nothing. */
 /* db (nullable, [C]) here and in the gate adjoints: the bias gradient db[c] += sum_pixels dz[., c] fused into the same
- * pass (atomic accumulation, so it can point straight at bias.grad across the passes of BPTT). */
+ * pass (accumulating, so it can point straight at bias.grad across the passes of BPTT).
+ * scratch (nullable, ramnet_colsum_scratch_bytes bytes, zeroed ONCE by the caller and then reused on one stream): the
+ * column sums are combined by the last block to finish instead of by atomics (cheaper, and deterministic). */
+size_t ramnet_colsum_scratch_bytes(void);
 int ramnet_relu_bwd(ramnet_handle *h, const float *dy, const float *y, float *dz, int64_t n, int C, float *db,
-                    int flags, void *stream);
+                    float *scratch, int flags, void *stream);
 /* ConvGRU adjoints (submodules.py:446-452).  gru_out_bwd: dzo = dh'*u*(1-o^2); columns [C,2C) of dzru =
  * dh'*(o-h)*u*(1-u); dh = dh'*(1-u).  gru_ru_bwd: columns [0,C) of dzru = drh*h*r*(1-r); dh += drh*r. */
 int ramnet_gru_out_bwd(ramnet_handle *h, const float *dhn, const float *hprev, const float *u, const float *o,
                        float *dzo, float *dzru, float *dh, float *db_o /* [C] */, float *db_ru /* [2C], rows [C,2C) */,
-                       int64_t M, int C, int flags, void *stream);
+                       float *scratch, int64_t M, int C, int flags, void *stream);
 int ramnet_gru_ru_bwd(ramnet_handle *h, const float *drh, const float *hprev, const float *r, float *dzru,
-                      float *dh, float *db_ru /* [2C], rows [0,C) */, int64_t M, int C, int flags, void *stream);
+                      float *dh, float *db_ru /* [2C], rows [0,C) */, float *scratch, int64_t M, int C, int flags,
+                      void *stream);
 /* ConvLSTM adjoint (submodules.py:341-356): gates = post-activation (i,f,o,g) [M,C,4] stashed by RAMNET_EPI_LSTM (y2);
  * dz [M,4C] comes out in nn.Conv2d row order (gate-major); dh / dc may be NULL (no gradient through that output). */
 int ramnet_lstm_bwd(ramnet_handle *h, const float *dh, const float *dc, const float *gates, const float *c_prev,

@@ -73,11 +73,12 @@ SIGNATURES = {
                                      c_void_p]),
     'ramnet_zero_insert2x': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                      c_int, c_void_p]),
-    'ramnet_relu_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p]),
+    'ramnet_colsum_scratch_bytes': (c_size_t, []),
+    'ramnet_relu_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     'ramnet_gru_out_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                   c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
-    'ramnet_gru_ru_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
-                                  c_void_p]),
+                                   c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    'ramnet_gru_ru_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                  c_int, c_void_p]),
     'ramnet_lstm_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_int64, c_int, c_int, c_void_p]),
     'ramnet_pred_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -220,9 +220,67 @@ __device__ __forceinline__ void block_colsum_atomic(float4 *part, const float4 &
 }
 static inline bool colsum_fusable(int C) { return C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0; }
 
+// Atomic-free variant: every block stores its C column sums to scratch, the LAST block to finish (ticket counter) adds
+// them up in a fixed order and accumulates into db.  The per-block atomics above still cost ~14 us per launch at 4 blocks
+// per SM (592 x C adds onto 1 KB); here the tail is one block reading blocks x C floats (~2 us) and the result no longer
+// depends on the order in which blocks retire.  scratch layout: [0] ticket counter (returns to 0), [64...] partials
+// [gridDim.x][C]; one scratch region per accumulator (kColsumScratchFloats apart).
+constexpr int kColsumMaxBlocks = 1024, kColsumMaxC = 1024;
+constexpr size_t kColsumScratchFloats = 64 + (size_t)kColsumMaxBlocks * kColsumMaxC;
+__device__ __forceinline__ void block_colsum_lastblock(float4 *part, const float4 &a, int C4, float *__restrict__ db,
+                                                       float *__restrict__ scratch) {
+    __shared__ unsigned ticket;
+    const int C = 4 * C4;
+    float *partials = scratch + 64;
+    __syncthreads();
+    part[threadIdx.x] = a;
+    __syncthreads();
+    if ((int)threadIdx.x < C4) {
+        float4 acc = part[threadIdx.x];
+        for (int j = threadIdx.x + C4; j < 256; j += C4) f4_acc(acc, part[j]);
+        reinterpret_cast<float4 *>(partials + (size_t)blockIdx.x * C)[threadIdx.x] = acc;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) ticket = atomicAdd(reinterpret_cast<unsigned *>(scratch), 1u);
+    __syncthreads();
+    if (ticket != gridDim.x - 1) return;
+    __threadfence();
+    // last block: thread (g, c) sums blocks g, g + G, ... of column c; the G partial sums are folded through shared memory
+    const int G = 256 / C > 0 ? 256 / C : 1;
+    float *fold = reinterpret_cast<float *>(part);      // 256 float4 = 1024 floats of shared memory
+    for (int c0 = 0; c0 < C; c0 += 256) {
+        const int c = c0 + (int)threadIdx.x % (C < 256 ? C : 256), g = C < 256 ? (int)threadIdx.x / C : 0;
+        float acc = 0.f;
+        if (g < G && c < C) {
+            unsigned b = g;
+            for (; b + 7 * G < gridDim.x; b += 8 * G) {        // eight independent loads in flight (L2 latency ~700 clk each)
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = __ldcg(partials + (size_t)(b + q * G) * C + c);
+                acc += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+            }
+            for (; b < gridDim.x; b += G) acc += __ldcg(partials + (size_t)b * C + c);
+        }
+        __syncthreads();
+        fold[threadIdx.x] = acc;
+        __syncthreads();
+        if (g == 0 && c < C) {
+            for (int k = 1; k < G; ++k) acc += fold[threadIdx.x + k * C];
+            db[c] += acc;
+        }
+    }
+    if (threadIdx.x == 0) *reinterpret_cast<unsigned *>(scratch) = 0u;
+}
+__device__ __forceinline__ void block_colsum(float4 *part, const float4 &a, int C4, float *__restrict__ db,
+                                             float *__restrict__ scratch) {
+    if (scratch) block_colsum_lastblock(part, a, C4, db, scratch);
+    else block_colsum_atomic(part, a, C4, db);
+}
+
 __global__ void __launch_bounds__(256) relu_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ y,
                                                        float *__restrict__ dz, int64_t n4, int round, int C4,
-                                                       float *__restrict__ db) {
+                                                       float *__restrict__ db, float *__restrict__ scratch) {
     __shared__ float4 part[256];
     float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -244,7 +302,7 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const float *__restrict__
         st4(dz, i, z);
         f4_acc(sum, z);
     }
-    if (db) block_colsum_atomic(part, sum, C4, db);
+    if (db) block_colsum(part, sum, C4, db, scratch);
 }
 
 // ConvGRU candidate+blend adjoint.  in: dh' (dhn), h, u, o.  out: dzo = dh'*u*(1-o^2), dzu = dh'*(o-h)*u*(1-u)
@@ -253,7 +311,8 @@ __global__ void __launch_bounds__(256) gru_out_bwd_kernel(const float *__restric
                                                           const float *__restrict__ u, const float *__restrict__ o,
                                                           float *__restrict__ dzo, float *__restrict__ dzru,
                                                           float *__restrict__ dh, int64_t M, int C, int round,
-                                                          float *__restrict__ db_o, float *__restrict__ db_ru) {
+                                                          float *__restrict__ db_o, float *__restrict__ db_ru,
+                                                          float *__restrict__ scratch) {
     __shared__ float4 part[256];
     float4 sum_o = make_float4(0.f, 0.f, 0.f, 0.f), sum_u = sum_o;
     const int C4 = C >> 2;
@@ -274,8 +333,8 @@ __global__ void __launch_bounds__(256) gru_out_bwd_kernel(const float *__restric
         st4(dh, i, d);
         f4_acc(sum_o, a); f4_acc(sum_u, b);
     }
-    if (db_o) block_colsum_atomic(part, sum_o, C4, db_o);
-    if (db_ru) block_colsum_atomic(part, sum_u, C4, db_ru + C);       // update gate = rows [C, 2C) of the fused RU conv
+    if (db_o) block_colsum(part, sum_o, C4, db_o, scratch);
+    if (db_ru) block_colsum(part, sum_u, C4, db_ru + C, scratch ? scratch + kColsumScratchFloats : nullptr);   // update gate = rows [C, 2C)
 }
 
 // ConvGRU reset adjoint.  in: drh (grad of h*r), h, r.  out: dzr = drh*h*r*(1-r) into columns [0, C) of dzru,
@@ -283,7 +342,7 @@ __global__ void __launch_bounds__(256) gru_out_bwd_kernel(const float *__restric
 __global__ void __launch_bounds__(256) gru_ru_bwd_kernel(const float *__restrict__ drh, const float *__restrict__ h,
                                                          const float *__restrict__ r, float *__restrict__ dzru,
                                                          float *__restrict__ dh, int64_t M, int C, int round,
-                                                         float *__restrict__ db_ru) {
+                                                         float *__restrict__ db_ru, float *__restrict__ scratch) {
     __shared__ float4 part[256];
     float4 sum_r = make_float4(0.f, 0.f, 0.f, 0.f);
     const int C4 = C >> 2;
@@ -301,7 +360,7 @@ __global__ void __launch_bounds__(256) gru_ru_bwd_kernel(const float *__restrict
         st4(dh, i, d);
         f4_acc(sum_r, a);
     }
-    if (db_ru) block_colsum_atomic(part, sum_r, C4, db_ru);          // reset gate = rows [0, C)
+    if (db_ru) block_colsum(part, sum_r, C4, db_ru, scratch);          // reset gate = rows [0, C)
 }
 
 // ConvLSTM adjoint (submodules.py:341-356).  gates: post-activation [M][C][4] = (i, f, o, g) as stashed by the forward
@@ -602,14 +661,16 @@ extern "C" int ramnet_pack_weights_dgrad(ramnet_handle *h, const float *w_oihw, 
     return RAMNET_OK;
 }
 
+extern "C" size_t ramnet_colsum_scratch_bytes(void) { return 2 * kColsumScratchFloats * sizeof(float); }
+
 extern "C" int ramnet_relu_bwd(ramnet_handle *h, const float *dy, const float *y, float *dz, int64_t n, int C, float *db,
-                               int flags, void *stream) {
+                               float *scratch, int flags, void *stream) {
     RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && dy && y && dz && n > 0 && n % 4 == 0, "relu_bwd: bad argument");
     RAMNET_CHECK_ARG(!db || (C > 0 && n % C == 0), "relu_bwd: db needs the channel count C (n %% C == 0)");
     const bool fuse = db && colsum_fusable(C);
     relu_bwd_kernel<<<grid_for_colsum(h, n / 4, fuse), 256, 0, (cudaStream_t)stream>>>(dy, y, dz, n / 4, flags & RAMNET_FLAG_ROUND_TF32,
-                                                                         fuse ? C / 4 : 1, fuse ? db : nullptr);
+                                                                         fuse ? C / 4 : 1, fuse ? db : nullptr, scratch);
     RAMNET_LAUNCH_CHECK(h);
     if (db && !fuse) {
         launch_colsum(h, dz, n / C, C, db, (cudaStream_t)stream);
@@ -619,24 +680,24 @@ extern "C" int ramnet_relu_bwd(ramnet_handle *h, const float *dy, const float *y
 }
 
 extern "C" int ramnet_gru_out_bwd(ramnet_handle *h, const float *dhn, const float *hprev, const float *u, const float *o,
-                                  float *dzo, float *dzru, float *dh, float *db_o, float *db_ru, int64_t M, int C, int flags,
-                                  void *stream) {
+                                  float *dzo, float *dzru, float *dh, float *db_o, float *db_ru, float *scratch, int64_t M,
+                                  int C, int flags, void *stream) {
     RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && dhn && hprev && u && o && dzo && dzru && dh && M > 0 && C % 4 == 0, "gru_out_bwd: bad argument");
     RAMNET_CHECK_ARG((!db_o && !db_ru) || colsum_fusable(C), "gru_out_bwd: fused bias gradients need 256 %% (C/4) == 0");
     gru_out_bwd_kernel<<<grid_for_colsum(h, M * (C / 4), db_o || db_ru), 256, 0, (cudaStream_t)stream>>>(
-        dhn, hprev, u, o, dzo, dzru, dh, M, C, flags & RAMNET_FLAG_ROUND_TF32, db_o, db_ru);
+        dhn, hprev, u, o, dzo, dzru, dh, M, C, flags & RAMNET_FLAG_ROUND_TF32, db_o, db_ru, scratch);
     RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;
 }
 
 extern "C" int ramnet_gru_ru_bwd(ramnet_handle *h, const float *drh, const float *hprev, const float *r, float *dzru,
-                                 float *dh, float *db_ru, int64_t M, int C, int flags, void *stream) {
+                                 float *dh, float *db_ru, float *scratch, int64_t M, int C, int flags, void *stream) {
     RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && drh && hprev && r && dzru && dh && M > 0 && C % 4 == 0, "gru_ru_bwd: bad argument");
     RAMNET_CHECK_ARG(!db_ru || colsum_fusable(C), "gru_ru_bwd: the fused bias gradient needs 256 %% (C/4) == 0");
     gru_ru_bwd_kernel<<<grid_for_colsum(h, M * (C / 4), db_ru != nullptr), 256, 0, (cudaStream_t)stream>>>(
-        drh, hprev, r, dzru, dh, M, C, flags & RAMNET_FLAG_ROUND_TF32, db_ru);
+        drh, hprev, r, dzru, dh, M, C, flags & RAMNET_FLAG_ROUND_TF32, db_ru, scratch);
     RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;
 }

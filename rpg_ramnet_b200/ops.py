@@ -590,12 +590,31 @@ def zero_insert2x(x, Hout, Wout, skip=None, want_sum=False):
     return (y, xs) if want_sum else y
 
 
+_colsum_scratch = {}
+
+
+def _colsum_ws(device):
+    """Scratch of the atomic-free bias-gradient fold (ticket counter + per-block partial sums), one per (device, stream),
+    zeroed once: the kernels return the counter to 0.  Opt-in (RAMNET_COLSUM_LASTBLOCK=1): measured SLOWER than the
+    per-block atomics on B200 (relu_bwd 40 vs 27 us, training step 66.3 vs 62.9 ms, profiles/r02_colsum_ab.txt) because
+    the single last block's pass over blocks x C partial sums is a serial tail; kept for its fixed summation order."""
+    if os.environ.get('RAMNET_COLSUM_LASTBLOCK', '0') != '1':
+        return None
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _colsum_scratch.get(key)
+    if ws is None:
+        ws = _colsum_scratch[key] = torch.zeros(_lib.load().ramnet_colsum_scratch_bytes() // 4, dtype=torch.float32,
+                                                device=device)
+    return ws
+
+
 def relu_bwd(dy, y, round_tf32=False, db=None):
     """dz = dy * (y > 0); db [C] (optional) += column sums of dz (the layer's bias gradient, fused)."""
     _check_nhwc(dy, 'relu_bwd dy')
     _check_nhwc(y, 'relu_bwd y')
     dz = empty_nhwc(*y.shape, y.device)
     check(_lib.load().ramnet_relu_bwd(_h(y), _p(dy), _p(y), _p(dz), y.numel(), y.shape[1], _p(db),
+                                      _p(_colsum_ws(y.device) if db is not None else None),
                                       FLAG_ROUND_TF32 if round_tf32 else 0, _stream(y)))
     return dz
 
@@ -609,14 +628,16 @@ def gru_out_bwd(dhn, h, u, o, round_tf32=False, db_o=None, db_ru=None):
     N, C, H, W = h.shape
     dzo, dh = empty_nhwc(N, C, H, W, h.device), empty_nhwc(N, C, H, W, h.device)
     dzru = empty_nhwc(N, 2 * C, H, W, h.device)
+    ws = _colsum_ws(h.device) if (db_o is not None or db_ru is not None) else None
     check(_lib.load().ramnet_gru_out_bwd(_h(h), _p(dhn), _p(h), _p(u), _p(o), _p(dzo), _p(dzru), _p(dh), _p(db_o), _p(db_ru),
-                                         N * H * W, C, FLAG_ROUND_TF32 if round_tf32 else 0, _stream(h)))
+                                         _p(ws), N * H * W, C, FLAG_ROUND_TF32 if round_tf32 else 0, _stream(h)))
     return dzo, dzru, dh
 
 
 def gru_ru_bwd(drh, h, r, dzru, dh, round_tf32=False, db_ru=None):
     N, C, H, W = h.shape
-    check(_lib.load().ramnet_gru_ru_bwd(_h(h), _p(drh), _p(h), _p(r), _p(dzru), _p(dh), _p(db_ru), N * H * W, C,
+    check(_lib.load().ramnet_gru_ru_bwd(_h(h), _p(drh), _p(h), _p(r), _p(dzru), _p(dh), _p(db_ru),
+                                        _p(_colsum_ws(h.device) if db_ru is not None else None), N * H * W, C,
                                         FLAG_ROUND_TF32 if round_tf32 else 0, _stream(h)))
 
 
