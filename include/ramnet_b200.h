@@ -87,11 +87,14 @@ enum {
     RAMNET_FLAG_HPACK = 2,      /* ramnet_conv_fwd: w_packed is in ramnet_pack_weights_hpack's layout (horizontal taps as
                                    GEMM columns); stride 1, ksize 3/5, bias / relu / residual / pred epilogues.
                                    Default for Cout = 32 layers since round 2 (RAMNET_HPACK=0 on the Python side disables). */
-    RAMNET_FLAG_UPCONV = 4      /* ramnet_conv_fwd: bilinear x2 (align_corners=False) FOLLOWED BY the 5x5 stride-1 convolution
+    RAMNET_FLAG_UPCONV = 4,     /* ramnet_conv_fwd: bilinear x2 (align_corners=False) FOLLOWED BY the 5x5 stride-1 convolution
                                    (UpsampleConvLayer.forward, submodules.py:87-97) in one launch on the LOW-resolution
                                    input: desc.H/W are the input's, y0 is [N, Cout, 2H, 2W].  w_packed comes from
                                    ramnet_pack_weights_upconv (collapsed taps of the 4 output phases + border segments).
                                    Epilogues: BIAS_RELU, BIAS_RELU_ADD, BIAS_RELU_PRED.  TF32 path, x1 = NULL. */
+    RAMNET_FLAG_S2SEG = 8       /* ramnet_conv_fwd: 5x5 stride-2 convolution as four parity-plane K segments (multi-stage
+                                   halos); w_packed from ramnet_pack_weights_s2seg ([27 taps][Cout][Cin], the (1,1) plane
+                                   padded to 6 taps).  Epilogues BIAS, BIAS_RELU; TF32 path, x1 = NULL. */
 };
 
 /* One implicit-GEMM convolution:  y[m, n] = epi( sum_{tap,c} x[pix(m,tap), c] * w[tap, n, c] ).
@@ -182,6 +185,8 @@ int ramnet_pack_weights_hpack(ramnet_handle *h, const float *w_oihw, float *w_pa
  * segment (5x5 window on the low-resolution input) and of the 8 border segments (first / last row, first / last column,
  * 4 corners) the 5x5 filter collapsed through the bilinear x2 coefficients, one block of Cout rows per output phase
  * (py, px).  ramnet_upconv_packed_floats gives the size of w_packed in floats. */
+int ramnet_pack_weights_s2seg(ramnet_handle *h, const float *w_oihw, float *w_packed /* 27 * Cout * Cin floats */, int Cout,
+                              int Cin, void *stream);
 int64_t ramnet_upconv_packed_floats(int Cout, int Cin);
 int ramnet_pack_weights_upconv(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin, void *stream);
 int ramnet_pack_weights(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin,

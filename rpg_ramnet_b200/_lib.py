@@ -17,6 +17,7 @@ EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RES_RELU, EPI_GRU_RU, EPI_GRU_OUT, EPI_LSTM, E
 FLAG_ROUND_TF32 = 1
 FLAG_HPACK = 2
 FLAG_UPCONV = 4
+FLAG_S2SEG = 8
 LOSS_LOG_SPACE = 1
 WGRAD_FULL, WGRAD_PARTIAL_FIRST, WGRAD_PARTIAL_ADD, WGRAD_FINALIZE = range(4)
 RAMNET_EUNSUPPORTED = -3
@@ -55,6 +56,7 @@ SIGNATURES = {
     'ramnet_pack_weights_dgrad': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                           c_void_p]),
     'ramnet_pack_weights_hpack': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'ramnet_pack_weights_s2seg': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'ramnet_upconv_packed_floats': (c_int64, [c_int, c_int]),
     'ramnet_pack_weights_upconv': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'ramnet_plan_describe': (c_int, [POINTER(ConvDesc), c_int, c_char_p, c_size_t]),

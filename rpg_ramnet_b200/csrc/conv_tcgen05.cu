@@ -835,7 +835,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
                 const int ox = x0 + (tl & (g.PTX - 1)) * 8 + (row & 7), oy = y0 + (tl >> g.ptx_log2) * 16 + (row >> 3);
                 u.valid = oy < g.Ho && ox < g.Wo && img < g.N;
                 u.col = (half + kParts * j) * 16;
-                if constexpr (UP) {
+                if (UP && g.up) {
                     // depth-to-space: GEMM column (phase, co) of low-resolution pixel (oy, ox) is channel co of the
                     // high-resolution pixel (2 oy + py, 2 ox + px); a 16-column unit never straddles two phases
                     const int n = n0 + u.col, phase = n / g.up_cout;
@@ -1728,16 +1728,21 @@ bool plan_hpack(const ramnet_handle *h, const ramnet_conv_desc *d, HaloGeom *g) 
 //  - L2 -> SM delivers ~15 TB/s chip-wide (~50 B/clk/SM);
 //  - the epilogue is hidden under the next item when TMEM is double-buffered;
 //  - persistent scheduling => ceil(items / SMs) rounds.
-double halo_cost(const ramnet_handle *h, const ramnet_conv_desc *d, const HaloGeom &g) {
-    const int ntiles = g.PTX * g.PTY, chunks = (d->C0 + d->C1) / kChunk, taps = g.kh * g.kw;
-    const double halo_bytes = (double)g.nplanes * g.HX * g.HY * 128.0;
+double halo_cost(const ramnet_handle *h, const ramnet_conv_desc *d, const HaloGeom &g, int taps_override = 0,
+                 bool flat_issue = false) {
+    const int ntiles = g.PTX * g.PTY, chunks = (d->C0 + d->C1) / kChunk, taps = taps_override ? taps_override : g.kh * g.kw;
+    const double halo_bytes = (double)g.nplanes * g.HX * g.HY * 128.0 * (taps_override ? 4.0 : 1.0);   // s2seg: 4 planes per chunk
     const double bn_l = g.pair ? g.BN / 2.0 : (double)g.BN;     // weight rows read from / written to THIS SM's shared memory
     const double smem_tap = (ntiles * 4.0 * (128 + bn_l) * 32.0 + bn_l * 128.0 + halo_bytes / taps) / 128.0;
     const double math_tap = ntiles * 4.0 * g.BN / 2.0;
     // The issuing thread runs beside the (asynchronous) tensor pipe: per weight stage a barrier poll + fence + commit
     // (multicast across the pair: ~300 clk measured, ~60 single), shared by tpg taps, plus ~26 clk per MMA issued.
     // A tap costs whichever is slower (RAMNET_PROF: 410 / 514 clk per tap for 1 / 2 tiles of N = 64 in pair mode).
-    const double issue_tap = (g.pair ? 300.0 : 60.0) / g.tpg + 26.0 * 4.0 * ntiles;
+    // Round 2 (RAMNET_PROF on the parity-plane stride-2 layers, profiles/r02_s2seg.txt): in pair mode the fixed part is
+    // ~220 clk per TAP whatever tpg is (380 / 483 / 796 clk per tap for 1 / 2 / 4 tiles of N = 64 at tpg = 3).  The s2seg
+    // planner uses that (flat_issue); the stride-1 plans keep the round-1 term unless RAMNET_ISSUE_MODEL=1.
+    static const bool issue_v2 = [] { const char *e = getenv("RAMNET_ISSUE_MODEL"); return e && e[0] == '1'; }();
+    const double issue_tap = ((flat_issue || issue_v2) && g.pair ? 220.0 : (g.pair ? 300.0 : 60.0) / g.tpg) + 26.0 * 4.0 * ntiles;
     double tap = smem_tap > math_tap ? smem_tap : math_tap;
     if (issue_tap > tap) tap = issue_tap;
     tap += 10.0;
@@ -1763,6 +1768,7 @@ double halo_cost(const ramnet_handle *h, const ramnet_conv_desc *d, const HaloGe
     // stride 2: one 4-plane halo per item and a single K chunk for the first encoder -- the halo fetch is exposed and the
     // model above underestimates both modes by ~2x; measured (enc0, 32->64): pair 2x1 55 us vs single 1x1 67 us
     if (d->stride == 2 && !g.pair) cost *= 1.25;
+    if (flat_issue && !g.pair) cost *= 1.15;       // s2seg, measured: enc0 2x1 50.7 us single vs 45.2 us pair
     return cost;
 }
 
@@ -2467,6 +2473,102 @@ int conv_up_fwd_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *x
     return ramnet_set_error(RAMNET_EINVAL, "conv_fwd(upconv): unreachable");
 }
 
+// ================================================================================================
+// Stride-2 5x5 convolution as four parity-plane K segments (RAMNET_FLAG_S2SEG, round 2).  Input row 2*oy + r - pad =
+// 2*(oy + dy) + py: the taps with the same (py, px) form a stride-1 3x3 / 3x2 / 2x3 / 2x2 convolution of ONE parity
+// plane x[:, py::2, px::2].  The round-1 stride-2 path fetched all four planes of the halo as one stage (166 KB for a
+// 2-tile patch: a single stage, the MMA warp idle a third of the time waiting for it); here every plane is its own K
+// segment read through its own tensor map (a strided view of the same tensor), so a stage is one plane (41 KB) and the
+// stages pipeline.  Same 25 taps; the (1,1) plane's 4 taps are padded to 6 so that every segment is a multiple of the
+// 3 taps a weight stage holds.
+// ================================================================================================
+constexpr int kS2Taps[4] = {9, 6, 6, 6};
+constexpr int kS2TotalTaps = 27;
+__host__ __device__ inline void s2seg_shape(int sg, int &kh, int &kw) { kh = (sg & 2) ? 2 : 3; kw = (sg & 1) ? 2 : 3; }
+
+__global__ void pack_s2seg_kernel(const float *__restrict__ w, float *__restrict__ out, int Cout, int Cin) {
+    const int64_t total = (int64_t)kS2TotalTaps * Cout * Cin;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % Cin);
+        const int co = (int)((i / Cin) % Cout);
+        int tap = (int)(i / ((int64_t)Cin * Cout));
+        int sg = 0;
+        while (sg < 3 && tap >= (sg == 0 ? 9 : 6)) { tap -= (sg == 0 ? 9 : 6); ++sg; }
+        int kh, kw;
+        s2seg_shape(sg, kh, kw);
+        float v = 0.f;
+        if (tap < kh * kw) {
+            const int py = sg >> 1, px = sg & 1;
+            const int dy = -1 + tap / kw, dx = -1 + tap % kw;          // plane offsets; every segment starts at -1
+            const int r = 2 * dy + py + 2, sx = 2 * dx + px + 2;        // filter tap of the 5x5, pad 2
+            v = w[(((int64_t)co * Cin + ci) * 5 + r) * 5 + sx];
+        }
+        out[i] = round_tf32(v);
+    }
+}
+
+int conv_s2seg_fwd_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *x0, const float *wp, const EpiParams &ep,
+                        cudaStream_t s) {
+    RAMNET_CHECK_ARG(d->ksize == 5 && d->stride == 2 && d->C1 == 0 && d->H >= 2 && d->W >= 2,
+                     "conv_fwd(s2seg): 5x5 stride-2 single-source layers only");
+    RAMNET_CHECK_ARG(d->C0 % kChunk == 0 && d->Cout % 16 == 0, "conv_fwd(s2seg): C0 %% 32, Cout %% 16");
+    RAMNET_CHECK_ARG(d->epilogue == RAMNET_EPI_BIAS_RELU || d->epilogue == RAMNET_EPI_BIAS, "conv_fwd(s2seg): bias / relu epilogues");
+    ramnet_conv_desc dp = *d;           // the planner sees a 3x3 stride-1 convolution over one parity plane
+    dp.H = (d->H + 1) / 2; dp.W = (d->W + 1) / 2; dp.stride = 1; dp.ksize = 3;      // = the output size
+    static const int pair_mode = [] { const char *e = getenv("RAMNET_PAIR"); return e ? atoi(e) : 1; }();
+    static const int shapes[][2] = {{2, 1}, {1, 1}, {4, 1}, {2, 2}, {1, 2}};
+    double best = -1;
+    HaloGeom hg, cand;
+    if (const char *f = getenv("RAMNET_S2_FORCE")) {      // tuning aid: "PTX,PTY,BN,pair"
+        int ptx, pty, bn, pr = 0;
+        if (sscanf(f, "%d,%d,%d,%d", &ptx, &pty, &bn, &pr) >= 3 && fill_halo(&dp, nullptr, &cand, ptx, pty, bn, 0, 0, pr, 3)) {
+            best = 0; hg = cand;
+        }
+    }
+    for (int pass = 0; pass < 2 && best < 0; ++pass)
+        for (int pair = (pair_mode == 2 && pass == 0 ? 1 : 0); pair <= (pair_mode >= 1 ? 1 : 0); ++pair)
+            for (const auto &sh : shapes)
+                for (int bn = 256; bn >= 16; bn >>= 1) {
+                    if (!fill_halo(&dp, nullptr, &cand, sh[0], sh[1], bn, 0, 0, pair, 3)) continue;
+                    const double c = halo_cost(h, &dp, cand, kS2TotalTaps, true);
+                    if (best < 0 || c < best) { best = c; hg = cand; }
+                }
+    if (best < 0) return RAMNET_EUNSUPPORTED;
+    hg.up = 0; hg.up_cout = d->Cout; hg.nseg = 4; hg.total_taps = kS2TotalTaps;
+    int tap0 = 0;
+    for (int sg = 0; sg < 4; ++sg) {
+        UpSeg &u = hg.seg[sg];
+        s2seg_shape(sg, u.kh, u.kw);
+        u.lo_y = -1; u.lo_x = -1; u.vx = 0; u.vy = 0; u.cond = 0;
+        u.tap0 = tap0; u.ntaps = kS2Taps[sg]; tap0 += kS2Taps[sg];
+    }
+    if (getenv("RAMNET_DEBUG"))
+        fprintf(stderr, "[ramnet] s2seg plan %dx%d C=%d->%d: tiles %dx%d HX=%d HY=%d BN=%d a_st=%d b_st=%d tpg=%d nbuf=%d items=%d pair=%d\n",
+                d->H, d->W, d->C0, d->Cout, hg.PTX, hg.PTY, hg.HX, hg.HY, hg.BN, hg.a_stages, hg.b_stages, hg.tpg, hg.nbuf,
+                hg.items, hg.pair);
+    CUtensorMap m0, mw;
+    UpMaps um;
+    const int C = d->C0;
+    const cuuint64_t str[3] = {(cuuint64_t)2 * C * 4, (cuuint64_t)2 * d->W * C * 4, (cuuint64_t)d->H * d->W * C * 4};
+    const cuuint32_t box[4] = {kChunk, (cuuint32_t)hg.HX, (cuuint32_t)hg.HY, 1};
+    for (int sg = 0; sg < 4; ++sg) {
+        const int py = sg >> 1, px = sg & 1;
+        // plane (py, px) = x[:, py::2, px::2]; with odd H or W the odd plane is one row / column shorter and the box's
+        // out-of-bounds zero fill supplies exactly the padding the full-resolution convolution would read there
+        const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)(d->W - px + 1) / 2, (cuuint64_t)(d->H - py + 1) / 2, (cuuint64_t)d->N};
+        const float *base = x0 + ((int64_t)py * d->W + px) * C;
+        const int rc = encode(h, sg == 0 ? &m0 : &um.m[sg - 1], base, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    const cuuint64_t wd[3] = {(cuuint64_t)C, (cuuint64_t)d->Cout, (cuuint64_t)kS2TotalTaps};
+    const cuuint64_t wst[2] = {(cuuint64_t)C * 4, (cuuint64_t)C * d->Cout * 4};
+    const cuuint32_t wb[3] = {kChunk, (cuuint32_t)(hg.pair ? hg.BN / 2 : hg.BN), (cuuint32_t)hg.tpg};
+    int rc = encode(h, &mw, wp, 3, wd, wst, wb);
+    if (rc) return rc;
+    if (d->epilogue == RAMNET_EPI_BIAS) return launch_halo<RAMNET_EPI_BIAS, false, true>(h, m0, m0, mw, hg, ep, s, um);
+    return launch_halo<RAMNET_EPI_BIAS_RELU, false, true>(h, m0, m0, mw, hg, ep, s, um);
+}
+
 int conv_fwd_tf32_rect(ramnet_handle *h, const ramnet_conv_desc *d, const RectSpec *rect, const float *x0, const float *x1,
                        const float *wp, const EpiParams &ep, cudaStream_t s);
 
@@ -2480,7 +2582,8 @@ int conv_fwd_tf32_rect(ramnet_handle *h, const ramnet_conv_desc *d, const RectSp
     RAMNET_CHECK_ARG(d->C0 % kChunk == 0 && d->C1 % kChunk == 0,
                      "conv_fwd(tf32): C0=%d, C1=%d must be multiples of 32 (one 128-byte swizzle row)", d->C0, d->C1);
     RAMNET_CHECK_ARG(d->Cout % 16 == 0, "conv_fwd(tf32): Cout=%d must be a multiple of 16", d->Cout);
-    RAMNET_CHECK_ARG(d->stride == 1 || (d->H % 2 == 0 && d->W % 2 == 0), "conv_fwd(tf32): stride 2 needs even H, W");
+    RAMNET_CHECK_ARG(d->stride == 1 || (d->flags & RAMNET_FLAG_S2SEG) || (d->H % 2 == 0 && d->W % 2 == 0),
+                     "conv_fwd(tf32): stride 2 needs even H, W (or RAMNET_FLAG_S2SEG weights)");
     RAMNET_CHECK_ARG((((uintptr_t)x0 | (uintptr_t)x1 | (uintptr_t)wp) & 15) == 0, "conv_fwd(tf32): 16-byte alignment");
     RAMNET_CHECK_ARG((((uintptr_t)ep.y0 | (uintptr_t)ep.y1 | (uintptr_t)ep.y2 | (uintptr_t)ep.aux0 | (uintptr_t)ep.aux1) & 31) == 0 ||
                          d->epilogue == RAMNET_EPI_BIAS_RELU_PRED,
@@ -2488,6 +2591,12 @@ int conv_fwd_tf32_rect(ramnet_handle *h, const ramnet_conv_desc *d, const RectSp
     if (d->flags & RAMNET_FLAG_UPCONV) {
         RAMNET_CHECK_ARG(!rect && !x1, "conv_fwd(upconv): single source, no rectangular tap set");
         return conv_up_fwd_tf32(h, d, x0, wp, ep, s);
+    }
+    if (d->flags & RAMNET_FLAG_S2SEG) {
+        RAMNET_CHECK_ARG(!rect && !x1, "conv_fwd(s2seg): single source, no rectangular tap set");
+        const int rc = conv_s2seg_fwd_tf32(h, d, x0, wp, ep, s);
+        if (rc == RAMNET_EUNSUPPORTED) return ramnet_set_error(rc, "conv_fwd(s2seg): no halo configuration fits");
+        return rc;
     }
     HaloGeom hg;
     const bool want_hpack = (d->flags & RAMNET_FLAG_HPACK) != 0;
@@ -2868,6 +2977,18 @@ __global__ void pack_hpack_kernel(const float *__restrict__ w, float *__restrict
     }
 }
 }  // namespace
+
+extern "C" int ramnet_pack_weights_s2seg(ramnet_handle *h, const float *w_oihw, float *w_packed, int Cout, int Cin,
+                                         void *stream) {
+    RAMNET_DEVICE_GUARD(h);
+    RAMNET_CHECK_ARG(h && w_oihw && w_packed && Cout > 0 && Cout % 16 == 0 && Cin > 0 && Cin % 32 == 0,
+                     "pack_weights_s2seg: bad argument");
+    const int64_t total = (int64_t)kS2TotalTaps * Cout * Cin;
+    pack_s2seg_kernel<<<(unsigned)imin64((total + 255) / 256, (int64_t)h->sm_count * 8), 256, 0, (cudaStream_t)stream>>>(
+        w_oihw, w_packed, Cout, Cin);
+    RAMNET_LAUNCH_CHECK(h);
+    return RAMNET_OK;
+}
 
 extern "C" int64_t ramnet_upconv_packed_floats(int Cout, int Cin) { return (int64_t)kUpTotalTaps * 4 * Cout * Cin; }
 

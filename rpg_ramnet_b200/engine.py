@@ -107,11 +107,15 @@ def pack_conv(cache: WeightCache, key, conv, kind: int, norm_mod=None, norm_kind
         w, b = _fold_norm(w, b, norm_mod, norm_kind, training)
         p = Packed()
         hp = hpack_ok and ops.hpack_eligible(w.shape[0], w.shape[2], conv.stride[0], kind)
-        p.w = ops.pack_weights_hpack(w) if hp else ops.pack_weights(w, kind)
+        if hpack_ok and ops.s2seg_eligible(w.shape[1], w.shape[0], w.shape[2], conv.stride[0], kind):
+            p.w = ops.pack_weights_s2seg(w)
+        else:
+            p.w = ops.pack_weights_hpack(w) if hp else ops.pack_weights(w, kind)
         p.b = None if b is None else b.contiguous()
         p.Cout, p.ksize, p.stride = w.shape[0], w.shape[2], conv.stride[0]
         return p
-    hp_key = hpack_ok and ops.hpack_eligible(conv.weight.shape[0], conv.weight.shape[2], conv.stride[0], kind)
+    hp_key = hpack_ok and (ops.hpack_eligible(conv.weight.shape[0], conv.weight.shape[2], conv.stride[0], kind) or
+                           ops.s2seg_eligible(conv.weight.shape[1], conv.weight.shape[0], conv.weight.shape[2], conv.stride[0], kind))
     return cache.get(key, [conv.weight, conv.bias] + _norm_sources(norm_mod), (kind, training, hp_key), build)
 
 
@@ -230,7 +234,8 @@ def head_layer(cache, key, conv, x, tf32):
 def conv_layer(cache, key, conv, kind, x, epilogue, x1=None, res=None, norm_mod=None, norm_kind=None, training=False,
                round_out=False):
     p = pack_conv(cache, key, conv, kind, norm_mod, norm_kind, training,
-                  hpack_ok=epilogue in (ops.EPI_BIAS, ops.EPI_BIAS_RELU, ops.EPI_BIAS_RES_RELU) and x1 is None)
+                  hpack_ok=(epilogue in (ops.EPI_BIAS, ops.EPI_BIAS_RELU, ops.EPI_BIAS_RES_RELU) and x1 is None and
+                            not (conv.stride[0] == 2 and epilogue == ops.EPI_BIAS_RES_RELU)))
     if needs_grad(x, x1, res, conv.weight, conv.bias):
         _no_fold_in_training(norm_mod, norm_kind)
         from .autograd import ConvFn

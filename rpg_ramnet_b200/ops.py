@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 from ._lib import (ConvDesc, EPI_BIAS, EPI_BIAS_ADD, EPI_BIAS_RELU, EPI_BIAS_RELU_ADD, EPI_BIAS_RELU_PRED, EPI_BIAS_RES_RELU, EPI_GRU_OUT,  # noqa
-                   EPI_GRU_RU, EPI_LSTM, FLAG_HPACK, FLAG_ROUND_TF32, FLAG_UPCONV, MMA_FP32, MMA_TF32, check)
+                   EPI_GRU_RU, EPI_LSTM, FLAG_HPACK, FLAG_ROUND_TF32, FLAG_S2SEG, FLAG_UPCONV, MMA_FP32, MMA_TF32, check)
 
 
 def _stream(t: torch.Tensor):
@@ -212,6 +212,24 @@ def pack_weights_hpack(w_oihw: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def s2seg_eligible(Cin: int, Cout: int, ksize: int, stride: int, mma_kind: int) -> bool:
+    """5x5 stride-2 single-source layers (the encoders' strided convs) run as four parity-plane K segments
+    (RAMNET_FLAG_S2SEG): one plane per pipeline stage instead of all four in one.  RAMNET_S2SEG=0 disables."""
+    if os.environ.get('RAMNET_S2SEG', '1') == '0':
+        return False
+    return mma_kind == MMA_TF32 and stride == 2 and ksize == 5 and Cin % 32 == 0 and Cout % 16 == 0
+
+
+def pack_weights_s2seg(w_oihw: torch.Tensor) -> torch.Tensor:
+    w = w_oihw.detach().contiguous().float()
+    Cout, Cin, k, _ = w.shape
+    assert k == 5
+    out = torch.empty(27 * Cout * Cin, dtype=torch.float32, device=w.device)
+    check(_lib.load().ramnet_pack_weights_s2seg(_h(w), _p(w), _p(out), Cout, Cin, _stream(w)))
+    out._ramnet_s2seg = True          # conv_fwd sets RAMNET_FLAG_S2SEG for weights packed this way
+    return out
+
+
 def upconv_eligible(Cin: int, Cout: int, ksize: int, mma_kind: int) -> bool:
     """Layers ramnet_conv_fwd can run in up-conv mode (bilinear x2 + 5x5 conv in one launch on the low-resolution input,
     RAMNET_FLAG_UPCONV): TF32, 5x5, Cin % 32 == 0, 4 * Cout GEMM columns <= 512.  RAMNET_UPCONV=0 disables;
@@ -343,6 +361,8 @@ def conv_fwd(x0: torch.Tensor, x1: Optional[torch.Tensor], w_packed: torch.Tenso
             if a is not None:
                 _check_nhwc(a, 'conv_fwd ' + nm)
     flags = (FLAG_ROUND_TF32 if round_tf32 else 0) | (FLAG_HPACK if getattr(w_packed, '_ramnet_hpack', False) else 0)
+    if getattr(w_packed, '_ramnet_s2seg', False):
+        flags |= FLAG_S2SEG
     d = ConvDesc(N, H, W, C0, C1, Cout, ksize, stride, epilogue, mma_kind, flags, 0)
     lib = _lib.load()
     nws = lib.ramnet_conv_workspace_bytes(ctypes.byref(d))

@@ -63,3 +63,27 @@ def test_wgrad_fold_and_fused_sum_vs_torch(shape):
     ops.conv_wgrad(nhwc(dz), nhwc(x), None, Cout, k, 1, dw, None, ops.MMA_TF32)
     err = (dw.cpu().double() - w.grad).norm() / w.grad.norm()
     assert float(err) <= 1e-5
+
+
+@pytest.mark.parametrize('N,Cin,Cout,H,W,relu', [(1, 32, 64, 32, 64, True), (2, 64, 128, 18, 46, True), (1, 32, 32, 13, 21, False),
+                                                 (1, 128, 256, 64, 128, True), (3, 32, 64, 5, 7, True), (4, 32, 64, 256, 512, True)])
+def test_s2seg_forward_vs_torch(N, Cin, Cout, H, W, relu):
+    """5x5 stride-2 convolution as four parity-plane K segments (RAMNET_FLAG_S2SEG) == F.conv2d(stride=2, padding=2),
+    even and odd sizes (the odd planes are one row / column shorter; TMA zero fill is the padding)."""
+    from rpg_ramnet_b200 import ops
+    g = torch.Generator().manual_seed(N + Cin + Cout + H + W)
+    x = rna(torch.randn(N, Cin, H, W, generator=g))
+    w = rna(torch.randn(Cout, Cin, 5, 5, generator=g) * (1.0 / (Cin * 25)) ** 0.5)
+    b = torch.randn(Cout, generator=g) * 0.1
+    y = F.conv2d(x.to(dev()).double(), w.to(dev()).double(), b.to(dev()).double(), stride=2, padding=2)
+    y = torch.relu(y) if relu else y
+    wp = ops.pack_weights_s2seg(w.to(dev()))
+    assert getattr(wp, '_ramnet_s2seg', False)
+    out = ops.conv_fwd(nhwc(x), None, wp, b.to(dev()), Cout, 5, 2, ops.EPI_BIAS_RELU if relu else ops.EPI_BIAS, ops.MMA_TF32)
+    assert tuple(out.shape) == tuple(y.shape)
+    assert (out.double() - y).abs().max().item() <= 2e-5 * max(1.0, y.abs().max().item())
+    if H % 2 or W % 2:
+        return            # the single-stage stride-2 path it replaces takes even sizes only
+    old = ops.conv_fwd(nhwc(x), None, ops.pack_weights(w.to(dev()), ops.MMA_TF32), b.to(dev()), Cout, 5, 2,
+                       ops.EPI_BIAS_RELU if relu else ops.EPI_BIAS, ops.MMA_TF32)
+    assert (out - old).abs().max().item() <= 2e-5 * max(1.0, y.abs().max().item())

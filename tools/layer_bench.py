@@ -70,7 +70,10 @@ def main():
         Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
         w = torch.randn(Cout, C0 + C1, k, k, device=dev) * 0.02
         hp = epi == ops.EPI_BIAS_RELU and ops.hpack_eligible(Cout, k, stride, kind)
-        wp = ops.pack_weights_hpack(w) if hp else ops.pack_weights(w, kind)
+        if epi == ops.EPI_BIAS_RELU and not C1 and ops.s2seg_eligible(C0, Cout, k, stride, kind):
+            wp = ops.pack_weights_s2seg(w)
+        else:
+            wp = ops.pack_weights_hpack(w) if hp else ops.pack_weights(w, kind)
         b = torch.zeros(Cout, device=dev)
         Cs = Cout // 2 if epi == ops.EPI_GRU_RU else Cout
         aux0 = ops.empty_nhwc(B, Cs, Ho, Wo, dev).normal_() if epi in (ops.EPI_GRU_RU, ops.EPI_GRU_OUT) else None
