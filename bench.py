@@ -425,6 +425,9 @@ def main_ours(args):
     host_items = synth_sequence(B, H, W, L, K_EVENTS, seed=2 + rank, with_targets=False)
     host_items = [{k: v.pin_memory() for k, v in it.items()} for it in host_items]
     dev_items = [{k: v.to(dev) for k, v in it.items()} for it in host_items]
+    # the resident inputs are written once, here, and only read afterwards: the graph runner need not order its input
+    # copies after the work queued on the compute stream (engine.GraphRunner, `inputs_static`)
+    model.inputs_static = True
     h2d = sum(v.numel() * 4 for it in host_items for v in it.values())
     d2h = MAPS_PER_STEP * H * W * 4
 

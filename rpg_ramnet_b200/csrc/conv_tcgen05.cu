@@ -361,6 +361,12 @@ struct HaloGeom {
     unsigned long long *prof; // RAMNET_PROF=1: per-role wait-cycle counters (debug), else nullptr
 };
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 constexpr int kEpiWarps = RAMNET_EPI_WARPS;          // epilogue warps (multiple of 4: one or more per TMEM lane quarter)
 constexpr int kHaloThreads = 128 + 32 * kEpiWarps;
 
@@ -528,6 +534,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
     uint32_t *tap_tab = tmem_slot + 2;           // [ks*ks] halo offset of each filter tap, in 16-byte units
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (g.prof && threadIdx.x == 0) atomicMax(g.prof + 8, ~globaltimer_ns());        // ~min over CTAs of the entry time
     // Persistent grid (<= one CTA per SM, all resident): let the next kernel of the stream start its prologue on the
     // SMs this grid leaves idle / as its CTAs retire.
     pdl_launch_dependents();
@@ -597,6 +604,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
     const bool prof = g.prof != nullptr;
     unsigned long long w0 = 0, w1 = 0, w2 = 0;
     const long long t_start = clock64();
+    if (prof && threadIdx.x == 0) {
+        const unsigned long long t = globaltimer_ns();
+        atomicMax(g.prof + 9, t);
+        atomicMax(g.prof + 12, ~t);
+    }
 
     // item -> (Cout slice, image, patch origin); consecutive items share the weight slice (L2 reuse)
     const int patches_w = PAIR ? (patches + 1) >> 1 : patches;   // patches (pair mode: patch pairs) per Cout slice
@@ -1015,7 +1027,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (prof && threadIdx.x == 0) {
+        const unsigned long long t = globaltimer_ns();
+        atomicMax(g.prof + 10, t);
+        atomicMax(g.prof + 13, ~t);
+    }
     if constexpr (PAIR) cluster_sync_all();   // neither CTA retires while the other may still read its smem / signal its barriers
+    if (prof && threadIdx.x == 0) atomicMax(g.prof + 11, globaltimer_ns());
     if (warp == 3) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if constexpr (PAIR)
@@ -1532,14 +1550,20 @@ int launch_halo_pair(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap 
     static const bool do_prof = getenv("RAMNET_PROF") != nullptr;      // debug only: synchronises and prints
     if (do_prof) {
         static unsigned long long *buf = nullptr;
-        if (!buf) cudaMalloc(&buf, 64);
-        cudaMemsetAsync(buf, 0, 64, s);
+        if (!buf) cudaMalloc(&buf, 128);
+        cudaMemsetAsync(buf, 0, 128, s);
         HaloGeom gp = g;
         gp.prof = buf;
         RAMNET_CUDA(cudaLaunchKernelEx(&cfg, conv_tcgen05_halo_kernel<EPI, true, HP, UP>, m0, m1, mw, um, gp, ep));
-        unsigned long long hbuf[8];
-        cudaMemcpyAsync(hbuf, buf, 64, cudaMemcpyDeviceToHost, s);
+        unsigned long long hbuf[16];
+        cudaMemcpyAsync(hbuf, buf, 128, cudaMemcpyDeviceToHost, s);
         cudaStreamSynchronize(s);
+        {
+            const double e0 = (double)~hbuf[8];
+            fprintf(stderr, "[ramnet-prof] wall clock (us after the first CTA's entry): setup done %.1f .. %.1f | loops done %.1f .. %.1f | "
+                            "last cluster sync %.1f\n", ((double)~hbuf[12] - e0) / 1e3, ((double)hbuf[9] - e0) / 1e3,
+                    ((double)~hbuf[13] - e0) / 1e3, ((double)hbuf[10] - e0) / 1e3, ((double)hbuf[11] - e0) / 1e3);
+        }
         const double n = pairs;     // MMA counters: one issuer per pair; producer / epilogue counters: two CTAs per pair
         fprintf(stderr, "[ramnet-prof] pairs=%d items=%d per-pair kcycles: mma_total=%.1f wait_a_full=%.1f wait_b_full=%.1f "
                         "wait_acc_empty=%.1f | prodA_wait_empty=%.1f prodB_wait_empty=%.1f | epi(avg of warps) "

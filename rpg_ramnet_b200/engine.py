@@ -326,16 +326,30 @@ def pred_layer(x, pred_conv, norm_mod, norm_kind, training, return_logits=False,
 # CUDA-graph runner (inference): one captured graph per (pass type, state direction)
 # ------------------------------------------------------------------------------------------
 class GraphRunner:
-    """Replays a whole RAM-Net pass (head -> encoders -> state update -> decoder -> depth) as ONE CUDA
-    graph launch instead of ~30 Python-issued kernel launches (the reference issues ~70 per pass,
-    SURVEY.md §3.3).  Recurrent state ping-pongs between two persistent buffer sets so no state copy is
-    ever made: the graph for direction s reads set s and writes set 1-s.
+    """Replays a RAM-Net pass as TWO CUDA-graph launches instead of ~30 Python-issued kernel launches (the reference
+    issues ~70 per pass): the FRONT (head -> encoders -> state update, statenet.py:204-288) and the BACK
+    (residual blocks -> decoders -> depth, statenet.py:290-315).  The back of a pass reads nothing but the super states
+    the front wrote, and the front of the NEXT pass reads those same states and writes the other buffer set -- so the
+    next front runs on a second stream UNDER the current back (round 2).  Every conv kernel is a persistent grid of
+    one CTA (pair) per SM, so the overlap does not share SMs: it fills the SMs a kernel leaves idle in its last wave
+    and during its epilogue tail (at levels 1-2 a layer is 64-128 work items on 74 CTA pairs).
+    RAMNET_PASS_OVERLAP=0 keeps everything on the caller's stream.
+
+    Recurrent state ping-pongs between two persistent buffer sets so no state copy is ever made: the front for
+    direction s reads set s and writes set 1-s.
 
     Aliasing contract: the state tensors returned by a pass ARE these persistent buffers; they stay
     valid until the second-next pass overwrites them (callers that carry only the latest state —
     trainer/lstm_trainer.py:380, test.py:380 — are unaffected).  A caller that hands back the OLDER of the two
     sets (state kept for two or more passes, already overwritten) gets a RamnetError instead of silently reading
-    recycled memory; clone the states to keep them longer.  Depth maps are returned as fresh tensors."""
+    recycled memory; clone the states to keep them longer.  Depth maps are returned as fresh tensors.
+
+    `nxt` (run): the pass that WILL follow, when the caller knows it (ERGB2DepthRecurrent.forward does, within one
+    item): its front is launched before this pass's back.  Device inputs are copied into the staging slot after
+    everything already queued on the caller's stream (they may just have been produced there) unless the owner sets
+    `inputs_static` (inputs resident and not written by queued work: the copy then does not wait for the caller's
+    stream and the first front of an item can run under the last back of the previous one); host inputs come over
+    the copy stream and never wait for it."""
 
     def __init__(self, net, B, H, W, device):
         self.net, self.B, self.H, self.W, self.device = net, B, H, W, device
@@ -343,12 +357,17 @@ class GraphRunner:
         self.sets = [self._alloc_states(), self._alloc_states()]
         self.x_in, self.graphs = {}, {}
         self.param_sig = None
-        self.pool = None
+        self.pools = {'front': None, 'back': None}   # fronts never overlap fronts, backs never overlap backs
         # host inputs: staged H2D on a copy stream into a 2-slot ring per pass type, so the copy of the next pass
         # runs under the kernels of the current one (the reference copies on the compute stream, model.py:177,200)
         self.copy_stream = torch.cuda.Stream(device=device)
+        self.overlap = os.environ.get('RAMNET_PASS_OVERLAP', '1') != '0'
+        self.front_stream = torch.cuda.Stream(device=device) if self.overlap else None
+        self.inputs_static = False
         self.slot_ctr = {}
         self.last_dst = None        # buffer set the most recent pass wrote (the only one a caller may hand back)
+        self.back_done = [None, None]   # event: the last back that read set k has finished (before a front rewrites it)
+        self.pending = None         # front launched ahead for the announced next pass
 
     def _alloc_states(self):
         out = []
@@ -384,50 +403,91 @@ class GraphRunner:
             tuple((b.data_ptr(), b._version) for b in self.net.buffers()) + \
             (self.net.training, self.net._kind(), _WEIGHT_EPOCH)
 
-    def run(self, which, x, prev_super):
+    def run(self, which, x, prev_super, nxt=None):
+        cur = torch.cuda.current_stream(self.device)
         sig = self._sig()
         if sig != self.param_sig:           # weights changed (optimizer step / load_state_dict): re-capture
+            if self.pending is not None:
+                raise RamnetError('cuda_graphs: the weights changed between two passes of one item')
             self.graphs.clear()
             self.param_sig = sig
         src = self._which_set(prev_super)
-        if src is not None and self.last_dst is not None and src != self.last_dst:
-            raise RamnetError('cuda_graphs: the states passed in are the runner\'s buffer set that the previous pass has '
-                              'already overwritten (states returned by a pass are valid for one further pass only); '
-                              'clone() states that must live longer')
-        if src is None:                     # foreign or initial state: bring it into set 0
-            src = 0
-            mine = self._flat(self.sets[0])
-            if prev_super is None:
-                for t in mine:
-                    t.zero_()
-            else:
-                for t, f in zip(mine, self._flat(prev_super)):
-                    t.copy_(f)
+        fr, self.pending = self.pending, None
+        if fr is not None:
+            if fr['which'] != which or fr['x'] is not x or src != fr['src']:
+                raise RamnetError('cuda_graphs: the pass announced to the previous run() call (nxt=) is not the one being '
+                                  'run; its front has already been launched on the announced input and states')
+        else:
+            if src is not None and self.last_dst is not None and src != self.last_dst:
+                raise RamnetError('cuda_graphs: the states passed in are the runner\'s buffer set that the previous pass has '
+                                  'already overwritten (states returned by a pass are valid for one further pass only); '
+                                  'clone() states that must live longer')
+            foreign = src is None
+            if foreign:                     # foreign or initial state: bring it into set 0 (on the caller's stream)
+                src = 0
+                if self.back_done[0] is not None:
+                    cur.wait_event(self.back_done[0])
+                mine = self._flat(self.sets[0])
+                if prev_super is None:
+                    for t in mine:
+                        t.zero_()
+                else:
+                    for t, f in zip(mine, self._flat(prev_super)):
+                        t.copy_(f)
+            fr = self._launch_front(which, x, src, after_caller=foreign)
+        dst = fr['dst']
+        if nxt is not None and self.overlap:
+            self.pending = self._launch_front(nxt[0], nxt[1], dst)
+        if fr['event'] is not None:
+            cur.wait_event(fr['event'])
+        key = ('back', dst)
+        entry = self.graphs.get(key)
+        if entry is None:
+            entry = self.graphs[key] = self._capture_back(dst)
+        graph, pred = entry
+        graph.replay()
+        if self.overlap:
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self.back_done[dst] = ev
+        self.last_dst = dst
+        return self.sets[dst], pred.clone()
+
+    def _launch_front(self, which, x, src, after_caller=False):
+        """Stages the input and replays the front graph of a pass reading buffer set `src` (on the front stream when
+        passes overlap).  Returns what run() needs to finish the pass."""
+        cur = torch.cuda.current_stream(self.device)
         dst = 1 - src
         slot = self.stage(which, x)
         if slot is None:                    # ring full of inputs staged ahead but never consumed: drop them
             for sl in self.x_in[which]:
                 sl['staged_for'] = None
             slot = self.stage(which, x)
-        cur = torch.cuda.current_stream(self.device)
-        if slot['ready'] is not None:
-            cur.wait_event(slot['ready'])
-            slot['ready'] = None
-        key = (which, src, slot['idx'])
+        key = ('front', which, src, slot['idx'])
         entry = self.graphs.get(key)
         if entry is None:
-            entry = self._capture(which, slot['buf'], src, dst)
-            self.graphs[key] = entry
-        graph, pred = entry
-        graph.replay()
-        slot['done'].record(cur)            # the staging slot may be overwritten once this pass has read it
+            entry = self.graphs[key] = self._capture_front(which, slot['buf'], src, dst)
+        fs = self.front_stream if self.overlap else cur
+        if fs is not cur and after_caller:
+            fs.wait_stream(cur)             # the state was copied in on the caller's stream
+        if slot['ready'] is not None:
+            fs.wait_event(slot['ready'])
+            slot['ready'] = None
+        if fs is not cur and self.back_done[dst] is not None:
+            fs.wait_event(self.back_done[dst])      # the back of the second-last pass still reads the set written here
+        event = None
+        with torch.cuda.stream(fs):
+            entry[0].replay()
+            slot['done'].record(fs)         # the staging slot may be overwritten once this front has read it
+            if fs is not cur:
+                event = torch.cuda.Event()
+                event.record(fs)
         slot['staged_for'] = None
-        self.last_dst = dst
-        return self.sets[dst], pred.clone()
+        return {'which': which, 'x': x, 'src': src, 'dst': dst, 'event': event}
 
     def stage(self, which, x):
         """Brings the input of the next `which` pass into a staging slot and returns the slot.  Host tensors go
-        over the copy stream (asynchronously when pinned); device tensors are copied on the compute stream.
+        over the copy stream (asynchronously when pinned); device tensors are copied on the stream the front runs on.
         Idempotent per tensor: forward() stages the inputs of later passes ahead of time."""
         ring = self.x_in.get(which)
         if ring is None or ring[0]['buf'].shape != x.shape:
@@ -435,7 +495,7 @@ class GraphRunner:
                      'ready': None, 'done': torch.cuda.Event(), 'staged_for': None} for i in range(2)]
             self.x_in[which] = ring
             self.slot_ctr[which] = 0
-            self.graphs = {k: v for k, v in self.graphs.items() if k[0] != which}
+            self.graphs = {k: v for k, v in self.graphs.items() if not (k[0] == 'front' and k[1] == which)}
         for slot in ring:
             if slot['staged_for'] is x:
                 return slot
@@ -445,7 +505,16 @@ class GraphRunner:
         self.slot_ctr[which] += 1
         slot['staged_for'] = x
         if x.is_cuda:
-            slot['buf'].copy_(x, non_blocking=True)
+            cur = torch.cuda.current_stream(self.device)
+            if self.overlap:                    # same stream as the fronts: ordered after the slot's last reader
+                fs = self.front_stream
+                if not self.inputs_static:
+                    fs.wait_stream(cur)         # x may have been produced by work queued on the caller's stream
+                with torch.cuda.stream(fs):
+                    slot['buf'].copy_(x, non_blocking=True)
+                x.record_stream(fs)
+            else:
+                slot['buf'].copy_(x, non_blocking=True)
             slot['ready'] = None
         else:
             cs = self.copy_stream
@@ -456,20 +525,32 @@ class GraphRunner:
                 slot['ready'].record(cs)
         return slot
 
-    def _capture(self, which, xin, src, dst):
-        net = self.net
-        keep = [t.clone() for t in self._flat(self.sets[dst])]     # warm-up must not disturb live state
+    def _capture(self, kind, fn, dst):
+        """Warm-up (weight cache, kernel attributes) + capture of `fn`, with the live contents of buffer set `dst`
+        preserved.  Captures happen a handful of times per runner: the device is drained around them so that neither
+        the warm-up nor the restore can race with a pass in flight on the other stream."""
+        torch.cuda.synchronize(self.device)
+        keep = [t.clone() for t in self._flat(self.sets[dst])]
         side = torch.cuda.Stream(device=self.device)
-        side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
-            for _ in range(2):                                      # populates weight cache + kernel attributes
-                net._pass(which, xin, self.sets[src], None, out_states=self.sets[dst])
-        torch.cuda.current_stream(self.device).wait_stream(side)
+            for _ in range(2):
+                fn()
+        side.synchronize()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, pool=self.pool):
-            _, _, pred = net._pass(which, xin, self.sets[src], None, out_states=self.sets[dst])
-        if self.pool is None:
-            self.pool = graph.pool()
+        with torch.cuda.graph(graph, pool=self.pools[kind]):
+            out = fn()
+        if self.pools[kind] is None:
+            self.pools[kind] = graph.pool()
         for t, k in zip(self._flat(self.sets[dst]), keep):
             t.copy_(k)
-        return graph, pred
+        torch.cuda.synchronize(self.device)
+        return graph, out
+
+    def _capture_front(self, which, xin, src, dst):
+        net = self.net
+        graph, _ = self._capture('front', lambda: net._encode(which, xin, self.sets[src], None, out_states=self.sets[dst]), dst)
+        return graph, None
+
+    def _capture_back(self, dst):
+        net = self.net
+        return self._capture('back', lambda: net.forward_decoder(self.sets[dst]), dst)

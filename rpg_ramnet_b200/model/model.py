@@ -39,6 +39,9 @@ class BaseERGB2Depth(BaseModel):
         self.mma_kind = config.get('mma_kind', None)
         # optional: replay each pass as one CUDA graph (inference; see engine.GraphRunner for the aliasing contract)
         self.cuda_graphs = bool(config.get('cuda_graphs', False))
+        # cuda_graphs: device-resident inputs are not being written by work still queued on the caller's stream, so the
+        # runner need not order its input copies after that stream (engine.GraphRunner)
+        self.inputs_static = bool(config.get('inputs_static', False))
         self.gpu = torch.device('cuda:' + str(config['gpu']))
 
 
@@ -71,11 +74,14 @@ class ERGB2DepthRecurrent(BaseERGB2Depth):
         self.max_num_channels = self.base_num_channels * pow(2, self.num_encoders)
         self._runners = {}
 
-    def _run_pass(self, which, x, prev_super_states, last):
-        """forward_events / forward_images + forward_decoder, eagerly or as one CUDA-graph replay."""
+    def _run_pass(self, which, x, prev_super_states, last, nxt=None):
+        """forward_events / forward_images + forward_decoder, eagerly or as CUDA-graph replays.  `nxt`: the (which, x)
+        of the pass that follows within the same item, so that the runner can start it under this pass's decoder."""
         net = self.statenetphasedrecurrent
         if self._graphs_active():
-            s, pred = self._runner(x).run(which, x, prev_super_states)
+            runner = self._runner(x)
+            runner.inputs_static = self.inputs_static
+            s, pred = runner.run(which, x, prev_super_states, nxt)
             return s, {'encoders': [None] * net.num_encoders, 'state_comb': list(s)}, pred
         x = x.to(self.gpu, non_blocking=True)
         if prev_super_states is None:
@@ -133,7 +139,7 @@ class ERGB2DepthRecurrent(BaseERGB2Depth):
             for k in range(n_event_passes):
                 key = 'events{}'.format(k)
                 self._stage_ahead(plan[k:])
-                s, l, predictions[key] = self._run_pass(which, item[key], prev_super_states, last)
+                s, l, predictions[key] = self._run_pass(which, item[key], prev_super_states, last, nxt=plan[k + 1])
                 super_states[key], states_lstm[key] = s, l
                 prev_super_states, last = s, l
         if (not bool(bl)) or bl == 'rgb' or (bl == 'e' and self.loss_composition != 'image'):

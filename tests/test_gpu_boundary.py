@@ -258,3 +258,41 @@ def test_inference_output_stage_matches_test_py_restatement():
             assert abs(float(scale[n]) - float(want_scale)) <= 1e-5 * abs(float(want_scale))
     assert torch.isnan(scale[2])                       # NaN in the target propagates, as in the reference
     assert float(bgr_gt[2].reshape(-1, 3).float().std(0).max()) == 0.0      # one colour for the NaN-carrying ground truth
+
+
+@pytest.mark.parametrize('mode', ['host_pinned', 'device_static', 'device', 'no_overlap'])
+def test_graph_runner_pass_overlap_is_bit_identical_to_eager(mode, monkeypatch):
+    """Round 2: the front of the next pass (head, encoders, state update) runs on a second stream under the decoder of
+    the current one.  Same kernels on the same data => bit-identical depth maps and states over a long sequence, for
+    host inputs (copy stream), device inputs ordered after the caller's stream, and device inputs declared static."""
+    import rpg_ramnet_b200 as R
+    if mode == 'no_overlap':
+        monkeypatch.setenv('RAMNET_PASS_OVERLAP', '0')
+    cfg = dict(CFG, every_x_rgb_frame=2)
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        eager = R.ERGB2DepthRecurrent(dict(cfg))
+        graphed = R.ERGB2DepthRecurrent(dict(cfg, cuda_graphs=True, inputs_static=(mode == 'device_static')))
+    graphed.load_state_dict(eager.state_dict())
+    eager.eval().to(dev())
+    graphed.eval().to(dev())
+    seq = O.synth_sequence(2, 64, 96, 12, 2, seed=5, with_targets=False)
+    if mode == 'host_pinned':
+        seq_g = [{k: v.pin_memory() for k, v in it.items()} for it in seq]
+    else:
+        seq_g = [{k: v.to(dev()) for k, v in it.items()} for it in seq]
+    torch.cuda.synchronize()
+    sa = sb = None
+    la = lb = {'events0': None, 'events1': None, 'image': None}
+    with torch.no_grad():
+        for t, (it_a, it_b) in enumerate(zip(seq, seq_g)):
+            pa, sa_d, la = eager(it_a, sa, la)
+            pb, sb_d, lb = graphed(it_b, sb, lb)
+            sa, sb = sa_d['image'], sb_d['image']
+            for k in pa:
+                assert torch.equal(pa[k], pb[k]), (mode, t, k)
+            for x, y in zip(sa, sb):
+                assert torch.equal(x, y), (mode, t)
+    runner = next(iter(graphed._runners.values()))
+    assert runner.overlap == (mode != 'no_overlap')
+    assert {k[0] for k in runner.graphs} == {'front', 'back'}
