@@ -92,9 +92,12 @@ enum {
                                    input: desc.H/W are the input's, y0 is [N, Cout, 2H, 2W].  w_packed comes from
                                    ramnet_pack_weights_upconv (collapsed taps of the 4 output phases + border segments).
                                    Epilogues: BIAS_RELU, BIAS_RELU_ADD, BIAS_RELU_PRED.  TF32 path, x1 = NULL. */
-    RAMNET_FLAG_S2SEG = 8       /* ramnet_conv_fwd: 5x5 stride-2 convolution as four parity-plane K segments (multi-stage
+    RAMNET_FLAG_S2SEG = 8,      /* ramnet_conv_fwd: 5x5 stride-2 convolution as four parity-plane K segments (multi-stage
                                    halos); w_packed from ramnet_pack_weights_s2seg ([27 taps][Cout][Cin], the (1,1) plane
                                    padded to 6 taps).  Epilogues BIAS, BIAS_RELU; TF32 path, x1 = NULL. */
+    RAMNET_FLAG_SM_TIME = 16    /* ramnet_conv_fwd planning hint: the caller runs this launch concurrently with kernels of
+                                   another stream, so the tile plan minimises SM time (items / SMs) instead of the makespan
+                                   of a kernel alone on the GPU (ceil(items / SMs) waves).  Results are unaffected. */
 };
 
 /* One implicit-GEMM convolution:  y[m, n] = epi( sum_{tap,c} x[pix(m,tap), c] * w[tap, n, c] ).

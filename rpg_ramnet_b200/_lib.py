@@ -18,6 +18,7 @@ FLAG_ROUND_TF32 = 1
 FLAG_HPACK = 2
 FLAG_UPCONV = 4
 FLAG_S2SEG = 8
+FLAG_SM_TIME = 16
 LOSS_LOG_SPACE = 1
 WGRAD_FULL, WGRAD_PARTIAL_FIRST, WGRAD_PARTIAL_ADD, WGRAD_FINALIZE = range(4)
 RAMNET_EUNSUPPORTED = -3

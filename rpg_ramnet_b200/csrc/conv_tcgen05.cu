@@ -1787,8 +1787,15 @@ double halo_cost(const ramnet_handle *h, const ramnet_conv_desc *d, const HaloGe
                               : (double)ntiles * (g.BN / 32.0 + 0.5) * 900.0 + 500.0;
     const double per_item = g.nbuf == 2 ? (main > epi ? main : epi) + 300.0 : main + epi;
     const int workers = g.pair ? h->sm_count / 2 : h->sm_count;
-    const int64_t rounds = (g.items + workers - 1) / workers;
-    double cost = (double)rounds * per_item + (g.nbuf == 2 ? epi : 0.0) + 4000.0;
+    // Weight of the wave quantisation in the plan cost.  1 = makespan of a kernel that has the GPU to itself:
+    // ceil(items / workers) rounds.  0 (RAMNET_FLAG_SM_TIME) = SM time: items / workers rounds -- the right measure when
+    // another stream's kernel takes the SMs this one leaves idle in its last wave (engine.GraphRunner overlaps passes;
+    // measured 5020 -> 5137 maps/s).  RAMNET_PLAN_WAVES overrides for A/B runs.
+    static const double wave_env = [] { const char *e = getenv("RAMNET_PLAN_WAVES"); return e ? atof(e) : -1.0; }();
+    const double wave_w = wave_env >= 0.0 ? wave_env : ((d->flags & RAMNET_FLAG_SM_TIME) ? 0.0 : 1.0);
+    const double rounds_up = (double)((g.items + workers - 1) / workers), rounds_fr = (double)g.items / workers;
+    const double rounds = wave_w * rounds_up + (1.0 - wave_w) * (rounds_fr < 1.0 ? 1.0 : rounds_fr);
+    double cost = rounds * per_item + (g.nbuf == 2 ? epi : 0.0) + 4000.0;
     // stride 2: one 4-plane halo per item and a single K chunk for the first encoder -- the halo fetch is exposed and the
     // model above underestimates both modes by ~2x; measured (enc0, 32->64): pair 2x1 55 us vs single 1x1 67 us
     if (d->stride == 2 && !g.pair) cost *= 1.25;

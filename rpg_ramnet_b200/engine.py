@@ -532,12 +532,14 @@ class GraphRunner:
         torch.cuda.synchronize(self.device)
         keep = [t.clone() for t in self._flat(self.sets[dst])]
         side = torch.cuda.Stream(device=self.device)
-        with torch.cuda.stream(side):
+        # overlapping passes: the tile planner minimises SM time, not the makespan of a kernel alone on the GPU
+        hint = ops.FLAG_SM_TIME if self.overlap else 0
+        with ops.plan_flags(hint), torch.cuda.stream(side):
             for _ in range(2):
                 fn()
         side.synchronize()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, pool=self.pools[kind]):
+        with ops.plan_flags(hint), torch.cuda.graph(graph, pool=self.pools[kind]):
             out = fn()
         if self.pools[kind] is None:
             self.pools[kind] = graph.pool()

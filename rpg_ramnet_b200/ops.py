@@ -4,6 +4,7 @@ Activations are fp32 "pixel-major" tensors: logical shape [N, C, H, W] with chan
 strides, i.e. the memory is NHWC as include/ramnet_b200.h specifies.  PyTorch is used for device
 memory and streams only.
 """
+import contextlib
 import ctypes
 import os
 from typing import Optional
@@ -12,7 +13,7 @@ import torch
 
 from . import _lib
 from ._lib import (ConvDesc, EPI_BIAS, EPI_BIAS_ADD, EPI_BIAS_RELU, EPI_BIAS_RELU_ADD, EPI_BIAS_RELU_PRED, EPI_BIAS_RES_RELU, EPI_GRU_OUT,  # noqa
-                   EPI_GRU_RU, EPI_LSTM, FLAG_HPACK, FLAG_ROUND_TF32, FLAG_S2SEG, FLAG_UPCONV, MMA_FP32, MMA_TF32, check)
+                   EPI_GRU_RU, EPI_LSTM, FLAG_HPACK, FLAG_ROUND_TF32, FLAG_S2SEG, FLAG_SM_TIME, FLAG_UPCONV, MMA_FP32, MMA_TF32, check)
 
 
 def _stream(t: torch.Tensor):
@@ -212,6 +213,21 @@ def pack_weights_hpack(w_oihw: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# Planning hints OR-ed into every conv launch descriptor (engine.GraphRunner sets FLAG_SM_TIME while it captures passes
+# that will overlap on two streams).
+_PLAN_FLAGS = [0]
+
+
+@contextlib.contextmanager
+def plan_flags(flags: int):
+    old = _PLAN_FLAGS[0]
+    _PLAN_FLAGS[0] = old | flags
+    try:
+        yield
+    finally:
+        _PLAN_FLAGS[0] = old
+
+
 def s2seg_eligible(Cin: int, Cout: int, ksize: int, stride: int, mma_kind: int) -> bool:
     """5x5 stride-2 single-source layers (the encoders' strided convs) run as four parity-plane K segments
     (RAMNET_FLAG_S2SEG): one plane per pipeline stage instead of all four in one.  RAMNET_S2SEG=0 disables."""
@@ -268,7 +284,7 @@ def conv_up_fwd(x: torch.Tensor, w_packed_up: torch.Tensor, bias: Optional[torch
             _check_nhwc(aux0, 'conv_up_fwd aux0')
             if tuple(aux0.shape) != (N, Cout, 2 * H, 2 * W):
                 raise _lib.RamnetError(f'conv_up_fwd: aux0 shape {tuple(aux0.shape)} != {(N, Cout, 2 * H, 2 * W)}')
-    flags = FLAG_UPCONV | (FLAG_ROUND_TF32 if round_tf32 else 0)
+    flags = FLAG_UPCONV | (FLAG_ROUND_TF32 if round_tf32 else 0) | _PLAN_FLAGS[0]
     d = ConvDesc(N, H, W, Cin, 0, Cout, 5, 1, epilogue, MMA_TF32, flags, 0)
     with _Prof('conv', 2.0 * N * (2 * H) * (2 * W) * Cout * Cin * 25, dev,      # algorithmic FLOPs of the reference graph
                tag=PROFILE is not None and f'upconv {H}x{W} {Cin}->{Cout} e{epilogue}'):
@@ -363,6 +379,7 @@ def conv_fwd(x0: torch.Tensor, x1: Optional[torch.Tensor], w_packed: torch.Tenso
     flags = (FLAG_ROUND_TF32 if round_tf32 else 0) | (FLAG_HPACK if getattr(w_packed, '_ramnet_hpack', False) else 0)
     if getattr(w_packed, '_ramnet_s2seg', False):
         flags |= FLAG_S2SEG
+    flags |= _PLAN_FLAGS[0]
     d = ConvDesc(N, H, W, C0, C1, Cout, ksize, stride, epilogue, mma_kind, flags, 0)
     lib = _lib.load()
     nws = lib.ramnet_conv_workspace_bytes(ctypes.byref(d))
