@@ -17,6 +17,8 @@ weight-gradient partial tiles, a column-sum pass over dZ for the bias and an Acc
 Shapes the tap-packed kernel does not cover, FP32 mode, or RAMNET_WGRAD_DEFER=0 fall back to one full
 `ramnet_conv_wgrad` per call, accumulated into `.grad` directly.
 """
+import os
+
 import torch
 
 from . import ops
@@ -39,23 +41,53 @@ def _grad_of(p):
     return p.grad
 
 
+# Weight gradients feed nothing but the optimizer, so they run on a second stream beside the data-gradient chain that
+# BPTT serialises (round 2; RAMNET_WGRAD_STREAM=0 keeps them on the backward stream).  Both are persistent full-GPU
+# kernels: the gain is the SMs one leaves idle in its last wave, as for the inference passes (engine.GraphRunner).
+_WGRAD_STREAMS = {}
+
+
+def _wgrad_stream(device):
+    if os.environ.get('RAMNET_WGRAD_STREAM', '1') == '0':
+        return None
+    s = _WGRAD_STREAMS.get(device)
+    if s is None:
+        s = _WGRAD_STREAMS[device] = torch.cuda.Stream(device=device)
+    return s
+
+
 class _Deferred:
     """Per-process registry of the weight-gradient accumulators that hold partial tiles of the running backward pass."""
     pending = []            # (accumulator, targets) with targets = [(parameter, row_begin, row_end)] in dW row order
     queued = False
+    forked = []             # (backward stream, side stream) pairs to join when the backward pass ends
 
     @classmethod
-    def note(cls, acc, targets):
-        if not any(a is acc for a, _ in cls.pending):
-            cls.pending.append((acc, targets))
+    def _queue(cls):
         if not cls.queued:
             cls.queued = True
             torch.autograd.Variable._execution_engine.queue_callback(cls.flush)
 
     @classmethod
+    def note(cls, acc, targets):
+        if not any(a is acc for a, _ in cls.pending):
+            cls.pending.append((acc, targets))
+        cls._queue()
+
+    @classmethod
+    def fork(cls, cur, side):
+        """The side stream now holds work that `.grad` depends on: flush() joins it back into `cur`."""
+        if not any(c == cur and s_ == side for c, s_ in cls.forked):
+            cls.forked.append((cur, side))
+        cls._queue()
+
+    @classmethod
     def flush(cls):
         """End of the backward pass: one split sum + scatter per layer, accumulated into the parameters' .grad."""
         pending, cls.pending, cls.queued = cls.pending, [], False
+        forked, cls.forked = cls.forked, []
+        for cur, side in forked:
+            cur.wait_stream(side)
         with torch.no_grad():
             for acc, targets in pending:
                 if len(targets) == 1:
@@ -88,6 +120,21 @@ def _accumulator(weight, tag, builder):
 def _weight_grad(weights, dz, x0, x1, Cout, k, stride, kind, head=None):
     """dW of one fused conv.  `weights`: [(parameter, row_begin, row_end)].  Deferred when possible, else a full
     conv_wgrad accumulated into .grad now."""
+    side = _wgrad_stream(dz.device)
+    if side is not None:
+        cur = torch.cuda.current_stream(dz.device)
+        side.wait_stream(cur)                      # dz was produced on the backward stream just now
+        with torch.cuda.stream(side):
+            _weight_grad_on_stream(weights, dz, x0, x1, Cout, k, stride, kind, head)
+        for t in (dz, x0, x1):                     # freed by the backward stream while the side stream may still read them
+            if t is not None:
+                t.record_stream(side)
+        _Deferred.fork(cur, side)
+        return
+    _weight_grad_on_stream(weights, dz, x0, x1, Cout, k, stride, kind, head)
+
+
+def _weight_grad_on_stream(weights, dz, x0, x1, Cout, k, stride, kind, head):
     w0 = weights[0][0]
     tag = (tuple(dz.shape), tuple(x0.shape), None if x1 is None else tuple(x1.shape), stride, kind, head)
     if head is None:
@@ -237,6 +284,8 @@ class ConvFn(torch.autograd.Function):
         if x1 is not None and ctx.needs_input_grad[1]:
             dx1 = _dgrad(dz, weight, kind, stride, C0, Ct - C0, x1.shape[2:])
         dres = dz if (has_res and ctx.needs_input_grad[2]) else None
+        if dres is not None and _wgrad_stream(dz.device) is not None:
+            dres = dz.clone()      # autograd may accumulate into a returned gradient in place; the side stream still reads dz
         return dx0, dx1, dres, None, None, None, None, None, None, None
 
 
