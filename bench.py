@@ -259,6 +259,7 @@ def train_leg(args, torch, world, rank, local, dev, graphs):
     items = synth_sequence(B, H, W, L, K_EVENTS, seed=2 + rank, with_targets=True)
     items = [{k: v.to(dev) for k, v in it.items()} for it in items]
     keys = ['events0', 'image']
+    model.inputs_static = True      # resident inputs, written once above: the model's front stream need not wait for them
 
     def step():
         opt.zero_grad()

@@ -61,6 +61,7 @@ class _Deferred:
     pending = []            # (accumulator, targets) with targets = [(parameter, row_begin, row_end)] in dW row order
     queued = False
     forked = []             # (backward stream, side stream) pairs to join when the backward pass ends
+    streams = []            # streams backward nodes wrote parameter gradients on (the model's front stream, the caller's)
 
     @classmethod
     def _queue(cls):
@@ -75,6 +76,12 @@ class _Deferred:
         cls._queue()
 
     @classmethod
+    def note_stream(cls, cur):
+        if not any(c == cur for c in cls.streams):
+            cls.streams.append(cur)
+        cls._queue()
+
+    @classmethod
     def fork(cls, cur, side):
         """The side stream now holds work that `.grad` depends on: flush() joins it back into `cur`."""
         if not any(c == cur and s_ == side for c, s_ in cls.forked):
@@ -86,8 +93,14 @@ class _Deferred:
         """End of the backward pass: one split sum + scatter per layer, accumulated into the parameters' .grad."""
         pending, cls.pending, cls.queued = cls.pending, [], False
         forked, cls.forked = cls.forked, []
+        streams, cls.streams = cls.streams, []
         for cur, side in forked:
             cur.wait_stream(side)
+        if streams:       # our nodes write .grad themselves (no AccumulateGrad), so the engine does not join their streams
+            amb = torch.cuda.current_stream(streams[0].device)
+            for cur in streams:
+                if cur != amb:
+                    amb.wait_stream(cur)
         with torch.no_grad():
             for acc, targets in pending:
                 if len(targets) == 1:
@@ -121,8 +134,9 @@ def _weight_grad(weights, dz, x0, x1, Cout, k, stride, kind, head=None):
     """dW of one fused conv.  `weights`: [(parameter, row_begin, row_end)].  Deferred when possible, else a full
     conv_wgrad accumulated into .grad now."""
     side = _wgrad_stream(dz.device)
+    cur = torch.cuda.current_stream(dz.device)
+    _Deferred.note_stream(cur)
     if side is not None:
-        cur = torch.cuda.current_stream(dz.device)
         side.wait_stream(cur)                      # dz was produced on the backward stream just now
         with torch.cuda.stream(side):
             _weight_grad_on_stream(weights, dz, x0, x1, Cout, k, stride, kind, head)

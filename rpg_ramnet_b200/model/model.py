@@ -83,10 +83,17 @@ class ERGB2DepthRecurrent(BaseERGB2Depth):
             runner.inputs_static = self.inputs_static
             s, pred = runner.run(which, x, prev_super_states, nxt)
             return s, {'encoders': [None] * net.num_encoders, 'state_comb': list(s)}, pred
+        static = self.inputs_static
+        if not x.is_cuda:
+            fs = net._front_stream_on(torch.device('cuda', self.gpu) if isinstance(self.gpu, int) else torch.device(self.gpu))
+            if fs is not None:          # host input: copied on the stream that consumes it, no tie to the caller's stream
+                with torch.cuda.stream(fs):
+                    x = x.to(self.gpu, non_blocking=True)
+                static = True
         x = x.to(self.gpu, non_blocking=True)
         if prev_super_states is None:
             prev_super_states = self._zero_states(x.shape[0], x.shape[2], x.shape[3])
-        return net._pass(which, x, prev_super_states, last)
+        return net._pass(which, x, prev_super_states, last, inputs_static=static)
 
     def _graphs_active(self):
         return self.cuda_graphs and self.statenetphasedrecurrent.graph_capable() and not self.training

@@ -5,6 +5,8 @@ and the same three entry points `forward_events`, `forward_images`, `forward_dec
 same argument and return structure.  The arithmetic is the fused CUDA graph of
 rpg_ramnet_b200/engine.py; activations and states are fp32 NHWC-strided [N,C,H,W] tensors.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -67,6 +69,20 @@ class BaseStateNet(nn.Module):
                               self.num_output_channels, 1, activation=None, norm=self.norm)
 
 
+def _flat_tensors(obj):
+    """Every tensor inside a (nested) state container: lists / tuples / dicts of tensors or None."""
+    if obj is None:
+        return []
+    if torch.is_tensor(obj):
+        return [obj]
+    if isinstance(obj, dict):
+        obj = list(obj.values())
+    out = []
+    for o in obj:
+        out.extend(_flat_tensors(o))
+    return out
+
+
 class StateNetPhasedRecurrent(BaseStateNet):
     def __init__(self, num_input_channels_rgb, num_input_channels_events, num_output_channels=1, skip_type='sum',
                  state_combination='sum', activation='sigmoid', num_encoders=4, base_num_channels=32,
@@ -126,6 +142,7 @@ class StateNetPhasedRecurrent(BaseStateNet):
         self.build_prediction_layer()
         self._mma_kind_name = mma_kind
         self._wcache = E.WeightCache()
+        self._front_streams, self._front_tok = {}, None
 
     # ---- configuration the CUDA graph supports ------------------------------------------------
     def _kind(self):
@@ -148,11 +165,54 @@ class StateNetPhasedRecurrent(BaseStateNet):
             raise RamnetError('only num_output_channels=1 is implemented')
 
     # ---- encoders -----------------------------------------------------------------------------
-    def _pass(self, which, x, prev_super_state, prev_states_lstm, out_states=None, return_logits=False):
+    def _pass(self, which, x, prev_super_state, prev_states_lstm, out_states=None, return_logits=False, inputs_static=False):
         """One full pass: encoder of one modality + state update + decoder.  `out_states` (optional) are
-        preallocated state buffers the new super states are written into (CUDA-graph runner)."""
-        s, l = self._encode(which, x, prev_super_state, prev_states_lstm, out_states)
+        preallocated state buffers the new super states are written into (CUDA-graph runner).
+
+        Eager path (training, cuda_graphs off), round 2: the FRONT (head, encoders, state update) runs on a second stream
+        and the decoder on the caller's, so the front of the next pass -- which needs this pass's states, not its
+        decoder -- runs under this pass's decoder; autograd replays every node on its forward stream, so the backward
+        pass overlaps the same way.  Everything returned is ordered on the caller's stream.  RAMNET_FRONT_STREAM=0
+        disables.  The front stream waits for the caller's stream only when it has to: new weights, states it did not
+        produce itself, or a device input that is not declared static."""
+        fs = self._front_stream(x)
+        if fs is None or out_states is not None:
+            s, l = self._encode(which, x, prev_super_state, prev_states_lstm, out_states)
+            return s, l, self.forward_decoder(s, return_logits)
+        cur = torch.cuda.current_stream(x.device)
+        tok = (E._WEIGHT_EPOCH, self.training) + tuple(p._version for p in self.parameters())
+        flat_prev = _flat_tensors(prev_super_state) + _flat_tensors(prev_states_lstm)
+        ours = all(getattr(t, '_ramnet_front', None) is fs for t in flat_prev)
+        if tok != self._front_tok or not ours or not inputs_static:
+            fs.wait_stream(cur)
+            self._front_tok = tok
+        with torch.cuda.stream(fs):
+            s, l = self._encode(which, x, prev_super_state, prev_states_lstm, None)
+            done = torch.cuda.Event()
+            done.record(fs)
+        x.record_stream(fs)
+        for t in flat_prev:
+            t.record_stream(fs)
+        for t in _flat_tensors(s) + _flat_tensors(l):     # read by the decoder / the caller on `cur`, by the next front on `fs`
+            t.record_stream(cur)
+            try:
+                t._ramnet_front = fs
+            except AttributeError:
+                pass
+        cur.wait_event(done)
         return s, l, self.forward_decoder(s, return_logits)
+
+    def _front_stream(self, x):
+        return self._front_stream_on(x.device) if x.is_cuda else None
+
+    def _front_stream_on(self, device):
+        if device.type != 'cuda' or os.environ.get('RAMNET_FRONT_STREAM', '1') == '0':
+            return None
+        device = torch.device('cuda', torch.cuda.current_device() if device.index is None else device.index)
+        fs = self._front_streams.get(device)
+        if fs is None:
+            fs = self._front_streams[device] = torch.cuda.Stream(device=device)
+        return fs
 
     def graph_capable(self):
         """CUDA-graph replay covers the configurations whose only recurrent state is the super state."""
