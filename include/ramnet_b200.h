@@ -310,12 +310,37 @@ int ramnet_lstm_bwd(ramnet_handle *h, const float *dh, const float *dc, const fl
                     const float *c_new, float *dz, float *dc_prev, float *db /* [4C], nn.Conv2d row order */, int64_t M,
                     int C, int flags, void *stream);
 /* pred + sigmoid adjoint: dx[m,c] = g*w[c] (= dskip), dw[c] += sum g*(x+skip)[m,c], db += sum g, g = ddepth*s(1-s);
- * skip may be NULL */
+ * skip may be NULL; depth NULL: ddepth is the gradient of the LOGITS (g = ddepth; a norm layer follows the pred conv) */
 int ramnet_pred_bwd(ramnet_handle *h, const float *ddepth, const float *depth, const float *x, const float *skip,
                     const float *w, float *dx, float *dw, float *db, int64_t M, int C, void *stream);
 /* adjoint of ramnet_upsample2x_add: dx (= dskip) [N,H,W,C] from dy [N,2H,2W,C] */
 int ramnet_upsample2x_bwd(ramnet_handle *h, const float *dy, float *dx, int N, int H, int W, int C,
                           void *stream);
+
+/* ---- live normalisation layers (config key norm = 'BN' | 'IN') ------------------------------------------- *
+ * Replaces nn.BatchNorm2d / nn.InstanceNorm2d where their statistics cannot be folded into the conv weights
+ * (model/submodules.py:21-24,29-30 ConvLayer, :52-55,60-61 TransposedConvLayer, :82-85,91-92 UpsampleConvLayer,
+ * :188-194,203-211 ResidualBlock): train mode (batch / instance statistics, running-statistics update with momentum
+ * and the unbiased variance), the ResidualBlock's InstanceNorm2d without running statistics (also in eval mode), and
+ * eval-mode norms that gradients flow through (RAMNET_NORM_RUNNING).  z = conv output [N, HW, C] NHWC;
+ * y = act((z - mean) * invstd * gamma + beta (+ res)).  gamma / beta / res / running_* may be NULL.
+ * sums: ramnet_norm_scratch_bytes(N, C) bytes of scratch; stats (out, [G, C, 2] floats = mean, invstd with G = N for
+ * RAMNET_NORM_INSTANCE else 1) is what ramnet_norm_bwd needs back. */
+#define RAMNET_NORM_INSTANCE 1   /* statistics per (sample, channel) instead of per channel over the batch */
+#define RAMNET_NORM_RUNNING 2    /* normalise with running_mean / running_var; nothing is updated */
+#define RAMNET_NORM_RELU 4
+#define RAMNET_NORM_SIGMOID 8
+#define RAMNET_NORM_ROUND_TF32 16 /* round the stored output (forward: y, backward: dz) to TF32 */
+size_t ramnet_norm_scratch_bytes(int N, int C);
+int ramnet_norm_fwd(ramnet_handle *h, const float *z, const float *res, const float *gamma, const float *beta,
+                    float *running_mean, float *running_var, double momentum, double eps, int N, int64_t HW, int C,
+                    int flags, double *sums, float *stats, float *y, void *stream);
+/* dz = gamma * invstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * act'(y), xhat = (z - mean) * invstd (the two
+ * means are zero under RAMNET_NORM_RUNNING); dres (nullable) = g; dgamma / dbeta (nullable, [C]) accumulate (+=).
+ * coef: [G, C, 2] floats of scratch. */
+int ramnet_norm_bwd(ramnet_handle *h, const float *dy, const float *y, const float *z, const float *stats,
+                    const float *gamma, int N, int64_t HW, int C, int flags, double *sums, float *coef, float *dz,
+                    float *dres, float *dgamma, float *dbeta, void *stream);
 
 /* ---- a-12  scale_invariant_loss ---------------------------------------- *
  * Replaces model/loss.py:6-9 (boolean-mask gathers + host sync).

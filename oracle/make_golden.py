@@ -63,7 +63,17 @@ CASES = {
     'unet':          ('ERGB2Depth', _cfg(num_bins_rgb=6), 2, 64, 64, 1, 12, 1.5),
     'transposed':    ('ERGB2DepthRecurrent', _cfg(every_x_rgb_frame=1, use_upsample_conv=False),
                       1, 64, 64, 2, 13, 1.5),
+    # live norm layers (round 2): train-mode batch / instance statistics + running-statistics update, and the
+    # ResidualBlock's InstanceNorm2d (no running statistics: instance statistics in eval mode too)
+    'bn_train':      ('ERGB2DepthRecurrent', _cfg(every_x_rgb_frame=1, norm='BN'), 2, 64, 64, 2, 14, 1.5),
+    'in_train':      ('ERGB2DepthRecurrent', _cfg(every_x_rgb_frame=1, norm='IN'), 2, 64, 64, 2, 15, 1.5),
+    'in_eval':       ('ERGB2DepthRecurrent', _cfg(every_x_rgb_frame=1, norm='IN'), 2, 64, 64, 2, 16, 1.5),
+    'bn_train_tconv_lstm': ('ERGB2DepthRecurrent', _cfg(every_x_rgb_frame=1, norm='BN', use_upsample_conv=False,
+                                                        state_combination='convlstm', recurrent_block_type='convlstm'),
+                            2, 64, 64, 2, 17, 1.5),
+    'unet_bn_train': ('ERGB2Depth', _cfg(num_bins_rgb=6, norm='BN'), 2, 64, 64, 2, 18, 1.5),
 }
+TRAIN_MODE = {'bn_train', 'in_train', 'bn_train_tconv_lstm', 'unet_bn_train'}
 
 
 scale_weights = O.scale_weights
@@ -92,6 +102,8 @@ def run_model_case(ns, name, spec):
     arch, cfg, B, H, W, L, seed, wscale = spec
     model = ref_import.build_model(ns, arch, cfg)
     scale_weights(model, wscale)
+    train = name in TRAIN_MODE
+    model.train(train)
     seq = seq_inputs(cfg, B, H, W, L, seed)
     K = cfg.get('every_x_rgb_frame', 1)
     out = {}
@@ -111,17 +123,23 @@ def run_model_case(ns, name, spec):
                     for j, t in enumerate(flat_supers(s)):
                         out[f'super/{l}/{key}/{j}'] = t[:, ::8, ::4, ::4].numpy().astype(np.float32)
             prev_super, prev_lstm = supers, lstm
-    out['meta'] = np.array(json.dumps(dict(arch=arch, config=cfg, B=B, H=H, W=W, L=L, seed=seed, wscale=wscale)))
+    if train:       # running statistics after the sequence (updated in place by every train-mode forward)
+        for n, t in model.state_dict().items():
+            if n.endswith(('running_mean', 'running_var', 'num_batches_tracked')):
+                out['buf/' + n] = t.numpy().copy()
+    out['meta'] = np.array(json.dumps(dict(arch=arch, config=cfg, B=B, H=H, W=W, L=L, seed=seed, wscale=wscale,
+                                           train=train)))
     np.savez_compressed(os.path.join(OUT, f'model_{name}.npz'), **out)
     print(name, 'ok', {k: v.shape for k, v in out.items() if k.startswith('pred/0')})
 
 
-def run_grad_case(ns):
+def run_grad_case(ns, fname='grads_shipped.npz', train=False, seed=21, **cfg_kw):
     """fwd+bwd of the trainer's loss mix (SI only) -> loss value + per-tensor grad digests."""
-    cfg = _cfg(every_x_rgb_frame=1)
-    B, H, W, L, seed = 2, 64, 64, 2, 21
+    cfg = _cfg(every_x_rgb_frame=1, **cfg_kw)
+    B, H, W, L = 2, 64, 64, 2
     model = ref_import.build_model(ns, 'ERGB2DepthRecurrent', cfg)
     scale_weights(model, 1.5)
+    model.train(train)
     seq = seq_inputs(cfg, B, H, W, L, seed)
     comp, wts = ['image', 'events0'], [1.0, 1.0]
     prev_super, prev_lstm = {'image': None}, {'events0': None, 'image': None}
@@ -143,10 +161,10 @@ def run_grad_case(ns):
     out['grad_sum'] = np.array([float(p.grad.double().sum()) for _, p in model.named_parameters()])
     for n, p in model.named_parameters():
         out['head/' + n] = p.grad.flatten()[:16].numpy().astype(np.float32)
-    out['meta'] = np.array(json.dumps(dict(config=cfg, B=B, H=H, W=W, L=L, seed=seed, wscale=1.5,
+    out['meta'] = np.array(json.dumps(dict(config=cfg, B=B, H=H, W=W, L=L, seed=seed, wscale=1.5, train=train,
                                            loss_composition=comp, loss_weights=wts)))
-    np.savez_compressed(os.path.join(OUT, 'grads_shipped.npz'), **out)
-    print('grads ok loss', loss.item())
+    np.savez_compressed(os.path.join(OUT, fname), **out)
+    print(fname, 'ok loss', loss.item())
 
 
 def run_loss_cases(ns):
@@ -232,6 +250,10 @@ def main():
         run_model_case(ns, name, spec)
     if not only or 'grads' in only:
         run_grad_case(ns)
+    if not only or 'grads_norm' in only:
+        run_grad_case(ns, 'grads_bn_train.npz', train=True, seed=22, norm='BN')
+        run_grad_case(ns, 'grads_in_train.npz', train=True, seed=23, norm='IN')
+        run_grad_case(ns, 'grads_bn_eval.npz', train=False, seed=24, norm='BN')
     if not only or 'misc' in only:
         run_loss_cases(ns)
         run_adam_case()

@@ -147,15 +147,33 @@ def _conv2d(x, w, b=None, **kw):
 # --------------------------------------------------------------------------
 # a-2/a-3  ConvLayer                    RAM_Net/model/submodules.py:8-35
 # --------------------------------------------------------------------------
+_TRAINING = False
+
+
+class training_mode:
+    """Context manager: norm layers behave as in model.train() -- BatchNorm2d / InstanceNorm2d(track_running_stats)
+    normalise with batch / instance statistics and update the running statistics held in the state dict IN PLACE
+    (momentum 0.1, unbiased variance), as nn.BatchNorm2d.forward / nn.InstanceNorm2d.forward do."""
+
+    def __enter__(self):
+        global _TRAINING
+        self.prev, _TRAINING = _TRAINING, True
+
+    def __exit__(self, *exc):
+        global _TRAINING
+        _TRAINING = self.prev
+
+
 def _norm_eval(sd: StateDict, prefix: str, y: Tensor, kind: str) -> Tensor:
-    """Eval-mode BatchNorm2d / InstanceNorm2d(track_running_stats=True) that
-    follows a conv (submodules.py:21-24,29-30).  Eval only: running stats."""
+    """BatchNorm2d / InstanceNorm2d(track_running_stats=True) that follows a conv (submodules.py:21-24,29-30).
+    Eval: running statistics.  Under `training_mode`: batch / instance statistics + running update."""
+    rm, rv = sd[prefix + '.running_mean'].detach(), sd[prefix + '.running_var'].detach()
     if kind == 'BN':
-        return F.batch_norm(y, sd[prefix + '.running_mean'], sd[prefix + '.running_var'],
-                            sd[prefix + '.weight'], sd[prefix + '.bias'], False, 0.0, 1e-5)
-    if kind == 'IN':  # affine=False default, running stats used in eval
-        return F.batch_norm(y, sd[prefix + '.running_mean'], sd[prefix + '.running_var'],
-                            None, None, False, 0.0, 1e-5)
+        if _TRAINING and (prefix + '.num_batches_tracked') in sd:
+            sd[prefix + '.num_batches_tracked'].add_(1)
+        return F.batch_norm(y, rm, rv, sd[prefix + '.weight'], sd[prefix + '.bias'], _TRAINING, 0.1, 1e-5)
+    if kind == 'IN':  # affine=False default; running stats used in eval, instance stats (+ update) in train mode
+        return F.instance_norm(y, rm, rv, None, None, _TRAINING, 0.1, 1e-5)
     return y
 
 

@@ -20,6 +20,7 @@ FLAG_UPCONV = 4
 FLAG_S2SEG = 8
 FLAG_SM_TIME = 16
 LOSS_LOG_SPACE = 1
+NORM_INSTANCE, NORM_RUNNING, NORM_RELU, NORM_SIGMOID, NORM_ROUND_TF32 = 1, 2, 4, 8, 16
 WGRAD_FULL, WGRAD_PARTIAL_FIRST, WGRAD_PARTIAL_ADD, WGRAD_FINALIZE = range(4)
 RAMNET_EUNSUPPORTED = -3
 
@@ -84,6 +85,11 @@ SIGNATURES = {
                                   c_int, c_void_p]),
     'ramnet_lstm_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_int64, c_int, c_int, c_void_p]),
+    'ramnet_norm_scratch_bytes': (c_size_t, [c_int, c_int]),
+    'ramnet_norm_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, c_int,
+                                c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ramnet_norm_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'ramnet_pred_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_int64, c_int, c_void_p]),
     'ramnet_upsample2x_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

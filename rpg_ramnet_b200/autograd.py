@@ -413,13 +413,14 @@ class TransposedConvFn(torch.autograd.Function):
       d weight = the stride-2 conv's weight gradient with the roles swapped: "dZ" operand = x + skip, "X" operand = dZ."""
 
     @staticmethod
-    def forward(ctx, x, skip, weight, bias, packed_w, kind):
+    def forward(ctx, x, skip, weight, bias, packed_w, kind, relu=True):
         Cin, Cout, k, _ = weight.shape
         N, _, H, W = x.shape
         up, xs = ops.zero_insert2x(x, 2 * H, 2 * W, skip=skip, want_sum=True)
-        y = ops.conv_fwd(up, None, packed_w, None if bias is None else bias.detach(), Cout, k, 1, ops.EPI_BIAS_RELU, kind)
+        y = ops.conv_fwd(up, None, packed_w, None if bias is None else bias.detach(), Cout, k, 1,
+                         ops.EPI_BIAS_RELU if relu else ops.EPI_BIAS, kind)
         ctx.save_for_backward(xs, y)
-        ctx.weight, ctx.bias, ctx.kind, ctx.has_skip = weight, bias, kind, skip is not None
+        ctx.weight, ctx.bias, ctx.kind, ctx.has_skip, ctx.relu = weight, bias, kind, skip is not None, relu
         return y
 
     @staticmethod
@@ -427,15 +428,21 @@ class TransposedConvFn(torch.autograd.Function):
         xs, y = ctx.saved_tensors
         weight, bias, kind = ctx.weight, ctx.bias, ctx.kind
         Cin, Cout, k, _ = weight.shape
-        dz = ops.relu_bwd(_nhwc(dy), y, round_tf32=(kind == ops.MMA_TF32), db=_bias_sink(bias, Cout))
-        _bias_fallback(bias, dz)
+        if ctx.relu:
+            dz = ops.relu_bwd(_nhwc(dy), y, round_tf32=(kind == ops.MMA_TF32), db=_bias_sink(bias, Cout))
+            _bias_fallback(bias, dz)
+        else:                               # a norm layer follows (its adjoint has already rounded dz)
+            dz = _nhwc(dy)
+            if bias is not None:
+                with torch.no_grad():
+                    _grad_of(bias).add_(dz.sum(dim=(0, 2, 3)))
         _weight_grad([(weight, 0, Cin)], xs, dz, None, Cin, k, 2, kind)
         dx = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             wp = _cached_pack(weight, ('tconv_dx', kind), lambda: ops.pack_weights(weight, kind))
             dx = ops.conv_fwd(dz, None, wp, None, Cin, k, 2, ops.EPI_BIAS, kind)
         return (dx if ctx.needs_input_grad[0] else None, dx if (ctx.has_skip and ctx.needs_input_grad[1]) else None,
-                None, None, None, None)
+                None, None, None, None, None)
 
 
 class UpsampleAddFn(torch.autograd.Function):
@@ -465,6 +472,62 @@ class PredFn(torch.autograd.Function):
         x, skip, depth = ctx.saved_tensors
         weight, bias = ctx.weight, ctx.bias
         dx, dw, db = ops.pred_bwd(ddepth, depth, x, weight, skip)
+        with torch.no_grad():
+            _grad_of(weight).add_(dw.view(weight.shape))
+            if bias is not None:
+                _grad_of(bias).add_(db)
+        return dx, (dx if skip is not None else None), None, None
+
+
+class NormActFn(torch.autograd.Function):
+    """act(norm(z) (+ res)) for a live normalisation layer (train-mode BatchNorm2d / InstanceNorm2d, the
+    ResidualBlock's InstanceNorm2d without running statistics, or an eval-mode norm that gradients flow through):
+    submodules.py:29-33, 60-64, 91-95, 203-214.  z is the bias-only output of the conv before it (ConvFn with
+    EPI_BIAS keeps it for its own backward; no second copy).  Running statistics are updated in place by the forward
+    kernel; dgamma / dbeta accumulate straight into the parameters' .grad."""
+
+    @staticmethod
+    def forward(ctx, z, res, gamma, beta, norm_mod, kind, act, batch_stats, round_out):
+        g = None if gamma is None else gamma.detach().float().contiguous()
+        b = None if beta is None else beta.detach().float().contiguous()
+        rm, rv = getattr(norm_mod, 'running_mean', None), getattr(norm_mod, 'running_var', None)
+        y, stats = ops.norm_fwd(z, kind, act, g, b, res, rm, rv, norm_mod.momentum if norm_mod.momentum is not None else 0.1,
+                                norm_mod.eps, batch_stats, round_out)
+        if rm is not None and batch_stats and kind == 'BN' and getattr(norm_mod, 'num_batches_tracked', None) is not None:
+            norm_mod.num_batches_tracked.add_(1)
+        ctx.save_for_backward(z, y, stats)
+        ctx.gamma, ctx.beta = gamma, beta
+        ctx.cfg = (kind, act, batch_stats, round_out, res is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        z, y, stats = ctx.saved_tensors
+        kind, act, batch_stats, round_out, has_res = ctx.cfg
+        gamma, beta = ctx.gamma, ctx.beta
+        want_dres = has_res and ctx.needs_input_grad[1]
+        _Deferred.note_stream(torch.cuda.current_stream(z.device))
+        dz, dres = ops.norm_bwd(_nhwc(dy), y, z, stats, kind, act, None if gamma is None else gamma.detach().float().contiguous(),
+                                batch_stats, round_out, want_dres,
+                                None if gamma is None else _grad_of(gamma), None if beta is None else _grad_of(beta))
+        return dz, dres, None, None, None, None, None, None, None
+
+
+class PredLogitsFn(torch.autograd.Function):
+    """1x1 pred conv without its activation (a norm layer sits between them, statenet.py:116-117 with norm set)."""
+
+    @staticmethod
+    def forward(ctx, x, skip, weight, bias):
+        logits = ops.pred_logits(x, skip, weight.detach(), None if bias is None else bias.detach())
+        ctx.save_for_backward(x, skip)
+        ctx.weight, ctx.bias = weight, bias
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        x, skip = ctx.saved_tensors
+        weight, bias = ctx.weight, ctx.bias
+        dx, dw, db = ops.pred_logits_bwd(dlogits, x, weight, skip)
         with torch.no_grad():
             _grad_of(weight).add_(dw.view(weight.shape))
             if bias is not None:

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libramnet_sm100a.so')
-SOURCES = ['api.cu', 'voxel_grid.cu', 'conv_head.cu', 'conv_simt.cu', 'conv_tcgen05.cu', 'conv_bwd.cu', 'loss.cu', 'adam.cu', 'dataio.cu', 'pipe_rate.cu']
+SOURCES = ['api.cu', 'voxel_grid.cu', 'conv_head.cu', 'conv_simt.cu', 'conv_tcgen05.cu', 'conv_bwd.cu', 'norm.cu', 'loss.cu', 'adam.cu', 'dataio.cu', 'pipe_rate.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']
 

@@ -421,8 +421,11 @@ __global__ void __launch_bounds__(256) pred_bwd_kernel(const float *__restrict__
     float dbacc = 0.f;
     const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> 3;
     for (int64_t m = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3; m < M; m += stride) {
-        const float s = depth[m];
-        const float dl = ddepth[m] * s * (1.f - s);
+        float dl = ddepth[m];
+        if (depth) {
+            const float s = depth[m];
+            dl *= s * (1.f - s);
+        }
         if (lane8 == 0) dbacc += dl;
         for (int c = lane8 * 4, j = 0; c < C; c += 32, j += 4) {
             float4 xv = *reinterpret_cast<const float4 *>(x + m * C + c);
@@ -706,7 +709,7 @@ extern "C" int ramnet_pred_bwd(ramnet_handle *h, const float *ddepth, const floa
                                const float *skip, const float *w, float *dx, float *dw, float *db, int64_t M, int C,
                                void *stream) {
     RAMNET_DEVICE_GUARD(h);
-    RAMNET_CHECK_ARG(h && ddepth && depth && x && w && dx && dw && M > 0 && C % 4 == 0 && C <= 64, "pred_bwd: bad argument (C <= 64)");
+    RAMNET_CHECK_ARG(h && ddepth && x && w && dx && dw && M > 0 && C % 4 == 0 && C <= 64, "pred_bwd: bad argument (C <= 64)");
     const int blocks = (int)imin64((M * 8 + 255) / 256, (int64_t)h->sm_count * 8);
     pred_bwd_kernel<<<blocks, 256, (C + 1) * sizeof(float), (cudaStream_t)stream>>>(ddepth, depth, x, skip, w, dx, dw, db, M, C);
     RAMNET_LAUNCH_CHECK(h);

@@ -55,11 +55,9 @@ def _fold_norm(w, b, norm_mod, norm_kind, training):
     """Eval-mode BatchNorm2d / InstanceNorm2d(track_running_stats=True) folded into (w, b)."""
     if norm_kind not in ('BN', 'IN') or norm_mod is None:
         return w, b
-    if training:
-        raise RamnetError("norm='%s' in training mode (batch statistics) is not implemented; "
-                          "call model.eval() or use norm='none' (all shipped configs)" % norm_kind)
-    if getattr(norm_mod, 'running_mean', None) is None:
-        raise RamnetError('InstanceNorm2d without running statistics is not implemented')
+    if norm_mod.training or getattr(norm_mod, 'running_mean', None) is None:
+        raise RamnetError("internal: a norm layer with live statistics reached the weight folding (engine.norm_is_live "
+                          "routes those through ops.norm_fwd)")
     scale = torch.rsqrt(norm_mod.running_var.float() + norm_mod.eps)
     shift = -norm_mod.running_mean.float() * scale
     if getattr(norm_mod, 'weight', None) is not None:
@@ -68,6 +66,36 @@ def _fold_norm(w, b, norm_mod, norm_kind, training):
     w2 = w * scale.view(-1, 1, 1, 1)
     b2 = shift if b is None else b * scale + shift
     return w2, b2
+
+
+def _norm_params(nm):
+    return (getattr(nm, 'weight', None), getattr(nm, 'bias', None)) if nm is not None else (None, None)
+
+
+def norm_is_live(norm_mod, norm_kind, *grad_tensors) -> bool:
+    """True when the layer's norm cannot be folded into the conv weights and runs as its own kernels
+    (ops.norm_fwd): batch / instance statistics (module in train mode, or an InstanceNorm2d built without running
+    statistics: the ResidualBlock's, submodules.py:192-194), or gradients are wanted through it."""
+    if norm_kind not in ('BN', 'IN') or norm_mod is None:
+        return False
+    return bool(norm_mod.training) or getattr(norm_mod, 'running_mean', None) is None or \
+        needs_grad(*grad_tensors, *_norm_params(norm_mod))
+
+
+def norm_act(z, norm_mod, norm_kind, act, res=None, round_out=False):
+    """act(norm(z) (+ res)) with live statistics; differentiable when anything upstream wants gradients."""
+    batch_stats = bool(norm_mod.training) or getattr(norm_mod, 'running_mean', None) is None
+    gamma, beta = _norm_params(norm_mod)
+    if needs_grad(z, res, gamma, beta):
+        from .autograd import NormActFn
+        return NormActFn.apply(z, res, gamma, beta, norm_mod, norm_kind, act, batch_stats, round_out)
+    rm, rv = getattr(norm_mod, 'running_mean', None), getattr(norm_mod, 'running_var', None)
+    y, _ = ops.norm_fwd(z, norm_kind, act, None if gamma is None else gamma.detach().float().contiguous(),
+                        None if beta is None else beta.detach().float().contiguous(), res, rm, rv,
+                        norm_mod.momentum if norm_mod.momentum is not None else 0.1, norm_mod.eps, batch_stats, round_out)
+    if rm is not None and batch_stats and norm_kind == 'BN' and getattr(norm_mod, 'num_batches_tracked', None) is not None:
+        norm_mod.num_batches_tracked.add_(1)
+    return y
 
 
 class WeightCache:
@@ -233,6 +261,19 @@ def head_layer(cache, key, conv, x, tf32):
 
 def conv_layer(cache, key, conv, kind, x, epilogue, x1=None, res=None, norm_mod=None, norm_kind=None, training=False,
                round_out=False):
+    if norm_is_live(norm_mod, norm_kind, x, x1, res, conv.weight, conv.bias):
+        # conv (+ bias) -> norm kernels (statistics, normalise + activation (+ residual)): submodules.py:26-35, 200-215
+        if epilogue not in (ops.EPI_BIAS, ops.EPI_BIAS_RELU, ops.EPI_BIAS_RES_RELU):
+            raise RamnetError('internal: live norm after a fused epilogue that has no norm in the reference')
+        p = pack_conv(cache, key + '/raw', conv, kind, hpack_ok=x1 is None)
+        if needs_grad(x, x1, conv.weight, conv.bias):
+            from .autograd import ConvFn
+            z = ConvFn.apply(x, x1, None, conv.weight, conv.bias, p.w, ops.EPI_BIAS, kind, p.stride, False)
+        else:
+            z = run_conv(x, p, ops.EPI_BIAS, kind, x1=x1)
+        return norm_act(z, norm_mod, norm_kind, None if epilogue == ops.EPI_BIAS else 'relu',
+                        res=res if epilogue == ops.EPI_BIAS_RES_RELU else None,
+                        round_out=round_out and kind == ops.MMA_TF32)
     p = pack_conv(cache, key, conv, kind, norm_mod, norm_kind, training,
                   hpack_ok=(epilogue in (ops.EPI_BIAS, ops.EPI_BIAS_RELU, ops.EPI_BIAS_RES_RELU) and x1 is None and
                             not (conv.stride[0] == 2 and epilogue == ops.EPI_BIAS_RES_RELU)))
@@ -280,20 +321,33 @@ def transposed_conv_layer(cache, key, tconv, kind, x, skip=None, norm_mod=None, 
     + bias + ReLU.  A transposed convolution IS the data gradient of the stride-2 convolution with the same weight
     tensor, so it runs as zero-insertion + the forward tensor-core kernel on tap-flipped, channel-transposed weights."""
     w = tconv.weight                      # [Cin, Cout, k, k] == nn.Conv2d layout of the conv it is the adjoint of
-    if norm_kind in ('BN', 'IN') and norm_mod is not None:
-        raise RamnetError('TransposedConvLayer with BatchNorm/InstanceNorm is not implemented')
+    has_norm = norm_kind in ('BN', 'IN') and norm_mod is not None
+    live = norm_is_live(norm_mod, norm_kind, x, skip, w, tconv.bias)
     if tuple(tconv.stride) != (2, 2) or tuple(tconv.output_padding) != (1, 1) or \
             tuple(tconv.padding) != (w.shape[2] // 2,) * 2:
         raise RamnetError('TransposedConvLayer: only stride 2, padding k//2, output_padding 1 is implemented')
     Cin, Cout = w.shape[0], w.shape[1]
 
     def build():
+        wf, bf = w.detach().float(), None if tconv.bias is None else tconv.bias.detach().float()
+        if has_norm and not live:         # eval-mode norm: per-OUTPUT-channel scale (dim 1 of a ConvTranspose2d weight)
+            w2, bf = _fold_norm(wf.transpose(0, 1), bf, norm_mod, norm_kind, False)
+            wf = w2.transpose(0, 1).contiguous()
         p = Packed()
-        p.w = ops.pack_weights_dgrad(w.detach().float(), kind, 0, Cout)
-        p.b = None if tconv.bias is None else tconv.bias.detach().float().contiguous()
+        p.w = ops.pack_weights_dgrad(wf, kind, 0, Cout)
+        p.b = None if bf is None else bf.contiguous()
         p.Cout, p.ksize, p.stride = Cout, w.shape[2], 1
         return p
-    p = cache.get(key, [w, tconv.bias], (kind, 'tconv'), build)
+    p = cache.get(key, [w, tconv.bias] + (_norm_sources(norm_mod) if has_norm else []), (kind, 'tconv', live), build)
+    if live:
+        if needs_grad(x, skip, w, tconv.bias):
+            from .autograd import TransposedConvFn
+            z = TransposedConvFn.apply(x, skip, w, tconv.bias, p.w, kind, False)
+        else:
+            N, _, H, W = x.shape
+            up = ops.zero_insert2x(x, 2 * H, 2 * W, skip=skip)
+            z = ops.conv_fwd(up, None, p.w, p.b, Cout, p.ksize, 1, ops.EPI_BIAS, kind)
+        return norm_act(z, norm_mod, norm_kind, 'relu')
     if needs_grad(x, skip, w, tconv.bias):
         from .autograd import TransposedConvFn
         return TransposedConvFn.apply(x, skip, w, tconv.bias, p.w, kind)
@@ -312,6 +366,22 @@ def upsample_add(x, skip, tf32):
 def pred_layer(x, pred_conv, norm_mod, norm_kind, training, return_logits=False, skip=None):
     w = pred_conv.weight
     b = pred_conv.bias
+    if norm_is_live(norm_mod, norm_kind, x, skip, w, b):      # pred conv -> norm -> sigmoid (statenet.py:116-117,313)
+        if needs_grad(x, skip, w, b):
+            from .autograd import PredLogitsFn
+            z = PredLogitsFn.apply(x, skip, w, b)
+        else:
+            z = ops.pred_logits(x, skip, w, None if b is None else b.detach().float())
+        logits = None
+        if return_logits:                 # debugging aid (inference): the normalised logits, running statistics untouched
+            gamma, beta = _norm_params(norm_mod)
+            bs = bool(norm_mod.training) or getattr(norm_mod, 'running_mean', None) is None
+            logits, _ = ops.norm_fwd(z.detach(), norm_kind, None, None if gamma is None else gamma.detach().float().contiguous(),
+                                     None if beta is None else beta.detach().float().contiguous(), None,
+                                     None if bs else norm_mod.running_mean, None if bs else norm_mod.running_var,
+                                     0.0, norm_mod.eps, bs)
+        depth = norm_act(z, norm_mod, norm_kind, 'sigmoid')
+        return (depth, logits) if return_logits else depth
     if needs_grad(x, skip, w, b):
         _no_fold_in_training(norm_mod, norm_kind)
         if return_logits:

@@ -289,8 +289,6 @@ class StateNetPhasedRecurrent(BaseStateNet):
         pick = (lambda s: s[0]) if tup else (lambda s: s)
         x = ops.as_nhwc(pick(super_states[-1]))
         for i, rb in enumerate(self.resblocks):
-            if rb.norm == 'IN':
-                raise RamnetError("norm='IN' inside ResidualBlock uses per-instance statistics; not implemented")
             y = E.conv_layer(cache, f'res{i}/1', rb.conv1, kind, x, ops.EPI_BIAS_RELU, norm_mod=getattr(rb, 'bn1', None),
                              norm_kind=rb.norm, training=self.training, round_out=True)
             x = E.conv_layer(cache, f'res{i}/2', rb.conv2, kind, y, ops.EPI_BIAS_RES_RELU, res=x,
@@ -308,7 +306,9 @@ class StateNetPhasedRecurrent(BaseStateNet):
         # Up-conv decoders (inference, TF32): bilinear x2 + 5x5 conv in ONE launch on the low-resolution tensor
         # (ops.conv_up_fwd); the skip sum a decoder needs is formed by the epilogue of the layer before it
         # (EPI_BIAS_RELU_ADD), so neither the 4x tensor nor the sum is ever written on its own.
-        up_mode = [self.use_upsample_conv and tf32 and grad_free(dec) and
+        # live norms (train-mode statistics) sit between a conv and its activation: those layers run unfused
+        live_norm = any(E.norm_is_live(getattr(m, 'norm_layer', None), m.norm) for m in list(self.decoders) + [pr])
+        up_mode = [self.use_upsample_conv and tf32 and grad_free(dec) and not live_norm and
                    ops.upconv_eligible(dec.conv2d.in_channels, dec.conv2d.out_channels, dec.conv2d.kernel_size[0], kind)
                    for dec in self.decoders]
         skip_added = False          # x already holds x + skip of the decoder about to run
@@ -322,7 +322,8 @@ class StateNetPhasedRecurrent(BaseStateNet):
             last = i == nd - 1
             next_up = (not last) and up_mode[i + 1]
             nm, nk = getattr(dec, 'norm_layer', None), dec.norm
-            fuse = last and tf32 and dec.conv2d.out_channels % 32 == 0 and dec.conv2d.out_channels <= 256 and grad_free(dec)
+            fuse = last and tf32 and dec.conv2d.out_channels % 32 == 0 and dec.conv2d.out_channels <= 256 and \
+                grad_free(dec) and not live_norm
             if fuse:
                 pw, pb = pr.conv2d.weight.detach().float(), None if pr.conv2d.bias is None else pr.conv2d.bias.detach().float()
                 pw, pb = E._fold_norm(pw, pb, getattr(pr, 'norm_layer', None), pr.norm, self.training)

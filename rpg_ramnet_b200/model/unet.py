@@ -82,8 +82,6 @@ class UNet(BaseUNet):
                              round_out=True)
             blocks.append(x)
         for i, rb in enumerate(self.resblocks):
-            if rb.norm == 'IN':
-                raise RamnetError("norm='IN' inside ResidualBlock is not implemented")
             y = E.conv_layer(cache, f'res{i}/1', rb.conv1, kind, x, ops.EPI_BIAS_RELU, norm_mod=getattr(rb, 'bn1', None),
                              norm_kind=rb.norm, training=self.training, round_out=True)
             x = E.conv_layer(cache, f'res{i}/2', rb.conv2, kind, y, ops.EPI_BIAS_RES_RELU, res=x,

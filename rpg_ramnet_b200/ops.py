@@ -690,6 +690,74 @@ def pred_bwd(ddepth, depth, x, w, skip=None):
     return dx, dw, db
 
 
+NORM_ACT = {None: 0, 'none': 0, 'relu': _lib.NORM_RELU, 'sigmoid': _lib.NORM_SIGMOID}
+
+
+def norm_fwd(z, kind: str, act, gamma=None, beta=None, res=None, running_mean=None, running_var=None, momentum=0.1,
+             eps=1e-5, batch_stats=True, round_tf32=False):
+    """act(norm(z) (+ res)) for an NHWC conv output z (ramnet_norm_fwd).  kind 'BN': statistics per channel over the
+    batch; 'IN': per (sample, channel).  batch_stats=False normalises with the running statistics (eval-mode norm
+    that gradients flow through) and updates nothing; otherwise running_mean / running_var (when given) are updated
+    in place exactly as nn.BatchNorm2d / F.instance_norm do in train mode.  Returns (y, stats) -- stats [G, C, 2]
+    (mean, invstd) is what norm_bwd needs."""
+    _check_nhwc(z, 'norm_fwd z')
+    if res is not None:
+        _check_nhwc(res, 'norm_fwd res')
+    N, C, H, W = z.shape
+    flags = NORM_ACT[act] | (_lib.NORM_INSTANCE if kind == 'IN' else 0) | (0 if batch_stats else _lib.NORM_RUNNING) | \
+        (_lib.NORM_ROUND_TF32 if round_tf32 else 0)
+    G = N if (kind == 'IN' and batch_stats) else 1
+    sums = torch.empty(G * C * 2, dtype=torch.float64, device=z.device)
+    stats = torch.empty((G, C, 2), dtype=torch.float32, device=z.device)
+    y = empty_nhwc(N, C, H, W, z.device)
+    for t in (gamma, beta, running_mean, running_var):
+        if t is not None and not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == C):
+            raise _lib.RamnetError('norm_fwd: per-channel parameters must be contiguous fp32 CUDA tensors of C elements')
+    check(_lib.load().ramnet_norm_fwd(_h(z), _p(z), _p(res), _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+                                      float(momentum), float(eps), N, H * W, C, flags, _p(sums), _p(stats), _p(y), _stream(z)))
+    return y, stats
+
+
+def norm_bwd(dy, y, z, stats, kind: str, act, gamma=None, batch_stats=True, round_tf32=False, want_dres=False,
+             dgamma=None, dbeta=None):
+    """Adjoint of norm_fwd: returns (dz, dres); dgamma / dbeta ([C], optional) are accumulated into."""
+    _check_nhwc(dy, 'norm_bwd dy')
+    N, C, H, W = z.shape
+    flags = NORM_ACT[act] | (_lib.NORM_INSTANCE if kind == 'IN' else 0) | (0 if batch_stats else _lib.NORM_RUNNING) | \
+        (_lib.NORM_ROUND_TF32 if round_tf32 else 0)
+    G = stats.shape[0]
+    sums = torch.empty(G * C * 2, dtype=torch.float64, device=z.device)
+    coef = torch.empty((G, C, 2), dtype=torch.float32, device=z.device)
+    dz = empty_nhwc(N, C, H, W, z.device)
+    dres = empty_nhwc(N, C, H, W, z.device) if want_dres else None
+    check(_lib.load().ramnet_norm_bwd(_h(z), _p(dy), _p(y if NORM_ACT[act] else None), _p(z), _p(stats), _p(gamma), N, H * W, C,
+                                      flags, _p(sums), _p(coef), _p(dz), _p(dres), _p(dgamma), _p(dbeta), _stream(z)))
+    return dz, dres
+
+
+def pred_logits(x, skip, w, b):
+    """1x1 conv to one channel, no activation (a norm layer follows): [N,1,H,W]."""
+    _check_nhwc(x, 'pred_logits x')
+    N, C, H, W = x.shape
+    logits = torch.empty((N, 1, H, W), dtype=torch.float32, device=x.device)
+    wv = w.detach().reshape(-1).contiguous().float()
+    check(_lib.load().ramnet_pred_sigmoid(_h(x), _p(x), _p(skip), _p(wv), _p(b), _p(logits), None, N * H * W, C, _stream(x)))
+    return logits
+
+
+def pred_logits_bwd(dlogits, x, w, skip=None):
+    """Adjoint of pred_logits (ramnet_pred_bwd with depth = NULL)."""
+    _check_nhwc(x, 'pred_bwd x')
+    N, C, H, W = x.shape
+    dx = empty_nhwc(N, C, H, W, x.device)
+    dw = torch.zeros(C, dtype=torch.float32, device=x.device)
+    db = torch.zeros(1, dtype=torch.float32, device=x.device)
+    wv = w.detach().reshape(-1).contiguous().float()
+    check(_lib.load().ramnet_pred_bwd(_h(x), _p(dlogits.contiguous()), None, _p(x), _p(skip), _p(wv), _p(dx), _p(dw), _p(db),
+                                      N * H * W, C, _stream(x)))
+    return dx, dw, db
+
+
 def upsample2x_bwd(dy):
     _check_nhwc(dy, 'upsample2x_bwd dy')
     N, C, H2, W2 = dy.shape

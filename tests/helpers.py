@@ -12,7 +12,10 @@ from oracle import ramnet_oracle as O
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 MODEL_CASES = ['cfg1_shipped', 'cfg1_stress2', 'rect_b2', 'k5_shipped', 'lstm_state', 'lstm_enc', 'bn_eval',
-               'baseline_rgb', 'baseline_e', 'baseline_ergb0', 'unet', 'transposed']
+               'baseline_rgb', 'baseline_e', 'baseline_ergb0', 'unet', 'transposed',
+               # live norm layers: train-mode BatchNorm / InstanceNorm statistics, ResidualBlock InstanceNorm in eval mode
+               'bn_train', 'in_train', 'in_eval', 'bn_train_tconv_lstm', 'unet_bn_train']
+GRAD_CASES = ['grads_shipped', 'grads_bn_train', 'grads_in_train', 'grads_bn_eval']
 
 
 def load_case(name):
@@ -33,6 +36,7 @@ def build_product_model(meta, device_index=0, mma_kind=None):
         m = getattr(R, meta['arch'])(cfg)
     m.eval()
     O.scale_weights(m, meta['wscale'])
+    m.train(bool(meta.get('train', False)))
     return m, cfg
 
 
@@ -46,7 +50,11 @@ def case_inputs(meta):
 
 
 def run_oracle_sequence(sd, meta, seq):
-    """Drive the oracle over the sequence with state carry, like lstm_trainer.py:245-272."""
+    """Drive the oracle over the sequence with state carry, like lstm_trainer.py:245-272.  Cases generated with the
+    reference in train mode run under O.training_mode(): `sd`'s running statistics are updated in place."""
+    if meta.get('train', False):
+        with O.training_mode():
+            return run_oracle_sequence(sd, dict(meta, train=False), seq)
     cfg = meta['config']
     K = cfg.get('every_x_rgb_frame', 1)
     outs = []

@@ -474,3 +474,80 @@ def test_voxel_normalize_label_and_metrics_on_device():
     for n, v in zip(names, vals):
         np.testing.assert_allclose(v, float(g['metric_' + n]), rtol=2e-5, err_msg=n)
         np.testing.assert_allclose(getattr(M, n)(p, t), v, rtol=1e-12)
+
+
+# ----------------------------------------------------------------------------- live normalisation layers
+@pytest.mark.parametrize('kind,act,res', [('BN', 'relu', False), ('BN', 'relu', True), ('IN', 'relu', False),
+                                          ('IN', None, True), ('BN', 'sigmoid', False), ('BN', None, False)])
+@pytest.mark.parametrize('shape', [(2, 32, 9, 11), (3, 256, 8, 8), (4, 64, 128, 256), (2, 1, 16, 24), (1, 128, 5, 3)])
+def test_norm_fwd_bwd_vs_torch(kind, act, res, shape):
+    """ramnet_norm_fwd / ramnet_norm_bwd (train-mode BatchNorm2d / InstanceNorm2d + activation + residual) against
+    torch CPU float64 F.batch_norm / F.instance_norm: output, running statistics (momentum, unbiased variance), and
+    all gradients (dz, dres, dgamma, dbeta).  Shapes cover the float4 path, C = 1 (the pred layer) and a 8 M-element
+    tensor that makes every block walk several grid strides."""
+    from rpg_ramnet_b200 import ops
+    N, C, H, W = shape
+    g = torch.Generator().manual_seed(N * 1000 + C + H)
+    z = torch.randn(shape, generator=g) * 1.7 + 0.4 * torch.randn(1, C, 1, 1, generator=g)
+    r = torch.randn(shape, generator=g) if res else None
+    affine = kind == 'BN'
+    gamma = (0.75 + 0.5 * torch.rand(C, generator=g)) if affine else None
+    beta = (0.1 * torch.randn(C, generator=g)) if affine else None
+    rm0, rv0 = 0.1 * torch.randn(C, generator=g), 0.5 + torch.rand(C, generator=g)
+    dy = torch.randn(shape, generator=g)
+    # reference in float64
+    zd = z.double().requires_grad_(True)
+    rd = None if r is None else r.double().requires_grad_(True)
+    gd = None if gamma is None else gamma.double().requires_grad_(True)
+    bd = None if beta is None else beta.double().requires_grad_(True)
+    rm_ref, rv_ref = rm0.double().clone(), rv0.double().clone()
+    if kind == 'BN':
+        t = F.batch_norm(zd, rm_ref, rv_ref, gd, bd, True, 0.1, 1e-5)
+    else:
+        t = F.instance_norm(zd, rm_ref, rv_ref, None, None, True, 0.1, 1e-5)
+    if rd is not None:
+        t = t + rd
+    yr = torch.relu(t) if act == 'relu' else (torch.sigmoid(t) if act == 'sigmoid' else t)
+    yr.backward(dy.double())
+    # ours
+    rm, rv = rm0.to(dev()), rv0.to(dev())
+    zc = nhwc(z)
+    y, stats = ops.norm_fwd(zc, kind, act, None if gamma is None else gamma.to(dev()), None if beta is None else beta.to(dev()),
+                            None if r is None else nhwc(r), rm, rv, 0.1, 1e-5, True, False)
+    assert float((y.cpu().double() - yr.detach()).abs().max()) <= 2e-5
+    assert float((rm.cpu().double() - rm_ref).abs().max()) <= 1e-6
+    assert float((rv.cpu().double() - rv_ref).abs().max()) <= 1e-5 * float(rv_ref.abs().max())
+    dgam = torch.zeros(C, device=dev()) if affine else None
+    dbet = torch.zeros(C, device=dev()) if affine else None
+    dz, dres = ops.norm_bwd(nhwc(dy), y, zc, stats, kind, act, None if gamma is None else gamma.to(dev()), True, False,
+                            res, dgam, dbet)
+    scale = float(zd.grad.abs().max())
+    # relu masks are taken from the fp32 forward: entries within float rounding of zero may flip (none at this tolerance)
+    assert float((dz.cpu().double() - zd.grad).abs().max()) <= 5e-5 * max(scale, 1.0)
+    if res:
+        assert float((dres.cpu().double() - rd.grad).abs().max()) <= 1e-6 * max(1.0, float(rd.grad.abs().max()))
+    if affine:
+        assert float((dgam.cpu().double() - gd.grad).abs().max()) <= 2e-5 * max(1.0, float(gd.grad.abs().max()))
+        assert float((dbet.cpu().double() - bd.grad).abs().max()) <= 2e-5 * max(1.0, float(bd.grad.abs().max()))
+
+
+def test_norm_running_mode_matches_eval_batchnorm():
+    """RAMNET_NORM_RUNNING: an eval-mode BatchNorm2d that gradients flow through (running statistics, nothing updated)."""
+    from rpg_ramnet_b200 import ops
+    N, C, H, W = 2, 64, 12, 20
+    g = torch.Generator().manual_seed(5)
+    z, dy = torch.randn(N, C, H, W, generator=g), torch.randn(N, C, H, W, generator=g)
+    gamma, beta = 0.75 + 0.5 * torch.rand(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    rm0, rv0 = 0.1 * torch.randn(C, generator=g), 0.5 + torch.rand(C, generator=g)
+    zd, gd, bd = z.double().requires_grad_(True), gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    yr = torch.relu(F.batch_norm(zd, rm0.double(), rv0.double(), gd, bd, False, 0.1, 1e-5))
+    yr.backward(dy.double())
+    rm, rv = rm0.to(dev()), rv0.to(dev())
+    y, stats = ops.norm_fwd(nhwc(z), 'BN', 'relu', gamma.to(dev()), beta.to(dev()), None, rm, rv, 0.1, 1e-5, False, False)
+    assert torch.equal(rm.cpu(), rm0) and torch.equal(rv.cpu(), rv0)
+    assert float((y.cpu().double() - yr.detach()).abs().max()) <= 1e-5
+    dgam, dbet = torch.zeros(C, device=dev()), torch.zeros(C, device=dev())
+    dz, _ = ops.norm_bwd(nhwc(dy), y, nhwc(z), stats, 'BN', 'relu', gamma.to(dev()), False, False, False, dgam, dbet)
+    assert float((dz.cpu().double() - zd.grad).abs().max()) <= 1e-5
+    assert float((dgam.cpu().double() - gd.grad).abs().max()) <= 2e-5 * float(gd.grad.abs().max())
+    assert float((dbet.cpu().double() - bd.grad).abs().max()) <= 2e-5 * float(bd.grad.abs().max())

@@ -40,6 +40,16 @@ def test_model_matches_reference_golden(name, kind):
                     assert np.abs(got - ref).max() <= (5e-5 if kind == 'fp32' else 3e-3) * scale, \
                         f'{name} {kind} super/{l}/{key}/{j}'
     assert n == len([k for k in g.files if k.startswith('pred/')])
+    # train-mode norm cases: the running statistics the sequence leaves behind (momentum update, unbiased variance)
+    sd = model.state_dict()
+    for k in [k for k in g.files if k.startswith('buf/')]:
+        ref = g[k]
+        got = sd[k[4:]].cpu().numpy()
+        if ref.dtype.kind in 'iu':
+            assert np.array_equal(got, ref), k
+        else:
+            assert np.abs(got - ref).max() <= (1e-5 if kind == 'fp32' else 2e-3) * max(1.0, float(np.abs(ref).max())), \
+                f'{name} {kind} {k}'
 
 
 @pytest.mark.parametrize('kind', ['fp32', 'tf32'])

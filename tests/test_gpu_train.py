@@ -247,12 +247,15 @@ def test_head_upsample_pred_backward_vs_torch():
     assert _rel(gx.grad, tx.grad) <= 1e-5 and _rel(gw.grad, tw.grad) <= 1e-4 and _rel(gb.grad, tb.grad) <= 1e-4
 
 
+@pytest.mark.parametrize('case', ['grads_shipped', 'grads_bn_train', 'grads_in_train', 'grads_bn_eval'])
 @pytest.mark.parametrize('kind', KINDS)
-def test_model_gradients_match_reference(kind):
-    """Full BPTT over L=2 timesteps (4 passes), the trainer's loss mix (K_keys aliasing): loss value and all 68
-    parameter gradients vs the digests produced by the reference itself (tests/golden/grads_shipped.npz)."""
+def test_model_gradients_match_reference(kind, case):
+    """Full BPTT over L=2 timesteps (4 passes), the trainer's loss mix (K_keys aliasing): loss value and every
+    parameter gradient vs the digests produced by the reference itself (tests/golden/grads_*.npz): the shipped block
+    (68 tensors) and the norm='BN' / 'IN' variants in train mode (batch / instance statistics: ramnet_norm_fwd / _bwd)
+    and BatchNorm in eval mode with gradients flowing through it (RAMNET_NORM_RUNNING)."""
     import rpg_ramnet_b200 as R
-    g = np.load(os.path.join(GOLDEN, 'grads_shipped.npz'))
+    g = np.load(os.path.join(GOLDEN, case + '.npz'))
     meta = json.loads(str(g['meta']))
     meta.update(arch='ERGB2DepthRecurrent')
     model, cfg = build_product_model(meta, mma_kind=kind)
