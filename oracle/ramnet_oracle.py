@@ -139,8 +139,9 @@ class tf32_operands:
         _TF32_OPERANDS = self.prev
 
 
-def _conv2d(x, w, b=None, **kw):
-    if _TF32_OPERANDS and x.dtype == torch.float32:
+def _conv2d(x, w, b=None, exact=False, **kw):
+    """`exact`: a layer the product computes with fp32 FFMA even in TF32 mode (the 1x1 prediction conv)."""
+    if _TF32_OPERANDS and x.dtype == torch.float32 and not exact:
         return _RoundBwd.apply(F.conv2d(_RoundFwd.apply(x), _RoundFwd.apply(w), b, **kw))
     return F.conv2d(x, w, b, **kw)
 
@@ -178,10 +179,10 @@ def _norm_eval(sd: StateDict, prefix: str, y: Tensor, kind: str) -> Tensor:
 
 
 def conv_layer(sd: StateDict, prefix: str, x: Tensor, stride: int, padding: int,
-               relu: bool = True, norm: Optional[str] = None) -> Tensor:
+               relu: bool = True, norm: Optional[str] = None, exact: bool = False) -> Tensor:
     """ConvLayer.forward (submodules.py:26-35): conv (+bias unless BN, :13)
     -> optional norm -> optional relu."""
-    y = _conv2d(x, sd[prefix + '.conv2d.weight'], sd.get(prefix + '.conv2d.bias'),
+    y = _conv2d(x, sd[prefix + '.conv2d.weight'], sd.get(prefix + '.conv2d.bias'), exact=exact,
                  stride=stride, padding=padding)
     if norm in ('BN', 'IN'):
         y = _norm_eval(sd, prefix + '.norm_layer', y, norm)
@@ -203,9 +204,12 @@ def upsample_conv_layer(sd: StateDict, prefix: str, x: Tensor, norm: Optional[st
 def transposed_conv_layer(sd: StateDict, prefix: str, x: Tensor, norm: Optional[str] = None) -> Tensor:
     """TransposedConvLayer.forward (submodules.py:38-66): stride-2 5x5
     ConvTranspose2d, padding 2, output_padding 1 -> norm -> relu."""
-    y = F.conv_transpose2d(x, sd[prefix + '.transposed_conv2d.weight'],
-                           sd.get(prefix + '.transposed_conv2d.bias'),
-                           stride=2, padding=2, output_padding=1)
+    w = sd[prefix + '.transposed_conv2d.weight']
+    if _TF32_OPERANDS and x.dtype == torch.float32:
+        x, w = _RoundFwd.apply(x), _RoundFwd.apply(w)
+    y = F.conv_transpose2d(x, w, sd.get(prefix + '.transposed_conv2d.bias'), stride=2, padding=2, output_padding=1)
+    if _TF32_OPERANDS and y.dtype == torch.float32:
+        y = _RoundBwd.apply(y)
     if norm in ('BN', 'IN'):
         y = _norm_eval(sd, prefix + '.norm_layer', y, norm)
     return torch.relu(y)
@@ -359,7 +363,7 @@ def forward_decoder(sd: StateDict, cfg: NetCfg, supers, return_logits: bool = Fa
             x = upsample_conv_layer(sd, f'{P}decoders.{i}', x, cfg.norm)
         else:
             x = transposed_conv_layer(sd, f'{P}decoders.{i}', x, cfg.norm)
-    logits = conv_layer(sd, P + 'pred', x, 1, 0, relu=False, norm=cfg.norm)
+    logits = conv_layer(sd, P + 'pred', x, 1, 0, relu=False, norm=cfg.norm, exact=True)
     return (torch.sigmoid(logits), logits) if return_logits else torch.sigmoid(logits)
 
 
@@ -431,7 +435,7 @@ def ergb2depth_unet(sd: StateDict, config: dict, item: dict, return_logits: bool
     for i in range(cfg.num_encoders):
         x = x + blocks[cfg.num_encoders - i - 1]                # skip on EVERY decoder (unet.py:126-127)
         x = upsample_conv_layer(sd, f'{P}decoders.{i}', x, cfg.norm)
-    logits = conv_layer(sd, P + 'pred', x + head, 1, 0, relu=False, norm=cfg.norm)   # unet.py:129
+    logits = conv_layer(sd, P + 'pred', x + head, 1, 0, relu=False, norm=cfg.norm, exact=True)   # unet.py:129
     pred = torch.sigmoid(logits)
     return ({'image': pred}, {'image': logits}) if return_logits else {'image': pred}
 

@@ -13,6 +13,16 @@ pytestmark = pytest.mark.gpu
 SUPPORTED = list(MODEL_CASES)
 # north_star tolerance: fp32 depth maps within 1e-3 relative of the reference forward.
 REL_TOL = {'fp32': 1e-4, 'tf32': 1e-3}
+# Train-mode norm configurations (not shipped): the pred layer's BatchNorm / InstanceNorm rescales the logits to unit
+# variance, so the depth map is ~30x more sensitive to the 2^-11 operand rounding of kind::tf32 than the norm-free
+# models (whose seed-0 logits sit near 0).  Against the reference (fp32 operands) TF32 mode is held to 2e-2 there, and to
+# no worse than the CPU oracle evaluated on TF32-rounded operands deviates from it (test_live_norm_tf32_error_is_the_operand_
+# rounding_floor: 0.5 - 1.6e-2, i.e. any TF32 convolution shows it); mma_kind='fp32' meets 1e-4 against the reference itself.
+LIVE_NORM_TF32_TOL = 2e-2
+
+
+def _tol(name, kind, meta):
+    return LIVE_NORM_TF32_TOL if (kind == 'tf32' and meta.get('train', False)) else REL_TOL[kind]
 
 
 @pytest.mark.parametrize('kind', ['fp32', 'tf32'])
@@ -29,7 +39,7 @@ def test_model_matches_reference_golden(name, kind):
             ref = g[f'pred/{l}/{key}']
             assert p.shape == ref.shape and p.dtype == torch.float32
             err = max_rel_err(p.cpu().numpy(), ref)
-            assert err <= REL_TOL[kind], f'{name} {kind} pred/{l}/{key}: max rel err {err:.3e}'
+            assert err <= _tol(name, kind, meta), f'{name} {kind} pred/{l}/{key}: max rel err {err:.3e}'
             n += 1
         if supers.get('image') is not None:
             for key, s in supers.items():
@@ -50,6 +60,32 @@ def test_model_matches_reference_golden(name, kind):
         else:
             assert np.abs(got - ref).max() <= (1e-5 if kind == 'fp32' else 2e-3) * max(1.0, float(np.abs(ref).max())), \
                 f'{name} {kind} {k}'
+
+
+@pytest.mark.parametrize('name', ['bn_train', 'in_train', 'bn_train_tconv_lstm', 'unet_bn_train'])
+def test_live_norm_tf32_error_is_the_operand_rounding_floor(name):
+    """Why LIVE_NORM_TF32_TOL is not 1e-3: the CPU oracle itself, evaluated on TF32-rounded conv operands (fp32
+    accumulate, everything else exact), deviates from the reference's fp32 output by 0.5 - 1.6e-2 on these
+    configurations (1e-5 on the shipped block, 2e-4 with eval-mode BatchNorm) -- the sensitivity belongs to TF32 operand
+    rounding under unit-variance logits, not to this implementation.  The CUDA path must not be worse than that floor
+    (x1.5 for the different rounding points: the product also keeps recurrent states TF32-rounded)."""
+    g, meta = load_case(name)
+    model, _ = build_product_model(meta, mma_kind='tf32')
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model.to('cuda:0')
+    seq = case_inputs(meta)
+    outs = run_product_sequence(model, meta, seq)
+    with torch.no_grad(), O.tf32_operands():
+        ref = run_oracle_sequence(sd, meta, seq)
+    ours = floor = 0.0
+    for l, ((preds, _), (rpreds, _)) in enumerate(zip(outs, ref)):
+        for key, p in preds.items():
+            gold = g[f'pred/{l}/{key}']
+            ours = max(ours, max_rel_err(p.cpu().numpy(), gold))
+            floor = max(floor, max_rel_err(rpreds[key].numpy(), gold))
+    print(f'{name}: vs reference: CUDA tf32 {ours:.3e}, oracle on tf32-rounded operands {floor:.3e}')
+    assert floor >= 2e-3, 'the premise of LIVE_NORM_TF32_TOL no longer holds: tighten it'
+    assert ours <= 1.5 * floor, f'{name}: {ours:.3e} vs floor {floor:.3e}'
 
 
 @pytest.mark.parametrize('kind', ['fp32', 'tf32'])

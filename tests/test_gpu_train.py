@@ -281,10 +281,16 @@ def test_model_gradients_match_reference(kind, case):
     # few percent on individual gradient entries, ~1 % on per-tensor norms.
     tol = 2e-3 if kind == 'fp32' else 3e-2
     tol_elem = tol if kind == 'fp32' else 1.5e-1      # 16-entry samples of small-magnitude tensors are noisy in tf32
+    gmax = float(np.max(g['grad_l2']))
     for i, n in enumerate(g['names']):
         gr = params[str(n)].grad
         assert gr is not None, n
         l2 = float(gr.double().norm())
+        if g['grad_l2'][i] < 1e-6 * gmax:
+            # mathematically zero (a conv bias in front of an InstanceNorm: the norm removes the mean); the reference
+            # holds summation noise there and so do we (tf32: the noise of summing TF32-rounded dz)
+            assert l2 <= (1e-6 if kind == 'fp32' else 1e-4) * gmax, (n, l2, g['grad_l2'][i])
+            continue
         assert abs(l2 - g['grad_l2'][i]) <= tol * max(g['grad_l2'][i], 1e-7), (n, l2, g['grad_l2'][i])
         if kind == 'fp32':      # tf32: whole tensors are checked (5e-2 Frobenius) by test_tf32_gradients_match_tf32_operand_oracle;
             ref_head = g['head/' + str(n)]      # 16-entry samples of small-magnitude tensors only measure rounding noise there
