@@ -5,8 +5,9 @@
 // activation (+ the residual add of ResidualBlock.forward :213-214).  Eval-mode norms with running statistics never get
 // here: they are folded into the packed conv weights (engine._fold_norm).
 //
-// All tensors NHWC fp32 [N, H*W, C].  Statistics are accumulated in float64 (ATen's CPU kernels use double accumulators
-// for float input; E[z^2] - E[z]^2 in double has no cancellation problem at these magnitudes).  Every kernel is a
+// All tensors NHWC fp32 [N, H*W, C].  Statistics: runs of 8 elements per lane in fp32, everything above that in float64
+// (ATen's CPU kernels use double accumulators for float input; E[z^2] - E[z]^2 in double has no cancellation problem
+// at these magnitudes).  Every kernel is a
 // flat, fully coalesced float4 stream whose grid stride is a multiple of C/4, so a thread owns the same four channels
 // for its whole life: per-channel constants sit in registers and the per-channel sums fold through shared memory into
 // one float64 atomic per channel per block.  HBM-bound: forward = read z twice + write y (12 B / element), backward =
@@ -71,15 +72,26 @@ __global__ void __launch_bounds__(256) norm_stats_kernel(const float *__restrict
 #pragma unroll
     for (int e = 0; e < V; ++e) acc[e][0] = acc[e][1] = 0.0;
     const int64_t stride = (int64_t)gridDim.x * 256;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < vec_per_group; i += stride) {
-        float v[V];
-        Vec<V>::get(zg[i], v);
+    // runs of U elements per lane are summed in fp32 (U independent loads in flight), the runs in float64
+    constexpr int U = 8;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < vec_per_group; i += stride * U) {
+        T ld[U];
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-            const double d = (double)v[e];
-            acc[e][0] += d;
-            acc[e][1] = fma(d, d, acc[e][1]);
-        }
+        for (int u = 0; u < U; ++u)
+            if (i + u * stride < vec_per_group) ld[u] = zg[i + u * stride];
+        float fs[V], fq[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) fs[e] = fq[e] = 0.f;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (i + u * stride < vec_per_group) {
+                float v[V];
+                Vec<V>::get(ld[u], v);
+#pragma unroll
+                for (int e = 0; e < V; ++e) { fs[e] += v[e]; fq[e] = fmaf(v[e], v[e], fq[e]); }
+            }
+#pragma unroll
+        for (int e = 0; e < V; ++e) { acc[e][0] += (double)fs[e]; acc[e][1] += (double)fq[e]; }
     }
     fold_to_global<V, 2>(acc, CV, sums + (int64_t)blockIdx.y * C * 2);
 }
@@ -139,6 +151,7 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const float *__restrict
     const T *rg = res ? reinterpret_cast<const T *>(res) + base : nullptr;
     T *yg = reinterpret_cast<T *>(y) + base;
     const int64_t stride = (int64_t)gridDim.x * 256;
+#pragma unroll 4
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < vec_per_group; i += stride) {
         float v[V], r[V], o[V];
         Vec<V>::get(zg[i], v);
@@ -175,18 +188,36 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float *__res
 #pragma unroll
     for (int e = 0; e < V; ++e) acc[e][0] = acc[e][1] = 0.0;
     const int64_t stride = (int64_t)gridDim.x * 256;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < vec_per_group; i += stride) {
-        float d[V], o[V], v[V], g[V];
-        Vec<V>::get(dyg[i], d);
-        Vec<V>::get(zg[i], v);
-        if (yg) Vec<V>::get(yg[i], o);
+    constexpr int U = 4;          // runs of U elements per lane in fp32, U x 3 independent loads in flight
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < vec_per_group; i += stride * U) {
+        T ld_d[U], ld_z[U], ld_y[U];
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-            g[e] = yg ? act_bwd(d[e], o[e], flags) : d[e];
-            acc[e][0] += (double)g[e];
-            acc[e][1] = fma((double)g[e], (double)((v[e] - mean[e]) * inv[e]), acc[e][1]);
-        }
-        if (drg) drg[i] = Vec<V>::put(g);
+        for (int u = 0; u < U; ++u)
+            if (i + u * stride < vec_per_group) {
+                ld_d[u] = dyg[i + u * stride];
+                ld_z[u] = zg[i + u * stride];
+                if (yg) ld_y[u] = yg[i + u * stride];
+            }
+        float f1[V], f2[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) f1[e] = f2[e] = 0.f;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (i + u * stride < vec_per_group) {
+                float d[V], o[V], v[V], g[V];
+                Vec<V>::get(ld_d[u], d);
+                Vec<V>::get(ld_z[u], v);
+                if (yg) Vec<V>::get(ld_y[u], o);
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    g[e] = yg ? act_bwd(d[e], o[e], flags) : d[e];
+                    f1[e] += g[e];
+                    f2[e] = fmaf(g[e], (v[e] - mean[e]) * inv[e], f2[e]);
+                }
+                if (drg) drg[i + u * stride] = Vec<V>::put(g);
+            }
+#pragma unroll
+        for (int e = 0; e < V; ++e) { acc[e][0] += (double)f1[e]; acc[e][1] += (double)f2[e]; }
     }
     fold_to_global<V, 2>(acc, CV, sums + (int64_t)blockIdx.y * C * 2);
 }
@@ -235,6 +266,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const float *__rest
     const T *yg = y ? reinterpret_cast<const T *>(y) + base : nullptr;
     T *dzg = reinterpret_cast<T *>(dz) + base;
     const int64_t stride = (int64_t)gridDim.x * 256;
+#pragma unroll 4
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < vec_per_group; i += stride) {
         float d[V], o[V], v[V], r[V];
         Vec<V>::get(dyg[i], d);
