@@ -5,9 +5,8 @@
 // activation (+ the residual add of ResidualBlock.forward :213-214).  Eval-mode norms with running statistics never get
 // here: they are folded into the packed conv weights (engine._fold_norm).
 //
-// All tensors NHWC fp32 [N, H*W, C].  Statistics: runs of 8 elements per lane in fp32, everything above that in float64
-// (ATen's CPU kernels use double accumulators for float input; E[z^2] - E[z]^2 in double has no cancellation problem
-// at these magnitudes).  Every kernel is a
+// All tensors NHWC fp32 [N, H*W, C].  Statistics are accumulated in float64 (ATen's CPU kernels use double accumulators
+// for float input; E[z^2] - E[z]^2 in double has no cancellation problem at these magnitudes).  Every kernel is a
 // flat, fully coalesced float4 stream whose grid stride is a multiple of C/4, so a thread owns the same four channels
 // for its whole life: per-channel constants sit in registers and the per-channel sums fold through shared memory into
 // one float64 atomic per channel per block.  HBM-bound: forward = read z twice + write y (12 B / element), backward =
@@ -39,6 +38,13 @@ __device__ __forceinline__ float act_bwd(float dy, float y, int flags) {
     if (flags & RAMNET_NORM_SIGMOID) return dy * y * (1.f - y);
     return dy;
 }
+
+// The per-(group, channel) sums live in kReplicas copies ([G][kReplicas][C][2] doubles): block b adds into copy
+// b % kReplicas and the finalize kernels add the copies up.  One copy made ~1000 blocks queue their float64 atomics on
+// the same 2 C addresses (ncu: the BatchNorm statistics kernel took 49 us for 33 MB, the InstanceNorm one -- 4 x the
+// addresses -- 29 us).
+constexpr int kReplicas = 16;
+
 
 // Folds the block's per-thread float64 partial sums (NS per channel lane) and adds them to out[(c * NS) + k].
 template <int V, int NS>
@@ -72,51 +78,74 @@ __global__ void __launch_bounds__(256) norm_stats_kernel(const float *__restrict
 #pragma unroll
     for (int e = 0; e < V; ++e) acc[e][0] = acc[e][1] = 0.0;
     const int64_t stride = (int64_t)gridDim.x * 256;
-    // runs of U elements per lane are summed in fp32 (U independent loads in flight), the runs in float64
+    // U independent loads in flight per thread; every element goes into the float64 sums (fp32 partial sums of z^2 over
+    // the run were measured to move a gradient sample of the reference golden by 6e-3, at no gain in time)
     constexpr int U = 8;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < vec_per_group; i += stride * U) {
         T ld[U];
 #pragma unroll
         for (int u = 0; u < U; ++u)
             if (i + u * stride < vec_per_group) ld[u] = zg[i + u * stride];
-        float fs[V], fq[V];
-#pragma unroll
-        for (int e = 0; e < V; ++e) fs[e] = fq[e] = 0.f;
 #pragma unroll
         for (int u = 0; u < U; ++u)
             if (i + u * stride < vec_per_group) {
                 float v[V];
                 Vec<V>::get(ld[u], v);
 #pragma unroll
-                for (int e = 0; e < V; ++e) { fs[e] += v[e]; fq[e] = fmaf(v[e], v[e], fq[e]); }
+                for (int e = 0; e < V; ++e) {
+                    const double d = (double)v[e];
+                    acc[e][0] += d;
+                    acc[e][1] = fma(d, d, acc[e][1]);
+                }
             }
-#pragma unroll
-        for (int e = 0; e < V; ++e) { acc[e][0] += (double)fs[e]; acc[e][1] += (double)fq[e]; }
     }
-    fold_to_global<V, 2>(acc, CV, sums + (int64_t)blockIdx.y * C * 2);
+    fold_to_global<V, 2>(acc, CV, sums + ((int64_t)blockIdx.y * kReplicas + blockIdx.x % kReplicas) * C * 2);
 }
 
 // (sum, sum of squares) -> (mean, 1/sqrt(biased var + eps)); running statistics as nn.BatchNorm2d / F.instance_norm
 // update them: running = (1 - momentum) * running + momentum * stat, with the UNBIASED variance, averaged over the
 // instances for InstanceNorm (ATen runs it as a batch norm over [1, N*C, H, W] and averages the N updated copies).
+__device__ __forceinline__ void replica_sum(const double *__restrict__ sums, int g, int c, int C, double &s0, double &s1) {
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll
+    for (int r = 0; r < kReplicas; r += 2) {      // 2 * kReplicas independent loads
+        const double *p = sums + (((int64_t)g * kReplicas + r) * C + c) * 2;
+        a0 += p[0];
+        a1 += p[1];
+        b0 += p[(int64_t)C * 2];
+        b1 += p[(int64_t)C * 2 + 1];
+    }
+    s0 = a0 + b0;
+    s1 = a1 + b1;
+}
+
 __global__ void norm_finalize_kernel(const double *__restrict__ sums, int G, int C, double count, double eps,
                                      double momentum, float *__restrict__ running_mean, float *__restrict__ running_var,
                                      float *__restrict__ stats) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double mean_acc = 0.0, var_acc = 0.0;
-    for (int g = 0; g < G; ++g) {
-        const double s = sums[((int64_t)g * C + c) * 2], ss = sums[((int64_t)g * C + c) * 2 + 1];
-        const double mean = s / count;
-        double var = ss / count - mean * mean;
-        if (var < 0.0) var = 0.0;
-        stats[((int64_t)g * C + c) * 2] = (float)mean;
-        stats[((int64_t)g * C + c) * 2 + 1] = (float)(1.0 / sqrt(var + eps));
-        mean_acc += mean;
-        var_acc += var * (count / (count > 1.0 ? count - 1.0 : 1.0));
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // one thread per (group, channel)
+    if (idx >= G * C) return;
+    const int g = idx / C, c = idx - g * C;
+    const double unbias = count / (count > 1.0 ? count - 1.0 : 1.0);
+    double s, ss;
+    replica_sum(sums, g, c, C, s, ss);
+    const double mean = s / count;
+    double var = ss / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[(int64_t)idx * 2] = (float)mean;
+    stats[(int64_t)idx * 2 + 1] = (float)(1.0 / sqrt(var + eps));
+    if (g == 0 && (running_mean || running_var)) {
+        double mean_acc = mean, var_acc = var * unbias;
+        for (int gg = 1; gg < G; ++gg) {        // InstanceNorm with running statistics: average over the instances
+            replica_sum(sums, gg, c, C, s, ss);
+            const double m = s / count;
+            double v = ss / count - m * m;
+            if (v < 0.0) v = 0.0;
+            mean_acc += m;
+            var_acc += v * unbias;
+        }
+        if (running_mean) running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mean_acc / G);
+        if (running_var) running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * var_acc / G);
     }
-    if (running_mean) running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mean_acc / G);
-    if (running_var) running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * var_acc / G);
 }
 
 // RAMNET_NORM_RUNNING: the statistics are the running ones (an eval-mode norm that gradients flow through)
@@ -188,7 +217,7 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float *__res
 #pragma unroll
     for (int e = 0; e < V; ++e) acc[e][0] = acc[e][1] = 0.0;
     const int64_t stride = (int64_t)gridDim.x * 256;
-    constexpr int U = 4;          // runs of U elements per lane in fp32, U x 3 independent loads in flight
+    constexpr int U = 4;          // U x 3 independent loads in flight per thread
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < vec_per_group; i += stride * U) {
         T ld_d[U], ld_z[U], ld_y[U];
 #pragma unroll
@@ -198,9 +227,6 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float *__res
                 ld_z[u] = zg[i + u * stride];
                 if (yg) ld_y[u] = yg[i + u * stride];
             }
-        float f1[V], f2[V];
-#pragma unroll
-        for (int e = 0; e < V; ++e) f1[e] = f2[e] = 0.f;
 #pragma unroll
         for (int u = 0; u < U; ++u)
             if (i + u * stride < vec_per_group) {
@@ -211,32 +237,35 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float *__res
 #pragma unroll
                 for (int e = 0; e < V; ++e) {
                     g[e] = yg ? act_bwd(d[e], o[e], flags) : d[e];
-                    f1[e] += g[e];
-                    f2[e] = fmaf(g[e], (v[e] - mean[e]) * inv[e], f2[e]);
+                    acc[e][0] += (double)g[e];
+                    acc[e][1] = fma((double)g[e], (double)((v[e] - mean[e]) * inv[e]), acc[e][1]);
                 }
                 if (drg) drg[i + u * stride] = Vec<V>::put(g);
             }
-#pragma unroll
-        for (int e = 0; e < V; ++e) { acc[e][0] += (double)f1[e]; acc[e][1] += (double)f2[e]; }
     }
-    fold_to_global<V, 2>(acc, CV, sums + (int64_t)blockIdx.y * C * 2);
+    fold_to_global<V, 2>(acc, CV, sums + ((int64_t)blockIdx.y * kReplicas + blockIdx.x % kReplicas) * C * 2);
 }
 
 // (sum g, sum g xhat) -> per-(group, channel) means the data gradient subtracts; dgamma / dbeta accumulate (+=)
 __global__ void norm_bwd_finalize_kernel(const double *__restrict__ sums, int G, int C, double count, int running,
                                          float *__restrict__ coef, float *__restrict__ dgamma, float *__restrict__ dbeta) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s1 = 0.0, s2 = 0.0;
-    for (int g = 0; g < G; ++g) {
-        const double a = sums[((int64_t)g * C + c) * 2], b = sums[((int64_t)g * C + c) * 2 + 1];
-        coef[((int64_t)g * C + c) * 2] = running ? 0.f : (float)(a / count);
-        coef[((int64_t)g * C + c) * 2 + 1] = running ? 0.f : (float)(b / count);
-        s1 += a;
-        s2 += b;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // one thread per (group, channel)
+    if (idx >= G * C) return;
+    const int g = idx / C, c = idx - g * C;
+    double a, b;
+    replica_sum(sums, g, c, C, a, b);
+    coef[(int64_t)idx * 2] = running ? 0.f : (float)(a / count);
+    coef[(int64_t)idx * 2 + 1] = running ? 0.f : (float)(b / count);
+    if (g == 0 && (dgamma || dbeta)) {
+        double s1 = a, s2 = b;
+        for (int gg = 1; gg < G; ++gg) {
+            replica_sum(sums, gg, c, C, a, b);
+            s1 += a;
+            s2 += b;
+        }
+        if (dbeta) dbeta[c] += (float)s1;
+        if (dgamma) dgamma[c] += (float)s2;
     }
-    if (dbeta) dbeta[c] += (float)s1;
-    if (dgamma) dgamma[c] += (float)s2;
 }
 
 // backward pass 2: dz = gamma * invstd * (g - mean(g) - xhat * mean(g xhat))
@@ -300,7 +329,7 @@ int plan_norm(const ramnet_handle *h, const void *p0, int N, int64_t HW, int C, 
     g->count = (double)rows;
     g->vec_per_group = rows * (C / g->V);
     int64_t blocks = (g->vec_per_group + 256 * 8 - 1) / (256 * 8);
-    const int64_t cap = (int64_t)h->sm_count * 8 / g->G > 0 ? (int64_t)h->sm_count * 8 / g->G : 1;
+    const int64_t cap = (int64_t)h->sm_count * 4 / g->G > 0 ? (int64_t)h->sm_count * 4 / g->G : 1;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     g->grid = dim3((unsigned)blocks, (unsigned)g->G, 1);
@@ -308,7 +337,7 @@ int plan_norm(const ramnet_handle *h, const void *p0, int N, int64_t HW, int C, 
 }
 }  // namespace
 
-extern "C" size_t ramnet_norm_scratch_bytes(int N, int C) { return (size_t)N * C * 2 * sizeof(double); }
+extern "C" size_t ramnet_norm_scratch_bytes(int N, int C) { return (size_t)N * kReplicas * C * 2 * sizeof(double); }
 
 extern "C" int ramnet_norm_fwd(ramnet_handle *h, const float *z, const float *res, const float *gamma,
                                const float *beta, float *running_mean, float *running_var, double momentum, double eps,
@@ -325,16 +354,16 @@ extern "C" int ramnet_norm_fwd(ramnet_handle *h, const float *z, const float *re
     if (res && g.V == 4 && (((uintptr_t)res) & 15)) g.V = 1, g.vec_per_group *= 4;
     if (g.V == 1 && (C > 256 || 256 % C)) return ramnet_set_error(RAMNET_EUNSUPPORTED, "norm_fwd: unaligned operand with C=%d", C);
     cudaStream_t s = (cudaStream_t)stream;
-    const int cb = (C + 127) / 128;
+    const int cb = (C + 127) / 128, gcb = (g.G * C + 127) / 128;
     if (running) {
         norm_running_stats_kernel<<<cb, 128, 0, s>>>(running_mean, running_var, C, eps, stats);
         RAMNET_LAUNCH_CHECK(h);
     } else {
-        RAMNET_CUDA(cudaMemsetAsync(sums, 0, (size_t)g.G * C * 2 * sizeof(double), s));
+        RAMNET_CUDA(cudaMemsetAsync(sums, 0, (size_t)g.G * kReplicas * C * 2 * sizeof(double), s));
         if (g.V == 4) norm_stats_kernel<4><<<g.grid, 256, 0, s>>>(z, g.vec_per_group, C, sums);
         else norm_stats_kernel<1><<<g.grid, 256, 0, s>>>(z, g.vec_per_group, C, sums);
         RAMNET_LAUNCH_CHECK(h);
-        norm_finalize_kernel<<<cb, 128, 0, s>>>(sums, g.G, C, g.count, eps, momentum, running_mean, running_var, stats);
+        norm_finalize_kernel<<<gcb, 128, 0, s>>>(sums, g.G, C, g.count, eps, momentum, running_mean, running_var, stats);
         RAMNET_LAUNCH_CHECK(h);
     }
     if (g.V == 4) norm_apply_kernel<4><<<g.grid, 256, 0, s>>>(z, res, gamma, beta, stats, g.vec_per_group, C, flags, y);
@@ -358,12 +387,12 @@ extern "C" int ramnet_norm_bwd(ramnet_handle *h, const float *dy, const float *y
         g.V = 1, g.vec_per_group *= 4;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    const int cb = (C + 127) / 128;
-    RAMNET_CUDA(cudaMemsetAsync(sums, 0, (size_t)g.G * C * 2 * sizeof(double), s));
+    const int gcb = (g.G * C + 127) / 128;
+    RAMNET_CUDA(cudaMemsetAsync(sums, 0, (size_t)g.G * kReplicas * C * 2 * sizeof(double), s));
     if (g.V == 4) norm_bwd_reduce_kernel<4><<<g.grid, 256, 0, s>>>(dy, y, z, stats, g.vec_per_group, C, flags, sums, dres);
     else norm_bwd_reduce_kernel<1><<<g.grid, 256, 0, s>>>(dy, y, z, stats, g.vec_per_group, C, flags, sums, dres);
     RAMNET_LAUNCH_CHECK(h);
-    norm_bwd_finalize_kernel<<<cb, 128, 0, s>>>(sums, g.G, C, g.count, running ? 1 : 0, coef, dgamma, dbeta);
+    norm_bwd_finalize_kernel<<<gcb, 128, 0, s>>>(sums, g.G, C, g.count, running ? 1 : 0, coef, dgamma, dbeta);
     RAMNET_LAUNCH_CHECK(h);
     if (g.V == 4) norm_bwd_apply_kernel<4><<<g.grid, 256, 0, s>>>(dy, y, z, stats, coef, gamma, g.vec_per_group, C, flags, dz);
     else norm_bwd_apply_kernel<1><<<g.grid, 256, 0, s>>>(dy, y, z, stats, coef, gamma, g.vec_per_group, C, flags, dz);

@@ -15,7 +15,10 @@
 // operation by operation in float64 (B200 has full-rate-enough FP64 for 6 flops/event);
 // index arithmetic is int64 and bit-exact; the vote value is rounded to fp32 once, where
 // numpy casts it on accumulation.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+namespace cg = cooperative_groups;
 
 struct Vote {
     int64_t il, ir;  // flat voxel index or -1
@@ -63,6 +66,34 @@ __global__ void __launch_bounds__(256) voxel_grid_kernel(const double *__restric
     if (dT == 0.0) dT = 1.0;  // :92-93
     int oob = 0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const Vote v = event_vote(ev, i, t0, dT, bins, width, height);
+        if (v.il >= 0) red_add_f32(grid + v.il, v.vl);
+        if (v.ir >= 0) red_add_f32(grid + v.ir, v.vr);
+        oob += v.oob;
+    }
+    if (oob_count != nullptr && oob) atomicAdd(oob_count, oob);
+}
+
+// Same kernel with the zero fill of the grid folded in (small event counts: the separate 2.6 MB memset node and the
+// kernel boundary behind it were ~3 of the 8.3 us the call took up to 1e5 events).  Cooperative launch: every block is
+// resident, so the grid-wide barrier between "zero" and "vote" cannot deadlock; the runtime refuses the launch otherwise
+// and the caller falls back to memset + voxel_grid_kernel.
+__global__ void __launch_bounds__(256) voxel_grid_fused_kernel(const double *__restrict__ ev, int64_t n, int bins, int width,
+                                                               int height, float *__restrict__ grid, int64_t total,
+                                                               int32_t *__restrict__ oob_count) {
+    cg::grid_group gg = cg::this_grid();
+    const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, gsize = (int64_t)gridDim.x * blockDim.x;
+    float4 *g4 = reinterpret_cast<float4 *>(grid);       // 16-byte aligned (checked by the launcher)
+    const int64_t total4 = total >> 2;
+    for (int64_t i = gtid; i < total4; i += gsize) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = (total4 << 2) + gtid; i < total; i += gsize) grid[i] = 0.f;
+    if (oob_count != nullptr && gtid == 0) *oob_count = 0;
+    gg.sync();
+    const double t0 = __ldg(ev);
+    double dT = __dsub_rn(__ldg(ev + 4 * (n - 1)), t0);
+    if (dT == 0.0) dT = 1.0;  // :92-93
+    int oob = 0;
+    for (int64_t i = gtid; i < n; i += gsize) {
         const Vote v = event_vote(ev, i, t0, dT, bins, width, height);
         if (v.il >= 0) red_add_f32(grid + v.il, v.vl);
         if (v.ir >= 0) red_add_f32(grid + v.ir, v.vr);
@@ -208,6 +239,34 @@ static int check_args(ramnet_handle *h, const double *events, int64_t n, int bin
     return RAMNET_OK;
 }
 
+// Zero fill + votes in one cooperative launch; returns false when that path does not apply (the caller then runs
+// cudaMemsetAsync + voxel_grid_kernel).  RAMNET_VOXEL_FUSED=0 disables it.
+static bool launch_voxel_fused(ramnet_handle *h, const double *events, int64_t n, int bins, int width, int height, float *grid,
+                               int32_t *oob_count, cudaStream_t s) {
+    static const bool enabled = [] { const char *e = getenv("RAMNET_VOXEL_FUSED"); return !(e && e[0] == '0'); }();
+    static const int64_t fused_max = [] { const char *e = getenv("RAMNET_VOXEL_FUSED_MAX"); return e ? atoll(e) : 400000ll; }();
+    if (!enabled || n <= 0 || n > fused_max || (((uintptr_t)grid) & 15)) return false;
+    static int per_sm = -1, coop = -1;
+    if (coop < 0) {
+        int dev = h->device;
+        if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess) coop = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, voxel_grid_fused_kernel, 256, 0) != cudaSuccess) per_sm = 0;
+    }
+    if (!coop || per_sm <= 0) return false;
+    int64_t total = (int64_t)bins * width * height;
+    int64_t want = (n + 255) / 256;
+    if (want < (int64_t)h->sm_count * 2) want = (int64_t)h->sm_count * 2;       // enough stores in flight for the zero fill
+    const int blocks = (int)imin64(want, (int64_t)h->sm_count * imin64(per_sm, 4));
+    void *args[] = {(void *)&events, (void *)&n, (void *)&bins, (void *)&width, (void *)&height, (void *)&grid, (void *)&total,
+                    (void *)&oob_count};
+    if (cudaLaunchCooperativeKernel((const void *)voxel_grid_fused_kernel, dim3(blocks), dim3(256), args, 0, s) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    h->launches++;
+    return true;
+}
+
 extern "C" int ramnet_voxel_grid(ramnet_handle *h, const double *events, int64_t n, int bins, int width, int height,
                                  float *grid, int32_t *oob_count, void *stream) {
     RAMNET_DEVICE_GUARD(h);
@@ -215,6 +274,7 @@ extern "C" int ramnet_voxel_grid(ramnet_handle *h, const double *events, int64_t
     if (rc) return rc;
     RAMNET_CHECK_ARG(grid != nullptr, "voxel_grid: grid is NULL");
     cudaStream_t s = (cudaStream_t)stream;
+    if (launch_voxel_fused(h, events, n, bins, width, height, grid, oob_count, s)) return RAMNET_OK;
     RAMNET_CUDA(cudaMemsetAsync(grid, 0, sizeof(float) * (size_t)bins * width * height, s));
     if (oob_count) RAMNET_CUDA(cudaMemsetAsync(oob_count, 0, sizeof(int32_t), s));
     if (n == 0) return RAMNET_OK;
@@ -272,6 +332,11 @@ extern "C" int ramnet_voxel_grid_ex(ramnet_handle *h, const double *events, int6
         voxel_unpack_kernel<<<(int)imin64((hw + 255) / 256, (int64_t)h->sm_count * 8), 256, 0, s>>>(
             (const float4 *)workspace, grid, bins, hw, stats);
         RAMNET_LAUNCH_CHECK(h);
+    } else if (launch_voxel_fused(h, events, n, bins, width, height, grid, oob_count, s)) {
+        if (stats) {
+            voxel_nz_stats_kernel<<<pw_blocks, 256, 0, s>>>(grid, total, stats);
+            RAMNET_LAUNCH_CHECK(h);
+        }
     } else {
         RAMNET_CUDA(cudaMemsetAsync(grid, 0, sizeof(float) * (size_t)total, s));
         if (n > 0) {

@@ -707,7 +707,7 @@ def norm_fwd(z, kind: str, act, gamma=None, beta=None, res=None, running_mean=No
     flags = NORM_ACT[act] | (_lib.NORM_INSTANCE if kind == 'IN' else 0) | (0 if batch_stats else _lib.NORM_RUNNING) | \
         (_lib.NORM_ROUND_TF32 if round_tf32 else 0)
     G = N if (kind == 'IN' and batch_stats) else 1
-    sums = torch.empty(G * C * 2, dtype=torch.float64, device=z.device)
+    sums = torch.empty(_lib.load().ramnet_norm_scratch_bytes(N, C) // 8, dtype=torch.float64, device=z.device)
     stats = torch.empty((G, C, 2), dtype=torch.float32, device=z.device)
     y = empty_nhwc(N, C, H, W, z.device)
     for t in (gamma, beta, running_mean, running_var):
@@ -726,7 +726,7 @@ def norm_bwd(dy, y, z, stats, kind: str, act, gamma=None, batch_stats=True, roun
     flags = NORM_ACT[act] | (_lib.NORM_INSTANCE if kind == 'IN' else 0) | (0 if batch_stats else _lib.NORM_RUNNING) | \
         (_lib.NORM_ROUND_TF32 if round_tf32 else 0)
     G = stats.shape[0]
-    sums = torch.empty(G * C * 2, dtype=torch.float64, device=z.device)
+    sums = torch.empty(_lib.load().ramnet_norm_scratch_bytes(N, C) // 8, dtype=torch.float64, device=z.device)
     coef = torch.empty((G, C, 2), dtype=torch.float32, device=z.device)
     dz = empty_nhwc(N, C, H, W, z.device)
     dres = empty_nhwc(N, C, H, W, z.device) if want_dres else None
