@@ -246,6 +246,11 @@ static bool launch_voxel_fused(ramnet_handle *h, const double *events, int64_t n
     static const bool enabled = [] { const char *e = getenv("RAMNET_VOXEL_FUSED"); return !(e && e[0] == '0'); }();
     static const int64_t fused_max = [] { const char *e = getenv("RAMNET_VOXEL_FUSED_MAX"); return e ? atoll(e) : 400000ll; }();
     if (!enabled || n <= 0 || n > fused_max || (((uintptr_t)grid) & 15)) return false;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;      // a refused launch must not invalidate a capture
+    if (cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+        (void)cudaGetLastError();
+        return false;
+    }
     static int per_sm = -1, coop = -1;
     if (coop < 0) {
         int dev = h->device;

@@ -65,10 +65,9 @@ class UNet(BaseUNet):
         self._wcache = E.WeightCache()
 
     def forward(self, x, return_logits=False):
-        if self.skip_type != 'sum' or not self.use_upsample_conv or self.activation_name != 'sigmoid' \
-                or self.num_output_channels != 1:
-            raise RamnetError("UNet: only skip_type='sum', use_upsample_conv=True, sigmoid, 1 output channel "
-                              'are implemented')
+        if self.skip_type != 'sum' or self.activation_name != 'sigmoid' or self.num_output_channels != 1:
+            # skip_type='no_skip' is ill-formed upstream (decoders are built for 2C channels, unet.py:78, and fed C)
+            raise RamnetError("UNet: only skip_type='sum', sigmoid, 1 output channel are implemented")
         kind = E.resolve_mma_kind(self._mma_kind_name)
         tf32 = kind == ops.MMA_TF32
         cache, n = self._wcache, self.num_encoders
@@ -87,6 +86,10 @@ class UNet(BaseUNet):
             x = E.conv_layer(cache, f'res{i}/2', rb.conv2, kind, y, ops.EPI_BIAS_RES_RELU, res=x,
                              norm_mod=getattr(rb, 'bn2', None), norm_kind=rb.norm, training=self.training, round_out=True)
         for i, dec in enumerate(self.decoders):
+            if not self.use_upsample_conv:        # TransposedConvLayer decoders (unet.py:48-51), skip sum fused in
+                x = E.transposed_conv_layer(cache, f'dec{i}', dec.transposed_conv2d, kind, x, blocks[n - i - 1],
+                                            getattr(dec, 'norm_layer', None), dec.norm, self.training)
+                continue
             up = E.upsample_add(x, blocks[n - i - 1], tf32)
             x = E.conv_layer(cache, f'dec{i}', dec.conv2d, kind, up, ops.EPI_BIAS_RELU,
                              norm_mod=getattr(dec, 'norm_layer', None), norm_kind=dec.norm, training=self.training)

@@ -14,7 +14,8 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 MODEL_CASES = ['cfg1_shipped', 'cfg1_stress2', 'rect_b2', 'k5_shipped', 'lstm_state', 'lstm_enc', 'bn_eval',
                'baseline_rgb', 'baseline_e', 'baseline_ergb0', 'unet', 'transposed',
                # live norm layers: train-mode BatchNorm / InstanceNorm statistics, ResidualBlock InstanceNorm in eval mode
-               'bn_train', 'in_train', 'in_eval', 'bn_train_tconv_lstm', 'unet_bn_train']
+               'bn_train', 'in_train', 'in_eval', 'bn_train_tconv_lstm', 'unet_bn_train',
+               'unet_transposed', 'unet_transposed_in']
 GRAD_CASES = ['grads_shipped', 'grads_bn_train', 'grads_in_train', 'grads_bn_eval']
 
 
