@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RAMNET_ABI_VERSION 2
+#define RAMNET_ABI_VERSION 3
 
 enum {
     RAMNET_OK = 0,
@@ -362,14 +362,19 @@ int ramnet_si_loss_grad(ramnet_handle *h, const float *pred, const float *target
 /* ---- §8f-1  MultiScaleGradient loss -------------------------------------- *
  * Replaces model/loss.py:22-70 (4 x AvgPool2d + kornia spatial_gradient + boolean-mask sums) for C = 1 maps
  * [N,1,H,W]: stats[2*s] = sum |g|, stats[2*s+1] = count of non-NaN gradient entries at scale s (float64, zeroed by
- * the callee); value = (1/S) sum_s stats[2s]/stats[2s+1] * N * 2; grad = d value / d pred * scale (0 at NaN). */
+ * the callee); value = (1/S) sum_s stats[2s]/stats[2s+1] * N * 2; grad = d value / d pred * scale (0 at NaN).
+ * ramnet_msg_pooled_count = P, the pooled pixels over all scales.  workspace: ramnet_msg_workspace_bytes bytes of 16-byte
+ * aligned scratch (pooled maps + replicated statistics in _stats, pooled-pixel gradients in _grad).  signs (nullable in _stats; P int8 pairs): sign of the two Sobel components per
+ * pooled pixel, (0, 0) where NaN -- all the backward pass needs from the forward pass. */
+int64_t ramnet_msg_pooled_count(int N, int H, int W, int start_scale, int scales);
+size_t ramnet_msg_workspace_bytes(int N, int H, int W, int start_scale, int scales);
 int ramnet_msg_loss_stats(ramnet_handle *h, const float *pred, const float *target, int N, int H, int W,
-                          int start_scale, int scales, double *stats, void *stream);
+                          int start_scale, int scales, double *stats, float *workspace, signed char *signs, void *stream);
 int ramnet_msg_loss_value(ramnet_handle *h, const double *stats, int N, int scales, float *loss_out, void *stream);
 /* n_batch: batch size the value was normalised with (0 = N; the global batch when `stats` were all-reduced). */
-int ramnet_msg_loss_grad(ramnet_handle *h, const float *pred, const float *target, int N, int H, int W,
-                         int start_scale, int scales, const double *stats, int n_batch, float scale,
-                         const float *scale_dev, float *grad, void *stream);
+int ramnet_msg_loss_grad(ramnet_handle *h, const signed char *signs, int N, int H, int W, int start_scale, int scales,
+                         const double *stats, int n_batch, float scale, const float *scale_dev, float *workspace,
+                         float *grad, void *stream);
 /* preview=True branch (model/loss.py:46-47, TensorBoard only): out [N,1,H/pool,W/pool] = kornia sobel magnitude
  * sqrt(gx^2 + gy^2 + 1e-6) of AvgPool2d(pool)(pred - target). */
 int ramnet_msg_sobel_preview(ramnet_handle *h, const float *pred, const float *target, int N, int H, int W,

@@ -105,10 +105,13 @@ SIGNATURES = {
     'ramnet_si_loss_value': (c_int, [c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p]),
     'ramnet_si_loss_grad': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float, c_float,
                                     c_void_p, c_int, c_void_p, c_void_p]),
-    'ramnet_msg_loss_stats': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'ramnet_msg_pooled_count': (c_int64, [c_int, c_int, c_int, c_int, c_int]),
+    'ramnet_msg_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    'ramnet_msg_loss_stats': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                      c_void_p, c_void_p]),
     'ramnet_msg_loss_value': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
-    'ramnet_msg_loss_grad': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
-                                     c_float, c_void_p, c_void_p, c_void_p]),
+    'ramnet_msg_loss_grad': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                                     c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     'ramnet_msg_sobel_preview': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'ramnet_adam_step_dev': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double,
                                      c_double, c_double, c_double, c_void_p, c_int, c_void_p]),

@@ -141,17 +141,156 @@ __device__ __forceinline__ bool msg_sobel(const float *pred, const float *target
     return gx == gx && gy == gy;
 }
 
-__global__ void __launch_bounds__(256) msg_stats_kernel(const float *__restrict__ pred, const float *__restrict__ target,
-                                                        int N, int H, int W, int k, double *__restrict__ stats) {
-    const int hp = H / k, wp = W / k;
-    const int64_t total = (int64_t)N * hp * wp;
+// ---- round 2: three streaming kernels instead of "recompute everything per pooled pixel + scatter with atomics" -------
+// (the first version re-read 9 k^2 pixels of pred and target per pooled pixel and issued up to 8 k^2 global atomics for it:
+//  31 + 40 us per scale and term at batch 4, 256x512, 0.02 of the HBM peak; a real training step evaluates 16 terms x 4 scales)
+//   msg_pool_kernel : every scale's NaN-propagating average pool of (pred - target), ONE launch      -> workspace
+//   msg_stats_kernel: Sobel on the pooled maps, sum |g| and count per scale (grid.y = scale), signs  -> int8 pairs
+//   msg_gp_kernel   : d loss / d pooled pixel by GATHERING the signs of the <= 9 gradient pixels whose
+//                     (replicate-clamped) window contains it                                          -> workspace
+//   msg_grad_kernel : d loss / d pred = sum over the scales of the pooled-pixel gradient its window belongs to
+struct MsgGeom {
+    int N, H, W, scales;
+    int k[8];
+    int hp[8], wp[8];   // pooled map size per scale
+    int sh[8];          // log2(k) when k is a power of two, else -1
+    int64_t off[9];     // start of scale s in the concatenated pooled index space
+    int rowoff[9];      // start of scale s in the concatenated list of pooled-row GROUPS (kMsgRows rows of W / k[s] pixels)
+};
+constexpr int kMsgReplicas = 64;    // copies of the per-scale (sum, count) pairs the blocks' float64 atomics are spread over
+
+// Launch shape of the pooled-space kernels: blockIdx.x = a group of kMsgRows consecutive pooled rows of one scale,
+// blockIdx.y * 256 + threadIdx.x = pooled column: no per-thread 64-bit div / mod (where the first version spent its time)
+// and kMsgRows independent memory round trips per thread (one row per block was bound by block turnover).
+constexpr int kMsgRows = 4;
+__device__ __forceinline__ bool msg_locate(const MsgGeom &g, int &sc, int &k, int &hp, int &wp, int &row0, int &nrows, int &qx) {
+    const int grp = blockIdx.x;
+    sc = 0;
+    while (sc + 1 < g.scales && grp >= g.rowoff[sc + 1]) ++sc;
+    k = g.k[sc];
+    hp = g.hp[sc];
+    wp = g.wp[sc];
+    row0 = (grp - g.rowoff[sc]) * kMsgRows;        // row = n * hp + qy
+    nrows = min(kMsgRows, g.N * hp - row0);
+    qx = blockIdx.y * 256 + threadIdx.x;
+    return qx < wp;
+}
+
+// sum over a K x K window of (pred - target), every load issued before the first add (a runtime-k loop made the K * K / 4
+// vector loads of a thread one dependent round trip each: 20 us for the batch-4 maps); same summation order as msg_pooled
+template <int K>
+__device__ __forceinline__ float msg_window(const float *__restrict__ p, const float *__restrict__ t, int W) {
+    float acc = 0.f;
+    if constexpr (K % 4 == 0) {
+        float4 a[K][K / 4], b[K][K / 4];
+#pragma unroll
+        for (int y = 0; y < K; ++y)
+#pragma unroll
+            for (int x = 0; x < K / 4; ++x) {
+                a[y][x] = reinterpret_cast<const float4 *>(p + (int64_t)y * W)[x];
+                b[y][x] = reinterpret_cast<const float4 *>(t + (int64_t)y * W)[x];
+            }
+#pragma unroll
+        for (int y = 0; y < K; ++y)
+#pragma unroll
+            for (int x = 0; x < K / 4; ++x) {
+                acc += a[y][x].x - b[y][x].x; acc += a[y][x].y - b[y][x].y;
+                acc += a[y][x].z - b[y][x].z; acc += a[y][x].w - b[y][x].w;
+            }
+    } else {
+        float a[K][K], b[K][K];
+#pragma unroll
+        for (int y = 0; y < K; ++y)
+#pragma unroll
+            for (int x = 0; x < K; ++x) { a[y][x] = p[(int64_t)y * W + x]; b[y][x] = t[(int64_t)y * W + x]; }
+#pragma unroll
+        for (int y = 0; y < K; ++y)
+#pragma unroll
+            for (int x = 0; x < K; ++x) acc += a[y][x] - b[y][x];
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(256) msg_pool_kernel(const float *__restrict__ pred, const float *__restrict__ target,
+                                                       MsgGeom g, float *__restrict__ pooled) {
+    int sc, k, hp, wp, row0, nrows, qx;
+    if (!msg_locate(g, sc, k, hp, wp, row0, nrows, qx)) return;
+    float acc[kMsgRows];
+#pragma unroll
+    for (int rr = 0; rr < kMsgRows; ++rr) {
+        acc[rr] = 0.f;
+        if (rr >= nrows) continue;
+        const int64_t base = (int64_t)(row0 + rr) * k * g.W + (int64_t)qx * k;      // pooled row (n, qy) starts at image row (n * hp + qy) * k
+        const bool al = (g.W & 3) == 0 && (((uintptr_t)pred | (uintptr_t)target) & 15) == 0;
+        if (k == 1) {
+            acc[rr] = pred[base] - target[base];
+        } else if (k == 2) {
+            acc[rr] = msg_window<2>(pred + base, target + base, g.W);
+        } else if (k == 4 && al) {
+            acc[rr] = msg_window<4>(pred + base, target + base, g.W);
+        } else if (k == 8 && al) {
+            acc[rr] = msg_window<8>(pred + base, target + base, g.W);
+        } else if ((k & 3) == 0 && al) {                  // rows of k floats as float4 (16-byte aligned: W % 4 == 0, k % 4 == 0)
+            for (int y = 0; y < k; ++y) {
+                const float4 *p4 = reinterpret_cast<const float4 *>(pred + base + (int64_t)y * g.W);
+                const float4 *t4 = reinterpret_cast<const float4 *>(target + base + (int64_t)y * g.W);
+                for (int x = 0; x < (k >> 2); ++x) {
+                    const float4 a = p4[x], b = t4[x];
+                    acc[rr] += a.x - b.x; acc[rr] += a.y - b.y; acc[rr] += a.z - b.z; acc[rr] += a.w - b.w;   // msg_pooled's order
+                }
+            }
+        } else {
+            for (int y = 0; y < k; ++y)
+                for (int x = 0; x < k; ++x) acc[rr] += pred[base + (int64_t)y * g.W + x] - target[base + (int64_t)y * g.W + x];
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < kMsgRows; ++rr)
+        if (rr < nrows) pooled[g.off[sc] + (int64_t)(row0 + rr) * wp + qx] = (k == 1) ? acc[rr] : acc[rr] / (float)(k * k);
+}
+
+// Sobel weights along one axis for the gradient pixel r = q - 1 + j seen from pooled pixel q, with the replicate clamp
+// folded in: sum over d in {-1, 0, 1} with clamp(r + d) == q of smooth[d] / diff[d]
+__device__ __forceinline__ void msg_axis_weights(int q, int n, float (&sm)[3], float (&df)[3]) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int r = q - 1 + j;
+        float a = 0.f, b = 0.f;
+        if (r >= 0 && r < n) {
+#pragma unroll
+            for (int d = -1; d <= 1; ++d)
+                if (min(max(r + d, 0), n - 1) == q) { a += (d == 0) ? 2.f : 1.f; b += (float)d; }
+        }
+        sm[j] = a;
+        df[j] = b;
+    }
+}
+
+__global__ void __launch_bounds__(256) msg_stats_kernel(const float *__restrict__ pooled, MsgGeom g, double *__restrict__ rep,
+                                                        double *__restrict__ stats, char2 *__restrict__ signs) {
+    int sc, k, hp, wp, row0, nrows, qx;
+    const bool active = msg_locate(g, sc, k, hp, wp, row0, nrows, qx);
     double s = 0.0, cnt = 0.0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int qx = (int)(i % wp), qy = (int)((i / wp) % hp), n = (int)(i / ((int64_t)wp * hp));
-        float gx, gy;
-        if (msg_sobel(pred, target, n, H, W, k, hp, wp, qy, qx, gx, gy)) {
-            s += (double)fabsf(gx) + (double)fabsf(gy);
-            cnt += 2.0;
+    if (active) {
+        const int xl = max(qx - 1, 0), xr = min(qx + 1, wp - 1);
+#pragma unroll
+        for (int rr = 0; rr < kMsgRows; ++rr) {
+            if (rr >= nrows) continue;
+            const int row = row0 + rr, n = row / hp, qy = row - n * hp;
+            const float *Pn = pooled + g.off[sc] + (int64_t)n * hp * wp;    // this image's pooled map
+            const float *r0 = Pn + (int64_t)max(qy - 1, 0) * wp, *r1 = Pn + (int64_t)qy * wp, *r2 = Pn + (int64_t)min(qy + 1, hp - 1) * wp;
+            const float v00 = r0[xl], v01 = r0[qx], v02 = r0[xr], v10 = r1[xl], v11 = r1[qx], v12 = r1[xr];
+            const float v20 = r2[xl], v21 = r2[qx], v22 = r2[xr];
+            const float gx = ((v02 - v00) + 2.f * (v12 - v10) + (v22 - v20)) * 0.125f + 0.f * v11 + 0.f * v01 + 0.f * v21;
+            const float gy = ((v20 - v00) + 2.f * (v21 - v01) + (v22 - v02)) * 0.125f + 0.f * v11 + 0.f * v10 + 0.f * v12;
+            const bool ok = gx == gx && gy == gy;
+            if (ok) {
+                s += (double)fabsf(gx) + (double)fabsf(gy);
+                cnt += 2.0;
+            }
+            if (signs)
+                signs[g.off[sc] + (int64_t)row * wp + qx] =
+                    ok ? make_char2((gx > 0.f) - (gx < 0.f), (gy > 0.f) - (gy < 0.f)) : make_char2(0, 0);
         }
     }
 #pragma unroll
@@ -159,9 +298,28 @@ __global__ void __launch_bounds__(256) msg_stats_kernel(const float *__restrict_
         s += __shfl_xor_sync(0xffffffffu, s, o);
         cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(stats + 0, s);
-        atomicAdd(stats + 1, cnt);
+    __shared__ double sh[2][8];
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = cnt; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sh[threadIdx.x][w];
+        // `rep` is the replicated scratch [kMsgReplicas][2 * scales] (+ a ticket); the last block to finish adds the copies up
+        if (t != 0.0) atomicAdd(rep + (blockIdx.x % kMsgReplicas) * 2 * g.scales + 2 * sc + threadIdx.x, t);
+    }
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned *ticket = reinterpret_cast<unsigned *>(rep + kMsgReplicas * 2 * g.scales);
+        last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+    }
+    __syncthreads();
+    if (last && (int)threadIdx.x < 2 * g.scales) {
+        __threadfence();
+        double t = 0.0;
+        for (int r = 0; r < kMsgReplicas; ++r) t += __ldcg(rep + r * 2 * g.scales + threadIdx.x);
+        stats[threadIdx.x] = t;
     }
 }
 
@@ -171,52 +329,139 @@ __global__ void msg_value_kernel(const double *__restrict__ stats, int N, int sc
     *out = (float)(loss / (double)scales);
 }
 
-__global__ void __launch_bounds__(256) msg_grad_kernel(const float *__restrict__ pred, const float *__restrict__ target,
-                                                       int N, int H, int W, int k, const double *__restrict__ stats,
-                                                       int scales, int n_batch, float gscale,
-                                                       const float *__restrict__ scale_dev, float *__restrict__ grad) {
-    const int hp = H / k, wp = W / k;
-    const int64_t total = (int64_t)N * hp * wp;
-    // d loss / d g = sign(g) * B * 2 / (count * scales); Sobel /8; avg-pool adjoint 1/k^2
-    // (B = n_batch: the GLOBAL batch size when the statistics were all-reduced over data-parallel ranks)
-    const float up = gscale * (scale_dev ? *scale_dev : 1.f);
-    const float coef = up * (float)((double)n_batch * 2.0 / (stats[1] * (double)scales)) * 0.125f / (float)(k * k);
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int qx = (int)(i % wp), qy = (int)((i / wp) % hp), n = (int)(i / ((int64_t)wp * hp));
-        float gx, gy;
-        if (!msg_sobel(pred, target, n, H, W, k, hp, wp, qy, qx, gx, gy)) continue;
-        const float sx = (gx > 0.f) - (gx < 0.f), sy = (gy > 0.f) - (gy < 0.f);
-        const float kx[3][3] = {{-1, 0, 1}, {-2, 0, 2}, {-1, 0, 1}};
+// d loss / d pooled pixel: d loss / d g = sign(g) * B * 2 / (count * scales), Sobel / 8, avg-pool adjoint 1 / k^2
+// (B = n_batch: the GLOBAL batch size when the statistics were all-reduced over data-parallel ranks)
+__global__ void __launch_bounds__(256) msg_gp_kernel(const char2 *__restrict__ signs, MsgGeom g, const double *__restrict__ stats,
+                                                     int n_batch, float gscale, const float *__restrict__ scale_dev,
+                                                     float *__restrict__ gp) {
+    int sc, k, hp, wp, row0, nrows, qx;
+    const bool active = msg_locate(g, sc, k, hp, wp, row0, nrows, qx);
+    __shared__ float coef_sh;
+    if (threadIdx.x == 0) {     // one float64 division per block, not per thread
+        const float up = gscale * (scale_dev ? *scale_dev : 1.f);
+        coef_sh = up * (float)((double)n_batch * 2.0 / (stats[2 * sc + 1] * (double)g.scales)) * 0.125f / (float)(k * k);
+    }
+    __syncthreads();
+    if (!active) return;
+    const float coef = coef_sh;
 #pragma unroll
-        for (int dy = -1; dy <= 1; ++dy)
+    for (int rr = 0; rr < kMsgRows; ++rr) {
+        if (rr >= nrows) continue;
+        const int row = row0 + rr, n = row / hp, qy = row - n * hp;
+        const char2 *Sn = signs + g.off[sc] + (int64_t)n * hp * wp;
+        float acc = 0.f;
+        if (qy >= 1 && qy + 1 < hp && qx >= 1 && qx + 1 < wp) {
+            // interior: gradient pixel r = q - 1 + j reads q through the single tap d = 1 - j
+            const float sm[3] = {1.f, 2.f, 1.f}, df[3] = {1.f, 0.f, -1.f};
 #pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-                const float c = coef * (sx * kx[dy + 1][dx + 1] + sy * kx[dx + 1][dy + 1]);
-                if (c == 0.f) continue;
-                const int py = min(max(qy + dy, 0), hp - 1), px = min(max(qx + dx, 0), wp - 1);   // replicate-pad adjoint
-                float *gp = grad + ((int64_t)n * H + (int64_t)py * k) * W + (int64_t)px * k;
-                for (int y = 0; y < k; ++y)
-                    for (int x = 0; x < k; ++x) atomicAdd(gp + (int64_t)y * W + x, c);
+            for (int jy = 0; jy < 3; ++jy)
+#pragma unroll
+                for (int jx = 0; jx < 3; ++jx) {
+                    const char2 sg = Sn[(int64_t)(qy - 1 + jy) * wp + qx - 1 + jx];
+                    acc += (float)sg.x * sm[jy] * df[jx] + (float)sg.y * df[jy] * sm[jx];
+                }
+        } else {
+            float smy[3], dfy[3], smx[3], dfx[3];
+            msg_axis_weights(qy, hp, smy, dfy);
+            msg_axis_weights(qx, wp, smx, dfx);
+#pragma unroll
+            for (int jy = 0; jy < 3; ++jy) {
+                const int ry = qy - 1 + jy;
+                if (ry < 0 || ry >= hp) continue;
+#pragma unroll
+                for (int jx = 0; jx < 3; ++jx) {
+                    const int rx = qx - 1 + jx;
+                    if (rx < 0 || rx >= wp) continue;
+                    const char2 sg = Sn[(int64_t)ry * wp + rx];
+                    // gradient pixel r reads pooled pixel q = clamp(r + d): gx weight smooth_y[d_y] * diff_x[d_x], gy the transpose
+                    acc += (float)sg.x * smy[jy] * dfx[jx] + (float)sg.y * dfy[jy] * smx[jx];
+                }
             }
+        }
+        gp[g.off[sc] + (int64_t)row * wp + qx] = coef * acc;
     }
 }
 
-extern "C" int ramnet_msg_loss_stats(ramnet_handle *h, const float *pred, const float *target, int N, int H, int W,
-                                     int start_scale, int scales, double *stats, void *stream) {
-    RAMNET_DEVICE_GUARD(h);
-    RAMNET_CHECK_ARG(h && pred && target && stats && N > 0 && H > 0 && W > 0 && scales > 0 && scales <= 8 && start_scale >= 1,
-                     "msg_loss_stats: bad argument");
-    RAMNET_CHECK_ARG(H % (start_scale << (scales - 1)) == 0 && W % (start_scale << (scales - 1)) == 0,
-                     "msg_loss_stats: H, W must be divisible by start_scale * 2^(scales-1)");
-    cudaStream_t s = (cudaStream_t)stream;
-    RAMNET_CUDA(cudaMemsetAsync(stats, 0, 2 * scales * sizeof(double), s));
-    for (int sc = 0; sc < scales; ++sc) {
-        const int k = start_scale << sc;
-        const int64_t total = (int64_t)N * (H / k) * (W / k);
-        msg_stats_kernel<<<(int)imin64((total + 255) / 256, (int64_t)h->sm_count * 8), 256, 0, s>>>(pred, target, N, H, W, k,
-                                                                                                    stats + 2 * sc);
-        RAMNET_LAUNCH_CHECK(h);
+// a thread sums the pooled-pixel gradients of 4 consecutive pixels of a full-resolution row over the scales
+__global__ void __launch_bounds__(256) msg_grad_kernel(const float *__restrict__ gp, MsgGeom g, float *__restrict__ grad) {
+    const int W4 = (g.W + 3) >> 2;
+    const int64_t total = (int64_t)g.N * g.H * W4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int rowi = (int)(i / W4), x0 = (int)(i - (int64_t)rowi * W4) * 4;
+        const int n = rowi / g.H, y = rowi - n * g.H;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int sc = 0; sc < g.scales; ++sc) {
+            const int k = g.k[sc], hp = g.hp[sc], wp = g.wp[sc], sh = g.sh[sc];
+            const float *row = gp + g.off[sc] + ((int64_t)n * hp + (sh >= 0 ? y >> sh : y / k)) * wp;
+            if (sh >= 2) {              // k = 4, 8, ...: the four pixels share one pooled pixel
+                const float v = row[x0 >> sh];
+                acc[0] += v; acc[1] += v; acc[2] += v; acc[3] += v;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (x0 + e < g.W) acc[e] += row[sh >= 0 ? (x0 + e) >> sh : (x0 + e) / k];
+            }
+        }
+        float *out = grad + ((int64_t)n * g.H + y) * g.W + x0;
+        if (x0 + 3 < g.W && ((((uintptr_t)out) & 15) == 0)) {
+            *reinterpret_cast<float4 *>(out) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        } else {
+            for (int e = 0; e < 4 && x0 + e < g.W; ++e) out[e] = acc[e];
+        }
     }
+}
+
+static int msg_geom(int N, int H, int W, int start_scale, int scales, MsgGeom *g) {
+    RAMNET_CHECK_ARG(N > 0 && H > 0 && W > 0 && scales > 0 && scales <= 8 && start_scale >= 1, "msg_loss: bad argument");
+    RAMNET_CHECK_ARG(H % (start_scale << (scales - 1)) == 0 && W % (start_scale << (scales - 1)) == 0,
+                     "msg_loss: H, W must be divisible by start_scale * 2^(scales-1)");
+    g->N = N; g->H = H; g->W = W; g->scales = scales;
+    g->off[0] = 0;
+    g->rowoff[0] = 0;
+    for (int s = 0; s < scales; ++s) {
+        g->k[s] = start_scale << s;
+        g->hp[s] = H / g->k[s];
+        g->wp[s] = W / g->k[s];
+        g->sh[s] = -1;
+        for (int b = 0; b < 30; ++b)
+            if ((1 << b) == g->k[s]) g->sh[s] = b;
+        g->off[s + 1] = g->off[s] + (int64_t)N * (H / g->k[s]) * (W / g->k[s]);
+        const int64_t rows = (int64_t)g->rowoff[s] + ((int64_t)N * (H / g->k[s]) + kMsgRows - 1) / kMsgRows;   // groups of rows
+        RAMNET_CHECK_ARG(rows < 0x7fffffff, "msg_loss: too many rows");
+        g->rowoff[s + 1] = (int)rows;
+    }
+    return RAMNET_OK;
+}
+
+// pooled pixels over all scales P: signs = P int8 pairs; workspace = P floats (pooled maps / pooled-pixel gradients)
+// followed (16-byte aligned) by the replicated statistics scratch
+extern "C" int64_t ramnet_msg_pooled_count(int N, int H, int W, int start_scale, int scales) {
+    MsgGeom g;
+    return msg_geom(N, H, W, start_scale, scales, &g) == RAMNET_OK ? g.off[scales] : -1;
+}
+static size_t msg_rep_offset(const MsgGeom &g) { return (((size_t)g.off[g.scales] * sizeof(float)) + 15) & ~(size_t)15; }
+extern "C" size_t ramnet_msg_workspace_bytes(int N, int H, int W, int start_scale, int scales) {
+    MsgGeom g;
+    if (msg_geom(N, H, W, start_scale, scales, &g) != RAMNET_OK) return 0;
+    return msg_rep_offset(g) + (size_t)kMsgReplicas * 2 * scales * sizeof(double) + 16;      // + the last-block ticket
+}
+
+extern "C" int ramnet_msg_loss_stats(ramnet_handle *h, const float *pred, const float *target, int N, int H, int W,
+                                     int start_scale, int scales, double *stats, float *workspace, signed char *signs,
+                                     void *stream) {
+    RAMNET_DEVICE_GUARD(h);
+    RAMNET_CHECK_ARG(h && pred && target && stats && workspace, "msg_loss_stats: NULL argument");
+    MsgGeom g;
+    if (int rc = msg_geom(N, H, W, start_scale, scales, &g)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    RAMNET_CHECK_ARG((((uintptr_t)workspace) & 15) == 0, "msg_loss_stats: workspace must be 16-byte aligned");
+    double *rep = reinterpret_cast<double *>(reinterpret_cast<char *>(workspace) + msg_rep_offset(g));
+    RAMNET_CUDA(cudaMemsetAsync(rep, 0, (size_t)kMsgReplicas * 2 * scales * sizeof(double) + 16, s));
+    const dim3 grid((unsigned)g.rowoff[scales], (unsigned)((W / g.k[0] + 255) / 256), 1);     // pooled rows x column tiles
+    msg_pool_kernel<<<grid, 256, 0, s>>>(pred, target, g, workspace);
+    RAMNET_LAUNCH_CHECK(h);
+    msg_stats_kernel<<<grid, 256, 0, s>>>(workspace, g, rep, stats, reinterpret_cast<char2 *>(signs));
+    RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;
 }
 
@@ -228,21 +473,21 @@ extern "C" int ramnet_msg_loss_value(ramnet_handle *h, const double *stats, int 
     return RAMNET_OK;
 }
 
-extern "C" int ramnet_msg_loss_grad(ramnet_handle *h, const float *pred, const float *target, int N, int H, int W,
-                                    int start_scale, int scales, const double *stats, int n_batch, float scale,
-                                    const float *scale_dev, float *grad, void *stream) {
+extern "C" int ramnet_msg_loss_grad(ramnet_handle *h, const signed char *signs, int N, int H, int W, int start_scale,
+                                    int scales, const double *stats, int n_batch, float scale, const float *scale_dev,
+                                    float *workspace, float *grad, void *stream) {
     RAMNET_DEVICE_GUARD(h);
-    RAMNET_CHECK_ARG(h && pred && target && stats && grad && N > 0 && scales > 0 && scales <= 8 && start_scale >= 1,
-                     "msg_loss_grad: bad argument");
+    RAMNET_CHECK_ARG(h && signs && stats && workspace && grad, "msg_loss_grad: NULL argument");
+    MsgGeom g;
+    if (int rc = msg_geom(N, H, W, start_scale, scales, &g)) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    RAMNET_CUDA(cudaMemsetAsync(grad, 0, (size_t)N * H * W * sizeof(float), s));
-    for (int sc = 0; sc < scales; ++sc) {
-        const int k = start_scale << sc;
-        const int64_t total = (int64_t)N * (H / k) * (W / k);
-        msg_grad_kernel<<<(int)imin64((total + 255) / 256, (int64_t)h->sm_count * 8), 256, 0, s>>>(
-            pred, target, N, H, W, k, stats + 2 * sc, scales, n_batch > 0 ? n_batch : N, scale, scale_dev, grad);
-        RAMNET_LAUNCH_CHECK(h);
-    }
+    const dim3 grid((unsigned)g.rowoff[scales], (unsigned)((W / g.k[0] + 255) / 256), 1);
+    msg_gp_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const char2 *>(signs), g, stats, n_batch > 0 ? n_batch : N, scale,
+                                       scale_dev, workspace);
+    RAMNET_LAUNCH_CHECK(h);
+    const int64_t total4 = (int64_t)N * H * ((W + 3) / 4);
+    msg_grad_kernel<<<(int)imin64((total4 + 511) / 512, (int64_t)h->sm_count * 16), 256, 0, s>>>(workspace, g, grad);
+    RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;
 }
 

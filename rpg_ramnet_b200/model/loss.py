@@ -132,27 +132,28 @@ class _MultiScaleGrad(torch.autograd.Function):
     @staticmethod
     def forward(ctx, prediction, target, start_scale, num_scales, process_group):
         pred, tgt = prediction.detach().float().contiguous(), target.detach().float().contiguous()
-        stats = ops.msg_loss_stats(pred, tgt, start_scale, num_scales)
+        stats, signs = ops.msg_loss_stats(pred, tgt, start_scale, num_scales, want_signs=True)
         n_batch = pred.shape[0]
         exchange, group = _resolve_group(process_group)
         if exchange:        # global (sum |g|, count) per scale and the global batch size (loss.py:57 multiplies by B)
             import torch.distributed as dist
             dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
             n_batch *= dist.get_world_size(group)
-        ctx.save_for_backward(pred, tgt, stats)
-        ctx.cfg = (start_scale, num_scales, n_batch)
+        ctx.save_for_backward(signs, stats)       # 2 bytes per pooled pixel instead of the two maps
+        ctx.cfg = (start_scale, num_scales, n_batch, tuple(pred.shape))
         return ops.msg_loss_value(stats, n_batch, num_scales)
 
     @staticmethod
     def backward(ctx, grad_out):
-        pred, tgt, stats = ctx.saved_tensors
-        g = ops.msg_loss_grad(pred, tgt, stats, ctx.cfg[0], ctx.cfg[1], 1.0, n_batch=ctx.cfg[2], scale_dev=grad_out)
+        signs, stats = ctx.saved_tensors
+        g = ops.msg_loss_grad(signs, ctx.cfg[3], stats, ctx.cfg[0], ctx.cfg[1], 1.0, n_batch=ctx.cfg[2], scale_dev=grad_out)
         return g, None, None, None, None
 
 
 class MultiScaleGradient(torch.nn.Module):
     """Mirrors model/loss.py:22-63 (`MultiScaleGradient(start_scale=1, num_scales=4)`), device-side, no dynamic shapes:
-    per scale one reduction kernel (sum |Sobel|, count of non-NaN) and one gradient kernel.  `preview=True`
+    one pooling launch over all scales, one reduction launch (sum |Sobel|, count of non-NaN, signs) and two gather launches
+    for the gradient (no atomics).  `preview=True`
     (lstm_trainer.py:162-165, TensorBoard only) returns, per scale, the Sobel magnitude of the pooled difference
     (device kernel) resized to (2H, 2W) with the reference's bicubic `torch.nn.Upsample(align_corners=True)`."""
 

@@ -775,15 +775,23 @@ def lstm_bwd(dh, dc, gates, c_prev, c_new, round_tf32=False, db=None):
     return dz, dc_prev
 
 
-def msg_loss_stats(pred, target, start_scale=1, scales=4):
+def msg_loss_stats(pred, target, start_scale=1, scales=4, want_signs=False):
+    """-> stats [2 * scales] float64 (sum |g|, count per scale); with want_signs also the int8 sign pairs per pooled
+    pixel that msg_loss_grad consumes (the only thing the backward pass needs from the forward pass)."""
     pred, target = pred.contiguous(), target.contiguous()
     N, C, H, W = pred.shape
     if C != 1:
         raise _lib.RamnetError('multi_scale_grad_loss: single-channel depth maps [N,1,H,W] expected')
+    lib = _lib.load()
+    P = lib.ramnet_msg_pooled_count(N, H, W, start_scale, scales)
+    if P <= 0:
+        raise _lib.RamnetError(f'multi_scale_grad_loss: {H}x{W} is not divisible by start_scale * 2^(scales-1)')
     stats = torch.empty(2 * scales, dtype=torch.float64, device=pred.device)
-    check(_lib.load().ramnet_msg_loss_stats(_h(pred), _p(pred), _p(target), N, H, W, start_scale, scales, _p(stats),
-                                            _stream(pred)))
-    return stats
+    ws = torch.empty(lib.ramnet_msg_workspace_bytes(N, H, W, start_scale, scales), dtype=torch.uint8, device=pred.device)
+    signs = torch.empty((P, 2), dtype=torch.int8, device=pred.device) if want_signs else None
+    check(lib.ramnet_msg_loss_stats(_h(pred), _p(pred), _p(target), N, H, W, start_scale, scales, _p(stats), _p(ws),
+                                    _p(signs), _stream(pred)))
+    return (stats, signs) if want_signs else stats
 
 
 def msg_loss_value(stats, N, scales=4):
@@ -792,14 +800,16 @@ def msg_loss_value(stats, N, scales=4):
     return out
 
 
-def msg_loss_grad(pred, target, stats, start_scale=1, scales=4, scale=1.0, n_batch=0, scale_dev=None):
-    pred, target = pred.contiguous(), target.contiguous()
-    N, C, H, W = pred.shape
-    grad = torch.empty_like(pred)
+def msg_loss_grad(signs, shape, stats, start_scale=1, scales=4, scale=1.0, n_batch=0, scale_dev=None):
+    """d loss / d pred [N,1,H,W] from the sign pairs of msg_loss_stats(want_signs=True) and the (possibly all-reduced) stats."""
+    N, C, H, W = shape
+    dev = signs.device
+    grad = torch.empty((N, C, H, W), dtype=torch.float32, device=dev)
+    ws = torch.empty(signs.shape[0], dtype=torch.float32, device=dev)
     if scale_dev is not None and (scale_dev.dtype != torch.float32 or not scale_dev.is_cuda):
-        scale_dev = scale_dev.to(device=pred.device, dtype=torch.float32)
-    check(_lib.load().ramnet_msg_loss_grad(_h(pred), _p(pred), _p(target), N, H, W, start_scale, scales, _p(stats),
-                                           int(n_batch), scale, _p(scale_dev), _p(grad), _stream(pred)))
+        scale_dev = scale_dev.to(device=dev, dtype=torch.float32)
+    check(_lib.load().ramnet_msg_loss_grad(_h(signs), _p(signs), N, H, W, start_scale, scales, _p(stats), int(n_batch), scale,
+                                           _p(scale_dev), _p(ws), _p(grad), _stream(signs)))
     return grad
 
 
