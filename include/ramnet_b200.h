@@ -205,8 +205,10 @@ int ramnet_upsample2x_add(ramnet_handle *h, const float *x, const float *skip, f
 /* ---- a-8  prediction head ---------------------------------------------- *
  * Replaces pred (1x1 conv, no activation, statenet.py:116-117) + torch.sigmoid
  * (:313); `skip` (may be NULL) is unet.py:129's x + head.  x: NHWC [M, C];
- * w: [C]; logits / depth: [M] (= [N,1,H,W]); either output may be NULL. */
-int ramnet_pred_sigmoid(ramnet_handle *h, const float *x, const float *skip, const float *w,
+ * w: [C]; logits / depth: [M] (= [N,1,H,W]); either output may be NULL.
+ * w_skip (nullable, [C]): skip_type 'concat' (unet.py:11-12): logits = x . w + skip . w_skip instead of (x + skip) . w,
+ * i.e. the 1x1 conv over cat([x, skip]) without the concatenated tensor. */
+int ramnet_pred_sigmoid(ramnet_handle *h, const float *x, const float *skip, const float *w, const float *w_skip,
                         const float *bias, float *logits, float *depth, int64_t M, int C, void *stream);
 
 /* Tensor-core head conv (TF32 mode, 5*Cin <= 32): ramnet_head_im2row unrolls the five horizontal taps into a
@@ -310,9 +312,12 @@ int ramnet_lstm_bwd(ramnet_handle *h, const float *dh, const float *dc, const fl
                     const float *c_new, float *dz, float *dc_prev, float *db /* [4C], nn.Conv2d row order */, int64_t M,
                     int C, int flags, void *stream);
 /* pred + sigmoid adjoint: dx[m,c] = g*w[c] (= dskip), dw[c] += sum g*(x+skip)[m,c], db += sum g, g = ddepth*s(1-s);
- * skip may be NULL; depth NULL: ddepth is the gradient of the LOGITS (g = ddepth; a norm layer follows the pred conv) */
+ * skip may be NULL; depth NULL: ddepth is the gradient of the LOGITS (g = ddepth; a norm layer follows the pred conv).
+ * w_skip (nullable; concat form, see ramnet_pred_sigmoid): dskip[m,c] = g*w_skip[c] goes to its own buffer, dw is [2C]
+ * with dw[C+c] += sum g*skip[m,c] and dw[c] += sum g*x[m,c]. */
 int ramnet_pred_bwd(ramnet_handle *h, const float *ddepth, const float *depth, const float *x, const float *skip,
-                    const float *w, float *dx, float *dw, float *db, int64_t M, int C, void *stream);
+                    const float *w, const float *w_skip, float *dx, float *dskip, float *dw, float *db, int64_t M, int C,
+                    void *stream);
 /* adjoint of ramnet_upsample2x_add: dx (= dskip) [N,H,W,C] from dy [N,2H,2W,C] */
 int ramnet_upsample2x_bwd(ramnet_handle *h, const float *dy, float *dx, int N, int H, int W, int C,
                           void *stream);

@@ -73,9 +73,11 @@ CASES = {
                             2, 64, 64, 2, 17, 1.5),
     'unet_bn_train': ('ERGB2Depth', _cfg(num_bins_rgb=6, norm='BN'), 2, 64, 64, 2, 18, 1.5),
     'unet_transposed': ('ERGB2Depth', _cfg(num_bins_rgb=6, use_upsample_conv=False), 2, 64, 96, 1, 19, 1.5),
+    'unet_concat':   ('ERGB2Depth', _cfg(num_bins_rgb=6, skip_type='concat'), 2, 64, 96, 1, 25, 1.5),
+    'unet_concat_bn_train': ('ERGB2Depth', _cfg(num_bins_rgb=6, skip_type='concat', norm='BN'), 2, 64, 64, 2, 26, 1.5),
     'unet_transposed_in': ('ERGB2Depth', _cfg(num_bins_rgb=6, use_upsample_conv=False, norm='IN'), 1, 64, 64, 2, 20, 1.5),
 }
-TRAIN_MODE = {'bn_train', 'in_train', 'bn_train_tconv_lstm', 'unet_bn_train', 'unet_transposed_in'}
+TRAIN_MODE = {'bn_train', 'in_train', 'bn_train_tconv_lstm', 'unet_bn_train', 'unet_transposed_in', 'unet_concat_bn_train'}
 
 
 scale_weights = O.scale_weights

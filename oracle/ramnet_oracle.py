@@ -433,12 +433,14 @@ def ergb2depth_unet(sd: StateDict, config: dict, item: dict, return_logits: bool
     for i in range(cfg.num_residual_blocks):
         x = residual_block(sd, f'{P}resblocks.{i}', x, cfg.norm)
     for i in range(cfg.num_encoders):
-        x = x + blocks[cfg.num_encoders - i - 1]                # skip on EVERY decoder (unet.py:126-127)
+        skip = blocks[cfg.num_encoders - i - 1]                 # skip on EVERY decoder (unet.py:126-127)
+        x = torch.cat([x, skip], 1) if cfg.skip_type == 'concat' else x + skip      # unet.py:11-16
         if cfg.use_upsample_conv:
             x = upsample_conv_layer(sd, f'{P}decoders.{i}', x, cfg.norm)
         else:
             x = transposed_conv_layer(sd, f'{P}decoders.{i}', x, cfg.norm)
-    logits = conv_layer(sd, P + 'pred', x + head, 1, 0, relu=False, norm=cfg.norm, exact=True)   # unet.py:129
+    xh = torch.cat([x, head], 1) if cfg.skip_type == 'concat' else x + head
+    logits = conv_layer(sd, P + 'pred', xh, 1, 0, relu=False, norm=cfg.norm, exact=True)   # unet.py:129
     pred = torch.sigmoid(logits)
     return ({'image': pred}, {'image': logits}) if return_logits else {'image': pred}
 

@@ -458,25 +458,25 @@ class UpsampleAddFn(torch.autograd.Function):
 
 
 class PredFn(torch.autograd.Function):
-    """1x1 pred conv + sigmoid."""
+    """1x1 pred conv + sigmoid over x (+ skip), or over cat([x, skip]) when `concat` (unet.py:11-12,129)."""
 
     @staticmethod
-    def forward(ctx, x, skip, weight, bias):
-        depth = ops.pred_sigmoid(x, skip, weight.detach(), None if bias is None else bias.detach())
+    def forward(ctx, x, skip, weight, bias, concat=False):
+        depth = ops.pred_sigmoid(x, skip, weight.detach(), None if bias is None else bias.detach(), concat=concat)
         ctx.save_for_backward(x, skip, depth)
-        ctx.weight, ctx.bias = weight, bias
+        ctx.weight, ctx.bias, ctx.concat = weight, bias, concat
         return depth
 
     @staticmethod
     def backward(ctx, ddepth):
         x, skip, depth = ctx.saved_tensors
         weight, bias = ctx.weight, ctx.bias
-        dx, dw, db = ops.pred_bwd(ddepth, depth, x, weight, skip)
+        dx, dskip, dw, db = ops.pred_bwd(ddepth, depth, x, weight, skip, ctx.concat)
         with torch.no_grad():
             _grad_of(weight).add_(dw.view(weight.shape))
             if bias is not None:
                 _grad_of(bias).add_(db)
-        return dx, (dx if skip is not None else None), None, None
+        return dx, dskip, None, None, None
 
 
 class NormActFn(torch.autograd.Function):
@@ -517,19 +517,19 @@ class PredLogitsFn(torch.autograd.Function):
     """1x1 pred conv without its activation (a norm layer sits between them, statenet.py:116-117 with norm set)."""
 
     @staticmethod
-    def forward(ctx, x, skip, weight, bias):
-        logits = ops.pred_logits(x, skip, weight.detach(), None if bias is None else bias.detach())
+    def forward(ctx, x, skip, weight, bias, concat=False):
+        logits = ops.pred_logits(x, skip, weight.detach(), None if bias is None else bias.detach(), concat)
         ctx.save_for_backward(x, skip)
-        ctx.weight, ctx.bias = weight, bias
+        ctx.weight, ctx.bias, ctx.concat = weight, bias, concat
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
         x, skip = ctx.saved_tensors
         weight, bias = ctx.weight, ctx.bias
-        dx, dw, db = ops.pred_logits_bwd(dlogits, x, weight, skip)
+        dx, dskip, dw, db = ops.pred_logits_bwd(dlogits, x, weight, skip, ctx.concat)
         with torch.no_grad():
             _grad_of(weight).add_(dw.view(weight.shape))
             if bias is not None:
                 _grad_of(bias).add_(db)
-        return dx, (dx if skip is not None else None), None, None
+        return dx, dskip, None, None, None

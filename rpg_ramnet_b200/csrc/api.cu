@@ -156,8 +156,10 @@ extern "C" int ramnet_upsample2x_add(ramnet_handle *h, const float *x, const flo
 // prediction head: logits[m] = sum_c (x[m,c] (+ skip[m,c])) * w[c] + b ; depth = sigmoid(logits)
 // 8 lanes per pixel, float4 per lane per iteration -> fully coalesced 128 B rows for C=32.
 // ---------------------------------------------------------------------------------
+// w_skip != nullptr: skip_type 'concat' (unet.py:11-12,129): logits = x . w + skip . w_skip instead of (x + skip) . w
 __global__ void __launch_bounds__(256) pred_sigmoid_kernel(const float *__restrict__ x, const float *__restrict__ skip,
-                                                           const float *__restrict__ w, const float *__restrict__ bias,
+                                                           const float *__restrict__ w, const float *__restrict__ w_skip,
+                                                           const float *__restrict__ bias,
                                                            float *__restrict__ logits, float *__restrict__ depth,
                                                            int64_t M, int C) {
     const int lane8 = threadIdx.x & 7;
@@ -171,7 +173,12 @@ __global__ void __launch_bounds__(256) pred_sigmoid_kernel(const float *__restri
                 float4 a = *reinterpret_cast<const float4 *>(x + m * C + c);
                 if (skip) {
                     float4 s = *reinterpret_cast<const float4 *>(skip + m * C + c);
-                    a.x += s.x; a.y += s.y; a.z += s.z; a.w += s.w;
+                    if (w_skip) {
+                        const float4 ws = __ldg(reinterpret_cast<const float4 *>(w_skip + c));
+                        acc += s.x * ws.x + s.y * ws.y + s.z * ws.z + s.w * ws.w;
+                    } else {
+                        a.x += s.x; a.y += s.y; a.z += s.z; a.w += s.w;
+                    }
                 }
                 const float4 ww = __ldg(reinterpret_cast<const float4 *>(w + c));
                 acc += a.x * ww.x + a.y * ww.y + a.z * ww.z + a.w * ww.w;
@@ -189,12 +196,13 @@ __global__ void __launch_bounds__(256) pred_sigmoid_kernel(const float *__restri
 }
 
 extern "C" int ramnet_pred_sigmoid(ramnet_handle *h, const float *x, const float *skip, const float *w,
-                                   const float *bias, float *logits, float *depth, int64_t M, int C, void *stream) {
+                                   const float *w_skip, const float *bias, float *logits, float *depth, int64_t M, int C,
+                                   void *stream) {
     RAMNET_DEVICE_GUARD(h);
-    RAMNET_CHECK_ARG(h && x && w && (logits || depth), "ramnet_pred_sigmoid: NULL argument");
+    RAMNET_CHECK_ARG(h && x && w && (logits || depth) && (!w_skip || skip), "ramnet_pred_sigmoid: NULL argument");
     RAMNET_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0, "ramnet_pred_sigmoid: bad shape M=%lld C=%d (C%%4)", (long long)M, C);
     const int blocks = (int)imin64((M * 8 + 255) / 256, (int64_t)h->sm_count * 16);
-    pred_sigmoid_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, skip, w, bias, logits, depth, M, C);
+    pred_sigmoid_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, skip, w, w_skip, bias, logits, depth, M, C);
     RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;
 }

@@ -404,20 +404,25 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(const float *__restrict__
 }
 
 // prediction head adjoint: dlogit = ddepth * s(1-s); dx[m, c] = dlogit[m] * w[c]; dw[c] += sum_m dlogit*x[m,c]; db += sum dlogit
+// w_skip != nullptr (skip_type 'concat'): the skip has its own weights: dskip[m, c] = dlogit[m] * w_skip[c],
+// dw[C + c] += sum_m dlogit * skip[m, c], and dw[c] sums x alone.
 __global__ void __launch_bounds__(256) pred_bwd_kernel(const float *__restrict__ ddepth, const float *__restrict__ depth,
                                                        const float *__restrict__ x, const float *__restrict__ skip,
-                                                       const float *__restrict__ w,
-                                                       float *__restrict__ dx, float *__restrict__ dw,
+                                                       const float *__restrict__ w, const float *__restrict__ w_skip,
+                                                       float *__restrict__ dx, float *__restrict__ dskip, float *__restrict__ dw,
                                                        float *__restrict__ db, int64_t M, int C) {
-    extern __shared__ float sacc[];   // [C + 1]
-    for (int c = threadIdx.x; c <= C; c += blockDim.x) sacc[c] = 0.f;
+    extern __shared__ float sacc[];   // [2C + 1]: dw (x part), dw (skip part, concat only), db
+    for (int c = threadIdx.x; c <= 2 * C; c += blockDim.x) sacc[c] = 0.f;
     __syncthreads();
     const int lane8 = threadIdx.x & 7;
-    float wreg[8], dwreg[8];   // C <= 64: lane handles channels lane8*4.. (+32)
+    float wreg[8], wsreg[8], dwreg[8], dwsreg[8];   // C <= 64: lane handles channels lane8*4.. (+32)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { wreg[j] = 0.f; dwreg[j] = 0.f; }
+    for (int j = 0; j < 8; ++j) { wreg[j] = 0.f; wsreg[j] = 0.f; dwreg[j] = 0.f; dwsreg[j] = 0.f; }
     for (int c = lane8 * 4, j = 0; c < C; c += 32, j += 4)
-        for (int e = 0; e < 4; ++e) wreg[j + e] = w[c + e];
+        for (int e = 0; e < 4; ++e) {
+            wreg[j + e] = w[c + e];
+            if (w_skip) wsreg[j + e] = w_skip[c + e];
+        }
     float dbacc = 0.f;
     const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> 3;
     for (int64_t m = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3; m < M; m += stride) {
@@ -431,18 +436,27 @@ __global__ void __launch_bounds__(256) pred_bwd_kernel(const float *__restrict__
             float4 xv = *reinterpret_cast<const float4 *>(x + m * C + c);
             if (skip) {
                 const float4 sv = *reinterpret_cast<const float4 *>(skip + m * C + c);
-                xv.x += sv.x; xv.y += sv.y; xv.z += sv.z; xv.w += sv.w;
+                if (w_skip) {
+                    *reinterpret_cast<float4 *>(dskip + m * C + c) =
+                        make_float4(dl * wsreg[j], dl * wsreg[j + 1], dl * wsreg[j + 2], dl * wsreg[j + 3]);
+                    dwsreg[j] += dl * sv.x; dwsreg[j + 1] += dl * sv.y; dwsreg[j + 2] += dl * sv.z; dwsreg[j + 3] += dl * sv.w;
+                } else {
+                    xv.x += sv.x; xv.y += sv.y; xv.z += sv.z; xv.w += sv.w;
+                }
             }
             *reinterpret_cast<float4 *>(dx + m * C + c) = make_float4(dl * wreg[j], dl * wreg[j + 1], dl * wreg[j + 2], dl * wreg[j + 3]);
             dwreg[j] += dl * xv.x; dwreg[j + 1] += dl * xv.y; dwreg[j + 2] += dl * xv.z; dwreg[j + 3] += dl * xv.w;
         }
     }
     for (int c = lane8 * 4, j = 0; c < C; c += 32, j += 4)
-        for (int e = 0; e < 4; ++e) atomicAdd(&sacc[c + e], dwreg[j + e]);
-    if (lane8 == 0) atomicAdd(&sacc[C], dbacc);
+        for (int e = 0; e < 4; ++e) {
+            atomicAdd(&sacc[c + e], dwreg[j + e]);
+            if (w_skip) atomicAdd(&sacc[C + c + e], dwsreg[j + e]);
+        }
+    if (lane8 == 0) atomicAdd(&sacc[2 * C], dbacc);
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(dw + c, sacc[c]);
-    if (threadIdx.x == 0 && db) atomicAdd(db, sacc[C]);
+    for (int c = threadIdx.x; c < (w_skip ? 2 * C : C); c += blockDim.x) atomicAdd(dw + c, sacc[c]);
+    if (threadIdx.x == 0 && db) atomicAdd(db, sacc[2 * C]);
 }
 
 // adjoint of (x + skip) -> bilinear x2: dx[m] gathers from the <= 3x3 output pixels it feeds; dskip = dx.
@@ -706,12 +720,14 @@ extern "C" int ramnet_gru_ru_bwd(ramnet_handle *h, const float *drh, const float
 }
 
 extern "C" int ramnet_pred_bwd(ramnet_handle *h, const float *ddepth, const float *depth, const float *x,
-                               const float *skip, const float *w, float *dx, float *dw, float *db, int64_t M, int C,
-                               void *stream) {
+                               const float *skip, const float *w, const float *w_skip, float *dx, float *dskip, float *dw,
+                               float *db, int64_t M, int C, void *stream) {
     RAMNET_DEVICE_GUARD(h);
     RAMNET_CHECK_ARG(h && ddepth && x && w && dx && dw && M > 0 && C % 4 == 0 && C <= 64, "pred_bwd: bad argument (C <= 64)");
+    RAMNET_CHECK_ARG(!w_skip || (skip && dskip), "pred_bwd: the concat form needs skip and dskip");
     const int blocks = (int)imin64((M * 8 + 255) / 256, (int64_t)h->sm_count * 8);
-    pred_bwd_kernel<<<blocks, 256, (C + 1) * sizeof(float), (cudaStream_t)stream>>>(ddepth, depth, x, skip, w, dx, dw, db, M, C);
+    pred_bwd_kernel<<<blocks, 256, (2 * C + 1) * sizeof(float), (cudaStream_t)stream>>>(ddepth, depth, x, skip, w, w_skip, dx, dskip,
+                                                                                        dw, db, M, C);
     RAMNET_LAUNCH_CHECK(h);
     return RAMNET_OK;
 }

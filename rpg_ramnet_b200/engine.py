@@ -363,15 +363,16 @@ def upsample_add(x, skip, tf32):
     return ops.upsample2x_add(x, skip, round_tf32=tf32)
 
 
-def pred_layer(x, pred_conv, norm_mod, norm_kind, training, return_logits=False, skip=None):
+def pred_layer(x, pred_conv, norm_mod, norm_kind, training, return_logits=False, skip=None, concat=False):
+    """pred (+ norm) + sigmoid over x (+ skip); concat: over cat([x, skip]) (UNet with skip_type='concat', unet.py:129)."""
     w = pred_conv.weight
     b = pred_conv.bias
     if norm_is_live(norm_mod, norm_kind, x, skip, w, b):      # pred conv -> norm -> sigmoid (statenet.py:116-117,313)
         if needs_grad(x, skip, w, b):
             from .autograd import PredLogitsFn
-            z = PredLogitsFn.apply(x, skip, w, b)
+            z = PredLogitsFn.apply(x, skip, w, b, concat)
         else:
-            z = ops.pred_logits(x, skip, w, None if b is None else b.detach().float())
+            z = ops.pred_logits(x, skip, w, None if b is None else b.detach().float(), concat)
         logits = None
         if return_logits:                 # debugging aid (inference): the normalised logits, running statistics untouched
             gamma, beta = _norm_params(norm_mod)
@@ -387,9 +388,9 @@ def pred_layer(x, pred_conv, norm_mod, norm_kind, training, return_logits=False,
         if return_logits:
             raise RamnetError('return_logits is an inference-only debugging aid')
         from .autograd import PredFn
-        return PredFn.apply(x, skip, w, b)
+        return PredFn.apply(x, skip, w, b, concat)
     wf, bf = _fold_norm(w.detach().float(), None if b is None else b.detach().float(), norm_mod, norm_kind, training)
-    return ops.pred_sigmoid(x, skip, wf, bf, want_logits=return_logits)
+    return ops.pred_sigmoid(x, skip, wf, bf, want_logits=return_logits, concat=concat)
 
 
 # ------------------------------------------------------------------------------------------

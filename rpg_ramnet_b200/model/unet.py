@@ -65,9 +65,12 @@ class UNet(BaseUNet):
         self._wcache = E.WeightCache()
 
     def forward(self, x, return_logits=False):
-        if self.skip_type != 'sum' or self.activation_name != 'sigmoid' or self.num_output_channels != 1:
+        if self.skip_type not in ('sum', 'concat') or self.activation_name != 'sigmoid' or self.num_output_channels != 1:
             # skip_type='no_skip' is ill-formed upstream (decoders are built for 2C channels, unet.py:78, and fed C)
-            raise RamnetError("UNet: only skip_type='sum', sigmoid, 1 output channel are implemented")
+            raise RamnetError("UNet: skip_type 'sum' or 'concat', sigmoid, 1 output channel are implemented")
+        concat = self.skip_type == 'concat'
+        if concat and not self.use_upsample_conv:
+            raise RamnetError("UNet: skip_type='concat' with TransposedConvLayer decoders is not implemented")
         kind = E.resolve_mma_kind(self._mma_kind_name)
         tf32 = kind == ops.MMA_TF32
         cache, n = self._wcache, self.num_encoders
@@ -90,8 +93,14 @@ class UNet(BaseUNet):
                 x = E.transposed_conv_layer(cache, f'dec{i}', dec.transposed_conv2d, kind, x, blocks[n - i - 1],
                                             getattr(dec, 'norm_layer', None), dec.norm, self.training)
                 continue
-            up = E.upsample_add(x, blocks[n - i - 1], tf32)
-            x = E.conv_layer(cache, f'dec{i}', dec.conv2d, kind, up, ops.EPI_BIAS_RELU,
+            if concat:
+                # cat([x, skip]) -> bilinear x2 -> conv == conv over the virtual concat [up(x) | up(skip)]: the kernel's two
+                # K segments (the ConvGRU's [x | h] mechanism), no concatenated tensor (unet.py:11-12,126-127)
+                up, up1 = E.upsample_add(x, None, tf32), E.upsample_add(blocks[n - i - 1], None, tf32)
+            else:
+                up, up1 = E.upsample_add(x, blocks[n - i - 1], tf32), None
+            x = E.conv_layer(cache, f'dec{i}', dec.conv2d, kind, up, ops.EPI_BIAS_RELU, x1=up1,
                              norm_mod=getattr(dec, 'norm_layer', None), norm_kind=dec.norm, training=self.training)
         pr = self.pred
-        return E.pred_layer(x, pr.conv2d, getattr(pr, 'norm_layer', None), pr.norm, self.training, return_logits, skip=head)
+        return E.pred_layer(x, pr.conv2d, getattr(pr, 'norm_layer', None), pr.norm, self.training, return_logits, skip=head,
+                            concat=concat)

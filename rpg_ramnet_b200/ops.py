@@ -405,18 +405,29 @@ def upsample2x_add(x: torch.Tensor, skip: Optional[torch.Tensor], round_tf32: bo
     return y
 
 
+def _pred_weights(w, C, concat):
+    """-> (w [C], w_skip [C] or None): skip_type 'concat' splits the [1, 2C, 1, 1] weight into the x and the skip half."""
+    wv = w.detach().reshape(-1).contiguous().float()
+    if not concat:
+        return wv, None
+    if wv.numel() != 2 * C:
+        raise _lib.RamnetError(f'pred (concat): weight has {wv.numel()} input channels, expected {2 * C}')
+    return wv[:C].contiguous(), wv[C:].contiguous()
+
+
 def pred_sigmoid(x: torch.Tensor, skip: Optional[torch.Tensor], w: torch.Tensor, b: Optional[torch.Tensor],
-                 want_logits: bool = False):
-    """1x1 conv to one channel + sigmoid. Returns depth [N,1,H,W] (and logits)."""
+                 want_logits: bool = False, concat: bool = False):
+    """1x1 conv to one channel + sigmoid. Returns depth [N,1,H,W] (and logits).  concat: the conv runs over
+    cat([x, skip]) (unet.py:11-12) without materialising it."""
     _check_nhwc(x, 'pred_sigmoid x')
     if skip is not None:
         _check_nhwc(skip, 'pred_sigmoid skip')
     N, C, H, W = x.shape
     depth = torch.empty((N, 1, H, W), dtype=torch.float32, device=x.device)
     logits = torch.empty_like(depth) if want_logits else None
-    wv = w.detach().reshape(-1).contiguous().float()
+    wv, ws = _pred_weights(w, C, concat)
     with _Prof('pred_sigmoid', 2.0 * N * H * W * C, x.device):
-        check(_lib.load().ramnet_pred_sigmoid(_h(x), _p(x), _p(skip), _p(wv), _p(b), _p(logits), _p(depth),
+        check(_lib.load().ramnet_pred_sigmoid(_h(x), _p(x), _p(skip), _p(wv), _p(ws), _p(b), _p(logits), _p(depth),
                                               N * H * W, C, _stream(x)))
     return (depth, logits) if want_logits else depth
 
@@ -678,16 +689,18 @@ def gru_ru_bwd(drh, h, r, dzru, dh, round_tf32=False, db_ru=None):
                                         FLAG_ROUND_TF32 if round_tf32 else 0, _stream(h)))
 
 
-def pred_bwd(ddepth, depth, x, w, skip=None):
+def pred_bwd(ddepth, depth, x, w, skip=None, concat=False):
+    """-> (dx, dskip, dw, db): dskip is dx itself for the summed skip, its own tensor for the concatenated one (dw then [2C])."""
     _check_nhwc(x, 'pred_bwd x')
     N, C, H, W = x.shape
     dx = empty_nhwc(N, C, H, W, x.device)
-    dw = torch.zeros(C, dtype=torch.float32, device=x.device)
+    wv, ws = _pred_weights(w, C, concat)
+    dskip = empty_nhwc(N, C, H, W, x.device) if concat else None
+    dw = torch.zeros(2 * C if concat else C, dtype=torch.float32, device=x.device)
     db = torch.zeros(1, dtype=torch.float32, device=x.device)
-    wv = w.detach().reshape(-1).contiguous().float()
-    check(_lib.load().ramnet_pred_bwd(_h(x), _p(ddepth.contiguous()), _p(depth.contiguous()), _p(x), _p(skip), _p(wv), _p(dx), _p(dw),
-                                      _p(db), N * H * W, C, _stream(x)))
-    return dx, dw, db
+    check(_lib.load().ramnet_pred_bwd(_h(x), _p(ddepth.contiguous()), _p(None if depth is None else depth.contiguous()), _p(x),
+                                      _p(skip), _p(wv), _p(ws), _p(dx), _p(dskip), _p(dw), _p(db), N * H * W, C, _stream(x)))
+    return dx, (dskip if concat else (dx if skip is not None else None)), dw, db
 
 
 NORM_ACT = {None: 0, 'none': 0, 'relu': _lib.NORM_RELU, 'sigmoid': _lib.NORM_SIGMOID}
@@ -735,27 +748,19 @@ def norm_bwd(dy, y, z, stats, kind: str, act, gamma=None, batch_stats=True, roun
     return dz, dres
 
 
-def pred_logits(x, skip, w, b):
+def pred_logits(x, skip, w, b, concat=False):
     """1x1 conv to one channel, no activation (a norm layer follows): [N,1,H,W]."""
     _check_nhwc(x, 'pred_logits x')
     N, C, H, W = x.shape
     logits = torch.empty((N, 1, H, W), dtype=torch.float32, device=x.device)
-    wv = w.detach().reshape(-1).contiguous().float()
-    check(_lib.load().ramnet_pred_sigmoid(_h(x), _p(x), _p(skip), _p(wv), _p(b), _p(logits), None, N * H * W, C, _stream(x)))
+    wv, ws = _pred_weights(w, C, concat)
+    check(_lib.load().ramnet_pred_sigmoid(_h(x), _p(x), _p(skip), _p(wv), _p(ws), _p(b), _p(logits), None, N * H * W, C, _stream(x)))
     return logits
 
 
-def pred_logits_bwd(dlogits, x, w, skip=None):
+def pred_logits_bwd(dlogits, x, w, skip=None, concat=False):
     """Adjoint of pred_logits (ramnet_pred_bwd with depth = NULL)."""
-    _check_nhwc(x, 'pred_bwd x')
-    N, C, H, W = x.shape
-    dx = empty_nhwc(N, C, H, W, x.device)
-    dw = torch.zeros(C, dtype=torch.float32, device=x.device)
-    db = torch.zeros(1, dtype=torch.float32, device=x.device)
-    wv = w.detach().reshape(-1).contiguous().float()
-    check(_lib.load().ramnet_pred_bwd(_h(x), _p(dlogits.contiguous()), None, _p(x), _p(skip), _p(wv), _p(dx), _p(dw), _p(db),
-                                      N * H * W, C, _stream(x)))
-    return dx, dw, db
+    return pred_bwd(dlogits, None, x, w, skip, concat)
 
 
 def upsample2x_bwd(dy):

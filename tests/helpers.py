@@ -15,7 +15,7 @@ MODEL_CASES = ['cfg1_shipped', 'cfg1_stress2', 'rect_b2', 'k5_shipped', 'lstm_st
                'baseline_rgb', 'baseline_e', 'baseline_ergb0', 'unet', 'transposed',
                # live norm layers: train-mode BatchNorm / InstanceNorm statistics, ResidualBlock InstanceNorm in eval mode
                'bn_train', 'in_train', 'in_eval', 'bn_train_tconv_lstm', 'unet_bn_train',
-               'unet_transposed', 'unet_transposed_in']
+               'unet_transposed', 'unet_transposed_in', 'unet_concat', 'unet_concat_bn_train']
 GRAD_CASES = ['grads_shipped', 'grads_bn_train', 'grads_in_train', 'grads_bn_eval']
 
 

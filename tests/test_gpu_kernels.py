@@ -350,6 +350,27 @@ def test_pred_sigmoid(with_skip):
     assert (d.cpu() - torch.sigmoid(logits_ref)).abs().max().item() <= 1e-6
 
 
+def test_pred_concat_forward_backward():
+    """skip_type 'concat' (unet.py:11-12,129): 1x1 conv over cat([x, skip]) without the concatenated tensor, and its adjoint."""
+    from rpg_ramnet_b200 import autograd as AG, ops
+    N, C, H, W = 2, 32, 17, 23
+    x, s = _rand((N, C, H, W), 1), _rand((N, C, H, W), 2)
+    w, b, gd = _rand((1, 2 * C, 1, 1), 3, 0.3), _rand((1,), 4), _rand((N, 1, H, W), 5)
+    tx, ts = x.double().requires_grad_(True), s.double().requires_grad_(True)
+    tw, tb = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    ref = torch.sigmoid(F.conv2d(torch.cat([tx, ts], 1), tw, tb))
+    ref.backward(gd.double())
+    gx, gs = nhwc(x).requires_grad_(True), nhwc(s).requires_grad_(True)
+    gw, gb = w.to(dev()).requires_grad_(True), b.to(dev()).requires_grad_(True)
+    d = AG.PredFn.apply(gx, gs, gw, gb, True)
+    assert (d.cpu().double() - ref.detach()).abs().max().item() <= 1e-6
+    d.backward(gd.to(dev()))
+    for got, want in ((gx.grad, tx.grad), (gs.grad, ts.grad), (gw.grad, tw.grad), (gb.grad, tb.grad)):
+        assert float((got.cpu().double() - want).abs().max()) <= 1e-4 * max(1.0, float(want.abs().max()))
+    l = ops.pred_logits(nhwc(x), nhwc(s), w.to(dev()), b.to(dev()), concat=True)
+    assert (l.cpu().double() - F.conv2d(torch.cat([x, s], 1).double(), w.double(), b.double())).abs().max().item() <= 1e-5
+
+
 def test_layout_roundtrip_and_tf32_rounding():
     from rpg_ramnet_b200 import _lib, ops
     x = _rand((2, 37, 9, 13), 8)

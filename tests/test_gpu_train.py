@@ -164,11 +164,14 @@ def test_lstm_state_model_trains_like_the_oracle():
         assert float((p.grad.cpu() - ref).norm()) <= 2e-3 * float(ref.norm()) + 2e-8, n
 
 
-def test_unet_baseline_trains_like_the_oracle():
-    """ERGB2Depth / UNet (skip on every decoder, pred on x + head): loss and all gradients vs oracle autograd."""
+@pytest.mark.parametrize('case', ['unet', 'unet_concat', 'unet_transposed'])
+def test_unet_baseline_trains_like_the_oracle(case):
+    """ERGB2Depth / UNet (skip on every decoder, pred on x + head): loss and all gradients vs oracle autograd, for the
+    summed skip, the concatenated skip (conv over the virtual concat, pred with split weights) and TransposedConvLayer
+    decoders."""
     import rpg_ramnet_b200 as R
     from helpers import load_case
-    g, meta = load_case('unet')
+    g, meta = load_case(case)
     meta = dict(meta, H=32, W=32, B=2)
     model, cfg = build_product_model(meta, mma_kind='fp32')
     model.to('cuda:0')
