@@ -49,7 +49,24 @@ loss = sum(terms)
 loss.backward()
 opt.step()
 ev = O.synth_events(20000, 64, 48, seed=2)
-grid = R.events_to_voxel_grid(ev, 5, 64, 48)
+grid = R.events_to_voxel_grid(ev, 5, 64, 48)           # fused zero-fill + votes (cooperative launch)
+# live norm layers (train-mode BatchNorm statistics, forward + backward), TransposedConvLayer decoders, ConvLSTM state
+ncfg = dict(cfg, norm='BN', use_upsample_conv=False, state_combination='convlstm')
+torch.manual_seed(0)
+with contextlib.redirect_stdout(io.StringIO()):
+    nmodel = R.ERGB2DepthRecurrent(ncfg)
+nmodel.train().to('cuda:0')
+nseq = O.synth_sequence(2, 64, 64, 1, 1, seed=3, with_targets=True)
+npreds, _, _ = nmodel(nseq[0], None, {'events0': None, 'image': None})
+nloss = sum(R.scale_invariant_loss(npreds[k], nseq[0]['depth_' + k].to('cuda:0')) for k in npreds)
+nloss.backward()
+# UNet baseline with the concatenated skip (two-source decoder convs, split-weight pred) and InstanceNorm
+ucfg = dict(cfg, num_bins_rgb=6, skip_type='concat', norm='IN')
+with contextlib.redirect_stdout(io.StringIO()):
+    umodel = R.ERGB2Depth(ucfg)
+umodel.train().to('cuda:0')
+upred, _, _ = umodel({'image': torch.rand(1, 6, 64, 64)}, None, None)
+upred['image'].mean().backward()
 torch.cuda.synchronize()
-print(f'sanitize target ok: fwd max rel err {worst:.2e}, loss {loss.item():.6f}, launches {R.launch_count(0)}, '
+print(f'sanitize target ok: fwd max rel err {worst:.2e}, loss {loss.item():.6f}, norm-model loss {nloss.item():.6f}, launches {R.launch_count(0)}, '
       f'RAMNET_PAIR={os.environ.get("RAMNET_PAIR", "default")}')
