@@ -184,6 +184,30 @@ def test_cuda_graph_replay_is_bit_identical_to_eager(name):
                 m.statenetphasedrecurrent.resblocks[0].conv1.weight.mul_(1.01)
 
 
+def test_cuda_graph_replay_with_live_instance_norm():
+    """norm='IN' in eval mode: the ConvLayers' InstanceNorm folds (running statistics) but the ResidualBlock's has none
+    and computes instance statistics inside the captured back graph (ramnet_norm_fwd: scratch from the graph pool,
+    float64 atomics -- so graph and eager agree to rounding, not bit for bit) -- and both match the reference golden."""
+    g, meta = load_case('in_eval')
+    eager, _ = build_product_model(meta, mma_kind='tf32')
+    eager.to('cuda:0')
+    graphed, _ = build_product_model(dict(meta, config=dict(meta['config'], cuda_graphs=True)), mma_kind='tf32')
+    graphed.to('cuda:0')
+    assert graphed._graphs_active()
+    seq = case_inputs(meta)
+    for rep in range(2):
+        sa = sb = None
+        la, lb = {'events0': None, 'image': None}, {'events0': None, 'image': None}
+        with torch.no_grad():
+            for l, item in enumerate(seq):
+                pa, sa_d, la = eager(item, sa, la)
+                pb, sb_d, lb = graphed(item, sb, lb)
+                sa, sb = sa_d['image'], sb_d['image']
+                for k in pa:
+                    assert max_rel_err(pb[k].cpu().numpy(), pa[k].cpu().numpy()) <= 1e-5, (rep, l, k)
+                    assert max_rel_err(pb[k].cpu().numpy(), g[f'pred/{l}/{k}']) <= 1e-3, (rep, l, k)
+
+
 def test_unsupported_and_bad_shapes_raise():
     import rpg_ramnet_b200 as R
     g, meta = load_case('cfg1_shipped')
