@@ -465,6 +465,17 @@ def si_loss_grad(pred: Tensor, target: Tensor, weight: float = 1.0, n_lambda: fl
     return torch.where(ok, (2.0 * weight / n) * (d - n_lambda * mean), torch.zeros_like(d))
 
 
+def spatial_gradient(p: Tensor) -> Tensor:
+    """kornia.filters.spatial_gradient(p, mode='sobel', order=1, normalized=True) restated: [B,C,H,W] -> [B*C,2,H,W]
+    (x derivative, y derivative), 3x3 Sobel / 8, replicate padding.  tests/test_oracle_golden.py cross-checks it against
+    OpenCV's Sobel (an independent implementation of the same published operator), which is as far as it can be pinned
+    without kornia."""
+    kx = torch.tensor([[-1., 0., 1.], [-2., 0., 2.], [-1., 0., 1.]], dtype=p.dtype) / 8.0
+    k = torch.stack([kx, kx.t()]).unsqueeze(1)                      # [2,1,3,3]
+    b, c, h, w = p.shape
+    return F.conv2d(F.pad(p.reshape(b * c, 1, h, w), [1, 1, 1, 1], mode='replicate'), k)   # [b*c,2,h,w]
+
+
 def multi_scale_grad_loss(pred: Tensor, target: Tensor, start_scale: int = 1, num_scales: int = 4) -> Tensor:
     """MultiScaleGradient.forward (model/loss.py:33-63).  kornia.filters.spatial_gradient (kornia==0.4.0,
     requirements.txt:32, NOT vendored and not installed here) restated from its published behaviour: normalised
@@ -472,13 +483,10 @@ def multi_scale_grad_loss(pred: Tensor, target: Tensor, start_scale: int = 1, nu
     reference output exists to check it against in this container."""
     diff = pred - target
     B = target.shape[0]
-    kx = torch.tensor([[-1., 0., 1.], [-2., 0., 2.], [-1., 0., 1.]], dtype=pred.dtype) / 8.0
-    k = torch.stack([kx, kx.t()]).unsqueeze(1)                      # [2,1,3,3]
     loss = 0
     for s in range(num_scales):
         p = F.avg_pool2d(diff, start_scale * 2 ** s, start_scale * 2 ** s)
-        b, c, h, w = p.shape
-        g = F.conv2d(F.pad(p.reshape(b * c, 1, h, w), [1, 1, 1, 1], mode='replicate'), k)   # [b*c,2,h,w]
+        g = spatial_gradient(p)
         ok = ~torch.isnan(g)
         loss = loss + torch.abs(g[ok]).sum() / ok.sum() * B * 2
     return loss / num_scales
