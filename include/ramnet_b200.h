@@ -95,9 +95,13 @@ enum {
     RAMNET_FLAG_S2SEG = 8,      /* ramnet_conv_fwd: 5x5 stride-2 convolution as four parity-plane K segments (multi-stage
                                    halos); w_packed from ramnet_pack_weights_s2seg ([27 taps][Cout][Cin], the (1,1) plane
                                    padded to 6 taps).  Epilogues BIAS, BIAS_RELU; TF32 path, x1 = NULL. */
-    RAMNET_FLAG_SM_TIME = 16    /* ramnet_conv_fwd planning hint: the caller runs this launch concurrently with kernels of
+    RAMNET_FLAG_SM_TIME = 16,   /* ramnet_conv_fwd planning hint: the caller runs this launch concurrently with kernels of
                                    another stream, so the tile plan minimises SM time (items / SMs) instead of the makespan
                                    of a kernel alone on the GPU (ceil(items / SMs) waves).  Results are unaffected. */
+    RAMNET_FLAG_DYNAMIC = 32,   /* ramnet_conv_fwd (TF32): work items are drawn from a global counter instead of a static round
+                                   robin, so that CTAs that start late (SMs still held by a kernel of another stream) take
+                                   less.  `workspace` must then point at 8 bytes that are zero at launch and belong to this
+                                   launch site alone (two ints: the kernel resets them when it ends).  Results are unaffected. */
 };
 
 /* One implicit-GEMM convolution:  y[m, n] = epi( sum_{tap,c} x[pix(m,tap), c] * w[tap, n, c] ).

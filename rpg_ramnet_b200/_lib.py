@@ -19,6 +19,7 @@ FLAG_HPACK = 2
 FLAG_UPCONV = 4
 FLAG_S2SEG = 8
 FLAG_SM_TIME = 16
+FLAG_DYNAMIC = 32
 LOSS_LOG_SPACE = 1
 NORM_INSTANCE, NORM_RUNNING, NORM_RELU, NORM_SIGMOID, NORM_ROUND_TF32 = 1, 2, 4, 8, 16
 WGRAD_FULL, WGRAD_PARTIAL_FIRST, WGRAD_PARTIAL_ADD, WGRAD_FINALIZE = range(4)

@@ -359,6 +359,8 @@ struct HaloGeom {
     int pair;                // 1: CTA-pair mode (cta_group::2, M = 256): a work item is two patches x one BN-wide slice
     int items;               // patches (pair mode: patch pairs) * n_slices
     unsigned long long *prof; // RAMNET_PROF=1: per-role wait-cycle counters (debug), else nullptr
+    int *sched;              // RAMNET_FLAG_DYNAMIC: {next-item counter, finished workers} in global memory (both 0 at launch,
+                             // reset by the last worker); nullptr = static round-robin item assignment
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -505,6 +507,44 @@ __device__ __forceinline__ void halo_arrive_leader(uint64_t *bar) {
     }
 }
 
+// ---- dynamic work distribution (RAMNET_FLAG_DYNAMIC) ------------------------------------------------------------------
+// Static assignment (item = worker, worker + nworkers, ...) gives every worker the same share whenever it starts.  When two
+// streams overlap (engine.GraphRunner), a kernel's CTAs start at different times -- as the SMs of the other stream's kernel
+// free up -- so the early ones finish early and idle.  Here warp 3 of the (leader) CTA, idle after the TMEM allocation,
+// draws items from a global counter and feeds them to the roles through a 4-slot shared-memory ring (one full / one empty
+// mbarrier per slot; in pair mode the leader also writes the peer's ring and the peer's warps release slots on the
+// leader's barriers).  The first item stays static (no start-up latency); the counter pair resets itself.
+// MEASURED NEGATIVE (profiles/r02_dynamic_items.txt): bit-identical and ~1 % slower per kernel in isolation, but the
+// two-stream forward step got SLOWER with it (12.6 -> 13.0 ms back graphs only, 13.8 front only, 13.45 both), so
+// engine.GraphRunner leaves it off (RAMNET_DYNAMIC=1 / front / back turns it on for A/B runs).
+constexpr int kSchedRing = 4;
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0, spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!done && ++spins > kSpinLimit) __trap();
+    }
+}
+template <bool PAIR>
+__device__ __forceinline__ void sched_publish(int *ring, uint64_t *full, int s, int item) {
+    asm volatile("st.volatile.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(ring + s)), "r"(item) : "memory");
+    mbar_arrive(full + s);
+    if constexpr (PAIR) {
+        uint32_t pr, pf;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, 1;" : "=r"(pr) : "r"(smem_u32(ring + s)));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, 1;" : "=r"(pf) : "r"(smem_u32(full + s)));
+        asm volatile("st.volatile.shared::cluster.s32 [%0], %1;" ::"r"(pr), "r"(item) : "memory");
+        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(pf) : "memory");
+    }
+}
+
 template <int EPI, bool PAIR, bool HPACK = false, bool UP = false>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(const __grid_constant__ CUtensorMap map_x0,
                                                                             const __grid_constant__ CUtensorMap map_x1,
@@ -531,7 +571,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
     uint64_t *acc_full = b_empty + g.b_stages;   // [2]
     uint64_t *acc_empty = acc_full + 2;          // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
-    uint32_t *tap_tab = tmem_slot + 2;           // [ks*ks] halo offset of each filter tap, in 16-byte units
+    uint32_t *tap_tab = tmem_slot + 2;           // [96] halo offset of each filter tap, in 16-byte units
+    int *sched_ring = reinterpret_cast<int *>(tap_tab + 96);                           // [kSchedRing] item ids (-1 = no more)
+    uint64_t *sched_full = reinterpret_cast<uint64_t *>(sched_ring + kSchedRing);      // [kSchedRing]
+    uint64_t *sched_empty = sched_full + kSchedRing;                                   // [kSchedRing]
+    const bool dyn = g.sched != nullptr;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (g.prof && threadIdx.x == 0) atomicMax(g.prof + 8, ~globaltimer_ns());        // ~min over CTAs of the entry time
@@ -555,6 +599,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
         for (int s = 0; s < g.a_stages; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
         for (int s = 0; s < g.b_stages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, kEpiWarps * (PAIR ? 2 : 1)); }
+        // a ring slot is released by every role warp that reads it: halo producer, weight producer, epilogue warps of
+        // each CTA + the leader's MMA warp
+        for (int s = 0; s < kSchedRing; ++s) { mbar_init(sched_full + s, 1); mbar_init(sched_empty + s, (2 + kEpiWarps) * (PAIR ? 2 : 1) + 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 3) {
@@ -660,11 +707,48 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
     };
     const int nseg = UP ? g.nseg : 1;
 
-    if (warp == 0) {
+    // next work item of this worker (-1: none): static round robin, or the scheduler's ring (every lane of the calling warp
+    // reads the slot, one lane releases it)
+    auto feed = [&](int &fli, int cur) -> int {
+        if (!dyn) {
+            const int nx = cur < 0 ? worker : cur + nworkers;
+            return nx < g.items ? nx : -1;
+        }
+        const int sl = fli & (kSchedRing - 1);
+        if constexpr (PAIR) mbar_wait_cluster(sched_full + sl, (uint32_t)(fli / kSchedRing) & 1u);
+        else mbar_wait(sched_full + sl, (uint32_t)(fli / kSchedRing) & 1u);
+        int it;
+        asm volatile("ld.volatile.shared::cta.s32 %0, [%1];" : "=r"(it) : "r"(smem_u32(sched_ring + sl)) : "memory");
+        __syncwarp();
+        if (elect_one()) halo_arrive_leader<PAIR>(sched_empty + sl);
+        __syncwarp();
+        ++fli;
+        return it;
+    };
+
+    if (warp == 3 && dyn && leader) {
+        // ---------------- scheduler: draws items and publishes them kSchedRing ahead of the slowest role ----------------
+        if (lane == 0) {
+            for (int li = 0;; ++li) {
+                const int sl = li & (kSchedRing - 1);
+                mbar_wait(sched_empty + sl, ((uint32_t)(li / kSchedRing) & 1u) ^ 1u);
+                int item = li == 0 ? worker : nworkers + atomicAdd(g.sched, 1);
+                if (item >= g.items) item = -1;
+                sched_publish<PAIR>(sched_ring, sched_full, sl, item);
+                if (item < 0) break;
+            }
+            __threadfence();
+            if (atomicAdd(g.sched + 1, 1) == nworkers - 1) {     // every worker has drawn its last item: reset for the next launch
+                g.sched[0] = 0;
+                g.sched[1] = 0;
+                __threadfence();
+            }
+        }
+    } else if (warp == 0) {
         // ---------------- halo producer: one box per (item, 32-channel chunk) ----------------
-        int stage = 0;
+        int stage = 0, fli = 0;
         uint32_t phase = 0;
-        for (int item = worker; item < g.items; item += nworkers) {
+        for (int item = feed(fli, -1); item >= 0; item = feed(fli, item)) {
             int n0, img, x0, y0;
             decode(item, n0, img, x0, y0);
             int pf = 0, tf[4];
@@ -701,9 +785,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
         if (prof && lane == 0) atomicAdd(g.prof + 4, w0);
     } else if (warp == 2) {
         // ---------------- weight producer: one [BN x 32] tile per (item, chunk, tap) ----------------
-        int stage = 0;
+        int stage = 0, fli = 0;
         uint32_t phase = 0;
-        for (int item = worker; item < g.items; item += nworkers) {
+        for (int item = feed(fli, -1); item >= 0; item = feed(fli, item)) {
             const int n0 = (item / patches_w) * g.BN + (int)cta_rank * bn_local;   // pair mode: this CTA's half of the slice
             int pf = 0, tf[4];
             if constexpr (UP) item_bits(item, pf, tf);
@@ -741,9 +825,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
         }
         int sa = 0, sb = 0;
         uint32_t pa = 0, pb = 0;
-        int li = 0;   // local item counter
+        int li = 0, fli = 0;   // local item counter
         int ready = 0;   // weight stages known to be full, starting at sb
-        for (int item = worker; item < g.items; item += nworkers, ++li) {
+        for (int item = feed(fli, -1); item >= 0; item = feed(fli, item), ++li) {
             const int buf = (g.nbuf == 2) ? (li & 1) : 0;
             const uint32_t use = (uint32_t)((g.nbuf == 2) ? (li >> 1) : li);
             mbar_wait_t(acc_empty + buf, (use & 1) ^ 1, prof, w2);          // epilogue has drained this buffer
@@ -829,8 +913,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_tcgen05_halo_kernel(cons
         const int row = quarter * 32 + lane;      // M row: 8 pixels along x per group, 16 groups along y
         const int nch = (g.BN / 16 - half + kParts - 1) / kParts;
         const int units = ntiles * nch;
-        int li = 0;
-        for (int item = worker; item < g.items; item += nworkers, ++li) {
+        int li = 0, fli = 0;
+        for (int item = feed(fli, -1); item >= 0; item = feed(fli, item), ++li) {
             int n0, img, x0, y0;
             decode(item, n0, img, x0, y0);
             const int buf = (g.nbuf == 2) ? (li & 1) : 0;
@@ -1577,12 +1661,19 @@ int launch_halo_pair(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap 
     return RAMNET_OK;
 }
 
+// RAMNET_FLAG_DYNAMIC: the {counter, finished} pair of the launch being issued (set by conv_fwd_tf32_rect around its
+// dispatch; every tensor-core forward launch goes through launch_halo)
+static thread_local int *tl_sched_slot = nullptr;
+
 template <int EPI, bool HP = false, bool UP = false>
 int launch_halo(ramnet_handle *h, const CUtensorMap &m0, const CUtensorMap &m1, const CUtensorMap &mw,
-                const HaloGeom &g, const EpiParams &ep, cudaStream_t s, const UpMaps &um = no_up_maps()) {
+                const HaloGeom &g_in, const EpiParams &ep, cudaStream_t s, const UpMaps &um = no_up_maps()) {
+    HaloGeom g = g_in;
+    const int workers = g.pair ? h->sm_count / 2 : h->sm_count;
+    g.sched = (tl_sched_slot && g.items > workers) ? tl_sched_slot : nullptr;     // a single wave has nothing to redistribute
     const size_t a_stride = (size_t)g.nplanes * g.plane_stride;
     const size_t smem = g.a_stages * a_stride + (size_t)g.b_stages * g.tpg * (g.pair ? g.BN / 2 : g.BN) * kChunk * 4 +
-                        (2 * g.a_stages + 2 * g.b_stages + 4) * 8 + 16 + 96 * 4 + 1024;
+                        (2 * g.a_stages + 2 * g.b_stages + 4) * 8 + 16 + 96 * 4 + kSchedRing * 4 + 2 * kSchedRing * 8 + 1024;
     if (g.pair) return launch_halo_pair<EPI, true, HP, UP>(h, m0, m1, mw, g, ep, smem, s, um);
     static size_t configured = 0;
     if (smem > configured) {
@@ -1631,7 +1722,7 @@ bool fill_halo(const ramnet_conv_desc *d, const RectSpec *rect, HaloGeom *g, int
     g->pair = pair;
     g->N = d->N; g->H = d->H; g->W = d->W; g->Cout = d->Cout; g->C0 = d->C0; g->C1 = d->C1;
     g->Ho = conv_out_dim(d->H, d->stride); g->Wo = conv_out_dim(d->W, d->stride);
-    g->ks = d->ksize; g->pad = d->ksize / 2; g->stride = d->stride; g->prof = nullptr;
+    g->ks = d->ksize; g->pad = d->ksize / 2; g->stride = d->stride; g->prof = nullptr; g->sched = nullptr;
     g->nplanes = d->stride == 1 ? 1 : 4;
     // halo extent along one axis, in plane pixels: shifts floor((r - pad)/stride) for r = 0..ks-1
     auto fdiv = [](int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); };
@@ -1705,7 +1796,7 @@ bool fill_hpack(const ramnet_conv_desc *d, HaloGeom *g, int pty, int cs, int pai
     g->pair = pair;
     g->N = d->N; g->H = d->H; g->W = d->W; g->Cout = d->Cout; g->C0 = d->C0; g->C1 = d->C1;
     g->Ho = d->H; g->Wo = d->W;
-    g->ks = ks; g->pad = ks / 2; g->stride = 1; g->prof = nullptr; g->nplanes = 1; g->lo = -g->pad;
+    g->ks = ks; g->pad = ks / 2; g->stride = 1; g->prof = nullptr; g->sched = nullptr; g->nplanes = 1; g->lo = -g->pad;
     g->hpack = 1; g->cs = cs; g->kwp = ks;
     g->up = 0; g->up_cout = 0; g->nseg = 1; g->total_taps = ks;
     g->kh = ks; g->kw = 1;                      // "taps" of the weight pipeline = filter rows
@@ -2604,8 +2695,13 @@ int conv_fwd_tf32_rect(ramnet_handle *h, const ramnet_conv_desc *d, const RectSp
                        const float *wp, const EpiParams &ep, cudaStream_t s);
 
 int conv_fwd_tf32(ramnet_handle *h, const ramnet_conv_desc *d, const float *x0, const float *x1, const float *wp,
-                  const EpiParams &ep, void *, size_t, cudaStream_t s) {
-    return conv_fwd_tf32_rect(h, d, nullptr, x0, x1, wp, ep, s);
+                  const EpiParams &ep, void *workspace, size_t ws_bytes, cudaStream_t s) {
+    // RAMNET_FLAG_DYNAMIC: the first 8 bytes of the workspace are this launch's {item counter, finished workers} pair
+    tl_sched_slot = ((d->flags & RAMNET_FLAG_DYNAMIC) && workspace && ws_bytes >= 8 && (((uintptr_t)workspace) & 3) == 0)
+                        ? static_cast<int *>(workspace) : nullptr;
+    const int rc = conv_fwd_tf32_rect(h, d, nullptr, x0, x1, wp, ep, s);
+    tl_sched_slot = nullptr;
+    return rc;
 }
 
 int conv_fwd_tf32_rect(ramnet_handle *h, const ramnet_conv_desc *d, const RectSpec *rect, const float *x0, const float *x1,

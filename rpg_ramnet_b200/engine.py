@@ -604,7 +604,13 @@ class GraphRunner:
         keep = [t.clone() for t in self._flat(self.sets[dst])]
         side = torch.cuda.Stream(device=self.device)
         # overlapping passes: the tile planner minimises SM time, not the makespan of a kernel alone on the GPU
+        # RAMNET_DYNAMIC=1 | front | back (default off): work items drawn from a global counter (RAMNET_FLAG_DYNAMIC) so that
+        # CTAs that start late -- their SM still ran the other stream's kernel -- take less of the work.  Validated
+        # (bit-identical) but measured slower in this two-stream schedule: profiles/r02_dynamic_items.txt
         hint = ops.FLAG_SM_TIME if self.overlap else 0
+        dyn = os.environ.get('RAMNET_DYNAMIC', '0')
+        if self.overlap and (dyn == '1' or dyn == kind):
+            hint |= ops.FLAG_DYNAMIC
         with ops.plan_flags(hint), torch.cuda.stream(side):
             for _ in range(2):
                 fn()

@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 from ._lib import (ConvDesc, EPI_BIAS, EPI_BIAS_ADD, EPI_BIAS_RELU, EPI_BIAS_RELU_ADD, EPI_BIAS_RELU_PRED, EPI_BIAS_RES_RELU, EPI_GRU_OUT,  # noqa
-                   EPI_GRU_RU, EPI_LSTM, FLAG_HPACK, FLAG_ROUND_TF32, FLAG_S2SEG, FLAG_SM_TIME, FLAG_UPCONV, MMA_FP32, MMA_TF32, check)
+                   EPI_GRU_RU, EPI_LSTM, FLAG_DYNAMIC, FLAG_HPACK, FLAG_ROUND_TF32, FLAG_S2SEG, FLAG_SM_TIME, FLAG_UPCONV, MMA_FP32, MMA_TF32, check)
 
 
 def _stream(t: torch.Tensor):
@@ -215,7 +215,7 @@ def pack_weights_hpack(w_oihw: torch.Tensor) -> torch.Tensor:
 
 # Planning hints OR-ed into every conv launch descriptor (engine.GraphRunner sets FLAG_SM_TIME while it captures passes
 # that will overlap on two streams).
-_PLAN_FLAGS = [0]
+_PLAN_FLAGS = [FLAG_DYNAMIC if os.environ.get('RAMNET_FORCE_DYNAMIC') == '1' else 0]      # RAMNET_FORCE_DYNAMIC: A/B aid (every TF32 conv launch)
 
 
 @contextlib.contextmanager
@@ -285,11 +285,14 @@ def conv_up_fwd(x: torch.Tensor, w_packed_up: torch.Tensor, bias: Optional[torch
             if tuple(aux0.shape) != (N, Cout, 2 * H, 2 * W):
                 raise _lib.RamnetError(f'conv_up_fwd: aux0 shape {tuple(aux0.shape)} != {(N, Cout, 2 * H, 2 * W)}')
     flags = FLAG_UPCONV | (FLAG_ROUND_TF32 if round_tf32 else 0) | _PLAN_FLAGS[0]
+    slot = _sched_slot(dev) if (flags & FLAG_DYNAMIC) else None
+    if slot is None:
+        flags &= ~FLAG_DYNAMIC
     d = ConvDesc(N, H, W, Cin, 0, Cout, 5, 1, epilogue, MMA_TF32, flags, 0)
     with _Prof('conv', 2.0 * N * (2 * H) * (2 * W) * Cout * Cin * 25, dev,      # algorithmic FLOPs of the reference graph
                tag=PROFILE is not None and f'upconv {H}x{W} {Cin}->{Cout} e{epilogue}'):
         check(_lib.load().ramnet_conv_fwd(_h(x), ctypes.byref(d), _p(x), None, _p(w_packed_up), _p(bias), _p(aux0), _p(aux1),
-                                          _p(y0), _p(out1), None, None, 0, _stream(x)))
+                                          _p(y0), _p(out1), None, _p(slot), 8 if slot is not None else 0, _stream(x)))
     return y0
 
 
@@ -323,6 +326,26 @@ class _Prof:
 
 
 _workspaces = {}      # (device, stream) -> [buffers, newest last]
+_sched_pools = {}     # device -> [zeroed int32 pool, next free pair]
+SCHED_SLOT_OVERRIDE = None
+
+
+def _sched_slot(device):
+    """8 zeroed bytes for ONE launch site of a RAMNET_FLAG_DYNAMIC convolution (item counter + finished-worker count;
+    the kernel resets them when it ends).  Slots are never reused: a captured CUDA graph bakes the address in and
+    replays it for the life of the process.  None when the pool is exhausted (the launch then runs with the static
+    assignment)."""
+    if SCHED_SLOT_OVERRIDE is not None:        # tests: one slot for many launches exercises the kernel's self-reset
+        return SCHED_SLOT_OVERRIDE
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    pool = _sched_pools.get(key)
+    if pool is None:
+        pool = _sched_pools[key] = [torch.zeros(1 << 16, dtype=torch.int32, device=device), 0]
+    if 2 * pool[1] + 2 > pool[0].numel():
+        return None
+    slot = pool[0][2 * pool[1]:2 * pool[1] + 2]
+    pool[1] += 1
+    return slot
 
 
 def _workspace(device, nbytes: int):
@@ -380,10 +403,17 @@ def conv_fwd(x0: torch.Tensor, x1: Optional[torch.Tensor], w_packed: torch.Tenso
     if getattr(w_packed, '_ramnet_s2seg', False):
         flags |= FLAG_S2SEG
     flags |= _PLAN_FLAGS[0]
+    ws, nws = None, 0
+    if (flags & FLAG_DYNAMIC) and mma_kind == MMA_TF32:
+        ws = _sched_slot(dev)
+        nws = 8 if ws is not None else 0
+    if ws is None:
+        flags &= ~FLAG_DYNAMIC
     d = ConvDesc(N, H, W, C0, C1, Cout, ksize, stride, epilogue, mma_kind, flags, 0)
     lib = _lib.load()
-    nws = lib.ramnet_conv_workspace_bytes(ctypes.byref(d))
-    ws = _workspace(dev, nws)
+    if ws is None:
+        nws = lib.ramnet_conv_workspace_bytes(ctypes.byref(d))
+        ws = _workspace(dev, nws)
     with _Prof('conv', 2.0 * N * Ho * Wo * Cout * (C0 + C1) * ksize * ksize, dev,
                tag=PROFILE is not None and f'conv {H}x{W} {C0}+{C1}->{Cout} k{ksize} s{stride} e{epilogue}'):
         check(lib.ramnet_conv_fwd(_h(x0), ctypes.byref(d), _p(x0), _p(x1), _p(w_packed), _p(bias), _p(aux0),

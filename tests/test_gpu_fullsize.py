@@ -224,3 +224,66 @@ def test_config3_shape_training_step_loss_and_grads_vs_oracle():
         g_ours, g_ref = named[name].grad.detach().cpu().double(), sd[name].grad.double()
         rel = float((g_ours - g_ref).norm() / g_ref.norm().clamp_min(1e-30))
         assert rel <= 6e-2, f'{name}: relative Frobenius error {rel:.3e}'      # TF32 vs fp32 oracle; measured worst 4.4e-2
+
+
+@pytest.mark.parametrize('layer', ['gru0_ru', 'gru0_out', 'enc0_s2seg', 'dec2_upconv_pred', 'dec1_upconv', 'lstm0', 'res_single_wave'])
+def test_dynamic_work_distribution_is_bit_identical(layer):
+    """RAMNET_FLAG_DYNAMIC (items drawn from a global counter through the shared-memory ring, engine.GraphRunner's overlapped
+    launches) against the static round robin on multi-wave layers of the bench shape: bit-identical outputs, and the
+    counter pair resets itself (the same 8-byte slot serves five launches in a row and reads zero afterwards)."""
+    from rpg_ramnet_b200 import ops
+    dev = torch.device('cuda', 0)
+    g = torch.Generator().manual_seed(5)
+    B = 4
+
+    def rnd(n, c, h, w, scale=1.0):
+        return (torch.randn(n, c, h, w, generator=g) * scale).to(dev).contiguous(memory_format=torch.channels_last)
+
+    kind = ops.MMA_TF32
+    if layer in ('gru0_ru', 'gru0_out', 'lstm0'):
+        C, H, W = 64, 128, 256
+        x, h = rnd(B, C, H, W), rnd(B, C, H, W)
+        cout = {'gru0_ru': 2 * C, 'gru0_out': C, 'lstm0': 4 * C}[layer]
+        epi = {'gru0_ru': ops.EPI_GRU_RU, 'gru0_out': ops.EPI_GRU_OUT, 'lstm0': ops.EPI_LSTM}[layer]
+        w = torch.randn(cout, 2 * C, 3, 3, generator=g).to(dev) * 0.05
+        wp = ops.pack_weights(w, kind, lstm_interleave=(layer == 'lstm0'))
+        b = torch.randn(cout, generator=g).to(dev) * 0.1
+        aux1 = rnd(B, C, H, W).sigmoid() if layer == 'gru0_out' else None
+        run = lambda: ops.conv_fwd(x, h, wp, b, cout, 3, 1, epi, kind, aux0=h, aux1=aux1, round_tf32=True)
+    elif layer == 'enc0_s2seg':
+        x = rnd(B, 32, 256, 512)
+        w = torch.randn(64, 32, 5, 5, generator=g).to(dev) * 0.05
+        wp, b = ops.pack_weights_s2seg(w), torch.randn(64, generator=g).to(dev) * 0.1
+        run = lambda: ops.conv_fwd(x, None, wp, b, 64, 5, 2, ops.EPI_BIAS_RELU, kind, round_tf32=True)
+    elif layer in ('dec2_upconv_pred', 'dec1_upconv'):
+        cin, cout, H, W = (64, 32, 128, 256) if layer == 'dec2_upconv_pred' else (128, 64, 64, 128)
+        x = rnd(B, cin, H, W)
+        w = torch.randn(cout, cin, 5, 5, generator=g).to(dev) * 0.05
+        wp, b = ops.pack_weights_upconv(w), torch.randn(cout, generator=g).to(dev) * 0.1
+        if layer == 'dec2_upconv_pred':
+            pw, pb = torch.randn(cout, generator=g).to(dev) * 0.3, torch.zeros(1, device=dev)
+            run = lambda: ops.conv_up_fwd(x, wp, b, cout, ops.EPI_BIAS_RELU_PRED, aux0=pw, aux1=pb)
+        else:
+            run = lambda: ops.conv_up_fwd(x, wp, b, cout, ops.EPI_BIAS_RELU, round_tf32=True)
+    else:   # one work item per worker: the launcher keeps the static assignment (nothing to redistribute)
+        x = rnd(B, 256, 32, 64)
+        w = torch.randn(256, 256, 3, 3, generator=g).to(dev) * 0.02
+        wp, b = ops.pack_weights(w, kind), torch.zeros(256, device=dev)
+        run = lambda: ops.conv_fwd(x, None, wp, b, 256, 3, 1, ops.EPI_BIAS_RELU, kind, round_tf32=True)
+
+    def outs(r):
+        return list(r) if isinstance(r, (tuple, list)) else [r]
+
+    ref = [t.clone() for t in outs(run())]
+    slot = torch.zeros(2, dtype=torch.int32, device=dev)
+    ops.SCHED_SLOT_OVERRIDE = slot
+    try:
+        with ops.plan_flags(ops.FLAG_DYNAMIC):
+            for rep in range(5):
+                got = outs(run())
+                for a, bb in zip(ref, got):
+                    assert torch.equal(a, bb), (layer, rep)
+                torch.cuda.synchronize()
+                assert slot.tolist() == [0, 0], (layer, rep, slot.tolist())
+    finally:
+        ops.SCHED_SLOT_OVERRIDE = None
