@@ -34,7 +34,7 @@ for rep in range(2):                  # rep 0 warms the weight caches / attribut
     terms += [0.25 * R.multi_scale_grad_loss(preds[k], seq[0]['depth_' + k]) for k in preds]
     sum(terms).backward()
     opt.step()
-    for n in (1000000, 10000000):
+    for n in (100000, 1000000, 10000000):        # fused zero-fill kernel / direct kernel / packed accumulator
         ev = torch.from_numpy(synth_events(n, W, H, seed=0)).to('cuda:0')
         g = R.events_to_voxel_grid(ev, 5, W, H)
     grids = torch.randn(32, 5, H, W, device='cuda:0') * (torch.rand(32, 5, H, W, device='cuda:0') < 0.1)
@@ -45,4 +45,14 @@ for rep in range(2):                  # rep 0 warms the weight caches / attribut
     eval_metrics(torch.rand(32, 1, H, W, device='cuda:0'), lab, ['mse', 'abs_rel_diff', 'scale_invariant_error'])
     torch.cuda.synchronize()
     torch.cuda.nvtx.range_pop()
+# live norm layers: one train-mode BatchNorm pass (forward + backward) at the bench shape
+ncfg = dict(cfg, norm='BN')
+torch.manual_seed(0)
+with contextlib.redirect_stdout(io.StringIO()):
+    nmodel = R.ERGB2DepthRecurrent(ncfg)
+nmodel.train().to('cuda:0')
+for rep in range(2):
+    npreds, _, _ = nmodel(seq[0], None, {'events0': None, 'image': None})
+    sum(R.scale_invariant_loss(npreds[k], seq[0]['depth_' + k]) for k in npreds).backward()
+    torch.cuda.synchronize()
 print('launches', R.launch_count(0))
